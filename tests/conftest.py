@@ -1,0 +1,41 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests must fail loudly (not skip) on a GPU box; on a box without a GPU they are
+    deselected by `-m "not gpu"`.  If someone runs them anyway without CUDA, skip."""
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden.npz")
+    return np.load(path, allow_pickle=False)
+
+
+def state_from_golden(golden, prefix):
+    """Collect {state_dict_key: ndarray} stored under `prefix/`."""
+    pre = prefix.rstrip("/") + "/"
+    return {k[len(pre):]: golden[k] for k in golden.files if k.startswith(pre)}
