@@ -1,0 +1,211 @@
+/*
+ * rlctr.h -- C ABI of librlctr_sm100a.so: the B200 (sm_100a) hot path of
+ * jqsl2012/RL_CTR_Prediction.
+ *
+ * The reference has no operator/FFI layer of its own: its seam
+ * is the nn.Module surface of src/models/p_model.py, src/models/Feature_embedding.py and
+ * the loop functions of src/main/pretrain_main.py / src/all_main/main.py.  Each entry
+ * point below names the reference lines whose ATen op sequence it replaces; the Python
+ * package rl_ctr_prediction_b200 binds these symbols with ctypes behind drop-in classes of
+ * the same names, constructors and state_dict keys (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - the caller owns every buffer (tables, optimizer state, outputs, workspaces); the
+ *     library never allocates or frees device memory and keeps no global mutable state;
+ *   - all work is enqueued on the `stream` argument: no implicit synchronisation, no use
+ *     of the default stream, safe to capture into a CUDA graph;
+ *   - return value: 0 = success, negative = RLCTR_E* argument error, positive = cudaError_t;
+ *   - all device pointers must be 16-byte aligned unless noted; ids are int64 as in the
+ *     reference's LongTensor contract (src/models/creat_data.py:15-19);
+ *   - an id outside [0, n_rows) is treated as an all-zero row (no fault, no update).
+ *
+ * Table layout ("fused row"): one row per feature id, `row_stride` floats (multiple of 4,
+ * or exactly 1 for the LR table), column `lin_col` = first-order weight (nn.Embedding(N,1),
+ * p_model.py:14,34,69,263; -1 if the model has none), columns emb_col .. emb_col+dim-1 =
+ * the latent vector (p_model.py:38,267; for FFM the F per-field vectors of p_model.py:76-78
+ * interleaved, dim = F*D), remaining columns zero padding.  The 128-bit aligned fused row
+ * turns the reference's two gathers per field (4 B + 4*D B, two DRAM sectors each) into
+ * one aligned vector read.
+ */
+#ifndef RLCTR_H_
+#define RLCTR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLCTR_VERSION 100
+
+#define RLCTR_OK            0
+#define RLCTR_EINVAL       (-1)   /* bad argument (NULL, negative size, ...)            */
+#define RLCTR_EUNSUPPORTED (-2)   /* shape outside what the kernels are built for        */
+#define RLCTR_EWORKSPACE   (-3)   /* workspace too small                                 */
+#define RLCTR_EALIGN       (-4)   /* pointer not 16-byte aligned / stride not allowed    */
+
+typedef struct CUstream_st* rlctr_stream_t;   /* == cudaStream_t */
+
+/* One embedding table in the fused-row layout described above. */
+typedef struct rlctr_table {
+    float*  data;        /* [n_rows, row_stride] */
+    int64_t n_rows;      /* feature_nums */
+    int32_t row_stride;  /* floats per row: 1, or a multiple of 4 */
+    int32_t lin_col;     /* column of the first-order weight, -1 = none */
+    int32_t emb_col;     /* first column of the latent vector */
+    int32_t dim;         /* latent_dims (FFM: field_nums*latent_dims), 0 = none */
+} rlctr_table;
+
+/* torch.optim.Adam state for one table (src/main/pretrain_main.py:181).  `sched[t]` holds
+ * the two Python-double scalars torch derives at step t, cast to fp32:
+ * (lr / (1 - beta1^t), sqrt(1 - beta2^t)).  `step` is a DEVICE scalar so a captured CUDA
+ * graph can be replayed while the step advances (rlctr_step_advance). */
+typedef struct rlctr_adam {
+    float*         exp_avg;      /* [n_rows, row_stride] */
+    float*         exp_avg_sq;   /* [n_rows, row_stride] */
+    int32_t*       stamp;        /* [n_rows] last step at which the row is up to date; NULL in sparse mode */
+    const float*   sched;        /* [sched_len][2], index = step (entry 0 unused) */
+    const int32_t* step;         /* device scalar: the step being applied, >= 1 */
+    int32_t        sched_len;
+    float          beta1, beta2, eps, weight_decay;
+} rlctr_adam;
+
+/* Where the gradient of a gathered row comes from.  For sorted position k with
+ * slot = sorted_slots[k], b = slot / fields, f = slot % fields, the row gradient is
+ *     staged[slot]                                   (generic, row_stride floats)
+ *   + dlogit[b] at lin_col                           (d z / d w = 1)
+ *   + dlogit[b] * (sums[b] - row) on the latent cols (FM: d z / d v_f = S - v_f)
+ *   + extra[b, f*dim .. ]          on the latent cols (dense tail, e.g. the DeepFM tower)
+ * any of the four pointers may be NULL. */
+typedef struct rlctr_rowgrad {
+    const float* staged;   /* [n, row_stride] */
+    const float* dlogit;   /* [B] */
+    const float* sums;     /* [B, row_stride] from rlctr_embed_fwd */
+    const float* extra;    /* [B, fields*dim] */
+    int32_t      fields;
+} rlctr_rowgrad;
+
+int         rlctr_version(void);
+const char* rlctr_strerror(int code);
+
+/* ------------------------------------------------------------------------------------
+ * K1  fused gather + first order + FM second order.
+ * Replaces, per batch: nn.Embedding gathers p_model.py:23,47,54,303,311,320 and the
+ * sum/pow/sub/mul temporaries of LR.forward :18-26, FM.forward :40-57, DeepFM.to_fm
+ * :296-313 (one gather feeds the FM term and the tower input, reference gathers twice).
+ *   logit[b]   = bias + sum_f w[x_f] (+ 0.5*sum_d[(sum_f v)^2 - sum_f v^2] if RLCTR_FM_TERM)
+ *   pctr[b*pctr_stride] = sigmoid(logit)          (optional; stride lets M models fill [B,M])
+ *   sums[b, :] = column sums over the F gathered rows (saved for the backward; optional)
+ *   rows_out[b, f*dim + d] = v_f[d]               (bit-exact copy; optional)
+ * ------------------------------------------------------------------------------------ */
+#define RLCTR_FM_TERM 1
+int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, const float* bias,
+                    float* logit, float* pctr, int64_t pctr_stride, float* sums, float* rows_out,
+                    int64_t batch, int32_t fields, int32_t flags, rlctr_stream_t stream);
+
+/* Plain bit-exact row gather out[k, :] = table[ids[k], :] (nn.Embedding.forward); the owner
+ * side of the sharded lookup.  out has row_stride floats per row. */
+int rlctr_gather_rows(const int64_t* ids, int64_t n, const rlctr_table* table, float* out,
+                      rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  FFM over the interleaved table (dim = fields*latent): p_model.py:82-100.
+ *   logit[b] = bias + sum_f w[x_f] + sum_{i<j} <T_j[x_i], T_i[x_j]>
+ * rlctr_ffm_bwd_rows writes the staged row gradients grad_rows[b*F+i, :] =
+ * dlogit[b] * [1, T_0[x_i]^T-partner ...] i.e. column block j of row i gets
+ * dlogit[b]*T_i[x_j] (zero on the diagonal) -- autograd of :91 (SURVEY section 3.7 FFM).
+ * ------------------------------------------------------------------------------------ */
+int rlctr_ffm_fwd(const int64_t* ids, const rlctr_table* table, const float* bias,
+                  float* logit, float* pctr, int64_t pctr_stride,
+                  int64_t batch, int32_t fields, int32_t latent, rlctr_stream_t stream);
+int rlctr_ffm_bwd_rows(const int64_t* ids, const rlctr_table* table, const float* dlogit,
+                       float* grad_rows, int64_t batch, int32_t fields, int32_t latent,
+                       rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5  RL state encoder: Feature_Embedding.forward, Feature_embedding.py:51-59.
+ *   out[b, 0:P]      = <v_i, v_j> for (i,j) in the order of :40-43, P = F(F-1)/2
+ *   out[b, P:P+F*D]  = v_0 .. v_{F-1}
+ * out_stride = floats between consecutive samples (>= P + F*D).
+ * ------------------------------------------------------------------------------------ */
+int rlctr_featemb_fwd(const int64_t* ids, const rlctr_table* table, float* out, int64_t out_stride,
+                      int64_t batch, int32_t fields, rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Loss head: torch.sigmoid + nn.BCELoss(mean) forward AND their autograd
+ * (p_model.py:55; src/main/pretrain_main.py:167,98,101), with torch's exact clamp
+ * semantics (log >= -100; (p-y)/max((1-p)p,1e-12)):
+ *   pctr = sigmoid(logit); loss[0] = mean BCE; dlogit[b] = dL/dlogit[b].
+ * Exactly one of labels_i64 / labels_f32 is non-NULL.  ws: RLCTR_REDUCE_WS_BYTES bytes,
+ * zeroed once by the caller (the kernel leaves its counter zeroed).  The mean is a
+ * fixed-shape two-level tree: bit-identical from run to run.
+ * ------------------------------------------------------------------------------------ */
+#define RLCTR_REDUCE_WS_BYTES 16640
+int rlctr_bce_fwd_bwd(const float* logit, const int64_t* labels_i64, const float* labels_f32,
+                      float* pctr, float* loss, float* dlogit, void* ws, int64_t batch,
+                      rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  deterministic scatter: sort (id, slot) pairs, segment-reduce, fused Adam.
+ * Replaces aten::embedding_dense_backward (dense [N,D] zero-fill + index_add) and the
+ * dense foreach Adam over all N rows (src/main/pretrain_main.py:101-102).
+ * ------------------------------------------------------------------------------------ */
+size_t rlctr_sort_ws_bytes(int64_t n, int64_t n_rows);
+/* sorted_ids/sorted_slots [n]: stable ascending sort of ids (slot = position in `ids`). */
+int rlctr_sort_ids(const int64_t* ids, int64_t n, int64_t n_rows,
+                   uint32_t* sorted_ids, uint32_t* sorted_slots,
+                   void* ws, size_t ws_bytes, rlctr_stream_t stream);
+
+size_t rlctr_rows_ws_bytes(int64_t n);
+/* For every distinct id: g = sum over its occurrences (slot order) of the row gradient,
+ * then one Adam step with L2 (g += wd*p) on that row; stamp[id] = *step.  No atomics on
+ * the data path; bit-identical from run to run. */
+int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
+                    const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
+                    void* ws, size_t ws_bytes, rlctr_stream_t stream);
+/* Same reduction, but the sums are stored into a dense [n_rows,row_stride] gradient
+ * (rows of untouched ids are not written): the literal embedding_dense_backward. */
+int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
+                          const rlctr_rowgrad* grad, const rlctr_table* table, float* dense_grad,
+                          void* ws, size_t ws_bytes, rlctr_stream_t stream);
+/* Lazy-exact mode: bring every distinct id of the batch up to step (*step - 1) by replaying
+ * the L2-only Adam steps it missed (g = wd*p), so the forward reads what dense Adam would
+ * have produced.  Call with *step already advanced to the step about to be applied. */
+int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table* table,
+                       const rlctr_adam* opt, rlctr_stream_t stream);
+/* Replay the missed L2-only steps of rows [row_begin,row_end) up to *step.  Called once per
+ * step this IS dense Adam (mode A); called before eval/state_dict/epoch end it is
+ * the flush of the lazy mode (mode B). */
+int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
+                     int64_t row_begin, int64_t row_end, rlctr_stream_t stream);
+/* Dense Adam for the replicated parameters (bias, tower, policy nets): torch semantics. */
+int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const float* sched, const int32_t* step, float beta1, float beta2, float eps,
+                     float weight_decay, rlctr_stream_t stream);
+int rlctr_step_advance(int32_t* step, int32_t delta, rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K6  ensemble scoring + reward: generate_preds.
+ *   variant 0: src/all_main/main.py:183-271 (action in 2..M, reward +1/-1)
+ *   variant 1: src/all_main/hybrid_td3_main_per.py:56-133 (action in 1..M, reward 1/0)
+ * pctr, w, w_out are [B, M] row-major, M <= 8.
+ * ------------------------------------------------------------------------------------ */
+int rlctr_generate_preds(const float* pctr, const float* w, const int64_t* action, const int64_t* label,
+                         float* y, float* w_out, float* reward, int64_t batch, int32_t models,
+                         int32_t variant, rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * REINFORCE head: PG_model.py:53-58,104-107 (softmax, -log pi(a), loss, and its autograd).
+ *   variant 0: literal  loss = (sum_b -logp_b) * mean_b(vt_b)
+ *   variant 1: per-sample loss = mean_b(-logp_b * vt_b)
+ * act in 1..A (A <= 32).  ws: RLCTR_REDUCE_WS_BYTES bytes zeroed once by the caller.
+ * ------------------------------------------------------------------------------------ */
+int rlctr_reinforce_loss_bwd(const float* logits, const int64_t* act, const float* vt,
+                             float* logp, float* loss, float* dlogits, void* ws,
+                             int64_t batch, int32_t actions, int32_t variant, rlctr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLCTR_H_ */

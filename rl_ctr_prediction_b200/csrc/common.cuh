@@ -1,0 +1,101 @@
+// common.cuh -- shared device helpers for librlctr_sm100a (B200, sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rlctr.h"
+
+#define RLCTR_FULL 0xffffffffu
+#define RLCTR_SMS 148          // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+#define RLCTR_LAUNCH_CHECK()                         \
+    do {                                             \
+        cudaError_t e__ = cudaGetLastError();        \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+#define RLCTR_CUDA(call)                             \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+static inline bool rlctr_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// lanes-per-row for a fused row of `rs` floats read as float4 chunks: 1,2,4 or 8 (rs <= 32)
+static inline int rlctr_lanes_per_row(int rs) {
+    int chunks = rs / 4;
+    int l = 1;
+    while (l < chunks) l <<= 1;
+    return l;
+}
+
+namespace rlctr {
+
+// 128-bit read-only gather of one row chunk.  Rows are touched once per kernel (random ids),
+// so skip L1 allocation is NOT requested: neighbouring chunks of one row share 32 B sectors
+// across the three per-row requests and L1 merges them.
+__device__ __forceinline__ float4 ldg4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ld4(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+// streaming store: outputs written once and not re-read by this kernel
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+    __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float f4get(const float4& v, int i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void f4set(float4& v, int i, float x) {
+    if (i == 0) v.x = x; else if (i == 1) v.y = x; else if (i == 2) v.z = x; else v.w = x;
+}
+__device__ __forceinline__ float4 shfl_xor4(float4 v, int off) {
+    v.x = __shfl_xor_sync(RLCTR_FULL, v.x, off);
+    v.y = __shfl_xor_sync(RLCTR_FULL, v.y, off);
+    v.z = __shfl_xor_sync(RLCTR_FULL, v.z, off);
+    v.w = __shfl_xor_sync(RLCTR_FULL, v.w, off);
+    return v;
+}
+
+// torch.sigmoid in fp32: 1/(1+exp(-z)) with the accurate expf (saturates to exactly 0/1 like
+// the reference -- SURVEY N2; do not replace with __expf or a logits-BCE).
+__device__ __forceinline__ float sigmoidf_ref(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// ---- torch.optim.Adam (_single_tensor_adam, non-capturable branch), one element ----------
+struct AdamHyper {
+    float beta1, beta2, eps, wd;
+};
+
+// one step with gradient g (L2 folded in like torch: g += wd*p)
+__device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamHyper& h,
+                                          float step_size, float bc2_sqrt) {
+    g = g + h.wd * p;
+    m = m + (1.0f - h.beta1) * (g - m);                 // exp_avg.lerp_(grad, 1-beta1)
+    v = v * h.beta2 + (1.0f - h.beta2) * g * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+    float denom = sqrtf(v) / bc2_sqrt + h.eps;
+    p = p + (-step_size) * m / denom;                   // addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+// replay the L2-only steps (from, to] a row missed (g = wd*p): what dense Adam does to an
+// untouched row every step.  sched[t] = (step_size_t, bc2_sqrt_t).
+__device__ __forceinline__ void adam_replay4(float4& p, float4& m, float4& v, int from, int to,
+                                             const float2* __restrict__ sched, const AdamHyper& h) {
+    for (int t = from + 1; t <= to; ++t) {
+        float2 s = __ldg(&sched[t]);
+        adam_elem(p.x, m.x, v.x, 0.f, h, s.x, s.y);
+        adam_elem(p.y, m.y, v.y, 0.f, h, s.x, s.y);
+        adam_elem(p.z, m.z, v.z, 0.f, h, s.x, s.y);
+        adam_elem(p.w, m.w, v.w, 0.f, h, s.x, s.y);
+    }
+}
+
+}  // namespace rlctr

@@ -1,0 +1,512 @@
+// optim.cu -- K3: deterministic scatter of embedding-row gradients fused with torch-exact Adam.
+//
+//   sort (id, slot) pairs  ->  one head lane-group per distinct id walks its run of equal ids
+//   (stable sort => slot order, the order aten::embedding_dense_backward accumulates in on CPU)
+//   -> Adam on that row in registers -> one write of p, m, v.  No atomics on the data path.
+//   Runs longer than LONG_RUN (heavy-hitter ids of Zipf fields) are handed to a block-per-row
+//   kernel with a fixed-shape tree so the result stays bit-identical from run to run.
+//
+// Modes: the reference's dense Adam moves EVERY row every step (L2 folded into the
+// gradient).  rlctr_adam_flush replays those L2-only steps: called every step it is dense Adam
+// (mode A); called lazily (rlctr_rows_catchup for the ids of the batch before the forward,
+// rlctr_adam_flush before eval/state_dict) it gives the same numbers with O(touched) traffic
+// (mode B).  With stamp == NULL untouched rows are left alone (mode C, "sparse").
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace rlctr {
+
+constexpr int LONG_RUN = 32;
+
+struct TableView {
+    float* data;
+    int64_t n_rows;
+    int rs, lin_col, emb_col, dim;
+};
+static inline TableView view_of(const rlctr_table* t) {
+    return TableView{t->data, t->n_rows, t->row_stride, t->lin_col, t->emb_col, t->dim};
+}
+struct AdamView {
+    float* m;
+    float* v;
+    int32_t* stamp;
+    const float2* sched;
+    const int32_t* step;
+    AdamHyper h;
+};
+static inline AdamView view_of(const rlctr_adam* a) {
+    return AdamView{a->exp_avg, a->exp_avg_sq, a->stamp, reinterpret_cast<const float2*>(a->sched), a->step,
+                    AdamHyper{a->beta1, a->beta2, a->eps, a->weight_decay}};
+}
+struct GradView {
+    const float* staged;
+    const float* dlogit;
+    const float* sums;
+    const float* extra;
+    int fields;
+};
+
+__global__ void __launch_bounds__(256)
+sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, uint32_t* __restrict__ keys,
+                 uint32_t* __restrict__ vals) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = __ldg(ids + i);
+        keys[i] = ((uint64_t)id < (uint64_t)n_rows) ? (uint32_t)id : (uint32_t)n_rows;   // out-of-range -> sentinel, sorted last
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// gradient of columns col0..col0+3 of the row gathered at `slot` (rlctr_rowgrad in rlctr.h)
+__device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t slot, int col0, const float4& p,
+                                                const TableView& t) {
+    float4 r = f4zero();
+    if (g.staged) r = ldg4(g.staged + (int64_t)slot * t.rs + col0);
+    if (g.dlogit || g.extra) {
+        const uint32_t b = slot / (uint32_t)g.fields;
+        const uint32_t f = slot - b * (uint32_t)g.fields;
+        const float dz = g.dlogit ? __ldg(g.dlogit + b) : 0.f;
+        float4 S = f4zero();
+        const bool fm = g.sums && g.dlogit;
+        if (fm) S = ldg4(g.sums + (int64_t)b * t.rs + col0);
+        const float* ex = g.extra ? g.extra + ((int64_t)b * g.fields + f) * t.dim : nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = col0 + k;
+            float add = 0.f;
+            if (col == t.lin_col) {
+                add = dz;
+            } else if (col >= t.emb_col && col < t.emb_col + t.dim) {
+                if (fm) add = dz * (f4get(S, k) - f4get(p, k));
+                if (ex) add += __ldg(ex + col - t.emb_col);
+            }
+            f4set(r, k, f4get(r, k) + add);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void adam_apply4(float4& p, float4& m, float4& v, const float4& g, float2 s,
+                                            const AdamHyper& h) {
+    adam_elem(p.x, m.x, v.x, g.x, h, s.x, s.y);
+    adam_elem(p.y, m.y, v.y, g.y, h, s.x, s.y);
+    adam_elem(p.z, m.z, v.z, g.z, h, s.x, s.y);
+    adam_elem(p.w, m.w, v.w, g.w, h, s.x, s.y);
+}
+
+// finish one distinct row: Adam (APPLY==0) or store into the dense gradient (APPLY==1)
+template <int APPLY>
+__device__ __forceinline__ void finish_row(int64_t id, int col0, float4 p, const float4& acc, const TableView& t,
+                                           const AdamView& a, float* dense_grad, int step, int stamp_in) {
+    const int64_t off = id * t.rs + col0;
+    if (APPLY == 1) {
+        st4(dense_grad + off, acc);
+        return;
+    }
+    float4 m = ld4(a.m + off), v = ld4(a.v + off);
+    if (a.stamp && stamp_in < step - 1) adam_replay4(p, m, v, stamp_in, step - 1, a.sched, a.h);
+    adam_apply4(p, m, v, acc, __ldg(&a.sched[step]), a.h);
+    st4(t.data + off, p);
+    st4(a.m + off, m);
+    st4(a.v + off, v);
+}
+
+// one lane-group (LPR lanes, a float4 chunk each) per sorted position; only run heads work
+template <int LPR, int APPLY>
+__global__ void __launch_bounds__(256)
+rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                  GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
+                  int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = gt / LPR;
+    const int c = (int)(gt % LPR), col0 = 4 * c;
+    bool head = false;
+    uint32_t id = 0;
+    if (k < n) {
+        id = __ldg(sorted_ids + k);
+        head = (id < (uint64_t)t.n_rows) && (k == 0 || __ldg(sorted_ids + k - 1) != id);
+    }
+    if (head && k + LONG_RUN < n && __ldg(sorted_ids + k + LONG_RUN) == id) {
+        if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)k;      // order is irrelevant: rows are independent
+        head = false;
+    }
+    const bool work = head && col0 < t.rs;
+    int step = 0, stamp_in = 0;
+    if (work) {
+        if (APPLY == 0) {
+            step = __ldg(a.step);
+            if (a.stamp) stamp_in = a.stamp[id];
+        }
+        const float4 p = ld4(t.data + (int64_t)id * t.rs + col0);
+        float4 acc = f4zero();
+        int64_t kk = k;
+        uint32_t nxt = id;
+        while (nxt == id) {
+            const uint32_t slot = __ldg(sorted_slots + kk);
+            ++kk;
+            nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
+            acc = f4add(acc, rowgrad_chunk(g, slot, col0, p, t));
+        }
+        finish_row<APPLY>(id, col0, p, acc, t, a, dense_grad, step, stamp_in);
+    }
+    if (APPLY == 0 && a.stamp) {
+        __syncwarp();                                    // all chunk lanes read the stamp before lane 0 rewrites it
+        if (work && c == 0) a.stamp[id] = step;
+    }
+}
+
+// block per long run: NSUB lane-groups stride the run, fixed-shape tree in shared memory
+template <int LPR, int APPLY>
+__global__ void __launch_bounds__(256)
+rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                 GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
+                 const int32_t* __restrict__ long_count, const uint32_t* __restrict__ long_list) {
+    constexpr int NSUB = 256 / LPR;
+    __shared__ float4 red[256];
+    __shared__ int64_t s_end;
+    const int sub = threadIdx.x / LPR, c = threadIdx.x % LPR, col0 = 4 * c;
+    const bool chunk_on = col0 < t.rs;
+    const int nlong = *long_count;
+    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        const int64_t k = long_list[li];
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (threadIdx.x == 0) {                          // upper bound of the run by bisection
+            int64_t lo = k, hi = n;                      // ids[lo] == id, ids[hi] > id (or hi == n)
+            while (hi - lo > 1) {
+                int64_t mid = (lo + hi) >> 1;
+                if (__ldg(sorted_ids + mid) == id) lo = mid; else hi = mid;
+            }
+            s_end = hi;
+        }
+        __syncthreads();
+        const int64_t end = s_end;
+        float4 p = f4zero(), acc = f4zero();
+        int step = 0, stamp_in = 0;
+        if (chunk_on) {
+            p = ld4(t.data + (int64_t)id * t.rs + col0);
+            for (int64_t kk = k + sub; kk < end; kk += NSUB)
+                acc = f4add(acc, rowgrad_chunk(g, __ldg(sorted_slots + kk), col0, p, t));
+            if (APPLY == 0 && sub == 0) {
+                step = __ldg(a.step);
+                if (a.stamp) stamp_in = a.stamp[id];
+            }
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int half = NSUB / 2; half > 0; half >>= 1) {
+            if (sub < half) red[threadIdx.x] = f4add(red[threadIdx.x], red[threadIdx.x + half * LPR]);
+            __syncthreads();
+        }
+        if (sub == 0 && chunk_on) finish_row<APPLY>(id, col0, p, red[threadIdx.x], t, a, dense_grad, step, stamp_in);
+        __syncthreads();
+        if (APPLY == 0 && a.stamp && threadIdx.x == 0) a.stamp[id] = __ldg(a.step);
+    }
+}
+
+// lazy mode: bring the distinct ids of the batch up to step-1 before the forward reads them
+template <int LPR>
+__global__ void __launch_bounds__(256)
+rows_catchup_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = gt / LPR;
+    const int c = (int)(gt % LPR), col0 = 4 * c;
+    bool work = false;
+    uint32_t id = 0;
+    if (k < n) {
+        id = __ldg(sorted_ids + k);
+        work = (id < (uint64_t)t.n_rows) && (k == 0 || __ldg(sorted_ids + k - 1) != id) && col0 < t.rs;
+    }
+    const int upto = __ldg(a.step) - 1;
+    bool stale = false;
+    if (work) {
+        const int st = a.stamp[id];
+        stale = st < upto;
+        if (stale) {
+            const int64_t off = (int64_t)id * t.rs + col0;
+            float4 p = ld4(t.data + off), m = ld4(a.m + off), v = ld4(a.v + off);
+            adam_replay4(p, m, v, st, upto, a.sched, a.h);
+            st4(t.data + off, p);
+            st4(a.m + off, m);
+            st4(a.v + off, v);
+        }
+    }
+    __syncwarp();
+    if (stale && c == 0) a.stamp[id] = upto;
+}
+
+// streaming pass over rows [r0,r1): replay the steps each row missed up to *step.  Coalesced
+// float4 traffic: 3 reads + 3 writes of the table-sized arrays at most (stamps set by the
+// companion fill kernel because the chunks of one row may sit in different warps).
+__global__ void __launch_bounds__(256)
+adam_flush_kernel(TableView t, AdamView a, int64_t r0, int64_t r1) {
+    const int chunks = t.rs >> 2;
+    const int64_t total = (r1 - r0) * chunks;
+    const int upto = __ldg(a.step);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = r0 + i / chunks;
+        const int st = __ldg(a.stamp + row);
+        if (st >= upto) continue;
+        const int64_t off = row * t.rs + 4 * (i % chunks);
+        float4 p = ld4(t.data + off), m = ld4(a.m + off), v = ld4(a.v + off);
+        adam_replay4(p, m, v, st, upto, a.sched, a.h);
+        st4(t.data + off, p);
+        st4(a.m + off, m);
+        st4(a.v + off, v);
+    }
+}
+__global__ void __launch_bounds__(256)
+adam_flush_scalar_kernel(TableView t, AdamView a, int64_t r0, int64_t r1) {   // row_stride == 1 (LR)
+    const int upto = __ldg(a.step);
+    for (int64_t row = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < r1; row += (int64_t)gridDim.x * blockDim.x) {
+        const int st = a.stamp[row];
+        if (st >= upto) continue;
+        float p = t.data[row], m = a.m[row], v = a.v[row];
+        for (int s = st + 1; s <= upto; ++s) {
+            const float2 sc = __ldg(&a.sched[s]);
+            adam_elem(p, m, v, 0.f, a.h, sc.x, sc.y);
+        }
+        t.data[row] = p; a.m[row] = m; a.v[row] = v;
+        a.stamp[row] = upto;
+    }
+}
+__global__ void __launch_bounds__(256)
+stamp_fill_kernel(int32_t* __restrict__ stamp, const int32_t* __restrict__ step, int64_t r0, int64_t r1) {
+    const int upto = __ldg(step);
+    for (int64_t row = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < r1; row += (int64_t)gridDim.x * blockDim.x)
+        stamp[row] = upto;
+}
+
+// row_stride == 1 (the LR table): one lane per sorted position
+template <int APPLY>
+__global__ void __launch_bounds__(256)
+rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                   GradView g, TableView t, AdamView a, float* __restrict__ dense_grad) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t id = __ldg(sorted_ids + k);
+    if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
+    float acc = 0.f;
+    int64_t kk = k;
+    uint32_t nxt = id;
+    while (nxt == id) {                                   // LR runs: sequential, slot order
+        const uint32_t slot = __ldg(sorted_slots + kk);
+        ++kk;
+        nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
+        float gsl = g.staged ? __ldg(g.staged + slot) : 0.f;
+        if (g.dlogit) gsl += __ldg(g.dlogit + slot / (uint32_t)g.fields);
+        acc += gsl;
+    }
+    if (APPLY == 1) { dense_grad[id] = acc; return; }
+    const int step = __ldg(a.step);
+    float p = t.data[id], m = a.m[id], v = a.v[id];
+    if (a.stamp) {
+        const int st = a.stamp[id];
+        for (int s = st + 1; s <= step - 1; ++s) {
+            const float2 sc = __ldg(&a.sched[s]);
+            adam_elem(p, m, v, 0.f, a.h, sc.x, sc.y);
+        }
+        a.stamp[id] = step;
+    }
+    const float2 sc = __ldg(&a.sched[step]);
+    adam_elem(p, m, v, acc, a.h, sc.x, sc.y);
+    t.data[id] = p; a.m[id] = m; a.v[id] = v;
+}
+__global__ void __launch_bounds__(256)
+rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t id = __ldg(sorted_ids + k);
+    if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
+    const int upto = __ldg(a.step) - 1;
+    const int st = a.stamp[id];
+    if (st >= upto) return;
+    float p = t.data[id], m = a.m[id], v = a.v[id];
+    for (int s = st + 1; s <= upto; ++s) {
+        const float2 sc = __ldg(&a.sched[s]);
+        adam_elem(p, m, v, 0.f, a.h, sc.x, sc.y);
+    }
+    t.data[id] = p; a.m[id] = m; a.v[id] = v;
+    a.stamp[id] = upto;
+}
+
+__global__ void __launch_bounds__(256)
+dense_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  int64_t n, const float2* __restrict__ sched, const int32_t* __restrict__ step, AdamHyper h) {
+    const float2 sc = __ldg(&sched[__ldg(step)]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_elem(pp, mm, vv, g[i], h, sc.x, sc.y);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+__global__ void step_advance_kernel(int32_t* step, int32_t delta) { *step += delta; }
+
+static inline int grid_1d(int64_t threads, int cap_blocks) {
+    int64_t blocks = (threads + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    return (int)(blocks < cap_blocks ? blocks : cap_blocks);
+}
+static inline int key_bits(int64_t n_rows) {     // bits needed for keys 0..n_rows (sentinel included)
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) <= n_rows) ++b;
+    return b;
+}
+struct RowsWs {
+    int32_t* long_count;
+    uint32_t* long_list;
+};
+static inline size_t rows_ws_bytes(int64_t n) { return 16 + sizeof(uint32_t) * (size_t)(n / LONG_RUN + 1); }
+
+template <int APPLY>
+static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_rowgrad* grad,
+                       const rlctr_table* table, const rlctr_adam* opt, float* dense_grad, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    if (!sorted_ids || !sorted_slots || !grad || !table || !table->data || n < 0) return RLCTR_EINVAL;
+    if (APPLY == 0 && (!opt || !opt->exp_avg || !opt->exp_avg_sq || !opt->sched || !opt->step)) return RLCTR_EINVAL;
+    if (APPLY == 1 && !dense_grad) return RLCTR_EINVAL;
+    if ((grad->dlogit || grad->extra) && grad->fields <= 0) return RLCTR_EINVAL;
+    if (n == 0) return RLCTR_OK;
+    TableView t = view_of(table);
+    AdamView a = APPLY == 0 ? view_of(opt) : AdamView{};
+    GradView g{grad->staged, grad->dlogit, grad->sums, grad->extra, grad->fields};
+    if (t.rs == 1) {
+        if (grad->extra || grad->sums) return RLCTR_EUNSUPPORTED;
+        rows_scalar_kernel<APPLY><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
+    if (t.rs % 4 != 0 || t.rs > 32) return RLCTR_EUNSUPPORTED;
+    if (ws_bytes < rows_ws_bytes(n) || !ws) return RLCTR_EWORKSPACE;
+    RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
+    RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
+    const int lpr = rlctr_lanes_per_row(t.rs);
+    const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
+#define LAUNCH_ROWS(L)                                                                                              \
+    rows_short_kernel<L, APPLY><<<blocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad,           \
+                                                        w.long_count, w.long_list);                                \
+    rows_long_kernel<L, APPLY><<<RLCTR_SMS, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad,         \
+                                                          w.long_count, w.long_list)
+    switch (lpr) {
+        case 1: LAUNCH_ROWS(1); break;
+        case 2: LAUNCH_ROWS(2); break;
+        case 4: LAUNCH_ROWS(4); break;
+        default: LAUNCH_ROWS(8); break;
+    }
+#undef LAUNCH_ROWS
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+}  // namespace rlctr
+
+using namespace rlctr;
+
+extern "C" size_t rlctr_sort_ws_bytes(int64_t n, int64_t n_rows) {
+    if (n <= 0) return 16;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, key_bits(n_rows));
+    size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    return 2 * arr + temp + 256;
+}
+
+extern "C" int rlctr_sort_ids(const int64_t* ids, int64_t n, int64_t n_rows, uint32_t* sorted_ids,
+                              uint32_t* sorted_slots, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
+    if (!ids || !sorted_ids || !sorted_slots || !ws || n < 0 || n_rows <= 0) return RLCTR_EINVAL;
+    if (n >= ((int64_t)1 << 32) || n_rows >= ((int64_t)1 << 32) - 1) return RLCTR_EUNSUPPORTED;
+    if (n == 0) return RLCTR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    if (ws_bytes < 2 * arr + 256) return RLCTR_EWORKSPACE;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ws);
+    uint32_t* vals = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + arr);
+    void* temp = reinterpret_cast<char*>(ws) + 2 * arr;
+    size_t temp_bytes = ws_bytes - 2 * arr;
+    sort_prep_kernel<<<grid_1d(n, RLCTR_SMS * 8), 256, 0, st>>>(ids, n, n_rows, keys, vals);
+    RLCTR_LAUNCH_CHECK();
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, sorted_ids, vals, sorted_slots, n, 0,
+                                                    key_bits(n_rows), st);
+    if (e != cudaSuccess) return (int)e;
+    return RLCTR_OK;
+}
+
+extern "C" size_t rlctr_rows_ws_bytes(int64_t n) { return rows_ws_bytes(n < 0 ? 0 : n); }
+
+extern "C" int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
+                               const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt, void* ws,
+                               size_t ws_bytes, rlctr_stream_t stream) {
+    return launch_rows<0>(sorted_ids, sorted_slots, n, grad, table, opt, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
+                                     const rlctr_rowgrad* grad, const rlctr_table* table, float* dense_grad, void* ws,
+                                     size_t ws_bytes, rlctr_stream_t stream) {
+    return launch_rows<1>(sorted_ids, sorted_slots, n, grad, table, nullptr, dense_grad, ws, ws_bytes,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table* table,
+                                  const rlctr_adam* opt, rlctr_stream_t stream) {
+    if (!sorted_ids || !table || !table->data || !opt || !opt->stamp || !opt->sched || !opt->step || n < 0)
+        return RLCTR_EINVAL;
+    if (n == 0) return RLCTR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableView t = view_of(table);
+    AdamView a = view_of(opt);
+    if (t.rs == 1) {
+        rows_catchup_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted_ids, n, t, a);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
+    if (t.rs % 4 != 0 || t.rs > 32) return RLCTR_EUNSUPPORTED;
+    const int lpr = rlctr_lanes_per_row(t.rs);
+    const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
+    switch (lpr) {
+        case 1: rows_catchup_kernel<1><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
+        case 2: rows_catchup_kernel<2><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
+        case 4: rows_catchup_kernel<4><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
+        default: rows_catchup_kernel<8><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
+    }
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt, int64_t row_begin, int64_t row_end,
+                                rlctr_stream_t stream) {
+    if (!table || !table->data || !opt || !opt->stamp || !opt->sched || !opt->step) return RLCTR_EINVAL;
+    if (row_begin < 0 || row_end > table->n_rows || row_begin > row_end) return RLCTR_EINVAL;
+    if (row_begin == row_end) return RLCTR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableView t = view_of(table);
+    AdamView a = view_of(opt);
+    if (t.rs == 1) {
+        adam_flush_scalar_kernel<<<grid_1d(row_end - row_begin, RLCTR_SMS * 8), 256, 0, st>>>(t, a, row_begin, row_end);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
+    if (t.rs % 4 != 0) return RLCTR_EUNSUPPORTED;
+    adam_flush_kernel<<<grid_1d((row_end - row_begin) * (t.rs / 4), RLCTR_SMS * 8), 256, 0, st>>>(t, a, row_begin, row_end);
+    RLCTR_LAUNCH_CHECK();
+    stamp_fill_kernel<<<grid_1d(row_end - row_begin, RLCTR_SMS * 8), 256, 0, st>>>(a.stamp, a.step, row_begin, row_end);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const float* sched, const int32_t* step, float beta1, float beta2, float eps,
+                                float weight_decay, rlctr_stream_t stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !sched || !step || n < 0) return RLCTR_EINVAL;
+    if (n == 0) return RLCTR_OK;
+    dense_adam_kernel<<<grid_1d(n, RLCTR_SMS * 8), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, reinterpret_cast<const float2*>(sched), step,
+        AdamHyper{beta1, beta2, eps, weight_decay});
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_step_advance(int32_t* step, int32_t delta, rlctr_stream_t stream) {
+    if (!step) return RLCTR_EINVAL;
+    step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, delta);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
