@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: train samples/sec + HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (SURVEY section 8d, config C2 == BASELINE.json configs[1]): one STEP = one training step of LR,
+FM and DeepFM (forward, BCE loss, backward, Adam lr=1e-3 wd=1e-5 with the reference's dense-Adam
+numerics) on ONE batch of B=65536 samples x F=15 fields, latent D=10, N=10,000,000 rows per table,
+ids uniform over disjoint per-field ranges (tables >> L2, ~95% unique rows per batch), labels ~5% CTR.
+value = B * steps / time: whole-job samples/s, inputs resident in HBM.  The lazy-exact optimizer's
+flush (the pass that makes every untouched row equal to the reference's dense-Adam state) runs once
+at the end INSIDE the timed region, so the tables at the end are the reference's tables.
+
+e2e = the same steps through the drop-in API (model(x); BCELoss; zero_grad; backward; optimizer.step();
+loss.item()) with each batch copied from pinned host memory inside the timed region.
+
+--impl reference: the reference's own CPU implementation of the same step (oracle/torch_port.py: the
+same stock ATen CPU kernels the reference's modules call, dense torch.optim.Adam) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_FIELDS = 15
+MODELS = ("LR", "FM", "DeepFM")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dims", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_batch(gen, B, N, device):
+    """uniform ids over disjoint per-field ranges of N/F rows; ~5% positive labels."""
+    per = N // F_FIELDS
+    x = torch.randint(0, per, (B, F_FIELDS), generator=gen, device=device, dtype=torch.int64)
+    x += torch.arange(F_FIELDS, device=device, dtype=torch.int64) * per
+    y = (torch.rand(B, generator=gen, device=device) < 0.05).to(torch.int64)
+    return x, y
+
+
+def alg_bytes(key, m):
+    """ALGORITHMIC bytes of one launch (DESIGN.md 'Kernels'): logical row sizes
+    4*(D+1), int64 ids, each distinct row's Adam state read and written once.  U = expected number of
+    distinct ids of a uniform batch."""
+    name = key.split("[")[0]
+    if name == "rlctr_sort_ids":
+        return 16.0 * m["n"]                                   # read int64 ids, write u32 key + u32 slot
+    if name == "rlctr_adam_flush":
+        return m["n_rows"] * (24.0 * m["rs"] + 8.0)
+    B, F, N = m["B"], m["F"], m["n_rows"]
+    logical = (m["dim"] + (1 if m["lin"] else 0)) if m["rs"] > 1 else 1
+    n = B * F
+    per = N / F
+    U = F * per * (1.0 - (1.0 - 1.0 / per) ** B)
+    if name == "rlctr_embed_fwd":
+        b = B * (F * 8 + F * 4 * logical + 4)
+        if m.get("sums"):
+            b += B * 4 * logical
+        if m.get("rows"):
+            b += n * m["dim"] * 4
+        return float(b)
+    if name == "rlctr_rows_adam":
+        b = U * 24 * logical + n * 8 + B * 4
+        if m["model"] in ("FM", "DeepFM"):
+            b += B * 4 * logical                               # saved column sums
+        if m.get("extra"):
+            b += n * m["dim"] * 4                              # tower input gradient
+        if m.get("staged"):
+            b += n * 4 * logical
+        if m.get("stamp"):
+            b += U * 8
+        return float(b)
+    if name == "rlctr_rows_catchup":
+        return float(n * 4 + U * 4)                            # lower bound: stale rows add 24*logical each
+    if name == "rlctr_ffm_fwd":
+        return float(B * (F * 8 + F * 4 * logical + 4) + n * 4 * logical)
+    return 0.0
+
+
+class Clocks:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU port of the reference modules, dense Adam, all host threads
+# ----------------------------------------------------------------------------------------------
+def cpu_models(N, D):
+    from oracle import torch_port as TP
+    torch.manual_seed(1)
+    ms = []
+    for name in MODELS:
+        m = TP.PortCTR(name, N, F_FIELDS, D)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if "embedding" in k or k == "linear.weight":
+                    p.mul_(0.1)
+        m.train()
+        ms.append((m, TP.make_adam(m)))
+    return ms
+
+
+def cpu_step(ms, x, y):
+    from oracle import torch_port as TP
+    lossf = torch.nn.BCELoss()
+    for m, opt in ms:
+        TP.ctr_train_step(m, opt, lossf, x, y.unsqueeze(1))
+
+
+def run_cpu(B, N, D, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(1)
+    ms = cpu_models(N, D)
+    batches = [make_batch(gen, B, N, "cpu") for _ in range(min(steps + warmup, 4))]
+    for i in range(warmup):
+        cpu_step(ms, *batches[i % len(batches)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_step(ms, *batches[(warmup + i) % len(batches)])
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, N, D = args.batch, args.rows, args.dims
+    # bound the run: one dense-Adam step costs O(N) on the CPU; time a probe step, then shrink N (which
+    # only FAVOURS the reference: its step time is ~linear in N) if K steps would not fit
+    sample = f"full workload: B={B}, N={N} rows, all three models, dense Adam"
+    n_used = N
+    probe_n = min(N, 1_000_000)
+    _, t_probe, cores = run_cpu(B, probe_n, D, 1, 1)
+    est = t_probe * (N / probe_n) * (args.steps + args.warmup)
+    if est > 200.0:
+        n_used = max(int(N * 200.0 / est), 100_000)
+        sample = (f"B={B}, table rows reduced to N={n_used} (of {N}) so that {args.steps}+{args.warmup} steps end within "
+                  f"minutes; the reference's step time is ~linear in N, so this OVERSTATES its throughput")
+    v, t_step, cores = run_cpu(B, n_used, D, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "train samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, N, D),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(B, N, D):
+    return {"workload": "C2: LR+FM+DeepFM train step (fwd, BCE, bwd, Adam lr=1e-3 wd=1e-5, reference dense-Adam "
+                        "numerics) on one batch", "batch": B, "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
+            "ids": "uniform over disjoint per-field ranges", "l2": "inputs larger than L2: 3 tables x 3 arrays x "
+            f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step"}
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch.distributed as dist
+    from rl_ctr_prediction_b200 import _lib, optim, p_model, pretrain_main as PM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, D, K, W = args.batch, args.rows, args.dims, args.steps, args.warmup
+    W = max(W, 3)
+    lib = _lib.load()
+    torch.manual_seed(1 + rank)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+
+    def build_models():
+        ms = []
+        for name in MODELS:
+            m = {"LR": lambda: p_model.LR(N, device=dev), "FM": lambda: p_model.FM(N, D, device=dev),
+                 "DeepFM": lambda: p_model.DeepFM(N, F_FIELDS, D, device=dev)}[name]()
+            with torch.no_grad():
+                m.table.mul_(0.1)
+            m.train()
+            ms.append((m, optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5, mode="lazy")))
+        return ms
+
+    lossf = torch.nn.BCELoss()
+
+    def step(ms, x, y):
+        out = []
+        for m, opt in ms:
+            if isinstance(m, p_model.DeepFM):
+                p = m(x)
+                tl = lossf(p, y.unsqueeze(1).float())
+                m.zero_grad()
+                tl.backward()
+                opt.step()
+            else:
+                tl = PM.fused_train_step(m, opt, x, y)
+            out.append(tl)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (`value`) -------------------------------------
+    ms = build_models()
+    batches = [make_batch(gen, B, N, dev) for _ in range(K + W)]
+    prof = _lib.KernelTimer()
+    for i in range(W):
+        step(ms, *batches[i])
+    barrier()
+    clocks = Clocks(local)
+    clocks.start()
+    l0 = lib.rlctr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.set_timer(prof)
+    e0.record()
+    for i in range(K):
+        step(ms, *batches[W + i])
+    for m, _ in ms:
+        m.flush()
+    e1.record()
+    barrier()
+    _lib.set_timer(None)
+    launches = lib.rlctr_launch_count() - l0
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = B * K * world / (ms_total / 1e3)
+
+    # ---------------- roofline of the dominant kernel --------------------------------------
+    kern = prof.summary(alg_bytes)   # name -> (launches, mean ms, algorithmic bytes per launch)
+    peak, peak_src = peaks()
+    roof = None
+    if kern:
+        name = max(kern, key=lambda k: kern[k][0] * kern[k][1])
+        n_l, mean_ms, alg = kern[name]
+        achieved = alg / (mean_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "launches_timed": n_l, "mean_ms": mean_ms,
+                "share_of_step": n_l * mean_ms / ms_total,
+                "all_kernels": {k: {"launches": v[0], "mean_ms": v[1], "GBps": v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 else None}
+                                for k, v in kern.items()}}
+    del ms, batches
+    torch.cuda.empty_cache()
+
+    # ---------------- end to end through the drop-in API (`e2e`) ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        ms = build_models()
+        gen_c = torch.Generator().manual_seed(100 + rank)
+        host = []
+        for _ in range(K + W):
+            x, y = make_batch(gen_c, B, N, "cpu")
+            host.append((x.pin_memory(), y.pin_memory()))
+
+        def e2e_step(xh, yh):
+            x = xh.to(dev, non_blocking=True)
+            y = torch.unsqueeze(yh, 1).to(dev, non_blocking=True)
+            total = 0.0
+            for m, opt in ms:
+                p = m(x)                                   # src/main/pretrain_main.py:96-103, per model
+                tl = lossf(p, y.float())
+                m.zero_grad()
+                tl.backward()
+                opt.step()
+                total += tl.item()                         # device -> host read of the step's loss
+            return total
+
+        for i in range(W):
+            e2e_step(*host[i])
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            e2e_step(*host[W + i])
+        for m, _ in ms:
+            m.flush()
+        e1.record()
+        barrier()
+        ms_e2e = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * K * world / (t.item() / 1e3), "unit": "samples/s",
+               "h2d_bytes_per_step": B * F_FIELDS * 8 + B * 8, "d2h_bytes_per_step": 4 * len(MODELS),
+               "ms_per_step": t.item() / K, "api": "model(x); nn.BCELoss; zero_grad; backward; optim.Adam.step; loss.item()"}
+        del ms, host
+        torch.cuda.empty_cache()
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, t_step, cores = run_cpu(B, N, D, args.cpu_steps, 1)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_steps} steps (after 1 warm-up) of the same workload (B={B}, N={N}), "
+                         f"{t_step:.2f} s/step, dense Adam over all rows (reference semantics)"}
+
+    if rank == 0:
+        line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D),
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,14 +59,15 @@ typedef struct rlctr_table {
 
 /* torch.optim.Adam state for one table (src/main/pretrain_main.py:181).  `sched[t]` holds
  * the two Python-double scalars torch derives at step t, cast to fp32:
- * (lr / (1 - beta1^t), sqrt(1 - beta2^t)).  `step` is a DEVICE scalar so a captured CUDA
- * graph can be replayed while the step advances (rlctr_step_advance). */
+ * (lr / (1 - beta1^t), sqrt(1 - beta2^t)).  `step` is a DEVICE scalar holding the number of
+ * COMPLETED optimizer steps (0 after construction), so a captured CUDA graph can be replayed
+ * while the step advances (rlctr_step_advance, +1 after the update kernels of a step). */
 typedef struct rlctr_adam {
     float*         exp_avg;      /* [n_rows, row_stride] */
     float*         exp_avg_sq;   /* [n_rows, row_stride] */
     int32_t*       stamp;        /* [n_rows] last step at which the row is up to date; NULL in sparse mode */
     const float*   sched;        /* [sched_len][2], index = step (entry 0 unused) */
-    const int32_t* step;         /* device scalar: the step being applied, >= 1 */
+    const int32_t* step;         /* device scalar: completed steps t; update kernels apply step t+1 */
     int32_t        sched_len;
     float          beta1, beta2, eps, weight_decay;
 } rlctr_adam;
@@ -78,15 +79,20 @@ typedef struct rlctr_adam {
  *   + dlogit[b] * (sums[b] - row) on the latent cols (FM: d z / d v_f = S - v_f)
  *   + extra[b, f*dim .. ]          on the latent cols (dense tail, e.g. the DeepFM tower)
  * any of the four pointers may be NULL. */
+#define RLCTR_STAGED_PARTNER 1   /* staged[slot] = d logit / d row (rlctr_ffm_fwd `partners`): the row
+                                  * gradient is dlogit[b] * staged[slot] and nothing else            */
 typedef struct rlctr_rowgrad {
     const float* staged;   /* [n, row_stride] */
     const float* dlogit;   /* [B] */
     const float* sums;     /* [B, row_stride] from rlctr_embed_fwd */
     const float* extra;    /* [B, fields*dim] */
     int32_t      fields;
+    int32_t      flags;    /* 0 or RLCTR_STAGED_PARTNER */
 } rlctr_rowgrad;
 
 int         rlctr_version(void);
+/* kernels launched by this library in this process so far (host-side tally; bench.py's gpu_launches) */
+unsigned long long rlctr_launch_count(void);
 const char* rlctr_strerror(int code);
 
 /* ------------------------------------------------------------------------------------
@@ -110,18 +116,16 @@ int rlctr_gather_rows(const int64_t* ids, int64_t n, const rlctr_table* table, f
                       rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
- * K2  FFM over the interleaved table (dim = fields*latent): p_model.py:82-100.
+ * K2  FFM over the interleaved table (dim = fields*latent; column block t of row id is
+ * field_feature_embeddings[t].weight[id]): p_model.py:82-100.
  *   logit[b] = bias + sum_f w[x_f] + sum_{i<j} <T_j[x_i], T_i[x_j]>
- * rlctr_ffm_bwd_rows writes the staged row gradients grad_rows[b*F+i, :] =
- * dlogit[b] * [1, T_0[x_i]^T-partner ...] i.e. column block j of row i gets
- * dlogit[b]*T_i[x_j] (zero on the diagonal) -- autograd of :91 (SURVEY section 3.7 FFM).
+ * partners (optional, training; [B*F, row_stride]): partners[b*F+i, block j] = T_i[x_j] for
+ * j != i, 0 on the diagonal, 1 at lin_col -- d logit / d row_i, the autograd of :91 (SURVEY
+ * section 3.7 FFM).  Feed it to rlctr_rows_adam as `staged` with RLCTR_STAGED_PARTNER.
  * ------------------------------------------------------------------------------------ */
 int rlctr_ffm_fwd(const int64_t* ids, const rlctr_table* table, const float* bias,
-                  float* logit, float* pctr, int64_t pctr_stride,
+                  float* logit, float* pctr, int64_t pctr_stride, float* partners,
                   int64_t batch, int32_t fields, int32_t latent, rlctr_stream_t stream);
-int rlctr_ffm_bwd_rows(const int64_t* ids, const rlctr_table* table, const float* dlogit,
-                       float* grad_rows, int64_t batch, int32_t fields, int32_t latent,
-                       rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K5  RL state encoder: Feature_Embedding.forward, Feature_embedding.py:51-59.
@@ -136,15 +140,22 @@ int rlctr_featemb_fwd(const int64_t* ids, const rlctr_table* table, float* out, 
  * Loss head: torch.sigmoid + nn.BCELoss(mean) forward AND their autograd
  * (p_model.py:55; src/main/pretrain_main.py:167,98,101), with torch's exact clamp
  * semantics (log >= -100; (p-y)/max((1-p)p,1e-12)):
- *   pctr = sigmoid(logit); loss[0] = mean BCE; dlogit[b] = dL/dlogit[b].
+ *   pctr = sigmoid(logit); loss[0] = mean BCE; dlogit[b] = dL/dlogit[b]; dbias[0] = sum_b dlogit[b].
  * Exactly one of labels_i64 / labels_f32 is non-NULL.  ws: RLCTR_REDUCE_WS_BYTES bytes,
  * zeroed once by the caller (the kernel leaves its counter zeroed).  The mean is a
  * fixed-shape two-level tree: bit-identical from run to run.
  * ------------------------------------------------------------------------------------ */
 #define RLCTR_REDUCE_WS_BYTES 16640
 int rlctr_bce_fwd_bwd(const float* logit, const int64_t* labels_i64, const float* labels_f32,
-                      float* pctr, float* loss, float* dlogit, void* ws, int64_t batch,
+                      float* pctr, float* loss, float* dlogit, float* dbias, void* ws, int64_t batch,
                       rlctr_stream_t stream);
+/* The drop-in loop keeps the caller's own loss (nn.BCELoss at src/main/pretrain_main.py:98), so
+ * autograd hands back dL/dpctr: this is torch's sigmoid_backward, dlogit = grad_p*(1-p)*p, plus
+ * dbias[0] = sum_b dlogit[b] (the gradient of the `bias` parameter, p_model.py:16,36) as a
+ * fixed-shape tree.  grad_p == NULL: dlogit is an input and only the sum is taken.  dbias, ws
+ * optional (ws as in rlctr_bce_fwd_bwd). */
+int rlctr_sigmoid_bwd(const float* grad_p, const float* pctr, float* dlogit, float* dbias, void* ws,
+                      int64_t batch, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  deterministic scatter: sort (id, slot) pairs, segment-reduce, fused Adam.
@@ -159,8 +170,9 @@ int rlctr_sort_ids(const int64_t* ids, int64_t n, int64_t n_rows,
 
 size_t rlctr_rows_ws_bytes(int64_t n);
 /* For every distinct id: g = sum over its occurrences (slot order) of the row gradient,
- * then one Adam step with L2 (g += wd*p) on that row; stamp[id] = *step.  No atomics on
- * the data path; bit-identical from run to run. */
+ * then Adam step *step+1 with L2 (g += wd*p) on that row (after replaying the L2-only steps
+ * stamp[id]+1 .. *step it missed); stamp[id] = *step+1.  No atomics on the data path;
+ * bit-identical from run to run.  Follow with rlctr_step_advance(+1). */
 int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                     const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
                     void* ws, size_t ws_bytes, rlctr_stream_t stream);
@@ -169,9 +181,9 @@ int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, in
 int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                           const rlctr_rowgrad* grad, const rlctr_table* table, float* dense_grad,
                           void* ws, size_t ws_bytes, rlctr_stream_t stream);
-/* Lazy-exact mode: bring every distinct id of the batch up to step (*step - 1) by replaying
- * the L2-only Adam steps it missed (g = wd*p), so the forward reads what dense Adam would
- * have produced.  Call with *step already advanced to the step about to be applied. */
+/* Lazy-exact mode: bring every distinct id of the batch up to *step (the completed steps) by
+ * replaying the L2-only Adam steps it missed (g = wd*p), so the forward reads exactly what the
+ * reference's dense Adam would have produced. */
 int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table* table,
                        const rlctr_adam* opt, rlctr_stream_t stream);
 /* Replay the missed L2-only steps of rows [row_begin,row_end) up to *step.  Called once per
@@ -179,7 +191,8 @@ int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table*
  * the flush of the lazy mode (mode B). */
 int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
                      int64_t row_begin, int64_t row_end, rlctr_stream_t stream);
-/* Dense Adam for the replicated parameters (bias, tower, policy nets): torch semantics. */
+/* Dense Adam for the replicated parameters (bias, tower, policy nets): applies step *step+1
+ * with torch semantics. */
 int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                      const float* sched, const int32_t* step, float beta1, float beta2, float eps,
                      float weight_decay, rlctr_stream_t stream);

@@ -7,10 +7,16 @@
 #define RLCTR_FULL 0xffffffffu
 #define RLCTR_SMS 148          // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+// host-side tally of kernels this library launched (rlctr_launch_count): bench.py reports it as
+// `gpu_launches`; it is the only process-global the library keeps and nothing reads it back.
+extern unsigned long long g_rlctr_launches;
+#define RLCTR_COUNT_LAUNCH(n) __atomic_fetch_add(&g_rlctr_launches, (unsigned long long)(n), __ATOMIC_RELAXED)
+
 #define RLCTR_LAUNCH_CHECK()                         \
     do {                                             \
         cudaError_t e__ = cudaGetLastError();        \
         if (e__ != cudaSuccess) return (int)e__;     \
+        RLCTR_COUNT_LAUNCH(1);                       \
     } while (0)
 
 #define RLCTR_CUDA(call)                             \

@@ -1,0 +1,124 @@
+// ffm.cu -- K2: FFM forward over the interleaved table (p_model.py:59-100).  sm_100a.
+//
+// The reference keeps F tables of [N, D] and gathers F*F rows of 40 B per sample (p_model.py:87).
+// Here one id owns ONE contiguous fused row
+//     [ T_0[id] | T_1[id] | ... | T_{F-1}[id] | w[id] | pad ]      (F*D + 1 floats, padded to x4)
+// so a sample reads F contiguous rows of ~600 B as coalesced 128-bit chunks instead of F*F
+// scattered 40 B rows.  A warp owns a sample: the F rows are staged in shared
+// memory, then the P = F(F-1)/2 pair dots <T_j[x_i], T_i[x_j]> are taken from there.
+//
+// Training: the same kernel optionally writes the "partner rows"
+//     partners[b*F + i, block j] = T_i[x_j]     (j != i; zero on the diagonal, lin col = 1)
+// i.e. d logit / d row_i, so the backward is a pure scale by dlogit[b] done inside the
+// sort/segment-reduce/Adam kernel (optim.cu, RLCTR_STAGED_PARTNER) and never re-gathers.
+#include "common.cuh"
+
+namespace rlctr {
+
+constexpr int FFM_WARPS = 4;
+
+__global__ void __launch_bounds__(FFM_WARPS * 32)
+ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int rs,
+               int lin_col, int emb_col, const float* __restrict__ bias, float* __restrict__ logit,
+               float* __restrict__ pctr, int64_t pctr_stride, float* __restrict__ partners,
+               int64_t batch, int fields, int latent) {
+    extern __shared__ __align__(16) float smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npair = fields * (fields - 1) / 2;
+    const int chunks = rs >> 2;
+    float* stage = smem + (size_t)wib * fields * rs;                       // [F][rs] of this warp
+    unsigned char* pi = reinterpret_cast<unsigned char*>(smem + (size_t)FFM_WARPS * fields * rs);
+    unsigned char* pj = pi + npair;
+    for (int i = threadIdx.x; i < fields - 1; i += blockDim.x) {
+        const int base = i * fields - i * (i + 1) / 2;                     // pair order of p_model.py:89-91
+        for (int j = i + 1; j < fields; ++j) {
+            pi[base + j - i - 1] = (unsigned char)i;
+            pj[base + j - i - 1] = (unsigned char)j;
+        }
+    }
+    __syncthreads();
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    const int64_t warp0 = (int64_t)blockIdx.x * FFM_WARPS + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * FFM_WARPS;
+    const int total = fields * chunks;                                     // float4 chunks per sample
+    for (int64_t b = warp0; b < batch; b += nwarps) {
+        // ---- gather: lane-strided over the F*chunks float4 of the sample (all loads independent)
+        for (int t = lane; t < total; t += 32) {
+            const int f = t / chunks, c = t - f * chunks;
+            const int64_t id = __ldg(ids + b * fields + f);
+            float4 r = f4zero();
+            if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(tab + id * rs + 4 * c);
+            st4(stage + f * rs + 4 * c, r);
+        }
+        __syncwarp();
+        // ---- first order + pair dots
+        float acc = 0.f;
+        if (lin_col >= 0)
+            for (int f = lane; f < fields; f += 32) acc += stage[f * rs + lin_col];
+        for (int p = lane; p < npair; p += 32) {
+            const int i = pi[p], j = pj[p];
+            const float* a = stage + i * rs + emb_col + j * latent;        // T_j[x_i]
+            const float* c = stage + j * rs + emb_col + i * latent;        // T_i[x_j]
+            float d = 0.f;
+            for (int k = 0; k < latent; ++k) d = fmaf(a[k], c[k], d);
+            acc += d;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(RLCTR_FULL, acc, off);
+        if (lane == 0) {
+            const float z = b0 + acc;
+            if (logit) logit[b] = z;
+            if (pctr) pctr[b * pctr_stride] = sigmoidf_ref(z);
+        }
+        // ---- partner rows (training): row (b,i), column block j  <-  stage[j][block i]
+        if (partners) {
+            float* out = partners + (b * fields) * (int64_t)rs;
+            const int per_sample = fields * rs;
+            for (int t = lane; t < per_sample; t += 32) {
+                const int i = t / rs, col = t - i * rs;
+                float v = 0.f;
+                const int e = col - emb_col;
+                if (col == lin_col) v = 1.0f;
+                else if (e >= 0 && e < fields * latent) {
+                    const int j = e / latent, k = e - j * latent;
+                    if (j != i) v = stage[j * rs + emb_col + i * latent + k];
+                }
+                __stcs(out + t, v);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace rlctr
+
+using namespace rlctr;
+
+extern "C" int rlctr_ffm_fwd(const int64_t* ids, const rlctr_table* table, const float* bias, float* logit,
+                             float* pctr, int64_t pctr_stride, float* partners, int64_t batch, int32_t fields,
+                             int32_t latent, rlctr_stream_t stream) {
+    if (!ids || !table || !table->data || table->n_rows <= 0 || batch < 0) return RLCTR_EINVAL;
+    if (fields < 2 || fields > 255 || latent <= 0) return RLCTR_EUNSUPPORTED;
+    const int rs = table->row_stride;
+    if (rs % 4 != 0 || table->dim != fields * latent || table->emb_col < 0 ||
+        table->emb_col + table->dim > rs || table->lin_col >= rs)
+        return RLCTR_EINVAL;
+    if (!rlctr_aligned16(table->data) || (partners && !rlctr_aligned16(partners))) return RLCTR_EALIGN;
+    if (pctr && pctr_stride < 1) return RLCTR_EINVAL;
+    if (batch == 0) return RLCTR_OK;
+    const int npair = fields * (fields - 1) / 2;
+    const size_t smem = (size_t)FFM_WARPS * fields * rs * sizeof(float) + 2 * (size_t)npair;
+    if (smem > 200 * 1024) return RLCTR_EUNSUPPORTED;
+    RLCTR_CUDA(cudaFuncSetAttribute(ffm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int64_t want = (batch + FFM_WARPS - 1) / FFM_WARPS;
+    int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    const int64_t cap = (int64_t)RLCTR_SMS * per_sm;
+    const int grid = (int)(want < cap ? want : cap);
+    ffm_fwd_kernel<<<grid, FFM_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        ids, table->data, table->n_rows, rs, table->lin_col, table->emb_col, bias, logit, pctr, pctr_stride,
+        partners, batch, fields, latent);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}

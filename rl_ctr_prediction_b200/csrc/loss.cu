@@ -44,10 +44,11 @@ __device__ __forceinline__ bool last_block_arrives(unsigned int* counter) {
 
 __global__ void __launch_bounds__(256)
 bce_kernel(const float* __restrict__ logit, const int64_t* __restrict__ yi, const float* __restrict__ yf,
-           float* __restrict__ pctr, float* __restrict__ loss, float* __restrict__ dlogit, void* ws, int64_t batch) {
+           float* __restrict__ pctr, float* __restrict__ loss, float* __restrict__ dlogit, float* __restrict__ dbias,
+           void* ws, int64_t batch) {
     __shared__ float sm[8];
     const float ginv = 1.0f / (float)batch;            // mean-reduction backward: grad / numel
-    float acc = 0.f;
+    float acc = 0.f, dsum = 0.f;
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < batch; b += (int64_t)gridDim.x * blockDim.x) {
         const float z = __ldg(logit + b);
         const float y = yi ? (float)__ldg(yi + b) : __ldg(yf + b);
@@ -56,20 +57,57 @@ bce_kernel(const float* __restrict__ logit, const int64_t* __restrict__ yi, cons
         acc += (y - 1.0f) * fmaxf(log1pf(-p), -100.0f) - y * fmaxf(logf(p), -100.0f);
         // backward: grad*(p-y)/max((1-p)*p, 1e-12), then sigmoid_backward: g*(1-p)*p
         const float dp = ginv * (p - y) / fmaxf((1.0f - p) * p, 1e-12f);
+        const float dz = dp * (1.0f - p) * p;
         if (pctr) pctr[b] = p;
-        if (dlogit) dlogit[b] = dp * (1.0f - p) * p;
+        if (dlogit) dlogit[b] = dz;
+        dsum += dz;
     }
     RedWs w = red_ws(ws);
-    const float bs = block_sum_256(acc, sm);
-    if (threadIdx.x == 0) w.partial[blockIdx.x] = bs;
+    const float bs = block_sum_256(acc, sm), ds = block_sum_256(dsum, sm);
+    if (threadIdx.x == 0) { w.partial[blockIdx.x] = bs; w.partial[RED_MAX_BLOCKS + blockIdx.x] = ds; }
     if (last_block_arrives(w.counter)) {
-        float t = 0.f;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t += __ldcg(w.partial + i);
+        float t = 0.f, d = 0.f;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) {
+            t += __ldcg(w.partial + i);
+            d += __ldcg(w.partial + RED_MAX_BLOCKS + i);
+        }
         t = block_sum_256(t, sm);
+        d = block_sum_256(d, sm);
         if (threadIdx.x == 0) {
             if (loss) loss[0] = t / (float)batch;
+            if (dbias) dbias[0] = d;                   // d L / d bias = sum_b dlogit[b]
             *w.counter = 0;                            // leave the workspace re-usable
         }
+    }
+}
+
+// torch sigmoid_backward after a user-side loss (e.g. nn.BCELoss): dlogit = g * (1 - p) * p, and
+// the bias gradient sum_b dlogit[b] as a fixed-shape tree.  grad_p == NULL: dlogit is given, only sum it.
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_kernel(const float* __restrict__ grad_p, const float* __restrict__ pctr, float* __restrict__ dlogit,
+                   float* __restrict__ dbias, void* ws, int64_t batch) {
+    __shared__ float sm[8];
+    float dsum = 0.f;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < batch; b += (int64_t)gridDim.x * blockDim.x) {
+        float dz;
+        if (grad_p) {
+            const float p = __ldg(pctr + b);
+            dz = __ldg(grad_p + b) * (1.0f - p) * p;
+            dlogit[b] = dz;
+        } else {
+            dz = dlogit[b];
+        }
+        dsum += dz;
+    }
+    if (!dbias) return;
+    RedWs w = red_ws(ws);
+    const float ds = block_sum_256(dsum, sm);
+    if (threadIdx.x == 0) w.partial[blockIdx.x] = ds;
+    if (last_block_arrives(w.counter)) {
+        float d = 0.f;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) d += __ldcg(w.partial + i);
+        d = block_sum_256(d, sm);
+        if (threadIdx.x == 0) { dbias[0] = d; *w.counter = 0; }
     }
 }
 
@@ -235,10 +273,20 @@ static inline int red_grid(int64_t batch) {
 using namespace rlctr;
 
 extern "C" int rlctr_bce_fwd_bwd(const float* logit, const int64_t* labels_i64, const float* labels_f32, float* pctr,
-                                 float* loss, float* dlogit, void* ws, int64_t batch, rlctr_stream_t stream) {
+                                 float* loss, float* dlogit, float* dbias, void* ws, int64_t batch,
+                                 rlctr_stream_t stream) {
     if (!logit || !ws || batch <= 0) return RLCTR_EINVAL;
     if ((labels_i64 == nullptr) == (labels_f32 == nullptr)) return RLCTR_EINVAL;
-    bce_kernel<<<red_grid(batch), 256, 0, (cudaStream_t)stream>>>(logit, labels_i64, labels_f32, pctr, loss, dlogit, ws, batch);
+    bce_kernel<<<red_grid(batch), 256, 0, (cudaStream_t)stream>>>(logit, labels_i64, labels_f32, pctr, loss, dlogit,
+                                                                  dbias, ws, batch);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_sigmoid_bwd(const float* grad_p, const float* pctr, float* dlogit, float* dbias, void* ws,
+                                 int64_t batch, rlctr_stream_t stream) {
+    if (!dlogit || batch <= 0 || (grad_p && !pctr) || (dbias && !ws)) return RLCTR_EINVAL;
+    sigmoid_bwd_kernel<<<red_grid(batch), 256, 0, (cudaStream_t)stream>>>(grad_p, pctr, dlogit, dbias, ws, batch);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
@@ -269,6 +317,9 @@ extern "C" int rlctr_reinforce_loss_bwd(const float* logits, const int64_t* act,
     }
     return RLCTR_OK;
 }
+
+unsigned long long g_rlctr_launches = 0;
+extern "C" unsigned long long rlctr_launch_count(void) { return __atomic_load_n(&g_rlctr_launches, __ATOMIC_RELAXED); }
 
 extern "C" int rlctr_version(void) { return RLCTR_VERSION; }
 

@@ -45,6 +45,7 @@ struct GradView {
     const float* sums;
     const float* extra;
     int fields;
+    int flags;
 };
 
 __global__ void __launch_bounds__(256)
@@ -62,6 +63,10 @@ __device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t slot
                                                 const TableView& t) {
     float4 r = f4zero();
     if (g.staged) r = ldg4(g.staged + (int64_t)slot * t.rs + col0);
+    if (g.flags & RLCTR_STAGED_PARTNER) {               // FFM: d z / d row is staged, scale by dL/dz
+        const float dz = __ldg(g.dlogit + slot / (uint32_t)g.fields);
+        return make_float4(dz * r.x, dz * r.y, dz * r.z, dz * r.w);
+    }
     if (g.dlogit || g.extra) {
         const uint32_t b = slot / (uint32_t)g.fields;
         const uint32_t f = slot - b * (uint32_t)g.fields;
@@ -134,7 +139,7 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
     int step = 0, stamp_in = 0;
     if (work) {
         if (APPLY == 0) {
-            step = __ldg(a.step);
+            step = __ldg(a.step) + 1;
             if (a.stamp) stamp_in = a.stamp[id];
         }
         const float4 p = ld4(t.data + (int64_t)id * t.rs + col0);
@@ -187,7 +192,7 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
             for (int64_t kk = k + sub; kk < end; kk += NSUB)
                 acc = f4add(acc, rowgrad_chunk(g, __ldg(sorted_slots + kk), col0, p, t));
             if (APPLY == 0 && sub == 0) {
-                step = __ldg(a.step);
+                step = __ldg(a.step) + 1;
                 if (a.stamp) stamp_in = a.stamp[id];
             }
         }
@@ -199,8 +204,79 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
         }
         if (sub == 0 && chunk_on) finish_row<APPLY>(id, col0, p, red[threadIdx.x], t, a, dense_grad, step, stamp_in);
         __syncthreads();
-        if (APPLY == 0 && a.stamp && threadIdx.x == 0) a.stamp[id] = __ldg(a.step);
+        if (APPLY == 0 && a.stamp && threadIdx.x == 0) a.stamp[id] = __ldg(a.step) + 1;
     }
+}
+
+// wide rows (row_stride > 32 floats: the interleaved FFM table): one WARP per sorted position,
+// lanes stride the float4 chunks of the row (WCH chunks per lane); runs are walked sequentially
+// in slot order so the sum is bit-identical from run to run.
+constexpr int WCH = 2;                                   // rows up to 32*4*WCH = 256 floats
+template <int APPLY>
+__global__ void __launch_bounds__(256)
+rows_wide_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                 GradView g, TableView t, AdamView a, float* __restrict__ dense_grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const uint32_t id = __ldg(sorted_ids + k);
+    if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;   // warp-uniform
+    const int chunks = t.rs >> 2;
+    float4 p[WCH], acc[WCH];
+#pragma unroll
+    for (int u = 0; u < WCH; ++u) {
+        const int c = lane + 32 * u;
+        acc[u] = f4zero();
+        p[u] = c < chunks ? ld4(t.data + (int64_t)id * t.rs + 4 * c) : f4zero();
+    }
+    int64_t kk = k;
+    uint32_t nxt = id;
+    while (nxt == id) {
+        const uint32_t slot = __ldg(sorted_slots + kk);
+        ++kk;
+        nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < WCH; ++u) {
+            const int c = lane + 32 * u;
+            if (c < chunks) acc[u] = f4add(acc[u], rowgrad_chunk(g, slot, 4 * c, p[u], t));
+        }
+    }
+    int step = 0, stamp_in = 0;
+    if (APPLY == 0) {
+        step = __ldg(a.step) + 1;
+        if (a.stamp) stamp_in = a.stamp[id];
+    }
+#pragma unroll
+    for (int u = 0; u < WCH; ++u) {
+        const int c = lane + 32 * u;
+        if (c < chunks) finish_row<APPLY>(id, 4 * c, p[u], acc[u], t, a, dense_grad, step, stamp_in);
+    }
+    if (APPLY == 0 && a.stamp) {
+        __syncwarp();
+        if (lane == 0) a.stamp[id] = step;
+    }
+}
+__global__ void __launch_bounds__(256)
+rows_catchup_wide_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const uint32_t id = __ldg(sorted_ids + k);
+    if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
+    const int upto = __ldg(a.step);
+    const int st = a.stamp[id];
+    if (st >= upto) return;
+    const int chunks = t.rs >> 2;
+    for (int c = lane; c < chunks; c += 32) {
+        const int64_t off = (int64_t)id * t.rs + 4 * c;
+        float4 p = ld4(t.data + off), m = ld4(a.m + off), v = ld4(a.v + off);
+        adam_replay4(p, m, v, st, upto, a.sched, a.h);
+        st4(t.data + off, p);
+        st4(a.m + off, m);
+        st4(a.v + off, v);
+    }
+    __syncwarp();
+    if (lane == 0) a.stamp[id] = upto;
 }
 
 // lazy mode: bring the distinct ids of the batch up to step-1 before the forward reads them
@@ -216,7 +292,7 @@ rows_catchup_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableVie
         id = __ldg(sorted_ids + k);
         work = (id < (uint64_t)t.n_rows) && (k == 0 || __ldg(sorted_ids + k - 1) != id) && col0 < t.rs;
     }
-    const int upto = __ldg(a.step) - 1;
+    const int upto = __ldg(a.step);
     bool stale = false;
     if (work) {
         const int st = a.stamp[id];
@@ -297,7 +373,7 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
         acc += gsl;
     }
     if (APPLY == 1) { dense_grad[id] = acc; return; }
-    const int step = __ldg(a.step);
+    const int step = __ldg(a.step) + 1;
     float p = t.data[id], m = a.m[id], v = a.v[id];
     if (a.stamp) {
         const int st = a.stamp[id];
@@ -317,7 +393,7 @@ rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, T
     if (k >= n) return;
     const uint32_t id = __ldg(sorted_ids + k);
     if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
-    const int upto = __ldg(a.step) - 1;
+    const int upto = __ldg(a.step);
     const int st = a.stamp[id];
     if (st >= upto) return;
     float p = t.data[id], m = a.m[id], v = a.v[id];
@@ -332,7 +408,7 @@ rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, T
 __global__ void __launch_bounds__(256)
 dense_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   int64_t n, const float2* __restrict__ sched, const int32_t* __restrict__ step, AdamHyper h) {
-    const float2 sc = __ldg(&sched[__ldg(step)]);
+    const float2 sc = __ldg(&sched[__ldg(step) + 1]);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float pp = p[i], mm = m[i], vv = v[i];
         adam_elem(pp, mm, vv, g[i], h, sc.x, sc.y);
@@ -368,14 +444,20 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
     if (n == 0) return RLCTR_OK;
     TableView t = view_of(table);
     AdamView a = APPLY == 0 ? view_of(opt) : AdamView{};
-    GradView g{grad->staged, grad->dlogit, grad->sums, grad->extra, grad->fields};
+    GradView g{grad->staged, grad->dlogit, grad->sums, grad->extra, grad->fields, grad->flags};
+    if ((g.flags & RLCTR_STAGED_PARTNER) && (!g.staged || !g.dlogit || g.fields <= 0)) return RLCTR_EINVAL;
     if (t.rs == 1) {
         if (grad->extra || grad->sums) return RLCTR_EUNSUPPORTED;
         rows_scalar_kernel<APPLY><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad);
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
     }
-    if (t.rs % 4 != 0 || t.rs > 32) return RLCTR_EUNSUPPORTED;
+    if (t.rs % 4 != 0 || t.rs > 128 * WCH) return RLCTR_EUNSUPPORTED;
+    if (t.rs > 32) {
+        rows_wide_kernel<APPLY><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
     if (ws_bytes < rows_ws_bytes(n) || !ws) return RLCTR_EWORKSPACE;
     RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
     RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
@@ -393,6 +475,7 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
         default: LAUNCH_ROWS(8); break;
     }
 #undef LAUNCH_ROWS
+    RLCTR_COUNT_LAUNCH(1);                              // two kernels, one check
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
@@ -427,6 +510,7 @@ extern "C" int rlctr_sort_ids(const int64_t* ids, int64_t n, int64_t n_rows, uin
     cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, sorted_ids, vals, sorted_slots, n, 0,
                                                     key_bits(n_rows), st);
     if (e != cudaSuccess) return (int)e;
+    RLCTR_COUNT_LAUNCH(2 + (key_bits(n_rows) + 7) / 8);   // cub onesweep: histogram, scan, one kernel per 8-bit digit
     return RLCTR_OK;
 }
 
@@ -458,7 +542,12 @@ extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const r
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
     }
-    if (t.rs % 4 != 0 || t.rs > 32) return RLCTR_EUNSUPPORTED;
+    if (t.rs % 4 != 0 || t.rs > 128 * WCH) return RLCTR_EUNSUPPORTED;
+    if (t.rs > 32) {
+        rows_catchup_wide_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(sorted_ids, n, t, a);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
     const int lpr = rlctr_lanes_per_row(t.rs);
     const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
     switch (lpr) {

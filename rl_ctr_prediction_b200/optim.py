@@ -1,0 +1,114 @@
+"""``Adam`` with the constructor / ``step()`` / ``zero_grad()`` surface of ``torch.optim.Adam`` as the
+reference builds it (``torch.optim.Adam(params=model.parameters(), lr=..., weight_decay=...)``,
+src/main/pretrain_main.py:181), so the reference's ``train(model, optimizer, ...)`` drives it unchanged.
+
+Embedding tables (parameters created by :mod:`.p_model`) never see a dense ``[N, D]`` gradient: the
+backward pass leaves (sorted ids, dlogit, saved sums) on the module and ``step()`` runs the
+deterministic sort / segment-reduce / fused Adam kernel (rlctr_rows_adam).  Every other parameter
+(bias, tower, policy nets) takes the fused dense Adam kernel (rlctr_dense_adam).  Numerics are
+torch's ``_single_tensor_adam`` (L2 folded into the gradient) element by element.
+
+``mode``: 'lazy' (default; reference numbers, O(touched rows) traffic), 'dense' (the literal
+reference work: every row every step), 'sparse' (untouched rows frozen -- NOT the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .tables import AdamSchedule, TableAdamState, table_struct
+
+
+class Adam:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, mode="lazy"):
+        params = list(params)
+        if not params:
+            raise ValueError("optimizer got an empty parameter list")
+        self.lr, self.betas, self.eps, self.weight_decay, self.mode = float(lr), tuple(betas), float(eps), \
+            float(weight_decay), mode
+        self.param_groups = [{"params": params, "lr": self.lr, "betas": self.betas, "eps": self.eps,
+                              "weight_decay": self.weight_decay}]
+        self._tables, self._dense = [], []
+        for p in params:
+            owner = getattr(p, "_rlctr_owner", None)
+            if owner is not None:
+                if not p.is_cuda:
+                    raise _lib.RlctrError("move the model to the CUDA device before building the optimizer")
+                # a fresh optimizer == fresh Adam state (the reference re-creates Adam every epoch,
+                # src/main/pretrain_main.py:175-181): settle what the previous one still owes first
+                owner.flush()
+                owner._opt = TableAdamState(p.data, owner._geom, self.lr, self.betas, self.eps, self.weight_decay, mode)
+                self._tables.append(owner)
+            else:
+                self._dense.append(p)
+        self._dense_state = {}
+        self._dense_step = None
+        self._dense_sched = None
+        self._host_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True):
+        for owner in self._tables:
+            owner._stash = None
+        for p in self._dense:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        lib = _lib.load()
+        st = _lib.stream()
+        self._host_step += 1
+        for owner in self._tables:
+            opt = owner._opt
+            opt.sched.ensure(self._host_step + 1)
+            stash = owner._stash
+            owner._stash = None
+            data = owner.table.data
+            if stash is not None:
+                t, a = table_struct(data, owner._geom), opt.struct()
+                g = _lib.RowGrad(_lib.ptr(stash.staged), _lib.ptr(stash.dlogit), _lib.ptr(stash.sums),
+                                 _lib.ptr(stash.extra), stash.fields, stash.flags)
+                ws_bytes = lib.rlctr_rows_ws_bytes(stash.n)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=data.device)
+                _lib.call("rlctr_rows_adam", lib.rlctr_rows_adam, _lib.ptr(stash.sorted_ids), _lib.ptr(stash.sorted_slots),
+                          stash.n, C.byref(g), C.byref(t), C.byref(a), _lib.ptr(ws), ws_bytes, st,
+                          key=f"rlctr_rows_adam[{type(owner).__name__}]",
+                          meta=dict(owner._meta(stash.n // stash.fields, stash.fields), extra=stash.extra is not None,
+                                    staged=stash.staged is not None, stamp=opt.stamp is not None))
+            _lib.check(lib.rlctr_step_advance(_lib.ptr(opt.step), 1, st), "rlctr_step_advance")
+            opt.host_step = self._host_step
+            if opt.stamp is not None:
+                opt.dirty = True
+                if self.mode == "dense":
+                    opt.flush(data)
+        # ---- replicated dense parameters
+        live = [p for p in self._dense if p.grad is not None]
+        if live:
+            dev = live[0].device
+            if self._dense_step is None:
+                self._dense_step = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._dense_sched = AdamSchedule(self.lr, self.betas, dev)
+                self._dense_done = 0
+            self._dense_sched.ensure(self._dense_done + 2)
+            for p in live:
+                state = self._dense_state.get(p)
+                if state is None:
+                    state = (torch.zeros_like(p.data), torch.zeros_like(p.data))
+                    self._dense_state[p] = state
+                grad = p.grad.contiguous()
+                _lib.check(lib.rlctr_dense_adam(_lib.ptr(p.data), _lib.ptr(grad), _lib.ptr(state[0]), _lib.ptr(state[1]),
+                                                p.numel(), _lib.ptr(self._dense_sched.tensor), _lib.ptr(self._dense_step),
+                                                self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
+                           "rlctr_dense_adam")
+            _lib.check(lib.rlctr_step_advance(_lib.ptr(self._dense_step), 1, st), "rlctr_step_advance")
+            self._dense_done += 1
+
+    def flush(self):
+        for owner in self._tables:
+            owner.flush()

@@ -1,0 +1,341 @@
+"""Drop-in CTR model classes over the sm_100a hot path (mirror of the reference's
+``src/models/p_model.py``: same class names, constructor signatures, ``forward(x: int64[B,F]) ->
+pctr float32[B,1]`` and ``state_dict`` keys / shapes -- SURVEY section 8b).
+
+What differs is everything underneath: parameters live in one fused-row table per model
+(:mod:`.tables`), ``forward`` is one fused gather + interaction kernel, and ``backward`` does not
+materialise a dense ``[N, D]`` gradient: it leaves ``(sorted ids, dlogit, saved sums)`` on the
+module for :class:`rl_ctr_prediction_b200.optim.Adam`, whose ``step()`` runs the
+sort / segment-reduce / fused-Adam kernel.  There is no CPU path: calling a model with host
+tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .tables import Geometry, table_struct
+from . import mlp as _mlp
+
+
+class RowsStash:
+    """What one backward pass leaves for the optimizer (struct rlctr_rowgrad + the sorted ids)."""
+    __slots__ = ("sorted_ids", "sorted_slots", "n", "dlogit", "sums", "extra", "staged", "fields", "flags")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+
+def _check_ids(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise _lib.RlctrError("rl_ctr_prediction_b200 models run on a CUDA (sm_100a) device only; "
+                              "move the features with .to(device) -- there is no CPU fallback")
+    if x.dtype != torch.int64:
+        x = x.long()
+    if x.dim() != 2:
+        raise ValueError("features must be int64 [batch, field_nums]")
+    return x.contiguous()
+
+
+def sort_ids(x: torch.Tensor, n_rows: int):
+    """(sorted_ids u32[n], sorted_slots u32[n]) of the flattened ids: rlctr_sort_ids."""
+    lib = _lib.load()
+    n = x.numel()
+    dev = x.device
+    sid = torch.empty(n, dtype=torch.int32, device=dev)
+    sslot = torch.empty(n, dtype=torch.int32, device=dev)
+    ws_bytes = lib.rlctr_sort_ws_bytes(n, n_rows)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("rlctr_sort_ids", lib.rlctr_sort_ids, _lib.ptr(x), n, n_rows, _lib.ptr(sid), _lib.ptr(sslot), _lib.ptr(ws),
+              ws_bytes, _lib.stream(), meta={"n": n})
+    return sid, sslot
+
+
+class _GatherInteract(torch.autograd.Function):
+    """ids -> fused gather + first/second order -> (out[B,1], rows[B,F*D] | empty).
+
+    ``out`` is the post-sigmoid pCTR when ``apply_sigmoid`` else the logit.  The table gradient is
+    never materialised: backward stashes it in row form on the module (returns None for it)."""
+
+    @staticmethod
+    def forward(ctx, module, ids, table, bias, want_rows, apply_sigmoid, sorted_pair):
+        lib = _lib.load()
+        g = module._geom
+        B, F = ids.shape
+        dev = ids.device
+        need_bwd = sorted_pair is not None
+        out = torch.empty(B, 1, dtype=torch.float32, device=dev)
+        logit = None if apply_sigmoid else out
+        pctr = out if apply_sigmoid else None
+        sums = None
+        rows = torch.empty(B, F * g.dim, dtype=torch.float32, device=dev) if want_rows else None
+        partners = None
+        t = table_struct(table, g)
+        if module._kind == "ffm":
+            if need_bwd:
+                partners = torch.empty(B * F, g.row_stride, dtype=torch.float32, device=dev)
+            _lib.call("rlctr_ffm_fwd", lib.rlctr_ffm_fwd, _lib.ptr(ids), C.byref(t), _lib.ptr(bias), _lib.ptr(logit),
+                      _lib.ptr(pctr), 1, _lib.ptr(partners), B, F, module.latent_dims, _lib.stream(),
+                      key="rlctr_ffm_fwd" + ("[train]" if need_bwd else "[infer]"), meta=module._meta(B, F))
+        else:
+            if need_bwd and module._kind == "fm":
+                sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
+            flags = _lib.RLCTR_FM_TERM if module._fm_term else 0
+            _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(ids), C.byref(t), _lib.ptr(bias), _lib.ptr(logit),
+                      _lib.ptr(pctr), 1, _lib.ptr(sums), _lib.ptr(rows), B, F, flags, _lib.stream(),
+                      key=f"rlctr_embed_fwd[{type(module).__name__}]",
+                      meta=dict(module._meta(B, F), sums=sums is not None, rows=want_rows))
+        ctx.module, ctx.sorted_pair, ctx.apply_sigmoid = module, sorted_pair, apply_sigmoid
+        ctx.sums, ctx.partners, ctx.shape = sums, partners, (B, F)
+        ctx.has_bias = bias is not None
+        if apply_sigmoid:
+            ctx.save_for_backward(out)
+        if rows is None:
+            rows = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(rows)
+        return out, rows
+
+    @staticmethod
+    def backward(ctx, gout, grows):
+        lib = _lib.load()
+        module = ctx.module
+        if ctx.sorted_pair is None:
+            raise _lib.RlctrError("backward through a forward that ran without gradient bookkeeping")
+        B, F = ctx.shape
+        dev = gout.device
+        gout = gout.contiguous()
+        dbias = torch.empty(1, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        ws = module._reduce_ws(dev)
+        if ctx.apply_sigmoid:
+            (p,) = ctx.saved_tensors
+            dlogit = torch.empty(B, dtype=torch.float32, device=dev)
+            _lib.check(lib.rlctr_sigmoid_bwd(_lib.ptr(gout), _lib.ptr(p), _lib.ptr(dlogit), _lib.ptr(dbias),
+                                             _lib.ptr(ws), B, _lib.stream()), "rlctr_sigmoid_bwd")
+        else:
+            dlogit = gout.reshape(B)
+            if dbias is not None:
+                _lib.check(lib.rlctr_sigmoid_bwd(None, None, _lib.ptr(dlogit), _lib.ptr(dbias), _lib.ptr(ws), B,
+                                                 _lib.stream()), "rlctr_sigmoid_bwd")
+        if module._stash is not None:
+            raise _lib.RlctrError("two backward passes without an optimizer step in between are not supported "
+                                  "(the reference loop does one: src/main/pretrain_main.py:100-102)")
+        extra = grows.contiguous() if (grows is not None and grows.numel() > 0) else None
+        sid, sslot = ctx.sorted_pair
+        module._stash = RowsStash(sorted_ids=sid, sorted_slots=sslot, n=B * F, dlogit=dlogit, sums=ctx.sums,
+                                  extra=extra, staged=ctx.partners, fields=F,
+                                  flags=_lib.RLCTR_STAGED_PARTNER if ctx.partners is not None else 0)
+        return None, None, None, dbias, None, None, None
+
+
+class _TableModel(nn.Module):
+    """Shared machinery of the drop-in classes: the fused table, reference-keyed state_dict, the
+    lazy-exact optimizer hand-shake."""
+
+    _kind = "fm"          # 'lr' | 'fm' | 'ffm'
+    _fm_term = False
+
+    def _init_table(self, geom: Geometry, columns, device=None):
+        """columns: list of (first_col, tensor[N, w]) in the reference's creation order."""
+        self._geom = geom
+        dev = torch.device(device) if device is not None else None
+        data = torch.zeros(geom.n_rows, geom.row_stride, dtype=torch.float32, device=dev)
+        for col, w in columns:
+            # nn.Embedding.reset_parameters == normal_(0, 1), drawn in the reference's creation order:
+            # with the default (CPU) construction the same torch.manual_seed gives the reference's values
+            if dev is not None and dev.type == "cuda":
+                data[:, col:col + w].normal_()
+            else:
+                data[:, col:col + w].copy_(torch.empty(geom.n_rows, w).normal_())
+        self.table = nn.Parameter(data)
+        self.table._rlctr_owner = self
+        self._opt = None
+        self._stash = None
+        self._ws = {}
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self.table._rlctr_owner = self          # .to(device) may have replaced the Parameter object
+        self._ws = {}
+        return out
+
+    def _meta(self, B, F):
+        g = self._geom
+        return {"model": type(self).__name__, "B": B, "F": F, "rs": g.row_stride, "dim": g.dim, "n_rows": g.n_rows,
+                "lin": g.lin_col >= 0}
+
+    def _reduce_ws(self, dev):
+        ws = self._ws.get("reduce")
+        if ws is None or ws.device != dev:
+            ws = torch.zeros(_lib.RLCTR_REDUCE_WS_BYTES, dtype=torch.uint8, device=dev)
+            self._ws["reduce"] = ws
+        return ws
+
+    # ---- reference-keyed state_dict -----------------------------------------------------------
+    def _ref_items(self):
+        """[(reference key, first column, width)]"""
+        raise NotImplementedError
+
+    def flush(self):
+        """Make the table equal to what the reference's dense Adam would hold right now."""
+        if self._opt is not None:
+            self._opt.flush(self.table.data)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        self.flush()
+        for name, p in self._parameters.items():
+            if name != "table" and p is not None:
+                destination[prefix + name] = p if keep_vars else p.detach()
+        tab = self.table.detach()
+        for key, col, w in self._ref_items():
+            destination[prefix + key] = tab[:, col:col + w].clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        self.flush()
+        handled = set()
+        with torch.no_grad():
+            for key, col, w in self._ref_items():
+                k = prefix + key
+                handled.add(k)
+                if k not in state_dict:
+                    missing_keys.append(k)
+                    continue
+                src = state_dict[k]
+                if tuple(src.shape) != (self._geom.n_rows, w):
+                    error_msgs.append(f"size mismatch for {k}: checkpoint {tuple(src.shape)} vs model "
+                                      f"{(self._geom.n_rows, w)}")
+                    continue
+                self.table.data[:, col:col + w].copy_(src)
+            for name, p in self._parameters.items():
+                if name == "table" or p is None:
+                    continue
+                k = prefix + name
+                handled.add(k)
+                if k not in state_dict:
+                    missing_keys.append(k)
+                elif tuple(state_dict[k].shape) != tuple(p.shape):
+                    error_msgs.append(f"size mismatch for {k}")
+                else:
+                    p.data.copy_(state_dict[k])
+        if strict:
+            for k in state_dict:
+                if k.startswith(prefix) and k not in handled:
+                    head = k[len(prefix):].split(".", 1)[0]
+                    if head not in self._modules:
+                        unexpected_keys.append(k)
+
+    # ---- forward plumbing ---------------------------------------------------------------------
+    def _run(self, x, want_rows, apply_sigmoid):
+        x = _check_ids(x)
+        if x.shape[1] != getattr(self, "field_nums", x.shape[1]):
+            raise ValueError(f"expected {self.field_nums} fields, got {x.shape[1]}")
+        track = torch.is_grad_enabled() and self.table.requires_grad
+        sorted_pair = None
+        if track:
+            sorted_pair = sort_ids(x, self._geom.n_rows)
+            opt = self._opt
+            if opt is not None and opt.stamp is not None and opt.dirty:
+                lib = _lib.load()
+                t, a = table_struct(self.table.data, self._geom), opt.struct()
+                _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sorted_pair[0]), x.numel(), C.byref(t),
+                          C.byref(a), _lib.stream(), key=f"rlctr_rows_catchup[{type(self).__name__}]",
+                          meta=self._meta(*x.shape))
+        else:
+            self.flush()
+        bias = getattr(self, "bias", None)
+        return _GatherInteract.apply(self, x, self.table, bias, want_rows, apply_sigmoid, sorted_pair)
+
+    def zero_grad(self, set_to_none: bool = True):
+        self._stash = None
+        return super().zero_grad(set_to_none)
+
+
+class LR(_TableModel):
+    """p_model.py:9-26  sigma(bias + sum_f w[x_f])."""
+    _kind = "lr"
+
+    def __init__(self, feature_nums, output_dim=1, device=None):
+        super().__init__()
+        assert output_dim == 1
+        self.feature_nums = feature_nums
+        self._init_table(Geometry.lr(feature_nums), [(0, 1)], device)
+        self.bias = nn.Parameter(torch.zeros((output_dim,), device=device))
+
+    def _ref_items(self):
+        return [("linear.weight", 0, 1)]
+
+    def forward(self, x):
+        return self._run(x, False, True)[0]
+
+
+class FM(_TableModel):
+    """p_model.py:28-57  sigma(bias + sum_f w[x_f] + 0.5 sum_d[(sum_f v)^2 - sum_f v^2])."""
+    _kind = "fm"
+    _fm_term = True
+
+    def __init__(self, feature_nums, latent_dims, output_dim=1, device=None):
+        super().__init__()
+        assert output_dim == 1
+        self.feature_nums, self.latent_dims = feature_nums, int(latent_dims)
+        g = Geometry.fm(feature_nums, self.latent_dims)
+        self._init_table(g, [(g.lin_col, 1), (g.emb_col, g.dim)], device)
+        self.bias = nn.Parameter(torch.zeros((output_dim,), device=device))
+
+    def _ref_items(self):
+        g = self._geom
+        return [("linear.weight", g.lin_col, 1), ("feature_embedding.weight", g.emb_col, g.dim)]
+
+    def forward(self, x):
+        return self._run(x, False, True)[0]
+
+
+class FFM(_TableModel):
+    """p_model.py:59-100  sigma(bias + sum_f w[x_f] + sum_{i<j} <T_j[x_i], T_i[x_j]>)."""
+    _kind = "ffm"
+
+    def __init__(self, feature_nums, field_nums, latent_dims, output_dim=1, device=None):
+        super().__init__()
+        assert output_dim == 1
+        self.feature_nums, self.field_nums, self.latent_dims = feature_nums, int(field_nums), int(latent_dims)
+        g = Geometry.ffm(feature_nums, self.field_nums, self.latent_dims)
+        cols = [(g.lin_col, 1)] + [(g.emb_col + t * self.latent_dims, self.latent_dims) for t in range(self.field_nums)]
+        self._init_table(g, cols, device)
+        self.bias = nn.Parameter(torch.zeros((output_dim,), device=device))
+
+    def _ref_items(self):
+        g, D = self._geom, self.latent_dims
+        return [("linear.weight", g.lin_col, 1)] + \
+               [(f"field_feature_embeddings.{t}.weight", g.emb_col + t * D, D) for t in range(self.field_nums)]
+
+    def forward(self, x):
+        return self._run(x, False, True)[0]
+
+
+def _tower(in_dims: int, device=None) -> nn.Sequential:
+    """[in -> 300 -> 200 -> 1], ReLU + Dropout(0.2) after each hidden layer (p_model.py:276-293); Linear
+    layers sit at Sequential indices 0, 3, 6 as in the reference's state_dict.  The Linear layers are
+    :class:`rl_ctr_prediction_b200.mlp.Linear` (tcgen05 3xTF32 GEMM kernels, same parameters)."""
+    mods, d = [], in_dims
+    for width in (300, 200):
+        mods += [_mlp.Linear(d, width, device=device), nn.ReLU(), nn.Dropout(p=0.2)]
+        d = width
+    mods.append(_mlp.Linear(d, 1, device=device))
+    return nn.Sequential(*mods)
+
+
+class DeepFM(FM):
+    """p_model.py:256-324  FM logit + MLP(concat_f v_f).  One gather feeds both terms (the reference
+    gathers the table twice, :303 and :320)."""
+
+    def __init__(self, feature_nums, field_nums, latent_dims, output_dim=1, device=None):
+        super().__init__(feature_nums, latent_dims, output_dim, device)
+        self.field_nums = int(field_nums)
+        self.mlp = _tower(self.field_nums * self.latent_dims, device)
+
+    def forward(self, x):
+        z_fm, rows = self._run(x, True, False)
+        return torch.sigmoid(z_fm + self.mlp(rows))

@@ -1,0 +1,285 @@
+"""CTR pre-training loop API -- drop-in for the reference's ``src/main/pretrain_main.py``.
+
+Same function names, argument meaning and return values (``setup_seed``, ``get_model``,
+``get_dataset``, ``train``, ``test``, ``submission``, ``eva_stopping``, ``main``), so a script written
+against the reference works after changing its import.  What changes:
+
+* ``get_model`` builds the :mod:`.p_model` classes (fused-row tables + sm_100a kernels);
+* ``main`` builds :class:`rl_ctr_prediction_b200.optim.Adam` where the reference builds
+  ``torch.optim.Adam`` (:181) -- same arguments, fresh state every epoch like the reference;
+* batches are sliced from one pinned int64 tensor (as ``src/all_main/pretrain_main_2.py:61,71-72``
+  does) instead of 8 DataLoader worker processes;
+* ``fused_train_step`` is the same step with the loss head inside the library (no per-op ATen
+  launches); ``train(..., fused=True)`` uses it.
+
+The reference's own ``train`` / ``test`` (which take the optimizer as an argument) also drive these
+models unchanged; ``tests/test_gpu_loop.py`` checks exactly that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime
+import os
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import optim as _optim
+from . import p_model as Model
+from .tables import table_struct
+
+
+def setup_seed(seed):
+    """pretrain_main.py:17-22."""
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    torch.backends.cudnn.deterministic = True
+
+
+_MODELS = {
+    "LR": lambda n, f, d: Model.LR(n),
+    "FM": lambda n, f, d: Model.FM(n, d),
+    "FFM": lambda n, f, d: Model.FFM(n, f, d),
+    "DeepFM": lambda n, f, d: Model.DeepFM(n, f, d),
+}
+
+
+def get_model(model_name, feature_nums, field_nums, latent_dims):
+    """pretrain_main.py:25-45 (name -> class).  Names outside the hot-path scope raise instead of
+    returning None as the reference silently does."""
+    try:
+        return _MODELS[model_name](int(feature_nums), int(field_nums), int(latent_dims))
+    except KeyError:
+        raise NotImplementedError(f"model {model_name!r} is outside this build's scope "
+                                  f"(available: {sorted(_MODELS)})") from None
+
+
+def get_dataset(datapath, dataset_name, campaign_id, valid_day, test_day):
+    """pretrain_main.py:47-88: ``train.txt`` rows ``click,id_0..id_{F-1}`` (src/encode/data_.py:85) and
+    ``day_index.csv`` rows ``day,first_row,last_row``; train = every day but valid/test."""
+    data_path = datapath + dataset_name + campaign_id
+    train_fm = np.loadtxt(data_path + "train.txt", delimiter=",", dtype=np.int64, ndmin=2)
+    field_nums = train_fm.shape[1] - 1
+    feature_nums = int(train_fm[:, 1:].max()) + 1
+    day_indexs = np.loadtxt(data_path + "day_index.csv", delimiter=",", dtype=np.int64, ndmin=2)
+
+    def rows_of(day):
+        rec = day_indexs[day_indexs[:, 0] == day][0]
+        return train_fm[rec[1]: rec[2] + 1]
+
+    train_days = [d for d in day_indexs[:, 0].tolist() if d not in (valid_day, test_day)]
+    train_data = np.concatenate([rows_of(d) for d in train_days], axis=0) if train_days else train_fm[:0]
+    return train_fm, day_indexs, train_data, rows_of(valid_day), rows_of(test_day), field_nums, feature_nums
+
+
+class BatchSlices:
+    """Iterable of ``(features int64[b,F], labels int64[b])`` batches cut from one pinned tensor
+    (the last batch is partial, like a DataLoader without ``drop_last``)."""
+
+    def __init__(self, data: np.ndarray, batch_size: int):
+        t = torch.from_numpy(np.ascontiguousarray(data.astype(np.int64)))
+        self.data = t.pin_memory() if torch.cuda.is_available() else t
+        self.batch_size = int(batch_size)
+
+    def __len__(self):
+        return (len(self.data) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for s in range(0, len(self.data), self.batch_size):
+            chunk = self.data[s: s + self.batch_size]
+            yield chunk[:, 1:], chunk[:, 0]
+
+
+def fused_train_step(model, optimizer, features, labels):
+    """One training step of pretrain_main.py:96-102 with the loss head inside the library:
+    sort -> catch-up -> gather+interaction -> sigmoid+BCE (+ their autograd) -> segment-reduce+Adam.
+    Numerically the same step as ``loss(model(x), y); zero_grad(); backward(); optimizer.step()`` with
+    ``nn.BCELoss``.  LR / FM / FFM (models without a dense tower).  Returns the loss (device scalar)."""
+    if isinstance(model, Model.DeepFM):
+        raise NotImplementedError("fused_train_step covers the tower-less models; DeepFM goes through autograd")
+    lib = _lib.load()
+    x = Model._check_ids(features)
+    B, F = x.shape
+    dev = x.device
+    g = model._geom
+    st = _lib.stream()
+    y = labels.reshape(-1).contiguous()
+    sid, sslot = Model.sort_ids(x, g.n_rows)
+    opt = model._opt
+    t = table_struct(model.table.data, g)
+    if opt is not None and opt.stamp is not None and opt.dirty:
+        a = opt.struct()
+        _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sid), x.numel(), C.byref(t), C.byref(a), st,
+                  key=f"rlctr_rows_catchup[{type(model).__name__}]", meta=model._meta(B, F))
+    logit = torch.empty(B, dtype=torch.float32, device=dev)
+    sums = partners = None
+    if model._kind == "ffm":
+        partners = torch.empty(B * F, g.row_stride, dtype=torch.float32, device=dev)
+        _lib.call("rlctr_ffm_fwd", lib.rlctr_ffm_fwd, _lib.ptr(x), C.byref(t), _lib.ptr(model.bias.data), _lib.ptr(logit),
+                  None, 1, _lib.ptr(partners), B, F, model.latent_dims, st, key="rlctr_ffm_fwd[train]",
+                  meta=model._meta(B, F))
+    else:
+        if model._kind == "fm":
+            sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
+        _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(x), C.byref(t), _lib.ptr(model.bias.data),
+                  _lib.ptr(logit), None, 1, _lib.ptr(sums), None, B, F, _lib.RLCTR_FM_TERM if model._fm_term else 0, st,
+                  key=f"rlctr_embed_fwd[{type(model).__name__}]", meta=dict(model._meta(B, F), sums=sums is not None, rows=False))
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dlogit = torch.empty(B, dtype=torch.float32, device=dev)
+    dbias = torch.empty(1, dtype=torch.float32, device=dev)
+    yi = y if y.dtype == torch.int64 else None
+    yf = None if yi is not None else y.float()
+    _lib.check(lib.rlctr_bce_fwd_bwd(_lib.ptr(logit), _lib.ptr(yi), _lib.ptr(yf), None, _lib.ptr(loss), _lib.ptr(dlogit),
+                                     _lib.ptr(dbias), _lib.ptr(model._reduce_ws(dev)), B, st), "rlctr_bce_fwd_bwd")
+    model._stash = Model.RowsStash(sorted_ids=sid, sorted_slots=sslot, n=B * F, dlogit=dlogit, sums=sums, extra=None,
+                                   staged=partners, fields=F,
+                                   flags=_lib.RLCTR_STAGED_PARTNER if partners is not None else 0)
+    model.bias.grad = dbias
+    optimizer.step()
+    return loss.reshape(())
+
+
+def train(model, optimizer, data_loader, loss, device, fused=False):
+    """pretrain_main.py:91-107: returns the mean of the per-batch losses."""
+    model.train()
+    total_loss, intervals = 0.0, 0
+    for features, labels in data_loader:
+        features = features.long().to(device, non_blocking=True)
+        labels = torch.unsqueeze(labels, 1).to(device, non_blocking=True)
+        if fused and not isinstance(model, Model.DeepFM):
+            train_loss = fused_train_step(model, optimizer, features, labels)
+        else:
+            y = model(features)
+            train_loss = loss(y, labels.float())
+            model.zero_grad()
+            train_loss.backward()
+            optimizer.step()
+        total_loss += train_loss.item()
+        intervals += 1
+    return total_loss / intervals
+
+
+def _predict_all(model, data_loader, loss, device):
+    model.eval()
+    targets, predicts, losses = [], [], []
+    with torch.no_grad():
+        for features, labels in data_loader:
+            features = features.long().to(device, non_blocking=True)
+            labels = torch.unsqueeze(labels, 1).to(device, non_blocking=True)
+            y = model(features)
+            if loss is not None:
+                losses.append(loss(y, labels.float()))
+            targets.append(labels)
+            predicts.append(y)
+    targets = torch.cat(targets).cpu().numpy()
+    predicts = torch.cat(predicts).cpu().numpy()
+    return targets, predicts, [l.item() for l in losses]
+
+
+def test(model, data_loader, loss, device):
+    """pretrain_main.py:110-126: (AUC via sklearn, mean per-batch loss)."""
+    from sklearn.metrics import roc_auc_score
+    targets, predicts, losses = _predict_all(model, data_loader, loss, device)
+    return roc_auc_score(targets, predicts), sum(losses) / len(losses)
+
+
+def submission(model, data_loader, device):
+    """pretrain_main.py:128-139: (list of [pctr], AUC)."""
+    from sklearn.metrics import roc_auc_score
+    targets, predicts, _ = _predict_all(model, data_loader, None, device)
+    return predicts.tolist(), roc_auc_score(targets, predicts)
+
+
+def eva_stopping(valid_aucs, valid_losses, type):
+    """pretrain_main.py:239-251: stop after five strictly worsening epochs."""
+    series, worse = (valid_aucs, lambda a, b: a < b) if type == "auc" else (valid_losses, lambda a, b: a > b)
+    if len(series) < 5:
+        return False
+    return all(worse(series[-k], series[-k - 1]) for k in range(1, 5))
+
+
+def main(data_path, dataset_name, campaign_id, valid_day, test_day, latent_dims, model_name, epoch, learning_rate,
+         weight_decay, early_stop_type, batch_size, device, save_param_dir, optimizer_mode="lazy", fused=False):
+    """pretrain_main.py:142-236.  Rolling window of 5 checkpoints, early stop, best -> ``<name>best.pth``,
+    prediction CSVs -- with the reference's state_dict keys, so checkpoints are interchangeable."""
+    os.makedirs(save_param_dir + campaign_id, exist_ok=True)
+    device = torch.device(device)
+    latent_dims = int(latent_dims)             # the reference's argparse leaves it a string
+    _, _, train_data, valid_data, test_data, field_nums, feature_nums = get_dataset(
+        data_path, dataset_name, campaign_id, valid_day, test_day)
+    loaders = [BatchSlices(d, batch_size) for d in (train_data, valid_data, test_data)]
+    model = get_model(model_name, feature_nums, field_nums, latent_dims).to(device)
+    loss = nn.BCELoss()
+    valid_aucs, valid_losses, early_stop_index, is_early_stop = [], [], 0, False
+    ckpt = lambda tag: save_param_dir + campaign_id + model_name + str(tag) + ".pth"
+    start = datetime.datetime.now()
+    for epoch_i in range(epoch):
+        t0 = datetime.datetime.now()
+        learning_rate += 1e-4                                               # :180
+        optimizer = _optim.Adam(params=model.parameters(), lr=learning_rate, weight_decay=weight_decay,
+                                mode=optimizer_mode)                       # :181, fresh state per epoch
+        train_average_loss = train(model, optimizer, loaders[0], loss, device, fused=fused)
+        torch.save(model.state_dict(), ckpt(epoch_i % 5))
+        auc, valid_loss = test(model, loaders[1], loss, device)
+        valid_aucs.append(auc)
+        valid_losses.append(valid_loss)
+        print("epoch:", epoch_i, "training average loss:", train_average_loss, "validation auc:", auc,
+              "validation loss:", valid_loss, "[{}s]".format((datetime.datetime.now() - t0).seconds))
+        if eva_stopping(valid_aucs, valid_losses, early_stop_type):
+            early_stop_index, is_early_stop = (epoch_i - 4) % 5, True
+            break
+    if is_early_stop:
+        test_model = get_model(model_name, feature_nums, field_nums, latent_dims).to(device)
+        test_model.load_state_dict(torch.load(ckpt(early_stop_index), map_location=device))
+    else:
+        test_model = model
+    auc, test_loss = test(test_model, loaders[2], loss, device)
+    torch.save(test_model.state_dict(), ckpt("best"))
+    print("\ntest auc:", auc, datetime.datetime.now(), "[{}s]".format((datetime.datetime.now() - start).seconds))
+    submission_path = data_path + dataset_name + campaign_id + model_name + "/"
+    os.makedirs(submission_path, exist_ok=True)
+    day_aucs = []
+    for day, loader in ((valid_day, loaders[1]), (test_day, loaders[2])):
+        predicts, day_auc = submission(test_model, loader, device)
+        np.savetxt(submission_path + str(day) + "_test_submission.csv",
+                   np.column_stack([np.arange(len(predicts)), np.asarray(predicts).reshape(-1)]),
+                   delimiter=",", fmt=["%d", "%.9g"])
+        day_aucs.append([day, day_auc])
+    np.savetxt(submission_path + "day_aucs.csv", np.column_stack([np.arange(2), np.asarray(day_aucs)]), delimiter=",",
+               fmt=["%d", "%d", "%.17g"])
+    for i in range(5):
+        if os.path.exists(ckpt(i)):
+            os.remove(ckpt(i))
+    return auc, test_loss
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--data_path", default="../../data/")
+    ap.add_argument("--dataset_name", default="ipinyou/", help="ipinyou, cretio, yoyi")
+    ap.add_argument("--valid_day", default=11, type=int)
+    ap.add_argument("--test_day", default=12, type=int)
+    ap.add_argument("--campaign_id", default="1458/", help="1458, 3386")
+    ap.add_argument("--model_name", default="FM", help="LR, FM, FFM, DeepFM")
+    ap.add_argument("--latent_dims", default=8, type=int)
+    ap.add_argument("--epoch", type=int, default=100)
+    ap.add_argument("--learning_rate", type=float, default=1e-3)
+    ap.add_argument("--weight_decay", type=float, default=1e-5)
+    ap.add_argument("--early_stop_type", default="loss", help="auc, loss")
+    ap.add_argument("--batch_size", type=int, default=4096)
+    ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--save_param_dir", default="../models/model_params/")
+    ap.add_argument("--optimizer_mode", default="lazy", choices=["lazy", "dense", "sparse"])
+    ap.add_argument("--fused", action="store_true")
+    a = ap.parse_args()
+    setup_seed(1)
+    main(a.data_path, a.dataset_name, a.campaign_id, a.valid_day, a.test_day, a.latent_dims, a.model_name, a.epoch,
+         a.learning_rate, a.weight_decay, a.early_stop_type, a.batch_size, a.device, a.save_param_dir,
+         a.optimizer_mode, a.fused)

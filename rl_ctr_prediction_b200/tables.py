@@ -1,0 +1,115 @@
+"""Fused-row embedding tables: the HBM layout behind the drop-in model classes.
+
+The reference keeps a first-order ``nn.Embedding(N, 1)`` and a latent ``nn.Embedding(N, D)`` (FFM:
+F of them) and gathers each separately (src/models/p_model.py:14,34,38,69,76-78,263,267).  Here
+one id owns ONE 16-byte aligned row (include/rlctr.h "fused row"):
+
+    LR      [w]                                   row_stride 1
+    FM      [w, v_0 .. v_{D-1}, pad]              row_stride = round4(1 + D)
+    FFM     [T_0 | T_1 | .. | T_{F-1} | w | pad]  row_stride = round4(F*D + 1)
+
+so a field costs one aligned 128-bit-chunked read instead of two (or F+1) sector-straddling ones.
+``state_dict()`` / ``load_state_dict()`` convert to and from the reference's keys and shapes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+def round4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+@dataclass(frozen=True)
+class Geometry:
+    n_rows: int
+    row_stride: int
+    lin_col: int
+    emb_col: int
+    dim: int
+
+    @staticmethod
+    def lr(n):
+        return Geometry(n, 1, 0, 0, 0)
+
+    @staticmethod
+    def fm(n, d, with_linear=True):
+        if with_linear:
+            return Geometry(n, round4(1 + d), 0, 1, d)
+        return Geometry(n, round4(d), -1, 0, d)
+
+    @staticmethod
+    def ffm(n, f, d):
+        return Geometry(n, round4(f * d + 1), f * d, 0, f * d)
+
+
+def table_struct(data: torch.Tensor, g: Geometry) -> _lib.Table:
+    return _lib.Table(_lib.ptr(data), g.n_rows, g.row_stride, g.lin_col, g.emb_col, g.dim)
+
+
+class AdamSchedule:
+    """The two Python-double scalars torch.optim.Adam derives per step (torch/optim/adam.py
+    ``_single_tensor_adam``): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t), tabulated
+    for t = 0..len-1 and kept on the device so the step index can be a device scalar."""
+
+    def __init__(self, lr, betas, device, length=8192):
+        self.lr, self.betas, self.device = float(lr), (float(betas[0]), float(betas[1])), device
+        self.length = 0
+        self.tensor = None
+        self.ensure(length)
+
+    def ensure(self, steps: int):
+        if steps < self.length:
+            return False
+        n = max(steps + 1, 2 * self.length, 1024)
+        b1, b2 = self.betas
+        rows = [(0.0, 1.0)]
+        for t in range(1, n):
+            rows.append((self.lr / (1 - b1 ** t), (1 - b2 ** t) ** 0.5))
+        self.tensor = torch.tensor(rows, dtype=torch.float64).to(torch.float32).to(self.device).contiguous()
+        self.length = n
+        return True
+
+
+class TableAdamState:
+    """exp_avg / exp_avg_sq / per-row stamp for one fused table, plus the lazy-exact bookkeeping.
+
+    mode 'lazy'   (default): rows are brought up to date when touched (rlctr_rows_catchup) and by
+                  ``flush()`` before anything reads the whole table -- same numbers as the reference's
+                  dense Adam with O(touched rows) HBM traffic per step.
+    mode 'dense'  : every step also streams the whole table (the literal reference work).
+    mode 'sparse' : untouched rows are left alone (numerically NOT the reference; SURVEY H1 mode C).
+    """
+
+    def __init__(self, param: torch.Tensor, geom: Geometry, lr, betas, eps, weight_decay, mode):
+        assert mode in ("lazy", "dense", "sparse")
+        self.geom, self.mode = geom, mode
+        dev = param.device
+        self.exp_avg = torch.zeros_like(param)
+        self.exp_avg_sq = torch.zeros_like(param)
+        self.stamp = None if mode == "sparse" else torch.zeros(geom.n_rows, dtype=torch.int32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)     # completed steps (device scalar)
+        self.host_step = 0
+        self.sched = AdamSchedule(lr, betas, dev)
+        self.betas, self.eps, self.weight_decay = betas, float(eps), float(weight_decay)
+        self.dirty = False           # True while some rows lag behind `step` (lazy mode)
+
+    def struct(self) -> _lib.Adam:
+        return _lib.Adam(_lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.stamp),
+                         _lib.ptr(self.sched.tensor), _lib.ptr(self.step), self.sched.length,
+                         self.betas[0], self.betas[1], self.eps, self.weight_decay)
+
+    def flush(self, data: torch.Tensor):
+        """Replay the L2-only steps every row missed (rlctr_adam_flush)."""
+        if self.stamp is None or not self.dirty:
+            return
+        lib = _lib.load()
+        t, a = table_struct(data, self.geom), self.struct()
+        _lib.call("rlctr_adam_flush", lib.rlctr_adam_flush, C.byref(t), C.byref(a), 0, self.geom.n_rows, _lib.stream(),
+                  meta={"rs": self.geom.row_stride, "n_rows": self.geom.n_rows})
+        self.dirty = False

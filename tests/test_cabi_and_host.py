@@ -1,0 +1,123 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/rlctr.h
+declares, ctypes struct layouts match the header, and the host logic (fused-row layout, reference-keyed
+state_dict, Adam schedule, init RNG order) behaves like the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from oracle import torch_port as TP
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rl_ctr_prediction_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "rlctr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rlctr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from rl_ctr_prediction_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/rlctr.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+    assert lib.rlctr_version() == 100
+    assert lib.rlctr_strerror(-1) == b"invalid argument"
+
+
+def test_struct_layouts_match_header():
+    from rl_ctr_prediction_b200 import _lib
+    assert C.sizeof(_lib.Table) == 32           # ptr, i64, 4 x i32
+    assert C.sizeof(_lib.Adam) == 64            # 5 ptr, i32, 4 x f32 (+pad)
+    assert C.sizeof(_lib.RowGrad) == 40         # 4 ptr, 2 x i32
+    assert _lib.Table.row_stride.offset == 16 and _lib.Adam.sched_len.offset == 40
+
+
+def test_argument_errors_need_no_gpu(lib):
+    # argument validation happens before any CUDA call
+    assert lib.rlctr_embed_fwd(None, None, None, None, None, 1, None, None, 4, 15, 1, None) == -1
+    assert lib.rlctr_generate_preds(None, None, None, None, None, None, None, 4, 3, 0, None) == -1
+    assert lib.rlctr_sort_ids(None, 1, 1, None, None, None, 0, None) == -1
+    assert lib.rlctr_rows_ws_bytes(1000) >= 16
+
+
+@pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
+def test_state_dict_is_reference_keyed_and_init_matches_seed(name):
+    """Same torch.manual_seed => same initial parameters as the reference-ordered constructors, and
+    state_dict()/load_state_dict() speak the reference's keys and shapes."""
+    from rl_ctr_prediction_b200 import pretrain_main as PM
+    N, F, D = 50, 15, 10
+    torch.manual_seed(1)
+    port = TP.PortCTR(name, N, F, D)
+    torch.manual_seed(1)
+    m = PM.get_model(name, N, F, D)
+    sd, ref = m.state_dict(), port.state_dict()
+    assert set(sd.keys()) == set(ref.keys())
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+        assert torch.equal(sd[k], ref[k]), k
+    # load a perturbed checkpoint back
+    ref2 = {k: v + 1 for k, v in ref.items()}
+    m.load_state_dict(ref2)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref2[k])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({k: v for k, v in ref2.items() if k != "linear.weight"})
+    # pad columns stay zero
+    g = m._geom
+    used = torch.zeros(g.row_stride, dtype=torch.bool)
+    if g.lin_col >= 0:
+        used[g.lin_col] = True
+    used[g.emb_col:g.emb_col + g.dim] = True
+    assert torch.all(m.table.data[:, ~used] == 0)
+
+
+def test_feature_embedding_host_surface():
+    from rl_ctr_prediction_b200.Feature_embedding import Feature_Embedding
+    torch.manual_seed(1)
+    port = TP.PortFeatureEmbedding(40, 15, 10)
+    torch.manual_seed(1)
+    fe = Feature_Embedding(40, 15, 10)
+    assert torch.equal(fe.state_dict()["feature_embedding.weight"], port.state_dict()["feature_embedding.weight"])
+    assert fe.output_dims == 255 and fe.row[:3] == [0, 0, 0] and fe.col[:3] == [1, 2, 3]
+    fe.load_embedding({"feature_embedding.weight": torch.ones(40, 10)})
+    assert torch.all(fe.table.data[:, :10] == 1) and torch.all(fe.table.data[:, 10:] == 0)
+
+
+def test_adam_schedule_matches_torch_scalars():
+    from rl_ctr_prediction_b200.tables import AdamSchedule
+    s = AdamSchedule(1e-3, (0.9, 0.999), torch.device("cpu"), 16)
+    for t in (1, 2, 10, 1500):
+        s.ensure(t)
+        ss, bc = O.adam_schedule(t, 1e-3)
+        assert s.tensor[t, 0].item() == np.float32(ss) and s.tensor[t, 1].item() == np.float32(bc)
+
+
+def test_models_refuse_cpu_inputs():
+    from rl_ctr_prediction_b200 import _lib, p_model
+    m = p_model.FM(20, 4)
+    with pytest.raises(_lib.RlctrError):
+        m(torch.zeros(3, 15, dtype=torch.long))
+
+
+def test_eva_stopping_and_get_model():
+    from rl_ctr_prediction_b200 import pretrain_main as PM
+    assert PM.eva_stopping([5, 4, 3, 2, 1], [], "auc") and not PM.eva_stopping([5, 4, 3, 3, 1], [], "auc")
+    assert PM.eva_stopping([], [1, 2, 3, 4, 5], "loss") and not PM.eva_stopping([], [1, 2, 3, 4], "loss")
+    with pytest.raises(NotImplementedError):
+        PM.get_model("nope", 10, 15, 4)

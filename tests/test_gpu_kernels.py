@@ -1,0 +1,533 @@
+"""Parity of every C-ABI entry point (include/rlctr.h) against the CPU oracle and the golden vectors
+produced by the real reference modules.  Calls go through ctypes into librlctr_sm100a.so.
+
+Bars (BASELINE.json north_star): gathered rows bit-exact; logits, loss, gradients, Adam state and
+policy log-probs within 1e-5 relative in fp32 (RTOL below; ATOL covers values near zero).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_from_golden
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rl_ctr_prediction_b200 import _lib
+    return _lib.load()
+
+
+def L():
+    from rl_ctr_prediction_b200 import _lib
+    return _lib
+
+
+def T():
+    from rl_ctr_prediction_b200 import tables
+    return tables
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a.astype(np.float64), b.astype(np.float64), rtol=rtol, atol=atol)
+
+
+def fused_fm_table(lin, emb):
+    """[N, round4(1+D)] = [w | v | pad]"""
+    N, D = emb.shape
+    g = T().Geometry.fm(N, D)
+    tab = torch.zeros(N, g.row_stride)
+    tab[:, 0:1] = torch.as_tensor(lin).reshape(N, 1)
+    tab[:, 1:1 + D] = torch.as_tensor(emb)
+    return tab.to(DEV), g
+
+
+def fused_ffm_table(lin, tables):
+    Fn, N, D = tables.shape
+    g = T().Geometry.ffm(N, Fn, D)
+    tab = torch.zeros(N, g.row_stride)
+    for t in range(Fn):
+        tab[:, t * D:(t + 1) * D] = torch.as_tensor(tables[t])
+    tab[:, g.lin_col] = torch.as_tensor(lin).reshape(N)
+    return tab.to(DEV), g
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV).contiguous()
+
+
+def st():
+    return L().stream()
+
+
+def rng_case(seed, B, F, N, D, zipf=True, scale=0.3):
+    rng = np.random.default_rng(seed)
+    if zipf:
+        per = max(N // F, 1)
+        ids = np.stack([np.minimum(rng.zipf(1.3, size=B) - 1, per - 1) + f * per for f in range(F)], axis=1)
+        ids = np.minimum(ids, N - 1)
+    else:
+        ids = rng.integers(0, N, size=(B, F))
+    emb = (rng.standard_normal((N, D)) * scale).astype(np.float32)
+    lin = (rng.standard_normal((N, 1)) * scale).astype(np.float32)
+    bias = np.array([0.1], dtype=np.float32)
+    y = (rng.random(B) < 0.3).astype(np.int64)
+    return ids.astype(np.int64), emb, lin, bias, y
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 forward
+# ------------------------------------------------------------------------------------------------
+def run_embed_fwd(lib, ids, tab, g, bias, fm=True, want_rows=True, want_sums=True):
+    B, F = ids.shape
+    ids_d = dev(ids)
+    logit = torch.empty(B, device=DEV)
+    pctr = torch.empty(B, device=DEV)
+    sums = torch.empty(B, g.row_stride, device=DEV) if want_sums else None
+    rows = torch.empty(B, F * g.dim, device=DEV) if want_rows else None
+    t = T().table_struct(tab, g)
+    rc = lib.rlctr_embed_fwd(L().ptr(ids_d), C.byref(t), L().ptr(dev(bias)), L().ptr(logit), L().ptr(pctr), 1,
+                             L().ptr(sums), L().ptr(rows), B, F, 1 if fm else 0, st())
+    assert rc == 0, L().load().rlctr_strerror(rc)
+    torch.cuda.synchronize()
+    return logit, pctr, sums, rows
+
+
+@pytest.mark.parametrize("D", [10, 8, 16, 4, 2])
+@pytest.mark.parametrize("B,F", [(1, 15), (37, 15), (1000, 15), (64, 3), (50, 33)])
+def test_embed_fwd_fm(lib, B, F, D):
+    ids, emb, lin, bias, _ = rng_case(B * 131 + D, B, F, 997, D)
+    tab, g = fused_fm_table(lin, emb)
+    logit, pctr, sums, rows = run_embed_fwd(lib, ids, tab, g, bias)
+    # gathered rows: bit-exact
+    assert np.array_equal(rows.cpu().numpy().reshape(B, F, D), emb[ids])
+    close(logit, O.fm_logit(ids, emb, lin, bias).reshape(-1))
+    close(logit, O.fm_logit(ids, emb, lin, bias, np.float64).reshape(-1))
+    close(pctr, O.sigmoid(O.fm_logit(ids, emb, lin, bias)).reshape(-1))
+    close(sums[:, 1:1 + D], emb[ids].sum(axis=1))
+
+
+def test_embed_fwd_golden_kat(lib, golden):
+    x = golden["kat/x"]
+    sd = state_from_golden(golden, "kat/FM/init")
+    tab, g = fused_fm_table(sd["linear.weight"], sd["feature_embedding.weight"])
+    _, pctr, _, _ = run_embed_fwd(lib, x, tab, g, sd["bias"])
+    close(pctr, golden["kat/FM/pctr"].reshape(-1))
+    # LR on the fused table (no FM term) and on the scalar table
+    sd = state_from_golden(golden, "kat/LR/init")
+    tab, g = fused_fm_table(sd["linear.weight"], np.zeros((64, 10), np.float32))
+    _, pctr, _, _ = run_embed_fwd(lib, x, tab, g, sd["bias"], fm=False)
+    close(pctr, golden["kat/LR/pctr"].reshape(-1))
+    g1 = T().Geometry.lr(64)
+    tab1 = dev(sd["linear.weight"].reshape(-1))
+    _, pctr, _, _ = run_embed_fwd(lib, x, tab1, g1, sd["bias"], fm=False, want_rows=False, want_sums=False)
+    close(pctr, golden["kat/LR/pctr"].reshape(-1))
+
+
+def test_embed_fwd_hand_kat(lib):
+    # F=2, D=2, v1=(1,2), v2=(3,4): 0.5*sum_d[(sum v)^2 - sum v^2] = 11
+    emb = np.array([[1, 2], [3, 4]], np.float32)
+    lin = np.zeros((2, 1), np.float32)
+    tab, g = fused_fm_table(lin, emb)
+    logit, _, _, _ = run_embed_fwd(lib, np.array([[0, 1]]), tab, g, np.zeros(1, np.float32))
+    assert logit.item() == 11.0
+
+
+def test_embed_fwd_saturation_and_oob(lib):
+    # default N(0,1) init saturates fp32 sigmoid to exactly 0/1; out-of-range id = zero row
+    ids, emb, lin, bias, _ = rng_case(5, 256, 15, 500, 10, scale=1.0)
+    tab, g = fused_fm_table(lin, emb)
+    _, pctr, _, _ = run_embed_fwd(lib, ids, tab, g, bias)
+    ref = O.sigmoid(O.fm_logit(ids, emb, lin, bias)).reshape(-1)
+    close(pctr, ref)
+    p = pctr.cpu().numpy()
+    assert ((p == 0) | (p == 1)).sum() == ((ref == 0) | (ref == 1)).sum() > 0
+    ids2 = ids.copy()
+    ids2[:, 3] = 10 ** 9
+    emb0 = np.vstack([emb, np.zeros((1, 10), np.float32)])
+    lin0 = np.vstack([lin, np.zeros((1, 1), np.float32)])
+    ids_ref = ids2.copy()
+    ids_ref[:, 3] = 500
+    logit, _, _, _ = run_embed_fwd(lib, ids2, tab, g, bias)
+    close(logit, O.fm_logit(ids_ref, emb0, lin0, bias).reshape(-1))
+
+
+def test_embed_fwd_empty_and_errors(lib):
+    ids, emb, lin, bias, _ = rng_case(1, 4, 15, 100, 10)
+    tab, g = fused_fm_table(lin, emb)
+    t = T().table_struct(tab, g)
+    assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(t), None, None, None, 1, None, None, 0, 15, 1, st()) == 0
+    assert lib.rlctr_embed_fwd(None, C.byref(t), None, None, None, 1, None, None, 4, 15, 1, st()) == -1
+    bad = L().Table(L().ptr(tab), 100, 10, 0, 1, 9)          # stride not a multiple of 4
+    assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(bad), None, None, None, 1, None, None, 4, 15, 1, st()) == -2
+
+
+def test_gather_rows_bit_exact(lib):
+    ids, emb, lin, _, _ = rng_case(9, 5000, 15, 30000, 10, zipf=False)
+    tab, g = fused_fm_table(lin, emb)
+    flat = dev(ids.reshape(-1))
+    out = torch.empty(flat.numel(), g.row_stride, device=DEV)
+    t = T().table_struct(tab, g)
+    assert lib.rlctr_gather_rows(L().ptr(flat), flat.numel(), C.byref(t), L().ptr(out), st()) == 0
+    assert torch.equal(out, tab[flat])
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 FFM
+# ------------------------------------------------------------------------------------------------
+def run_ffm(lib, ids, tab, g, bias, D, partners=False):
+    B, F = ids.shape
+    logit = torch.empty(B, device=DEV)
+    pctr = torch.empty(B, device=DEV)
+    part = torch.empty(B * F, g.row_stride, device=DEV) if partners else None
+    t = T().table_struct(tab, g)
+    rc = lib.rlctr_ffm_fwd(L().ptr(dev(ids)), C.byref(t), L().ptr(dev(bias)), L().ptr(logit), L().ptr(pctr), 1,
+                           L().ptr(part), B, F, D, st())
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    return logit, pctr, part
+
+
+@pytest.mark.parametrize("B,F,D", [(1, 15, 10), (77, 15, 10), (300, 15, 8), (40, 4, 3), (16, 22, 4)])
+def test_ffm_fwd(lib, B, F, D):
+    rng = np.random.default_rng(B + F + D)
+    N = 211
+    ids = rng.integers(0, N, size=(B, F)).astype(np.int64)
+    tables = (rng.standard_normal((F, N, D)) * 0.3).astype(np.float32)
+    lin = (rng.standard_normal((N, 1)) * 0.3).astype(np.float32)
+    bias = np.array([-0.2], np.float32)
+    tab, g = fused_ffm_table(lin, tables)
+    logit, pctr, part = run_ffm(lib, ids, tab, g, bias, D, partners=True)
+    close(logit, O.ffm_logit(ids, tables, lin, bias, np.float64).reshape(-1))
+    close(pctr, O.sigmoid(O.ffm_logit(ids, tables, lin, bias)).reshape(-1))
+    # partner rows == d logit / d row: G[t, b, f] of the oracle with dz = 1, plus 1 at the linear col
+    G = O.ffm_row_grads(np.ones(B, np.float32), ids, tables)          # [F_table, B, F_field, D]
+    part = part.cpu().numpy().reshape(B, F, g.row_stride)
+    for t in range(F):
+        assert np.array_equal(part[:, :, t * D:(t + 1) * D], G[t])
+    assert np.all(part[:, :, g.lin_col] == 1.0)
+    assert np.all(part[:, :, g.lin_col + 1:] == 0.0)
+
+
+def test_ffm_golden_kat(lib, golden):
+    sd = state_from_golden(golden, "kat/FFM/init")
+    tables = np.stack([sd[f"field_feature_embeddings.{t}.weight"] for t in range(15)])
+    tab, g = fused_ffm_table(sd["linear.weight"], tables)
+    _, pctr, _ = run_ffm(lib, golden["kat/x"], tab, g, sd["bias"], 10)
+    close(pctr, golden["kat/FFM/pctr"].reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 Feature_Embedding
+# ------------------------------------------------------------------------------------------------
+def test_featemb_golden(lib, golden):
+    for wkey, xkey, okey in (("kat/FE/weight", "kat/x", "kat/FE/out"), ("fe/weight", "fe/x", "fe/out")):
+        w, x, ref = golden[wkey], golden[xkey], golden[okey]
+        N, D = w.shape
+        g = T().Geometry.fm(N, D, with_linear=False)
+        tab = torch.zeros(N, g.row_stride)
+        tab[:, :D] = torch.as_tensor(w)
+        tab = tab.to(DEV)
+        B, F = x.shape
+        out = torch.empty(B, ref.shape[1], device=DEV)
+        t = T().table_struct(tab, g)
+        assert lib.rlctr_featemb_fwd(L().ptr(dev(x)), C.byref(t), L().ptr(out), out.stride(0), B, F, st()) == 0
+        close(out, ref)
+        # the flattened rows are a bit-exact copy
+        assert np.array_equal(out[:, F * (F - 1) // 2:].cpu().numpy(), w[x].reshape(B, -1))
+        close(out, O.feature_embedding(x, w))
+
+
+# ------------------------------------------------------------------------------------------------
+# loss head
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 48, 4096, 300001])
+def test_bce_fwd_bwd(lib, B):
+    rng = np.random.default_rng(B)
+    z = (rng.standard_normal(B) * 30).astype(np.float32)       # deep into the saturated regime (N2)
+    y = (rng.random(B) < 0.4).astype(np.int64)
+    ws = torch.zeros(L().RLCTR_REDUCE_WS_BYTES, dtype=torch.uint8, device=DEV)
+    pctr = torch.empty(B, device=DEV)
+    loss = torch.empty(1, device=DEV)
+    dz = torch.empty(B, device=DEV)
+    db = torch.empty(1, device=DEV)
+    for yi, yf in ((dev(y), None), (None, dev(y, torch.float32))):
+        rc = lib.rlctr_bce_fwd_bwd(L().ptr(dev(z)), L().ptr(yi), L().ptr(yf), L().ptr(pctr), L().ptr(loss), L().ptr(dz),
+                                   L().ptr(db), L().ptr(ws), B, st())
+        assert rc == 0
+        p_ref, l_ref, dz_ref = O.loss_head(z, y)
+        close(pctr, p_ref.reshape(-1))
+        close(loss, l_ref, rtol=1e-5)
+        close(dz, dz_ref.reshape(-1), atol=1e-12)
+        close(db, dz_ref.astype(np.float64).sum(), rtol=1e-4, atol=1e-7)
+    # and against torch's own CPU autograd (the op the reference calls)
+    zt = torch.tensor(z, requires_grad=True)
+    lt = torch.nn.BCELoss()(torch.sigmoid(zt).view(-1, 1), torch.tensor(y).float().view(-1, 1))
+    lt.backward()
+    close(loss, lt.item(), rtol=1e-5)
+    close(dz, zt.grad, atol=1e-12)
+    # determinism: fixed-shape tree
+    l1 = loss.clone()
+    lib.rlctr_bce_fwd_bwd(L().ptr(dev(z)), L().ptr(dev(y)), None, L().ptr(pctr), L().ptr(loss), L().ptr(dz),
+                          L().ptr(db), L().ptr(ws), B, st())
+    assert torch.equal(l1, loss)
+
+
+def test_sigmoid_bwd(lib):
+    B = 1000
+    rng = np.random.default_rng(0)
+    p = rng.random(B).astype(np.float32)
+    g = rng.standard_normal(B).astype(np.float32)
+    ws = torch.zeros(L().RLCTR_REDUCE_WS_BYTES, dtype=torch.uint8, device=DEV)
+    dz = torch.empty(B, device=DEV)
+    db = torch.empty(1, device=DEV)
+    assert lib.rlctr_sigmoid_bwd(L().ptr(dev(g)), L().ptr(dev(p)), L().ptr(dz), L().ptr(db), L().ptr(ws), B, st()) == 0
+    ref = g * (np.float32(1) - p) * p
+    close(dz, ref, atol=1e-9)
+    close(db, ref.astype(np.float64).sum(), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 sort + segment-reduce + Adam
+# ------------------------------------------------------------------------------------------------
+def do_sort(lib, ids_flat_d, n_rows):
+    n = ids_flat_d.numel()
+    sid = torch.empty(n, dtype=torch.int32, device=DEV)
+    ss = torch.empty(n, dtype=torch.int32, device=DEV)
+    wsb = lib.rlctr_sort_ws_bytes(n, n_rows)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_sort_ids(L().ptr(ids_flat_d), n, n_rows, L().ptr(sid), L().ptr(ss), L().ptr(ws), wsb, st()) == 0
+    return sid, ss
+
+
+@pytest.mark.parametrize("n,n_rows", [(1, 10), (720, 255), (100000, 1000), (983040, 10_000_000)])
+def test_sort_ids_stable(lib, n, n_rows):
+    rng = np.random.default_rng(n)
+    ids = rng.integers(0, n_rows, size=n).astype(np.int64)
+    sid, ss = do_sort(lib, dev(ids), n_rows)
+    order = np.argsort(ids, kind="stable")
+    assert np.array_equal(sid.cpu().numpy().astype(np.int64), ids[order])
+    assert np.array_equal(ss.cpu().numpy().astype(np.int64), order)
+
+
+def adam_struct(m, v, stamp, sched, step, wd=1e-5):
+    return L().Adam(L().ptr(m), L().ptr(v), L().ptr(stamp), L().ptr(sched), L().ptr(step), sched.shape[0], 0.9, 0.999,
+                    1e-8, wd)
+
+
+def make_sched(lr, n=64):
+    return T().AdamSchedule(lr, (0.9, 0.999), torch.device(DEV), n).tensor
+
+
+@pytest.mark.parametrize("D", [10, 8, 16])
+@pytest.mark.parametrize("zipf", [True, False])
+def test_rows_grad_dense_fm(lib, D, zipf):
+    """embedding_dense_backward parity: FM row gradients scattered into a dense [N, rs] gradient."""
+    B, F, N = 600, 15, 400
+    ids, emb, lin, bias, y = rng_case(D + 100 * zipf, B, F, N, D, zipf=zipf)
+    if zipf:
+        ids[:, 0] = 0                       # one id hit by every sample: the long-run path (> LONG_RUN)
+        ids[0, 1] = ids[0, 0]               # repeated id inside one sample
+    tab, g = fused_fm_table(lin, emb)
+    logit, _, sums, _ = run_embed_fwd(lib, ids, tab, g, bias, want_rows=False)
+    _, _, dz_ref = O.loss_head(logit.cpu().numpy(), y)
+    dz = dev(dz_ref.reshape(-1))
+    sid, ss = do_sort(lib, dev(ids.reshape(-1)), N)
+    dense = torch.zeros(N, g.row_stride, device=DEV)
+    grad = L().RowGrad(None, L().ptr(dz), L().ptr(sums), None, F, 0)
+    t = T().table_struct(tab, g)
+    wsb = lib.rlctr_rows_ws_bytes(B * F)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_rows_grad_dense(L().ptr(sid), L().ptr(ss), B * F, C.byref(grad), C.byref(t), L().ptr(dense),
+                                     L().ptr(ws), wsb, st()) == 0
+    demb, dlin = O.fm_row_grads(dz_ref, ids, emb)
+    ref_emb = O.scatter_dense(ids, demb, N, np.float64)
+    ref_lin = O.scatter_dense(ids, dlin.reshape(B, F, 1), N, np.float64)
+    close(dense[:, 1:1 + D], ref_emb, rtol=2e-5, atol=1e-7)
+    close(dense[:, 0:1], ref_lin, rtol=2e-5, atol=1e-7)
+    # bit-identical from run to run (no atomics on the data path)
+    dense2 = torch.zeros_like(dense)
+    lib.rlctr_rows_grad_dense(L().ptr(sid), L().ptr(ss), B * F, C.byref(grad), C.byref(t), L().ptr(dense2),
+                              L().ptr(ws), wsb, st())
+    assert torch.equal(dense, dense2)
+
+
+def test_rows_grad_golden_fm(lib, golden):
+    """dense gradient of step 0 of the golden FM trajectory == autograd of the real reference."""
+    for case in ("train", "sat"):
+        sd = state_from_golden(golden, f"{case}/FM/init")
+        x, y = golden["train/x"][0], golden["train/y"][0]
+        N = 255
+        tab, g = fused_fm_table(sd["linear.weight"], sd["feature_embedding.weight"])
+        B, F = x.shape
+        logit, _, sums, _ = run_embed_fwd(lib, x, tab, g, sd["bias"], want_rows=False)
+        ws0 = torch.zeros(L().RLCTR_REDUCE_WS_BYTES, dtype=torch.uint8, device=DEV)
+        dz = torch.empty(B, device=DEV)
+        loss = torch.empty(1, device=DEV)
+        assert lib.rlctr_bce_fwd_bwd(L().ptr(logit), L().ptr(dev(y)), None, None, L().ptr(loss), L().ptr(dz), None,
+                                     L().ptr(ws0), B, st()) == 0
+        close(loss, golden[f"{case}/FM/loss0"])
+        sid, ss = do_sort(lib, dev(x.reshape(-1)), N)
+        dense = torch.zeros(N, g.row_stride, device=DEV)
+        grad = L().RowGrad(None, L().ptr(dz), L().ptr(sums), None, F, 0)
+        t = T().table_struct(tab, g)
+        wsb = lib.rlctr_rows_ws_bytes(B * F)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        assert lib.rlctr_rows_grad_dense(L().ptr(sid), L().ptr(ss), B * F, C.byref(grad), C.byref(t), L().ptr(dense),
+                                         L().ptr(ws), wsb, st()) == 0
+        close(dense[:, 1:11], golden[f"{case}/FM/grad0/feature_embedding.weight"], rtol=2e-5, atol=1e-8)
+        close(dense[:, 0:1], golden[f"{case}/FM/grad0/linear.weight"], rtol=2e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("mode", ["lazy", "dense"])
+def test_rows_adam_matches_dense_adam(lib, mode):
+    """K3 + lazy replay == the reference's dense Adam with L2 over EVERY row, 4 steps."""
+    B, F, N, D, STEPS, lr, wd = 64, 15, 300, 10, 4, 1e-3, 1e-5
+    ids0, emb, lin, bias, _ = rng_case(77, B, F, N, D)
+    tab, g = fused_fm_table(lin, emb)
+    rs = g.row_stride
+    m = torch.zeros_like(tab)
+    v = torch.zeros_like(tab)
+    stamp = torch.zeros(N, dtype=torch.int32, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    sched = make_sched(lr)
+    a = adam_struct(m, v, stamp, sched, step, wd)
+    t = T().table_struct(tab, g)
+    # oracle state (padded layout, pad columns stay 0)
+    P = tab.cpu().numpy().copy()
+    Mo, Vo = np.zeros_like(P), np.zeros_like(P)
+    rng = np.random.default_rng(3)
+    for s in range(1, STEPS + 1):
+        ids = rng.integers(0, N // 3, size=(B, F)).astype(np.int64) + (s % 3) * (N // 3)   # rows go stale and come back
+        dzv = (rng.standard_normal(B) * 0.01).astype(np.float32)
+        staged = (rng.standard_normal((B * F, rs)) * 0.01).astype(np.float32)
+        staged[:, 1 + D:] = 0
+        sid, ss = do_sort(lib, dev(ids.reshape(-1)), N)
+        if mode == "lazy":
+            assert lib.rlctr_rows_catchup(L().ptr(sid), B * F, C.byref(t), C.byref(a), st()) == 0
+            # rows of this batch now equal the dense-Adam state after s-1 steps
+            got = tab.cpu().numpy()
+            uniq = np.unique(ids)
+            close(got[uniq], P[uniq], rtol=2e-5, atol=1e-7)
+        grad = L().RowGrad(L().ptr(dev(staged)), L().ptr(dev(dzv)), None, None, F, 0)
+        wsb = lib.rlctr_rows_ws_bytes(B * F)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        assert lib.rlctr_rows_adam(L().ptr(sid), L().ptr(ss), B * F, C.byref(grad), C.byref(t), C.byref(a), L().ptr(ws),
+                                   wsb, st()) == 0
+        assert lib.rlctr_step_advance(L().ptr(step), 1, st()) == 0
+        if mode == "dense":
+            assert lib.rlctr_adam_flush(C.byref(t), C.byref(a), 0, N, st()) == 0
+        # oracle: dense gradient = scatter(staged) + dz at the linear column, Adam over ALL rows
+        G = O.scatter_dense(ids, staged.reshape(B, F, rs), N)
+        G[:, 0] += O.scatter_dense(ids, np.repeat(dzv, F).reshape(B, F, 1), N)[:, 0]
+        P, Mo, Vo = O.adam_step(P, G, Mo, Vo, s, lr, wd)
+        P[:, 1 + D:] = 0
+    assert lib.rlctr_adam_flush(C.byref(t), C.byref(a), 0, N, st()) == 0
+    torch.cuda.synchronize()
+    assert step.item() == STEPS and int(stamp.min()) == STEPS
+    close(tab, P, rtol=2e-5, atol=1e-7)
+    close(m, Mo, rtol=2e-5, atol=1e-9)
+    close(v, Vo, rtol=2e-5, atol=1e-12)
+
+
+def test_dense_adam(lib):
+    n, lr, wd = 12345, 1e-3, 1e-5
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal(n).astype(np.float32)
+    P, Mo, Vo = p.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    pd_, m, v = dev(p), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    sched = make_sched(lr)
+    pt = torch.tensor(p.copy(), requires_grad=True)
+    topt = torch.optim.Adam([pt], lr=lr, weight_decay=wd)
+    for s in range(1, 4):
+        gnp = rng.standard_normal(n).astype(np.float32)
+        assert lib.rlctr_dense_adam(L().ptr(pd_), L().ptr(dev(gnp)), L().ptr(m), L().ptr(v), n, L().ptr(sched),
+                                    L().ptr(step), 0.9, 0.999, 1e-8, wd, st()) == 0
+        assert lib.rlctr_step_advance(L().ptr(step), 1, st()) == 0
+        P, Mo, Vo = O.adam_step(P, gnp, Mo, Vo, s, lr, wd)
+        pt.grad = torch.tensor(gnp)
+        topt.step()
+    close(pd_, P, rtol=2e-6, atol=1e-8)
+    close(pd_, pt.detach(), rtol=2e-6, atol=1e-8)           # torch.optim.Adam itself (CPU)
+
+
+# ------------------------------------------------------------------------------------------------
+# K6 generate_preds, REINFORCE head
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [3, 5, 6])
+def test_generate_preds_golden(lib, golden, M):
+    pre = f"gp/v0_M{M}/"
+    pctr, w, lab = golden[pre + "pctr"], golden[pre + "w"], golden[pre + "label"]
+    B = pctr.shape[0]
+    for variant, akey in ((0, pre + "action"), (1, f"gp/v1_M{M}/action")):
+        act = golden[akey]
+        y = torch.empty(B, device=DEV)
+        wo = torch.empty(B, M, device=DEV)
+        r = torch.empty(B, device=DEV)
+        assert lib.rlctr_generate_preds(L().ptr(dev(pctr)), L().ptr(dev(w)), L().ptr(dev(act.reshape(-1))),
+                                        L().ptr(dev(lab.reshape(-1))), L().ptr(y), L().ptr(wo), L().ptr(r), B, M, variant,
+                                        st()) == 0
+        vpre = pre if variant == 0 else f"gp/v1_M{M}/"
+        close(y, golden[vpre + "y"].reshape(-1), rtol=1e-5, atol=1e-7)
+        assert np.array_equal(r.cpu().numpy(), golden[vpre + "reward"].reshape(-1))
+        if variant == 0:
+            close(wo, golden[pre + "w_out"], rtol=1e-5, atol=1e-7)
+
+
+def test_generate_preds_random_vs_oracle(lib):
+    rng = np.random.default_rng(11)
+    for M in (2, 3, 8):
+        B = 5000
+        pctr = rng.random((B, M)).astype(np.float32)
+        w = O.softmax(rng.standard_normal((B, M)).astype(np.float32) * 2)
+        lab = (rng.random(B) < 0.5).astype(np.int64)
+        for variant, lo in ((0, 2), (1, 1)):
+            act = rng.integers(lo, M + 1, size=B).astype(np.int64)
+            act[:7] = 0                                            # no branch matches: y = r = 1 (main.py:185-186)
+            y = torch.empty(B, device=DEV)
+            wo = torch.empty(B, M, device=DEV)
+            r = torch.empty(B, device=DEV)
+            assert lib.rlctr_generate_preds(L().ptr(dev(pctr)), L().ptr(dev(w)), L().ptr(dev(act)), L().ptr(dev(lab)),
+                                            L().ptr(y), L().ptr(wo), L().ptr(r), B, M, variant, st()) == 0
+            yo, wo_o, ro = O.generate_preds(pctr, w, act, lab, variant)
+            close(y, yo.reshape(-1), rtol=1e-5, atol=1e-7)
+            close(wo, wo_o, rtol=1e-5, atol=1e-7)
+            # rewards compare y with the baseline: allow flips only where they are within rounding of each other
+            mism = r.cpu().numpy() != ro.reshape(-1)
+            assert mism.mean() < 1e-3
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_reinforce_head(lib, golden, variant):
+    logits, acts = golden["pg/logits"], golden["pg/acts"].reshape(-1)
+    B, A = logits.shape
+    ws = torch.zeros(L().RLCTR_REDUCE_WS_BYTES, dtype=torch.uint8, device=DEV)
+    for vt_key, loss_key, dl_key in (("pg/vt_norm", "pg/loss_literal", "pg/dlogits_literal"),
+                                     ("pg/vt_raw", "pg/loss_literal_raw", "pg/dlogits_literal_raw")):
+        vt = golden[vt_key].astype(np.float32)
+        logp = torch.empty(B, device=DEV)
+        loss = torch.empty(1, device=DEV)
+        dl = torch.empty(B, A, device=DEV)
+        assert lib.rlctr_reinforce_loss_bwd(L().ptr(dev(logits)), L().ptr(dev(acts)), L().ptr(dev(vt)), L().ptr(logp),
+                                            L().ptr(loss), L().ptr(dl), L().ptr(ws), B, A, variant, st()) == 0
+        close(logp, golden["pg/logp"], rtol=1e-5, atol=1e-7)                # policy log-probs: the 1e-5 bar
+        lo, losso, dlo = O.reinforce_loss(logits, acts, vt, variant)
+        close(logp, lo, rtol=1e-5, atol=1e-7)
+        close(loss, losso, rtol=1e-4, atol=1e-5)
+        close(dl, dlo, rtol=1e-4, atol=1e-7)
+        if variant == 0:
+            close(loss, golden[loss_key], rtol=1e-4, atol=2e-5)
+            close(dl, golden[dl_key], rtol=1e-4, atol=1e-7)

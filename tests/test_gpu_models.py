@@ -1,0 +1,237 @@
+"""Drop-in surface parity: the p_model classes, optim.Adam and the loop functions on the B200 against
+golden trajectories recorded from the REAL reference modules (tests/golden/make_golden.py) -- the
+reference's loop body ``y = model(x); loss(y, labels); zero_grad(); backward(); optimizer.step()``
+(src/main/pretrain_main.py:96-102) with dense ``torch.optim.Adam(lr=1e-3, weight_decay=1e-5)``.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_from_golden
+from oracle import np_oracle as O
+from oracle import torch_port as TP
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+RTOL, ATOL = 1e-5, 1e-6
+F, D = 15, 10
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a.astype(np.float64), b.astype(np.float64), rtol=rtol, atol=atol)
+
+
+def build(name, N, D_=D):
+    from rl_ctr_prediction_b200 import pretrain_main as PM
+    return PM.get_model(name, N, F, D_)
+
+
+def load(model, sd):
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    return model
+
+
+def assert_state(model, ref_sd, rtol=2e-5, atol=2e-7):
+    sd = model.state_dict()
+    assert set(sd.keys()) == set(ref_sd.keys())
+    for k, v in ref_sd.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+        close(sd[k], v, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
+def test_state_dict_keys_and_kat(golden, name):
+    sd = state_from_golden(golden, f"kat/{name}/init")
+    m = load(build(name, 64), sd).to(DEV).eval()
+    out_sd = m.state_dict()
+    assert set(out_sd.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert np.array_equal(out_sd[k].cpu().numpy(), v), k           # layout round trip is bit-exact
+    with torch.no_grad():
+        p = m(torch.as_tensor(golden["kat/x"]).to(DEV))
+    assert p.shape == (4, 1) and p.dtype == torch.float32
+    close(p, golden[f"kat/{name}/pctr"])
+
+
+@pytest.mark.parametrize("mode", ["lazy", "dense"])
+@pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
+def test_training_trajectory_matches_reference(golden, name, mode):
+    """3 steps of the reference loop body; every pctr, every loss and the final state_dict of ALL rows
+    (touched or not -- dense Adam + L2 moves them all) match the reference."""
+    from rl_ctr_prediction_b200 import optim
+    sd = state_from_golden(golden, f"train/{name}/init")
+    m = load(build(name, 255), sd).to(DEV)
+    m.eval()                       # golden trajectories were recorded with dropout off
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5, mode=mode)
+    lossf = torch.nn.BCELoss()
+    xs, ys = golden["train/x"], golden["train/y"]
+    for s in range(3):
+        x = torch.as_tensor(xs[s]).to(DEV)
+        y = torch.as_tensor(ys[s]).unsqueeze(1).to(DEV)
+        p = m(x)
+        tl = lossf(p, y.float())
+        m.zero_grad()
+        tl.backward()
+        opt.step()
+        close(p, golden[f"train/{name}/pctr{s}"])
+        close(tl, golden[f"train/{name}/loss{s}"])
+    assert_state(m, state_from_golden(golden, f"train/{name}/final"))
+
+
+@pytest.mark.parametrize("name", ["LR", "FM", "FFM"])
+def test_fused_train_step_matches_reference(golden, name):
+    from rl_ctr_prediction_b200 import optim, pretrain_main as PM
+    sd = state_from_golden(golden, f"train/{name}/init")
+    m = load(build(name, 255), sd).to(DEV)
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
+    for s in range(3):
+        x = torch.as_tensor(golden["train/x"][s]).to(DEV)
+        y = torch.as_tensor(golden["train/y"][s]).to(DEV)
+        tl = PM.fused_train_step(m, opt, x, y)
+        close(tl, golden[f"train/{name}/loss{s}"])
+    assert_state(m, state_from_golden(golden, f"train/{name}/final"))
+
+
+def test_saturated_regime(golden):
+    """Default N(0,1) init: fp32 sigmoid saturates, BCELoss clamps."""
+    from rl_ctr_prediction_b200 import optim
+    m = load(build("FM", 255), state_from_golden(golden, "sat/FM/init")).to(DEV)
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
+    lossf = torch.nn.BCELoss()
+    for s in range(2):
+        x = torch.as_tensor(golden["train/x"][s]).to(DEV)
+        y = torch.as_tensor(golden["train/y"][s]).unsqueeze(1).to(DEV)
+        p = m(x)
+        tl = lossf(p, y.float())
+        m.zero_grad()
+        tl.backward()
+        opt.step()
+        close(p, golden[f"sat/FM/pctr{s}"], rtol=2e-5)
+        close(tl, golden[f"sat/FM/loss{s}"], rtol=2e-5)
+    assert_state(m, state_from_golden(golden, "sat/FM/final"), rtol=5e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("D2", [8, 16])
+def test_other_latent_dims(golden, D2):
+    from rl_ctr_prediction_b200 import optim
+    m = load(build("FM", 255, D2), state_from_golden(golden, f"dims/FM{D2}/init")).to(DEV)
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
+    x = torch.as_tensor(golden["train/x"][0]).to(DEV)
+    y = torch.as_tensor(golden["train/y"][0]).unsqueeze(1).to(DEV)
+    p = m(x)
+    tl = torch.nn.BCELoss()(p, y.float())
+    m.zero_grad()
+    tl.backward()
+    opt.step()
+    close(p, golden[f"dims/FM{D2}/pctr0"])
+    close(tl, golden[f"dims/FM{D2}/loss0"])
+    assert_state(m, state_from_golden(golden, f"dims/FM{D2}/final"))
+
+
+def test_loop_api_matches_reference_train_and_test(golden):
+    """pretrain_main.train / test over a 3-batch 'epoch' == the reference's own train()/test() driving
+    the reference FM (golden 'loop/*'), including sklearn AUC."""
+    from rl_ctr_prediction_b200 import optim, pretrain_main as PM
+    for fused in (False, True):
+        m = load(build("FM", 255), state_from_golden(golden, "train/FM/init")).to(DEV)
+        opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
+        loader = [(torch.as_tensor(golden["train/x"][s]), torch.as_tensor(golden["train/y"][s])) for s in range(3)]
+        avg = PM.train(m, opt, loader, torch.nn.BCELoss(), torch.device(DEV), fused=fused)
+        auc, tloss = PM.test(m, loader, torch.nn.BCELoss(), torch.device(DEV))
+        close(avg, golden["loop/FM/train_avg_loss"])
+        close(tloss, golden["loop/FM/test_loss"])
+        assert abs(auc - float(golden["loop/FM/test_auc"])) <= 1e-5
+        assert_state(m, state_from_golden(golden, "loop/FM/final"))
+
+
+def test_fresh_optimizer_each_epoch_and_eval_flush(golden):
+    """The reference re-creates Adam every epoch (N4) and evaluates between epochs: a lazy table must
+    be flushed by eval()/state_dict()/a new optimizer.  Checked against the CPU port run densely."""
+    from rl_ctr_prediction_b200 import optim
+    torch.manual_seed(5)
+    N = 400
+    port = TP.PortCTR("FM", N, F, D)
+    with torch.no_grad():
+        for k, p in port.named_parameters():
+            if k != "bias":
+                p.mul_(0.1)
+    m = build("FM", N)
+    m.load_state_dict(port.state_dict())
+    m.to(DEV)
+    rng = np.random.default_rng(2)
+    lossf = torch.nn.BCELoss()
+    for epoch in range(2):
+        popt = TP.make_adam(port, lr=1e-3 + 1e-4 * epoch)
+        opt = optim.Adam(params=m.parameters(), lr=1e-3 + 1e-4 * epoch, weight_decay=1e-5)
+        for s in range(5):
+            x = torch.as_tensor(rng.integers(0, N // 4, size=(32, F)) + (s % 4) * (N // 4))
+            y = torch.as_tensor((rng.random(32) < 0.3).astype(np.int64)).unsqueeze(1)
+            TP.ctr_train_step(port, popt, lossf, x, y)
+            p = m(x.to(DEV))
+            tl = lossf(p, y.to(DEV).float())
+            m.zero_grad()
+            tl.backward()
+            opt.step()
+        xe = torch.as_tensor(rng.integers(0, N, size=(64, F)))
+        with torch.no_grad():
+            port.eval(); m.eval()
+            close(m(xe.to(DEV)), port(xe), rtol=2e-5)
+            port.train(); m.train()
+    ref = {k: v.numpy() for k, v in port.state_dict().items()}
+    assert_state(m, ref, rtol=5e-5, atol=1e-6)
+
+
+def test_cpu_tensors_are_refused():
+    from rl_ctr_prediction_b200 import _lib
+    m = build("FM", 64)
+    with pytest.raises(_lib.RlctrError):
+        m(torch.zeros(2, F, dtype=torch.long))
+
+
+def test_large_batch_round_trip_properties():
+    """Size-independent checks at the bench shape (B=65536, N=10M): rows_out is a bit-exact gather, the
+    FM identity 0.5*sum_d[(sum v)^2 - sum v^2] == sum_{i<j} <v_i, v_j> ties K1 to K5, and one lazy step
+    followed by flush equals one dense step."""
+    import ctypes as C
+    from rl_ctr_prediction_b200 import _lib, optim, p_model, Feature_embedding
+    from rl_ctr_prediction_b200.tables import table_struct
+    torch.manual_seed(0)
+    N, B = 10_000_000, 65536
+    m = p_model.FM(N, D, device=DEV)
+    with torch.no_grad():
+        m.table.mul_(0.1)
+    per = N // F
+    x = (torch.randint(0, per, (B, F), device=DEV) + torch.arange(F, device=DEV) * per).long()
+    lib = _lib.load()
+    g = m._geom
+    rows = torch.empty(B, F * D, device=DEV)
+    logit = torch.empty(B, device=DEV)
+    t = table_struct(m.table.data, g)
+    assert lib.rlctr_embed_fwd(_lib.ptr(x), C.byref(t), _lib.ptr(m.bias.data), _lib.ptr(logit), None, 1, None,
+                               _lib.ptr(rows), B, F, 1, _lib.stream()) == 0
+    assert torch.equal(rows.view(B, F, D), m.table.data[x][:, :, 1:1 + D])
+    fe = Feature_embedding.Feature_Embedding(N, F, D, device=DEV)
+    with torch.no_grad():
+        fe.table.data[:, :D].copy_(m.table.data[:, 1:1 + D])
+    state = fe(x)
+    second = state[:, :105].double().sum(dim=1)
+    first = m.table.data[x][:, :, 0].double().sum(dim=1)
+    close(logit.double(), first + second, rtol=1e-5, atol=1e-5)
+    # lazy + flush == dense, bit for bit (same kernels, same per-element arithmetic)
+    y = (torch.rand(B, device=DEV) < 0.05).long().unsqueeze(1)
+    m2 = p_model.FM(N, D, device=DEV)
+    with torch.no_grad():
+        m2.table.copy_(m.table)
+    lossf = torch.nn.BCELoss()
+    for model, mode in ((m, "lazy"), (m2, "dense")):
+        opt = optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, mode=mode)
+        for _ in range(2):
+            tl = lossf(model(x), y.float())
+            model.zero_grad()
+            tl.backward()
+            opt.step()
+        model.flush()
+    assert torch.equal(m.table.data, m2.table.data)
