@@ -69,7 +69,10 @@ typedef struct rlctr_adam {
     const float*   sched;        /* [sched_len][2], index = step (entry 0 unused) */
     const int32_t* step;         /* device scalar: completed steps t; update kernels apply step t+1 */
     int32_t        sched_len;
-    float          beta1, beta2, eps, weight_decay;
+    /* hyper-parameters as the Python DOUBLES torch.optim.Adam holds: the kernels use float(1 - beta1),
+     * float(1 - beta2), float(eps), float(weight_decay) exactly as torch derives them in double and casts
+     * at the op (1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative) */
+    double         beta1, beta2, eps, weight_decay;
 } rlctr_adam;
 
 /* Where the gradient of a gathered row comes from.  For sorted position k with
@@ -194,8 +197,8 @@ int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
 /* Dense Adam for the replicated parameters (bias, tower, policy nets): applies step *step+1
  * with torch semantics. */
 int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                     const float* sched, const int32_t* step, float beta1, float beta2, float eps,
-                     float weight_decay, rlctr_stream_t stream);
+                     const float* sched, const int32_t* step, double beta1, double beta2, double eps,
+                     double weight_decay, rlctr_stream_t stream);
 int rlctr_step_advance(int32_t* step, int32_t delta, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

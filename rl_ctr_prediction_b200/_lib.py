@@ -34,7 +34,7 @@ class Adam(C.Structure):
     """struct rlctr_adam"""
     _fields_ = [("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("stamp", C.c_void_p),
                 ("sched", C.c_void_p), ("step", C.c_void_p), ("sched_len", C.c_int32),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float)]
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double)]
 
 
 class RowGrad(C.Structure):
@@ -43,7 +43,7 @@ class RowGrad(C.Structure):
                 ("extra", C.c_void_p), ("fields", C.c_int32), ("flags", C.c_int32)]
 
 
-_P, _I64, _I32, _SZ, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_float
+_P, _I64, _I32, _SZ, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
 _TP, _AP, _GP = C.POINTER(Table), C.POINTER(Adam), C.POINTER(RowGrad)
 
 # name -> (restype, argtypes); must list every symbol include/rlctr.h declares

@@ -78,15 +78,18 @@ __device__ __forceinline__ float sigmoidf_ref(float z) { return 1.0f / (1.0f + e
 
 // ---- torch.optim.Adam (_single_tensor_adam, non-capturable branch), one element ----------
 struct AdamHyper {
-    float beta1, beta2, eps, wd;
+    float beta2, omb1, omb2, eps, wd;     // omb = float(1 - beta) taken in DOUBLE first, like torch's Python scalars
 };
+static inline AdamHyper adam_hyper(double beta1, double beta2, double eps, double wd) {
+    return AdamHyper{(float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)wd};
+}
 
 // one step with gradient g (L2 folded in like torch: g += wd*p)
 __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamHyper& h,
                                           float step_size, float bc2_sqrt) {
     g = g + h.wd * p;
-    m = m + (1.0f - h.beta1) * (g - m);                 // exp_avg.lerp_(grad, 1-beta1)
-    v = v * h.beta2 + (1.0f - h.beta2) * g * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+    m = m + h.omb1 * (g - m);                           // exp_avg.lerp_(grad, 1-beta1)
+    v = v * h.beta2 + h.omb2 * g * g;                   // mul_(beta2).addcmul_(g, g, 1-beta2)
     float denom = sqrtf(v) / bc2_sqrt + h.eps;
     p = p + (-step_size) * m / denom;                   // addcdiv_(exp_avg, denom, value=-step_size)
 }

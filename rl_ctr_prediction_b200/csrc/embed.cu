@@ -84,7 +84,7 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
         // sum over the F rows: lanes owning the same chunk sit LPR apart
 #pragma unroll
         for (int off = LPR; off < 32; off <<= 1) {
-            s = shfl_xor4(s, off);
+            s = f4add(s, shfl_xor4(s, off));
             q += __shfl_xor_sync(RLCTR_FULL, q, off);
         }
         float t = 0.f;

@@ -37,7 +37,7 @@ struct AdamView {
 };
 static inline AdamView view_of(const rlctr_adam* a) {
     return AdamView{a->exp_avg, a->exp_avg_sq, a->stamp, reinterpret_cast<const float2*>(a->sched), a->step,
-                    AdamHyper{a->beta1, a->beta2, a->eps, a->weight_decay}};
+                    adam_hyper(a->beta1, a->beta2, a->eps, a->weight_decay)};
 }
 struct GradView {
     const float* staged;
@@ -582,13 +582,13 @@ extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
 }
 
 extern "C" int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                const float* sched, const int32_t* step, float beta1, float beta2, float eps,
-                                float weight_decay, rlctr_stream_t stream) {
+                                const float* sched, const int32_t* step, double beta1, double beta2, double eps,
+                                double weight_decay, rlctr_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || !sched || !step || n < 0) return RLCTR_EINVAL;
     if (n == 0) return RLCTR_OK;
     dense_adam_kernel<<<grid_1d(n, RLCTR_SMS * 8), 256, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, n, reinterpret_cast<const float2*>(sched), step,
-        AdamHyper{beta1, beta2, eps, weight_decay});
+        adam_hyper(beta1, beta2, eps, weight_decay));
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layouts_match_header():
     from rl_ctr_prediction_b200 import _lib
     assert C.sizeof(_lib.Table) == 32           # ptr, i64, 4 x i32
-    assert C.sizeof(_lib.Adam) == 64            # 5 ptr, i32, 4 x f32 (+pad)
+    assert C.sizeof(_lib.Adam) == 80            # 5 ptr, i32 (+pad), 4 x f64
     assert C.sizeof(_lib.RowGrad) == 40         # 4 ptr, 2 x i32
     assert _lib.Table.row_stride.offset == 16 and _lib.Adam.sched_len.offset == 40
 
