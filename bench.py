@@ -79,6 +79,8 @@ def alg_bytes(key, m):
         return 16.0 * m["n"]                                   # read int64 ids, write u32 key + u32 slot
     if name == "rlctr_adam_flush":
         return m["n_rows"] * (24.0 * m["rs"] + 8.0)
+    if name in ("rlctr_linear_fwd", "rlctr_linear_bwd"):
+        return 0.0                                             # tensor-bound: reported in FLOP/s (gemm_flops)
     B, F, N = m["B"], m["F"], m["n_rows"]
     logical = (m["dim"] + (1 if m["lin"] else 0)) if m["rs"] > 1 else 1
     n = B * F
@@ -107,6 +109,14 @@ def alg_bytes(key, m):
     if name == "rlctr_ffm_fwd":
         return float(B * (F * 8 + F * 4 * logical + 4) + n * 4 * logical)
     return 0.0
+
+
+def gemm_flops(key, m):
+    """fp32-equivalent FLOPs of one dense-layer call (the 3xTF32 split issues 3x this on the tensor pipe)."""
+    f = 2.0 * m["B"] * m["K"] * m["N"]
+    if key.startswith("rlctr_linear_bwd"):
+        return f * (2.0 if m.get("dx") else 1.0)
+    return f
 
 
 class Clocks:
@@ -310,6 +320,13 @@ def b200_arm(args):
     kern = prof.summary(alg_bytes)   # name -> (launches, mean ms, algorithmic bytes per launch)
     peak, peak_src = peaks()
     roof = None
+    gemm = {}
+    for k in list(kern):
+        if k.startswith("rlctr_linear"):
+            n_l, mean_ms, _ = kern.pop(k)
+            fl = sum(gemm_flops(k, m) for _, _, m in prof.records[k]) / n_l
+            gemm[k] = {"launches": n_l, "mean_ms": mean_ms, "fp32_equiv_TFLOPs": fl / (mean_ms / 1e3) / 1e12,
+                       "tensor_pipe_TFLOPs_3x": 3 * fl / (mean_ms / 1e3) / 1e12}
     if kern:
         name = max(kern, key=lambda k: kern[k][0] * kern[k][1])
         n_l, mean_ms, alg = kern[name]
@@ -379,7 +396,7 @@ def b200_arm(args):
         line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D),
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+                "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

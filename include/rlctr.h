@@ -221,6 +221,25 @@ int rlctr_reinforce_loss_bwd(const float* logits, const int64_t* act, const floa
                              float* logp, float* loss, float* dlogits, void* ws,
                              int64_t batch, int32_t actions, int32_t variant, rlctr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * K4  dense layers on the tcgen05 tensor cores (3xTF32 split: fp32-grade accuracy).
+ * nn.Linear of the DeepFM tower (p_model.py:276-293) and of the policy networks
+ * (PG_model.py:42-51, DDQN_model.py:20-52, DDPG_for_PG_model.py:20-81): weight [out,in] row-major,
+ * bias [out], activations [batch, features] row-major (dense, no padding).
+ *   fwd: y = x w^T + bias, ReLU fused if RLCTR_MLP_RELU
+ *   bwd: with RLCTR_MLP_RELU, gy is first masked IN PLACE by (y > 0) (y = the saved forward output);
+ *        dx = gy w (optional), dw = gy^T x (optional, split-K with a fixed-order reduction),
+ *        db = column sums of gy (optional).  ws: rlctr_mlp_ws_bytes(batch, in, out) bytes.
+ * ------------------------------------------------------------------------------------ */
+#define RLCTR_MLP_RELU 1
+size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
+int rlctr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t batch,
+                     int32_t in_dim, int32_t out_dim, int32_t flags, void* ws, size_t ws_bytes,
+                     rlctr_stream_t stream);
+int rlctr_linear_bwd(const float* x, const float* w, const float* y, float* gy, float* dx, float* dw,
+                     float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, void* ws,
+                     size_t ws_bytes, rlctr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

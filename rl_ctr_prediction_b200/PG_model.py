@@ -69,7 +69,7 @@ class Net(nn.Module):
             layers += [_mlp.Linear(input_dims, width, device=device), nn.ReLU(), nn.Dropout(p=0.2)]
             input_dims, width = width, width // 2
         layers.append(_mlp.Linear(input_dims, action_numbers, device=device))
-        self.mlp = nn.Sequential(*layers)
+        self.mlp = _mlp.Tower(*layers)
 
     def logits(self, x):
         return self.mlp(self.embedding_layer.forward(x))

@@ -68,6 +68,9 @@ SIGNATURES = {
     "rlctr_step_advance": (C.c_int, [_P, _I32, _P]),
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "rlctr_mlp_ws_bytes": (_SZ, [_I64, _I32, _I32]),
+    "rlctr_linear_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
+    "rlctr_linear_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
 }
 
 _lib = None

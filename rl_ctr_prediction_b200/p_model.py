@@ -324,7 +324,7 @@ def _tower(in_dims: int, device=None) -> nn.Sequential:
         mods += [_mlp.Linear(d, width, device=device), nn.ReLU(), nn.Dropout(p=0.2)]
         d = width
     mods.append(_mlp.Linear(d, 1, device=device))
-    return nn.Sequential(*mods)
+    return _mlp.Tower(*mods)
 
 
 class DeepFM(FM):

@@ -553,3 +553,64 @@ def test_reinforce_head(lib, golden, variant):
         if variant == 0:
             close(loss, golden[loss_key], rtol=1e-4, atol=2e-5)
             close(dl, golden[dl_key], rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 tcgen05 3xTF32 dense layers
+# ------------------------------------------------------------------------------------------------
+def linear_case(B, K, N, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    return x, w, b
+
+
+@pytest.mark.parametrize("B,K,N", [(1, 150, 300), (128, 32, 16), (1000, 150, 300), (777, 300, 200), (513, 200, 1),
+                                   (4096, 255, 1024), (300, 1024, 512), (65536, 150, 300)])
+@pytest.mark.parametrize("relu", [0, 1])
+def test_linear_fwd_3xtf32(lib, B, K, N, relu):
+    x, w, b = linear_case(B, K, N, B + K + N)
+    y = torch.empty(B, N, device=DEV)
+    assert lib.rlctr_linear_fwd(L().ptr(dev(x)), L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, None, 0, st()) == 0
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    if relu:
+        ref = np.maximum(ref, 0)
+    close(y, ref, rtol=1e-5)                 # fp32-grade: plain TF32 would be ~1e-3
+    # and at least as close to the fp64 truth as fp32 SGEMM is, up to a small factor
+    ref32 = x @ w.T + b
+    if relu:
+        ref32 = np.maximum(ref32, 0)
+    err = np.abs(y.cpu().numpy() - ref).max()
+    err32 = np.abs(ref32 - ref).max()
+    assert err <= max(16 * err32, 2e-6 * np.abs(ref).max()), (err, err32)
+
+
+@pytest.mark.parametrize("B,K,N", [(64, 150, 300), (1000, 150, 300), (777, 300, 200), (513, 200, 1), (65536, 300, 200),
+                                   (4096, 255, 1024)])
+@pytest.mark.parametrize("relu", [0, 1])
+def test_linear_bwd_3xtf32(lib, B, K, N, relu):
+    x, w, b = linear_case(B, K, N, B + K + N + 1)
+    rng = np.random.default_rng(5)
+    gy = rng.standard_normal((B, N)).astype(np.float32)
+    y = np.maximum(x @ w.T + b, 0).astype(np.float32) if relu else None
+    gyd = dev(gy)
+    dx = torch.empty(B, K, device=DEV)
+    dw = torch.empty(N, K, device=DEV)
+    db = torch.empty(N, device=DEV)
+    wsb = lib.rlctr_mlp_ws_bytes(B, K, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_linear_bwd(L().ptr(dev(x)), L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd), L().ptr(dx), L().ptr(dw),
+                                L().ptr(db), B, K, N, relu, L().ptr(ws), wsb, st()) == 0
+    g64 = gy.astype(np.float64)
+    if relu:
+        g64 = g64 * (y > 0)
+    close(dx, g64 @ w.astype(np.float64), rtol=1e-5)
+    close(dw, g64.T @ x.astype(np.float64), rtol=1e-5)
+    close(db, g64.sum(axis=0), rtol=1e-5)
+    # deterministic split-K: bit-identical on a second run
+    dw2 = torch.empty_like(dw)
+    gyd2 = dev(gy)
+    lib.rlctr_linear_bwd(L().ptr(dev(x)), L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd2), None, L().ptr(dw2), None, B, K, N,
+                         relu, L().ptr(ws), wsb, st())
+    assert torch.equal(dw, dw2)

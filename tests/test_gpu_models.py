@@ -47,7 +47,13 @@ def assert_state(model, ref_sd, rtol=2e-5, atol=None):
     assert set(sd.keys()) == set(ref_sd.keys())
     for k, v in ref_sd.items():
         assert tuple(sd[k].shape) == tuple(v.shape), k
-        close(sd[k], v, rtol=rtol, atol=atol)
+        a = atol
+        if k.startswith("mlp.") and atol is None:
+            # Adam normalises each element's update by its own gradient history, so a dense weight whose
+            # gradient is ~0 (rounding-level) moves by an ill-conditioned +-lr per step: two correct fp32
+            # GEMMs (this one, cuBLAS, MKL) disagree there by a few 1e-6 after 3 steps at lr=1e-3.
+            a = max(rtol * float(np.abs(v).max()), 5e-6)
+        close(sd[k], v, rtol=rtol, atol=a)
 
 
 @pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
@@ -243,3 +249,24 @@ def test_large_batch_round_trip_properties():
             opt.step()
         model.flush()
     assert torch.equal(m.table.data, m2.table.data)
+
+
+def test_tower_matches_torch_fp32():
+    """mlp.Tower (tcgen05 3xTF32) vs the same weights in stock torch fp32 on the CPU: output and all gradients."""
+    from rl_ctr_prediction_b200 import p_model
+    torch.manual_seed(3)
+    tower = p_model._tower(150).to(DEV).eval()
+    ref = TP._tower(150)
+    ref.load_state_dict({k: v.cpu() for k, v in tower.state_dict().items()})
+    ref.eval()
+    x = torch.randn(2000, 150)
+    xd = x.to(DEV).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    out, out_ref = tower(xd), ref(xr)
+    close(out, out_ref.detach())
+    g = torch.randn(2000, 1)
+    out.backward(g.to(DEV))
+    out_ref.backward(g)
+    close(xd.grad, xr.grad)
+    for (k, p), (_, q) in zip(tower.named_parameters(), ref.named_parameters()):
+        close(p.grad, q.grad)
