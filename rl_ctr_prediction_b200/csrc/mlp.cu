@@ -43,8 +43,9 @@ constexpr int GEMM_TMEM_COLS = 512;
 struct GemmArgs {
     const float* A; int64_t sam, sak;     // A[m*sam + k*sak]   (one of the two strides is 1)
     const float* B; int64_t sbn, sbk;     // B[n*sbn + k*sbk]
-    int vec_a, vec_b;                     // elements per global vector load along the contiguous dimension (1, 2, 4)
+    int mode_a, mode_b;                   // staging mode: 4/2/1 = k-contiguous, that many fp32 per copy; 0 = row-contiguous
     float* C; int64_t ldc;                // C[(split*M + m)*ldc + n]
+    int cvec;                             // widest aligned vector store for a C row segment (1, 2, 4)
     const float* bias;                    // [N] or null (ignored when splits > 1)
     int M, N, K;
     int n_tile;                           // UMMA N (multiple of 16, <= 256)
@@ -115,76 +116,115 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
     return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2)));
 }
 
-__device__ __forceinline__ void split_store(char* hi, char* lo, uint32_t off, float x) {
-    // hi = x rounded to nearest tf32 (10 explicit mantissa bits): the tensor core then reads it exactly;
-    // lo = x - hi is exact in fp32, |lo| <= 2^-11 |x| with a random sign, and loses only 2^-21 |x| to the
-    // tensor core's own truncation.
-    const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-    *reinterpret_cast<float*>(hi + off) = h;
-    *reinterpret_cast<float*>(lo + off) = x - h;
+// hi = x rounded to nearest tf32 (10 explicit mantissa bits): the tensor core then reads it exactly;
+// lo = x - hi is exact in fp32, |lo| <= 2^-11 |x| with a random sign, and loses only 2^-21 |x| to the
+// tensor core's own truncation.
+__device__ __forceinline__ float tf32_rn(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
-// Stage one operand tile: rows [r0, r0+rows) x k [k0, k0+32) of G[r*sr + k*sk], zero-filled outside (R, K).
-// VEC contiguous elements per global load (along k when KCONTIG, along rows otherwise); LOADS_IN_FLIGHT
-// independent vector loads are issued before any is consumed (latency hiding: the loaders are the
-// producers of a tensor-core pipeline and see full DRAM/L2 latency).
-template <int VEC, bool KCONTIG>
-__device__ __forceinline__ void load_tile_v(const float* __restrict__ G, int64_t sr, int64_t sk, int R, int K, int r0,
-                                            int k0, int rows, char* hi, char* lo, int tid, int nthreads) {
-    constexpr int U = 8;
-    const int per = KCONTIG ? (GEMM_BK / VEC) : (rows / VEC);     // vectors along the contiguous dimension
-    const int nvec = rows * GEMM_BK / VEC;
-    for (int base = tid; base < nvec; base += nthreads * U) {
-        float buf[U][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int v = base + u * nthreads;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) buf[u][e] = 0.f;
-            if (v < nvec) {
-                const int c = v % per, o = v / per;
-                const int r = KCONTIG ? o : c * VEC, k = KCONTIG ? c * VEC : o;
-                const int gr = r0 + r, gk = k0 + k;
-                const float* src = G + (int64_t)gr * sr + (int64_t)gk * sk;
-                const bool full = KCONTIG ? (gr < R && gk + VEC <= K) : (gk < K && gr + VEC <= R);
-                if (full) {
-                    if (VEC == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(src)); buf[u][0] = t.x; buf[u][1] = t.y; buf[u][2 % VEC] = t.z; buf[u][3 % VEC] = t.w; }
-                    else if (VEC == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(src)); buf[u][0] = t.x; buf[u][1 % VEC] = t.y; }
-                    else buf[u][0] = __ldg(src);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const bool ok = KCONTIG ? (gr < R && gk + e < K) : (gk < K && gr + e < R);
-                        if (ok) buf[u][e] = __ldg(src + (KCONTIG ? (int64_t)e * sk : (int64_t)e * sr));
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int v = base + u * nthreads;
-            if (v < nvec) {
-                const int c = v % per, o = v / per;
-                const int r = KCONTIG ? o : c * VEC, k = KCONTIG ? c * VEC : o;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    split_store(hi, lo, KCONTIG ? sw128_off(r, k + e) : sw128_off(r + e, k), buf[u][e]);
-            }
-        }
-    }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void load_tile(const float* __restrict__ G, int64_t sr, int64_t sk, int vec, int R, int K,
-                                          int r0, int k0, int rows, char* hi, char* lo, int tid, int nthreads) {
-    if (sk == 1) {
-        if (vec == 4) load_tile_v<4, true>(G, sr, sk, R, K, r0, k0, rows, hi, lo, tid, nthreads);
-        else if (vec == 2) load_tile_v<2, true>(G, sr, sk, R, K, r0, k0, rows, hi, lo, tid, nthreads);
-        else load_tile_v<1, true>(G, sr, sk, R, K, r0, k0, rows, hi, lo, tid, nthreads);
+// Operand staging, two phases per k-block:
+//   issue  : cp.async (LDGSTS) global -> smem `raw` tile in the swizzled layout, zero-filled outside (R, K);
+//            asynchronous, so PREFETCH k-blocks of copies are in flight per thread with no register cost.
+//            k-contiguous operands: VEC fp32 per copy, a thread keeps its k-chunk and walks rows with constant
+//            strides (no index arithmetic in the loop); row-contiguous operands (dgrad's W^T, wgrad's dY^T and
+//            X): 4-byte copies, lanes along rows, k unrolled.
+//   convert: after cp.async.wait_group + a named barrier over the loader warps, raw -> (hi in place, lo)
+//            with 128-bit shared-memory accesses.
+constexpr int LOADER_THREADS = GEMM_LOADER_WARPS * 32;
+
+template <int VEC>
+__device__ __forceinline__ void tile_issue_k(const float* __restrict__ G, int64_t sr, int R, int K, int r0, int k0,
+                                             int rows, uint32_t raw, int tid) {
+    constexpr int PER = GEMM_BK / VEC;                 // vectors per row
+    constexpr int RSTEP = LOADER_THREADS / PER;        // rows advanced per iteration
+    const int c = tid % PER, rr = tid / PER;
+    const int gk = k0 + c * VEC;
+    const int kvalid = gk < K ? min(K - gk, VEC) : 0;
+    const float* src = G + (int64_t)(r0 + rr) * sr + gk;
+    const int64_t src_step = (int64_t)RSTEP * sr;
+    if (VEC >= 2) {                                    // RSTEP % 8 == 0: the swizzle phase (row & 7) is loop-invariant
+        uint32_t dst = raw + sw128_off(rr, c * VEC);
+        for (int r = rr; r < rows; r += RSTEP) {
+            const int valid = (r0 + r < R) ? kvalid : 0;
+            cp_async<4 * VEC>(dst, valid ? src : G, 4 * valid);
+            dst += RSTEP * 128;
+            src += src_step;
+        }
     } else {
-        if (vec == 4) load_tile_v<4, false>(G, sr, sk, R, K, r0, k0, rows, hi, lo, tid, nthreads);
-        else if (vec == 2) load_tile_v<2, false>(G, sr, sk, R, K, r0, k0, rows, hi, lo, tid, nthreads);
-        else load_tile_v<1, false>(G, sr, sk, R, K, r0, k0, rows, hi, lo, tid, nthreads);
+        for (int r = rr; r < rows; r += RSTEP) {
+            const int valid = (r0 + r < R) ? kvalid : 0;
+            cp_async<4>(raw + sw128_off(r, c), valid ? src : G, 4 * valid);
+            src += src_step;
+        }
     }
+}
+__device__ __forceinline__ void tile_issue_r(const float* __restrict__ G, int64_t sk, int R, int K, int r0, int k0,
+                                             int rows, uint32_t raw, int tid) {
+    for (int r = tid; r < rows; r += LOADER_THREADS) {
+        const bool rok = r0 + r < R;
+        const float* src = G + (r0 + r) + (int64_t)k0 * sk;
+        const uint32_t dst = raw + r * 128;
+        const int r7 = r & 7;
+#pragma unroll
+        for (int k = 0; k < GEMM_BK; ++k) {
+            const bool ok = rok && (k0 + k < K);
+            cp_async<4>(dst + ((((k >> 2) ^ r7) << 4) | ((k & 3) << 2)), ok ? src + (int64_t)k * sk : G, ok ? 4 : 0);
+        }
+    }
+}
+// mode: 4 / 2 / 1 = k-contiguous with that vector width; 0 = row-contiguous
+__device__ __forceinline__ void tile_issue_any(int mode, const float* __restrict__ G, int64_t sr, int64_t sk, int R, int K,
+                                               int r0, int k0, int rows, uint32_t raw, int tid) {
+    if (mode == 4) tile_issue_k<4>(G, sr, R, K, r0, k0, rows, raw, tid);
+    else if (mode == 2) tile_issue_k<2>(G, sr, R, K, r0, k0, rows, raw, tid);
+    else if (mode == 1) tile_issue_k<1>(G, sr, R, K, r0, k0, rows, raw, tid);
+    else tile_issue_r(G, sk, R, K, r0, k0, rows, raw, tid);
+}
+// rows is a multiple of 16: thread tid owns 16-byte chunk (tid % 8) of rows tid/8, tid/8 + 16, ...
+__device__ __forceinline__ void tile_convert(int rows, char* hi, char* lo, int tid) {
+    const int c = tid & 7, rr = tid >> 3;
+    uint32_t off = (uint32_t)(rr * 128 + ((c ^ (rr & 7)) << 4));
+    for (int r = rr; r < rows; r += LOADER_THREADS / 8) {
+        const float4 x = *reinterpret_cast<const float4*>(hi + off);
+        const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        off += (LOADER_THREADS / 8) * 128;
+    }
+}
+
+// walks this CTA's (tile, k-block) work items in order; used twice by the loaders (issue / convert cursors)
+struct ItemCursor {
+    int tile, kb, kb1, mt, nt, stage;
+    uint32_t phase;
+    bool valid;
+};
+__device__ __forceinline__ void cursor_set_tile(ItemCursor& c, const GemmArgs& g, int total_tiles) {
+    const int kb_total = (g.K + GEMM_BK - 1) / GEMM_BK;
+    while (c.tile < total_tiles) {
+        const int split = c.tile / (g.m_tiles * g.n_tiles);
+        const int mn = c.tile - split * (g.m_tiles * g.n_tiles);
+        c.mt = mn / g.n_tiles;
+        c.nt = mn - c.mt * g.n_tiles;
+        c.kb = split * g.kb_per_split;
+        c.kb1 = min(c.kb + g.kb_per_split, kb_total);
+        if (c.kb < c.kb1) { c.valid = true; return; }
+        c.tile += gridDim.x;                                   // empty split: no k-blocks to stage
+    }
+    c.valid = false;
+}
+__device__ __forceinline__ void cursor_next(ItemCursor& c, const GemmArgs& g, int total_tiles) {
+    if (++c.stage == g.stages) { c.stage = 0; c.phase ^= 1; }
+    if (++c.kb >= c.kb1) { c.tile += gridDim.x; cursor_set_tile(c, g, total_tiles); }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -220,26 +260,34 @@ gemm3x_tf32_kernel(const GemmArgs g) {
 
     if (warp < GEMM_LOADER_WARPS) {
         // ================= loaders =================
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int split = tile / (g.m_tiles * g.n_tiles);
-            const int mn = tile - split * (g.m_tiles * g.n_tiles);
-            const int mt = mn / g.n_tiles, nt = mn - mt * g.n_tiles;
-            const int kb0 = split * g.kb_per_split;
-            const int kb_total = (g.K + GEMM_BK - 1) / GEMM_BK;
-            const int kb1 = min(kb0 + g.kb_per_split, kb_total);
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                unsigned char* st = smem + (size_t)stage * stage_bytes;
-                load_tile(g.A, g.sam, g.sak, g.vec_a, g.M, g.K, mt * GEMM_BM, kb * GEMM_BK, GEMM_BM, (char*)st,
-                          (char*)st + a_bytes, threadIdx.x, GEMM_LOADER_WARPS * 32);
-                load_tile(g.B, g.sbn, g.sbk, g.vec_b, g.N, g.K, nt * g.n_tile, kb * GEMM_BK, g.n_tile, (char*)st + 2 * a_bytes,
-                          (char*)st + 2 * a_bytes + b_bytes, threadIdx.x, GEMM_LOADER_WARPS * 32);
-                fence_proxy_async();                   // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(smem_u32(&full_bar[stage]));
-                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        const int tid = threadIdx.x;
+        ItemCursor ci{(int)blockIdx.x, 0, 0, 0, 0, 0, 0u, false}, cc = ci;
+        cursor_set_tile(ci, g, total_tiles);
+        cursor_set_tile(cc, g, total_tiles);
+        const int prefetch = g.stages >= 3 ? 2 : 1;            // k-blocks of copies in flight per thread
+        int lead = 0;                                          // issued - converted
+        while (cc.valid) {
+            if (ci.valid && lead <= prefetch) {
+                mbar_wait(smem_u32(&empty_bar[ci.stage]), ci.phase ^ 1);
+                const uint32_t st = smem_u32(smem + (size_t)ci.stage * stage_bytes);
+                tile_issue_any(g.mode_a, g.A, g.sam, g.sak, g.M, g.K, ci.mt * GEMM_BM, ci.kb * GEMM_BK, GEMM_BM, st, tid);
+                tile_issue_any(g.mode_b, g.B, g.sbn, g.sbk, g.N, g.K, ci.nt * g.n_tile, ci.kb * GEMM_BK, g.n_tile,
+                               st + 2 * a_bytes, tid);
+                cp_async_commit();
+                cursor_next(ci, g, total_tiles);
+                ++lead;
+                if (ci.valid && lead <= prefetch) continue;    // fill the pipeline first
             }
+            // oldest outstanding group of THIS thread has landed once at most (lead-1) newer groups remain
+            if (lead >= 3) cp_async_wait<2>(); else if (lead == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+            asm volatile("bar.sync 1, %0;" ::"n"(LOADER_THREADS) : "memory");     // every loader's copies of this k-block landed
+            char* st = reinterpret_cast<char*>(smem + (size_t)cc.stage * stage_bytes);
+            tile_convert(GEMM_BM, st, st + a_bytes, tid);
+            tile_convert(g.n_tile, st + 2 * a_bytes, st + 2 * a_bytes + b_bytes, tid);
+            fence_proxy_async();                               // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(smem_u32(&full_bar[cc.stage]));
+            cursor_next(cc, g, total_tiles);
+            --lead;
         }
     } else if (warp == GEMM_LOADER_WARPS) {
         // ================= MMA issuer =================
@@ -298,20 +346,32 @@ gemm3x_tf32_kernel(const GemmArgs g) {
             const int m = mt * GEMM_BM + q * 32 + lane;
             float* crow = g.C + ((int64_t)split * g.M + m) * g.ldc;
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+            const bool fuse = g.splits == 1;
             for (int c0 = 0; c0 < g.n_tile; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(taddr + (uint32_t)c0, r);
                 tmem_ld_wait();
-                if (m < g.M) {
+                const int n0 = nt * g.n_tile + c0;
+                if (m < g.M && n0 < g.N) {
+                    float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int n = nt * g.n_tile + c0 + j;
-                        if (n < g.N) {
-                            float v = empty_split ? 0.f : __uint_as_float(r[j]);
-                            if (g.bias && g.splits == 1) v += __ldg(g.bias + n);
-                            if (g.relu && g.splits == 1) v = fmaxf(v, 0.f);
-                            crow[n] = v;
-                        }
+                        float x = empty_split ? 0.f : __uint_as_float(r[j]);
+                        if (fuse && g.bias && n0 + j < g.N) x += __ldg(g.bias + n0 + j);
+                        if (fuse && g.relu) x = fmaxf(x, 0.f);
+                        v[j] = x;
+                    }
+                    float* dst = crow + n0;
+                    if (n0 + 16 <= g.N && g.cvec == 4) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else if (n0 + 16 <= g.N && g.cvec == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < g.N) dst[j] = v[j];
                     }
                 }
             }
@@ -337,8 +397,10 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, in
 
 // column sums of dY [B, N] (the bias gradient), fixed-shape: each block owns 32 columns, 8 warps stride the
 // rows, smem tree over the 8 partials.
+// wt != null: rows are scaled by wt[r] first (dW of a single-output layer: sum_b gy[b] * x[b, :])
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ Y, float* __restrict__ part, int64_t rows, int N, int rows_per_block) {
+colsum_partial_kernel(const float* __restrict__ Y, const float* __restrict__ wt, float* __restrict__ part, int64_t rows,
+                      int N, int rows_per_block) {
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + lane;
@@ -346,7 +408,8 @@ colsum_partial_kernel(const float* __restrict__ Y, float* __restrict__ part, int
     const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
     float s = 0.f;
     if (n < N)
-        for (int64_t r = r0 + w; r < r1; r += 8) s += __ldg(Y + r * N + n);
+#pragma unroll 4
+        for (int64_t r = r0 + w; r < r1; r += 8) s += wt ? __ldg(wt + r) * __ldg(Y + r * N + n) : __ldg(Y + r * N + n);
     red[w][lane] = s;
     __syncthreads();
     if (w == 0) {
@@ -362,6 +425,35 @@ __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const float* g, const float* __restrict__ out, float* dy, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dy[i] = __ldg(out + i) > 0.f ? g[i] : 0.f;
+}
+
+// ---- single-output layer (the tower's last Linear(200,1), p_model.py:290): GEMV-shaped, CUDA cores, HBM-bound
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ y, int64_t rows, int K, int relu) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + r * K + k), __ldg(w + k), s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(RLCTR_FULL, s, off);
+        if (lane == 0) {
+            float v = s + b0;
+            if (relu) v = fmaxf(v, 0.f);
+            y[r] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+outer_rows_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ dx, int64_t rows, int K) {
+    const int64_t total = rows * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K;
+        dx[i] = __ldg(gy + r) * __ldg(w + (int)(i - r * K));
+    }
 }
 
 static int round16(int n) { return (n + 15) / 16 * 16; }
@@ -416,8 +508,9 @@ static int launch_gemm(const float* A, int64_t sam, int64_t sak, const float* B,
     g.M = M; g.N = N; g.K = K;
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages; g.relu = relu;
-    g.vec_a = vec_of(A, sak == 1 ? sam : sak);
-    g.vec_b = vec_of(B, sbk == 1 ? sbn : sbk);
+    g.cvec = vec_of(C, ldc);
+    g.mode_a = sak == 1 ? vec_of(A, sam) : 0;
+    g.mode_b = sbk == 1 ? vec_of(B, sbn) : 0;
     RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total < RLCTR_SMS ? total : RLCTR_SMS;
@@ -426,7 +519,7 @@ static int launch_gemm(const float* A, int64_t sam, int64_t sak, const float* B,
     return RLCTR_OK;
 }
 
-constexpr int COLSUM_ROWS_PER_BLOCK = 4096;
+constexpr int COLSUM_ROWS_PER_BLOCK = 512;
 
 }  // namespace rlctr
 
@@ -436,7 +529,8 @@ extern "C" size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_
     if (batch <= 0 || in_dim <= 0 || out_dim <= 0) return 256;
     GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
     size_t wgrad = (size_t)p.splits * out_dim * in_dim * sizeof(float);
-    size_t colsum = (size_t)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK) * out_dim * sizeof(float);
+    const size_t yb = (size_t)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
+    size_t colsum = yb * ((size_t)out_dim + (out_dim == 1 ? (size_t)in_dim : 0)) * sizeof(float);
     return wgrad + colsum + 512;
 }
 
@@ -447,6 +541,13 @@ extern "C" int rlctr_linear_fwd(const float* x, const float* w, const float* bia
     if (!x || !w || !y || batch < 0 || in_dim <= 0 || out_dim <= 0) return RLCTR_EINVAL;
     if (batch == 0) return RLCTR_OK;
     if (batch > 0x7fffffff) return RLCTR_EUNSUPPORTED;
+    if (out_dim == 1) {
+        int64_t blocks = (batch + 7) / 8;
+        gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, (cudaStream_t)stream>>>(
+            x, w, bias, y, batch, in_dim, (flags & RLCTR_MLP_RELU) ? 1 : 0);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
     GemmPlan p = plan_gemm((int)batch, out_dim, in_dim, false);
     return launch_gemm(x, in_dim, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim,
                        (flags & RLCTR_MLP_RELU) ? 1 : 0, p, (cudaStream_t)stream);
@@ -466,6 +567,35 @@ extern "C" int rlctr_linear_bwd(const float* x, const float* w, const float* y, 
         int grid = (int)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8);
         relu_bwd_kernel<<<grid, 256, 0, st>>>(gy, y, gy, n);
         RLCTR_LAUNCH_CHECK();
+    }
+    if (out_dim == 1) {
+        if (dx) {
+            const int64_t n = batch * in_dim;
+            int64_t blocks = (n + 255) / 256;
+            outer_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(dy, w, dx, batch, in_dim);
+            RLCTR_LAUNCH_CHECK();
+        }
+        if (dw || db) {
+            if (!ws || ws_bytes < rlctr_mlp_ws_bytes(batch, in_dim, out_dim)) return RLCTR_EWORKSPACE;
+            float* part = reinterpret_cast<float*>(ws);
+            const int yb = (int)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
+            if (dw) {
+                dim3 grid((in_dim + 31) / 32, yb);
+                colsum_partial_kernel<<<grid, 256, 0, st>>>(x, dy, part, batch, in_dim, COLSUM_ROWS_PER_BLOCK);
+                RLCTR_LAUNCH_CHECK();
+                splitk_reduce_kernel<<<(in_dim + 255) / 256, 256, 0, st>>>(part, dw, in_dim, yb);
+                RLCTR_LAUNCH_CHECK();
+            }
+            if (db) {
+                float* part2 = part + (size_t)yb * in_dim;
+                dim3 grid(1, yb);
+                colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, nullptr, part2, batch, 1, COLSUM_ROWS_PER_BLOCK);
+                RLCTR_LAUNCH_CHECK();
+                splitk_reduce_kernel<<<1, 256, 0, st>>>(part2, db, 1, yb);
+                RLCTR_LAUNCH_CHECK();
+            }
+        }
+        return RLCTR_OK;
     }
     if (dx) {   // dX[B,in] = dY[B,out] * W[out,in]:  B operand = W^T, n-contiguous
         GemmPlan p = plan_gemm((int)batch, in_dim, out_dim, false);
@@ -496,7 +626,7 @@ extern "C" int rlctr_linear_bwd(const float* x, const float* w, const float* y, 
                                                (((size_t)p.splits * out_dim * in_dim * sizeof(float) + 255) & ~(size_t)255));
         const int yb = (int)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
         dim3 grid((out_dim + 31) / 32, yb);
-        colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, part, batch, out_dim, COLSUM_ROWS_PER_BLOCK);
+        colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, nullptr, part, batch, out_dim, COLSUM_ROWS_PER_BLOCK);
         RLCTR_LAUNCH_CHECK();
         splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(part, db, out_dim, yb);
         RLCTR_LAUNCH_CHECK();
