@@ -94,16 +94,48 @@ __device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g,
     p = p + (-step_size) * m / denom;                   // addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-// replay the L2-only steps (from, to] a row missed (g = wd*p): what dense Adam does to an
-// untouched row every step.  sched[t] = (step_size_t, bc2_sqrt_t).
+// ---- the L2-only step (g = wd*p): what dense Adam does to a row no sample touched ----------
+// These steps are replayed by the million (every row, every step), so they are the one place where the
+// IEEE sqrt and divisions are replaced by the SFU approximations: sqrt(v) = v * rsqrt(v) and a / d =
+// a * rcp(d) (about 2 ulp each).  The perturbation is ~2e-7 of an update of size ~lr, i.e. ~1e-10 per
+// step on parameters of size ~0.1 -- far inside the 1e-5 parity bar -- and it does not accumulate
+// faster than sqrt(steps).  Steps that carry a data gradient keep the exact formula (adam_elem).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void adam_l2_elem(float& p, float& m, float& v, const AdamHyper& h, float step_size,
+                                             float inv_bc2_sqrt) {
+    const float g = h.wd * p;
+    m = fmaf(h.omb1, g - m, m);
+    v = fmaf(h.omb2 * g, g, v * h.beta2);
+    const float sq = v > 0.f ? v * rsqrt_approx(v) : 0.f;
+    const float denom = fmaf(sq, inv_bc2_sqrt, h.eps);
+    p = fmaf(-step_size * m, rcp_approx(denom), p);
+}
+__device__ __forceinline__ void adam_l2_step4(float4& p, float4& m, float4& v, float2 s, const AdamHyper& h) {
+    const float ib = rcp_approx(s.y);
+    adam_l2_elem(p.x, m.x, v.x, h, s.x, ib);
+    adam_l2_elem(p.y, m.y, v.y, h, s.x, ib);
+    adam_l2_elem(p.z, m.z, v.z, h, s.x, ib);
+    adam_l2_elem(p.w, m.w, v.w, h, s.x, ib);
+}
+// replay the L2-only steps (from, to] a row missed.  sched[t] = (step_size_t, bc2_sqrt_t).
 __device__ __forceinline__ void adam_replay4(float4& p, float4& m, float4& v, int from, int to,
                                              const float2* __restrict__ sched, const AdamHyper& h) {
+    for (int t = from + 1; t <= to; ++t) adam_l2_step4(p, m, v, __ldg(&sched[t]), h);
+}
+__device__ __forceinline__ void adam_replay1(float& p, float& m, float& v, int from, int to,
+                                             const float2* __restrict__ sched, const AdamHyper& h) {
     for (int t = from + 1; t <= to; ++t) {
-        float2 s = __ldg(&sched[t]);
-        adam_elem(p.x, m.x, v.x, 0.f, h, s.x, s.y);
-        adam_elem(p.y, m.y, v.y, 0.f, h, s.x, s.y);
-        adam_elem(p.z, m.z, v.z, 0.f, h, s.x, s.y);
-        adam_elem(p.w, m.w, v.w, 0.f, h, s.x, s.y);
+        const float2 s = __ldg(&sched[t]);
+        adam_l2_elem(p, m, v, h, s.x, rcp_approx(s.y));
     }
 }
 

@@ -256,78 +256,83 @@ rows_wide_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
         if (lane == 0) a.stamp[id] = step;
     }
 }
-__global__ void __launch_bounds__(256)
-rows_catchup_wide_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= n) return;
-    const uint32_t id = __ldg(sorted_ids + k);
-    if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
-    const int upto = __ldg(a.step);
-    const int st = a.stamp[id];
+// ---- replay kernels (lazy-exact mode) -------------------------------------------------------------------
+// Work items are 16-byte row chunks; every item needs a DIFFERENT number of replay steps (its row's
+// staleness), so a one-item-per-thread mapping leaves most lanes of a warp idle while the stalest one
+// finishes.  Here each LANE walks its own queue of items: it replays one step per loop iteration and, the
+// moment its item is done, stores it and switches to the next one, which was prefetched into registers
+// while the current one was being replayed.  Lanes never wait for each other's items.
+struct ReplayItem {
+    float4 p, m, v;
+    int64_t off;         // float offset of the chunk (-1: nothing to do)
+    int t;               // steps already applied
+};
+// FLUSH: items are all chunks of rows [r0, r1).  CATCHUP: items are (sorted position, chunk); only run heads count.
+template <bool CATCHUP>
+__device__ __forceinline__ void replay_fetch(ReplayItem& it, int64_t k, int c, int64_t n_items, const TableView& t,
+                                             const AdamView& a, int64_t r0, const uint32_t* __restrict__ sorted_ids,
+                                             int upto) {
+    it.off = -1;
+    it.t = upto;
+    if (k >= n_items) return;
+    int64_t row;
+    if (CATCHUP) {
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
+        row = id;
+    } else {
+        row = r0 + k;
+    }
+    const int st = __ldg(a.stamp + row);
     if (st >= upto) return;
-    const int chunks = t.rs >> 2;
-    for (int c = lane; c < chunks; c += 32) {
-        const int64_t off = (int64_t)id * t.rs + 4 * c;
-        float4 p = ld4(t.data + off), m = ld4(a.m + off), v = ld4(a.v + off);
-        adam_replay4(p, m, v, st, upto, a.sched, a.h);
-        st4(t.data + off, p);
-        st4(a.m + off, m);
-        st4(a.v + off, v);
-    }
-    __syncwarp();
-    if (lane == 0) a.stamp[id] = upto;
+    it.t = st;
+    it.off = row * t.rs + 4 * c;
+    it.p = ld4(t.data + it.off);
+    it.m = ld4(a.m + it.off);
+    it.v = ld4(a.v + it.off);
 }
-
-// lazy mode: bring the distinct ids of the batch up to step-1 before the forward reads them
-template <int LPR>
+template <bool CATCHUP>
 __global__ void __launch_bounds__(256)
-rows_catchup_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
-    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t k = gt / LPR;
-    const int c = (int)(gt % LPR), col0 = 4 * c;
-    bool work = false;
-    uint32_t id = 0;
-    if (k < n) {
-        id = __ldg(sorted_ids + k);
-        work = (id < (uint64_t)t.n_rows) && (k == 0 || __ldg(sorted_ids + k - 1) != id) && col0 < t.rs;
-    }
+replay_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
+    const int chunks = t.rs >> 2;
+    const uint32_t stride = gridDim.x * blockDim.x;       // items (chunks) between two items of one lane
+    const uint32_t dk = stride / chunks, dc = stride % chunks;
     const int upto = __ldg(a.step);
-    bool stale = false;
-    if (work) {
-        const int st = a.stamp[id];
-        stale = st < upto;
-        if (stale) {
-            const int64_t off = (int64_t)id * t.rs + col0;
-            float4 p = ld4(t.data + off), m = ld4(a.m + off), v = ld4(a.v + off);
-            adam_replay4(p, m, v, st, upto, a.sched, a.h);
-            st4(t.data + off, p);
-            st4(a.m + off, m);
-            st4(a.v + off, v);
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t k = i0 / chunks;                              // (k, c) = item index / chunks, % chunks, advanced incrementally
+    int c = (int)(i0 % chunks);
+    ReplayItem cur, nxt;
+    replay_fetch<CATCHUP>(cur, k, c, n_items, t, a, r0, sorted_ids, upto);
+    bool cur_real = k < n_items;
+    k += dk; c += dc; if (c >= chunks) { c -= chunks; ++k; }
+    replay_fetch<CATCHUP>(nxt, k, c, n_items, t, a, r0, sorted_ids, upto);
+    while (true) {
+        if (cur.t >= upto) {                             // current item finished (or was nothing to do): switch
+            if (cur.off >= 0) {
+                st4(t.data + cur.off, cur.p);
+                st4(a.m + cur.off, cur.m);
+                st4(a.v + cur.off, cur.v);
+            }
+            if (!cur_real) break;                        // ran past the end of the queue: this lane is done
+            cur = nxt;
+            cur_real = k < n_items;
+            k += dk; c += dc; if (c >= chunks) { c -= chunks; ++k; }
+            replay_fetch<CATCHUP>(nxt, k, c, n_items, t, a, r0, sorted_ids, upto);
+            continue;
         }
+        ++cur.t;
+        adam_l2_step4(cur.p, cur.m, cur.v, __ldg(&a.sched[cur.t]), a.h);
     }
-    __syncwarp();
-    if (stale && c == 0) a.stamp[id] = upto;
 }
-
-// streaming pass over rows [r0,r1): replay the steps each row missed up to *step.  Coalesced
-// float4 traffic: 3 reads + 3 writes of the table-sized arrays at most (stamps set by the
-// companion fill kernel because the chunks of one row may sit in different warps).
+// stamps are written after the replay kernel has completed (the chunks of one row are replayed by
+// different threads, each of which reads the row's stamp)
 __global__ void __launch_bounds__(256)
-adam_flush_kernel(TableView t, AdamView a, int64_t r0, int64_t r1) {
-    const int chunks = t.rs >> 2;
-    const int64_t total = (r1 - r0) * chunks;
-    const int upto = __ldg(a.step);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = r0 + i / chunks;
-        const int st = __ldg(a.stamp + row);
-        if (st >= upto) continue;
-        const int64_t off = row * t.rs + 4 * (i % chunks);
-        float4 p = ld4(t.data + off), m = ld4(a.m + off), v = ld4(a.v + off);
-        adam_replay4(p, m, v, st, upto, a.sched, a.h);
-        st4(t.data + off, p);
-        st4(a.m + off, m);
-        st4(a.v + off, v);
+catchup_stamp_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, int64_t n_rows, int32_t* __restrict__ stamp,
+                     const int32_t* __restrict__ step) {
+    const int upto = __ldg(step);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (id < (uint64_t)n_rows && (k == 0 || __ldg(sorted_ids + k - 1) != id)) stamp[id] = upto;
     }
 }
 __global__ void __launch_bounds__(256)
@@ -337,10 +342,7 @@ adam_flush_scalar_kernel(TableView t, AdamView a, int64_t r0, int64_t r1) {   //
         const int st = a.stamp[row];
         if (st >= upto) continue;
         float p = t.data[row], m = a.m[row], v = a.v[row];
-        for (int s = st + 1; s <= upto; ++s) {
-            const float2 sc = __ldg(&a.sched[s]);
-            adam_elem(p, m, v, 0.f, a.h, sc.x, sc.y);
-        }
+        adam_replay1(p, m, v, st, upto, a.sched, a.h);
         t.data[row] = p; a.m[row] = m; a.v[row] = v;
         a.stamp[row] = upto;
     }
@@ -377,10 +379,7 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     float p = t.data[id], m = a.m[id], v = a.v[id];
     if (a.stamp) {
         const int st = a.stamp[id];
-        for (int s = st + 1; s <= step - 1; ++s) {
-            const float2 sc = __ldg(&a.sched[s]);
-            adam_elem(p, m, v, 0.f, a.h, sc.x, sc.y);
-        }
+        adam_replay1(p, m, v, st, step - 1, a.sched, a.h);
         a.stamp[id] = step;
     }
     const float2 sc = __ldg(&a.sched[step]);
@@ -397,10 +396,7 @@ rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, T
     const int st = a.stamp[id];
     if (st >= upto) return;
     float p = t.data[id], m = a.m[id], v = a.v[id];
-    for (int s = st + 1; s <= upto; ++s) {
-        const float2 sc = __ldg(&a.sched[s]);
-        adam_elem(p, m, v, 0.f, a.h, sc.x, sc.y);
-    }
+    adam_replay1(p, m, v, st, upto, a.sched, a.h);
     t.data[id] = p; a.m[id] = m; a.v[id] = v;
     a.stamp[id] = upto;
 }
@@ -542,20 +538,10 @@ extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const r
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
     }
-    if (t.rs % 4 != 0 || t.rs > 128 * WCH) return RLCTR_EUNSUPPORTED;
-    if (t.rs > 32) {
-        rows_catchup_wide_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(sorted_ids, n, t, a);
-        RLCTR_LAUNCH_CHECK();
-        return RLCTR_OK;
-    }
-    const int lpr = rlctr_lanes_per_row(t.rs);
-    const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
-    switch (lpr) {
-        case 1: rows_catchup_kernel<1><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
-        case 2: rows_catchup_kernel<2><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
-        case 4: rows_catchup_kernel<4><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
-        default: rows_catchup_kernel<8><<<blocks, 256, 0, st>>>(sorted_ids, n, t, a); break;
-    }
+    if (t.rs % 4 != 0) return RLCTR_EUNSUPPORTED;
+    replay_kernel<true><<<grid_1d(n * (t.rs / 4), RLCTR_SMS * 8), 256, 0, st>>>(t, a, 0, n, sorted_ids);
+    RLCTR_LAUNCH_CHECK();
+    catchup_stamp_kernel<<<grid_1d(n, RLCTR_SMS * 8), 256, 0, st>>>(sorted_ids, n, t.n_rows, a.stamp, a.step);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
@@ -574,7 +560,8 @@ extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
         return RLCTR_OK;
     }
     if (t.rs % 4 != 0) return RLCTR_EUNSUPPORTED;
-    adam_flush_kernel<<<grid_1d((row_end - row_begin) * (t.rs / 4), RLCTR_SMS * 8), 256, 0, st>>>(t, a, row_begin, row_end);
+    replay_kernel<false><<<grid_1d((row_end - row_begin) * (t.rs / 4), RLCTR_SMS * 8), 256, 0, st>>>(
+        t, a, row_begin, row_end - row_begin, nullptr);
     RLCTR_LAUNCH_CHECK();
     stamp_fill_kernel<<<grid_1d(row_end - row_begin, RLCTR_SMS * 8), 256, 0, st>>>(a.stamp, a.step, row_begin, row_end);
     RLCTR_LAUNCH_CHECK();

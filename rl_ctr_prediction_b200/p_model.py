@@ -41,8 +41,25 @@ def _check_ids(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous()
 
 
+_SORT_CACHE = {"key": None, "x": None, "out": None}
+
+
 def sort_ids(x: torch.Tensor, n_rows: int):
-    """(sorted_ids u32[n], sorted_slots u32[n]) of the flattened ids: rlctr_sort_ids."""
+    """(sorted_ids u32[n], sorted_slots u32[n]) of the flattened ids: rlctr_sort_ids.
+
+    One batch usually feeds several models (LR, FM, DeepFM... train on the same features, and the RL
+    step scores M models on them): the sorted view of a batch is computed once and shared while the SAME
+    tensor object (unmodified: same ``_version``) is presented again for a table of the same height.  The
+    cache keeps that tensor alive, so its storage cannot be recycled under the key."""
+    key = (id(x), x._version, x.data_ptr(), tuple(x.shape), int(n_rows))
+    if _SORT_CACHE["key"] == key and _SORT_CACHE["x"] is x:
+        return _SORT_CACHE["out"]
+    out = _sort_ids(x, n_rows)
+    _SORT_CACHE.update(key=key, x=x, out=out)
+    return out
+
+
+def _sort_ids(x: torch.Tensor, n_rows: int):
     lib = _lib.load()
     n = x.numel()
     dev = x.device
