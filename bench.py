@@ -228,9 +228,12 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(B, N, D):
+def workload_config(B, N, D, world=1):
     return {"workload": "C2: LR+FM+DeepFM train step (fwd, BCE, bwd, Adam lr=1e-3 wd=1e-5, reference dense-Adam "
-                        "numerics) on one batch", "batch": B, "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
+                        "numerics) on one batch" + ("" if world == 1 else f"; tables row-sharded over {world} GPUs "
+                        "(id mod G), 3 NCCL all-to-alls per model step, dense grads all-reduced"),
+            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "single GPU" if world == 1 else f"dp{world} x row-sharded tables",
+            "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
             "ids": "uniform over disjoint per-field ranges", "l2": "inputs larger than L2: 3 tables x 3 arrays x "
             f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step"}
 
@@ -258,8 +261,12 @@ def b200_arm(args):
     def build_models():
         ms = []
         for name in MODELS:
-            m = {"LR": lambda: p_model.LR(N, device=dev), "FM": lambda: p_model.FM(N, D, device=dev),
-                 "DeepFM": lambda: p_model.DeepFM(N, F_FIELDS, D, device=dev)}[name]()
+            if world > 1:      # BASELINE.json configs[3]: tables row-sharded over the GPUs, NCCL all-to-all
+                from rl_ctr_prediction_b200 import sharded
+                m = sharded.ShardedCTR(name, N, F_FIELDS, D, device=dev)
+            else:
+                m = {"LR": lambda: p_model.LR(N, device=dev), "FM": lambda: p_model.FM(N, D, device=dev),
+                     "DeepFM": lambda: p_model.DeepFM(N, F_FIELDS, D, device=dev)}[name]()
             with torch.no_grad():
                 m.table.mul_(0.1)
             m.train()
@@ -271,7 +278,9 @@ def b200_arm(args):
     def step(ms, x, y):
         out = []
         for m, opt in ms:
-            if isinstance(m, p_model.DeepFM):
+            if world > 1:
+                tl = m.train_step(x, y, opt)
+            elif isinstance(m, p_model.DeepFM):
                 p = m(x)
                 tl = lossf(p, y.unsqueeze(1).float())
                 m.zero_grad()
@@ -355,6 +364,9 @@ def b200_arm(args):
             y = torch.unsqueeze(yh, 1).to(dev, non_blocking=True)
             total = 0.0
             for m, opt in ms:
+                if world > 1:
+                    total += m.train_step(x, yh.to(dev, non_blocking=True), opt).item()
+                    continue
                 p = m(x)                                   # src/main/pretrain_main.py:96-103, per model
                 tl = lossf(p, y.float())
                 m.zero_grad()
@@ -395,7 +407,7 @@ def b200_arm(args):
     if rank == 0:
         line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world),
                 "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line))
     if world > 1:

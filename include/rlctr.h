@@ -240,6 +240,22 @@ int rlctr_linear_bwd(const float* x, const float* w, const float* y, float* gy, 
                      float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, void* ws,
                      size_t ws_bytes, rlctr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU row sharding (no counterpart in the reference, which is single-device: SURVEY section 8e).
+ * owner(id) = id mod world, local_row(id) = id div world.  Groups the n ids of a local batch by
+ * owner, stably:
+ *   send_local[k]   local row (at its owner) of the k-th element of the send buffer (-1: out of range)
+ *   send_slots[k]   position in `ids` of that element
+ *   pos_of_slot[i]  position in the send buffer of ids[i]   (the inverse permutation, int64 so it can be
+ *                   fed back as the `ids` of rlctr_embed_fwd over the received rows)
+ *   bucket_ends[o]  end offset of owner o's bucket in the send buffer, -1 if the bucket is empty
+ * The all-to-all exchanges themselves are NCCL calls made by the host on these buffers.
+ * ------------------------------------------------------------------------------------ */
+size_t rlctr_bucket_ws_bytes(int64_t n, int32_t world);
+int rlctr_bucket_by_owner(const int64_t* ids, int64_t n, int32_t world, int64_t n_rows, int64_t* send_local,
+                          int64_t* pos_of_slot, uint32_t* send_slots, int64_t* bucket_ends, void* ws,
+                          size_t ws_bytes, rlctr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,8 @@ SIGNATURES = {
     "rlctr_mlp_ws_bytes": (_SZ, [_I64, _I32, _I32]),
     "rlctr_linear_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
     "rlctr_linear_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
+    "rlctr_bucket_ws_bytes": (_SZ, [_I64, _I32]),
+    "rlctr_bucket_by_owner": (C.c_int, [_P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 
 _lib = None

@@ -1,0 +1,87 @@
+// shard.cu -- multi-GPU row sharding: route the ids of a local batch to the ranks that own their rows.
+//
+// Tables are row-sharded over G ranks: owner(id) = id mod G, local_row(id) = id div G (modulo balances the
+// Zipf heads of the real vocabularies).  rlctr_bucket_by_owner groups the n = B*F ids of
+// the local batch by owner, STABLY (slot order inside a bucket), so that the owner-side segmented reduction
+// sums the row gradients in a fixed order and the whole sharded step is bit-identical from run to run.
+// The all-to-all itself is NCCL (torch.distributed) on the buffers this kernel lays out.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace rlctr {
+
+__global__ void __launch_bounds__(256)
+owner_keys_kernel(const int64_t* __restrict__ ids, int64_t n, int world, int64_t n_rows, uint32_t* __restrict__ keys,
+                  uint32_t* __restrict__ vals) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = __ldg(ids + i);
+        // out-of-range ids go to rank 0 with an out-of-range local row: gathered as a zero row, never updated
+        keys[i] = ((uint64_t)id < (uint64_t)n_rows) ? (uint32_t)(id % world) : 0u;
+        vals[i] = (uint32_t)i;
+    }
+}
+__global__ void __launch_bounds__(256)
+owner_pack_kernel(const int64_t* __restrict__ ids, int64_t n, int world, int64_t n_rows,
+                  const uint32_t* __restrict__ sorted_owner, const uint32_t* __restrict__ sorted_slots,
+                  int64_t* __restrict__ send_local, int64_t* __restrict__ pos_of_slot, int64_t* __restrict__ counts) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = __ldg(sorted_slots + k);
+        const int64_t id = __ldg(ids + slot);
+        send_local[k] = ((uint64_t)id < (uint64_t)n_rows) ? id / world : (int64_t)-1;
+        pos_of_slot[slot] = k;
+        const uint32_t o = __ldg(sorted_owner + k);
+        if (k == n - 1 || __ldg(sorted_owner + k + 1) != o) {          // last element of bucket o
+            // bucket o ends at k+1; starts are recovered on the host side as a difference of ends
+            counts[o] = k + 1;
+        }
+    }
+}
+static inline int bits_for(int world) {
+    int b = 1;
+    while ((1 << b) < world) ++b;
+    return b;
+}
+
+}  // namespace rlctr
+
+using namespace rlctr;
+
+extern "C" size_t rlctr_bucket_ws_bytes(int64_t n, int32_t world) {
+    if (n <= 0) return 256;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, n, 0, bits_for(world));
+    size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    return 3 * arr + temp + 256;
+}
+
+extern "C" int rlctr_bucket_by_owner(const int64_t* ids, int64_t n, int32_t world, int64_t n_rows, int64_t* send_local,
+                                     int64_t* pos_of_slot, uint32_t* send_slots, int64_t* bucket_ends, void* ws,
+                                     size_t ws_bytes, rlctr_stream_t stream) {
+    if (!ids || !send_local || !pos_of_slot || !send_slots || !bucket_ends || !ws || n < 0 || world < 1 || n_rows <= 0)
+        return RLCTR_EINVAL;
+    if (n >= ((int64_t)1 << 32) || world > 1024) return RLCTR_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    // bucket_ends[o] = end offset of bucket o in the send buffer; empty buckets are filled in by the caller
+    // from the preceding end (initialise to -1 here)
+    RLCTR_CUDA(cudaMemsetAsync(bucket_ends, 0xff, sizeof(int64_t) * world, st));
+    if (n == 0) return RLCTR_OK;
+    size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    if (ws_bytes < rlctr_bucket_ws_bytes(n, world)) return RLCTR_EWORKSPACE;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ws);
+    uint32_t* vals = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + arr);
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 2 * arr);
+    void* temp = reinterpret_cast<char*>(ws) + 3 * arr;
+    size_t temp_bytes = ws_bytes - 3 * arr;
+    int64_t blocks = (n + 255) / 256;
+    int grid = (int)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8);
+    owner_keys_kernel<<<grid, 256, 0, st>>>(ids, n, world, n_rows, keys, vals);
+    RLCTR_LAUNCH_CHECK();
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, skeys, vals, send_slots, n, 0, bits_for(world), st);
+    if (e != cudaSuccess) return (int)e;
+    RLCTR_COUNT_LAUNCH(3);
+    owner_pack_kernel<<<grid, 256, 0, st>>>(ids, n, world, n_rows, skeys, send_slots, send_local, pos_of_slot, bucket_ends);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""1-vs-G equivalence of the sharded path on real GPUs (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tests/dist_check.py
+
+Every rank builds the same single-GPU model, shards it, trains G ranks x local batch B/G for a few steps,
+and compares the gathered tables / dense parameters with the single-GPU model trained on the concatenated
+global batch.  Prints one JSON line per model; exits non-zero on mismatch."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rl_ctr_prediction_b200 import optim, pretrain_main as PM, sharded  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    N, F, D, B, STEPS = 5003, 15, 10, 256 * world, 4
+    ok = True
+    for name in ("LR", "FM", "FFM", "DeepFM"):
+        torch.manual_seed(7)
+        single = PM.get_model(name, N, F, D)
+        with torch.no_grad():
+            single.table.mul_(0.1)
+        single.to(dev).eval()
+        m = sharded.ShardedCTR.from_model(single)
+        m.eval()
+        opt_s = optim.Adam(single.parameters(), lr=1e-3, weight_decay=1e-5)
+        opt_m = optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
+        rng = np.random.default_rng(11)
+        lossf = torch.nn.BCELoss()
+        for s in range(STEPS):
+            x = torch.as_tensor(rng.integers(0, N, size=(B, F))).to(dev)
+            y = torch.as_tensor((rng.random(B) < 0.3).astype(np.int64)).to(dev)
+            p = single(x)
+            tl = lossf(p, y.unsqueeze(1).float())
+            single.zero_grad()
+            tl.backward()
+            opt_s.step()
+            lo, hi = rank * (B // world), (rank + 1) * (B // world)
+            m.train_step(x[lo:hi].contiguous(), y[lo:hi].contiguous(), opt_m)
+        single.flush()
+        full = m.gather_table()
+        scale = single.table.data.abs().max().item()
+        err = (full - single.table.data).abs().max().item() / scale
+        errs = {"table": err, "bias": (m.bias.data - single.bias.data).abs().max().item()}
+        if m.mlp is not None:
+            for (k, a), (_, b) in zip(m.mlp.state_dict().items(), single.mlp.state_dict().items()):
+                errs["mlp." + k] = ((a - b).abs().max() / b.abs().max()).item()
+        good = all(v <= 2e-5 for v in errs.values())
+        ok = ok and good
+        if rank == 0:
+            print(json.dumps({"model": name, "world": world, "ok": good, "max_rel_err_vs_single_gpu": errs}))
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

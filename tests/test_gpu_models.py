@@ -270,3 +270,42 @@ def test_tower_matches_torch_fp32():
     close(xd.grad, xr.grad)
     for (k, p), (_, q) in zip(tower.named_parameters(), ref.named_parameters()):
         close(p.grad, q.grad)
+
+
+@pytest.fixture(scope="module")
+def single_rank_group():
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        import socket
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                device_id=torch.device(DEV))
+    yield None
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
+def test_sharded_world1_equals_single_gpu(golden, name, single_rank_group):
+    """The sharded path (bucket -> all-to-all -> owner gather -> interaction over received rows -> row
+    gradients back -> owner-side Adam) at world_size 1 takes the same steps as the single-GPU model --
+    and therefore as the reference (golden trajectory)."""
+    from rl_ctr_prediction_b200 import optim, sharded
+    sd = state_from_golden(golden, f"train/{name}/init")
+    single = load(build(name, 255), sd).to(DEV)
+    m = sharded.ShardedCTR.from_model(single)
+    m.eval()                                               # dropout off, as in the golden trajectories
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
+    for s in range(3):
+        x = torch.as_tensor(golden["train/x"][s]).to(DEV)
+        y = torch.as_tensor(golden["train/y"][s]).to(DEV)
+        with torch.no_grad():
+            close(m(x), golden[f"train/{name}/pctr{s}"])
+        tl = m.train_step(x, y, opt)
+        close(tl, golden[f"train/{name}/loss{s}"])
+    full = m.gather_table()
+    single.table.data.copy_(full)
+    single.bias.data.copy_(m.bias.data)
+    if m.mlp is not None:
+        single.mlp.load_state_dict(m.mlp.state_dict())
+    assert_state(single, state_from_golden(golden, f"train/{name}/final"))
