@@ -81,6 +81,12 @@ def alg_bytes(key, m):
         return m["n_rows"] * (24.0 * m["rs"] + 8.0)
     if name in ("rlctr_linear_fwd", "rlctr_linear_bwd"):
         return 0.0                                             # tensor-bound: reported in FLOP/s (gemm_flops)
+    if name == "rlctr_bucket_by_owner":
+        return 28.0 * m["n"]                                   # read int64 id; write int64 local row, int64 pos, u32 slot
+    if name == "rlctr_gather_rows":
+        return m["n"] * (8.0 + 8.0 * m["rs"])                  # id + row read + row write
+    if "B" not in m:
+        return 0.0
     B, F, N = m["B"], m["F"], m["n_rows"]
     logical = (m["dim"] + (1 if m["lin"] else 0)) if m["rs"] > 1 else 1
     n = B * F
@@ -93,7 +99,11 @@ def alg_bytes(key, m):
         if m.get("rows"):
             b += n * m["dim"] * 4
         return float(b)
+    if name == "rlctr_rows_grad_dense":
+        return float(n * (4 * logical * 2 + 8) + B * 4 * (1 + logical))
     if name == "rlctr_rows_adam":
+        if m["model"].startswith("Sharded"):                   # owner side: n = rows received, gradients staged
+            return float(U * 24 * logical + n * (8 + 4 * logical) + (U * 8 if m.get("stamp") else 0))
         b = U * 24 * logical + n * 8 + B * 4
         if m["model"] in ("FM", "DeepFM"):
             b += B * 4 * logical                               # saved column sums
