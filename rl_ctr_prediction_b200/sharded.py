@@ -62,7 +62,24 @@ class CudaBackend:
 
 
 class ExchangePlan:
-    __slots__ = ("n", "send_local", "pos_of_slot", "send_slots", "send_counts", "recv_counts", "recv_local", "n_recv")
+    __slots__ = ("n", "send_local", "pos_of_slot", "send_slots", "send_counts", "recv_counts", "recv_local", "n_recv",
+                 "sorted_recv")
+
+
+_PLAN_CACHE = {"key": None, "x": None, "plan": None}
+
+
+def cached_exchange_plan(x, n_rows, group, backend) -> ExchangePlan:
+    """Models that consume the same batch and shard the same vocabulary the same way (LR, FM, DeepFM...
+    over one feature space) share the id exchange: the bucketing, the count exchange with its host
+    synchronisation and the id all-to-all run once per batch, not once per model.  Keyed on the identity
+    of the (unmodified) features tensor, which the cache keeps alive."""
+    key = (id(x), x._version, x.data_ptr(), tuple(x.shape), int(n_rows), id(group))
+    if _PLAN_CACHE["key"] == key and _PLAN_CACHE["x"] is x:
+        return _PLAN_CACHE["plan"]
+    plan = exchange_plan(x, n_rows, group, backend)
+    _PLAN_CACHE.update(key=key, x=x, plan=plan)
+    return plan
 
 
 def _counts_from_ends(ends_host, n):
@@ -91,6 +108,7 @@ def exchange_plan(ids, n_rows, group, backend) -> ExchangePlan:
     p.n_recv = int(sum(p.recv_counts))
     p.recv_local = torch.empty(p.n_recv, dtype=torch.int64, device=flat.device)
     dist.all_to_all_single(p.recv_local, p.send_local, p.recv_counts, p.send_counts, group=group)
+    p.sorted_recv = None
     return p
 
 
@@ -210,10 +228,12 @@ class ShardedCTR(nn.Module):
     # ---- the step ---------------------------------------------------------------------------------
     def _lookup(self, x, train):
         lib = _lib.load()
-        plan = exchange_plan(x, self.feature_nums, self.group, self.backend)
+        plan = cached_exchange_plan(x, self.feature_nums, self.group, self.backend)
         sorted_pair = None
         if train:
-            sorted_pair = Model._sort_ids(plan.recv_local, self._geom.n_rows) if plan.n_recv else None
+            if plan.n_recv and (plan.sorted_recv is None or plan.sorted_recv[0] != self._geom.n_rows):
+                plan.sorted_recv = (self._geom.n_rows, Model._sort_ids(plan.recv_local, self._geom.n_rows))
+            sorted_pair = plan.sorted_recv[1] if plan.n_recv else None
             opt = self._opt
             if sorted_pair is not None and opt is not None and opt.stamp is not None and opt.dirty:
                 t, a = table_struct(self.table.data, self._geom), opt.struct()

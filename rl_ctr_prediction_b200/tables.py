@@ -5,7 +5,7 @@ F of them) and gathers each separately (src/models/p_model.py:14,34,38,69,76-78,
 one id owns ONE 16-byte aligned row (include/rlctr.h "fused row"):
 
     LR      [w]                                   row_stride 1
-    FM      [w, v_0 .. v_{D-1}, pad]              row_stride = round4(1 + D)
+    FM      [w, v_0 .. v_{D-1}, pad]              row_stride = 16 floats (one 64 B DRAM block) for D <= 15
     FFM     [T_0 | T_1 | .. | T_{F-1} | w | pad]  row_stride = round4(F*D + 1)
 
 so a field costs one aligned 128-bit-chunked read instead of two (or F+1) sector-straddling ones.
@@ -25,6 +25,16 @@ def round4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def row_floats(used: int) -> int:
+    """Floats per fused row.  Rows that fit in 64 bytes are padded to exactly 64 B and are therefore
+    64-byte aligned: ncu shows HBM serves a random access in 64 B blocks (two 32 B sectors), so a 48 B row at
+    a 48 B pitch straddles two blocks two times out of three and costs ~107 B of DRAM traffic per access
+    (profiles/r1_ncu_top_kernels.md); a 64 B row costs exactly 64.  Wider rows span several blocks anyway
+    and only keep the 16 B alignment the 128-bit loads need."""
+    n = round4(used)
+    return 16 if n <= 16 else n
+
+
 @dataclass(frozen=True)
 class Geometry:
     n_rows: int
@@ -40,8 +50,8 @@ class Geometry:
     @staticmethod
     def fm(n, d, with_linear=True):
         if with_linear:
-            return Geometry(n, round4(1 + d), 0, 1, d)
-        return Geometry(n, round4(d), -1, 0, d)
+            return Geometry(n, row_floats(1 + d), 0, 1, d)
+        return Geometry(n, row_floats(d), -1, 0, d)
 
     @staticmethod
     def ffm(n, f, d):

@@ -231,6 +231,48 @@ def main():
     put("pg/loss_literal_raw", loss2)
     put("pg/dlogits_literal_raw", logits2.grad)
 
+    # ---- 8. policy networks of src/all_main/main.py: DDQN (DDQN_model.py) and DDPG (DDPG_for_PG_model.py) ----
+    DQ = importlib.import_module("src.models.DDQN_model")
+    DP = importlib.import_module("src.models.DDPG_for_PG_model")
+    Fn, Dn, M, b = 15, 10, 3, 64
+    g = torch.Generator().manual_seed(21)
+    torch.manual_seed(5)
+    dq = DQ.DoubleDQN(1000, Fn, Dn, action_nums=M, memory_size=256, batch_size=b, device="cpu")
+    state(dq.eval_net, "ddqn/eval_init")
+    s0 = torch.randn(b, 255, generator=g) * 0.3
+    s1 = torch.randn(b, 255, generator=g) * 0.3
+    a0 = torch.randint(2, M + 1, (b, 1), generator=g)
+    r0 = (torch.rand(b, 1, generator=g) < 0.5).float() * 2 - 1
+    put("ddqn/s0", s0); put("ddqn/s1", s1); put("ddqn/a0", a0); put("ddqn/r0", r0)
+    dq.eval_net.eval()
+    put("ddqn/q_eval_mode", dq.eval_net(s0))
+    put("ddqn/best_action", dq.choose_best_action(s0))
+    dq.eval_net.train()
+    for it in range(2):
+        dq.learn(s0, a0, r0, s1)
+    state(dq.eval_net, "ddqn/eval_final")
+    state(dq.target_net, "ddqn/target_final")
+
+    torch.manual_seed(6)
+    dp = DP.DDPG(1000, Fn, Dn, action_nums=M, memory_size=256, batch_size=b, device="cpu")
+    for nm in ("Actor", "Critic", "Actor_", "Critic_"):
+        state(getattr(dp, nm), f"ddpg/{nm}_init")
+    w0 = torch.softmax(torch.randn(b, M, generator=g), dim=1)
+    da = a0.float()
+    put("ddpg/w0", w0)
+    dp.Actor.eval()
+    put("ddpg/actor_eval", dp.Actor(s0, da))
+    dp.Actor.train()
+    tds, als = [], []
+    for it in range(2):
+        tds.append(dp.learn_c(s0, w0, r0, s1, da))
+        als.append(dp.learn_a(s0, da))
+        dp.soft_update(dp.Actor, dp.Actor_)
+        dp.soft_update(dp.Critic, dp.Critic_)
+    put("ddpg/td_errors", np.array(tds)); put("ddpg/a_losses", np.array(als))
+    for nm in ("Actor", "Critic", "Actor_", "Critic_"):
+        state(getattr(dp, nm), f"ddpg/{nm}_final")
+
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, len(G), "arrays,", os.path.getsize(OUT), "bytes")
 

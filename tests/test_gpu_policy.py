@@ -1,0 +1,122 @@
+"""Policy networks of the src/all_main/main.py pipeline on the B200 path (tcgen05 GEMMs + fused dense Adam)
+against golden vectors recorded from the REAL reference classes (DDQN_model.DoubleDQN,
+DDPG_for_PG_model.DDPG; tests/golden/make_golden.py section 8), plus the whole RL+CTR step."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_from_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def close(a, b, rtol=1e-5, atol=None):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    if atol is None:
+        atol = rtol * (np.abs(b).max() if b.size else 0.0)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def load(net, golden, prefix):
+    sd = {k: torch.as_tensor(v) for k, v in state_from_golden(golden, prefix).items()}
+    net.load_state_dict(sd)
+    return net
+
+
+def check_state(net, golden, prefix, rtol=2e-5):
+    ref = state_from_golden(golden, prefix)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+            continue
+        # Adam turns rounding-level gradient differences of near-zero-gradient weights into +-lr-sized steps
+        # (see tests/test_gpu_models.py::assert_state): absolute floor of a few 1e-6 for dense weights
+        close(sd[k], v, rtol=rtol, atol=max(rtol * float(np.abs(v).max()), 5e-6))
+
+
+def test_ddqn_matches_reference(golden):
+    from rl_ctr_prediction_b200 import DDQN_model
+    torch.manual_seed(0)
+    dq = DDQN_model.DoubleDQN(1000, 15, 10, action_nums=3, memory_size=256, batch_size=64, device=DEV)
+    load(dq.eval_net, golden, "ddqn/eval_init")
+    s0, s1 = torch.as_tensor(golden["ddqn/s0"]).to(DEV), torch.as_tensor(golden["ddqn/s1"]).to(DEV)
+    a0, r0 = torch.as_tensor(golden["ddqn/a0"]).to(DEV), torch.as_tensor(golden["ddqn/r0"]).to(DEV)
+    dq.eval_net.eval()
+    with torch.no_grad():
+        close(dq.eval_net(s0), golden["ddqn/q_eval_mode"])
+    assert np.array_equal(dq.choose_best_action(s0).cpu().numpy(), golden["ddqn/best_action"])
+    dq.eval_net.train()
+    for _ in range(2):
+        dq.learn(s0, a0, r0, s1)
+    check_state(dq.eval_net, golden, "ddqn/eval_final")
+    check_state(dq.target_net, golden, "ddqn/target_final")
+
+
+def test_ddpg_matches_reference(golden):
+    from rl_ctr_prediction_b200 import DDPG_for_PG_model
+    dp = DDPG_for_PG_model.DDPG(1000, 15, 10, action_nums=3, memory_size=256, batch_size=64, device=DEV)
+    for nm in ("Actor", "Critic", "Actor_", "Critic_"):
+        load(getattr(dp, nm), golden, f"ddpg/{nm}_init")
+    s0, s1 = torch.as_tensor(golden["ddqn/s0"]).to(DEV), torch.as_tensor(golden["ddqn/s1"]).to(DEV)
+    r0 = torch.as_tensor(golden["ddqn/r0"]).to(DEV)
+    da = torch.as_tensor(golden["ddqn/a0"]).float().to(DEV)
+    w0 = torch.as_tensor(golden["ddpg/w0"]).to(DEV)
+    dp.Actor.eval()
+    with torch.no_grad():
+        close(dp.Actor(s0, da), golden["ddpg/actor_eval"])
+    dp.Actor.train()
+    tds, als = [], []
+    for _ in range(2):
+        tds.append(dp.learn_c(s0, w0, r0, s1, da))
+        als.append(dp.learn_a(s0, da))
+        dp.soft_update(dp.Actor, dp.Actor_)
+        dp.soft_update(dp.Critic, dp.Critic_)
+    close(np.array(tds), golden["ddpg/td_errors"], rtol=2e-5)
+    close(np.array(als), golden["ddpg/a_losses"], rtol=2e-5)
+    for nm in ("Actor", "Critic", "Actor_", "Critic_"):
+        check_state(getattr(dp, nm), golden, f"ddpg/{nm}_final")
+
+
+def test_rl_ctr_step_runs_and_is_consistent():
+    """The full src/all_main/main.py step: encoder -> DDQN/DDPG act -> generate_preds over {LR, FM, FFM} -> store ->
+    learn.  Checks shapes, value ranges, the replay contents and that generate_preds inside the step equals the
+    oracle on the same inputs."""
+    from oracle import np_oracle as O
+    from rl_ctr_prediction_b200 import all_main, ensemble, p_model
+    from rl_ctr_prediction_b200.Feature_embedding import Feature_Embedding
+    torch.manual_seed(3)
+    N, F, D, B, M = 5000, 15, 10, 512, 3
+    models = {0: p_model.LR(N), 1: p_model.FM(N, D), 2: p_model.FFM(N, F, D)}
+    for m in models.values():
+        with torch.no_grad():
+            m.table.mul_(0.1)
+        m.to(DEV).eval()
+    fe = Feature_Embedding(N, F, D).to(DEV)
+    fe.load_embedding(models[1].state_dict())
+    ddqn, ddpg = all_main.get_model(M, N, F, D, 128, 4096, DEV, "1458")
+    rng = np.random.default_rng(0)
+    for it in range(3):
+        x = torch.as_tensor(rng.integers(0, N, size=(B, F))).to(DEV)
+        y = torch.as_tensor((rng.random((B, 1)) < 0.3).astype(np.int64)).to(DEV)
+        y_preds, rewards, td, al = all_main.train_step(ddqn, ddpg, models, x, y, fe, 0.5, DEV)
+        assert y_preds.shape == (B, 1) and rewards.shape == (B, 1)
+        assert set(np.unique(rewards.cpu().numpy())) <= {-1.0, 1.0}
+        assert np.isfinite(td) and np.isfinite(al)
+    assert ddqn.memory_counter == 3 * B and ddpg.memory_counter == 3 * B
+    stored = ddqn.memory[:3 * B]
+    assert torch.equal(stored[2 * B:3 * B, :F].long(), x)                  # ids survive the float32 ring buffer (N < 2^24)
+    assert set(np.unique(stored[:, F].cpu().numpy())) <= {2.0, 3.0}
+    # generate_preds on the step's own inputs == oracle
+    pctr = ensemble.score_models(models, x)
+    w = torch.softmax(torch.randn(B, M, device=DEV), dim=1)
+    act = torch.randint(2, M + 1, (B, 1), device=DEV)
+    yv, wv, rv = ensemble.generate_preds(models, x, act, w, y, DEV, "train", pctr=pctr)
+    yo, wo, ro = O.generate_preds(pctr.cpu().numpy(), w.cpu().numpy(), act.cpu().numpy(), y.cpu().numpy())
+    close(yv, yo)
+    close(wv, wo)
+    assert (rv.cpu().numpy() != ro).mean() < 0.01
