@@ -55,6 +55,12 @@ typedef struct rlctr_table {
     int32_t lin_col;     /* column of the first-order weight, -1 = none */
     int32_t emb_col;     /* first column of the latent vector */
     int32_t dim;         /* latent_dims (FFM: field_nums*latent_dims), 0 = none */
+    int32_t row_pitch;   /* floats between consecutive rows, >= row_stride (0 means row_stride).  A trainable
+                          * table is laid out [ p | exp_avg | exp_avg_sq ] per row (row_pitch = 3*row_stride,
+                          * rlctr_adam.exp_avg = data + row_stride, .exp_avg_sq = data + 2*row_stride) so the
+                          * optimizer touches ONE contiguous 3*row_stride*4-byte record per row instead of three
+                          * random 64 B blocks: random HBM accesses are activation-rate bound, not byte bound
+                          * (profiles/r1_gather_probe.md).  The Adam arrays always use the table's pitch. */
 } rlctr_table;
 
 /* torch.optim.Adam state for one table (src/main/pretrain_main.py:181).  `sched[t]` holds
@@ -63,8 +69,8 @@ typedef struct rlctr_table {
  * COMPLETED optimizer steps (0 after construction), so a captured CUDA graph can be replayed
  * while the step advances (rlctr_step_advance, +1 after the update kernels of a step). */
 typedef struct rlctr_adam {
-    float*         exp_avg;      /* [n_rows, row_stride] */
-    float*         exp_avg_sq;   /* [n_rows, row_stride] */
+    float*         exp_avg;      /* [n_rows, row_stride] at the table's row_pitch */
+    float*         exp_avg_sq;   /* [n_rows, row_stride] at the table's row_pitch */
     int32_t*       stamp;        /* [n_rows] last step at which the row is up to date; NULL in sparse mode */
     const float*   sched;        /* [sched_len][2], index = step (entry 0 unused) */
     const int32_t* step;         /* device scalar: completed steps t; update kernels apply step t+1 */

@@ -27,7 +27,7 @@ class RlctrError(RuntimeError):
 class Table(C.Structure):
     """struct rlctr_table"""
     _fields_ = [("data", C.c_void_p), ("n_rows", C.c_int64), ("row_stride", C.c_int32),
-                ("lin_col", C.c_int32), ("emb_col", C.c_int32), ("dim", C.c_int32)]
+                ("lin_col", C.c_int32), ("emb_col", C.c_int32), ("dim", C.c_int32), ("row_pitch", C.c_int32)]
 
 
 class Adam(C.Structure):

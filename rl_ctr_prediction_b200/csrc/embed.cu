@@ -15,7 +15,7 @@ namespace rlctr {
 // ------------------------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(256)
-embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows,
+embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch,
                  int rs, int lin_col, int emb_col, int dim, const float* __restrict__ bias,
                  float* __restrict__ logit, float* __restrict__ pctr, int64_t pctr_stride,
                  float* __restrict__ sums, float* __restrict__ rows_out,
@@ -63,8 +63,8 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
             }
             float4 ra = f4zero(), rb = f4zero();
             const bool oka = (uint64_t)ia < (uint64_t)n_rows, okb = (uint64_t)ib < (uint64_t)n_rows;
-            if (oka) ra = ldg4(tab + ia * rs + col0);
-            if (okb) rb = ldg4(tab + ib * rs + col0);
+            if (oka) ra = ldg4(tab + ia * pitch + col0);
+            if (okb) rb = ldg4(tab + ib * pitch + col0);
             s = f4add(s, f4add(ra, rb));
             if (fm) {
 #pragma unroll
@@ -114,7 +114,7 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
 
 // LR table: one float per row (row_stride == 1).  Lane f gathers w[x_f]; warp-sum.
 __global__ void __launch_bounds__(256)
-embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows,
+embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch,
                         const float* __restrict__ bias, float* __restrict__ logit,
                         float* __restrict__ pctr, int64_t pctr_stride, float* __restrict__ sums,
                         int64_t batch, int fields) {
@@ -126,7 +126,7 @@ embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict
         float s = 0.f;
         for (int f = lane; f < fields; f += 32) {
             const int64_t id = __ldg(ids + b * fields + f);
-            if ((uint64_t)id < (uint64_t)n_rows) s += __ldg(tab + id);
+            if ((uint64_t)id < (uint64_t)n_rows) s += __ldg(tab + id * pitch);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(RLCTR_FULL, s, off);
@@ -144,7 +144,7 @@ embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __restrict__ tab,
-                   int64_t n_rows, int rs, float* __restrict__ out) {
+                   int64_t n_rows, int pitch, int rs, float* __restrict__ out) {
     const int chunks = rs >> 2;
     const int64_t total = n * chunks;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -153,17 +153,17 @@ gather_rows_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __re
         const int c = (int)(t - k * chunks);
         const int64_t id = __ldg(ids + k);
         float4 r = f4zero();
-        if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(tab + id * rs + 4 * c);
+        if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(tab + id * pitch + 4 * c);
         st4_stream(out + k * rs + 4 * c, r);
     }
 }
 __global__ void __launch_bounds__(256)
 gather_rows_scalar_kernel(const int64_t* __restrict__ ids, int64_t n, const float* __restrict__ tab,
-                          int64_t n_rows, float* __restrict__ out) {
+                          int64_t n_rows, int pitch, float* __restrict__ out) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
          t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t id = __ldg(ids + t);
-        out[t] = ((uint64_t)id < (uint64_t)n_rows) ? __ldg(tab + id) : 0.f;
+        out[t] = ((uint64_t)id < (uint64_t)n_rows) ? __ldg(tab + id * pitch) : 0.f;
     }
 }
 
@@ -173,7 +173,7 @@ gather_rows_scalar_kernel(const int64_t* __restrict__ ids, int64_t n, const floa
 // ------------------------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(128)
-featemb_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows,
+featemb_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch,
                    int rs, int emb_col, int dim, float* __restrict__ out, int64_t out_stride,
                    int64_t batch, int fields) {
     constexpr int RPW = 32 / LPR;
@@ -201,8 +201,8 @@ featemb_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ ta
             if (chunk_on && fa < fields) ia = __ldg(ids + b * fields + fa);
             if (chunk_on && fb < fields) ib = __ldg(ids + b * fields + fb);
             float4 ra = f4zero(), rb = f4zero();
-            if ((uint64_t)ia < (uint64_t)n_rows) ra = ldg4(tab + ia * rs + col0);
-            if ((uint64_t)ib < (uint64_t)n_rows) rb = ldg4(tab + ib * rs + col0);
+            if ((uint64_t)ia < (uint64_t)n_rows) ra = ldg4(tab + ia * pitch + col0);
+            if ((uint64_t)ib < (uint64_t)n_rows) rb = ldg4(tab + ib * pitch + col0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int d = col0 + k - emb_col;
@@ -236,8 +236,11 @@ static int grid_for_warps(int64_t items, int warps_per_block, int blocks_per_sm)
 
 using namespace rlctr;
 
+static inline int pitch_of(const rlctr_table* t) { return t->row_pitch > 0 ? t->row_pitch : t->row_stride; }
+
 static int check_table(const rlctr_table* t) {
     if (!t || !t->data || t->n_rows <= 0) return RLCTR_EINVAL;
+    if (pitch_of(t) < t->row_stride || (t->row_stride != 1 && pitch_of(t) % 4 != 0)) return RLCTR_EUNSUPPORTED;
     if (t->row_stride != 1 && (t->row_stride % 4 != 0 || t->row_stride <= 0)) return RLCTR_EUNSUPPORTED;
     if (t->row_stride != 1 && !rlctr_aligned16(t->data)) return RLCTR_EALIGN;
     if (t->dim < 0 || t->emb_col < 0 || t->emb_col + t->dim > t->row_stride) return RLCTR_EINVAL;
@@ -259,7 +262,7 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
     if (rs == 1) {
         if (rows_out || (flags & RLCTR_FM_TERM) || table->lin_col != 0) return RLCTR_EUNSUPPORTED;
         int grid = grid_for_warps(batch, 8, 8);
-        embed_fwd_scalar_kernel<<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, bias, logit, pctr,
+        embed_fwd_scalar_kernel<<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, pitch_of(table), bias, logit, pctr,
                                                      pctr_stride, sums, batch, fields);
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
@@ -268,7 +271,7 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
     if (sums && !rlctr_aligned16(sums)) return RLCTR_EALIGN;
     int grid = grid_for_warps(batch, 8, 8);
 #define LAUNCH_EMBED(L)                                                                              \
-    embed_fwd_kernel<L><<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, rs, table->lin_col,   \
+    embed_fwd_kernel<L><<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, pitch_of(table), rs, table->lin_col,   \
                                               table->emb_col, table->dim, bias, logit, pctr,         \
                                               pctr_stride, sums, rows_out, batch, fields, flags)
     switch (rlctr_lanes_per_row(rs)) {
@@ -293,12 +296,12 @@ extern "C" int rlctr_gather_rows(const int64_t* ids, int64_t n, const rlctr_tabl
     if (rs == 1) {
         int64_t blocks = (n + 255) / 256;
         int grid = (int)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8);
-        gather_rows_scalar_kernel<<<grid, 256, 0, st>>>(ids, n, table->data, table->n_rows, out);
+        gather_rows_scalar_kernel<<<grid, 256, 0, st>>>(ids, n, table->data, table->n_rows, pitch_of(table), out);
     } else {
         if (!rlctr_aligned16(out)) return RLCTR_EALIGN;
         int64_t blocks = (n * (rs / 4) + 255) / 256;
         int grid = (int)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8);
-        gather_rows_kernel<<<grid, 256, 0, st>>>(ids, n, table->data, table->n_rows, rs, out);
+        gather_rows_kernel<<<grid, 256, 0, st>>>(ids, n, table->data, table->n_rows, pitch_of(table), rs, out);
     }
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
@@ -321,7 +324,7 @@ extern "C" int rlctr_featemb_fwd(const int64_t* ids, const rlctr_table* table, f
     if (smem > 48 * 1024) return RLCTR_EUNSUPPORTED;
     int grid = grid_for_warps(batch, nw, 16);
 #define LAUNCH_FE(L)                                                                               \
-    featemb_fwd_kernel<L><<<grid, nw * 32, smem, st>>>(ids, table->data, table->n_rows, rs,        \
+    featemb_fwd_kernel<L><<<grid, nw * 32, smem, st>>>(ids, table->data, table->n_rows, pitch_of(table), rs, \
                                                        table->emb_col, dim, out, out_stride, batch, fields)
     switch (rlctr_lanes_per_row(rs)) {
         case 1: LAUNCH_FE(1); break;

@@ -18,7 +18,7 @@ namespace rlctr {
 constexpr int FFM_WARPS = 4;
 
 __global__ void __launch_bounds__(FFM_WARPS * 32)
-ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int rs,
+ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch, int rs,
                int lin_col, int emb_col, const float* __restrict__ bias, float* __restrict__ logit,
                float* __restrict__ pctr, int64_t pctr_stride, float* __restrict__ partners,
                int64_t batch, int fields, int latent) {
@@ -47,7 +47,7 @@ ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, i
             const int f = t / chunks, c = t - f * chunks;
             const int64_t id = __ldg(ids + b * fields + f);
             float4 r = f4zero();
-            if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(tab + id * rs + 4 * c);
+            if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(tab + id * pitch + 4 * c);
             st4(stage + f * rs + 4 * c, r);
         }
         __syncwarp();
@@ -117,7 +117,8 @@ extern "C" int rlctr_ffm_fwd(const int64_t* ids, const rlctr_table* table, const
     const int64_t cap = (int64_t)RLCTR_SMS * per_sm;
     const int grid = (int)(want < cap ? want : cap);
     ffm_fwd_kernel<<<grid, FFM_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        ids, table->data, table->n_rows, rs, table->lin_col, table->emb_col, bias, logit, pctr, pctr_stride,
+        ids, table->data, table->n_rows, table->row_pitch > 0 ? table->row_pitch : rs, rs, table->lin_col, table->emb_col, bias,
+        logit, pctr, pctr_stride,
         partners, batch, fields, latent);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;

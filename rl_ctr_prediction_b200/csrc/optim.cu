@@ -23,9 +23,11 @@ struct TableView {
     float* data;
     int64_t n_rows;
     int rs, lin_col, emb_col, dim;
+    int pitch;           // floats between rows of data / exp_avg / exp_avg_sq
 };
 static inline TableView view_of(const rlctr_table* t) {
-    return TableView{t->data, t->n_rows, t->row_stride, t->lin_col, t->emb_col, t->dim};
+    return TableView{t->data, t->n_rows, t->row_stride, t->lin_col, t->emb_col, t->dim,
+                     t->row_pitch > 0 ? t->row_pitch : t->row_stride};
 }
 struct AdamView {
     float* m;
@@ -102,13 +104,14 @@ __device__ __forceinline__ void adam_apply4(float4& p, float4& m, float4& v, con
 // finish one distinct row: Adam (APPLY==0) or store into the dense gradient (APPLY==1)
 template <int APPLY>
 __device__ __forceinline__ void finish_row(int64_t id, int col0, float4 p, const float4& acc, const TableView& t,
-                                           const AdamView& a, float* dense_grad, int step, int stamp_in) {
-    const int64_t off = id * t.rs + col0;
+                                           const AdamView& a, float* dense_grad, int step, int stamp_in,
+                                           const float4* m_pre = nullptr, const float4* v_pre = nullptr) {
     if (APPLY == 1) {
-        st4(dense_grad + off, acc);
+        st4(dense_grad + id * t.rs + col0, acc);
         return;
     }
-    float4 m = ld4(a.m + off), v = ld4(a.v + off);
+    const int64_t off = id * t.pitch + col0;
+    float4 m = m_pre ? *m_pre : ld4(a.m + off), v = v_pre ? *v_pre : ld4(a.v + off);
     if (a.stamp && stamp_in < step - 1) adam_replay4(p, m, v, stamp_in, step - 1, a.sched, a.h);
     adam_apply4(p, m, v, acc, __ldg(&a.sched[step]), a.h);
     st4(t.data + off, p);
@@ -142,7 +145,10 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
             step = __ldg(a.step) + 1;
             if (a.stamp) stamp_in = a.stamp[id];
         }
-        const float4 p = ld4(t.data + (int64_t)id * t.rs + col0);
+        const int64_t off = (int64_t)id * t.pitch + col0;
+        const float4 p = ld4(t.data + off);
+        float4 m0 = f4zero(), v0 = f4zero();             // issued with p: one contiguous record when pitch = 3*rs
+        if (APPLY == 0) { m0 = ld4(a.m + off); v0 = ld4(a.v + off); }
         float4 acc = f4zero();
         int64_t kk = k;
         uint32_t nxt = id;
@@ -152,7 +158,7 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
             nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
             acc = f4add(acc, rowgrad_chunk(g, slot, col0, p, t));
         }
-        finish_row<APPLY>(id, col0, p, acc, t, a, dense_grad, step, stamp_in);
+        finish_row<APPLY>(id, col0, p, acc, t, a, dense_grad, step, stamp_in, &m0, &v0);
     }
     if (APPLY == 0 && a.stamp) {
         __syncwarp();                                    // all chunk lanes read the stamp before lane 0 rewrites it
@@ -188,7 +194,7 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
         float4 p = f4zero(), acc = f4zero();
         int step = 0, stamp_in = 0;
         if (chunk_on) {
-            p = ld4(t.data + (int64_t)id * t.rs + col0);
+            p = ld4(t.data + (int64_t)id * t.pitch + col0);
             for (int64_t kk = k + sub; kk < end; kk += NSUB)
                 acc = f4add(acc, rowgrad_chunk(g, __ldg(sorted_slots + kk), col0, p, t));
             if (APPLY == 0 && sub == 0) {
@@ -227,7 +233,7 @@ rows_wide_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
     for (int u = 0; u < WCH; ++u) {
         const int c = lane + 32 * u;
         acc[u] = f4zero();
-        p[u] = c < chunks ? ld4(t.data + (int64_t)id * t.rs + 4 * c) : f4zero();
+        p[u] = c < chunks ? ld4(t.data + (int64_t)id * t.pitch + 4 * c) : f4zero();
     }
     int64_t kk = k;
     uint32_t nxt = id;
@@ -286,7 +292,7 @@ __device__ __forceinline__ void replay_fetch(ReplayItem& it, int64_t k, int c, i
     const int st = __ldg(a.stamp + row);
     if (st >= upto) return;
     it.t = st;
-    it.off = row * t.rs + 4 * c;
+    it.off = row * t.pitch + 4 * c;
     it.p = ld4(t.data + it.off);
     it.m = ld4(a.m + it.off);
     it.v = ld4(a.v + it.off);
@@ -341,9 +347,10 @@ adam_flush_scalar_kernel(TableView t, AdamView a, int64_t r0, int64_t r1) {   //
     for (int64_t row = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < r1; row += (int64_t)gridDim.x * blockDim.x) {
         const int st = a.stamp[row];
         if (st >= upto) continue;
-        float p = t.data[row], m = a.m[row], v = a.v[row];
+        const int64_t o = row * t.pitch;
+        float p = t.data[o], m = a.m[o], v = a.v[o];
         adam_replay1(p, m, v, st, upto, a.sched, a.h);
-        t.data[row] = p; a.m[row] = m; a.v[row] = v;
+        t.data[o] = p; a.m[o] = m; a.v[o] = v;
         a.stamp[row] = upto;
     }
 }
@@ -376,7 +383,8 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     }
     if (APPLY == 1) { dense_grad[id] = acc; return; }
     const int step = __ldg(a.step) + 1;
-    float p = t.data[id], m = a.m[id], v = a.v[id];
+    const int64_t o = (int64_t)id * t.pitch;
+    float p = t.data[o], m = a.m[o], v = a.v[o];
     if (a.stamp) {
         const int st = a.stamp[id];
         adam_replay1(p, m, v, st, step - 1, a.sched, a.h);
@@ -384,7 +392,7 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     }
     const float2 sc = __ldg(&a.sched[step]);
     adam_elem(p, m, v, acc, a.h, sc.x, sc.y);
-    t.data[id] = p; a.m[id] = m; a.v[id] = v;
+    t.data[o] = p; a.m[o] = m; a.v[o] = v;
 }
 __global__ void __launch_bounds__(256)
 rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
@@ -395,9 +403,10 @@ rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, T
     const int upto = __ldg(a.step);
     const int st = a.stamp[id];
     if (st >= upto) return;
-    float p = t.data[id], m = a.m[id], v = a.v[id];
+    const int64_t o = (int64_t)id * t.pitch;
+    float p = t.data[o], m = a.m[o], v = a.v[o];
     adam_replay1(p, m, v, st, upto, a.sched, a.h);
-    t.data[id] = p; a.m[id] = m; a.v[id] = v;
+    t.data[o] = p; a.m[o] = m; a.v[o] = v;
     a.stamp[id] = upto;
 }
 

@@ -157,9 +157,10 @@ class _TableModel(nn.Module):
 
     def _init_table(self, geom: Geometry, columns, device=None):
         """columns: list of (first_col, tensor[N, w]) in the reference's creation order."""
+        geom = geom.with_state()            # trainable: Adam state interleaved with the row (tables.Geometry)
         self._geom = geom
         dev = torch.device(device) if device is not None else None
-        data = torch.zeros(geom.n_rows, geom.row_stride, dtype=torch.float32, device=dev)
+        data = torch.zeros(geom.n_rows, geom.row_pitch, dtype=torch.float32, device=dev)
         for col, w in columns:
             # nn.Embedding.reset_parameters == normal_(0, 1), drawn in the reference's creation order:
             # with the default (CPU) construction the same torch.manual_seed gives the reference's values

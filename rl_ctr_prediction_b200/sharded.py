@@ -154,10 +154,11 @@ class ShardedCTR(nn.Module):
             g = Geometry.ffm(n_local, self.field_nums, self.latent_dims)
         else:
             g = Geometry.fm(n_local, self.latent_dims)
+        g = g.with_state()
         self._geom = g
         self._kind = {"LR": "lr", "FM": "fm", "DeepFM": "fm", "FFM": "ffm"}[kind]
         dev = torch.device(device) if device is not None else None
-        data = torch.zeros(g.n_rows, g.row_stride, dtype=torch.float32, device=dev)
+        data = torch.zeros(g.n_rows, g.row_pitch, dtype=torch.float32, device=dev)
         used = [g.lin_col] if g.lin_col >= 0 else []
         used += list(range(g.emb_col, g.emb_col + g.dim))
         if used:
@@ -215,11 +216,11 @@ class ShardedCTR(nn.Module):
         """The full fused table [N, row_stride], rebuilt on every rank (tests / checkpointing)."""
         self.flush()
         n_max = shard_rows(self.feature_nums, self.world, 0)
-        mine = torch.zeros(n_max, self._geom.row_stride, dtype=torch.float32, device=self.table.device)
+        mine = torch.zeros(n_max, self._geom.row_pitch, dtype=torch.float32, device=self.table.device)
         mine[:self._geom.n_rows] = self.table.data
         parts = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(parts, mine, group=self.group)
-        full = torch.empty(self.feature_nums, self._geom.row_stride, dtype=torch.float32, device=mine.device)
+        full = torch.empty(self.feature_nums, self._geom.row_pitch, dtype=torch.float32, device=mine.device)
         for r in range(self.world):
             cnt = shard_rows(self.feature_nums, self.world, r)
             full[r::self.world] = parts[r][:cnt]
@@ -252,7 +253,7 @@ class ShardedCTR(nn.Module):
         B, F = x.shape
         dev = x.device
         g = self._geom
-        gl = Geometry(max(plan.n, 1), g.row_stride, g.lin_col, g.emb_col, g.dim)
+        gl = g.rows_only(max(plan.n, 1))
         t = table_struct(rows, gl)
         pos = plan.pos_of_slot.view(B, F)
         logit = torch.empty(B, dtype=torch.float32, device=dev)

@@ -42,6 +42,22 @@ class Geometry:
     lin_col: int
     emb_col: int
     dim: int
+    pitch: int = 0            # floats between rows; 0 = row_stride.  3*row_stride: [p | exp_avg | exp_avg_sq] records
+
+    @property
+    def row_pitch(self):
+        return self.pitch or self.row_stride
+
+    @property
+    def has_state(self):
+        return self.row_pitch >= 3 * self.row_stride
+
+    def with_state(self):
+        """The trainable layout: Adam's exp_avg / exp_avg_sq interleaved with the row (one contiguous record)."""
+        return Geometry(self.n_rows, self.row_stride, self.lin_col, self.emb_col, self.dim, 3 * self.row_stride)
+
+    def rows_only(self, n_rows=None):
+        return Geometry(self.n_rows if n_rows is None else n_rows, self.row_stride, self.lin_col, self.emb_col, self.dim, 0)
 
     @staticmethod
     def lr(n):
@@ -59,7 +75,7 @@ class Geometry:
 
 
 def table_struct(data: torch.Tensor, g: Geometry) -> _lib.Table:
-    return _lib.Table(_lib.ptr(data), g.n_rows, g.row_stride, g.lin_col, g.emb_col, g.dim)
+    return _lib.Table(_lib.ptr(data), g.n_rows, g.row_stride, g.lin_col, g.emb_col, g.dim, g.row_pitch)
 
 
 class AdamSchedule:
@@ -100,8 +116,14 @@ class TableAdamState:
         assert mode in ("lazy", "dense", "sparse")
         self.geom, self.mode = geom, mode
         dev = param.device
-        self.exp_avg = torch.zeros_like(param)
-        self.exp_avg_sq = torch.zeros_like(param)
+        rs = geom.row_stride
+        if geom.has_state:            # [p | exp_avg | exp_avg_sq] records: the state lives inside the table's rows
+            param[:, rs:3 * rs].zero_()
+            self.exp_avg = param[:, rs:2 * rs]
+            self.exp_avg_sq = param[:, 2 * rs:3 * rs]
+        else:
+            self.exp_avg = torch.zeros_like(param)
+            self.exp_avg_sq = torch.zeros_like(param)
         self.stamp = None if mode == "sparse" else torch.zeros(geom.n_rows, dtype=torch.int32, device=dev)
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)     # completed steps (device scalar)
         self.host_step = 0
@@ -110,7 +132,7 @@ class TableAdamState:
         self.dirty = False           # True while some rows lag behind `step` (lazy mode)
 
     def struct(self) -> _lib.Adam:
-        return _lib.Adam(_lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.stamp),
+        return _lib.Adam(self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), _lib.ptr(self.stamp),
                          _lib.ptr(self.sched.tensor), _lib.ptr(self.step), self.sched.length,
                          self.betas[0], self.betas[1], self.eps, self.weight_decay)
 

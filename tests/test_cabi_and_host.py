@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header():
     from rl_ctr_prediction_b200 import _lib
-    assert C.sizeof(_lib.Table) == 32           # ptr, i64, 4 x i32
+    assert C.sizeof(_lib.Table) == 40           # ptr, i64, 5 x i32 (+pad)
     assert C.sizeof(_lib.Adam) == 80            # 5 ptr, i32 (+pad), 4 x f64
     assert C.sizeof(_lib.RowGrad) == 40         # 4 ptr, 2 x i32
     assert _lib.Table.row_stride.offset == 16 and _lib.Adam.sched_len.offset == 40
@@ -84,7 +84,10 @@ def test_state_dict_is_reference_keyed_and_init_matches_seed(name):
     if g.lin_col >= 0:
         used[g.lin_col] = True
     used[g.emb_col:g.emb_col + g.dim] = True
-    assert torch.all(m.table.data[:, ~used] == 0)
+    assert torch.all(m.table.data[:, :g.row_stride][:, ~used] == 0)
+    # trainable tables carry Adam's exp_avg / exp_avg_sq inside each row record, zero until an optimizer runs
+    assert g.row_pitch == 3 * g.row_stride and m.table.shape[1] == g.row_pitch
+    assert torch.all(m.table.data[:, g.row_stride:] == 0)
 
 
 def test_feature_embedding_host_surface():
