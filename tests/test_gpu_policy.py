@@ -163,3 +163,63 @@ def test_rl_ctr_step_runs_and_is_consistent():
     close(yv, yo)
     close(wv, wo)
     assert (rv.cpu().numpy() != ro).mean() < 0.01
+
+
+@pytest.mark.parametrize("variant", ["literal", "per_sample"])
+def test_reinforce_policy_gradient_learn(variant):
+    """PG_model.PolicyGradient.learn (state encoder kernel -> tcgen05 MLP -> REINFORCE head kernel -> fused Adam) vs
+    the reference's formulas evaluated with stock torch on the CPU (PG_model.py:53-58,104-107,156-179 with the N9
+    input-dims fix): per-sample policy log-probs within 1e-5, loss, and the updated network."""
+    import torch.nn as nn
+    from oracle import torch_port as TP
+    from rl_ctr_prediction_b200 import PG_model
+    torch.manual_seed(11)
+    N, F, D, A, B = 3000, 15, 10, 4, 512
+    pg = PG_model.PolicyGradient(N, F, D, action_nums=A, device=DEV, loss_variant=variant)
+    for m in pg.policy_net.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0                                      # deterministic comparison (torch's Philox masks differ across devices)
+    with torch.no_grad():
+        pg.policy_net.embedding_layer.table.mul_(0.2)
+    # CPU replica of the same network
+    fe = TP.PortFeatureEmbedding(N, F, D)
+    fe.load_state_dict(pg.policy_net.embedding_layer.state_dict())
+    dims = [255, 1024, 512, 256, 128]
+    layers = []
+    for i in range(4):
+        layers += [nn.Linear(dims[i], dims[i + 1]), nn.ReLU(), nn.Dropout(p=0.0)]
+    layers.append(nn.Linear(128, A))
+    ref = nn.Sequential(*layers)
+    ref.load_state_dict({k: v.cpu() for k, v in pg.policy_net.mlp.state_dict().items()})
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-4, weight_decay=1e-5)
+    rng = np.random.default_rng(4)
+    x = torch.as_tensor(rng.integers(0, N, size=(B, F)))
+    a = torch.as_tensor(rng.integers(1, A + 1, size=(B, 1)))
+    r = torch.as_tensor((rng.random(B) < 0.5).astype(np.float32) * 2 - 1)
+    vt = torch.as_tensor(rng.standard_normal(B).astype(np.float32))            # raw returns: non-degenerate gradient (N9)
+    # act: the acting path (softmax policy) agrees
+    with torch.no_grad():
+        close(pg.policy_net.forward(x.to(DEV)), torch.softmax(ref(fe(x)), dim=1))
+    pg.store_transition(x.to(DEV), a.to(DEV), r.to(DEV))
+    assert pg.ep_states.shape == (B, F)
+    g = pg.discount_and_norm_rewards()
+    gref = np.cumsum(r.numpy()[::-1].astype(np.float64))[::-1]
+    close(g, (gref - gref.mean()) / gref.std(), rtol=1e-12)
+    loss = pg.learn(vt=vt.to(DEV))
+    probs = torch.softmax(ref(fe(x)), dim=1)
+    logp_ref = torch.log(probs.gather(1, a - 1)).view(-1)
+    if variant == "literal":
+        loss_ref = torch.mean(torch.mul(torch.sum(-logp_ref), vt))             # PG_model.py:105-106
+    else:
+        loss_ref = torch.mean(-logp_ref * vt)
+    ropt.zero_grad()
+    loss_ref.backward()
+    ropt.step()
+    close(pg.last_logp, logp_ref.detach(), rtol=1e-5)                          # the north-star quantity
+    close(loss, loss_ref.detach(), rtol=1e-4, atol=1e-4 * float(np.abs(logp_ref.detach().numpy()).sum()) * 1e-2)
+    for (k, p), (_, q) in zip(pg.policy_net.mlp.state_dict().items(), ref.state_dict().items()):
+        # one Adam step of size lr: every element moved by ~1e-4 in the same direction
+        assert (p.cpu() - q).abs().max().item() <= 2.2e-4, k
+        agree = ((p.cpu() - q).abs() <= 2e-6).float().mean().item()
+        assert agree >= 0.98, (k, agree)
+    assert pg.ep_states.numel() == 0                                            # episode cleared (:176-179)
