@@ -75,6 +75,10 @@ typedef struct rlctr_adam {
     const float*   sched;        /* [sched_len][2], index = step (entry 0 unused) */
     const int32_t* step;         /* device scalar: completed steps t; update kernels apply step t+1 */
     int32_t        sched_len;
+    int32_t        stamp_col;    /* >= 0: the row's stamp is the int32 stored at float offset stamp_col of the row RECORD
+                                  * itself (a padding column of the row, or the 4th float of an LR record [w|m|v|stamp]);
+                                  * `stamp` is then ignored.  The stamp rides along with data the kernels touch anyway:
+                                  * no second random HBM access per row.  -1: separate `stamp` array (NULL = not lazy). */
     /* hyper-parameters as the Python DOUBLES torch.optim.Adam holds: the kernels use float(1 - beta1),
      * float(1 - beta2), float(eps), float(weight_decay) exactly as torch derives them in double and casts
      * at the op (1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative) */

@@ -33,7 +33,7 @@ class Table(C.Structure):
 class Adam(C.Structure):
     """struct rlctr_adam"""
     _fields_ = [("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("stamp", C.c_void_p),
-                ("sched", C.c_void_p), ("step", C.c_void_p), ("sched_len", C.c_int32),
+                ("sched", C.c_void_p), ("step", C.c_void_p), ("sched_len", C.c_int32), ("stamp_col", C.c_int32),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double)]
 
 

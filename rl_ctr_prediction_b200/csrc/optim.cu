@@ -24,22 +24,36 @@ struct TableView {
     int64_t n_rows;
     int rs, lin_col, emb_col, dim;
     int pitch;           // floats between rows of data / exp_avg / exp_avg_sq
+    int used;            // columns that carry parameters: chunks past ceil(used/4) are pure padding and are skipped
 };
 static inline TableView view_of(const rlctr_table* t) {
+    int used = t->emb_col + t->dim;
+    if (t->lin_col + 1 > used) used = t->lin_col + 1;
+    if (used < 1) used = 1;
     return TableView{t->data, t->n_rows, t->row_stride, t->lin_col, t->emb_col, t->dim,
-                     t->row_pitch > 0 ? t->row_pitch : t->row_stride};
+                     t->row_pitch > 0 ? t->row_pitch : t->row_stride, used};
 }
 struct AdamView {
     float* m;
     float* v;
-    int32_t* stamp;
+    int32_t* stamp;      // separate per-row stamps, or
+    int stamp_col;       // >= 0: the stamp is the int32 at float offset stamp_col of the row record itself
     const float2* sched;
     const int32_t* step;
     AdamHyper h;
 };
 static inline AdamView view_of(const rlctr_adam* a) {
-    return AdamView{a->exp_avg, a->exp_avg_sq, a->stamp, reinterpret_cast<const float2*>(a->sched), a->step,
+    return AdamView{a->exp_avg, a->exp_avg_sq, a->stamp_col >= 0 ? nullptr : a->stamp, a->stamp_col >= 0 ? a->stamp_col : -1,
+                    reinterpret_cast<const float2*>(a->sched), a->step,
                     adam_hyper(a->beta1, a->beta2, a->eps, a->weight_decay)};
+}
+__device__ __forceinline__ bool is_lazy(const AdamView& a) { return a.stamp != nullptr || a.stamp_col >= 0; }
+__device__ __forceinline__ int load_stamp(const TableView& t, const AdamView& a, int64_t id) {
+    return a.stamp_col >= 0 ? __float_as_int(t.data[id * t.pitch + a.stamp_col]) : a.stamp[id];
+}
+// in-record stamps travel with the chunk that holds them: patch it before the chunk is stored
+__device__ __forceinline__ void embed_stamp(float4& p, int col0, const AdamView& a, int value) {
+    if (a.stamp_col >= 0 && (a.stamp_col & ~3) == col0) f4set(p, a.stamp_col & 3, __int_as_float(value));
 }
 struct GradView {
     const float* staged;
@@ -112,8 +126,9 @@ __device__ __forceinline__ void finish_row(int64_t id, int col0, float4 p, const
     }
     const int64_t off = id * t.pitch + col0;
     float4 m = m_pre ? *m_pre : ld4(a.m + off), v = v_pre ? *v_pre : ld4(a.v + off);
-    if (a.stamp && stamp_in < step - 1) adam_replay4(p, m, v, stamp_in, step - 1, a.sched, a.h);
+    if (is_lazy(a) && stamp_in < step - 1) adam_replay4(p, m, v, stamp_in, step - 1, a.sched, a.h);
     adam_apply4(p, m, v, acc, __ldg(&a.sched[step]), a.h);
+    embed_stamp(p, col0, a, step);
     st4(t.data + off, p);
     st4(a.m + off, m);
     st4(a.v + off, v);
@@ -138,12 +153,12 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
         if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)k;      // order is irrelevant: rows are independent
         head = false;
     }
-    const bool work = head && col0 < t.rs;
+    const bool work = head && col0 < ((APPLY == 0) ? ((t.used + 3) & ~3) : t.rs);
     int step = 0, stamp_in = 0;
     if (work) {
         if (APPLY == 0) {
             step = __ldg(a.step) + 1;
-            if (a.stamp) stamp_in = a.stamp[id];
+            if (is_lazy(a)) stamp_in = load_stamp(t, a, id);
         }
         const int64_t off = (int64_t)id * t.pitch + col0;
         const float4 p = ld4(t.data + off);
@@ -158,6 +173,7 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
             nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
             acc = f4add(acc, rowgrad_chunk(g, slot, col0, p, t));
         }
+        if (APPLY == 0 && a.stamp_col >= 0) __syncwarp(__activemask());   // every chunk lane has read the in-record stamp
         finish_row<APPLY>(id, col0, p, acc, t, a, dense_grad, step, stamp_in, &m0, &v0);
     }
     if (APPLY == 0 && a.stamp) {
@@ -199,7 +215,7 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
                 acc = f4add(acc, rowgrad_chunk(g, __ldg(sorted_slots + kk), col0, p, t));
             if (APPLY == 0 && sub == 0) {
                 step = __ldg(a.step) + 1;
-                if (a.stamp) stamp_in = a.stamp[id];
+                if (is_lazy(a)) stamp_in = load_stamp(t, a, id);
             }
         }
         red[threadIdx.x] = acc;
@@ -250,7 +266,8 @@ rows_wide_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
     int step = 0, stamp_in = 0;
     if (APPLY == 0) {
         step = __ldg(a.step) + 1;
-        if (a.stamp) stamp_in = a.stamp[id];
+        if (is_lazy(a)) stamp_in = load_stamp(t, a, id);
+        __syncwarp();
     }
 #pragma unroll
     for (int u = 0; u < WCH; ++u) {
@@ -300,7 +317,7 @@ __device__ __forceinline__ void replay_fetch(ReplayItem& it, int64_t k, int c, i
 template <bool CATCHUP>
 __global__ void __launch_bounds__(256)
 replay_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
-    const int chunks = t.rs >> 2;
+    const int chunks = (t.used + 3) >> 2;                 // trailing all-padding chunks are never touched
     const uint32_t stride = gridDim.x * blockDim.x;       // items (chunks) between two items of one lane
     const uint32_t dk = stride / chunks, dc = stride % chunks;
     const int upto = __ldg(a.step);
@@ -330,6 +347,94 @@ replay_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32
         adam_l2_step4(cur.p, cur.m, cur.v, __ldg(&a.sched[cur.t]), a.h);
     }
 }
+// In-record stamps (stamp_col >= 0): the stamp is part of the record, so ONE lane owns a whole row (all of its
+// CH active chunks): it reads the stamp with the data, replays, and writes the new stamp with the data -- no
+// separate stamp array, no second random access per row, no ordering problem between the chunks of a row.
+template <int CH>
+struct ReplayRow {
+    float4 p[CH], m[CH], v[CH];
+    int64_t off;
+    int t;
+};
+template <int CH, bool CATCHUP>
+__device__ __forceinline__ void replay_row_fetch(ReplayRow<CH>& it, int64_t k, int64_t n_items, const TableView& t,
+                                                 const AdamView& a, int64_t r0, const uint32_t* __restrict__ sorted_ids,
+                                                 int upto) {
+    it.off = -1;
+    it.t = upto;
+    if (k >= n_items) return;
+    int64_t row;
+    if (CATCHUP) {
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
+        row = id;
+    } else {
+        row = r0 + k;
+    }
+    const int64_t off = row * t.pitch;
+    const int st = __float_as_int(t.data[off + a.stamp_col]);
+    if (st >= upto) return;
+    it.t = st;
+    it.off = off;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        it.p[c] = ld4(t.data + off + 4 * c);
+        it.m[c] = ld4(a.m + off + 4 * c);
+        it.v[c] = ld4(a.v + off + 4 * c);
+    }
+}
+template <int CH, bool CATCHUP>
+__global__ void __launch_bounds__(128)
+replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int upto = __ldg(a.step);
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ReplayRow<CH> cur, nxt;
+    replay_row_fetch<CH, CATCHUP>(cur, k, n_items, t, a, r0, sorted_ids, upto);
+    bool cur_real = k < n_items;
+    k += stride;
+    replay_row_fetch<CH, CATCHUP>(nxt, k, n_items, t, a, r0, sorted_ids, upto);
+    while (true) {
+        if (cur.t >= upto) {
+            if (cur.off >= 0) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    embed_stamp(cur.p[c], 4 * c, a, upto);
+                    st4(t.data + cur.off + 4 * c, cur.p[c]);
+                    st4(a.m + cur.off + 4 * c, cur.m[c]);
+                    st4(a.v + cur.off + 4 * c, cur.v[c]);
+                }
+            }
+            if (!cur_real) break;
+            cur = nxt;
+            cur_real = k < n_items;
+            k += stride;
+            replay_row_fetch<CH, CATCHUP>(nxt, k, n_items, t, a, r0, sorted_ids, upto);
+            continue;
+        }
+        ++cur.t;
+        const float2 sc = __ldg(&a.sched[cur.t]);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) adam_l2_step4(cur.p[c], cur.m[c], cur.v[c], sc, a.h);
+    }
+}
+template <bool CATCHUP>
+static int launch_replay_rows(const TableView& t, const AdamView& a, int64_t r0, int64_t n_items,
+                              const uint32_t* sorted_ids, cudaStream_t st) {
+    const int ch = (t.used + 3) >> 2;
+    int64_t blocks = (n_items + 127) / 128;
+    const int grid = (int)(blocks < RLCTR_SMS * 8 ? (blocks < 1 ? 1 : blocks) : RLCTR_SMS * 8);
+    switch (ch) {
+        case 1: replay_rows_kernel<1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 2: replay_rows_kernel<2, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 3: replay_rows_kernel<3, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 4: replay_rows_kernel<4, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        default: return RLCTR_EUNSUPPORTED;
+    }
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
 // stamps are written after the replay kernel has completed (the chunks of one row are replayed by
 // different threads, each of which reads the row's stamp)
 __global__ void __launch_bounds__(256)
@@ -345,13 +450,13 @@ __global__ void __launch_bounds__(256)
 adam_flush_scalar_kernel(TableView t, AdamView a, int64_t r0, int64_t r1) {   // row_stride == 1 (LR)
     const int upto = __ldg(a.step);
     for (int64_t row = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < r1; row += (int64_t)gridDim.x * blockDim.x) {
-        const int st = a.stamp[row];
+        const int st = load_stamp(t, a, row);
         if (st >= upto) continue;
         const int64_t o = row * t.pitch;
         float p = t.data[o], m = a.m[o], v = a.v[o];
         adam_replay1(p, m, v, st, upto, a.sched, a.h);
         t.data[o] = p; a.m[o] = m; a.v[o] = v;
-        a.stamp[row] = upto;
+        if (a.stamp_col >= 0) t.data[o + a.stamp_col] = __int_as_float(upto); else a.stamp[row] = upto;
     }
 }
 __global__ void __launch_bounds__(256)
@@ -385,10 +490,10 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     const int step = __ldg(a.step) + 1;
     const int64_t o = (int64_t)id * t.pitch;
     float p = t.data[o], m = a.m[o], v = a.v[o];
-    if (a.stamp) {
-        const int st = a.stamp[id];
+    if (is_lazy(a)) {
+        const int st = load_stamp(t, a, id);
         adam_replay1(p, m, v, st, step - 1, a.sched, a.h);
-        a.stamp[id] = step;
+        if (a.stamp_col >= 0) t.data[o + a.stamp_col] = __int_as_float(step); else a.stamp[id] = step;
     }
     const float2 sc = __ldg(&a.sched[step]);
     adam_elem(p, m, v, acc, a.h, sc.x, sc.y);
@@ -401,13 +506,13 @@ rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, T
     const uint32_t id = __ldg(sorted_ids + k);
     if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
     const int upto = __ldg(a.step);
-    const int st = a.stamp[id];
+    const int st = load_stamp(t, a, id);
     if (st >= upto) return;
     const int64_t o = (int64_t)id * t.pitch;
     float p = t.data[o], m = a.m[o], v = a.v[o];
     adam_replay1(p, m, v, st, upto, a.sched, a.h);
     t.data[o] = p; a.m[o] = m; a.v[o] = v;
-    a.stamp[id] = upto;
+    if (a.stamp_col >= 0) t.data[o + a.stamp_col] = __int_as_float(upto); else a.stamp[id] = upto;
 }
 
 __global__ void __launch_bounds__(256)
@@ -444,6 +549,8 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
                        cudaStream_t st) {
     if (!sorted_ids || !sorted_slots || !grad || !table || !table->data || n < 0) return RLCTR_EINVAL;
     if (APPLY == 0 && (!opt || !opt->exp_avg || !opt->exp_avg_sq || !opt->sched || !opt->step)) return RLCTR_EINVAL;
+    if (APPLY == 0 && opt->stamp_col >= (table->row_pitch > 0 ? table->row_pitch : table->row_stride)) return RLCTR_EINVAL;
+    if (APPLY == 0 && opt->stamp_col >= 0 && table->row_stride > 32) return RLCTR_EUNSUPPORTED;   // wide rows: separate stamps
     if (APPLY == 1 && !dense_grad) return RLCTR_EINVAL;
     if ((grad->dlogit || grad->extra) && grad->fields <= 0) return RLCTR_EINVAL;
     if (n == 0) return RLCTR_OK;
@@ -536,7 +643,8 @@ extern "C" int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t*
 
 extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table* table,
                                   const rlctr_adam* opt, rlctr_stream_t stream) {
-    if (!sorted_ids || !table || !table->data || !opt || !opt->stamp || !opt->sched || !opt->step || n < 0)
+    if (!sorted_ids || !table || !table->data || !opt || (!opt->stamp && opt->stamp_col < 0) || !opt->sched || !opt->step ||
+        n < 0)
         return RLCTR_EINVAL;
     if (n == 0) return RLCTR_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -548,7 +656,8 @@ extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const r
         return RLCTR_OK;
     }
     if (t.rs % 4 != 0) return RLCTR_EUNSUPPORTED;
-    replay_kernel<true><<<grid_1d(n * (t.rs / 4), RLCTR_SMS * 8), 256, 0, st>>>(t, a, 0, n, sorted_ids);
+    if (a.stamp_col >= 0) return launch_replay_rows<true>(t, a, 0, n, sorted_ids, st);
+    replay_kernel<true><<<grid_1d(n * ((t.used + 3) / 4), RLCTR_SMS * 8), 256, 0, st>>>(t, a, 0, n, sorted_ids);
     RLCTR_LAUNCH_CHECK();
     catchup_stamp_kernel<<<grid_1d(n, RLCTR_SMS * 8), 256, 0, st>>>(sorted_ids, n, t.n_rows, a.stamp, a.step);
     RLCTR_LAUNCH_CHECK();
@@ -557,7 +666,7 @@ extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const r
 
 extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt, int64_t row_begin, int64_t row_end,
                                 rlctr_stream_t stream) {
-    if (!table || !table->data || !opt || !opt->stamp || !opt->sched || !opt->step) return RLCTR_EINVAL;
+    if (!table || !table->data || !opt || (!opt->stamp && opt->stamp_col < 0) || !opt->sched || !opt->step) return RLCTR_EINVAL;
     if (row_begin < 0 || row_end > table->n_rows || row_begin > row_end) return RLCTR_EINVAL;
     if (row_begin == row_end) return RLCTR_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -569,7 +678,8 @@ extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
         return RLCTR_OK;
     }
     if (t.rs % 4 != 0) return RLCTR_EUNSUPPORTED;
-    replay_kernel<false><<<grid_1d((row_end - row_begin) * (t.rs / 4), RLCTR_SMS * 8), 256, 0, st>>>(
+    if (a.stamp_col >= 0) return launch_replay_rows<false>(t, a, row_begin, row_end - row_begin, nullptr, st);
+    replay_kernel<false><<<grid_1d((row_end - row_begin) * ((t.used + 3) / 4), RLCTR_SMS * 8), 256, 0, st>>>(
         t, a, row_begin, row_end - row_begin, nullptr);
     RLCTR_LAUNCH_CHECK();
     stamp_fill_kernel<<<grid_1d(row_end - row_begin, RLCTR_SMS * 8), 256, 0, st>>>(a.stamp, a.step, row_begin, row_end);

@@ -80,10 +80,10 @@ class Adam:
                           stash.n, C.byref(g), C.byref(t), C.byref(a), _lib.ptr(ws), ws_bytes, st,
                           key=f"rlctr_rows_adam[{type(owner).__name__}]",
                           meta=dict(owner._meta(stash.n // stash.fields, stash.fields), extra=stash.extra is not None,
-                                    staged=stash.staged is not None, stamp=opt.stamp is not None))
+                                    staged=stash.staged is not None, stamp=opt.lazy))
             _lib.check(lib.rlctr_step_advance(_lib.ptr(opt.step), 1, st), "rlctr_step_advance")
             opt.host_step = self._host_step
-            if opt.stamp is not None:
+            if opt.lazy:
                 opt.dirty = True
                 if self.mode == "dense":
                     opt.flush(data)

@@ -256,7 +256,7 @@ class _TableModel(nn.Module):
         if track:
             sorted_pair = sort_ids(x, self._geom.n_rows)
             opt = self._opt
-            if opt is not None and opt.stamp is not None and opt.dirty:
+            if opt is not None and opt.lazy and opt.dirty:
                 lib = _lib.load()
                 t, a = table_struct(self.table.data, self._geom), opt.struct()
                 _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sorted_pair[0]), x.numel(), C.byref(t),

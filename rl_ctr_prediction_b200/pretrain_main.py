@@ -113,7 +113,7 @@ def fused_train_step(model, optimizer, features, labels):
     sid, sslot = Model.sort_ids(x, g.n_rows)
     opt = model._opt
     t = table_struct(model.table.data, g)
-    if opt is not None and opt.stamp is not None and opt.dirty:
+    if opt is not None and opt.lazy and opt.dirty:
         a = opt.struct()
         _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sid), x.numel(), C.byref(t), C.byref(a), st,
                   key=f"rlctr_rows_catchup[{type(model).__name__}]", meta=model._meta(B, F))

@@ -236,7 +236,7 @@ class ShardedCTR(nn.Module):
                 plan.sorted_recv = (self._geom.n_rows, Model._sort_ids(plan.recv_local, self._geom.n_rows))
             sorted_pair = plan.sorted_recv[1] if plan.n_recv else None
             opt = self._opt
-            if sorted_pair is not None and opt is not None and opt.stamp is not None and opt.dirty:
+            if sorted_pair is not None and opt is not None and opt.lazy and opt.dirty:
                 t, a = table_struct(self.table.data, self._geom), opt.struct()
                 _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sorted_pair[0]), plan.n_recv, C.byref(t),
                           C.byref(a), _lib.stream(), key=f"rlctr_rows_catchup[Sharded{self.kind}]",

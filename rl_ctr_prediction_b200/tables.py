@@ -52,9 +52,27 @@ class Geometry:
     def has_state(self):
         return self.row_pitch >= 3 * self.row_stride
 
+    @property
+    def used(self):
+        return max(self.lin_col + 1, self.emb_col + self.dim, 1)
+
+    @property
+    def stamp_col(self):
+        """Float offset inside the row record where the lazy-Adam stamp lives (-1: separate array).  LR records are
+        [w | m | v | stamp]; a row of at most 16 floats whose last active 16-byte chunk has a padding column keeps the
+        stamp there; anything else (full rows, wide FFM rows) uses a separate int32 array."""
+        if not self.has_state:
+            return -1
+        if self.row_stride == 1:
+            return 3 if self.row_pitch >= 4 else -1
+        if self.row_stride <= 16 and self.used % 4 != 0:
+            return self.used
+        return -1
+
     def with_state(self):
         """The trainable layout: Adam's exp_avg / exp_avg_sq interleaved with the row (one contiguous record)."""
-        return Geometry(self.n_rows, self.row_stride, self.lin_col, self.emb_col, self.dim, 3 * self.row_stride)
+        pitch = 4 if self.row_stride == 1 else 3 * self.row_stride
+        return Geometry(self.n_rows, self.row_stride, self.lin_col, self.emb_col, self.dim, pitch)
 
     def rows_only(self, n_rows=None):
         return Geometry(self.n_rows if n_rows is None else n_rows, self.row_stride, self.lin_col, self.emb_col, self.dim, 0)
@@ -124,21 +142,34 @@ class TableAdamState:
         else:
             self.exp_avg = torch.zeros_like(param)
             self.exp_avg_sq = torch.zeros_like(param)
-        self.stamp = None if mode == "sparse" else torch.zeros(geom.n_rows, dtype=torch.int32, device=dev)
+        self.stamp_col = -1
+        if mode == "sparse":
+            self.stamp = None
+        elif geom.stamp_col >= 0:
+            self.stamp = None                         # the stamp rides inside the record (tables.Geometry.stamp_col)
+            self.stamp_col = geom.stamp_col
+            param[:, self.stamp_col].zero_()
+        else:
+            self.stamp = torch.zeros(geom.n_rows, dtype=torch.int32, device=dev)
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)     # completed steps (device scalar)
         self.host_step = 0
         self.sched = AdamSchedule(lr, betas, dev)
         self.betas, self.eps, self.weight_decay = betas, float(eps), float(weight_decay)
         self.dirty = False           # True while some rows lag behind `step` (lazy mode)
 
+    @property
+    def lazy(self):
+        """True when untouched rows are owed their L2-only steps (modes 'lazy' and 'dense')."""
+        return self.stamp is not None or self.stamp_col >= 0
+
     def struct(self) -> _lib.Adam:
         return _lib.Adam(self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), _lib.ptr(self.stamp),
-                         _lib.ptr(self.sched.tensor), _lib.ptr(self.step), self.sched.length,
+                         _lib.ptr(self.sched.tensor), _lib.ptr(self.step), self.sched.length, self.stamp_col,
                          self.betas[0], self.betas[1], self.eps, self.weight_decay)
 
     def flush(self, data: torch.Tensor):
         """Replay the L2-only steps every row missed (rlctr_adam_flush)."""
-        if self.stamp is None or not self.dirty:
+        if not self.lazy or not self.dirty:
             return
         lib = _lib.load()
         t, a = table_struct(data, self.geom), self.struct()

@@ -86,7 +86,7 @@ def test_state_dict_is_reference_keyed_and_init_matches_seed(name):
     used[g.emb_col:g.emb_col + g.dim] = True
     assert torch.all(m.table.data[:, :g.row_stride][:, ~used] == 0)
     # trainable tables carry Adam's exp_avg / exp_avg_sq inside each row record, zero until an optimizer runs
-    assert g.row_pitch == 3 * g.row_stride and m.table.shape[1] == g.row_pitch
+    assert g.row_pitch == (4 if g.row_stride == 1 else 3 * g.row_stride) and m.table.shape[1] == g.row_pitch   # LR: [w|m|v|stamp]
     assert torch.all(m.table.data[:, g.row_stride:] == 0)
 
 

@@ -345,7 +345,7 @@ def test_sort_ids_stable(lib, n, n_rows):
 
 
 def adam_struct(m, v, stamp, sched, step, wd=1e-5):
-    return L().Adam(L().ptr(m), L().ptr(v), L().ptr(stamp), L().ptr(sched), L().ptr(step), sched.shape[0], 0.9, 0.999,
+    return L().Adam(L().ptr(m), L().ptr(v), L().ptr(stamp), L().ptr(sched), L().ptr(step), sched.shape[0], -1, 0.9, 0.999,
                     1e-8, wd)
 
 
