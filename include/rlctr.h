@@ -116,12 +116,14 @@ const char* rlctr_strerror(int code);
  *   logit[b]   = bias + sum_f w[x_f] (+ 0.5*sum_d[(sum_f v)^2 - sum_f v^2] if RLCTR_FM_TERM)
  *   pctr[b*pctr_stride] = sigmoid(logit)          (optional; stride lets M models fill [B,M])
  *   sums[b, :] = column sums over the F gathered rows (saved for the backward; optional)
- *   rows_out[b, f*dim + d] = v_f[d]               (bit-exact copy; optional)
+ *   rows_out[b*rows_pitch + f*dim + d] = v_f[d]   (bit-exact copy; optional; rows_pitch = 0 means fields*dim;
+ *                                                  a pitch that is a multiple of 4 floats lets the tower's first
+ *                                                  GEMM fetch the rows by TMA; pad columns are never written)
  * ------------------------------------------------------------------------------------ */
 #define RLCTR_FM_TERM 1
 int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, const float* bias,
                     float* logit, float* pctr, int64_t pctr_stride, float* sums, float* rows_out,
-                    int64_t batch, int32_t fields, int32_t flags, rlctr_stream_t stream);
+                    int64_t rows_pitch, int64_t batch, int32_t fields, int32_t flags, rlctr_stream_t stream);
 
 /* Plain bit-exact row gather out[k, :] = table[ids[k], :] (nn.Embedding.forward); the owner
  * side of the sharded lookup.  out has row_stride floats per row. */
@@ -235,18 +237,21 @@ int rlctr_reinforce_loss_bwd(const float* logits, const int64_t* act, const floa
  * K4  dense layers on the tcgen05 tensor cores (3xTF32 split: fp32-grade accuracy).
  * nn.Linear of the DeepFM tower (p_model.py:276-293) and of the policy networks
  * (PG_model.py:42-51, DDQN_model.py:20-52, DDPG_for_PG_model.py:20-81): weight [out,in] row-major,
- * bias [out], activations [batch, features] row-major (dense, no padding).
- *   fwd: y = x w^T + bias, ReLU fused if RLCTR_MLP_RELU
+ * bias [out], activations [batch, features] row-major; the layer INPUT x may be padded: ldx floats between its
+ * rows (0 = in_dim).  y, gy, dx, dw, db are dense.  When x, gy and the workspace are 16-byte aligned with
+ * ldx % 4 == 0 (and out_dim % 4 == 0 for the backward) the operands are fetched by TMA (csrc/mlp_tma.cu);
+ * any other shape takes the software-staged kernel (csrc/mlp.cu) -- same numbers, slower.
+ *   fwd: y = x w^T + bias, ReLU fused if RLCTR_MLP_RELU (ws: rlctr_mlp_ws_bytes bytes, or NULL = no TMA path)
  *   bwd: with RLCTR_MLP_RELU, gy is first masked IN PLACE by (y > 0) (y = the saved forward output);
  *        dx = gy w (optional), dw = gy^T x (optional, split-K with a fixed-order reduction),
  *        db = column sums of gy (optional).  ws: rlctr_mlp_ws_bytes(batch, in, out) bytes.
  * ------------------------------------------------------------------------------------ */
 #define RLCTR_MLP_RELU 1
 size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
-int rlctr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t batch,
+int rlctr_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t batch,
                      int32_t in_dim, int32_t out_dim, int32_t flags, void* ws, size_t ws_bytes,
                      rlctr_stream_t stream);
-int rlctr_linear_bwd(const float* x, const float* w, const float* y, float* gy, float* dx, float* dw,
+int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, const float* y, float* gy, float* dx, float* dw,
                      float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, void* ws,
                      size_t ws_bytes, rlctr_stream_t stream);
 

@@ -51,7 +51,7 @@ SIGNATURES = {
     "rlctr_version": (C.c_int, []),
     "rlctr_strerror": (C.c_char_p, [C.c_int]),
     "rlctr_launch_count": (C.c_ulonglong, []),
-    "rlctr_embed_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _P]),
+    "rlctr_embed_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _P]),
     "rlctr_gather_rows": (C.c_int, [_P, _I64, _TP, _P, _P]),
     "rlctr_ffm_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "rlctr_featemb_fwd": (C.c_int, [_P, _TP, _P, _I64, _I64, _I32, _P]),
@@ -69,8 +69,8 @@ SIGNATURES = {
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_mlp_ws_bytes": (_SZ, [_I64, _I32, _I32]),
-    "rlctr_linear_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
-    "rlctr_linear_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
+    "rlctr_linear_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
+    "rlctr_linear_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
     "rlctr_bucket_ws_bytes": (_SZ, [_I64, _I32]),
     "rlctr_bucket_by_owner": (C.c_int, [_P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
 }

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch,
                  int rs, int lin_col, int emb_col, int dim, const float* __restrict__ bias,
                  float* __restrict__ logit, float* __restrict__ pctr, int64_t pctr_stride,
-                 float* __restrict__ sums, float* __restrict__ rows_out,
+                 float* __restrict__ sums, float* __restrict__ rows_out, int64_t rows_pitch,
                  int64_t batch, int fields, int flags) {
     constexpr int RPW = 32 / LPR;                   // rows per warp request
     const int lane = threadIdx.x & 31;
@@ -76,8 +76,8 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
                 for (int k = 0; k < 4; ++k) {
                     if (!is_emb[k]) continue;
                     const int d = col0 + k - emb_col;
-                    if (chunk_on && fa < fields) rows_out[(b * fields + fa) * dim + d] = f4get(ra, k);
-                    if (chunk_on && fb < fields) rows_out[(b * fields + fb) * dim + d] = f4get(rb, k);
+                    if (chunk_on && fa < fields) rows_out[b * rows_pitch + fa * dim + d] = f4get(ra, k);
+                    if (chunk_on && fb < fields) rows_out[b * rows_pitch + fb * dim + d] = f4get(rb, k);
                 }
             }
         }
@@ -250,7 +250,7 @@ static int check_table(const rlctr_table* t) {
 
 extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, const float* bias,
                                float* logit, float* pctr, int64_t pctr_stride, float* sums,
-                               float* rows_out, int64_t batch, int32_t fields, int32_t flags,
+                               float* rows_out, int64_t rows_pitch, int64_t batch, int32_t fields, int32_t flags,
                                rlctr_stream_t stream) {
     int rc = check_table(table);
     if (rc) return rc;
@@ -259,6 +259,8 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
     cudaStream_t st = (cudaStream_t)stream;
     const int rs = table->row_stride;
     if (pctr && pctr_stride < 1) return RLCTR_EINVAL;
+    if (rows_pitch == 0) rows_pitch = (int64_t)fields * table->dim;
+    if (rows_out && rows_pitch < (int64_t)fields * table->dim) return RLCTR_EINVAL;
     if (rs == 1) {
         if (rows_out || (flags & RLCTR_FM_TERM) || table->lin_col != 0) return RLCTR_EUNSUPPORTED;
         int grid = grid_for_warps(batch, 8, 8);
@@ -273,7 +275,7 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
 #define LAUNCH_EMBED(L)                                                                              \
     embed_fwd_kernel<L><<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, pitch_of(table), rs, table->lin_col,   \
                                               table->emb_col, table->dim, bias, logit, pctr,         \
-                                              pctr_stride, sums, rows_out, batch, fields, flags)
+                                              pctr_stride, sums, rows_out, rows_pitch, batch, fields, flags)
     switch (rlctr_lanes_per_row(rs)) {
         case 1: LAUNCH_EMBED(1); break;
         case 2: LAUNCH_EMBED(2); break;

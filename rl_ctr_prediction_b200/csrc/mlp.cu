@@ -28,6 +28,7 @@
 // is XOR-ed with (row & 7).  Descriptor: start address, SBO = 1024 B (8-row group pitch), layout type
 // SWIZZLE_128B, version 1; advancing K by one MMA (8 tf32 = 32 B) adds 32 B to the start address.
 #include "common.cuh"
+#include "mlp_tma.cuh"
 
 namespace rlctr {
 
@@ -399,8 +400,8 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, in
 // rows, smem tree over the 8 partials.
 // wt != null: rows are scaled by wt[r] first (dW of a single-output layer: sum_b gy[b] * x[b, :])
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ Y, const float* __restrict__ wt, float* __restrict__ part, int64_t rows,
-                      int N, int rows_per_block) {
+colsum_partial_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ wt, float* __restrict__ part,
+                      int64_t rows, int N, int rows_per_block) {
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + lane;
@@ -409,7 +410,7 @@ colsum_partial_kernel(const float* __restrict__ Y, const float* __restrict__ wt,
     float s = 0.f;
     if (n < N)
 #pragma unroll 4
-        for (int64_t r = r0 + w; r < r1; r += 8) s += wt ? __ldg(wt + r) * __ldg(Y + r * N + n) : __ldg(Y + r * N + n);
+        for (int64_t r = r0 + w; r < r1; r += 8) s += wt ? __ldg(wt + r) * __ldg(Y + r * ldy + n) : __ldg(Y + r * ldy + n);
     red[w][lane] = s;
     __syncthreads();
     if (w == 0) {
@@ -429,7 +430,7 @@ relu_bwd_kernel(const float* g, const float* __restrict__ out, float* dy, int64_
 
 // ---- single-output layer (the tower's last Linear(200,1), p_model.py:290): GEMV-shaped, CUDA cores, HBM-bound
 __global__ void __launch_bounds__(256)
-gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+gemv_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ y, int64_t rows, int K, int relu) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -437,7 +438,7 @@ gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     const float b0 = bias ? __ldg(bias) : 0.f;
     for (int64_t r = warp0; r < rows; r += nwarps) {
         float s = 0.f;
-        for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + r * K + k), __ldg(w + k), s);
+        for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + r * ldx + k), __ldg(w + k), s);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(RLCTR_FULL, s, off);
         if (lane == 0) {
@@ -521,42 +522,87 @@ static int launch_gemm(const float* A, int64_t sam, int64_t sak, const float* B,
 
 constexpr int COLSUM_ROWS_PER_BLOCK = 512;
 
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+static inline int round4(int n) { return (n + 3) / 4 * 4; }
+
+// workspace of one Linear call: [split-K partials of dW | column-sum partials | W_hi | W_lo]
+struct MlpWs {
+    size_t wgrad, colsum, wsplit, total;
+    int in_pitch;
+};
+static MlpWs mlp_ws(int64_t batch, int in_dim, int out_dim) {
+    MlpWs w;
+    const GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
+    int splits = p.splits;
+    const int s2 = tma::plan_splits(out_dim, in_dim, (int)batch, true);
+    if (s2 > splits) splits = s2;
+    w.wgrad = align256((size_t)splits * out_dim * in_dim * sizeof(float));
+    const size_t yb = (size_t)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
+    w.colsum = align256(yb * ((size_t)out_dim + (out_dim == 1 ? (size_t)in_dim : 0)) * sizeof(float));
+    w.in_pitch = round4(in_dim);
+    w.wsplit = align256((size_t)out_dim * w.in_pitch * sizeof(float));
+    w.total = w.wgrad + w.colsum + 2 * w.wsplit + 256;
+    return w;
+}
+
 }  // namespace rlctr
 
 using namespace rlctr;
 
 extern "C" size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim) {
     if (batch <= 0 || in_dim <= 0 || out_dim <= 0) return 256;
-    GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
-    size_t wgrad = (size_t)p.splits * out_dim * in_dim * sizeof(float);
-    const size_t yb = (size_t)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
-    size_t colsum = yb * ((size_t)out_dim + (out_dim == 1 ? (size_t)in_dim : 0)) * sizeof(float);
-    return wgrad + colsum + 512;
+    return mlp_ws(batch, in_dim, out_dim).total;
 }
 
-extern "C" int rlctr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t batch,
+// (W_hi, W_lo) images of the weight at the end of the workspace; null when the workspace is absent / too small
+static bool split_weights_into(void* ws, size_t ws_bytes, const MlpWs& l, const float* w, int in_dim, int out_dim,
+                               cudaStream_t st, float** whi, float** wlo, int* rc) {
+    *rc = RLCTR_OK;
+    if (!tma::enabled() || !ws || ws_bytes < l.total || !rlctr_aligned16(ws) || out_dim == 1) return false;
+    char* base = reinterpret_cast<char*>(ws) + l.wgrad + l.colsum;
+    *whi = reinterpret_cast<float*>(base);
+    *wlo = reinterpret_cast<float*>(base + l.wsplit);
+    *rc = tma::split_weight(w, *whi, *wlo, out_dim, in_dim, l.in_pitch, st);
+    return *rc == RLCTR_OK;
+}
+
+extern "C" int rlctr_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t batch,
                                 int32_t in_dim, int32_t out_dim, int32_t flags, void* ws, size_t ws_bytes,
                                 rlctr_stream_t stream) {
-    (void)ws; (void)ws_bytes;
     if (!x || !w || !y || batch < 0 || in_dim <= 0 || out_dim <= 0) return RLCTR_EINVAL;
+    if (ldx == 0) ldx = in_dim;
+    if (ldx < in_dim) return RLCTR_EINVAL;
     if (batch == 0) return RLCTR_OK;
     if (batch > 0x7fffffff) return RLCTR_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int relu = (flags & RLCTR_MLP_RELU) ? 1 : 0;
     if (out_dim == 1) {
         int64_t blocks = (batch + 7) / 8;
-        gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, (cudaStream_t)stream>>>(
-            x, w, bias, y, batch, in_dim, (flags & RLCTR_MLP_RELU) ? 1 : 0);
+        gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
+            x, ldx, w, bias, y, batch, in_dim, relu);
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
     }
+    const MlpWs l = mlp_ws(batch, in_dim, out_dim);
+    float *whi = nullptr, *wlo = nullptr;
+    int rc = RLCTR_OK;
+    if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &rc)) {
+        rc = tma::gemm(tma::Operand{x, nullptr, ldx, false}, tma::Operand{whi, wlo, l.in_pitch, false}, y, out_dim, bias,
+                       (int)batch, out_dim, in_dim, relu, false, st);
+        if (rc != RLCTR_EUNSUPPORTED) return rc;
+    } else if (rc) {
+        return rc;
+    }
     GemmPlan p = plan_gemm((int)batch, out_dim, in_dim, false);
-    return launch_gemm(x, in_dim, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim,
-                       (flags & RLCTR_MLP_RELU) ? 1 : 0, p, (cudaStream_t)stream);
+    return launch_gemm(x, ldx, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim, relu, p, st);
 }
 
-extern "C" int rlctr_linear_bwd(const float* x, const float* w, const float* y, float* gy, float* dx, float* dw,
+extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, const float* y, float* gy, float* dx, float* dw,
                                 float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, void* ws,
                                 size_t ws_bytes, rlctr_stream_t stream) {
     if (!x || !w || !gy || batch <= 0 || in_dim <= 0 || out_dim <= 0) return RLCTR_EINVAL;
+    if (ldx == 0) ldx = in_dim;
+    if (ldx < in_dim) return RLCTR_EINVAL;
     if (batch > 0x7fffffff) return RLCTR_EUNSUPPORTED;
     if ((flags & RLCTR_MLP_RELU) && !y) return RLCTR_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
@@ -568,6 +614,11 @@ extern "C" int rlctr_linear_bwd(const float* x, const float* w, const float* y, 
         relu_bwd_kernel<<<grid, 256, 0, st>>>(gy, y, gy, n);
         RLCTR_LAUNCH_CHECK();
     }
+    const MlpWs l = mlp_ws(batch, in_dim, out_dim);
+    if ((dw || db) && (!ws || ws_bytes < l.total)) return RLCTR_EWORKSPACE;
+    float* part = reinterpret_cast<float*>(ws);
+    float* cpart = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.wgrad) : nullptr;
+    const int yb = (int)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
     if (out_dim == 1) {
         if (dx) {
             const int64_t n = batch * in_dim;
@@ -575,60 +626,66 @@ extern "C" int rlctr_linear_bwd(const float* x, const float* w, const float* y, 
             outer_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(dy, w, dx, batch, in_dim);
             RLCTR_LAUNCH_CHECK();
         }
-        if (dw || db) {
-            if (!ws || ws_bytes < rlctr_mlp_ws_bytes(batch, in_dim, out_dim)) return RLCTR_EWORKSPACE;
-            float* part = reinterpret_cast<float*>(ws);
-            const int yb = (int)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
-            if (dw) {
-                dim3 grid((in_dim + 31) / 32, yb);
-                colsum_partial_kernel<<<grid, 256, 0, st>>>(x, dy, part, batch, in_dim, COLSUM_ROWS_PER_BLOCK);
-                RLCTR_LAUNCH_CHECK();
-                splitk_reduce_kernel<<<(in_dim + 255) / 256, 256, 0, st>>>(part, dw, in_dim, yb);
-                RLCTR_LAUNCH_CHECK();
-            }
-            if (db) {
-                float* part2 = part + (size_t)yb * in_dim;
-                dim3 grid(1, yb);
-                colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, nullptr, part2, batch, 1, COLSUM_ROWS_PER_BLOCK);
-                RLCTR_LAUNCH_CHECK();
-                splitk_reduce_kernel<<<1, 256, 0, st>>>(part2, db, 1, yb);
-                RLCTR_LAUNCH_CHECK();
-            }
+        if (dw) {
+            dim3 grid((in_dim + 31) / 32, yb);
+            colsum_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, cpart, batch, in_dim, COLSUM_ROWS_PER_BLOCK);
+            RLCTR_LAUNCH_CHECK();
+            splitk_reduce_kernel<<<(in_dim + 255) / 256, 256, 0, st>>>(cpart, dw, in_dim, yb);
+            RLCTR_LAUNCH_CHECK();
+        }
+        if (db) {
+            float* part2 = cpart + (size_t)yb * in_dim;
+            dim3 grid(1, yb);
+            colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, 1, nullptr, part2, batch, 1, COLSUM_ROWS_PER_BLOCK);
+            RLCTR_LAUNCH_CHECK();
+            splitk_reduce_kernel<<<1, 256, 0, st>>>(part2, db, 1, yb);
+            RLCTR_LAUNCH_CHECK();
         }
         return RLCTR_OK;
     }
-    if (dx) {   // dX[B,in] = dY[B,out] * W[out,in]:  B operand = W^T, n-contiguous
-        GemmPlan p = plan_gemm((int)batch, in_dim, out_dim, false);
-        int rc = launch_gemm(dy, out_dim, 1, w, 1, in_dim, dx, in_dim, nullptr, (int)batch, in_dim, out_dim, 0, p, st);
+    if (dx) {   // dX[B,in] = dY[B,out] * W[out,in]:  B operand = W, contiguous along N
+        float *whi = nullptr, *wlo = nullptr;
+        int rc = RLCTR_OK;
+        bool done = false;
+        if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &rc)) {
+            rc = tma::gemm(tma::Operand{dy, nullptr, out_dim, false}, tma::Operand{whi, wlo, l.in_pitch, true}, dx, in_dim,
+                           nullptr, (int)batch, in_dim, out_dim, 0, false, st);
+            if (rc == RLCTR_OK) done = true;
+            else if (rc != RLCTR_EUNSUPPORTED) return rc;
+        } else if (rc) {
+            return rc;
+        }
+        if (!done) {
+            GemmPlan p = plan_gemm((int)batch, in_dim, out_dim, false);
+            rc = launch_gemm(dy, out_dim, 1, w, 1, in_dim, dx, in_dim, nullptr, (int)batch, in_dim, out_dim, 0, p, st);
+            if (rc) return rc;
+        }
+    }
+    if (dw) {   // dW[out,in] = dY^T[out,B] * X[B,in]: both operands contiguous along M / N, K = batch; split-K
+        const int64_t mn = (int64_t)out_dim * in_dim;
+        int splits = tma::enabled() ? tma::plan_splits(out_dim, in_dim, (int)batch, true) : 0;
+        int rc = RLCTR_EUNSUPPORTED;
+        if (splits >= 1)
+            rc = tma::gemm(tma::Operand{dy, nullptr, out_dim, true}, tma::Operand{x, nullptr, ldx, true}, splits == 1 ? dw : part,
+                           in_dim, nullptr, out_dim, in_dim, (int)batch, 0, true, st);
+        if (rc == RLCTR_EUNSUPPORTED) {
+            GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
+            splits = p.splits;
+            rc = launch_gemm(dy, 1, out_dim, x, 1, ldx, splits == 1 ? dw : part, in_dim, nullptr, out_dim, in_dim, (int)batch,
+                             0, p, st);
+        }
         if (rc) return rc;
-    }
-    if (dw || db) {
-        if (!ws || ws_bytes < rlctr_mlp_ws_bytes(batch, in_dim, out_dim)) return RLCTR_EWORKSPACE;
-    }
-    if (dw) {   // dW[out,in] = dY^T[out,B] * X[B,in]: both operands strided along K = batch; split-K
-        GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
-        float* part = reinterpret_cast<float*>(ws);
-        if (p.splits == 1) {
-            int rc = launch_gemm(dy, 1, out_dim, x, 1, in_dim, dw, in_dim, nullptr, out_dim, in_dim, (int)batch, 0, p, st);
-            if (rc) return rc;
-        } else {
-            int rc = launch_gemm(dy, 1, out_dim, x, 1, in_dim, part, in_dim, nullptr, out_dim, in_dim, (int)batch, 0, p, st);
-            if (rc) return rc;
-            const int64_t mn = (int64_t)out_dim * in_dim;
+        if (splits > 1) {
             int64_t blocks = (mn + 255) / 256;
-            splitk_reduce_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(part, dw, mn, p.splits);
+            splitk_reduce_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(part, dw, mn, splits);
             RLCTR_LAUNCH_CHECK();
         }
     }
     if (db) {
-        GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
-        float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) +
-                                               (((size_t)p.splits * out_dim * in_dim * sizeof(float) + 255) & ~(size_t)255));
-        const int yb = (int)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
         dim3 grid((out_dim + 31) / 32, yb);
-        colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, nullptr, part, batch, out_dim, COLSUM_ROWS_PER_BLOCK);
+        colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, out_dim, nullptr, cpart, batch, out_dim, COLSUM_ROWS_PER_BLOCK);
         RLCTR_LAUNCH_CHECK();
-        splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(part, db, out_dim, yb);
+        splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(cpart, db, out_dim, yb);
         RLCTR_LAUNCH_CHECK();
     }
     return RLCTR_OK;

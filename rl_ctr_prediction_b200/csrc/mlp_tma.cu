@@ -1,0 +1,513 @@
+// mlp_tma.cu -- K4 (second generation): the dense-layer GEMMs with TMA-fed operand tiles.
+//
+//     C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU)        fp32 in, fp32 out, 3xTF32 split (see mlp.cu)
+//
+// What changed against gemm3x_tf32_kernel (mlp.cu), which ncu showed latency-bound at 14 % tensor-pipe
+// activity with every warp parked on an mbarrier (profiles/r1_ncu_top_kernels.md):
+//   * operand tiles are fetched by TMA (cp.async.bulk.tensor, SWIZZLE_128B, zero fill outside the tensor): one
+//     elected thread issues whole boxes, no per-thread address arithmetic, no LDGSTS issue slots;
+//   * the small operand of forward / dgrad -- the WEIGHT -- is split into (hi, lo) ONCE per call by a tiny
+//     elementwise kernel and arrives ready-made through two tensor maps: nothing to convert on the B side;
+//   * the converter warps only touch the streamed activation tile: raw -> hi (in place) and lo, elementwise at
+//     identical byte offsets, so they are independent of the swizzle and of the operand's major-ness;
+//   * operands that are contiguous along M/N instead of K (dgrad's W, wgrad's dY^T and X) are consumed in place
+//     as MN-major UMMA operands (TMA boxes of 32 mn x 32 k in the SWIZZLE_128B_BASE32B layout): no 4-byte
+//     transposing copies.
+//
+// Warp roles (320 threads, one CTA per SM, persistent over output tiles):
+//     warps 0-3  converters        wait raw[s] -> split -> fence.proxy.async -> arrive full[s]
+//     warp  4    TMA producer      wait empty[s] -> expect_tx + boxes of A, B(hi), B(lo) -> raw[s]
+//     warp  5    MMA issuer        wait full[s] -> 4 k-steps x 3 tcgen05.mma -> commit empty[s] / tmem_full[acc]
+//     warps 6-9  epilogue          tcgen05.ld -> bias / ReLU -> global          (TMEM double-buffered)
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "mlp_tma.cuh"
+
+namespace rlctr {
+namespace tma {
+
+constexpr int BM = 128;                   // UMMA M
+constexpr int BK = 32;                    // fp32 per k-block row: 128 B = one swizzle atom
+constexpr int UK = 8;                     // K of one tcgen05.mma kind::tf32
+constexpr int CONV_WARPS = 4;
+constexpr int EPI_WARPS = 4;
+constexpr int PRODUCER_WARP = CONV_WARPS;
+constexpr int MMA_WARP = CONV_WARPS + 1;
+constexpr int THREADS = 32 * (CONV_WARPS + 2 + EPI_WARPS);
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t A_TILE_BYTES = BM * 128;
+
+struct Args {
+    float* C; int64_t ldc;                // C[(split*M + m)*ldc + n]
+    int cvec;
+    const float* bias;
+    int M, N, K;
+    int n_tile, m_tiles, n_tiles, splits, kb_per_split, stages;
+    int a_mn, b_mn;                       // 1: operand is contiguous along M (N) instead of K
+    int b_presplit;                       // 1: B arrives as (hi, lo) through mapB / mapBlo
+    int relu;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A protocol bug must surface as an error, not as a hung GPU box: give up after ~4 s.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+    printf("rlctr gemm3x_tma_kernel: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+           (int)threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 0x3fffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) mbar_timeout(bar, parity);
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one TMA box: 2-D tile of the tensor described by `map`, coordinates (c0 = innermost, c1), lands at `dst` and
+// reports its bytes on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+//   K-major : rows of 128 B (32 fp32 of K), 8-row groups 1024 B apart (SBO); one MMA (K = 8) advances 32 B
+//   MN-major: 32-bit operands have ONE legal MN-major layout, SWIZZLE_128B_BASE32B (Swizzle<2,5,2>: 32-byte chunks
+//             XOR-ed with (k-row & 3); TMA mode SWIZZLE_128B_ATOM_32B): k-rows of 128 B (32 mn), groups of 4 k-rows
+//             512 B apart (SBO), blocks of 32 mn 4096 B apart (LBO = one 32x32 TMA box); one MMA (K = 8) advances 1024 B
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;                  // LBO: next block of 32 mn
+    d |= (uint64_t)(512 >> 4) << 32;                   // SBO: next group of 4 k-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// raw -> (hi in place, lo): elementwise, same byte offset in both tiles (layout-agnostic)
+__device__ __forceinline__ void split_tile(char* hi, char* lo, int bytes, int tid) {
+    for (int off = tid * 16; off < bytes; off += CONV_WARPS * 32 * 16) {
+        const float4 x = *reinterpret_cast<const float4*>(hi + off);
+        const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+    }
+}
+
+struct TileWalk {                          // this CTA's (tile, k-block) sequence, identical in every role
+    int tile, kb0, kb1, mt, nt, split;
+};
+__device__ __forceinline__ bool tile_decode(TileWalk& w, const Args& g, int total_tiles) {
+    if (w.tile >= total_tiles) return false;
+    const int mn = g.m_tiles * g.n_tiles;
+    w.split = w.tile / mn;
+    const int r = w.tile - w.split * mn;
+    w.mt = r / g.n_tiles;
+    w.nt = r - w.mt * g.n_tiles;
+    const int kb_total = (g.K + BK - 1) / BK;
+    w.kb0 = w.split * g.kb_per_split;
+    w.kb1 = min(w.kb0 + g.kb_per_split, kb_total);
+    return true;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapBlo, const Args g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t raw_bar[MAX_STAGES], full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b_bytes = (uint32_t)g.n_tile * 128;
+    const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_bytes;
+    const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&raw_bar[s]), 1);
+            mbar_init(smem_u32(&full_bar[s]), CONV_WARPS * 32);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == PRODUCER_WARP && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        if (g.b_presplit) tma_prefetch_desc(&mapBlo);
+    }
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < CONV_WARPS) {
+        // ================= converters =================
+        const int tid = threadIdx.x;
+        int stage = 0;
+        uint32_t phase = 0;
+        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(smem_u32(&raw_bar[stage]), phase);
+                char* st = reinterpret_cast<char*>(smem + (size_t)stage * stage_bytes);
+                split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, tid);
+                if (!g.b_presplit) split_tile(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_bytes, b_bytes, tid);
+                fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(smem_u32(&full_bar[stage]));
+                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == PRODUCER_WARP) {
+        // ================= TMA producer =================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = A_TILE_BYTES + (g.b_presplit ? 2 * b_bytes : b_bytes);
+        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+            const int m0 = w.mt * BM, n0 = w.nt * g.n_tile;
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                if (lane == 0) {
+                    const uint32_t bar = smem_u32(&raw_bar[stage]);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + 2 * A_TILE_BYTES;
+                    const int k0 = kb * BK;
+                    mbar_expect_tx(bar, tx);
+                    if (g.a_mn) {
+                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, &mapA, m0 + 32 * j, k0, bar);
+                    } else {
+                        tma_load_2d(sa, &mapA, k0, m0, bar);
+                    }
+                    if (g.b_mn) {
+                        for (int j = 0; j < g.n_tile / 32; ++j) {
+                            tma_load_2d(sb + j * 4096, &mapB, n0 + 32 * j, k0, bar);
+                            if (g.b_presplit) tma_load_2d(sb + b_bytes + j * 4096, &mapBlo, n0 + 32 * j, k0, bar);
+                        }
+                    } else {
+                        tma_load_2d(sb, &mapB, k0, n0, bar);
+                        if (g.b_presplit) tma_load_2d(sb + b_bytes, &mapBlo, k0, n0, bar);
+                    }
+                }
+                __syncwarp();
+                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================= MMA issuer =================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, M = 128, N = n_tile,
+        // bit 15 / 16 = A / B is MN-major
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.a_mn ? 1 : 0) << 15) |
+                               ((uint32_t)(g.b_mn ? 1 : 0) << 16) | ((uint32_t)(g.n_tile >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+        const uint32_t a_step = g.a_mn ? 1024u : (uint32_t)UK * 4u;      // bytes per MMA along K
+        const uint32_t b_step = g.b_mn ? 1024u : (uint32_t)UK * 4u;
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+            mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);       // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+            for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                mbar_wait(smem_u32(&raw_bar[stage]), phase);                 // TMA bytes (the pre-split B tiles) landed
+                mbar_wait(smem_u32(&full_bar[stage]), phase);                // converters done
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES, b_hi = sa + 2 * A_TILE_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint32_t ao = (uint32_t)k * a_step, bo = (uint32_t)k * b_step;
+                        const uint64_t dah = g.a_mn ? desc_mn_major(a_hi + ao) : desc_k_major(a_hi + ao);
+                        const uint64_t dal = g.a_mn ? desc_mn_major(a_lo + ao) : desc_k_major(a_lo + ao);
+                        const uint64_t dbh = g.b_mn ? desc_mn_major(b_hi + bo) : desc_k_major(b_hi + bo);
+                        const uint64_t dbl = g.b_mn ? desc_mn_major(b_lo + bo) : desc_k_major(b_lo + bo);
+                        const uint32_t first = (kb > w.kb0 || k > 0) ? 1u : 0u;
+                        umma_tf32(d_tmem, dal, dbh, idesc, first);
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));                // frees the smem slot when these MMAs retire
+                    if (kb == w.kb1 - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                }
+                __syncwarp();
+                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+            if (w.kb1 <= w.kb0 && lane == 0) umma_commit(smem_u32(&tmem_full_bar[acc]));   // empty split
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+            const bool empty_split = w.kb1 <= w.kb0;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+            tc_fence_after();
+            const int m = w.mt * BM + q * 32 + lane;
+            float* crow = g.C + ((int64_t)w.split * g.M + m) * g.ldc;
+            const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+            const bool fuse = g.splits == 1;
+            for (int c0 = 0; c0 < g.n_tile; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                const int n0 = w.nt * g.n_tile + c0;
+                if (m < g.M && n0 < g.N) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x = empty_split ? 0.f : __uint_as_float(r[j]);
+                        if (fuse && g.bias && n0 + j < g.N) x += __ldg(g.bias + n0 + j);
+                        if (fuse && g.relu) x = fmaxf(x, 0.f);
+                        v[j] = x;
+                    }
+                    float* dst = crow + n0;
+                    if (n0 + 16 <= g.N && g.cvec == 4) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else if (n0 + 16 <= g.N && g.cvec == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < g.N) dst[j] = v[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// (hi, lo) images of a weight matrix [rows, cols] -> [rows, pitch] (pitch % 4 == 0, zero padded): the B
+// operand of forward (K-major) and dgrad (MN-major) reads them through TMA without any conversion.
+__global__ void __launch_bounds__(256)
+split_weight_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int rows, int cols, int pitch) {
+    const int64_t total = (int64_t)rows * pitch;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / pitch), c = (int)(i - (int64_t)r * pitch);
+        const float x = c < cols ? __ldg(w + (int64_t)r * cols + c) : 0.f;
+        const float h = tf32_rn(x);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp32 tensor [dim1][dim0] (dim0 contiguous, `pitch` floats between rows), box {32, box1}, SWIZZLE_128B, zero fill
+static bool make_map(CUtensorMap* map, const float* ptr, int64_t dim0, int64_t dim1, int64_t pitch, int box1,
+                     bool mn_major = false) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box1};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+static bool tma_ok(const float* p, int64_t pitch) { return p && (((uintptr_t)p) & 15u) == 0 && pitch % 4 == 0 && pitch > 0; }
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+int enabled() {
+    return env_int("RLCTR_GEMM_TMA", 1) != 0 && encode_fn() != nullptr;   // env read per call: tests switch paths
+}
+
+static int round_to(int n, int q) { return (n + q - 1) / q * q; }
+
+struct Plan {
+    int n_tile, n_tiles, m_tiles, splits, kb_per_split, stages;
+    size_t smem;
+};
+static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split) {
+    Plan p;
+    const int nt_max = env_int("RLCTR_GEMM_NT_MAX", 160);           // <= 160 keeps three 72 KB stages in flight
+    const int q = b_mn ? 32 : 16;
+    p.n_tiles = (N + nt_max - 1) / nt_max;
+    p.n_tile = round_to((N + p.n_tiles - 1) / p.n_tiles, q);
+    if (p.n_tile > 256) { p.n_tile = 256; p.n_tiles = (N + 255) / 256; }
+    p.m_tiles = (M + BM - 1) / BM;
+    const int kb_total = (K + BK - 1) / BK;
+    p.splits = 1;
+    if (allow_split) {
+        const int tiles = p.m_tiles * p.n_tiles;
+        int s = RLCTR_SMS / (tiles > 0 ? tiles : 1);
+        if (s < 1) s = 1;
+        int max_s = kb_total / 8;
+        if (max_s < 1) max_s = 1;
+        p.splits = s < max_s ? s : max_s;
+    }
+    p.kb_per_split = (kb_total + p.splits - 1) / p.splits;
+    if (p.kb_per_split < 1) p.kb_per_split = 1;
+    p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    if (p.splits < 1) p.splits = 1;
+    const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.n_tile * 128;
+    int st = (int)((size_t)(220 * 1024) / stage_bytes);
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st < 1) st = 1;
+    p.stages = st;
+    p.smem = stage_bytes * st + 1024;
+    return p;
+}
+int plan_splits(int M, int N, int K, bool b_mn) { return make_plan(M, N, K, b_mn, true).splits; }
+
+static int vec_of(const float* p, int64_t pitch) {
+    const uintptr_t a = (uintptr_t)p;
+    if (pitch % 4 == 0 && a % 16 == 0) return 4;
+    if (pitch % 2 == 0 && a % 8 == 0) return 2;
+    return 1;
+}
+
+int split_weight(const float* w, float* hi, float* lo, int rows, int cols, int pitch, cudaStream_t st) {
+    const int64_t total = (int64_t)rows * pitch;
+    int64_t blocks = (total + 255) / 256;
+    split_weight_kernel<<<(unsigned)(blocks < RLCTR_SMS * 4 ? blocks : RLCTR_SMS * 4), 256, 0, st>>>(w, hi, lo, rows, cols, pitch);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+// RLCTR_EUNSUPPORTED: the caller falls back to the software-staged kernel (mlp.cu)
+int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float* bias, int M, int N, int K, int relu,
+         bool allow_split, cudaStream_t st) {
+    if (!enabled()) return RLCTR_EUNSUPPORTED;
+    if (!tma_ok(A.ptr, A.pitch) || !tma_ok(B.ptr, B.pitch) || (B.lo && !tma_ok(B.lo, B.pitch))) return RLCTR_EUNSUPPORTED;
+    if (A.lo) return RLCTR_EUNSUPPORTED;                  // the streamed operand is always converted in the kernel
+    const Plan p = make_plan(M, N, K, B.mn_major, allow_split);
+    if (p.n_tile > 256 || (B.mn_major && p.n_tile % 32 != 0)) return RLCTR_EUNSUPPORTED;
+    CUtensorMap mA, mB, mBlo;
+    // K-major operand [R rows][K]: dims {K, R}, box {32, tile rows}.  MN-major operand [K rows][R]: dims {R, K}, box {32, 32}.
+    bool ok = A.mn_major ? make_map(&mA, A.ptr, M, K, A.pitch, 32, true) : make_map(&mA, A.ptr, K, M, A.pitch, BM);
+    ok = ok && (B.mn_major ? make_map(&mB, B.ptr, N, K, B.pitch, 32, true) : make_map(&mB, B.ptr, K, N, B.pitch, p.n_tile));
+    if (B.lo) ok = ok && (B.mn_major ? make_map(&mBlo, B.lo, N, K, B.pitch, 32, true) : make_map(&mBlo, B.lo, K, N, B.pitch, p.n_tile));
+    else mBlo = mB;
+    if (!ok) return RLCTR_EUNSUPPORTED;
+    Args g;
+    g.C = C; g.ldc = ldc; g.cvec = vec_of(C, ldc); g.bias = bias;
+    g.M = M; g.N = N; g.K = K;
+    g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
+    g.stages = p.stages;
+    g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
+    RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = total < RLCTR_SMS ? total : RLCTR_SMS;
+    gemm3x_tma_kernel<<<grid, THREADS, p.smem, st>>>(mA, mB, mBlo, g);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+}  // namespace tma
+}  // namespace rlctr

@@ -17,22 +17,35 @@ import torch.nn as nn
 from . import _lib
 
 
+def _rows_view(x):
+    """(x as [rows, K] fp32 CUDA tensor, floats between rows).  A row-padded view (the tower input DeepFM gathers into a
+    [B, round4(F*D)] buffer so that TMA can address it) is passed through with its pitch; anything else is made dense."""
+    if not x.is_cuda:
+        raise _lib.RlctrError("rl_ctr_prediction_b200.mlp.Linear runs on a CUDA (sm_100a) device only")
+    K = x.shape[-1]
+    if x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1 and x.stride(0) >= K and x.shape[0] > 1:
+        return x, x.stride(0)
+    x2 = x.reshape(-1, K).contiguous().float()
+    return x2, K
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
         lib = _lib.load()
-        if not x.is_cuda:
-            raise _lib.RlctrError("rl_ctr_prediction_b200.mlp.Linear runs on a CUDA (sm_100a) device only")
-        x2 = x.reshape(-1, x.shape[-1]).contiguous().float()
+        x2, ldx = _rows_view(x)
         B, K = x2.shape
         N = weight.shape[0]
         y = torch.empty(B, N, dtype=torch.float32, device=x.device)
         flags = _lib.RLCTR_MLP_RELU if relu else 0
         w = weight.detach().contiguous()
-        _lib.call("rlctr_linear_fwd", lib.rlctr_linear_fwd, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(bias.detach() if bias is not None else None),
-                  _lib.ptr(y), B, K, N, flags, None, 0, _lib.stream(), key=f"rlctr_linear_fwd[{K}x{N}]",
-                  meta={"B": B, "K": K, "N": N})
+        ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _lib.call("rlctr_linear_fwd", lib.rlctr_linear_fwd, x2.data_ptr(), ldx, _lib.ptr(w),
+                  _lib.ptr(bias.detach() if bias is not None else None), _lib.ptr(y), B, K, N, flags, _lib.ptr(ws), ws_bytes,
+                  _lib.stream(), key=f"rlctr_linear_fwd[{K}x{N}]", meta={"B": B, "K": K, "N": N})
         ctx.relu = relu
+        ctx.ldx = ldx
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x2, w, y if relu else None)
         ctx.in_shape = x.shape
@@ -55,7 +68,7 @@ class _LinearFn(torch.autograd.Function):
         ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         flags = _lib.RLCTR_MLP_RELU if ctx.relu else 0
-        _lib.call("rlctr_linear_bwd", lib.rlctr_linear_bwd, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(y), _lib.ptr(gy2), _lib.ptr(dx),
+        _lib.call("rlctr_linear_bwd", lib.rlctr_linear_bwd, x2.data_ptr(), ctx.ldx, _lib.ptr(w), _lib.ptr(y), _lib.ptr(gy2), _lib.ptr(dx),
                   _lib.ptr(dw), _lib.ptr(db), B, K, N, flags, _lib.ptr(ws), ws_bytes, _lib.stream(),
                   key=f"rlctr_linear_bwd[{K}x{N}]", meta={"B": B, "K": K, "N": N, "dx": need_dx})
         if dx is not None:

@@ -89,7 +89,9 @@ class _GatherInteract(torch.autograd.Function):
         logit = None if apply_sigmoid else out
         pctr = out if apply_sigmoid else None
         sums = None
-        rows = torch.empty(B, F * g.dim, dtype=torch.float32, device=dev) if want_rows else None
+        # tower input: rows of F*D floats at a 16-byte aligned pitch, so the first GEMM can fetch them by TMA
+        rows_pitch = (F * g.dim + 3) // 4 * 4
+        rows = torch.empty(B, rows_pitch, dtype=torch.float32, device=dev) if want_rows else None
         partners = None
         t = table_struct(table, g)
         if module._kind == "ffm":
@@ -103,7 +105,7 @@ class _GatherInteract(torch.autograd.Function):
                 sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
             flags = _lib.RLCTR_FM_TERM if module._fm_term else 0
             _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(ids), C.byref(t), _lib.ptr(bias), _lib.ptr(logit),
-                      _lib.ptr(pctr), 1, _lib.ptr(sums), _lib.ptr(rows), B, F, flags, _lib.stream(),
+                      _lib.ptr(pctr), 1, _lib.ptr(sums), _lib.ptr(rows), rows_pitch, B, F, flags, _lib.stream(),
                       key=f"rlctr_embed_fwd[{type(module).__name__}]",
                       meta=dict(module._meta(B, F), sums=sums is not None, rows=want_rows))
         ctx.module, ctx.sorted_pair, ctx.apply_sigmoid = module, sorted_pair, apply_sigmoid
@@ -114,6 +116,8 @@ class _GatherInteract(torch.autograd.Function):
         if rows is None:
             rows = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(rows)
+        elif rows_pitch != F * g.dim:
+            rows = rows[:, :F * g.dim]                  # [B, F*D] view of the padded buffer (pad columns never read)
         return out, rows
 
     @staticmethod

@@ -128,7 +128,7 @@ def fused_train_step(model, optimizer, features, labels):
         if model._kind == "fm":
             sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
         _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(x), C.byref(t), _lib.ptr(model.bias.data),
-                  _lib.ptr(logit), None, 1, _lib.ptr(sums), None, B, F, _lib.RLCTR_FM_TERM if model._fm_term else 0, st,
+                  _lib.ptr(logit), None, 1, _lib.ptr(sums), None, 0, B, F, _lib.RLCTR_FM_TERM if model._fm_term else 0, st,
                   key=f"rlctr_embed_fwd[{type(model).__name__}]", meta=dict(model._meta(B, F), sums=sums is not None, rows=False))
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     dlogit = torch.empty(B, dtype=torch.float32, device=dev)

@@ -271,7 +271,7 @@ class ShardedCTR(nn.Module):
                 trows = torch.empty(B, F * g.dim, dtype=torch.float32, device=dev)
             flags = _lib.RLCTR_FM_TERM if self.kind in ("FM", "DeepFM") else 0
             _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(pos), C.byref(t), _lib.ptr(self.bias.data), _lib.ptr(logit),
-                      None, 1, _lib.ptr(sums), _lib.ptr(trows), B, F, flags, _lib.stream(),
+                      None, 1, _lib.ptr(sums), _lib.ptr(trows), 0, B, F, flags, _lib.stream(),
                       key=f"rlctr_embed_fwd[Sharded{self.kind}]", meta=dict(self._meta(B, F), sums=sums is not None,
                                                                             rows=trows is not None))
         return logit, sums, partners, trows, gl

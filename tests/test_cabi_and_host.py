@@ -50,7 +50,7 @@ def test_struct_layouts_match_header():
 
 def test_argument_errors_need_no_gpu(lib):
     # argument validation happens before any CUDA call
-    assert lib.rlctr_embed_fwd(None, None, None, None, None, 1, None, None, 4, 15, 1, None) == -1
+    assert lib.rlctr_embed_fwd(None, None, None, None, None, 1, None, None, 0, 4, 15, 1, None) == -1
     assert lib.rlctr_generate_preds(None, None, None, None, None, None, None, 4, 3, 0, None) == -1
     assert lib.rlctr_sort_ids(None, 1, 1, None, None, None, 0, None) == -1
     assert lib.rlctr_rows_ws_bytes(1000) >= 16

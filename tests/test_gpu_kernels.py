@@ -121,7 +121,7 @@ def run_embed_fwd(lib, ids, tab, g, bias, fm=True, want_rows=True, want_sums=Tru
     rows = torch.empty(B, F * g.dim, device=DEV) if want_rows else None
     t = T().table_struct(tab, g)
     rc = lib.rlctr_embed_fwd(L().ptr(ids_d), C.byref(t), L().ptr(dev(bias)), L().ptr(logit), L().ptr(pctr), 1,
-                             L().ptr(sums), L().ptr(rows), B, F, 1 if fm else 0, st())
+                             L().ptr(sums), L().ptr(rows), 0, B, F, 1 if fm else 0, st())
     assert rc == 0, L().load().rlctr_strerror(rc)
     torch.cuda.synchronize()
     return logit, pctr, sums, rows
@@ -190,10 +190,10 @@ def test_embed_fwd_empty_and_errors(lib):
     ids, emb, lin, bias, _ = rng_case(1, 4, 15, 100, 10)
     tab, g = fused_fm_table(lin, emb)
     t = T().table_struct(tab, g)
-    assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(t), None, None, None, 1, None, None, 0, 15, 1, st()) == 0
-    assert lib.rlctr_embed_fwd(None, C.byref(t), None, None, None, 1, None, None, 4, 15, 1, st()) == -1
+    assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(t), None, None, None, 1, None, None, 0, 0, 15, 1, st()) == 0
+    assert lib.rlctr_embed_fwd(None, C.byref(t), None, None, None, 1, None, None, 0, 4, 15, 1, st()) == -1
     bad = L().Table(L().ptr(tab), 100, 10, 0, 1, 9)          # stride not a multiple of 4
-    assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(bad), None, None, None, 1, None, None, 4, 15, 1, st()) == -2
+    assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(bad), None, None, None, 1, None, None, 0, 4, 15, 1, st()) == -2
 
 
 def test_gather_rows_bit_exact(lib):
@@ -566,13 +566,33 @@ def linear_case(B, K, N, seed=0):
     return x, w, b
 
 
+def padded(x, ld):
+    """device copy of x [B, K] inside a [B, ld] buffer (pad columns hold NaN: nothing may read them)"""
+    B, K = x.shape
+    buf = torch.full((B, ld), float("nan"), device=DEV)
+    buf[:, :K] = dev(x)
+    return buf
+
+
+# path: "tma" = 16-byte aligned pitch + workspace (TMA-fed kernel, csrc/mlp_tma.cu); "staged" = RLCTR_GEMM_TMA=0, dense x
+# (software-staged kernel, csrc/mlp.cu: what any shape TMA cannot address falls back to).  K = 150 / 255 are not multiples of 4: "tma" pads the pitch.
 @pytest.mark.parametrize("B,K,N", [(1, 150, 300), (128, 32, 16), (1000, 150, 300), (777, 300, 200), (513, 200, 1),
                                    (4096, 255, 1024), (300, 1024, 512), (65536, 150, 300)])
 @pytest.mark.parametrize("relu", [0, 1])
-def test_linear_fwd_3xtf32(lib, B, K, N, relu):
+@pytest.mark.parametrize("path", ["tma", "staged"])
+def test_linear_fwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
+    monkeypatch.setenv("RLCTR_GEMM_TMA", "1" if path == "tma" else "0")
     x, w, b = linear_case(B, K, N, B + K + N)
     y = torch.empty(B, N, device=DEV)
-    assert lib.rlctr_linear_fwd(L().ptr(dev(x)), L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, None, 0, st()) == 0
+    if path == "tma":
+        ld = (K + 3) // 4 * 4
+        xd = padded(x, ld)
+        wsb = lib.rlctr_mlp_ws_bytes(B, K, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        rc = lib.rlctr_linear_fwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, L().ptr(ws), wsb, st())
+    else:
+        rc = lib.rlctr_linear_fwd(L().ptr(dev(x)), 0, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, None, 0, st())
+    assert rc == 0
     ref = x.astype(np.float64) @ w.astype(np.float64).T + b
     if relu:
         ref = np.maximum(ref, 0)
@@ -587,9 +607,10 @@ def test_linear_fwd_3xtf32(lib, B, K, N, relu):
 
 
 @pytest.mark.parametrize("B,K,N", [(64, 150, 300), (1000, 150, 300), (777, 300, 200), (513, 200, 1), (65536, 300, 200),
-                                   (4096, 255, 1024)])
+                                   (65536, 150, 300), (4096, 255, 1024), (100, 64, 30)])
 @pytest.mark.parametrize("relu", [0, 1])
-def test_linear_bwd_3xtf32(lib, B, K, N, relu):
+@pytest.mark.parametrize("path", ["tma", "staged"])
+def test_linear_bwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
     x, w, b = linear_case(B, K, N, B + K + N + 1)
     rng = np.random.default_rng(5)
     gy = rng.standard_normal((B, N)).astype(np.float32)
@@ -600,7 +621,13 @@ def test_linear_bwd_3xtf32(lib, B, K, N, relu):
     db = torch.empty(N, device=DEV)
     wsb = lib.rlctr_mlp_ws_bytes(B, K, N)
     ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
-    assert lib.rlctr_linear_bwd(L().ptr(dev(x)), L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd), L().ptr(dx), L().ptr(dw),
+    monkeypatch.setenv("RLCTR_GEMM_TMA", "1" if path == "tma" else "0")
+    if path == "tma":
+        ld = (K + 3) // 4 * 4
+        xd = padded(x, ld)
+    else:
+        ld, xd = K, dev(x)
+    assert lib.rlctr_linear_bwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd), L().ptr(dx), L().ptr(dw),
                                 L().ptr(db), B, K, N, relu, L().ptr(ws), wsb, st()) == 0
     g64 = gy.astype(np.float64)
     if relu:
@@ -611,6 +638,6 @@ def test_linear_bwd_3xtf32(lib, B, K, N, relu):
     # deterministic split-K: bit-identical on a second run
     dw2 = torch.empty_like(dw)
     gyd2 = dev(gy)
-    lib.rlctr_linear_bwd(L().ptr(dev(x)), L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd2), None, L().ptr(dw2), None, B, K, N,
+    lib.rlctr_linear_bwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd2), None, L().ptr(dw2), None, B, K, N,
                          relu, L().ptr(ws), wsb, st())
     assert torch.equal(dw, dw2)

@@ -225,7 +225,7 @@ def test_large_batch_round_trip_properties():
     logit = torch.empty(B, device=DEV)
     t = table_struct(m.table.data, g)
     assert lib.rlctr_embed_fwd(_lib.ptr(x), C.byref(t), _lib.ptr(m.bias.data), _lib.ptr(logit), None, 1, None,
-                               _lib.ptr(rows), B, F, 1, _lib.stream()) == 0
+                               _lib.ptr(rows), 0, B, F, 1, _lib.stream()) == 0
     assert torch.equal(rows.view(B, F, D), m.table.data[x][:, :, 1:1 + D])
     fe = Feature_embedding.Feature_Embedding(N, F, D, device=DEV)
     with torch.no_grad():
