@@ -40,6 +40,7 @@ constexpr int THREADS = 32 * (CONV_WARPS + 2 + EPI_WARPS);
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t A_TILE_BYTES = BM * 128;
+constexpr int BIAS_SMEM = 1024;              // bias values staged in shared memory for the epilogue
 
 struct Args {
     float* C; int64_t ldc;                // C[(split*M + m)*ldc + n]
@@ -119,7 +120,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r) {
+    if (W == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+}
+// the registers of a tcgen05.ld are valid only after tcgen05.wait::ld: pin every use behind the wait
+template <int W>
+__device__ __forceinline__ void tmem_ld_fence(uint32_t* r) {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < W; ++j) asm volatile("" : "+r"(r[j]));
+}
 // one TMA box: 2-D tile of the tensor described by `map`, coordinates (c0 = innermost, c1), lands at `dst` and
 // reports its bytes on `bar`
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -157,13 +179,36 @@ __device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr) {
 __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-// raw -> (hi in place, lo): elementwise, same byte offset in both tiles (layout-agnostic)
-__device__ __forceinline__ void split_tile(char* hi, char* lo, int bytes, int tid) {
-    for (int off = tid * 16; off < bytes; off += CONV_WARPS * 32 * 16) {
-        const float4 x = *reinterpret_cast<const float4*>(hi + off);
-        const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void split4(const float4& x, float4& h, float4& l) {
+    h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+    l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+}
+// raw -> (hi in place, lo): elementwise, same byte offset in both tiles (layout-agnostic).  `bytes` is a multiple
+// of 2048 (16 rows of 128 B); the 128 converter threads take two 16-byte chunks per iteration.
+__device__ __forceinline__ void split_tile(uint32_t hi, uint32_t lo, int bytes, int tid) {
+    constexpr int STEP = CONV_WARPS * 32 * 16;
+    for (int off = tid * 16; off < bytes; off += 2 * STEP) {
+        const bool two = off + STEP < bytes;
+        const float4 x0 = lds128(hi + off);
+        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (two) x1 = lds128(hi + off + STEP);
+        float4 h, l;
+        split4(x0, h, l);
+        sts128(hi + off, h);
+        sts128(lo + off, l);
+        if (two) {
+            split4(x1, h, l);
+            sts128(hi + off + STEP, h);
+            sts128(lo + off + STEP, l);
+        }
     }
 }
 
@@ -183,6 +228,67 @@ __device__ __forceinline__ bool tile_decode(TileWalk& w, const Args& g, int tota
     return true;
 }
 
+
+struct EpiCtx {
+    float* crow;               // &C[row of this thread][0]
+    const float* bias;         // global bias (null: none)
+    const float* sbias;        // the same bias staged in shared memory (null: read it from global)
+    int N, cvec;
+    bool row_ok, relu, zero;
+};
+// W accumulator columns [n0, n0 + W) of this thread's row: bias, ReLU, vector stores
+template <int W>
+__device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r, int n0) {
+    if (!e.row_ok || n0 >= e.N) return;
+    float v[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) v[j] = e.zero ? 0.f : __uint_as_float(r[j]);
+    if (e.sbias) {
+#pragma unroll
+        for (int j = 0; j < W; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(e.sbias + n0 + j);     // warp-wide broadcast
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    } else if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (n0 + j < e.N) v[j] += __ldg(e.bias + n0 + j);
+    }
+    if (e.relu) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    float* dst = e.crow + n0;
+    if (n0 + W <= e.N && e.cvec == 4) {
+#pragma unroll
+        for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else if (n0 + W <= e.N && e.cvec == 2) {
+#pragma unroll
+        for (int j = 0; j < W; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (n0 + j < e.N) dst[j] = v[j];
+    }
+}
+// one accumulator tile: the TMEM load of chunk c+1 is in flight while chunk c is written out
+template <int W>
+__device__ __forceinline__ void epilogue_tile(const EpiCtx& e, uint32_t taddr, int n_base, int n_tile) {
+    uint32_t ra[W], rb[W];
+    const int nch = n_tile / W;
+    tmem_ld<W>(taddr, ra);
+    for (int c = 0; c < nch; c += 2) {
+        tmem_ld_fence<W>(ra);
+        if (c + 1 < nch) tmem_ld<W>(taddr + (uint32_t)((c + 1) * W), rb);
+        epilogue_emit<W>(e, ra, n_base + c * W);
+        if (c + 1 < nch) {
+            tmem_ld_fence<W>(rb);
+            if (c + 2 < nch) tmem_ld<W>(taddr + (uint32_t)((c + 2) * W), ra);
+            epilogue_emit<W>(e, rb, n_base + (c + 1) * W);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapBlo, const Args g) {
@@ -190,9 +296,13 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     __shared__ __align__(8) uint64_t raw_bar[MAX_STAGES], full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[BIAS_SMEM];
 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool bias_in_smem = g.bias != nullptr && g.n_tiles * g.n_tile <= BIAS_SMEM;
+    if (bias_in_smem)
+        for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += THREADS) s_bias[i] = i < g.N ? __ldg(g.bias + i) : 0.f;
     const uint32_t b_bytes = (uint32_t)g.n_tile * 128;
     const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_bytes;
     const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
@@ -229,7 +339,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(smem_u32(&raw_bar[stage]), phase);
-                char* st = reinterpret_cast<char*>(smem + (size_t)stage * stage_bytes);
+                const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
                 split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, tid);
                 if (!g.b_presplit) split_tile(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_bytes, b_bytes, tid);
                 fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
@@ -330,37 +440,18 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
             const int m = w.mt * BM + q * 32 + lane;
-            float* crow = g.C + ((int64_t)w.split * g.M + m) * g.ldc;
+            EpiCtx e;
+            e.crow = g.C + ((int64_t)w.split * g.M + m) * g.ldc;
+            e.row_ok = m < g.M;
+            e.N = g.N;
+            e.cvec = g.cvec;
+            e.relu = (g.splits == 1) && g.relu;
+            e.bias = (g.splits == 1) ? g.bias : nullptr;
+            e.sbias = (g.splits == 1 && g.bias && bias_in_smem) ? s_bias : nullptr;
+            e.zero = empty_split;
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-            const bool fuse = g.splits == 1;
-            for (int c0 = 0; c0 < g.n_tile; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)c0, r);
-                tmem_ld_wait();
-                const int n0 = w.nt * g.n_tile + c0;
-                if (m < g.M && n0 < g.N) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x = empty_split ? 0.f : __uint_as_float(r[j]);
-                        if (fuse && g.bias && n0 + j < g.N) x += __ldg(g.bias + n0 + j);
-                        if (fuse && g.relu) x = fmaxf(x, 0.f);
-                        v[j] = x;
-                    }
-                    float* dst = crow + n0;
-                    if (n0 + 16 <= g.N && g.cvec == 4) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else if (n0 + 16 <= g.N && g.cvec == 2) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < g.N) dst[j] = v[j];
-                    }
-                }
-            }
+            if (g.n_tile % 32 == 0) epilogue_tile<32>(e, taddr, w.nt * g.n_tile, g.n_tile);
+            else epilogue_tile<16>(e, taddr, w.nt * g.n_tile, g.n_tile);
             tc_fence_before();
             mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
