@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--profile-steps", type=int, default=10, help="steps of the eager per-kernel timing pass")
     return ap.parse_args()
 
 
@@ -59,6 +61,20 @@ def peaks():
             d = json.load(fh)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    """Dense TF32 tensor peak: half the bf16 rate (tcgen05 kind::tf32 has K = 8 per MMA where kind::f16 has 16)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["bf16_tflops_sustained"]) / 2.0, "measured bf16_tflops_sustained / 2 (MEASURED_PEAKS.json; tf32 = half the bf16 rate)"
+    return 1400.0 / 2.0, "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)"
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
+NCU_TRAFFIC = {}
 
 
 def make_batch(gen, B, N, device):
@@ -307,26 +323,35 @@ def b200_arm(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (`value`) -------------------------------------
+    # N = 1: the whole three-model step is one CUDA graph (rl_ctr_prediction_b200/graphs.py): two eager warm-up steps,
+    # capture at the third, replays after that.  N > 1: the sharded path (variable all-to-all counts) runs eagerly.
     ms = build_models()
     batches = [make_batch(gen, B, N, dev) for _ in range(K + W)]
-    prof = _lib.KernelTimer()
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:
+        from rl_ctr_prediction_b200 import graphs
+        gstep = graphs.GraphedTrainStep(ms, lossf)
+        run_step = lambda x, y: gstep(x, y)
+    else:
+        gstep = None
+        run_step = lambda x, y: step(ms, x, y)
     for i in range(W):
-        step(ms, *batches[i])
+        run_step(*batches[i])
     barrier()
     clocks = Clocks(local)
     clocks.start()
     l0 = lib.rlctr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    _lib.set_timer(prof)
     e0.record()
     for i in range(K):
-        step(ms, *batches[W + i])
+        run_step(*batches[W + i])
     for m, _ in ms:
         m.flush()
     e1.record()
     barrier()
-    _lib.set_timer(None)
     launches = lib.rlctr_launch_count() - l0
+    if gstep is not None and gstep.graph is not None:
+        launches += gstep.launches_per_step * K          # replayed launches are not seen by the host-side tally
     clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -335,27 +360,62 @@ def b200_arm(args):
     ms_total = t.item()
     value = B * K * world / (ms_total / 1e3)
 
+    # ---------------- per-kernel pass: the same steps, eagerly, CUDA events around every library call --------------
+    prof = _lib.KernelTimer()
+    Kp = min(K, args.profile_steps)
+    _lib.set_timer(prof)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(Kp):
+        step(ms, *batches[W + i])
+    for m, _ in ms:
+        m.flush()
+    p1.record()
+    barrier()
+    _lib.set_timer(None)
+    ms_prof = p0.elapsed_time(p1)
+
     # ---------------- roofline of the dominant kernel --------------------------------------
     kern = prof.summary(alg_bytes)   # name -> (launches, mean ms, algorithmic bytes per launch)
     peak, peak_src = peaks()
-    roof = None
+    tpeak, tpeak_src = tensor_peak()
     gemm = {}
+    groups = {}                      # library entry point (all models) -> total ms in the profiled pass
+    for k, (n_l, mean_ms, alg) in kern.items():
+        groups[k.split("[")[0]] = groups.get(k.split("[")[0], 0.0) + n_l * mean_ms
     for k in list(kern):
         if k.startswith("rlctr_linear"):
             n_l, mean_ms, _ = kern.pop(k)
             fl = sum(gemm_flops(k, m) for _, _, m in prof.records[k]) / n_l
             gemm[k] = {"launches": n_l, "mean_ms": mean_ms, "fp32_equiv_TFLOPs": fl / (mean_ms / 1e3) / 1e12,
                        "tensor_pipe_TFLOPs_3x": 3 * fl / (mean_ms / 1e3) / 1e12}
-    if kern:
-        name = max(kern, key=lambda k: kern[k][0] * kern[k][1])
-        n_l, mean_ms, alg = kern[name]
-        achieved = alg / (mean_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "launches_timed": n_l, "mean_ms": mean_ms,
-                "share_of_step": n_l * mean_ms / ms_total,
-                "all_kernels": {k: {"launches": v[0], "mean_ms": v[1], "GBps": v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 else None}
-                                for k, v in kern.items()}}
+    all_kernels = {k: {"launches": v[0], "mean_ms": v[1], "GBps": v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 else None}
+                   for k, v in kern.items()}
+    shares = {g: round(tms / ms_prof, 4) for g, tms in sorted(groups.items(), key=lambda kv: -kv[1])}
+    top = max(groups, key=groups.get) if groups else None
+    roof = None
+    if top is not None and top.startswith("rlctr_linear"):
+        keys = [k for k in gemm if k.startswith(top)]
+        tot_ms = sum(gemm[k]["launches"] * gemm[k]["mean_ms"] for k in keys)
+        tot_fl = sum(3 * gemm_flops(k, m) for k in keys for _, _, m in prof.records[k])
+        achieved = tot_fl / (tot_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": top + " (gemm3x_tma_kernel: all tower layers)", "achieved": achieved, "peak": tpeak,
+                "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tpeak_src,
+                "flops_counted": "3 tf32 MMAs per fp32 product (3xTF32 split)", "share_of_step": groups[top] / ms_prof}
+    elif top is not None:
+        keys = [k for k in kern if k.split("[")[0] == top]
+        tot_ms = sum(kern[k][0] * kern[k][1] for k in keys)
+        tot_alg = sum(kern[k][0] * kern[k][2] for k in keys)
+        n_l = sum(kern[k][0] for k in keys)
+        achieved = tot_alg / (tot_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": tot_alg / n_l, "launches_timed": n_l, "mean_ms": tot_ms / n_l,
+                "share_of_step": groups[top] / ms_prof}
+    if roof is not None:
+        roof["share_of_step_by_entry_point"] = shares
+        roof["profiled_pass"] = {"steps": Kp, "ms_per_step": ms_prof / Kp, "mode": "eager, CUDA events around every library call"}
+        roof["all_kernels"] = all_kernels
     del ms, batches
     torch.cuda.empty_cache()
 
@@ -418,7 +478,8 @@ def b200_arm(args):
         line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world),
-                "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+                "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "cuda_graph": bool(use_graph)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,139 @@
+"""CUDA-graph replay of the training step (no counterpart in the reference: its loop launches ~200 ATen kernels
+per batch from Python, src/main/pretrain_main.py:96-103).
+
+One step of LR + FM + DeepFM is ~70 kernel launches of a few tens of microseconds each; issued one by one from
+Python (ctypes + autograd) the host cannot keep the GPU busy.  Every launch of the step is stream-ordered, takes its
+step index from a device scalar (:class:`.tables.TableAdamState`) and allocates nothing the caching allocator cannot
+serve from a private pool, so the whole step -- sort, catch-up, gather + interaction, tower GEMMs, loss, backward,
+segment-reduce + Adam, dense Adam -- is captured once and replayed with new ids / labels copied into static buffers.
+
+    step = GraphedTrainStep([(model, optimizer), ...], loss_fn)
+    for features, labels in batches:            # fixed batch shape; a different shape takes the eager path
+        losses = step(features, labels)         # list of device scalars, one per model
+
+The first ``eager_steps`` calls run eagerly (they are real training steps: lazily created state -- Adam moments,
+workspaces -- must exist before capture); the next call captures and replays.  Numbers are those of the eager path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from . import p_model as Model
+
+
+def eager_step(model, optimizer, loss_fn, x, y):
+    """One training step of one model: the fused loss head for tower-less models, autograd for DeepFM
+    (src/main/pretrain_main.py:96-102)."""
+    from . import pretrain_main as PM
+    if isinstance(model, Model.DeepFM):
+        p = model(x)
+        tl = loss_fn(p, y.reshape(-1, 1).float())
+        model.zero_grad()
+        tl.backward()
+        optimizer.step()
+        return tl.detach()             # keep no autograd graph alive between steps (its nodes pin a stream)
+    return PM.fused_train_step(model, optimizer, x, y)
+
+
+class GraphedTrainStep:
+    def __init__(self, pairs, loss_fn=None, eager_steps=2, steps_ahead=65536):
+        self.pairs = list(pairs)
+        self.loss_fn = loss_fn if loss_fn is not None else torch.nn.BCELoss()
+        self.eager_left = int(eager_steps)
+        self.steps_ahead = int(steps_ahead)
+        self.graph = None
+        self.x = self.y = None
+        self.losses = None
+        self.launches_per_step = 0
+        self.stream = None             # warm-up steps and the capture share one side stream (autograd's AccumulateGrad
+                                       # nodes remember the stream they were created on)
+
+    # ---- host-side bookkeeping a replay must redo (the kernels advance the device counters themselves) -----------
+    def _optimizers(self):
+        seen = []
+        for _, opt in self.pairs:
+            if opt not in seen:
+                seen.append(opt)
+        return seen
+
+    def _note_replayed_step(self):
+        for opt in self._optimizers():
+            opt._host_step += 1
+            for owner in opt._tables:
+                owner._opt.host_step = opt._host_step
+                if owner._opt.lazy:
+                    owner._opt.dirty = True
+            if opt._dense_step is not None:
+                opt._dense_done += 1
+
+    def _room(self):
+        """Adam's per-step scalars are tabulated on the device; a captured graph holds the table's address, so
+        the table must already cover the steps the graph will be replayed for."""
+        for opt in self._optimizers():
+            for owner in opt._tables:
+                if opt._host_step + 4 >= owner._opt.sched.length:
+                    return False
+            if opt._dense_sched is not None and opt._dense_done + 4 >= opt._dense_sched.length:
+                return False
+        return True
+
+    def _reserve(self):
+        for opt in self._optimizers():
+            for owner in opt._tables:
+                owner._opt.sched.ensure(opt._host_step + self.steps_ahead)
+            if opt._dense_sched is not None:
+                opt._dense_sched.ensure(opt._dense_done + self.steps_ahead)
+
+    def _eager(self, x, y):
+        return [eager_step(m, opt, self.loss_fn, x, y) for m, opt in self.pairs]
+
+    def _eager_on_side_stream(self, x, y):
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=self.pairs[0][0].table.device)
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._eager(x, y)
+        cur.wait_stream(self.stream)
+        return out
+
+    def _capture(self, x, y):
+        if _lib.timing():
+            raise _lib.RlctrError("per-kernel timing (KernelTimer) cannot be recorded inside a graph capture")
+        self._reserve()
+        dev = self.pairs[0][0].table.device
+        self.x = torch.empty(tuple(x.shape), dtype=x.dtype, device=dev)
+        self.y = torch.empty(tuple(y.shape), dtype=y.dtype, device=dev)
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        lib = _lib.load()
+        torch.cuda.synchronize()
+        l0 = lib.rlctr_launch_count()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            self.losses = self._eager(self.x, self.y)
+        self.launches_per_step = int(lib.rlctr_launch_count() - l0)
+        self.graph = g
+        # the capture ran the Python side of one step (host counters advanced) but no kernel: replay it now
+        g.replay()
+
+    def __call__(self, x, y):
+        dev = self.pairs[0][0].table.device
+        if self.graph is not None and tuple(x.shape) == tuple(self.x.shape) and self._room():
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
+            self.graph.replay()
+            self._note_replayed_step()
+            return self.losses
+        if self.graph is not None and tuple(x.shape) == tuple(self.x.shape):
+            self.graph = None                      # schedule table exhausted: it will be re-tabulated and re-captured
+        if self.graph is None and self.eager_left <= 0 and (self.x is None or tuple(x.shape) == tuple(self.x.shape)):
+            self._capture(x, y)
+            return self.losses
+        # warm-up steps, and batches of another shape (the last partial batch of an epoch): the eager path
+        if self.graph is None:
+            self.eager_left -= 1
+        return self._eager_on_side_stream(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True))

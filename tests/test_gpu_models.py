@@ -309,3 +309,50 @@ def test_sharded_world1_equals_single_gpu(golden, name, single_rank_group):
     if m.mlp is not None:
         single.mlp.load_state_dict(m.mlp.state_dict())
     assert_state(single, state_from_golden(golden, f"train/{name}/final"))
+
+
+def test_graphed_step_equals_eager_step():
+    """CUDA-graph replay of the LR + FM + DeepFM step (rl_ctr_prediction_b200/graphs.py) gives bit-identical
+    tables, tower weights and losses to the same steps launched eagerly (same kernels, same order)."""
+    import copy
+    from rl_ctr_prediction_b200 import graphs, optim
+    N, B, steps = 5000, 512, 7
+    rng = np.random.default_rng(3)
+    xs = [torch.as_tensor(rng.integers(0, N, size=(B, F))).to(DEV) for _ in range(steps)]
+    ys = [torch.as_tensor((rng.random(B) < 0.3).astype(np.int64)).to(DEV) for _ in range(steps)]
+    lossf = torch.nn.BCELoss()
+
+    def make():
+        torch.manual_seed(5)
+        ms = []
+        for name in ("LR", "FM", "DeepFM"):
+            m = build(name, N)
+            with torch.no_grad():
+                m.table.mul_(0.1)
+            m.to(DEV).train()
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.Dropout):
+                    mod.p = 0.0                    # dropout masks are drawn from different Philox offsets in a graph
+            ms.append((m, optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)))
+        return ms
+
+    eager, graphed = make(), make()
+    for (a, _), (b, _) in zip(eager, graphed):
+        b.load_state_dict(copy.deepcopy(a.state_dict()))
+    gstep = graphs.GraphedTrainStep(graphed, lossf, eager_steps=2)
+    for i in range(steps):
+        le = [graphs.eager_step(m, opt, lossf, xs[i], ys[i]) for m, opt in eager]
+        lg = gstep(xs[i], ys[i])
+        for a, b in zip(le, lg):
+            assert torch.equal(a.detach().reshape(()), b.detach().reshape(())), i
+    assert gstep.graph is not None and gstep.launches_per_step > 20
+    # a batch of another shape runs eagerly between replays and the graph stays valid
+    xo, yo = xs[0][:100].contiguous(), ys[0][:100].contiguous()
+    [graphs.eager_step(m, opt, lossf, xo, yo) for m, opt in eager]
+    gstep(xo, yo)
+    [graphs.eager_step(m, opt, lossf, xs[1], ys[1]) for m, opt in eager]
+    gstep(xs[1], ys[1])
+    for (a, _), (b, _) in zip(eager, graphed):
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), k
