@@ -356,46 +356,55 @@ struct ReplayRow {
     int64_t off;
     int t;
 };
-template <int CH, bool CATCHUP>
-__device__ __forceinline__ void replay_row_fetch(ReplayRow<CH>& it, int64_t k, int64_t n_items, const TableView& t,
-                                                 const AdamView& a, int64_t r0, const uint32_t* __restrict__ sorted_ids,
-                                                 int upto) {
-    it.off = -1;
-    it.t = upto;
-    if (k >= n_items) return;
-    int64_t row;
-    if (CATCHUP) {
-        const uint32_t id = __ldg(sorted_ids + k);
-        if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
-        row = id;
-    } else {
-        row = r0 + k;
-    }
-    const int64_t off = row * t.pitch;
-    const int st = __float_as_int(t.data[off + a.stamp_col]);
-    if (st >= upto) return;
-    it.t = st;
-    it.off = off;
+// row of work item k: FLUSH -> r0 + k; CATCHUP -> the id at sorted position k if that position is a run head.
+// The loads it issues are only consumed one item later (software prefetch of the id stream).
+template <bool CATCHUP>
+__device__ __forceinline__ int64_t replay_row_of(int64_t k, int64_t n_items, int64_t r0, const uint32_t* __restrict__ sorted_ids,
+                                                 int64_t n_rows) {
+    if (k >= n_items) return -1;
+    if (!CATCHUP) return r0 + k;
+    const uint32_t id = __ldg(sorted_ids + k);
+    const uint32_t prev = k > 0 ? __ldg(sorted_ids + k - 1) : 0xffffffffu;
+    return (id < (uint64_t)n_rows && prev != id) ? (int64_t)id : -1;
+}
+// issue the loads of a whole record WITHOUT looking at its stamp first: one DRAM round trip instead of two, and
+// nothing in the caller depends on the data until the item becomes current (a full replay of another row later)
+template <int CH>
+__device__ __forceinline__ void replay_row_issue(ReplayRow<CH>& it, int64_t row, const TableView& t, const AdamView& a) {
+    it.off = row < 0 ? -1 : row * t.pitch;
+    if (row >= 0) {
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        it.p[c] = ld4(t.data + off + 4 * c);
-        it.m[c] = ld4(a.m + off + 4 * c);
-        it.v[c] = ld4(a.v + off + 4 * c);
+        for (int c = 0; c < CH; ++c) {
+            it.p[c] = ld4(t.data + it.off + 4 * c);
+            it.m[c] = ld4(a.m + it.off + 4 * c);
+            it.v[c] = ld4(a.v + it.off + 4 * c);
+        }
     }
 }
+// the item becomes current: read the in-record stamp out of the data that has landed; up-to-date rows are dropped
+template <int CH>
+__device__ __forceinline__ void replay_row_arm(ReplayRow<CH>& it, const AdamView& a, int upto) {
+    it.t = upto;
+    if (it.off < 0) return;
+    // the in-record stamp sits in the first padding column (= `used`, tables.Geometry.stamp_col), i.e. always in the
+    // LAST active chunk: a compile-time register, only the element inside it is a run-time select
+    const int st = __float_as_int(f4get(it.p[CH - 1], a.stamp_col & 3));
+    if (st >= upto) it.off = -1; else it.t = st;
+}
 template <int CH, bool CATCHUP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int upto = __ldg(a.step);
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t kc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // index of the current item
+    if (kc >= n_items) return;
     ReplayRow<CH> cur, nxt;
-    replay_row_fetch<CH, CATCHUP>(cur, k, n_items, t, a, r0, sorted_ids, upto);
-    bool cur_real = k < n_items;
-    k += stride;
-    replay_row_fetch<CH, CATCHUP>(nxt, k, n_items, t, a, r0, sorted_ids, upto);
+    replay_row_issue<CH>(cur, replay_row_of<CATCHUP>(kc, n_items, r0, sorted_ids, t.n_rows), t, a);
+    replay_row_issue<CH>(nxt, replay_row_of<CATCHUP>(kc + stride, n_items, r0, sorted_ids, t.n_rows), t, a);
+    int64_t row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
+    replay_row_arm<CH>(cur, a, upto);
     while (true) {
-        if (cur.t >= upto) {
+        if (cur.t >= upto) {                             // current item finished (or had nothing to do): switch
             if (cur.off >= 0) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
@@ -405,11 +414,12 @@ replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const u
                     st4(a.v + cur.off + 4 * c, cur.v[c]);
                 }
             }
-            if (!cur_real) break;
-            cur = nxt;
-            cur_real = k < n_items;
-            k += stride;
-            replay_row_fetch<CH, CATCHUP>(nxt, k, n_items, t, a, r0, sorted_ids, upto);
+            kc += stride;
+            if (kc >= n_items) break;
+            cur = nxt;                                   // its loads were issued one whole item ago
+            replay_row_issue<CH>(nxt, row2, t, a);       // row2's id was fetched one item ago: no dependent wait here
+            row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
+            replay_row_arm<CH>(cur, a, upto);
             continue;
         }
         ++cur.t;
