@@ -247,13 +247,22 @@ int rlctr_reinforce_loss_bwd(const float* logits, const int64_t* act, const floa
  *        db = column sums of gy (optional).  ws: rlctr_mlp_ws_bytes(batch, in, out) bytes.
  * ------------------------------------------------------------------------------------ */
 #define RLCTR_MLP_RELU 1
+#define RLCTR_MLP_DROPOUT 2     /* fwd: y = keep ? y / (1-p) : 0 after bias / ReLU (nn.Dropout in train mode, p_model.py:284) */
+#define RLCTR_MLP_DX_MASK 4     /* bwd: dx *= (x > 0 ? dx_scale : 0): the ReLU (+dropout) backward of the layer that
+                                   produced x, fused into this layer's dgrad epilogue */
 size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
+/* Dropout mask: keep(element i) = hash(rng_state[0] (seed), rng_state[1] (counter) + i) >= p * 2^32, i = row * out_dim + col.
+ * rng_state is DEVICE memory so that a captured CUDA graph draws a new mask on every replay; rlctr_rng_advance moves the
+ * counter (call it with batch * out_dim after each forward that used the state).  The mask is not stored: the backward
+ * recovers it from the saved output (y == 0 <=> clipped by ReLU or dropped; gy_scale = 1 / (1-p)). */
+int rlctr_rng_advance(uint64_t* rng_state, uint64_t delta, rlctr_stream_t stream);
 int rlctr_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t batch,
-                     int32_t in_dim, int32_t out_dim, int32_t flags, void* ws, size_t ws_bytes,
-                     rlctr_stream_t stream);
+                     int32_t in_dim, int32_t out_dim, int32_t flags, float dropout_p, const uint64_t* rng_state,
+                     void* ws, size_t ws_bytes, rlctr_stream_t stream);
+/* RLCTR_MLP_RELU: gy <- gy * (y > 0 ? gy_scale : 0) in place first.  RLCTR_MLP_DX_MASK: see above (x is the mask source). */
 int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, const float* y, float* gy, float* dx, float* dw,
-                     float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, void* ws,
-                     size_t ws_bytes, rlctr_stream_t stream);
+                     float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, float gy_scale,
+                     float dx_scale, void* ws, size_t ws_bytes, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Multi-GPU row sharding (no counterpart in the reference, which is single-device: SURVEY section 8e).

@@ -18,6 +18,8 @@ RLCTR_FM_TERM = 1
 RLCTR_STAGED_PARTNER = 1
 RLCTR_REDUCE_WS_BYTES = 16640
 RLCTR_MLP_RELU = 1
+RLCTR_MLP_DROPOUT = 2
+RLCTR_MLP_DX_MASK = 4
 
 
 class RlctrError(RuntimeError):
@@ -69,8 +71,9 @@ SIGNATURES = {
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_mlp_ws_bytes": (_SZ, [_I64, _I32, _I32]),
-    "rlctr_linear_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
-    "rlctr_linear_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _SZ, _P]),
+    "rlctr_rng_advance": (C.c_int, [_P, C.c_uint64, _P]),
+    "rlctr_linear_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, C.c_float, _P, _P, _SZ, _P]),
+    "rlctr_linear_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, C.c_float, C.c_float, _P, _SZ, _P]),
     "rlctr_bucket_ws_bytes": (_SZ, [_I64, _I32]),
     "rlctr_bucket_by_owner": (C.c_int, [_P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
 }

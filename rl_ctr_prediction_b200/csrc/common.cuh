@@ -139,4 +139,24 @@ __device__ __forceinline__ void adam_replay1(float& p, float& m, float& v, int f
     }
 }
 
+// ---- counter-based dropout mask (mlp.cu / mlp_tma.cu) ----------------------------------------------------------
+// keep(element) = hash(seed, counter + element index) >= p * 2^32.  (seed, counter) live in device memory so that a
+// CUDA-graph replay draws a fresh mask every step (rlctr_rng_advance moves the counter).  Two rounds of a 32-bit
+// avalanche mix (multiply-xorshift) over the 128 bits of (seed, index): enough for dropout, 10 integer ops.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
+    uint32_t h = mix32((uint32_t)idx ^ (uint32_t)seed);
+    h = mix32(h ^ (uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32) ^ 0x9e3779b9U);
+    return h >= thresh;
+}
+static inline uint32_t dropout_thresh(float p) {
+    double t = (double)p * 4294967296.0;
+    if (t < 0.0) t = 0.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    return (uint32_t)t;
+}
+
 }  // namespace rlctr

@@ -421,12 +421,31 @@ colsum_partial_kernel(const float* __restrict__ Y, int64_t ldy, const float* __r
     }
 }
 
-// dY = g * (out > 0)  (ReLU backward on the saved post-activation), elementwise
+// dY = g * (out > 0 ? scale : 0)  (ReLU [+ dropout: scale = 1/(1-p)] backward on the saved output), elementwise
 __global__ void __launch_bounds__(256)
-relu_bwd_kernel(const float* g, const float* __restrict__ out, float* dy, int64_t n) {
+relu_bwd_kernel(const float* g, const float* __restrict__ out, float* dy, int64_t n, float scale) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dy[i] = __ldg(out + i) > 0.f ? g[i] : 0.f;
+        dy[i] = __ldg(out + i) > 0.f ? g[i] * scale : 0.f;
 }
+// dx[r, k] *= (x[r*ldx + k] > 0 ? scale : 0): the mask of the layer below applied to a dense dx (fallback of the fused
+// dgrad epilogue of mlp_tma.cu)
+__global__ void __launch_bounds__(256)
+mask_rows_kernel(float* __restrict__ dx, const float* __restrict__ x, int64_t ldx, int64_t rows, int K, float scale) {
+    const int64_t total = rows * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K;
+        const int k = (int)(i - r * K);
+        dx[i] = __ldg(x + r * ldx + k) > 0.f ? dx[i] * scale : 0.f;
+    }
+}
+// y[i] = keep(i) ? y[i] / (1-p) : 0 with the mask of common.cuh (fallback of the fused forward epilogue)
+__global__ void __launch_bounds__(256)
+dropout_kernel(float* __restrict__ y, int64_t n, const uint64_t* __restrict__ state, uint32_t thresh, float scale) {
+    const uint64_t seed = state[0], ctr = state[1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = dropout_keep(seed, ctr + (uint64_t)i, thresh) ? y[i] * scale : 0.f;
+}
+__global__ void rng_advance_kernel(uint64_t* state, uint64_t delta) { state[1] += delta; }
 
 // ---- single-output layer (the tower's last Linear(200,1), p_model.py:290): GEMV-shaped, CUDA cores, HBM-bound
 __global__ void __launch_bounds__(256)
@@ -449,11 +468,15 @@ gemv_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
     }
 }
 __global__ void __launch_bounds__(256)
-outer_rows_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ dx, int64_t rows, int K) {
+outer_rows_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ dx, int64_t rows, int K,
+                  const float* __restrict__ x, int64_t ldx, float scale) {
     const int64_t total = rows * K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / K;
-        dx[i] = __ldg(gy + r) * __ldg(w + (int)(i - r * K));
+        const int k = (int)(i - r * K);
+        float v = __ldg(gy + r) * __ldg(w + k);
+        if (x) v = __ldg(x + r * ldx + k) > 0.f ? v * scale : 0.f;      // ReLU(+dropout) mask of the layer below, fused
+        dx[i] = v;
     }
 }
 
@@ -566,40 +589,70 @@ static bool split_weights_into(void* ws, size_t ws_bytes, const MlpWs& l, const 
     return *rc == RLCTR_OK;
 }
 
+static int grid_elems(int64_t n) {
+    int64_t blocks = (n + 255) / 256;
+    return (int)(blocks < RLCTR_SMS * 8 ? (blocks < 1 ? 1 : blocks) : RLCTR_SMS * 8);
+}
+
+extern "C" int rlctr_rng_advance(uint64_t* state, uint64_t delta, rlctr_stream_t stream) {
+    if (!state) return RLCTR_EINVAL;
+    rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, delta);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
 extern "C" int rlctr_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t batch,
-                                int32_t in_dim, int32_t out_dim, int32_t flags, void* ws, size_t ws_bytes,
-                                rlctr_stream_t stream) {
+                                int32_t in_dim, int32_t out_dim, int32_t flags, float dropout_p, const uint64_t* rng_state,
+                                void* ws, size_t ws_bytes, rlctr_stream_t stream) {
     if (!x || !w || !y || batch < 0 || in_dim <= 0 || out_dim <= 0) return RLCTR_EINVAL;
     if (ldx == 0) ldx = in_dim;
     if (ldx < in_dim) return RLCTR_EINVAL;
+    const bool drop = (flags & RLCTR_MLP_DROPOUT) != 0 && dropout_p > 0.f;
+    if (drop && (!rng_state || !(dropout_p < 1.f))) return RLCTR_EINVAL;
     if (batch == 0) return RLCTR_OK;
     if (batch > 0x7fffffff) return RLCTR_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int relu = (flags & RLCTR_MLP_RELU) ? 1 : 0;
+    const uint32_t thresh = dropout_thresh(dropout_p);
+    const float dscale = drop ? 1.0f / (1.0f - dropout_p) : 1.f;
+    bool fused_drop = false;
+    int rc = RLCTR_OK;
     if (out_dim == 1) {
         int64_t blocks = (batch + 7) / 8;
         gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
             x, ldx, w, bias, y, batch, in_dim, relu);
         RLCTR_LAUNCH_CHECK();
-        return RLCTR_OK;
+    } else {
+        const MlpWs l = mlp_ws(batch, in_dim, out_dim);
+        float *whi = nullptr, *wlo = nullptr;
+        rc = RLCTR_EUNSUPPORTED;
+        int src = RLCTR_OK;
+        if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &src)) {
+            tma::Epilogue epi;
+            if (drop) { epi.drop_state = rng_state; epi.drop_thresh = thresh; epi.drop_scale = dscale; }
+            rc = tma::gemm(tma::Operand{x, nullptr, ldx, false}, tma::Operand{whi, wlo, l.in_pitch, false}, y, out_dim, bias,
+                           (int)batch, out_dim, in_dim, relu, false, st, &epi);
+            if (rc == RLCTR_OK) fused_drop = drop;
+        } else if (src) {
+            return src;
+        }
+        if (rc == RLCTR_EUNSUPPORTED) {
+            GemmPlan p = plan_gemm((int)batch, out_dim, in_dim, false);
+            rc = launch_gemm(x, ldx, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim, relu, p, st);
+        }
+        if (rc) return rc;
     }
-    const MlpWs l = mlp_ws(batch, in_dim, out_dim);
-    float *whi = nullptr, *wlo = nullptr;
-    int rc = RLCTR_OK;
-    if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &rc)) {
-        rc = tma::gemm(tma::Operand{x, nullptr, ldx, false}, tma::Operand{whi, wlo, l.in_pitch, false}, y, out_dim, bias,
-                       (int)batch, out_dim, in_dim, relu, false, st);
-        if (rc != RLCTR_EUNSUPPORTED) return rc;
-    } else if (rc) {
-        return rc;
+    if (drop && !fused_drop) {
+        const int64_t n = batch * out_dim;
+        dropout_kernel<<<grid_elems(n), 256, 0, st>>>(y, n, rng_state, thresh, dscale);
+        RLCTR_LAUNCH_CHECK();
     }
-    GemmPlan p = plan_gemm((int)batch, out_dim, in_dim, false);
-    return launch_gemm(x, ldx, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim, relu, p, st);
+    return RLCTR_OK;
 }
 
 extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, const float* y, float* gy, float* dx, float* dw,
-                                float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, void* ws,
-                                size_t ws_bytes, rlctr_stream_t stream) {
+                                float* db, int64_t batch, int32_t in_dim, int32_t out_dim, int32_t flags, float gy_scale,
+                                float dx_scale, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
     if (!x || !w || !gy || batch <= 0 || in_dim <= 0 || out_dim <= 0) return RLCTR_EINVAL;
     if (ldx == 0) ldx = in_dim;
     if (ldx < in_dim) return RLCTR_EINVAL;
@@ -611,9 +664,10 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         const int64_t n = batch * out_dim;
         int64_t blocks = (n + 255) / 256;
         int grid = (int)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8);
-        relu_bwd_kernel<<<grid, 256, 0, st>>>(gy, y, gy, n);
+        relu_bwd_kernel<<<grid, 256, 0, st>>>(gy, y, gy, n, gy_scale);
         RLCTR_LAUNCH_CHECK();
     }
+    const bool dx_mask = (flags & RLCTR_MLP_DX_MASK) != 0;
     const MlpWs l = mlp_ws(batch, in_dim, out_dim);
     if ((dw || db) && (!ws || ws_bytes < l.total)) return RLCTR_EWORKSPACE;
     float* part = reinterpret_cast<float*>(ws);
@@ -623,7 +677,8 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         if (dx) {
             const int64_t n = batch * in_dim;
             int64_t blocks = (n + 255) / 256;
-            outer_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(dy, w, dx, batch, in_dim);
+            outer_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
+                dy, w, dx, batch, in_dim, dx_mask ? x : nullptr, ldx, dx_scale);
             RLCTR_LAUNCH_CHECK();
         }
         if (dw) {
@@ -648,8 +703,10 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         int rc = RLCTR_OK;
         bool done = false;
         if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &rc)) {
+            tma::Epilogue epi;
+            if (dx_mask) { epi.mask_src = x; epi.mask_ld = ldx; epi.mask_scale = dx_scale; }
             rc = tma::gemm(tma::Operand{dy, nullptr, out_dim, false}, tma::Operand{whi, wlo, l.in_pitch, true}, dx, in_dim,
-                           nullptr, (int)batch, in_dim, out_dim, 0, false, st);
+                           nullptr, (int)batch, in_dim, out_dim, 0, false, st, &epi);
             if (rc == RLCTR_OK) done = true;
             else if (rc != RLCTR_EUNSUPPORTED) return rc;
         } else if (rc) {
@@ -659,6 +716,10 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
             GemmPlan p = plan_gemm((int)batch, in_dim, out_dim, false);
             rc = launch_gemm(dy, out_dim, 1, w, 1, in_dim, dx, in_dim, nullptr, (int)batch, in_dim, out_dim, 0, p, st);
             if (rc) return rc;
+            if (dx_mask) {
+                mask_rows_kernel<<<grid_elems(batch * in_dim), 256, 0, st>>>(dx, x, ldx, batch, in_dim, dx_scale);
+                RLCTR_LAUNCH_CHECK();
+            }
         }
     }
     if (dw) {   // dW[out,in] = dY^T[out,B] * X[B,in]: both operands contiguous along M / N, K = batch; split-K

@@ -51,6 +51,7 @@ struct Args {
     int a_mn, b_mn;                       // 1: operand is contiguous along M (N) instead of K
     int b_presplit;                       // 1: B arrives as (hi, lo) through mapB / mapBlo
     int relu;
+    Epilogue epi;                         // fused dropout (forward) / ReLU-dropout mask of the layer below (dgrad)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -235,6 +236,15 @@ struct EpiCtx {
     const float* sbias;        // the same bias staged in shared memory (null: read it from global)
     int N, cvec;
     bool row_ok, relu, zero;
+    // dropout of the forward output: element index = row * N + n
+    bool drop;
+    uint64_t drop_seed, drop_base;        // drop_base = counter + row * N
+    uint32_t drop_thresh;
+    float drop_scale;
+    // dgrad: dx *= (mask_row[n] > 0 ? mask_scale : 0)  (mask_row = the layer input's row: ReLU+dropout of the layer below)
+    const float* mask_row;
+    int mvec;
+    float mask_scale;
 };
 // W accumulator columns [n0, n0 + W) of this thread's row: bias, ReLU, vector stores
 template <int W>
@@ -257,6 +267,28 @@ __device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r
     if (e.relu) {
 #pragma unroll
         for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (e.drop) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            v[j] = dropout_keep(e.drop_seed, e.drop_base + (uint64_t)(n0 + j), e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+    }
+    if (e.mask_row) {
+        const float* mr = e.mask_row + n0;
+        if (n0 + W <= e.N && e.mvec == 4) {
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(mr + j));
+                v[j] = x.x > 0.f ? v[j] * e.mask_scale : 0.f;
+                v[j + 1] = x.y > 0.f ? v[j + 1] * e.mask_scale : 0.f;
+                v[j + 2] = x.z > 0.f ? v[j + 2] * e.mask_scale : 0.f;
+                v[j + 3] = x.w > 0.f ? v[j + 3] * e.mask_scale : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (n0 + j < e.N) v[j] = __ldg(mr + j) > 0.f ? v[j] * e.mask_scale : 0.f;
+        }
     }
     float* dst = e.crow + n0;
     if (n0 + W <= e.N && e.cvec == 4) {
@@ -432,6 +464,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     } else {
         // ================= epilogue =================
         const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+        uint64_t drop_seed = 0, drop_ctr = 0;
+        if (g.epi.drop_state) { drop_seed = g.epi.drop_state[0]; drop_ctr = g.epi.drop_state[1]; }
         int acc = 0;
         uint32_t acc_phase = 0;
         TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
@@ -449,6 +483,14 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             e.bias = (g.splits == 1) ? g.bias : nullptr;
             e.sbias = (g.splits == 1 && g.bias && bias_in_smem) ? s_bias : nullptr;
             e.zero = empty_split;
+            e.drop = g.epi.drop_state != nullptr && g.splits == 1;
+            e.drop_seed = drop_seed;
+            e.drop_base = drop_ctr + (uint64_t)m * (uint64_t)g.N;
+            e.drop_thresh = g.epi.drop_thresh;
+            e.drop_scale = g.epi.drop_scale;
+            e.mask_row = (g.epi.mask_src && g.splits == 1) ? g.epi.mask_src + (int64_t)m * g.epi.mask_ld : nullptr;
+            e.mvec = g.epi.mvec;
+            e.mask_scale = g.epi.mask_scale;
             const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
             if (g.n_tile % 32 == 0) epilogue_tile<32>(e, taddr, w.nt * g.n_tile, g.n_tile);
             else epilogue_tile<16>(e, taddr, w.nt * g.n_tile, g.n_tile);
@@ -573,7 +615,7 @@ int split_weight(const float* w, float* hi, float* lo, int rows, int cols, int p
 
 // RLCTR_EUNSUPPORTED: the caller falls back to the software-staged kernel (mlp.cu)
 int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float* bias, int M, int N, int K, int relu,
-         bool allow_split, cudaStream_t st) {
+         bool allow_split, cudaStream_t st, const Epilogue* epi) {
     if (!enabled()) return RLCTR_EUNSUPPORTED;
     if (!tma_ok(A.ptr, A.pitch) || !tma_ok(B.ptr, B.pitch) || (B.lo && !tma_ok(B.lo, B.pitch))) return RLCTR_EUNSUPPORTED;
     if (A.lo) return RLCTR_EUNSUPPORTED;                  // the streamed operand is always converted in the kernel
@@ -592,6 +634,9 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages;
     g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
+    g.epi = epi ? *epi : Epilogue{};
+    if ((g.epi.drop_state || g.epi.mask_src) && p.splits != 1) return RLCTR_EUNSUPPORTED;
+    if (g.epi.mask_src) g.epi.mvec = vec_of(g.epi.mask_src, g.epi.mask_ld);
     RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total < RLCTR_SMS ? total : RLCTR_SMS;

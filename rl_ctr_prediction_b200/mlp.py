@@ -3,11 +3,18 @@ DDQN_model.py:20-52; DDPG_for_PG_model.py:20-81) on the tcgen05 tensor cores.
 
 ``Linear`` keeps ``nn.Linear``'s parameters, init and state_dict keys (``weight [out,in]``,
 ``bias [out]``), so reference checkpoints load unchanged and the same ``torch.manual_seed`` gives the
-reference's initial weights.  Forward and backward are the 3xTF32 GEMM kernels of ``csrc/mlp.cu``
-(rlctr_linear_fwd / rlctr_linear_bwd): fp32-grade accuracy (the reference runs fp32 SGEMM,
-``allow_tf32=False``), no cuBLAS on the path.  ``Tower`` is an ``nn.Sequential`` that fuses each
-``Linear -> ReLU`` pair into the GEMM epilogue; ``nn.Dropout`` stays a torch op between kernels so
-train-mode masks are torch's Philox stream.
+reference's initial weights.  Forward and backward are the 3xTF32 GEMM kernels of ``csrc/mlp_tma.cu`` /
+``csrc/mlp.cu`` (rlctr_linear_fwd / rlctr_linear_bwd): fp32-grade accuracy (the reference runs fp32 SGEMM,
+``allow_tf32=False``), no cuBLAS on the path.
+
+``Tower`` is an ``nn.Sequential`` of ``Linear [-> ReLU] [-> Dropout]`` groups that runs as ONE autograd node:
+every group is a single GEMM whose epilogue applies bias, ReLU and (in train mode) the dropout mask, and in the
+backward the ReLU/dropout mask of layer i is applied inside the dgrad epilogue of layer i+1 -- no elementwise kernel
+touches an activation.  The mask is a counter-based hash of (seed, element index) kept in device memory
+(include/rlctr.h, rlctr_rng_advance): Bernoulli(1-p) scaled by 1/(1-p) exactly like ``nn.Dropout``, drawn from its
+own stream (the reference's CPU Philox stream cannot be reproduced on a GPU either -- SURVEY N6); ``eval()`` is the
+identity as in the reference.  A Sequential with any other module inside (BatchNorm in the DDQN/DDPG nets) runs
+module by module with ``Linear -> ReLU`` pairs fused.
 """
 from __future__ import annotations
 
@@ -29,21 +36,46 @@ def _rows_view(x):
     return x2, K
 
 
+def _fwd(lib, x2, ldx, w, bias, relu, drop_p=0.0, rng=None):
+    B, K = x2.shape
+    N = w.shape[0]
+    y = torch.empty(B, N, dtype=torch.float32, device=x2.device)
+    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DROPOUT if drop_p > 0.0 else 0)
+    ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device)
+    _lib.call("rlctr_linear_fwd", lib.rlctr_linear_fwd, x2.data_ptr(), ldx, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, K, N,
+              flags, float(drop_p), _lib.ptr(rng) if drop_p > 0.0 else None, _lib.ptr(ws), ws_bytes, _lib.stream(),
+              key=f"rlctr_linear_fwd[{K}x{N}]", meta={"B": B, "K": K, "N": N})
+    if drop_p > 0.0:
+        _lib.check(lib.rlctr_rng_advance(_lib.ptr(rng), B * N, _lib.stream()), "rlctr_rng_advance")
+    return y
+
+
+def _bwd(lib, x2, ldx, w, y, gy2, need_dx, need_dw, need_db, relu, gy_scale=1.0, dx_mask=False, dx_scale=1.0):
+    B, K = x2.shape
+    N = w.shape[0]
+    dev = x2.device
+    dx = torch.empty(B, K, dtype=torch.float32, device=dev) if need_dx else None
+    dw = torch.empty(N, K, dtype=torch.float32, device=dev) if need_dw else None
+    db = torch.empty(N, dtype=torch.float32, device=dev) if need_db else None
+    ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DX_MASK if dx_mask else 0)
+    _lib.call("rlctr_linear_bwd", lib.rlctr_linear_bwd, x2.data_ptr(), ldx, _lib.ptr(w), _lib.ptr(y) if relu else None,
+              _lib.ptr(gy2), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), B, K, N, flags, float(gy_scale), float(dx_scale),
+              _lib.ptr(ws), ws_bytes, _lib.stream(), key=f"rlctr_linear_bwd[{K}x{N}]",
+              meta={"B": B, "K": K, "N": N, "dx": need_dx})
+    return dx, dw, db
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
         lib = _lib.load()
         x2, ldx = _rows_view(x)
-        B, K = x2.shape
         N = weight.shape[0]
-        y = torch.empty(B, N, dtype=torch.float32, device=x.device)
-        flags = _lib.RLCTR_MLP_RELU if relu else 0
         w = weight.detach().contiguous()
-        ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        _lib.call("rlctr_linear_fwd", lib.rlctr_linear_fwd, x2.data_ptr(), ldx, _lib.ptr(w),
-                  _lib.ptr(bias.detach() if bias is not None else None), _lib.ptr(y), B, K, N, flags, _lib.ptr(ws), ws_bytes,
-                  _lib.stream(), key=f"rlctr_linear_fwd[{K}x{N}]", meta={"B": B, "K": K, "N": N})
+        y = _fwd(lib, x2, ldx, w, bias.detach() if bias is not None else None, relu)
         ctx.relu = relu
         ctx.ldx = ldx
         ctx.has_bias = bias is not None
@@ -61,16 +93,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.relu:
             gy2 = gy2.clone() if gy2.data_ptr() == gy.data_ptr() else gy2    # masked in place by the kernel
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        dev = x2.device
-        dx = torch.empty(B, K, dtype=torch.float32, device=dev) if need_dx else None
-        dw = torch.empty(N, K, dtype=torch.float32, device=dev) if need_dw else None
-        db = torch.empty(N, dtype=torch.float32, device=dev) if need_db else None
-        ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        flags = _lib.RLCTR_MLP_RELU if ctx.relu else 0
-        _lib.call("rlctr_linear_bwd", lib.rlctr_linear_bwd, x2.data_ptr(), ctx.ldx, _lib.ptr(w), _lib.ptr(y), _lib.ptr(gy2), _lib.ptr(dx),
-                  _lib.ptr(dw), _lib.ptr(db), B, K, N, flags, _lib.ptr(ws), ws_bytes, _lib.stream(),
-                  key=f"rlctr_linear_bwd[{K}x{N}]", meta={"B": B, "K": K, "N": N, "dx": need_dx})
+        dx, dw, db = _bwd(lib, x2, ctx.ldx, w, y, gy2, need_dx, need_dw, need_db, ctx.relu)
         if dx is not None:
             dx = dx.reshape(ctx.in_shape)
         return dx, dw, db, None
@@ -83,10 +106,106 @@ class Linear(nn.Linear):
         return _LinearFn.apply(x, self.weight, self.bias, relu)
 
 
+class _TowerFn(torch.autograd.Function):
+    """All layers of a Linear[-ReLU][-Dropout] stack as one autograd node (see the module docstring)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, rng, *params):
+        # spec: tuple of (relu, drop_p, has_bias) per layer; params: weight_0, bias_0, weight_1, bias_1, ... (bias may be None)
+        lib = _lib.load()
+        h, ld = _rows_view(x)
+        acts, lds, ws_ = [], [], []
+        for i, (relu, drop_p, has_bias) in enumerate(spec):
+            w = params[2 * i].detach().contiguous()
+            b = params[2 * i + 1].detach() if has_bias else None
+            acts.append(h)
+            lds.append(ld)
+            ws_.append(w)
+            h = _fwd(lib, h, ld, w, b, relu, drop_p, rng)
+            ld = h.shape[1]
+        ctx.spec, ctx.lds = spec, lds
+        ctx.in_shape = x.shape
+        ctx.n_layers = len(spec)
+        last_relu = spec[-1][0]
+        ctx.save_for_backward(*acts, *ws_, *( [h] if last_relu else [] ))
+        return h.reshape(*x.shape[:-1], h.shape[1])
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        L = ctx.n_layers
+        saved = ctx.saved_tensors
+        acts, ws_ = saved[:L], saved[L:2 * L]
+        spec = ctx.spec
+        B = acts[0].shape[0]
+        g = gy.reshape(B, -1).contiguous().float()
+        grads = [None] * (2 * L)
+        for i in range(L - 1, -1, -1):
+            relu, drop_p, has_bias = spec[i]
+            own_mask = relu and i == L - 1          # only the top layer masks its own incoming gradient
+            if own_mask and g.data_ptr() == gy.data_ptr():
+                g = g.clone()
+            below = spec[i - 1] if i > 0 else None
+            dx_mask = below is not None and below[0]                     # the layer below ended in ReLU (+ dropout)
+            dx_scale = 1.0 / (1.0 - below[1]) if (below is not None and below[1] > 0.0) else 1.0
+            if below is not None and not below[0] and below[1] > 0.0:
+                raise _lib.RlctrError("Dropout without a preceding ReLU is not fused; use separate modules")
+            need_dx = i > 0 or ctx.needs_input_grad[0]
+            need_dw = ctx.needs_input_grad[3 + 2 * i]
+            need_db = has_bias and ctx.needs_input_grad[3 + 2 * i + 1]
+            gy_scale = 1.0 / (1.0 - drop_p) if (own_mask and drop_p > 0.0) else 1.0
+            dx, dw, db = _bwd(lib, acts[i], ctx.lds[i], ws_[i], saved[2 * L] if own_mask else None, g, need_dx, need_dw,
+                              need_db, own_mask, gy_scale, dx_mask, dx_scale)
+            grads[2 * i], grads[2 * i + 1] = dw, db
+            g = dx
+        dx0 = g.reshape(ctx.in_shape) if (g is not None and ctx.needs_input_grad[0]) else None
+        return (dx0, None, None, *grads)
+
+
 class Tower(nn.Sequential):
-    """``nn.Sequential`` whose ``Linear -> nn.ReLU`` pairs run as one GEMM with a fused ReLU epilogue."""
+    """``nn.Sequential`` of Linear / ReLU / Dropout (reference state_dict indices kept: Linear layers at 0, 3, 6 ...)."""
+
+    def _groups(self):
+        """[(Linear, relu, dropout module or None)] if the Sequential is made only of Linear[-ReLU][-Dropout] groups."""
+        mods, i, out = list(self), 0, []
+        while i < len(mods):
+            if not isinstance(mods[i], Linear):
+                return None
+            lin, relu, drop = mods[i], False, None
+            i += 1
+            if i < len(mods) and isinstance(mods[i], nn.ReLU):
+                relu = True
+                i += 1
+            if i < len(mods) and isinstance(mods[i], nn.Dropout):
+                if not relu:
+                    return None
+                drop = mods[i]
+                i += 1
+            out.append((lin, relu, drop))
+        return out
+
+    def _rng_state(self, device):
+        st = getattr(self, "_rlctr_rng", None)
+        if st is None or st.device != device:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # CPU default generator: follows torch.manual_seed
+            st = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+            self._rlctr_rng = st
+        return st
 
     def forward(self, x):
+        groups = self._groups()
+        if groups is None or not x.is_cuda:
+            return self._forward_modules(x)
+        spec, params, any_drop = [], [], False
+        for lin, relu, drop in groups:
+            p = float(drop.p) if (drop is not None and drop.training and drop.p > 0.0) else 0.0
+            any_drop = any_drop or p > 0.0
+            spec.append((relu, p, lin.bias is not None))
+            params += [lin.weight, lin.bias]
+        rng = self._rng_state(x.device) if any_drop else None
+        return _TowerFn.apply(x, tuple(spec), rng, *params)
+
+    def _forward_modules(self, x):
         mods = list(self)
         i = 0
         while i < len(mods):

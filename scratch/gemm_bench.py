@@ -37,9 +37,9 @@ def run(K, N, ld):
     out = {}
     for mode in ("1", "0"):
         os.environ["RLCTR_GEMM_TMA"] = mode
-        f = lambda: _lib.check(lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 1, ws.data_ptr(), wsb, st), "fwd")
-        d = lambda: _lib.check(lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), dx.data_ptr(), None, None, B, K, N, 0, ws.data_ptr(), wsb, st), "dgrad")
-        g = lambda: _lib.check(lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), None, dw.data_ptr(), None, B, K, N, 0, ws.data_ptr(), wsb, st), "wgrad")
+        f = lambda: _lib.check(lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 1, 0.0, None, ws.data_ptr(), wsb, st), "fwd")
+        d = lambda: _lib.check(lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), dx.data_ptr(), None, None, B, K, N, 0, 1.0, 1.0, ws.data_ptr(), wsb, st), "dgrad")
+        g = lambda: _lib.check(lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), None, dw.data_ptr(), None, B, K, N, 0, 1.0, 1.0, ws.data_ptr(), wsb, st), "wgrad")
         tag = "tma" if mode == "1" else "staged"
         fl = 2.0 * B * K * N
         for name, fn in (("fwd", f), ("dgrad", d), ("wgrad", g)):
@@ -47,7 +47,7 @@ def run(K, N, ld):
             out[f"{tag}.{name}"] = {"us": round(us, 1), "fp32_TFLOPs": round(fl / us / 1e6, 1)}
     ref = x[:, :K].double() @ w.double().T + b.double()
     os.environ["RLCTR_GEMM_TMA"] = "1"
-    _lib.check(lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 0, ws.data_ptr(), wsb, st), "fwd")
+    _lib.check(lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 0, 0.0, None, ws.data_ptr(), wsb, st), "fwd")
     out["max_rel_err_fwd"] = float(((y.double() - ref).abs().max() / ref.abs().max()).item())
     return out
 

@@ -12,11 +12,11 @@ y = torch.empty(B, N, device=dev); gy = torch.randn(B, N, device=dev); dx = torc
 wsb = lib.rlctr_mlp_ws_bytes(B, K, N); ws = torch.empty(wsb, dtype=torch.uint8, device=dev); st = _lib.stream()
 for _ in range(4):
     if form == "fwd":
-        rc = lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 1, ws.data_ptr(), wsb, st)
+        rc = lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 1, 0.0, None, ws.data_ptr(), wsb, st)
     elif form == "dgrad":
-        rc = lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), dx.data_ptr(), None, None, B, K, N, 0, ws.data_ptr(), wsb, st)
+        rc = lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), dx.data_ptr(), None, None, B, K, N, 0, 1.0, 1.0, ws.data_ptr(), wsb, st)
     else:
-        rc = lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), None, dw.data_ptr(), None, B, K, N, 0, ws.data_ptr(), wsb, st)
+        rc = lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), None, dw.data_ptr(), None, B, K, N, 0, 1.0, 1.0, ws.data_ptr(), wsb, st)
     assert rc == 0, rc
 torch.cuda.synchronize()
 print("ok")

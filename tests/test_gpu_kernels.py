@@ -589,9 +589,9 @@ def test_linear_fwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
         xd = padded(x, ld)
         wsb = lib.rlctr_mlp_ws_bytes(B, K, N)
         ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
-        rc = lib.rlctr_linear_fwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, L().ptr(ws), wsb, st())
+        rc = lib.rlctr_linear_fwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, 0.0, None, L().ptr(ws), wsb, st())
     else:
-        rc = lib.rlctr_linear_fwd(L().ptr(dev(x)), 0, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, None, 0, st())
+        rc = lib.rlctr_linear_fwd(L().ptr(dev(x)), 0, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu, 0.0, None, None, 0, st())
     assert rc == 0
     ref = x.astype(np.float64) @ w.astype(np.float64).T + b
     if relu:
@@ -628,7 +628,7 @@ def test_linear_bwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
     else:
         ld, xd = K, dev(x)
     assert lib.rlctr_linear_bwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd), L().ptr(dx), L().ptr(dw),
-                                L().ptr(db), B, K, N, relu, L().ptr(ws), wsb, st()) == 0
+                                L().ptr(db), B, K, N, relu, 1.0, 1.0, L().ptr(ws), wsb, st()) == 0
     g64 = gy.astype(np.float64)
     if relu:
         g64 = g64 * (y > 0)
@@ -639,5 +639,55 @@ def test_linear_bwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
     dw2 = torch.empty_like(dw)
     gyd2 = dev(gy)
     lib.rlctr_linear_bwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(y)), L().ptr(gyd2), None, L().ptr(dw2), None, B, K, N,
-                         relu, L().ptr(ws), wsb, st())
+                         relu, 1.0, 1.0, L().ptr(ws), wsb, st())
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("path", ["tma", "staged"])
+@pytest.mark.parametrize("B,K,N", [(4096, 152, 300), (1000, 300, 200)])
+def test_linear_fused_dropout_and_masked_dgrad(lib, B, K, N, path, monkeypatch):
+    """Forward: y = dropout(relu(x w^T + b)) with the counter-hash mask: kept elements equal relu(.)/(1-p), the kept fraction is
+    1-p, the mask moves when the counter is advanced and repeats when it is not.  Backward of the layer above with
+    RLCTR_MLP_DX_MASK: dx = (gy w) * (x > 0 ? s : 0) -- the mask-as-input reference."""
+    monkeypatch.setenv("RLCTR_GEMM_TMA", "1" if path == "tma" else "0")
+    p = 0.2
+    x, w, b = linear_case(B, K, N, 11)
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    wsb = lib.rlctr_mlp_ws_bytes(B, K, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    rng = torch.tensor([1234567, 0], dtype=torch.int64, device=DEV)
+    FL = 1 | 2
+    y1, y2, y3 = (torch.empty(B, N, device=DEV) for _ in range(3))
+    args = lambda y: (L().ptr(xd), K, L().ptr(wd), L().ptr(bd), L().ptr(y), B, K, N, FL, p, L().ptr(rng), L().ptr(ws), wsb, st())
+    assert lib.rlctr_linear_fwd(*args(y1)) == 0
+    assert lib.rlctr_linear_fwd(*args(y2)) == 0
+    assert torch.equal(y1, y2)                                   # same (seed, counter) -> same mask
+    assert lib.rlctr_rng_advance(L().ptr(rng), B * N, st()) == 0
+    assert lib.rlctr_linear_fwd(*args(y3)) == 0
+    ref = np.maximum(x.astype(np.float64) @ w.astype(np.float64).T + b, 0)
+    y1n, y3n = y1.cpu().numpy(), y3.cpu().numpy()
+    pos = ref > 1e-3 * np.abs(ref).max()
+    kept = y1n[pos] != 0
+    assert abs(kept.mean() - (1 - p)) < 0.01, kept.mean()
+    assert abs((y3n[pos] != 0).mean() - (1 - p)) < 0.01
+    assert ((y1n[pos] != 0) != (y3n[pos] != 0)).mean() > 0.2      # a different mask after the counter moved
+    close(y1n[pos][kept], (ref[pos] / (1 - p))[kept], rtol=1e-5)
+    assert (y1n[ref == 0] == 0).all()
+    # both kernels draw the same mask (the fused epilogue and the elementwise fallback share the hash)
+    monkeypatch.setenv("RLCTR_GEMM_TMA", "0" if path == "tma" else "1")
+    y4 = torch.empty(B, N, device=DEV)
+    rng4 = torch.tensor([1234567, 0], dtype=torch.int64, device=DEV)
+    assert lib.rlctr_linear_fwd(L().ptr(xd), K, L().ptr(wd), L().ptr(bd), L().ptr(y4), B, K, N, FL, p, L().ptr(rng4),
+                                L().ptr(ws), wsb, st()) == 0
+    assert torch.equal(y4 != 0, y1 != 0)
+    monkeypatch.setenv("RLCTR_GEMM_TMA", "1" if path == "tma" else "0")
+    # masked dgrad: x plays the role of the layer-below output (zeros where it was clipped / dropped)
+    rs = np.random.default_rng(3)
+    xm = np.where(rs.random((B, K)) < 0.4, 0.0, np.abs(x)).astype(np.float32)
+    gy = rs.standard_normal((B, N)).astype(np.float32)
+    dx = torch.empty(B, K, device=DEV)
+    s = 1.0 / (1.0 - p)
+    assert lib.rlctr_linear_bwd(L().ptr(dev(xm)), K, L().ptr(wd), None, L().ptr(dev(gy)), L().ptr(dx), None, None, B, K, N, 4,
+                                1.0, s, L().ptr(ws), wsb, st()) == 0
+    refdx = (gy.astype(np.float64) @ w.astype(np.float64)) * np.where(xm > 0, s, 0.0)
+    close(dx, refdx, rtol=1e-5)

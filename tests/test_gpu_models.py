@@ -356,3 +356,69 @@ def test_graphed_step_equals_eager_step():
         sa, sb = a.state_dict(), b.state_dict()
         for k in sa:
             assert torch.equal(sa[k], sb[k]), k
+
+
+def test_tower_train_mode_matches_mask_as_input_reference():
+    """Train-mode DeepFM tower (fused ReLU + dropout epilogues, masks folded into the dgrad epilogues) against plain torch
+    given the SAME masks (recovered from the activations): output and every gradient (mask as an input)."""
+    from rl_ctr_prediction_b200 import mlp
+    torch.manual_seed(0)
+    Bt, K = 2048, 152
+    tower = mlp.Tower(mlp.Linear(K, 300), torch.nn.ReLU(), torch.nn.Dropout(0.2), mlp.Linear(300, 200), torch.nn.ReLU(),
+                      torch.nn.Dropout(0.2), mlp.Linear(200, 1)).to(DEV).train()
+    x = torch.randn(Bt, K, device=DEV, requires_grad=True)
+    # capture the hidden activations through the kernels themselves: run the first groups as their own towers with
+    # the same rng state
+    out = tower(x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    grads = {n: p.grad.clone() for n, p in tower.named_parameters()}
+    gx = x.grad.clone()
+    # reference: recompute with masks recovered layer by layer from a replay of the same rng counter
+    rng0 = tower._rlctr_rng.clone()
+    rng0[1] = 0
+    W = [tower[0], tower[3], tower[6]]
+    xr = x.detach().double().requires_grad_(True)
+    params = [(l.weight.detach().double().requires_grad_(True), l.bias.detach().double().requires_grad_(True)) for l in W]
+    h = xr
+    lib = _L().load()
+    counter = 0
+    for li in range(2):
+        w, b = params[li]
+        pre = torch.relu(h @ w.T + b)
+        # the kernel's mask for this layer: run the fused forward on the fp32 input with the counter where it stood
+        st_ = torch.tensor([int(rng0[0].item()), counter], dtype=torch.int64, device=DEV)
+        hin = h.detach().float().contiguous()
+        y = torch.empty(Bt, w.shape[0], device=DEV)
+        wsb = lib.rlctr_mlp_ws_bytes(Bt, hin.shape[1], w.shape[0])
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        assert lib.rlctr_linear_fwd(hin.data_ptr(), hin.shape[1], W[li].weight.data_ptr(), W[li].bias.data_ptr(), y.data_ptr(), Bt,
+                                    hin.shape[1], w.shape[0], 3, 0.2, st_.data_ptr(), ws.data_ptr(), wsb,
+                                    torch.cuda.current_stream().cuda_stream) == 0
+        keep = (y != 0) | (pre.detach() <= 0)
+        h = pre * keep.double() / 0.8
+        counter += Bt * w.shape[0]
+    w, b = params[2]
+    ref = h @ w.T + b
+    ref.backward(g.double())
+    close(out, ref.detach(), rtol=1e-5)
+    close(gx, xr.grad, rtol=2e-5)
+    for (n, got), (w_, b_) in zip([("w0", grads["0.weight"]), ("w1", grads["3.weight"]), ("w2", grads["6.weight"])], params):
+        close(got, w_.grad, rtol=2e-5)
+    for got, (w_, b_) in zip([grads["0.bias"], grads["3.bias"], grads["6.bias"]], params):
+        close(got, b_.grad, rtol=2e-5)
+    # eval mode: dropout is the identity
+    tower.eval()
+    with torch.no_grad():
+        e = tower(x.detach())
+    hh = x.detach().double()
+    for li, l in enumerate(W):
+        hh = hh @ l.weight.double().T + l.bias.double()
+        if li < 2:
+            hh = torch.relu(hh)
+    close(e, hh, rtol=1e-5)
+
+
+def _L():
+    from rl_ctr_prediction_b200 import _lib
+    return _lib
