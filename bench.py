@@ -391,7 +391,8 @@ def b200_arm(args):
                        "tensor_pipe_TFLOPs_3x": 3 * fl / (mean_ms / 1e3) / 1e12}
     all_kernels = {k: {"launches": v[0], "mean_ms": v[1], "GBps": v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 else None}
                    for k, v in kern.items()}
-    shares = {g: round(tms / ms_prof, 4) for g, tms in sorted(groups.items(), key=lambda kv: -kv[1])}
+    step_ms = ms_total / K                                # the graph-replay step the shares are read against
+    shares = {g: round(tms / Kp / step_ms, 4) for g, tms in sorted(groups.items(), key=lambda kv: -kv[1])}
     top = max(groups, key=groups.get) if groups else None
     roof = None
     if top is not None and top.startswith("rlctr_linear"):
@@ -401,7 +402,7 @@ def b200_arm(args):
         achieved = tot_fl / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": top + " (gemm3x_tma_kernel: all tower layers)", "achieved": achieved, "peak": tpeak,
                 "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tpeak_src,
-                "flops_counted": "3 tf32 MMAs per fp32 product (3xTF32 split)", "share_of_step": groups[top] / ms_prof}
+                "flops_counted": "3 tf32 MMAs per fp32 product (3xTF32 split)", "share_of_step": groups[top] / Kp / step_ms}
     elif top is not None:
         keys = [k for k in kern if k.split("[")[0] == top]
         tot_ms = sum(kern[k][0] * kern[k][1] for k in keys)
@@ -411,7 +412,7 @@ def b200_arm(args):
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": tot_alg / n_l, "launches_timed": n_l, "mean_ms": tot_ms / n_l,
-                "share_of_step": groups[top] / ms_prof}
+                "share_of_step": groups[top] / Kp / step_ms}
     if roof is not None:
         roof["share_of_step_by_entry_point"] = shares
         roof["profiled_pass"] = {"steps": Kp, "ms_per_step": ms_prof / Kp, "mode": "eager, CUDA events around every library call"}
@@ -429,7 +430,7 @@ def b200_arm(args):
             x, y = make_batch(gen_c, B, N, "cpu")
             host.append((x.pin_memory(), y.pin_memory()))
 
-        def e2e_step(xh, yh):
+        def e2e_step_eager(xh, yh):
             x = xh.to(dev, non_blocking=True)
             y = torch.unsqueeze(yh, 1).to(dev, non_blocking=True)
             total = 0.0
@@ -445,24 +446,54 @@ def b200_arm(args):
                 total += tl.item()                         # device -> host read of the step's loss
             return total
 
+        def timed(run):
+            barrier()
+            e0.record()
+            run()
+            for m, _ in ms:
+                m.flush()
+            e1.record()
+            barrier()
+            t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+
+        bytes_in, bytes_out = B * F_FIELDS * 8 + B * 8, 4 * len(MODELS)
+        if use_graph:
+            # the public call: GraphedTrainStep on pinned HOST batches; the copy of batch i+1 is issued before step i
+            # (graphs.GraphedTrainStep.prefetch) and every step's three losses are read back to the host
+            from rl_ctr_prediction_b200 import graphs
+            gs = graphs.GraphedTrainStep(ms, lossf)
+            sink = []
+
+            def run_graphed(lo, hi):
+                h = gs.prefetch(*host[lo])
+                for i in range(lo, hi):
+                    nxt = gs.prefetch(*host[i + 1]) if i + 1 < hi else None
+                    losses = gs(h)
+                    sink.append(torch.stack([l.reshape(()) for l in losses]).tolist())   # device -> host, every step
+                    h = nxt
+
+            run_graphed(0, W)
+            ms_e2e = timed(lambda: run_graphed(W, W + K))
+            e2e = {"value": B * K * world / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": bytes_in,
+                   "d2h_bytes_per_step": bytes_out, "ms_per_step": ms_e2e / K,
+                   "api": "graphs.GraphedTrainStep: step.prefetch(pinned host features, labels); losses = step(handle); "
+                          "losses read back every step"}
+            del gs
+            ms = build_models()
         for i in range(W):
-            e2e_step(*host[i])
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for i in range(K):
-            e2e_step(*host[W + i])
-        for m, _ in ms:
-            m.flush()
-        e1.record()
-        barrier()
-        ms_e2e = max(e0.elapsed_time(e1), 0.0)
-        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * K * world / (t.item() / 1e3), "unit": "samples/s",
-               "h2d_bytes_per_step": B * F_FIELDS * 8 + B * 8, "d2h_bytes_per_step": 4 * len(MODELS),
-               "ms_per_step": t.item() / K, "api": "model(x); nn.BCELoss; zero_grad; backward; optim.Adam.step; loss.item()"}
+            e2e_step_eager(*host[i])
+        ms_eager = timed(lambda: [e2e_step_eager(*host[W + i]) for i in range(K)])
+        eager = {"value": B * K * world / (ms_eager / 1e3), "unit": "samples/s", "h2d_bytes_per_step": bytes_in,
+                 "d2h_bytes_per_step": bytes_out, "ms_per_step": ms_eager / K,
+                 "api": "model(x); nn.BCELoss; zero_grad; backward; optim.Adam.step; loss.item()  (the reference's loop body, "
+                        "launched eagerly from Python: host-bound)"}
+        if e2e is None:
+            e2e = eager
+        else:
+            e2e["dropin_eager_loop"] = eager
         del ms, host
         torch.cuda.empty_cache()
 

@@ -36,6 +36,14 @@ def eager_step(model, optimizer, loss_fn, x, y):
     return PM.fused_train_step(model, optimizer, x, y)
 
 
+class Prefetched:
+    """A batch whose host -> device copy is in flight on the copy stream (GraphedTrainStep.prefetch)."""
+    __slots__ = ("x", "y", "ready", "slot")
+
+    def __init__(self, x, y, ready, slot):
+        self.x, self.y, self.ready, self.slot = x, y, ready, slot
+
+
 class GraphedTrainStep:
     def __init__(self, pairs, loss_fn=None, eager_steps=2, steps_ahead=65536):
         self.pairs = list(pairs)
@@ -46,6 +54,10 @@ class GraphedTrainStep:
         self.x = self.y = None
         self.losses = None
         self.launches_per_step = 0
+        self._copy_stream = None       # prefetch(): pinned host -> staging buffers, overlapped with the running step
+        self._stage = [None, None]
+        self._consumed = [None, None]
+        self._slot = 0
         self.stream = None             # warm-up steps and the capture share one side stream (autograd's AccumulateGrad
                                        # nodes remember the stream they were created on)
 
@@ -120,7 +132,41 @@ class GraphedTrainStep:
         # the capture ran the Python side of one step (host counters advanced) but no kernel: replay it now
         g.replay()
 
-    def __call__(self, x, y):
+    def prefetch(self, x, y):
+        """Start copying a (pinned) host batch to the device on a side stream and return a handle ``step(handle)``
+        consumes.  Call it for batch i+1 before ``step`` of batch i: the copy overlaps the running step."""
+        dev = self.pairs[0][0].table.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        slot = self._slot
+        self._slot ^= 1
+        st = self._stage[slot]
+        if st is None or tuple(st[0].shape) != tuple(x.shape) or tuple(st[1].shape) != tuple(y.shape):
+            st = (torch.empty(tuple(x.shape), dtype=x.dtype, device=dev), torch.empty(tuple(y.shape), dtype=y.dtype, device=dev))
+            self._stage[slot] = st
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        cs = self._copy_stream
+        if self._consumed[slot] is not None:
+            cs.wait_event(self._consumed[slot])            # the step that last read this slot has taken its copy
+        with torch.cuda.stream(cs):
+            st[0].copy_(x, non_blocking=True)
+            st[1].copy_(y, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        return Prefetched(st[0], st[1], ready, slot)
+
+    def __call__(self, x, y=None):
+        if isinstance(x, Prefetched):
+            h = x
+            torch.cuda.current_stream().wait_event(h.ready)
+            out = self._run(h.x, h.y)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._consumed[h.slot] = ev
+            return out
+        return self._run(x, y)
+
+    def _run(self, x, y):
         dev = self.pairs[0][0].table.device
         if self.graph is not None and tuple(x.shape) == tuple(self.x.shape) and self._room():
             self.x.copy_(x, non_blocking=True)
