@@ -513,7 +513,9 @@ def b200_arm(args):
                 "cuda_graph": bool(use_graph)}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)           # symmetric-memory mappings are released with the process; no collective teardown
 
 
 def main():

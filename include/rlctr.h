@@ -48,6 +48,7 @@ extern "C" {
 typedef struct CUstream_st* rlctr_stream_t;   /* == cudaStream_t */
 
 /* One embedding table in the fused-row layout described above. */
+#define RLCTR_MAX_WORLD 8
 typedef struct rlctr_table {
     float*  data;        /* [n_rows, row_stride] */
     int64_t n_rows;      /* feature_nums */
@@ -61,6 +62,13 @@ typedef struct rlctr_table {
                           * optimizer touches ONE contiguous 3*row_stride*4-byte record per row instead of three
                           * random 64 B blocks: random HBM accesses are activation-rate bound, not byte bound
                           * (profiles/r1_gather_probe.md).  The Adam arrays always use the table's pitch. */
+    /* Row sharding over the GPUs of one box.  world <= 1: not sharded.  world = 2, 4 or 8: row `id`
+     * lives on rank id % world at local row id / world; peers[r] is the base of rank r's shard as mapped into THIS
+     * process (CUDA peer / symmetric memory over NVLink; peers[own rank] == data); n_rows is then the GLOBAL row
+     * count.  Only the forward gathers (rlctr_embed_fwd) read through peers[]; the optimizer kernels always run on
+     * the owner against a table struct that describes the local shard (world = 0). */
+    int32_t world;
+    float*  peers[RLCTR_MAX_WORLD];
 } rlctr_table;
 
 /* torch.optim.Adam state for one table (src/main/pretrain_main.py:181).  `sched[t]` holds
@@ -101,6 +109,16 @@ typedef struct rlctr_rowgrad {
     const float* extra;    /* [B, fields*dim] */
     int32_t      fields;
     int32_t      flags;    /* 0 or RLCTR_STAGED_PARTNER */
+    /* Sharded tables: the owner reduces the gradients of ALL ranks' batches.  world > 1: a slot is a GLOBAL slot
+     * g = src_rank * n_per_rank + slot, and the four arrays above are read from rank src_rank's buffers through
+     * peer_*[src_rank] (peer-mapped memory, the pull side of the gradient exchange over NVLink); the plain pointers are
+     * ignored (NULL-ness of peer_*[0] decides which terms exist). */
+    int32_t      world;
+    uint32_t     n_per_rank;                       /* slots per rank (batch * fields, equal on every rank) */
+    const float* peer_staged[RLCTR_MAX_WORLD];
+    const float* peer_dlogit[RLCTR_MAX_WORLD];
+    const float* peer_sums[RLCTR_MAX_WORLD];
+    const float* peer_extra[RLCTR_MAX_WORLD];
 } rlctr_rowgrad;
 
 int         rlctr_version(void);
@@ -188,6 +206,13 @@ size_t rlctr_rows_ws_bytes(int64_t n);
  * then Adam step *step+1 with L2 (g += wd*p) on that row (after replaying the L2-only steps
  * stamp[id]+1 .. *step it missed); stamp[id] = *step+1.  No atomics on the data path;
  * bit-identical from run to run.  Follow with rlctr_step_advance(+1). */
+/* Sharded variant: `ids_all` are the ids of EVERY rank's batch (all-gathered, n_all = world * n_per_rank, uint32).  Keys
+ * are the LOCAL rows (id / world) of the ids this rank owns (id % world == rank); everything else sorts last as a
+ * sentinel and is skipped by the consumers.  sorted_slots are GLOBAL slots (positions in ids_all).  No counts travel
+ * to the host: the sorted arrays have n_all entries and rlctr_rows_catchup / rlctr_rows_adam are called with n = n_all. */
+int rlctr_sort_ids_sharded(const uint32_t* ids_all, int64_t n_all, int32_t world, int32_t rank, int64_t n_rows_global,
+                           uint32_t* sorted_rows, uint32_t* sorted_slots, void* ws, size_t ws_bytes,
+                           rlctr_stream_t stream);
 int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                     const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
                     void* ws, size_t ws_bytes, rlctr_stream_t stream);

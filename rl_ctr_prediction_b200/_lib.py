@@ -29,7 +29,8 @@ class RlctrError(RuntimeError):
 class Table(C.Structure):
     """struct rlctr_table"""
     _fields_ = [("data", C.c_void_p), ("n_rows", C.c_int64), ("row_stride", C.c_int32),
-                ("lin_col", C.c_int32), ("emb_col", C.c_int32), ("dim", C.c_int32), ("row_pitch", C.c_int32)]
+                ("lin_col", C.c_int32), ("emb_col", C.c_int32), ("dim", C.c_int32), ("row_pitch", C.c_int32),
+                ("world", C.c_int32), ("peers", C.c_void_p * 8)]
 
 
 class Adam(C.Structure):
@@ -42,7 +43,9 @@ class Adam(C.Structure):
 class RowGrad(C.Structure):
     """struct rlctr_rowgrad"""
     _fields_ = [("staged", C.c_void_p), ("dlogit", C.c_void_p), ("sums", C.c_void_p),
-                ("extra", C.c_void_p), ("fields", C.c_int32), ("flags", C.c_int32)]
+                ("extra", C.c_void_p), ("fields", C.c_int32), ("flags", C.c_int32),
+                ("world", C.c_int32), ("n_per_rank", C.c_uint32), ("peer_staged", C.c_void_p * 8),
+                ("peer_dlogit", C.c_void_p * 8), ("peer_sums", C.c_void_p * 8), ("peer_extra", C.c_void_p * 8)]
 
 
 _P, _I64, _I32, _SZ, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
@@ -61,6 +64,7 @@ SIGNATURES = {
     "rlctr_sigmoid_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
     "rlctr_sort_ws_bytes": (_SZ, [_I64, _I64]),
     "rlctr_sort_ids": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "rlctr_sort_ids_sharded": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P, _P, _SZ, _P]),
     "rlctr_rows_ws_bytes": (_SZ, [_I64]),
     "rlctr_rows_adam": (C.c_int, [_P, _P, _I64, _GP, _TP, _AP, _P, _SZ, _P]),
     "rlctr_rows_grad_dense": (C.c_int, [_P, _P, _I64, _GP, _TP, _P, _P, _SZ, _P]),

@@ -139,6 +139,29 @@ __device__ __forceinline__ void adam_replay1(float& p, float& m, float& v, int f
     }
 }
 
+// row-sharded tables: id -> (rank id & mask, local row id >> shift); mask == 0: one local table
+struct ShardView {
+    const float* peers[RLCTR_MAX_WORLD];
+    int shift, mask;
+};
+__device__ __forceinline__ const float* row_ptr(const float* tab, const ShardView& sv, int64_t id, int pitch) {
+    if (sv.mask == 0) return tab + id * pitch;
+    return sv.peers[id & sv.mask] + (id >> sv.shift) * (int64_t)pitch;      // NVLink read when the owner is a peer
+}
+static inline bool shard_view_of(const rlctr_table* t, ShardView* sv) {
+    sv->shift = 0; sv->mask = 0;
+    for (int r = 0; r < RLCTR_MAX_WORLD; ++r) sv->peers[r] = nullptr;
+    if (t->world <= 1) return true;
+    if (t->world != 2 && t->world != 4 && t->world != 8) return false;
+    while ((1 << sv->shift) < t->world) ++sv->shift;
+    sv->mask = t->world - 1;
+    for (int r = 0; r < t->world; ++r) {
+        if (!t->peers[r]) return false;
+        sv->peers[r] = t->peers[r];
+    }
+    return true;
+}
+
 // ---- counter-based dropout mask (mlp.cu / mlp_tma.cu) ----------------------------------------------------------
 // keep(element) = hash(seed, counter + element index) >= p * 2^32.  (seed, counter) live in device memory so that a
 // CUDA-graph replay draws a fresh mask every step (rlctr_rng_advance moves the counter).  Two rounds of a 32-bit

@@ -15,7 +15,7 @@ namespace rlctr {
 // ------------------------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(256)
-embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch,
+embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, const __grid_constant__ ShardView sv, int64_t n_rows, int pitch,
                  int rs, int lin_col, int emb_col, int dim, const float* __restrict__ bias,
                  float* __restrict__ logit, float* __restrict__ pctr, int64_t pctr_stride,
                  float* __restrict__ sums, float* __restrict__ rows_out, int64_t rows_pitch,
@@ -63,8 +63,8 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
             }
             float4 ra = f4zero(), rb = f4zero();
             const bool oka = (uint64_t)ia < (uint64_t)n_rows, okb = (uint64_t)ib < (uint64_t)n_rows;
-            if (oka) ra = ldg4(tab + ia * pitch + col0);
-            if (okb) rb = ldg4(tab + ib * pitch + col0);
+            if (oka) ra = ldg4(row_ptr(tab, sv, ia, pitch) + col0);
+            if (okb) rb = ldg4(row_ptr(tab, sv, ib, pitch) + col0);
             s = f4add(s, f4add(ra, rb));
             if (fm) {
 #pragma unroll
@@ -114,7 +114,7 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
 
 // LR table: one float per row (row_stride == 1).  Lane f gathers w[x_f]; warp-sum.
 __global__ void __launch_bounds__(256)
-embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch,
+embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, const __grid_constant__ ShardView sv, int64_t n_rows, int pitch,
                         const float* __restrict__ bias, float* __restrict__ logit,
                         float* __restrict__ pctr, int64_t pctr_stride, float* __restrict__ sums,
                         int64_t batch, int fields) {
@@ -126,7 +126,7 @@ embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict
         float s = 0.f;
         for (int f = lane; f < fields; f += 32) {
             const int64_t id = __ldg(ids + b * fields + f);
-            if ((uint64_t)id < (uint64_t)n_rows) s += __ldg(tab + id * pitch);
+            if ((uint64_t)id < (uint64_t)n_rows) s += __ldg(row_ptr(tab, sv, id, pitch));
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(RLCTR_FULL, s, off);
@@ -258,13 +258,15 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
     if (batch == 0) return RLCTR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int rs = table->row_stride;
+    ShardView sv;
+    if (!shard_view_of(table, &sv)) return RLCTR_EUNSUPPORTED;
     if (pctr && pctr_stride < 1) return RLCTR_EINVAL;
     if (rows_pitch == 0) rows_pitch = (int64_t)fields * table->dim;
     if (rows_out && rows_pitch < (int64_t)fields * table->dim) return RLCTR_EINVAL;
     if (rs == 1) {
         if (rows_out || (flags & RLCTR_FM_TERM) || table->lin_col != 0) return RLCTR_EUNSUPPORTED;
         int grid = grid_for_warps(batch, 8, 8);
-        embed_fwd_scalar_kernel<<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, pitch_of(table), bias, logit, pctr,
+        embed_fwd_scalar_kernel<<<grid, 256, 0, st>>>(ids, table->data, sv, table->n_rows, pitch_of(table), bias, logit, pctr,
                                                      pctr_stride, sums, batch, fields);
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
@@ -273,7 +275,7 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
     if (sums && !rlctr_aligned16(sums)) return RLCTR_EALIGN;
     int grid = grid_for_warps(batch, 8, 8);
 #define LAUNCH_EMBED(L)                                                                              \
-    embed_fwd_kernel<L><<<grid, 256, 0, st>>>(ids, table->data, table->n_rows, pitch_of(table), rs, table->lin_col,   \
+    embed_fwd_kernel<L><<<grid, 256, 0, st>>>(ids, table->data, sv, table->n_rows, pitch_of(table), rs, table->lin_col,   \
                                               table->emb_col, table->dim, bias, logit, pctr,         \
                                               pctr_stride, sums, rows_out, rows_pitch, batch, fields, flags)
     switch (rlctr_lanes_per_row(rs)) {

@@ -18,7 +18,8 @@ namespace rlctr {
 constexpr int FFM_WARPS = 4;
 
 __global__ void __launch_bounds__(FFM_WARPS * 32)
-ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, int64_t n_rows, int pitch, int rs,
+ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, const __grid_constant__ ShardView sv,
+               int64_t n_rows, int pitch, int rs,
                int lin_col, int emb_col, const float* __restrict__ bias, float* __restrict__ logit,
                float* __restrict__ pctr, int64_t pctr_stride, float* __restrict__ partners,
                int64_t batch, int fields, int latent) {
@@ -47,7 +48,7 @@ ffm_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, i
             const int f = t / chunks, c = t - f * chunks;
             const int64_t id = __ldg(ids + b * fields + f);
             float4 r = f4zero();
-            if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(tab + id * pitch + 4 * c);
+            if ((uint64_t)id < (uint64_t)n_rows) r = ldg4(row_ptr(tab, sv, id, pitch) + 4 * c);
             st4(stage + f * rs + 4 * c, r);
         }
         __syncwarp();
@@ -106,6 +107,8 @@ extern "C" int rlctr_ffm_fwd(const int64_t* ids, const rlctr_table* table, const
     if (!rlctr_aligned16(table->data) || (partners && !rlctr_aligned16(partners))) return RLCTR_EALIGN;
     if (pctr && pctr_stride < 1) return RLCTR_EINVAL;
     if (batch == 0) return RLCTR_OK;
+    ShardView sv;
+    if (!shard_view_of(table, &sv)) return RLCTR_EUNSUPPORTED;
     const int npair = fields * (fields - 1) / 2;
     const size_t smem = (size_t)FFM_WARPS * fields * rs * sizeof(float) + 2 * (size_t)npair;
     if (smem > 200 * 1024) return RLCTR_EUNSUPPORTED;
@@ -117,7 +120,7 @@ extern "C" int rlctr_ffm_fwd(const int64_t* ids, const rlctr_table* table, const
     const int64_t cap = (int64_t)RLCTR_SMS * per_sm;
     const int grid = (int)(want < cap ? want : cap);
     ffm_fwd_kernel<<<grid, FFM_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        ids, table->data, table->n_rows, table->row_pitch > 0 ? table->row_pitch : rs, rs, table->lin_col, table->emb_col, bias,
+        ids, table->data, sv, table->n_rows, table->row_pitch > 0 ? table->row_pitch : rs, rs, table->lin_col, table->emb_col, bias,
         logit, pctr, pctr_stride,
         partners, batch, fields, latent);
     RLCTR_LAUNCH_CHECK();

@@ -62,7 +62,42 @@ struct GradView {
     const float* extra;
     int fields;
     int flags;
+    // sharded tables: slots are global (src rank * n_per_rank + slot); the four arrays are read from the source
+    // rank's buffers over NVLink (peer-mapped pointers)
+    int world;
+    uint32_t n_per_rank;
+    const float* p_staged[RLCTR_MAX_WORLD];
+    const float* p_dlogit[RLCTR_MAX_WORLD];
+    const float* p_sums[RLCTR_MAX_WORLD];
+    const float* p_extra[RLCTR_MAX_WORLD];
 };
+// the gradient sources of one slot: for a sharded table, those of the rank the slot came from
+struct GradSrc {
+    const float* staged;
+    const float* dlogit;
+    const float* sums;
+    const float* extra;
+    uint32_t slot;
+};
+__device__ __forceinline__ GradSrc grad_src(const GradView& g, uint32_t slot) {
+    if (g.world <= 1) return GradSrc{g.staged, g.dlogit, g.sums, g.extra, slot};
+    const uint32_t src = slot / g.n_per_rank;
+    return GradSrc{g.p_staged[src], g.p_dlogit[src], g.p_sums[src], g.p_extra[src], slot - src * g.n_per_rank};
+}
+static inline GradView grad_view_of(const rlctr_rowgrad* grad) {
+    GradView g{};
+    g.staged = grad->staged; g.dlogit = grad->dlogit; g.sums = grad->sums; g.extra = grad->extra;
+    g.fields = grad->fields; g.flags = grad->flags;
+    g.world = grad->world; g.n_per_rank = grad->n_per_rank;
+    if (grad->world > 1) {
+        for (int r = 0; r < grad->world && r < RLCTR_MAX_WORLD; ++r) {
+            g.p_staged[r] = grad->peer_staged[r]; g.p_dlogit[r] = grad->peer_dlogit[r];
+            g.p_sums[r] = grad->peer_sums[r]; g.p_extra[r] = grad->peer_extra[r];
+        }
+        g.staged = grad->peer_staged[0]; g.dlogit = grad->peer_dlogit[0]; g.sums = grad->peer_sums[0]; g.extra = grad->peer_extra[0];
+    }
+    return g;
+}
 
 __global__ void __launch_bounds__(256)
 sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, uint32_t* __restrict__ keys,
@@ -74,23 +109,37 @@ sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, uin
     }
 }
 
+// sharded tables: keys are the local rows of the ids this rank owns; the rest sorts last (sentinel = n_local)
+__global__ void __launch_bounds__(256)
+sort_prep_sharded_kernel(const uint32_t* __restrict__ ids_all, int64_t n_all, int64_t n_rows_global, int shift, uint32_t mask,
+                         uint32_t rank, uint32_t n_local, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = __ldg(ids_all + i);
+        const bool mine = (uint64_t)id < (uint64_t)n_rows_global && (id & mask) == rank;
+        keys[i] = mine ? (id >> shift) : n_local;
+        vals[i] = (uint32_t)i;
+    }
+}
+
 // gradient of columns col0..col0+3 of the row gathered at `slot` (rlctr_rowgrad in rlctr.h)
-__device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t slot, int col0, const float4& p,
+__device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t gslot, int col0, const float4& p,
                                                 const TableView& t) {
+    const GradSrc q = grad_src(g, gslot);
+    const uint32_t slot = q.slot;
     float4 r = f4zero();
-    if (g.staged) r = ldg4(g.staged + (int64_t)slot * t.rs + col0);
+    if (q.staged) r = ldg4(q.staged + (int64_t)slot * t.rs + col0);
     if (g.flags & RLCTR_STAGED_PARTNER) {               // FFM: d z / d row is staged, scale by dL/dz
-        const float dz = __ldg(g.dlogit + slot / (uint32_t)g.fields);
+        const float dz = __ldg(q.dlogit + slot / (uint32_t)g.fields);
         return make_float4(dz * r.x, dz * r.y, dz * r.z, dz * r.w);
     }
-    if (g.dlogit || g.extra) {
+    if (q.dlogit || q.extra) {
         const uint32_t b = slot / (uint32_t)g.fields;
         const uint32_t f = slot - b * (uint32_t)g.fields;
-        const float dz = g.dlogit ? __ldg(g.dlogit + b) : 0.f;
+        const float dz = q.dlogit ? __ldg(q.dlogit + b) : 0.f;
         float4 S = f4zero();
-        const bool fm = g.sums && g.dlogit;
-        if (fm) S = ldg4(g.sums + (int64_t)b * t.rs + col0);
-        const float* ex = g.extra ? g.extra + ((int64_t)b * g.fields + f) * t.dim : nullptr;
+        const bool fm = q.sums && q.dlogit;
+        if (fm) S = ldg4(q.sums + (int64_t)b * t.rs + col0);
+        const float* ex = q.extra ? q.extra + ((int64_t)b * g.fields + f) * t.dim : nullptr;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int col = col0 + k;
@@ -492,8 +541,9 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
         const uint32_t slot = __ldg(sorted_slots + kk);
         ++kk;
         nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
-        float gsl = g.staged ? __ldg(g.staged + slot) : 0.f;
-        if (g.dlogit) gsl += __ldg(g.dlogit + slot / (uint32_t)g.fields);
+        const GradSrc q = grad_src(g, slot);
+        float gsl = q.staged ? __ldg(q.staged + q.slot) : 0.f;
+        if (q.dlogit) gsl += __ldg(q.dlogit + q.slot / (uint32_t)g.fields);
         acc += gsl;
     }
     if (APPLY == 1) { dense_grad[id] = acc; return; }
@@ -566,7 +616,8 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
     if (n == 0) return RLCTR_OK;
     TableView t = view_of(table);
     AdamView a = APPLY == 0 ? view_of(opt) : AdamView{};
-    GradView g{grad->staged, grad->dlogit, grad->sums, grad->extra, grad->fields, grad->flags};
+    if (grad->world > RLCTR_MAX_WORLD || (grad->world > 1 && grad->n_per_rank == 0)) return RLCTR_EINVAL;
+    GradView g = grad_view_of(grad);
     if ((g.flags & RLCTR_STAGED_PARTNER) && (!g.staged || !g.dlogit || g.fields <= 0)) return RLCTR_EINVAL;
     if (t.rs == 1) {
         if (grad->extra || grad->sums) return RLCTR_EUNSUPPORTED;
@@ -633,6 +684,34 @@ extern "C" int rlctr_sort_ids(const int64_t* ids, int64_t n, int64_t n_rows, uin
                                                     key_bits(n_rows), st);
     if (e != cudaSuccess) return (int)e;
     RLCTR_COUNT_LAUNCH(2 + (key_bits(n_rows) + 7) / 8);   // cub onesweep: histogram, scan, one kernel per 8-bit digit
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_sort_ids_sharded(const uint32_t* ids_all, int64_t n_all, int32_t world, int32_t rank, int64_t n_rows_global,
+                                      uint32_t* sorted_rows, uint32_t* sorted_slots, void* ws, size_t ws_bytes,
+                                      rlctr_stream_t stream) {
+    if (!ids_all || !sorted_rows || !sorted_slots || !ws || n_all < 0 || n_rows_global <= 0) return RLCTR_EINVAL;
+    if (world != 1 && world != 2 && world != 4 && world != 8) return RLCTR_EUNSUPPORTED;
+    if (rank < 0 || rank >= world) return RLCTR_EINVAL;
+    if (n_all >= ((int64_t)1 << 32) || n_rows_global >= ((int64_t)1 << 32) - 1) return RLCTR_EUNSUPPORTED;
+    if (n_all == 0) return RLCTR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int shift = 0;
+    while ((1 << shift) < world) ++shift;
+    const int64_t n_local = (n_rows_global - rank + world - 1) / world;         // rows of this rank's shard
+    size_t arr = ((size_t)n_all * sizeof(uint32_t) + 255) & ~(size_t)255;
+    if (ws_bytes < 2 * arr + 256) return RLCTR_EWORKSPACE;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ws);
+    uint32_t* vals = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + arr);
+    void* temp = reinterpret_cast<char*>(ws) + 2 * arr;
+    size_t temp_bytes = ws_bytes - 2 * arr;
+    sort_prep_sharded_kernel<<<grid_1d(n_all, RLCTR_SMS * 8), 256, 0, st>>>(ids_all, n_all, n_rows_global, shift, (uint32_t)(world - 1),
+                                                                             (uint32_t)rank, (uint32_t)n_local, keys, vals);
+    RLCTR_LAUNCH_CHECK();
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, sorted_rows, vals, sorted_slots, n_all, 0,
+                                                    key_bits(n_local), st);
+    if (e != cudaSuccess) return (int)e;
+    RLCTR_COUNT_LAUNCH(2 + (key_bits(n_local) + 7) / 8);
     return RLCTR_OK;
 }
 

@@ -74,6 +74,14 @@ class Adam:
                 t, a = table_struct(data, owner._geom), opt.struct()
                 g = _lib.RowGrad(_lib.ptr(stash.staged), _lib.ptr(stash.dlogit), _lib.ptr(stash.sums),
                                  _lib.ptr(stash.extra), stash.fields, stash.flags)
+                if stash.peer is not None:           # sharded table: the owner pulls every rank's gradient buffers
+                    g.world, g.n_per_rank = stash.peer["world"], stash.peer["n_per_rank"]
+                    for name in ("staged", "dlogit", "sums", "extra"):
+                        ptrs = stash.peer[name]
+                        if ptrs is not None:
+                            arr = getattr(g, "peer_" + name)
+                            for r, ptr_ in enumerate(ptrs):
+                                arr[r] = ptr_
                 ws_bytes = lib.rlctr_rows_ws_bytes(stash.n)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=data.device)
                 _lib.call("rlctr_rows_adam", lib.rlctr_rows_adam, _lib.ptr(stash.sorted_ids), _lib.ptr(stash.sorted_slots),

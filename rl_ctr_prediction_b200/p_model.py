@@ -23,7 +23,7 @@ from . import mlp as _mlp
 
 class RowsStash:
     """What one backward pass leaves for the optimizer (struct rlctr_rowgrad + the sorted ids)."""
-    __slots__ = ("sorted_ids", "sorted_slots", "n", "dlogit", "sums", "extra", "staged", "fields", "flags")
+    __slots__ = ("sorted_ids", "sorted_slots", "n", "dlogit", "sums", "extra", "staged", "fields", "flags", "peer")
 
     def __init__(self, **kw):
         for k in self.__slots__:

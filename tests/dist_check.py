@@ -59,8 +59,10 @@ def main():
         ok = ok and good
         if rank == 0:
             print(json.dumps({"model": name, "world": world, "ok": good, "max_rel_err_vs_single_gpu": errs}))
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    # every rank has printed / compared; leave without tearing the symmetric-memory mappings down collectively
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

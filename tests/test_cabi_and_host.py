@@ -40,12 +40,23 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.rlctr_strerror(-1) == b"invalid argument"
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors of the C structs: sizes and key offsets equal what gcc computes from include/rlctr.h itself."""
+    import subprocess
     from rl_ctr_prediction_b200 import _lib
-    assert C.sizeof(_lib.Table) == 40           # ptr, i64, 5 x i32 (+pad)
-    assert C.sizeof(_lib.Adam) == 80            # 5 ptr, i32 (+pad), 4 x f64
-    assert C.sizeof(_lib.RowGrad) == 40         # 4 ptr, 2 x i32
-    assert _lib.Table.row_stride.offset == 16 and _lib.Adam.sched_len.offset == 40
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rlctr.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(rlctr_table), sizeof(rlctr_adam), sizeof(rlctr_rowgrad), offsetof(rlctr_table,row_stride),'
+                   'offsetof(rlctr_adam,sched_len), offsetof(rlctr_table,peers), offsetof(rlctr_rowgrad,peer_staged),'
+                   'offsetof(rlctr_rowgrad,peer_extra));return 0;}\n')
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.Table), C.sizeof(_lib.Adam), C.sizeof(_lib.RowGrad), _lib.Table.row_stride.offset,
+            _lib.Adam.sched_len.offset, _lib.Table.peers.offset, _lib.RowGrad.peer_staged.offset, _lib.RowGrad.peer_extra.offset]
+    assert got == want, (got, want)
+    assert C.sizeof(_lib.Table) == 104 and C.sizeof(_lib.Adam) == 80 and C.sizeof(_lib.RowGrad) == 304
 
 
 def test_argument_errors_need_no_gpu(lib):

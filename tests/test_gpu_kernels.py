@@ -691,3 +691,128 @@ def test_linear_fused_dropout_and_masked_dgrad(lib, B, K, N, path, monkeypatch):
                                 1.0, s, L().ptr(ws), wsb, st()) == 0
     refdx = (gy.astype(np.float64) @ w.astype(np.float64)) * np.where(xm > 0, s, 0.0)
     close(dx, refdx, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# row sharding with G ranks emulated on ONE GPU: peers[] are G shard tensors in the same device memory
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_sort_and_peer_gather(lib, world):
+    from rl_ctr_prediction_b200 import sharded
+    N, B, F, rs, D = 5003, 300, 15, 16, 10
+    rng = np.random.default_rng(world)
+    full = rng.standard_normal((N, rs)).astype(np.float32)
+    full[:, 11:] = 0
+    n_max = sharded.shard_rows(N, world, 0)
+    shards = []
+    for r in range(world):
+        sh = torch.zeros(n_max, rs, device=DEV)
+        part = dev(full[r::world])
+        sh[:part.shape[0]] = part
+        shards.append(sh)
+    ids = rng.integers(0, N, size=(world, B, F))
+    ids[0, 0, 0] = N + 7
+    # ---- rlctr_sort_ids_sharded against the host restatement, for every rank
+    ids_all = torch.as_tensor(ids.reshape(-1)).to(DEV)
+    all32 = ids_all.clamp(-1, N).to(torch.int32)
+    n_all = all32.numel()
+    for rank in range(world):
+        srows = torch.empty(n_all, dtype=torch.int32, device=DEV)
+        sslots = torch.empty(n_all, dtype=torch.int32, device=DEV)
+        wsb = lib.rlctr_sort_ws_bytes(n_all, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        assert lib.rlctr_sort_ids_sharded(L().ptr(all32), n_all, world, rank, N, L().ptr(srows), L().ptr(sslots), L().ptr(ws),
+                                          wsb, st()) == 0
+        rows_h, pos_h = sharded.owned_sorted_view_host(ids_all.cpu(), world, rank, N)
+        k = rows_h.numel()
+        assert torch.equal(srows[:k].cpu().long(), rows_h) and torch.equal(sslots[:k].cpu().long(), pos_h)
+        assert bool((srows[k:].cpu().long() == sharded.shard_rows(N, world, rank)).all())      # sentinel tail
+    # ---- rlctr_embed_fwd through peers[]: same logits / sums / rows as the unsharded table
+    x = torch.as_tensor(ids[1]).to(DEV)
+    bias = dev(np.array([0.3], np.float32))
+    outs = []
+    for sharded_mode in (False, True):
+        if sharded_mode:
+            t = L().Table(shards[0].data_ptr(), N, rs, 0, 1, D, 0)
+            t.world = world
+            for r in range(world):
+                t.peers[r] = shards[r].data_ptr()
+        else:
+            t = L().Table(L().ptr(dev(full)), N, rs, 0, 1, D, 0)
+            keep = dev(full)
+            t = L().Table(L().ptr(keep), N, rs, 0, 1, D, 0)
+        logit = torch.empty(B, device=DEV)
+        sums = torch.empty(B, rs, device=DEV)
+        rows = torch.empty(B, F * D, device=DEV)
+        assert lib.rlctr_embed_fwd(L().ptr(x), C.byref(t), L().ptr(bias), L().ptr(logit), None, 1, L().ptr(sums), L().ptr(rows), 0,
+                                   B, F, 1, st()) == 0
+        outs.append((logit.clone(), sums.clone(), rows.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # a world that is not a power of two, or a missing peer, is refused
+    t.world = 3
+    assert lib.rlctr_embed_fwd(L().ptr(x), C.byref(t), L().ptr(bias), L().ptr(logit), None, 1, None, None, 0, B, F, 1, st()) == -2
+    t.world = world
+    t.peers[world - 1] = None
+    assert lib.rlctr_embed_fwd(L().ptr(x), C.byref(t), L().ptr(bias), L().ptr(logit), None, 1, None, None, 0, B, F, 1, st()) == -2
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_owner_update_equals_single_table(lib, world):
+    """G ranks' FM steps emulated on one GPU: each owner runs rlctr_rows_adam on its shard with the sorted owned view
+    and PULLS dlogit / sums / extra from the G source buffers (peer_* pointers); the union of the shards equals one
+    rlctr_rows_adam over the whole table with the concatenated batch -- bit for bit."""
+    from rl_ctr_prediction_b200 import sharded
+    from rl_ctr_prediction_b200.tables import AdamSchedule
+    N, B, F, rs, D = 3001, 200, 15, 16, 10
+    rng = np.random.default_rng(5 + world)
+    full = rng.standard_normal((N, rs)).astype(np.float32) * 0.1
+    full[:, 11:] = 0
+    ids = rng.integers(0, N, size=(world, B, F))
+    dl = [rng.standard_normal(B).astype(np.float32) * 0.01 for _ in range(world)]
+    sm = [rng.standard_normal((B, rs)).astype(np.float32) for _ in range(world)]
+    ex = [rng.standard_normal((B, F * D)).astype(np.float32) * 0.01 for _ in range(world)]
+    sched = AdamSchedule(1e-3, (0.9, 0.999), DEV)
+
+    def adam_struct(tab):
+        m, v = torch.zeros_like(tab), torch.zeros_like(tab)
+        step = torch.zeros(1, dtype=torch.int32, device=DEV)
+        a = L().Adam(m.data_ptr(), v.data_ptr(), None, L().ptr(sched.tensor), L().ptr(step), sched.length, -1, 0.9, 0.999, 1e-8, 1e-5)
+        return a, (m, v, step)
+
+    # ---- reference: one table, concatenated batch
+    tab = dev(full)
+    x_all = torch.as_tensor(ids.reshape(-1, F)).to(DEV)
+    sid = torch.empty(x_all.numel(), dtype=torch.int32, device=DEV)
+    ssl = torch.empty_like(sid)
+    wsb = lib.rlctr_sort_ws_bytes(x_all.numel(), N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_sort_ids(L().ptr(x_all), x_all.numel(), N, L().ptr(sid), L().ptr(ssl), L().ptr(ws), wsb, st()) == 0
+    dl_all, sm_all, ex_all = dev(np.concatenate(dl)), dev(np.concatenate(sm)), dev(np.concatenate(ex))
+    g = L().RowGrad(None, L().ptr(dl_all), L().ptr(sm_all), L().ptr(ex_all), F, 0)
+    t = L().Table(L().ptr(tab), N, rs, 0, 1, D, 0)
+    a, keep = adam_struct(tab)
+    rwb = lib.rlctr_rows_ws_bytes(x_all.numel())
+    rws = torch.empty(rwb, dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_rows_adam(L().ptr(sid), L().ptr(ssl), x_all.numel(), C.byref(g), C.byref(t), C.byref(a), L().ptr(rws), rwb, st()) == 0
+    # ---- sharded: per owner
+    dls, sms, exs = [dev(d) for d in dl], [dev(s) for s in sm], [dev(e) for e in ex]
+    all32 = x_all.reshape(-1).to(torch.int32)
+    n_all = all32.numel()
+    for rank in range(world):
+        n_local = sharded.shard_rows(N, world, rank)
+        shard = dev(full[rank::world])
+        srows = torch.empty(n_all, dtype=torch.int32, device=DEV)
+        sslots = torch.empty(n_all, dtype=torch.int32, device=DEV)
+        assert lib.rlctr_sort_ids_sharded(L().ptr(all32), n_all, world, rank, N, L().ptr(srows), L().ptr(sslots), L().ptr(ws), wsb,
+                                          st()) == 0
+        gs = L().RowGrad(None, None, None, None, F, 0)
+        gs.world, gs.n_per_rank = world, B * F
+        for r in range(world):
+            gs.peer_dlogit[r], gs.peer_sums[r], gs.peer_extra[r] = dls[r].data_ptr(), sms[r].data_ptr(), exs[r].data_ptr()
+        ts = L().Table(L().ptr(shard), n_local, rs, 0, 1, D, 0)
+        as_, keep2 = adam_struct(shard)
+        assert lib.rlctr_rows_adam(L().ptr(srows), L().ptr(sslots), n_all, C.byref(gs), C.byref(ts), C.byref(as_), L().ptr(rws), rwb,
+                                   st()) == 0
+        assert torch.equal(shard, tab[rank::world]), rank
+        assert torch.equal(keep2[0], keep[0][rank::world]) and torch.equal(keep2[1], keep[1][rank::world])

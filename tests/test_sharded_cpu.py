@@ -1,39 +1,16 @@
-"""world_size-2 gloo tests (CPU) of the row-sharding host logic in rl_ctr_prediction_b200/sharded.py:
-bucketing -> all-to-all #1 (ids) -> owner gather -> all-to-all #2 (rows) -> all-to-all #3 (row
-gradients).  The device operations (bucket, gather) are injected as a host backend built from torch
-ops -- the product backend is the CUDA C ABI and is covered by the -m gpu tests; what is checked here is
-the routing: counts, split sizes, permutations and their inverses across ranks."""
+"""world_size-2 gloo tests (CPU) of the row-sharding protocol in rl_ctr_prediction_b200/sharded.py:
+all_gather of the ids -> every owner keeps what it owns, sorted by local row in (source rank, slot) order ->
+the owner pulls each occurrence's gradient from the source rank's buffer (here: an all_gather standing in for the
+peer-mapped reads) and reduces per row.  The device kernels (rlctr_sort_ids_sharded, the peer reads of
+rlctr_embed_fwd / rlctr_rows_adam) are covered by the -m gpu tests, which emulate G ranks on one GPU; what is
+checked here is the routing: ownership, local rows, global slots and their decomposition, across real ranks."""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
-
-
-class HostBackend:
-    """Same contract as sharded.CudaBackend, on CPU tensors (TEST ONLY)."""
-
-    def bucket(self, ids_flat, world, n_rows):
-        n = ids_flat.numel()
-        ok = (ids_flat >= 0) & (ids_flat < n_rows)
-        owner = torch.where(ok, ids_flat % world, torch.zeros_like(ids_flat))
-        order = torch.sort(owner, stable=True).indices
-        send_local = torch.where(ok, ids_flat // world, torch.full_like(ids_flat, -1))[order]
-        pos_of_slot = torch.empty(n, dtype=torch.int64)
-        pos_of_slot[order] = torch.arange(n)
-        counts = torch.bincount(owner, minlength=world)
-        ends = torch.cumsum(counts, 0)
-        ends = torch.where(counts > 0, ends, torch.full_like(ends, -1))
-        return send_local, pos_of_slot, order.to(torch.int32), ends
-
-    def gather(self, local_ids, table, geom):
-        out = torch.zeros(local_ids.numel(), geom.row_stride)
-        ok = (local_ids >= 0) & (local_ids < geom.n_rows)
-        out[ok] = table[local_ids[ok]]
-        return out
 
 
 def _free_port():
@@ -50,40 +27,53 @@ def _worker(rank, world, port, N, B, F, rs):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from rl_ctr_prediction_b200 import sharded
-        from rl_ctr_prediction_b200.tables import Geometry
         torch.manual_seed(0)                                   # same full table on every rank
         full = torch.randn(N, rs)
         n_local = sharded.shard_rows(N, world, rank)
         shard = full[rank::world].contiguous()
         assert shard.shape[0] == n_local
-        geom = Geometry(n_local, rs, 0, 1, rs - 1)
         g = torch.Generator().manual_seed(100 + rank)          # different batch per rank
         ids = torch.randint(0, N, (B, F), generator=g)
         ids[0, 0] = N + 5                                      # out-of-range id: zero row, no update
         ids[1, :] = ids[2, :]                                  # duplicates
-        be = HostBackend()
-        plan = sharded.exchange_plan(ids, N, None, be)
-        assert sum(plan.send_counts) == B * F and plan.n_recv == sum(plan.recv_counts)
-        # every received local row belongs to this shard
-        ok = plan.recv_local >= 0
-        assert int(plan.recv_local[ok].max()) < n_local
-        rows = sharded.fetch_rows(plan, shard, geom, None, be)
-        got = rows[plan.pos_of_slot].view(B, F, rs)            # back in slot order
-        want = torch.zeros(B, F, rs)
-        inr = ids < N
-        want[inr] = full[ids[inr]]
-        assert torch.equal(got, want)                          # bit-exact routed gather
-        # gradients: send slot-indexed rows, the owner must see each against the right local row
-        grad_slot = torch.randn(B * F, rs, generator=g)
-        gbuf = grad_slot[plan.send_slots.long()]               # send-buffer order
-        recv = sharded.push_grads(plan, gbuf, None)
-        dense = torch.zeros(n_local, rs, dtype=torch.float64)
-        dense.index_add_(0, plan.recv_local[ok], recv[ok].double())
-        # reference: gather every rank's (ids, grads), keep the ones this rank owns
+        n = B * F
+        # ---- the one collective of the lookup: fixed-size all_gather of the ids
         all_ids = [torch.empty_like(ids) for _ in range(world)]
-        all_g = [torch.empty_like(grad_slot) for _ in range(world)]
         dist.all_gather(all_ids, ids)
-        dist.all_gather(all_g, grad_slot)
+        ids_all = torch.cat([a.reshape(-1) for a in all_ids])
+        rows, gslots = sharded.owned_sorted_view_host(ids_all, world, rank, N)
+        # every kept id is owned by this rank, addressed by its local row, in stable (row, rank, slot) order
+        assert bool(((ids_all[gslots] % world) == rank).all()) and bool((ids_all[gslots] // world == rows).all())
+        assert int(rows.max()) < n_local
+        key = rows * (world * n) + gslots
+        assert bool((key[1:] > key[:-1]).all())
+        # the union over the owners covers every in-range occurrence exactly once
+        cnt = torch.tensor([gslots.numel()])
+        dist.all_reduce(cnt)
+        assert int(cnt) == int(((ids_all >= 0) & (ids_all < N)).sum())
+        # ---- forward: row id is read at peers[id % G] + (id // G): emulate the peer tables with an all_gather
+        n_max = sharded.shard_rows(N, world, 0)
+        padded = torch.zeros(n_max, rs)
+        padded[:n_local] = shard
+        shards = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(shards, padded)
+        flat = ids.reshape(-1)
+        ok = flat < N
+        got = torch.zeros(n, rs)
+        for r in range(world):
+            sel = ok & (flat % world == r)
+            got[sel] = shards[r][flat[sel] // world]
+        want = torch.zeros(n, rs)
+        want[ok] = full[flat[ok]]
+        assert torch.equal(got, want)                          # bit-exact gather through the sharded addressing
+        # ---- backward: the owner pulls grad[src rank][slot] for global slot = src * n + slot
+        grad_slot = torch.randn(n, rs, generator=g)
+        all_g = [torch.empty_like(grad_slot) for _ in range(world)]
+        dist.all_gather(all_g, grad_slot)                      # stands in for the peer-mapped gradient buffers
+        src, slot = gslots // n, gslots % n
+        pulled = torch.stack([all_g[int(s)][int(k)] for s, k in zip(src, slot)]) if gslots.numel() else torch.zeros(0, rs)
+        dense = torch.zeros(n_local, rs, dtype=torch.float64)
+        dense.index_add_(0, rows, pulled.double())
         ref = torch.zeros(n_local, rs, dtype=torch.float64)
         for i_, g_ in zip(all_ids, all_g):
             f = i_.reshape(-1)
@@ -95,14 +85,17 @@ def _worker(rank, world, port, N, B, F, rs):
 
 
 @pytest.mark.parametrize("N,B,F", [(101, 64, 15), (7, 16, 3)])
-def test_exchange_round_trip_world2(N, B, F):
+def test_sharded_protocol_world2(N, B, F):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), N, B, F, 12), nprocs=world, join=True)
 
 
-def test_counts_from_ends_and_shard_rows():
+def test_shard_rows_and_owned_view():
     from rl_ctr_prediction_b200 import sharded
-    assert sharded._counts_from_ends([3, -1, 10, -1], 10) == [3, 0, 7, 0]
-    assert sharded._counts_from_ends([-1, -1], 0) == [0, 0]
     assert [sharded.shard_rows(10, 4, r) for r in range(4)] == [3, 3, 2, 2]
     assert sum(sharded.shard_rows(10_000_000, 8, r) for r in range(8)) == 10_000_000
+    ids = torch.tensor([5, 2, 9, 2, 100, 6, 1])
+    rows, pos = sharded.owned_sorted_view_host(ids, 2, 0, 10)          # even ids < 10: 2, 2, 6 -> rows 1, 1, 3
+    assert rows.tolist() == [1, 1, 3] and pos.tolist() == [1, 3, 5]
+    rows, pos = sharded.owned_sorted_view_host(ids, 2, 1, 10)          # odd ids: 5, 9, 1 -> rows 2, 4, 0
+    assert rows.tolist() == [0, 2, 4] and pos.tolist() == [6, 0, 2]
