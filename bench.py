@@ -257,7 +257,8 @@ def reference_arm(args):
 def workload_config(B, N, D, world=1):
     return {"workload": "C2: LR+FM+DeepFM train step (fwd, BCE, bwd, Adam lr=1e-3 wd=1e-5, reference dense-Adam "
                         "numerics) on one batch" + ("" if world == 1 else f"; tables row-sharded over {world} GPUs "
-                        "(id mod G), 3 NCCL all-to-alls per model step, dense grads all-reduced"),
+                        "(id mod G) in peer-mapped symmetric memory: forward gathers read remote shards over NVLink, owners "
+                        "pull gradients in the fused reduce+Adam kernel, one id all_gather per batch, dense grads all-reduced"),
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "single GPU" if world == 1 else f"dp{world} x row-sharded tables",
             "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
             "ids": "uniform over disjoint per-field ranges", "l2": "inputs larger than L2: 3 tables x 3 arrays x "
@@ -287,7 +288,7 @@ def b200_arm(args):
     def build_models():
         ms = []
         for name in MODELS:
-            if world > 1:      # BASELINE.json configs[3]: tables row-sharded over the GPUs, NCCL all-to-all
+            if world > 1:      # BASELINE.json configs[3]: tables row-sharded over the GPUs (peer-mapped shards over NVLink)
                 from rl_ctr_prediction_b200 import sharded
                 m = sharded.ShardedCTR(name, N, F_FIELDS, D, device=dev)
             else:
@@ -323,11 +324,12 @@ def b200_arm(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (`value`) -------------------------------------
-    # N = 1: the whole three-model step is one CUDA graph (rl_ctr_prediction_b200/graphs.py): two eager warm-up steps,
-    # capture at the third, replays after that.  N > 1: the sharded path (variable all-to-all counts) runs eagerly.
+    # The whole three-model step is one CUDA graph (rl_ctr_prediction_b200/graphs.py): two eager warm-up steps, capture
+    # at the third, replays after that.  N > 1: the sharded step has no host synchronisation either (fixed-size id
+    # all_gather, device barriers), so it is captured the same way.
     ms = build_models()
     batches = [make_batch(gen, B, N, dev) for _ in range(K + W)]
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     if use_graph:
         from rl_ctr_prediction_b200 import graphs
         gstep = graphs.GraphedTrainStep(ms, lossf)

@@ -26,6 +26,8 @@ def eager_step(model, optimizer, loss_fn, x, y):
     """One training step of one model: the fused loss head for tower-less models, autograd for DeepFM
     (src/main/pretrain_main.py:96-102)."""
     from . import pretrain_main as PM
+    if hasattr(model, "train_step"):           # sharded.ShardedCTR: the row-sharded step (device barriers, no host sync)
+        return model.train_step(x, y, optimizer).detach()
     if isinstance(model, Model.DeepFM):
         p = model(x)
         tl = loss_fn(p, y.reshape(-1, 1).float())
