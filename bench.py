@@ -157,7 +157,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -337,11 +337,11 @@ def b200_arm(args):
     else:
         gstep = None
         run_step = lambda x, y: step(ms, x, y)
+    clocks = Clocks(local)
+    clocks.start()                       # sampled from the warm-up on: the timed region itself lasts tens of milliseconds
     for i in range(W):
         run_step(*batches[i])
     barrier()
-    clocks = Clocks(local)
-    clocks.start()
     l0 = lib.rlctr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -14,7 +14,7 @@ namespace rlctr {
 // K1
 // ------------------------------------------------------------------------------------------
 template <int LPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, const __grid_constant__ ShardView sv, int64_t n_rows, int pitch,
                  int rs, int lin_col, int emb_col, int dim, const float* __restrict__ bias,
                  float* __restrict__ logit, float* __restrict__ pctr, int64_t pctr_stride,
@@ -273,7 +273,7 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
     }
     if (rs > 32) return RLCTR_EUNSUPPORTED;
     if (sums && !rlctr_aligned16(sums)) return RLCTR_EALIGN;
-    int grid = grid_for_warps(batch, 8, 8);
+    int grid = grid_for_warps(batch, 8, 5);      // 5 resident CTAs of 8 warps per SM (48 registers)
 #define LAUNCH_EMBED(L)                                                                              \
     embed_fwd_kernel<L><<<grid, 256, 0, st>>>(ids, table->data, sv, table->n_rows, pitch_of(table), rs, table->lin_col,   \
                                               table->emb_col, table->dim, bias, logit, pctr,         \

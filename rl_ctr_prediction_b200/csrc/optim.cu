@@ -185,7 +185,7 @@ __device__ __forceinline__ void finish_row(int64_t id, int col0, float4 p, const
 
 // one lane-group (LPR lanes, a float4 chunk each) per sorted position; only run heads work
 template <int LPR, int APPLY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
                   GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
                   int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
@@ -193,14 +193,19 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
     const int64_t k = gt / LPR;
     const int c = (int)(gt % LPR), col0 = 4 * c;
     bool head = false;
-    uint32_t id = 0;
+    uint32_t id = 0, slot0 = 0;
     if (k < n) {
+        // four independent loads up front: the id, its neighbours (run head? long run?) and the first slot, so that the
+        // gradient-side loads (dlogit / sums / extra, addressed by the slot) leave together with the record loads
         id = __ldg(sorted_ids + k);
-        head = (id < (uint64_t)t.n_rows) && (k == 0 || __ldg(sorted_ids + k - 1) != id);
-    }
-    if (head && k + LONG_RUN < n && __ldg(sorted_ids + k + LONG_RUN) == id) {
-        if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)k;      // order is irrelevant: rows are independent
-        head = false;
+        const uint32_t prev = k > 0 ? __ldg(sorted_ids + k - 1) : 0xffffffffu;
+        const uint32_t far = (k + LONG_RUN < n) ? __ldg(sorted_ids + k + LONG_RUN) : 0xffffffffu;
+        slot0 = __ldg(sorted_slots + k);
+        head = (id < (uint64_t)t.n_rows) && prev != id;
+        if (head && far == id) {
+            if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)k;      // order is irrelevant: rows are independent
+            head = false;
+        }
     }
     const bool work = head && col0 < ((APPLY == 0) ? ((t.used + 3) & ~3) : t.rs);
     int step = 0, stamp_in = 0;
@@ -213,10 +218,10 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
         const float4 p = ld4(t.data + off);
         float4 m0 = f4zero(), v0 = f4zero();             // issued with p: one contiguous record when pitch = 3*rs
         if (APPLY == 0) { m0 = ld4(a.m + off); v0 = ld4(a.v + off); }
-        float4 acc = f4zero();
-        int64_t kk = k;
-        uint32_t nxt = id;
-        while (nxt == id) {
+        float4 acc = rowgrad_chunk(g, slot0, col0, p, t);
+        int64_t kk = k + 1;
+        uint32_t nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
+        while (nxt == id) {                              // further occurrences of the same row, in slot order
             const uint32_t slot = __ldg(sorted_slots + kk);
             ++kk;
             nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
