@@ -74,7 +74,11 @@ def tensor_peak():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {      # profiles/r1_ncu_top_kernels.md (B=65536, N=10M, D=10); bytes per launch
+    "rlctr_rows_adam[FM]": 246.4e6 + 136.4e6, "rlctr_rows_adam[DeepFM]": 295.3e6 + 137.9e6,
+    "rlctr_rows_catchup[FM]": 238.6e6 + 122.5e6, "rlctr_rows_catchup[DeepFM]": 238.7e6 + 122.3e6,
+    "rlctr_embed_fwd[FM]": 128.7e6 + 5.6e6, "rlctr_embed_fwd[DeepFM]": 130.4e6 + 22.5e6,
+}
 
 
 def make_batch(gen, B, N, device):
@@ -391,7 +395,9 @@ def b200_arm(args):
             fl = sum(gemm_flops(k, m) for _, _, m in prof.records[k]) / n_l
             gemm[k] = {"launches": n_l, "mean_ms": mean_ms, "fp32_equiv_TFLOPs": fl / (mean_ms / 1e3) / 1e12,
                        "tensor_pipe_TFLOPs_3x": 3 * fl / (mean_ms / 1e3) / 1e12}
-    all_kernels = {k: {"launches": v[0], "mean_ms": v[1], "GBps": v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 else None}
+    all_kernels = {k: {"launches": v[0], "mean_ms": v[1], "GBps": v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 else None,
+                       "frac_of_hbm_peak": v[2] / (v[1] / 1e3) / 1e9 / peak if v[1] > 0 else None,
+                       "ncu_dram_bytes_per_launch": NCU_TRAFFIC.get(k)}
                    for k, v in kern.items()}
     step_ms = ms_total / K                                # the graph-replay step the shares are read against
     shares = {g: round(tms / Kp / step_ms, 4) for g, tms in sorted(groups.items(), key=lambda kv: -kv[1])}
@@ -407,13 +413,12 @@ def b200_arm(args):
                 "flops_counted": "3 tf32 MMAs per fp32 product (3xTF32 split)", "share_of_step": groups[top] / Kp / step_ms}
     elif top is not None:
         keys = [k for k in kern if k.split("[")[0] == top]
-        tot_ms = sum(kern[k][0] * kern[k][1] for k in keys)
-        tot_alg = sum(kern[k][0] * kern[k][2] for k in keys)
-        n_l = sum(kern[k][0] for k in keys)
-        achieved = tot_alg / (tot_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": tot_alg / n_l, "launches_timed": n_l, "mean_ms": tot_ms / n_l,
+        key = max(keys, key=lambda k: kern[k][0] * kern[k][1])        # the heaviest launch of the dominant entry point
+        n_l, mean_ms, alg = kern[key]
+        achieved = alg / (mean_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": key, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(key), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "launches_timed": n_l, "mean_ms": mean_ms,
                 "share_of_step": groups[top] / Kp / step_ms}
     if roof is not None:
         roof["share_of_step_by_entry_point"] = shares
