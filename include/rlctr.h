@@ -102,6 +102,9 @@ typedef struct rlctr_adam {
  * any of the four pointers may be NULL. */
 #define RLCTR_STAGED_PARTNER 1   /* staged[slot] = d logit / d row (rlctr_ffm_fwd `partners`): the row
                                   * gradient is dlogit[b] * staged[slot] and nothing else            */
+#define RLCTR_DZ_IN_SUMS     2   /* dlogit[b] is ALSO stored in the last (padding) column of sums[b, :] and is read from
+                                  * there: for a sharded table the owner then pulls ONE aligned 64-byte line per occurrence
+                                  * over NVLink instead of a 4-byte and a 64-byte one (needs row_stride > used columns)  */
 typedef struct rlctr_rowgrad {
     const float* staged;   /* [n, row_stride] */
     const float* dlogit;   /* [B] */

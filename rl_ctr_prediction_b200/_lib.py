@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_PKG, "librlctr_sm100a.so")
 
 RLCTR_FM_TERM = 1
 RLCTR_STAGED_PARTNER = 1
+RLCTR_DZ_IN_SUMS = 2
 RLCTR_REDUCE_WS_BYTES = 16640
 RLCTR_MLP_RELU = 1
 RLCTR_MLP_DROPOUT = 2

@@ -135,9 +135,11 @@ __device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t gslo
     if (q.dlogit || q.extra) {
         const uint32_t b = slot / (uint32_t)g.fields;
         const uint32_t f = slot - b * (uint32_t)g.fields;
-        const float dz = q.dlogit ? __ldg(q.dlogit + b) : 0.f;
-        float4 S = f4zero();
         const bool fm = q.sums && q.dlogit;
+        float dz = 0.f;
+        if (fm && (g.flags & RLCTR_DZ_IN_SUMS)) dz = __ldg(q.sums + (int64_t)b * t.rs + (t.rs - 1));   // same line as S
+        else if (q.dlogit) dz = __ldg(q.dlogit + b);
+        float4 S = f4zero();
         if (fm) S = ldg4(q.sums + (int64_t)b * t.rs + col0);
         const float* ex = q.extra ? q.extra + ((int64_t)b * g.fields + f) * t.dim : nullptr;
 #pragma unroll
@@ -192,6 +194,10 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t k = gt / LPR;
     const int c = (int)(gt % LPR), col0 = 4 * c;
+    // keys are sorted and everything this table does not own (out-of-range ids; for a sharded table the other ranks'
+    // ids, G-1 out of G positions) sorts last as a sentinel: a block that STARTS in that tail has nothing to do
+    const int64_t k_first = ((int64_t)blockIdx.x * blockDim.x) / LPR;
+    if (k_first >= n || __ldg(sorted_ids + k_first) >= (uint64_t)t.n_rows) return;
     bool head = false;
     uint32_t id = 0, slot0 = 0;
     if (k < n) {
@@ -410,22 +416,25 @@ struct ReplayRow {
     int64_t off;
     int t;
 };
-// row of work item k: FLUSH -> r0 + k; CATCHUP -> the id at sorted position k if that position is a run head.
+// row of work item k: FLUSH -> r0 + k; CATCHUP -> the id at sorted position k if that position is a run head
+// (-1: nothing to do at this position; -2: past the end -- of the items, or of the ids this table owns: out-of-range and,
+// for a sharded table, non-owned ids sort last as sentinels and may outnumber the real ones G-1 to 1).
 // The loads it issues are only consumed one item later (software prefetch of the id stream).
 template <bool CATCHUP>
 __device__ __forceinline__ int64_t replay_row_of(int64_t k, int64_t n_items, int64_t r0, const uint32_t* __restrict__ sorted_ids,
                                                  int64_t n_rows) {
-    if (k >= n_items) return -1;
+    if (k >= n_items) return -2;
     if (!CATCHUP) return r0 + k;
     const uint32_t id = __ldg(sorted_ids + k);
     const uint32_t prev = k > 0 ? __ldg(sorted_ids + k - 1) : 0xffffffffu;
-    return (id < (uint64_t)n_rows && prev != id) ? (int64_t)id : -1;
+    if (id >= (uint64_t)n_rows) return -2;             // sentinel: keys are sorted, so nothing but sentinels follows
+    return prev != id ? (int64_t)id : -1;
 }
 // issue the loads of a whole record WITHOUT looking at its stamp first: one DRAM round trip instead of two, and
 // nothing in the caller depends on the data until the item becomes current (a full replay of another row later)
 template <int CH>
 __device__ __forceinline__ void replay_row_issue(ReplayRow<CH>& it, int64_t row, const TableView& t, const AdamView& a) {
-    it.off = row < 0 ? -1 : row * t.pitch;
+    it.off = row < 0 ? row : row * t.pitch;
     if (row >= 0) {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
@@ -456,6 +465,7 @@ replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const u
     replay_row_issue<CH>(cur, replay_row_of<CATCHUP>(kc, n_items, r0, sorted_ids, t.n_rows), t, a);
     replay_row_issue<CH>(nxt, replay_row_of<CATCHUP>(kc + stride, n_items, r0, sorted_ids, t.n_rows), t, a);
     int64_t row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
+    if (cur.off == -2) return;
     replay_row_arm<CH>(cur, a, upto);
     while (true) {
         if (cur.t >= upto) {                             // current item finished (or had nothing to do): switch
@@ -469,7 +479,7 @@ replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const u
                 }
             }
             kc += stride;
-            if (kc >= n_items) break;
+            if (kc >= n_items || nxt.off == -2) break;   // end of the queue, or of the ids this table owns
             cur = nxt;                                   // its loads were issued one whole item ago
             replay_row_issue<CH>(nxt, row2, t, a);       // row2's id was fetched one item ago: no dependent wait here
             row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
@@ -538,7 +548,8 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t id = __ldg(sorted_ids + k);
-    if (id >= (uint64_t)t.n_rows || (k > 0 && __ldg(sorted_ids + k - 1) == id)) return;
+    if (id >= (uint64_t)t.n_rows) return;                 // sentinel tail
+    if (k > 0 && __ldg(sorted_ids + k - 1) == id) return;
     float acc = 0.f;
     int64_t kk = k;
     uint32_t nxt = id;
@@ -624,6 +635,7 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
     if (grad->world > RLCTR_MAX_WORLD || (grad->world > 1 && grad->n_per_rank == 0)) return RLCTR_EINVAL;
     GradView g = grad_view_of(grad);
     if ((g.flags & RLCTR_STAGED_PARTNER) && (!g.staged || !g.dlogit || g.fields <= 0)) return RLCTR_EINVAL;
+    if ((g.flags & RLCTR_DZ_IN_SUMS) && (t.rs <= t.used || !g.sums)) return RLCTR_EINVAL;
     if (t.rs == 1) {
         if (grad->extra || grad->sums) return RLCTR_EUNSUPPORTED;
         rows_scalar_kernel<APPLY><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad);

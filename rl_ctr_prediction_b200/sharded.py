@@ -327,6 +327,9 @@ class ShardedCTR(nn.Module):
         if self.world > 1:                                    # gradient of the GLOBAL mean loss
             dlogit.mul_(1.0 / self.world)
             dbias.mul_(1.0 / self.world)
+        dz_in_sums = self.world > 1 and self._kind == "fm"
+        if dz_in_sums:                                        # one aligned 64 B line per occurrence for the owners to pull
+            buf["sums"].view(B, -1)[:, -1] = dlogit
         for p in self.parameters():
             p.grad = None
         if tower_out is not None:
@@ -348,6 +351,7 @@ class ShardedCTR(nn.Module):
                     "sums": buf["sums_ptrs"], "extra": buf["extra_ptrs"]}
         self._stash = Model.RowsStash(sorted_ids=srows, sorted_slots=sslots, n=n_all, dlogit=dlogit, sums=buf["sums"],
                                       extra=buf["extra"], staged=buf["staged"], fields=F,
-                                      flags=_lib.RLCTR_STAGED_PARTNER if buf["staged"] is not None else 0, peer=peer)
+                                      flags=(_lib.RLCTR_STAGED_PARTNER if buf["staged"] is not None else 0) |
+                                            (_lib.RLCTR_DZ_IN_SUMS if dz_in_sums else 0), peer=peer)
         optimizer.step()
         return loss.reshape(())

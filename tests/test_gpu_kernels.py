@@ -757,8 +757,9 @@ def test_sharded_sort_and_peer_gather(lib, world):
     assert lib.rlctr_embed_fwd(L().ptr(x), C.byref(t), L().ptr(bias), L().ptr(logit), None, 1, None, None, 0, B, F, 1, st()) == -2
 
 
+@pytest.mark.parametrize("dz_in_sums", [0, 1])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_owner_update_equals_single_table(lib, world):
+def test_sharded_owner_update_equals_single_table(lib, world, dz_in_sums):
     """G ranks' FM steps emulated on one GPU: each owner runs rlctr_rows_adam on its shard with the sorted owned view
     and PULLS dlogit / sums / extra from the G source buffers (peer_* pointers); the union of the shards equals one
     rlctr_rows_adam over the whole table with the concatenated batch -- bit for bit."""
@@ -796,6 +797,10 @@ def test_sharded_owner_update_equals_single_table(lib, world):
     rws = torch.empty(rwb, dtype=torch.uint8, device=DEV)
     assert lib.rlctr_rows_adam(L().ptr(sid), L().ptr(ssl), x_all.numel(), C.byref(g), C.byref(t), C.byref(a), L().ptr(rws), rwb, st()) == 0
     # ---- sharded: per owner
+    if dz_in_sums:                     # RLCTR_DZ_IN_SUMS: dlogit rides in the last (padding) column of the sums row
+        for r in range(world):
+            sm[r] = sm[r].copy()
+            sm[r][:, rs - 1] = dl[r]
     dls, sms, exs = [dev(d) for d in dl], [dev(s) for s in sm], [dev(e) for e in ex]
     all32 = x_all.reshape(-1).to(torch.int32)
     n_all = all32.numel()
@@ -806,7 +811,7 @@ def test_sharded_owner_update_equals_single_table(lib, world):
         sslots = torch.empty(n_all, dtype=torch.int32, device=DEV)
         assert lib.rlctr_sort_ids_sharded(L().ptr(all32), n_all, world, rank, N, L().ptr(srows), L().ptr(sslots), L().ptr(ws), wsb,
                                           st()) == 0
-        gs = L().RowGrad(None, None, None, None, F, 0)
+        gs = L().RowGrad(None, None, None, None, F, 2 if dz_in_sums else 0)
         gs.world, gs.n_per_rank = world, B * F
         for r in range(world):
             gs.peer_dlogit[r], gs.peer_sums[r], gs.peer_extra[r] = dls[r].data_ptr(), sms[r].data_ptr(), exs[r].data_ptr()
