@@ -146,6 +146,16 @@ int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, const float* b
                     float* logit, float* pctr, int64_t pctr_stride, float* sums, float* rows_out,
                     int64_t rows_pitch, int64_t batch, int32_t fields, int32_t flags, rlctr_stream_t stream);
 
+/* Pairwise inner products over already-gathered rows: the InnerPNN tower input (p_model.py:178-198)
+ *   out[b, :] = [ E (fields*dim) | ip (P = fields*(fields-1)/2) ]   (ip_first != 0: [ ip | E ], Feature_embedding.py:51-59)
+ *   ip[p] = <E[i], E[j]> for the p-th pair (i < j, row-major)      rows: [batch, fields*dim] at pitch ld_rows
+ * and its backward  grows[b, i, :] = g_E[i, :] + sum_{j != i} g_ip[pair(i, j)] * E[j, :].  fields <= 23. */
+int rlctr_pairdots_fwd(const float* rows, int64_t ld_rows, float* out, int64_t ld_out, int64_t batch,
+                       int32_t fields, int32_t dim, int32_t ip_first, rlctr_stream_t stream);
+int rlctr_pairdots_bwd(const float* rows, int64_t ld_rows, const float* gout, int64_t ld_g, float* grows,
+                       int64_t ld_grows, int64_t batch, int32_t fields, int32_t dim, int32_t ip_first,
+                       rlctr_stream_t stream);
+
 /* Plain bit-exact row gather out[k, :] = table[ids[k], :] (nn.Embedding.forward); the owner
  * side of the sharded lookup.  out has row_stride floats per row. */
 int rlctr_gather_rows(const int64_t* ids, int64_t n, const rlctr_table* table, float* out,

@@ -78,6 +78,46 @@ class PortCTR(nn.Module):
         return torch.sigmoid(self.logit(x))
 
 
+class PortTail(nn.Module):
+    """WideAndDeep / FNN / InnerPNN of src/models/p_model.py:103-200,326-373: the same gather with another dense
+    tail.  Parameter creation order and state_dict keys are the reference's."""
+
+    def __init__(self, kind: str, feature_nums: int, field_nums: int = 15, latent_dims: int = 10):
+        super().__init__()
+        assert kind in ("WideAndDeep", "FNN", "InnerPNN")
+        self.kind, self.F, self.D = kind, field_nums, latent_dims
+        if kind == "WideAndDeep":
+            self.linear = nn.Embedding(feature_nums, 1)                    # p_model.py:115
+            self.bias = nn.Parameter(torch.zeros(1))                       # :116
+            self.embedding = nn.Embedding(feature_nums, latent_dims)       # :118
+            self.mlp = _tower(field_nums * latent_dims)
+        elif kind == "FNN":
+            self.feature_embedding = nn.Embedding(feature_nums, latent_dims)   # :336
+            self.mlp = _tower(field_nums * latent_dims)
+        else:
+            self.feature_embedding = nn.Embedding(feature_nums, latent_dims)   # :158
+            self.mlp = _tower(field_nums * latent_dims + field_nums * (field_nums - 1) // 2)
+            idx = torch.triu_indices(field_nums, field_nums, offset=1)         # :178-181 (i < j, row-major)
+            self.row, self.col = idx[0].tolist(), idx[1].tolist()
+
+    def forward(self, x):
+        FD = self.F * self.D
+        if self.kind == "WideAndDeep":                                     # :135-144
+            e = self.embedding(x)
+            return torch.sigmoid(self.bias + torch.sum(self.linear(x), dim=1) + self.mlp(e.view(-1, FD)))
+        e = self.feature_embedding(x)
+        if self.kind == "FNN":                                             # :365-373
+            return torch.sigmoid(self.mlp(e.view(-1, FD)))
+        ip = torch.sum(torch.mul(e[:, self.row], e[:, self.col]), dim=2)   # :189
+        return torch.sigmoid(self.mlp(torch.cat([e.view(-1, FD), ip], dim=1)))   # :194-198
+
+
+def make_port(kind: str, feature_nums: int, field_nums: int = 15, latent_dims: int = 10) -> nn.Module:
+    if kind in ("WideAndDeep", "FNN", "InnerPNN"):
+        return PortTail(kind, feature_nums, field_nums, latent_dims)
+    return PortCTR(kind, feature_nums, field_nums, latent_dims)
+
+
 class PortFeatureEmbedding(nn.Module):
     """Feature_embedding.py:31-59."""
 

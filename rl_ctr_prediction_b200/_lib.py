@@ -58,6 +58,8 @@ SIGNATURES = {
     "rlctr_strerror": (C.c_char_p, [C.c_int]),
     "rlctr_launch_count": (C.c_ulonglong, []),
     "rlctr_embed_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _P]),
+    "rlctr_pairdots_fwd": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P]),
+    "rlctr_pairdots_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P]),
     "rlctr_gather_rows": (C.c_int, [_P, _I64, _TP, _P, _P]),
     "rlctr_ffm_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "rlctr_featemb_fwd": (C.c_int, [_P, _TP, _P, _I64, _I64, _I32, _P]),

@@ -225,6 +225,78 @@ featemb_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ ta
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Pairwise inner products over already-gathered rows (InnerPNN, p_model.py:178-198): the tower input
+// [E (F*D) | ip (P)] (or [ip | E], the Feature_Embedding order) and its backward
+//     d E[i] = g_E[i] + sum_{j != i} g_ip[pair(i,j)] * E[j]
+// Warp per sample; E and g_ip are staged in shared memory; pair index by a byte table.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_tables(unsigned char* pi, unsigned char* pj, unsigned char* pidx, int fields) {
+    for (int i = threadIdx.x; i < fields; i += blockDim.x) {
+        const int base = i * fields - i * (i + 1) / 2;       // pairs (i, i+1..F-1) in the reference's order
+        for (int j = i + 1; j < fields; ++j) {
+            const int p = base + j - i - 1;
+            if (pi) { pi[p] = (unsigned char)i; pj[p] = (unsigned char)j; }
+            if (pidx) { pidx[i * fields + j] = (unsigned char)p; pidx[j * fields + i] = (unsigned char)p; }
+        }
+    }
+}
+__global__ void __launch_bounds__(128)
+pairdots_fwd_kernel(const float* __restrict__ rows, int64_t ld_rows, float* __restrict__ out, int64_t ld_out, int64_t batch,
+                    int fields, int dim, int ip_first) {
+    extern __shared__ float smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int fd = fields * dim, npair = fields * (fields - 1) / 2;
+    float* stage = smem + wib * fd;
+    unsigned char* pi = reinterpret_cast<unsigned char*>(smem + nw * fd);
+    unsigned char* pj = pi + npair;
+    pair_tables(pi, pj, nullptr, fields);
+    __syncthreads();
+    const int e_off = ip_first ? npair : 0, ip_off = ip_first ? 0 : fd;
+    for (int64_t b = (int64_t)blockIdx.x * nw + wib; b < batch; b += (int64_t)gridDim.x * nw) {
+        const float* r = rows + b * ld_rows;
+        float* o = out + b * ld_out;
+        for (int i = lane; i < fd; i += 32) { const float v = __ldg(r + i); stage[i] = v; o[e_off + i] = v; }
+        __syncwarp();
+        for (int p = lane; p < npair; p += 32) {
+            const float* vi = stage + pi[p] * dim;
+            const float* vj = stage + pj[p] * dim;
+            float acc = 0.f;
+            for (int d = 0; d < dim; ++d) acc += vi[d] * vj[d];      // mul then sum over d, in d order
+            o[ip_off + p] = acc;
+        }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(128)
+pairdots_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __restrict__ gout, int64_t ld_g,
+                    float* __restrict__ grows, int64_t ld_grows, int64_t batch, int fields, int dim, int ip_first) {
+    extern __shared__ float smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int fd = fields * dim, npair = fields * (fields - 1) / 2;
+    float* stage = smem + wib * (fd + npair);
+    float* gip = stage + fd;
+    unsigned char* pidx = reinterpret_cast<unsigned char*>(smem + nw * (fd + npair));
+    pair_tables(nullptr, nullptr, pidx, fields);
+    __syncthreads();
+    const int e_off = ip_first ? npair : 0, ip_off = ip_first ? 0 : fd;
+    for (int64_t b = (int64_t)blockIdx.x * nw + wib; b < batch; b += (int64_t)gridDim.x * nw) {
+        const float* r = rows + b * ld_rows;
+        const float* g = gout + b * ld_g;
+        for (int i = lane; i < fd; i += 32) stage[i] = __ldg(r + i);
+        for (int p = lane; p < npair; p += 32) gip[p] = __ldg(g + ip_off + p);
+        __syncwarp();
+        for (int t = lane; t < fd; t += 32) {
+            const int i = t / dim, d = t - i * dim;
+            float acc = __ldg(g + e_off + t);
+            for (int j = 0; j < fields; ++j)
+                if (j != i) acc = fmaf(gip[pidx[i * fields + j]], stage[j * dim + d], acc);
+            grows[b * ld_grows + t] = acc;
+        }
+        __syncwarp();
+    }
+}
+
 static int grid_for_warps(int64_t items, int warps_per_block, int blocks_per_sm) {
     int64_t want = (items + warps_per_block - 1) / warps_per_block;
     int64_t cap = (int64_t)RLCTR_SMS * blocks_per_sm;
@@ -337,6 +409,41 @@ extern "C" int rlctr_featemb_fwd(const int64_t* ids, const rlctr_table* table, f
         default: LAUNCH_FE(8); break;
     }
 #undef LAUNCH_FE
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+
+extern "C" int rlctr_pairdots_fwd(const float* rows, int64_t ld_rows, float* out, int64_t ld_out, int64_t batch,
+                                  int32_t fields, int32_t dim, int32_t ip_first, rlctr_stream_t stream) {
+    if (!rows || !out || batch < 0 || fields < 2 || dim <= 0) return RLCTR_EINVAL;
+    if (fields > 23) return RLCTR_EUNSUPPORTED;                         // pair indices are bytes: F <= 23 (P <= 253)
+    const int fd = fields * dim, npair = fields * (fields - 1) / 2;
+    if (ld_rows < fd || ld_out < fd + npair) return RLCTR_EINVAL;
+    if (batch == 0) return RLCTR_OK;
+    const int nw = 4;
+    const size_t smem = (size_t)nw * fd * sizeof(float) + 2 * (size_t)npair;
+    if (smem > 48 * 1024) return RLCTR_EUNSUPPORTED;
+    pairdots_fwd_kernel<<<grid_for_warps(batch, nw, 16), nw * 32, smem, (cudaStream_t)stream>>>(rows, ld_rows, out, ld_out, batch,
+                                                                                               fields, dim, ip_first ? 1 : 0);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_pairdots_bwd(const float* rows, int64_t ld_rows, const float* gout, int64_t ld_g, float* grows,
+                                  int64_t ld_grows, int64_t batch, int32_t fields, int32_t dim, int32_t ip_first,
+                                  rlctr_stream_t stream) {
+    if (!rows || !gout || !grows || batch < 0 || fields < 2 || dim <= 0) return RLCTR_EINVAL;
+    if (fields > 23) return RLCTR_EUNSUPPORTED;
+    const int fd = fields * dim, npair = fields * (fields - 1) / 2;
+    if (ld_rows < fd || ld_g < fd + npair || ld_grows < fd) return RLCTR_EINVAL;
+    if (batch == 0) return RLCTR_OK;
+    const int nw = 4;
+    const size_t smem = (size_t)nw * (fd + npair) * sizeof(float) + (size_t)fields * fields;
+    if (smem > 48 * 1024) return RLCTR_EUNSUPPORTED;
+    pairdots_bwd_kernel<<<grid_for_warps(batch, nw, 16), nw * 32, smem, (cudaStream_t)stream>>>(rows, ld_rows, gout, ld_g, grows,
+                                                                                               ld_grows, batch, fields, dim,
+                                                                                               ip_first ? 1 : 0);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -28,7 +28,7 @@ def eager_step(model, optimizer, loss_fn, x, y):
     from . import pretrain_main as PM
     if hasattr(model, "train_step"):           # sharded.ShardedCTR: the row-sharded step (device barriers, no host sync)
         return model.train_step(x, y, optimizer).detach()
-    if isinstance(model, Model.DeepFM):
+    if getattr(model, "mlp", None) is not None:          # DeepFM, W&D, FNN, IPNN: the tower goes through autograd
         p = model(x)
         tl = loss_fn(p, y.reshape(-1, 1).float())
         model.zero_grad()

@@ -101,7 +101,7 @@ class _GatherInteract(torch.autograd.Function):
                       _lib.ptr(pctr), 1, _lib.ptr(partners), B, F, module.latent_dims, _lib.stream(),
                       key="rlctr_ffm_fwd" + ("[train]" if need_bwd else "[infer]"), meta=module._meta(B, F))
         else:
-            if need_bwd and module._kind == "fm":
+            if need_bwd and module._kind == "fm" and module._fm_term:
                 sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
             flags = _lib.RLCTR_FM_TERM if module._fm_term else 0
             _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(ids), C.byref(t), _lib.ptr(bias), _lib.ptr(logit),
@@ -361,3 +361,102 @@ class DeepFM(FM):
     def forward(self, x):
         z_fm, rows = self._run(x, True, False)
         return torch.sigmoid(z_fm + self.mlp(rows))
+
+
+class _PairDots(torch.autograd.Function):
+    """rows [B, F*D] -> [E | ip] (InnerPNN tower input, p_model.py:189-194): rlctr_pairdots_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, rows, fields, dim):
+        lib = _lib.load()
+        B, fd = rows.shape
+        npair = fields * (fields - 1) // 2
+        ld_rows = rows.stride(0) if (rows.stride(1) == 1 and B > 1) else fd
+        if not (rows.stride(1) == 1 and (B == 1 or rows.stride(0) >= fd)):
+            rows, ld_rows = rows.contiguous(), fd
+        pitch = (fd + npair + 3) // 4 * 4                      # 16-byte aligned pitch: the tower's first GEMM reads it by TMA
+        out = torch.empty(B, pitch, dtype=torch.float32, device=rows.device)
+        _lib.call("rlctr_pairdots_fwd", lib.rlctr_pairdots_fwd, rows.data_ptr(), ld_rows, _lib.ptr(out), pitch, B, fields, dim, 0,
+                  _lib.stream(), meta={"B": B})
+        ctx.save_for_backward(rows)
+        ctx.geom = (fields, dim, ld_rows, pitch)
+        return out[:, :fd + npair] if pitch != fd + npair else out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (rows,) = ctx.saved_tensors
+        fields, dim, ld_rows, pitch = ctx.geom
+        B, fd = rows.shape
+        gout = gout.contiguous()
+        grows = torch.empty(B, fd, dtype=torch.float32, device=rows.device)
+        _lib.call("rlctr_pairdots_bwd", lib.rlctr_pairdots_bwd, rows.data_ptr(), ld_rows, _lib.ptr(gout), gout.shape[1],
+                  _lib.ptr(grows), fd, B, fields, dim, 0, _lib.stream(), meta={"B": B})
+        return grows, None, None
+
+
+class WideAndDeep(_TableModel):
+    """p_model.py:103-144  sigma(bias + sum_f w[x_f] + MLP(concat_f v_f)): the DeepFM layout without the FM term."""
+    _kind = "fm"
+    _fm_term = False
+
+    def __init__(self, feature_nums, field_nums, latent_dims, output_dim=1, device=None):
+        super().__init__()
+        assert output_dim == 1
+        self.feature_nums, self.field_nums, self.latent_dims = feature_nums, int(field_nums), int(latent_dims)
+        g = Geometry.fm(feature_nums, self.latent_dims)
+        self._init_table(g, [(g.lin_col, 1), (g.emb_col, g.dim)], device)          # linear, then embedding (:115,118)
+        self.bias = nn.Parameter(torch.zeros((output_dim,), device=device))
+        self.mlp = _tower(self.field_nums * self.latent_dims, device)
+
+    def _ref_items(self):
+        g = self._geom
+        return [("linear.weight", g.lin_col, 1), ("embedding.weight", g.emb_col, g.dim)]
+
+    def forward(self, x):
+        z, rows = self._run(x, True, False)
+        return torch.sigmoid(z + self.mlp(rows))
+
+
+class FNN(_TableModel):
+    """p_model.py:326-373  sigma(MLP(concat_f v_f)); ``load_embedding`` takes an FM checkpoint (:358-363)."""
+    _kind = "fm"
+    _fm_term = False
+
+    def __init__(self, feature_nums, field_nums, latent_dims, device=None):
+        super().__init__()
+        self.feature_nums, self.field_nums, self.latent_dims = feature_nums, int(field_nums), int(latent_dims)
+        g = Geometry.fm(feature_nums, self.latent_dims, with_linear=False)
+        self._init_table(g, [(g.emb_col, g.dim)], device)
+        self.mlp = self._make_tower(device)
+
+    def _make_tower(self, device):
+        return _tower(self.field_nums * self.latent_dims, device)
+
+    def _ref_items(self):
+        g = self._geom
+        return [("feature_embedding.weight", g.emb_col, g.dim)]
+
+    def load_embedding(self, pretrain_params):
+        self.flush()
+        g = self._geom
+        with torch.no_grad():
+            self.table.data[:, g.emb_col:g.emb_col + g.dim].copy_(pretrain_params["feature_embedding.weight"])
+
+    def _tower_input(self, rows):
+        return rows
+
+    def forward(self, x):
+        _, rows = self._run(x, True, False)
+        return torch.sigmoid(self.mlp(self._tower_input(rows)))
+
+
+class InnerPNN(FNN):
+    """p_model.py:146-200  sigma(MLP([concat_f v_f | <v_i, v_j> for i < j]))."""
+
+    def _make_tower(self, device):
+        F = self.field_nums
+        return _tower(F * self.latent_dims + F * (F - 1) // 2, device)
+
+    def _tower_input(self, rows):
+        return _PairDots.apply(rows, self.field_nums, self.latent_dims)

@@ -47,6 +47,9 @@ _MODELS = {
     "FM": lambda n, f, d: Model.FM(n, d),
     "FFM": lambda n, f, d: Model.FFM(n, f, d),
     "DeepFM": lambda n, f, d: Model.DeepFM(n, f, d),
+    "W&D": lambda n, f, d: Model.WideAndDeep(n, f, d),
+    "FNN": lambda n, f, d: Model.FNN(n, f, d),
+    "IPNN": lambda n, f, d: Model.InnerPNN(n, f, d),
 }
 
 
@@ -101,8 +104,8 @@ def fused_train_step(model, optimizer, features, labels):
     sort -> catch-up -> gather+interaction -> sigmoid+BCE (+ their autograd) -> segment-reduce+Adam.
     Numerically the same step as ``loss(model(x), y); zero_grad(); backward(); optimizer.step()`` with
     ``nn.BCELoss``.  LR / FM / FFM (models without a dense tower).  Returns the loss (device scalar)."""
-    if isinstance(model, Model.DeepFM):
-        raise NotImplementedError("fused_train_step covers the tower-less models; DeepFM goes through autograd")
+    if getattr(model, "mlp", None) is not None:
+        raise NotImplementedError("fused_train_step covers the tower-less models; DeepFM / W&D / FNN / IPNN go through autograd")
     lib = _lib.load()
     x = Model._check_ids(features)
     B, F = x.shape
@@ -152,7 +155,7 @@ def train(model, optimizer, data_loader, loss, device, fused=False):
     for features, labels in data_loader:
         features = features.long().to(device, non_blocking=True)
         labels = torch.unsqueeze(labels, 1).to(device, non_blocking=True)
-        if fused and not isinstance(model, Model.DeepFM):
+        if fused and getattr(model, "mlp", None) is None:
             train_loss = fused_train_step(model, optimizer, features, labels)
         else:
             y = model(features)

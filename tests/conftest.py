@@ -35,6 +35,13 @@ def golden():
     return np.load(path, allow_pickle=False)
 
 
+@pytest.fixture(scope="session")
+def golden_tails():
+    """WideAndDeep / FNN / InnerPNN trajectories from the real reference (tests/golden/make_golden_tails.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden_tails.npz")
+    return np.load(path, allow_pickle=False)
+
+
 def state_from_golden(golden, prefix):
     """Collect {state_dict_key: ndarray} stored under `prefix/`."""
     pre = prefix.rstrip("/") + "/"

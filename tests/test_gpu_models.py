@@ -422,3 +422,58 @@ def test_tower_train_mode_matches_mask_as_input_reference():
 def _L():
     from rl_ctr_prediction_b200 import _lib
     return _lib
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining p_model tails on the same gather
+# ------------------------------------------------------------------------------------------------
+_TAIL_NAMES = {"WideAndDeep": "W&D", "FNN": "FNN", "InnerPNN": "IPNN"}
+
+
+@pytest.mark.parametrize("mode", ["lazy", "dense"])
+@pytest.mark.parametrize("name", ["WideAndDeep", "FNN", "InnerPNN"])
+def test_tail_models_match_reference(golden, golden_tails, name, mode):
+    """W&D / FNN / IPNN: state_dict keys and shapes are the reference's; 3 steps of the reference loop body give the
+    reference's pctr, loss and final parameters (all rows)."""
+    from rl_ctr_prediction_b200 import optim
+    sd = state_from_golden(golden_tails, f"train/{name}/init")
+    m = load(build(_TAIL_NAMES[name], 255), sd).to(DEV)
+    out_sd = m.state_dict()
+    assert set(out_sd.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert np.array_equal(out_sd[k].cpu().numpy(), v), k
+    m.eval()
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5, mode=mode)
+    lossf = torch.nn.BCELoss()
+    xs, ys = golden["train/x"], golden["train/y"]
+    for s in range(3):
+        x = torch.as_tensor(xs[s]).to(DEV)
+        y = torch.as_tensor(ys[s]).unsqueeze(1).to(DEV)
+        p = m(x)
+        tl = lossf(p, y.float())
+        m.zero_grad()
+        tl.backward()
+        opt.step()
+        close(p, golden_tails[f"train/{name}/pctr{s}"])
+        close(tl, golden_tails[f"train/{name}/loss{s}"])
+    assert_state(m, state_from_golden(golden_tails, f"train/{name}/final"))
+
+
+def test_pairdots_kernels_against_torch():
+    """rlctr_pairdots_fwd / _bwd (InnerPNN) against the reference expression and its autograd, padded pitches included."""
+    from rl_ctr_prediction_b200 import p_model
+    Bt, Ft, Dt = 777, 15, 10
+    torch.manual_seed(2)
+    buf = torch.full((Bt, 152), float("nan"), device=DEV)
+    buf[:, :150] = torch.randn(Bt, 150, device=DEV)
+    rows = buf[:, :150].requires_grad_(True)
+    out = p_model._PairDots.apply(rows, Ft, Dt)
+    g = torch.randn(Bt, 150 + 105, device=DEV)
+    out.backward(g)
+    e = buf[:, :150].detach().double().view(Bt, Ft, Dt).requires_grad_(True)
+    idx = torch.triu_indices(Ft, Ft, offset=1)
+    ref = torch.cat([e.view(Bt, -1), (e[:, idx[0]] * e[:, idx[1]]).sum(dim=2)], dim=1)
+    ref.backward(g.double())
+    assert torch.equal(out[:, :150], buf[:, :150])
+    close(out, ref.detach(), rtol=1e-6)
+    close(rows.grad, e.grad.view(Bt, -1), rtol=1e-5)

@@ -164,6 +164,29 @@ def test_training_trajectory_torch_port(golden, name):
         close(m.state_dict()[k].numpy(), v, rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", ["WideAndDeep", "FNN", "InnerPNN"])
+def test_training_trajectory_torch_port_tails(golden, golden_tails, name):
+    """The restated W&D / FNN / IPNN reproduce the real reference modules' trajectories."""
+    init = state_from_golden(golden_tails, f"train/{name}/init")
+    N = [v for k, v in init.items() if k.endswith("embedding.weight")][0].shape[0]
+    m = TP.make_port(name, N, F, D)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})
+    m.eval()
+    opt = TP.make_adam(m)
+    xs, ys = torch.from_numpy(golden["train/x"]), torch.from_numpy(golden["train/y"])
+    for s in range(3):
+        loss = TP.ctr_train_step(m, opt, torch.nn.BCELoss(), xs[s], ys[s].view(-1, 1))
+        close(loss, golden_tails[f"train/{name}/loss{s}"], rtol=1e-6)
+    for k, v in state_from_golden(golden_tails, f"train/{name}/final").items():
+        close(m.state_dict()[k].numpy(), v, rtol=1e-6, atol=1e-7)
+    # same seed -> same initial parameters as the reference constructors (creation order)
+    torch.manual_seed(1)
+    fresh = TP.make_port(name, N, F, D)
+    for k, v in fresh.state_dict().items():
+        scale = 0.1 if ("embedding" in k or k == "linear.weight") else 1.0
+        close(v.numpy() * scale, init[k], rtol=1e-6, atol=1e-8)
+
+
 def test_port_init_matches_reference_seed(golden):
     """Same torch.manual_seed -> same initial parameters as the reference constructors."""
     for name in ("LR", "FM", "FFM", "DeepFM"):
