@@ -272,6 +272,17 @@ int rlctr_reinforce_loss_bwd(const float* logits, const int64_t* act, const floa
                              int64_t batch, int32_t actions, int32_t variant, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Evaluation metrics on the device (replaces the per-batch .tolist() + sklearn.metrics.roc_auc_score of test() /
+ * submission(), src/main/pretrain_main.py:110-139):
+ *   out[0] = ROC AUC of `pred` against the binary labels (ties get average ranks, as sklearn; NaN if one class only)
+ *   out[1] = mean BCE log-loss with torch's clamped logs
+ * Deterministic (fixed-order partial sums in double).  ws: rlctr_auc_ws_bytes(n) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------ */
+size_t rlctr_auc_ws_bytes(int64_t n);
+int rlctr_auc_logloss(const float* pred, const int64_t* labels_i64, const float* labels_f32, int64_t n, float* out,
+                      void* ws, size_t ws_bytes, rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * K4  dense layers on the tcgen05 tensor cores (3xTF32 split: fp32-grade accuracy).
  * nn.Linear of the DeepFM tower (p_model.py:276-293) and of the policy networks
  * (PG_model.py:42-51, DDQN_model.py:20-52, DDPG_for_PG_model.py:20-81): weight [out,in] row-major,

@@ -77,6 +77,8 @@ SIGNATURES = {
     "rlctr_step_advance": (C.c_int, [_P, _I32, _P]),
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "rlctr_auc_ws_bytes": (_SZ, [_I64]),
+    "rlctr_auc_logloss": (C.c_int, [_P, _P, _P, _I64, _P, _P, _SZ, _P]),
     "rlctr_mlp_ws_bytes": (_SZ, [_I64, _I32, _I32]),
     "rlctr_rng_advance": (C.c_int, [_P, C.c_uint64, _P]),
     "rlctr_linear_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, C.c_float, _P, _P, _SZ, _P]),

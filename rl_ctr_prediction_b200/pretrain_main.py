@@ -63,11 +63,33 @@ def get_model(model_name, feature_nums, field_nums, latent_dims):
                                   f"(available: {sorted(_MODELS)})") from None
 
 
+def load_encoded(path):
+    """``train.txt`` (rows ``click,id_0..id_{F-1}``, the on-disk contract of src/encode/data_.py:85) as int64 [n, 1+F].
+    The text is parsed once; a binary image ``<path>.int64.npy`` is kept beside it and memory-mapped on later runs
+    (the reference re-parses the CSV with pandas on every start, src/main/pretrain_main.py:52).  The image
+    is rebuilt whenever the text file is newer."""
+    cache = path + ".int64.npy"
+    try:
+        if os.path.exists(cache) and os.path.getmtime(cache) >= os.path.getmtime(path):
+            return np.load(cache, mmap_mode="r")
+    except (OSError, ValueError):
+        pass
+    data = np.loadtxt(path, delimiter=",", dtype=np.int64, ndmin=2)
+    try:
+        tmp = cache + ".tmp"
+        with open(tmp, "wb") as fh:
+            np.save(fh, data)
+        os.replace(tmp, cache)
+    except OSError:
+        pass                                   # read-only data directory: keep parsing the text
+    return data
+
+
 def get_dataset(datapath, dataset_name, campaign_id, valid_day, test_day):
     """pretrain_main.py:47-88: ``train.txt`` rows ``click,id_0..id_{F-1}`` (src/encode/data_.py:85) and
     ``day_index.csv`` rows ``day,first_row,last_row``; train = every day but valid/test."""
     data_path = datapath + dataset_name + campaign_id
-    train_fm = np.loadtxt(data_path + "train.txt", delimiter=",", dtype=np.int64, ndmin=2)
+    train_fm = load_encoded(data_path + "train.txt")
     field_nums = train_fm.shape[1] - 1
     feature_nums = int(train_fm[:, 1:].max()) + 1
     day_indexs = np.loadtxt(data_path + "day_index.csv", delimiter=",", dtype=np.int64, ndmin=2)
@@ -169,6 +191,7 @@ def train(model, optimizer, data_loader, loss, device, fused=False):
 
 
 def _predict_all(model, data_loader, loss, device):
+    """Predictions and labels of the whole loader, kept on the device (no per-batch .tolist())."""
     model.eval()
     targets, predicts, losses = [], [], []
     with torch.no_grad():
@@ -180,23 +203,23 @@ def _predict_all(model, data_loader, loss, device):
                 losses.append(loss(y, labels.float()))
             targets.append(labels)
             predicts.append(y)
-    targets = torch.cat(targets).cpu().numpy()
-    predicts = torch.cat(predicts).cpu().numpy()
-    return targets, predicts, [l.item() for l in losses]
+    return torch.cat(targets), torch.cat(predicts), losses
 
 
 def test(model, data_loader, loss, device):
-    """pretrain_main.py:110-126: (AUC via sklearn, mean per-batch loss)."""
-    from sklearn.metrics import roc_auc_score
+    """pretrain_main.py:110-126: (AUC, mean per-batch loss).  The AUC is computed on the device (metrics.roc_auc_score:
+    rlctr_auc_logloss, sklearn's tie handling) instead of .tolist() + sklearn.metrics.roc_auc_score."""
+    from . import metrics
     targets, predicts, losses = _predict_all(model, data_loader, loss, device)
-    return roc_auc_score(targets, predicts), sum(losses) / len(losses)
+    mean_loss = torch.stack(losses).double().mean().item() if losses else float("nan")   # mean of the per-batch losses (:126)
+    return metrics.roc_auc_score(targets, predicts), mean_loss
 
 
 def submission(model, data_loader, device):
     """pretrain_main.py:128-139: (list of [pctr], AUC)."""
-    from sklearn.metrics import roc_auc_score
+    from . import metrics
     targets, predicts, _ = _predict_all(model, data_loader, None, device)
-    return predicts.tolist(), roc_auc_score(targets, predicts)
+    return predicts.cpu().numpy().tolist(), metrics.roc_auc_score(targets, predicts)
 
 
 def eva_stopping(valid_aucs, valid_losses, type):

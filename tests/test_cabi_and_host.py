@@ -135,3 +135,21 @@ def test_eva_stopping_and_get_model():
     assert PM.eva_stopping([], [1, 2, 3, 4, 5], "loss") and not PM.eva_stopping([], [1, 2, 3, 4], "loss")
     with pytest.raises(NotImplementedError):
         PM.get_model("nope", 10, 15, 4)
+
+
+def test_encoded_text_is_parsed_once_and_cached(tmp_path):
+    """The CSV of src/encode/data_.py:85 stays the on-disk contract; its int64 image is cached beside it."""
+    from rl_ctr_prediction_b200 import pretrain_main as PM
+    rng = np.random.default_rng(0)
+    rows = np.column_stack([rng.integers(0, 2, 50), rng.integers(0, 1000, (50, 15))]).astype(np.int64)
+    path = str(tmp_path / "train.txt")
+    np.savetxt(path, rows, delimiter=",", fmt="%d")
+    a = PM.load_encoded(path)
+    assert np.array_equal(a, rows) and os.path.exists(path + ".int64.npy")
+    b = PM.load_encoded(path)                       # second call: memory-mapped image
+    assert isinstance(b, np.memmap) and np.array_equal(b, rows)
+    rows2 = rows.copy()
+    rows2[0, 1] = 7
+    np.savetxt(path, rows2, delimiter=",", fmt="%d")
+    os.utime(path, (os.path.getmtime(path) + 5, os.path.getmtime(path) + 5))
+    assert np.array_equal(PM.load_encoded(path), rows2)      # newer text invalidates the image

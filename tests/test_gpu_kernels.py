@@ -821,3 +821,34 @@ def test_sharded_owner_update_equals_single_table(lib, world, dz_in_sums):
                                    st()) == 0
         assert torch.equal(shard, tab[rank::world]), rank
         assert torch.equal(keep2[0], keep[0][rank::world]) and torch.equal(keep2[1], keep[1][rank::world])
+
+
+# ------------------------------------------------------------------------------------------------
+# device AUC / log-loss against sklearn
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["random", "ties", "saturated", "tiny", "large"])
+def test_auc_logloss_matches_sklearn(lib, case):
+    from sklearn.metrics import log_loss, roc_auc_score
+    from rl_ctr_prediction_b200 import metrics
+    rng = np.random.default_rng(7)
+    n = {"random": 10007, "ties": 5000, "saturated": 4096, "tiny": 2, "large": 1 << 20}[case]
+    y = (rng.random(n) < 0.2).astype(np.int64)
+    if case == "tiny":
+        y = np.array([0, 1], np.int64)
+    p = rng.random(n).astype(np.float32)
+    p = np.clip(0.6 * p + 0.4 * y * rng.random(n).astype(np.float32), 1e-6, 1 - 1e-6).astype(np.float32)
+    if case == "ties":
+        p = (np.round(p * 8) / 8).astype(np.float32).clip(0.0625, 0.9375)          # 8 distinct scores
+    if case == "saturated":
+        p[: n // 2] = np.where(rng.random(n // 2) < 0.5, 0.0, 1.0).astype(np.float32)   # exact 0 / 1 like N(0,1) init
+    out = metrics.auc_logloss(dev(p), torch.as_tensor(y).to(DEV)).cpu().numpy()
+    assert abs(out[0] - roc_auc_score(y, p)) < 2e-6
+    pc = p.astype(np.float64)
+    ll = np.mean(-(y * np.maximum(np.log(pc), -100)) - (1 - y) * np.maximum(np.log1p(-pc), -100)) if case != "saturated" else None
+    if ll is not None:
+        assert abs(out[1] - ll) < 1e-5 * max(1.0, abs(ll))
+    # float labels, and run-to-run determinism
+    out2 = metrics.auc_logloss(dev(p), dev(y.astype(np.float32))).cpu().numpy()
+    assert np.array_equal(out, out2)
+    # one class only: AUC undefined (sklearn raises; here NaN)
+    assert np.isnan(metrics.auc_logloss(dev(p), torch.zeros(n, dtype=torch.int64, device=DEV)).cpu().numpy()[0])
