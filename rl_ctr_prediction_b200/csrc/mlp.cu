@@ -722,13 +722,22 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
             }
         }
     }
+    bool db_done = false;
     if (dw) {   // dW[out,in] = dY^T[out,B] * X[B,in]: both operands contiguous along M / N, K = batch; split-K
         const int64_t mn = (int64_t)out_dim * in_dim;
         int splits = tma::enabled() ? tma::plan_splits(out_dim, in_dim, (int)batch, true) : 0;
         int rc = RLCTR_EUNSUPPORTED;
-        if (splits >= 1)
+        if (splits >= 1) {
+            // the converter warps of the TMA kernel sum dY's columns while they split the tile: db comes for free
+            float* dbp = (db && (size_t)splits * out_dim * sizeof(float) <= l.colsum) ? cpart : nullptr;
             rc = tma::gemm(tma::Operand{dy, nullptr, out_dim, true}, tma::Operand{x, nullptr, ldx, true}, splits == 1 ? dw : part,
-                           in_dim, nullptr, out_dim, in_dim, (int)batch, 0, true, st);
+                           in_dim, nullptr, out_dim, in_dim, (int)batch, 0, true, st, nullptr, dbp);
+            if (rc == RLCTR_OK && dbp) {
+                splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(dbp, db, out_dim, splits);
+                RLCTR_LAUNCH_CHECK();
+                db_done = true;
+            }
+        }
         if (rc == RLCTR_EUNSUPPORTED) {
             GemmPlan p = plan_gemm(out_dim, in_dim, (int)batch, true);
             splits = p.splits;
@@ -742,7 +751,7 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
             RLCTR_LAUNCH_CHECK();
         }
     }
-    if (db) {
+    if (db && !db_done) {
         dim3 grid((out_dim + 31) / 32, yb);
         colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, out_dim, nullptr, cpart, batch, out_dim, COLSUM_ROWS_PER_BLOCK);
         RLCTR_LAUNCH_CHECK();

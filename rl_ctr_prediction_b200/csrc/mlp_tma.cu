@@ -51,6 +51,7 @@ struct Args {
     int a_mn, b_mn;                       // 1: operand is contiguous along M (N) instead of K
     int b_presplit;                       // 1: B arrives as (hi, lo) through mapB / mapBlo
     int relu;
+    float* colsum_part;                   // wgrad only: [splits][M] partial column sums of the MN-major A operand (db), or null
     Epilogue epi;                         // fused dropout (forward) / ReLU-dropout mask of the layer below (dgrad)
 };
 
@@ -213,6 +214,27 @@ __device__ __forceinline__ void split_tile(uint32_t hi, uint32_t lo, int bytes, 
     }
 }
 
+// The same split for the MN-major A tile of wgrad (dY^T: [32 k-rows][128 m] as four 4096-byte blocks of 32 m) that ALSO
+// accumulates the raw values per column: the bias gradient db[m] = sum_k dY[k, m] falls out of the pass the converters
+// make anyway.  A thread always meets the same four logical columns of each m-block (the 32-byte-chunk swizzle XORs the
+// chunk index with (k & 3), and a thread's k-rows keep k & 3 fixed), so four float4 accumulators suffice.
+__device__ __forceinline__ void split_tile_colsum(uint32_t hi, uint32_t lo, int tid, float4 (&acc)[BM / 32]) {
+    constexpr int STEP = CONV_WARPS * 32 * 16;                    // 2048 B = 16 k-rows of one m-block
+#pragma unroll
+    for (int j = 0; j < BM / 32; ++j) {
+        const int off = tid * 16 + j * 4096;
+        const float4 x0 = lds128(hi + off), x1 = lds128(hi + off + STEP);
+        float4 h, l;
+        split4(x0, h, l);
+        sts128(hi + off, h);
+        sts128(lo + off, l);
+        split4(x1, h, l);
+        sts128(hi + off + STEP, h);
+        sts128(lo + off + STEP, l);
+        acc[j].x += x0.x + x1.x; acc[j].y += x0.y + x1.y; acc[j].z += x0.z + x1.z; acc[j].w += x0.w + x1.w;
+    }
+}
+
 struct TileWalk {                          // this CTA's (tile, k-block) sequence, identical in every role
     int tile, kb0, kb1, mt, nt, split;
 };
@@ -368,15 +390,48 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        const bool colsum = g.colsum_part != nullptr && g.a_mn;
         for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+            const bool sum_tile = colsum && w.nt == 0;     // every (split, m-tile) is met exactly once with nt == 0
+            float4 acc[BM / 32];
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(smem_u32(&raw_bar[stage]), phase);
                 const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-                split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, tid);
+                if (sum_tile) split_tile_colsum(st, st + A_TILE_BYTES, tid, acc);
+                else split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, tid);
                 if (!g.b_presplit) split_tile(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_bytes, b_bytes, tid);
                 fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
                 mbar_arrive(smem_u32(&full_bar[stage]));
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+            if (sum_tile) {
+                // 16 threads hold partial sums of the same columns: 4 lanes of every warp (the k-row residues r = 0..3,
+                // at lane r*8 + (((lc ^ r) << 1) | half)), times 4 warps.  Butterfly over r, then a fixed-order sum over
+                // the warps through shared memory (the bias staging area: wgrad has no bias).
+                const int r = (tid >> 3) & 3, half = tid & 1, lc = ((tid & 7) >> 1) ^ r, wq = tid >> 5;
+#pragma unroll
+                for (int step = 1; step <= 2; step <<= 1) {
+                    const int rp = r ^ step;
+                    const int src = rp * 8 + (((lc ^ rp) << 1) | half);
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j) {
+                        acc[j].x += __shfl_sync(RLCTR_FULL, acc[j].x, src);
+                        acc[j].y += __shfl_sync(RLCTR_FULL, acc[j].y, src);
+                        acc[j].z += __shfl_sync(RLCTR_FULL, acc[j].z, src);
+                        acc[j].w += __shfl_sync(RLCTR_FULL, acc[j].w, src);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(CONV_WARPS * 32) : "memory");      // previous tile's readers are done
+                if (r == 0) {
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j)
+                        *reinterpret_cast<float4*>(&s_bias[wq * BM + j * 32 + lc * 8 + half * 4]) = acc[j];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(CONV_WARPS * 32) : "memory");
+                const int m = w.mt * BM + tid;
+                if (m < g.M) g.colsum_part[(int64_t)w.split * g.M + m] = s_bias[tid] + s_bias[BM + tid] + s_bias[2 * BM + tid] + s_bias[3 * BM + tid];
             }
         }
     } else if (warp == PRODUCER_WARP) {
@@ -615,7 +670,7 @@ int split_weight(const float* w, float* hi, float* lo, int rows, int cols, int p
 
 // RLCTR_EUNSUPPORTED: the caller falls back to the software-staged kernel (mlp.cu)
 int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float* bias, int M, int N, int K, int relu,
-         bool allow_split, cudaStream_t st, const Epilogue* epi) {
+         bool allow_split, cudaStream_t st, const Epilogue* epi, float* colsum_part) {
     if (!enabled()) return RLCTR_EUNSUPPORTED;
     if (!tma_ok(A.ptr, A.pitch) || !tma_ok(B.ptr, B.pitch) || (B.lo && !tma_ok(B.lo, B.pitch))) return RLCTR_EUNSUPPORTED;
     if (A.lo) return RLCTR_EUNSUPPORTED;                  // the streamed operand is always converted in the kernel
@@ -634,6 +689,8 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages;
     g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
+    g.colsum_part = (colsum_part && A.mn_major && !bias) ? colsum_part : nullptr;
+    if (colsum_part && !g.colsum_part) return RLCTR_EUNSUPPORTED;
     g.epi = epi ? *epi : Epilogue{};
     if ((g.epi.drop_state || g.epi.mask_src) && p.splits != 1) return RLCTR_EUNSUPPORTED;
     if (g.epi.mask_src) g.epi.mvec = vec_of(g.epi.mask_src, g.epi.mask_ld);

@@ -31,7 +31,9 @@ int plan_splits(int M, int N, int K, bool b_mn);          // split-K factor the 
 int split_weight(const float* w, float* hi, float* lo, int rows, int cols, int pitch, cudaStream_t st);
 // C[(split*M + m)*ldc + n] = sum_k A[m,k] B[n,k]; RLCTR_EUNSUPPORTED when an operand is not TMA-addressable
 int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float* bias, int M, int N, int K, int relu,
-         bool allow_split, cudaStream_t st, const Epilogue* epi = nullptr);
+         bool allow_split, cudaStream_t st, const Epilogue* epi = nullptr, float* colsum_part = nullptr);
+// colsum_part (wgrad form only: A MN-major, no bias): [splits][M] partial sums over k of A[k, m] -- the bias gradient,
+// accumulated by the converter warps while they split the A tile; reduce over splits with the split-K reduction.
 
 }  // namespace tma
 }  // namespace rlctr
