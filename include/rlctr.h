@@ -156,6 +156,17 @@ int rlctr_pairdots_bwd(const float* rows, int64_t ld_rows, const float* gout, in
                        int64_t ld_grows, int64_t batch, int32_t fields, int32_t dim, int32_t ip_first,
                        rlctr_stream_t stream);
 
+/* DCN cross network (p_model.py:408-419,423-428) over gathered rows x0 [batch, dim] (pitch ldx):
+ *   x_{l+1} = x0 * <x_l, w_l> + b_l + x_l, l = 0..layers-1;  out = x_layers;  s_saved[batch, layers] = <x_l, w_l> (for bwd)
+ *   w, b: [layers, dim] (cross_net_w.{l}.weight, cross_net_b.{l} stacked).  dim <= 256, layers <= 6.
+ * bwd: gx0 = dL/dx0 (all paths), dw / db [layers, dim]; ws: rlctr_cross_ws_bytes bytes (per-block partials, fixed-order sum). */
+size_t rlctr_cross_ws_bytes(int64_t batch, int32_t dim, int32_t layers);
+int rlctr_cross_fwd(const float* x0, int64_t ldx, const float* w, const float* b, int32_t layers, float* out, int64_t ld_out,
+                    float* s_saved, int64_t batch, int32_t dim, rlctr_stream_t stream);
+int rlctr_cross_bwd(const float* x0, int64_t ldx, const float* w, const float* b, const float* s_saved, int32_t layers,
+                    const float* gout, int64_t ld_g, float* gx0, int64_t ld_gx, float* dw, float* db, int64_t batch,
+                    int32_t dim, void* ws, size_t ws_bytes, rlctr_stream_t stream);
+
 /* Plain bit-exact row gather out[k, :] = table[ids[k], :] (nn.Embedding.forward); the owner
  * side of the sharded lookup.  out has row_stride floats per row. */
 int rlctr_gather_rows(const int64_t* ids, int64_t n, const rlctr_table* table, float* out,

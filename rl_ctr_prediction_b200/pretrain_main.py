@@ -170,8 +170,36 @@ def fused_train_step(model, optimizer, features, labels):
     return loss.reshape(())
 
 
-def train(model, optimizer, data_loader, loss, device, fused=False):
+def train_graphed(model, optimizer, data_loader, loss, device):
+    """The same epoch as ``train`` with the step replayed as a CUDA graph (:mod:`.graphs`): the host->device copy of batch
+    i+1 overlaps step i, and every step's loss is read from pinned memory one step later instead of stalling the GPU with
+    ``.item()``.  Same numbers as ``train`` (a batch of another size -- the last one -- takes the eager step)."""
+    from . import graphs
+    model.train()
+    step = graphs.GraphedTrainStep([(model, optimizer)], loss)
+    it = iter(data_loader)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return float("nan")
+    handle = step.prefetch(cur[0].long(), cur[1])
+    total_loss, intervals, pending = 0.0, 0, None
+    while handle is not None:
+        nxt = next(it, None)
+        nxt_handle = step.prefetch(nxt[0].long(), nxt[1]) if nxt is not None else None
+        fetch = step.losses_to_host(step(handle))
+        if pending is not None:
+            total_loss += pending()[0]
+        pending, handle = fetch, nxt_handle
+        intervals += 1
+    total_loss += pending()[0]
+    return total_loss / intervals
+
+
+def train(model, optimizer, data_loader, loss, device, fused=False, graphed=False):
     """pretrain_main.py:91-107: returns the mean of the per-batch losses."""
+    if graphed:
+        return train_graphed(model, optimizer, data_loader, loss, device)
     model.train()
     total_loss, intervals = 0.0, 0
     for features, labels in data_loader:
@@ -231,7 +259,7 @@ def eva_stopping(valid_aucs, valid_losses, type):
 
 
 def main(data_path, dataset_name, campaign_id, valid_day, test_day, latent_dims, model_name, epoch, learning_rate,
-         weight_decay, early_stop_type, batch_size, device, save_param_dir, optimizer_mode="lazy", fused=False):
+         weight_decay, early_stop_type, batch_size, device, save_param_dir, optimizer_mode="lazy", fused=False, graphed=False):
     """pretrain_main.py:142-236.  Rolling window of 5 checkpoints, early stop, best -> ``<name>best.pth``,
     prediction CSVs -- with the reference's state_dict keys, so checkpoints are interchangeable."""
     os.makedirs(save_param_dir + campaign_id, exist_ok=True)
@@ -250,7 +278,7 @@ def main(data_path, dataset_name, campaign_id, valid_day, test_day, latent_dims,
         learning_rate += 1e-4                                               # :180
         optimizer = _optim.Adam(params=model.parameters(), lr=learning_rate, weight_decay=weight_decay,
                                 mode=optimizer_mode)                       # :181, fresh state per epoch
-        train_average_loss = train(model, optimizer, loaders[0], loss, device, fused=fused)
+        train_average_loss = train(model, optimizer, loaders[0], loss, device, fused=fused, graphed=graphed)
         torch.save(model.state_dict(), ckpt(epoch_i % 5))
         auc, valid_loss = test(model, loaders[1], loss, device)
         valid_aucs.append(auc)
@@ -304,8 +332,9 @@ if __name__ == "__main__":
     ap.add_argument("--save_param_dir", default="../models/model_params/")
     ap.add_argument("--optimizer_mode", default="lazy", choices=["lazy", "dense", "sparse"])
     ap.add_argument("--fused", action="store_true")
+    ap.add_argument("--graphed", action="store_true", help="replay the training step as a CUDA graph (graphs.GraphedTrainStep)")
     a = ap.parse_args()
     setup_seed(1)
     main(a.data_path, a.dataset_name, a.campaign_id, a.valid_day, a.test_day, a.latent_dims, a.model_name, a.epoch,
          a.learning_rate, a.weight_decay, a.early_stop_type, a.batch_size, a.device, a.save_param_dir,
-         a.optimizer_mode, a.fused)
+         a.optimizer_mode, a.fused, a.graphed)

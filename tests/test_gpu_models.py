@@ -149,11 +149,11 @@ def test_loop_api_matches_reference_train_and_test(golden):
     """pretrain_main.train / test over a 3-batch 'epoch' == the reference's own train()/test() driving
     the reference FM (golden 'loop/*'), including sklearn AUC."""
     from rl_ctr_prediction_b200 import optim, pretrain_main as PM
-    for fused in (False, True):
+    for fused, graphed in ((False, False), (True, False), (False, True)):
         m = load(build("FM", 255), state_from_golden(golden, "train/FM/init")).to(DEV)
         opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
         loader = [(torch.as_tensor(golden["train/x"][s]), torch.as_tensor(golden["train/y"][s])) for s in range(3)]
-        avg = PM.train(m, opt, loader, torch.nn.BCELoss(), torch.device(DEV), fused=fused)
+        avg = PM.train(m, opt, loader, torch.nn.BCELoss(), torch.device(DEV), fused=fused, graphed=graphed)
         auc, tloss = PM.test(m, loader, torch.nn.BCELoss(), torch.device(DEV))
         close(avg, golden["loop/FM/train_avg_loss"])
         close(tloss, golden["loop/FM/test_loss"])
