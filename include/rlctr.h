@@ -167,6 +167,30 @@ int rlctr_cross_bwd(const float* x0, int64_t ldx, const float* w, const float* b
                     const float* gout, int64_t ld_g, float* gx0, int64_t ld_gx, float* dw, float* db, int64_t batch,
                     int32_t dim, void* ws, size_t ws_bytes, rlctr_stream_t stream);
 
+/* OuterPNN product term (p_model.py:236,245-251; the reference's kernel matrix is a constant torch.ones((D, D))):
+ *   out[b, :] = [ rows[b, :fields*dim] | cross[dim] ],  cross[d] = sum_{i<dim} (S_d * 1) * S_d,  S = sum_f v_f
+ * bwd: grows[b, f*dim+d] = gout[b, f*dim+d] + gout[b, fields*dim+d] * 2 * dim * S_d. */
+int rlctr_fieldsq_fwd(const float* rows, int64_t ld_rows, float* out, int64_t ld_out, int64_t batch, int32_t fields,
+                      int32_t dim, rlctr_stream_t stream);
+int rlctr_fieldsq_bwd(const float* rows, int64_t ld_rows, const float* gout, int64_t ld_g, float* grows, int64_t ld_grows,
+                      int64_t batch, int32_t fields, int32_t dim, rlctr_stream_t stream);
+
+/* AFM attention tail (p_model.py:472-481) over gathered rows [batch, fields*dim] (pitch ld_rows):
+ *   ip_p = v_i * v_j (i < j);  a_p = relu(W_a ip_p + b_a);  s_p = <w_s, a_p> + b_s;  score = softmax_p(s);
+ *   attn = sum_p (score_p * m1_p) ip_p;  out[b] = <fc_w, attn * m2> + fc_b
+ * params / dparams: packed [W_a (dim x dim, row = output) | b_a | w_s | b_s | fc_w | fc_b], dim*dim + 3*dim + 2 floats
+ * (attention_net.weight/.bias, attention_softmax.weight/.bias, fc.weight/.bias).  m1 / m2: the two F.dropout masks of
+ * the reference (always on, :477,479): 0 or 1/(1-p), drawn as hash(rng_state[0], rng_state[1] + b*(P+dim) + col) like
+ * the tower's mask (rlctr_rng_advance by batch*(P+dim) after the forward; the backward takes the SAME rng_state values),
+ * or read from `masks` [batch, P+dim] when given (mask-as-input parity tests); dropout_p == 0: no dropout.
+ * dim in {4, 8, 10}; fields <= 23.  bwd: grows = d L / d rows (written, pitch ld_grows), ws: rlctr_afm_ws_bytes. */
+size_t rlctr_afm_ws_bytes(int64_t batch, int32_t dim);
+int rlctr_afm_fwd(const float* rows, int64_t ld_rows, const float* params, float* out, int64_t batch, int32_t fields,
+                  int32_t dim, float dropout_p, const uint64_t* rng_state, const float* masks, rlctr_stream_t stream);
+int rlctr_afm_bwd(const float* rows, int64_t ld_rows, const float* params, const float* gout, float* grows, int64_t ld_grows,
+                  float* dparams, int64_t batch, int32_t fields, int32_t dim, float dropout_p, const uint64_t* rng_state,
+                  const float* masks, void* ws, size_t ws_bytes, rlctr_stream_t stream);
+
 /* Plain bit-exact row gather out[k, :] = table[ids[k], :] (nn.Embedding.forward); the owner
  * side of the sharded lookup.  out has row_stride floats per row. */
 int rlctr_gather_rows(const int64_t* ids, int64_t n, const rlctr_table* table, float* out,

@@ -79,12 +79,17 @@ class PortCTR(nn.Module):
 
 
 class PortTail(nn.Module):
-    """WideAndDeep / FNN / InnerPNN of src/models/p_model.py:103-200,326-373: the same gather with another dense
-    tail.  Parameter creation order and state_dict keys are the reference's."""
+    """WideAndDeep / FNN / InnerPNN / OuterPNN / DCN / AFM of src/models/p_model.py:103-254,326-485: the same gather with
+    another dense tail.  Parameter creation order and state_dict keys are the reference's.
+
+    Two departures, both needed to run at all on a CPU and both stated in the tests: OuterPNN's constant ``kernel`` is
+    created on the module's device instead of ``.cuda()`` (p_model.py:236), and AFM's two always-on
+    ``F.dropout`` calls (:477,479) take ``dropout_p`` (0.2 like the reference; 0 for deterministic parity
+    runs) and optional explicit masks."""
 
     def __init__(self, kind: str, feature_nums: int, field_nums: int = 15, latent_dims: int = 10):
         super().__init__()
-        assert kind in ("WideAndDeep", "FNN", "InnerPNN")
+        assert kind in TAIL_KINDS
         self.kind, self.F, self.D = kind, field_nums, latent_dims
         if kind == "WideAndDeep":
             self.linear = nn.Embedding(feature_nums, 1)                    # p_model.py:115
@@ -94,14 +99,64 @@ class PortTail(nn.Module):
         elif kind == "FNN":
             self.feature_embedding = nn.Embedding(feature_nums, latent_dims)   # :336
             self.mlp = _tower(field_nums * latent_dims)
-        else:
+        elif kind == "InnerPNN":
             self.feature_embedding = nn.Embedding(feature_nums, latent_dims)   # :158
             self.mlp = _tower(field_nums * latent_dims + field_nums * (field_nums - 1) // 2)
             idx = torch.triu_indices(field_nums, field_nums, offset=1)         # :178-181 (i < j, row-major)
             self.row, self.col = idx[0].tolist(), idx[1].tolist()
+        elif kind == "OuterPNN":
+            self.feature_embedding = nn.Embedding(feature_nums, latent_dims)   # :214
+            self.mlp = _tower(latent_dims + field_nums * latent_dims)          # :217-232
+            self.kernel = torch.ones((latent_dims, latent_dims))               # :236 (not a parameter / buffer)
+        elif kind == "DCN":
+            fd = field_nums * latent_dims
+            self.feature_embedding = nn.Embedding(feature_nums, latent_dims)   # :387
+            mods, d = [], fd
+            for width in (300, 200):                                           # :396-400: ends in ReLU + Dropout
+                mods += [nn.Linear(d, width), nn.ReLU(), nn.Dropout(p=0.2)]
+                d = width
+            self.DN = nn.Sequential(*mods)
+            self.num_neural_layers = 5                                         # :394
+            self.cross_net_w = nn.ModuleList([nn.Linear(fd, 1, bias=False) for _ in range(5)])          # :409-411
+            self.cross_net_b = nn.ParameterList([nn.Parameter(torch.zeros((fd,))) for _ in range(5)])   # :415-417
+            self.linear = nn.Linear(200 + fd, 1)                               # :419
+        else:                                                                  # AFM :438-470
+            self.feature_embedding = nn.Embedding(feature_nums, latent_dims)
+            idx = torch.triu_indices(field_nums, field_nums, offset=1)
+            self.row, self.col = idx[0].tolist(), idx[1].tolist()
+            self.attention_net = nn.Linear(latent_dims, latent_dims)
+            self.attention_softmax = nn.Linear(latent_dims, 1)
+            self.fc = nn.Linear(latent_dims, 1)
+            self.linear = nn.Embedding(feature_nums, 1)
+            self.bias = nn.Parameter(torch.zeros((1,)))
+            self.dropout_p = 0.2
 
-    def forward(self, x):
+    def forward(self, x, masks=None):
         FD = self.F * self.D
+        if self.kind == "AFM":                                             # :472-485
+            e = self.feature_embedding(x)
+            ip = torch.mul(e[:, self.row], e[:, self.col])
+            sc = torch.relu(self.attention_net(ip))
+            sc = torch.softmax(self.attention_softmax(sc), dim=1)
+            P = len(self.row)
+            if masks is not None:                                          # explicit masks: [B, P + D] multipliers
+                sc = sc * masks[:, :P].unsqueeze(2)
+            else:
+                sc = torch.nn.functional.dropout(sc, p=self.dropout_p)
+            out = torch.sum(torch.mul(sc, ip), dim=1)
+            out = out * masks[:, P:] if masks is not None else torch.nn.functional.dropout(out, p=self.dropout_p)
+            return torch.sigmoid(self.bias + torch.sum(self.linear(x), dim=1) + self.fc(out))
+        if self.kind == "DCN":                                             # :421-435
+            e = self.feature_embedding(x).view(-1, FD)
+            x0, xl = e, e
+            for i in range(self.num_neural_layers):
+                xl = x0 * self.cross_net_w[i](xl) + self.cross_net_b[i] + xl
+            return torch.sigmoid(self.linear(torch.cat([xl, self.DN(e)], dim=1)))
+        if self.kind == "OuterPNN":                                        # :238-254
+            e = self.feature_embedding(x)
+            se = torch.sum(e, dim=1).unsqueeze(1)
+            cross = torch.sum(torch.mul(torch.mul(se, self.kernel), se), dim=1)
+            return torch.sigmoid(self.mlp(torch.cat([e.view(-1, FD), cross], dim=1)))
         if self.kind == "WideAndDeep":                                     # :135-144
             e = self.embedding(x)
             return torch.sigmoid(self.bias + torch.sum(self.linear(x), dim=1) + self.mlp(e.view(-1, FD)))
@@ -112,8 +167,11 @@ class PortTail(nn.Module):
         return torch.sigmoid(self.mlp(torch.cat([e.view(-1, FD), ip], dim=1)))   # :194-198
 
 
+TAIL_KINDS = ("WideAndDeep", "FNN", "InnerPNN", "OuterPNN", "DCN", "AFM")
+
+
 def make_port(kind: str, feature_nums: int, field_nums: int = 15, latent_dims: int = 10) -> nn.Module:
-    if kind in ("WideAndDeep", "FNN", "InnerPNN"):
+    if kind in TAIL_KINDS:
         return PortTail(kind, feature_nums, field_nums, latent_dims)
     return PortCTR(kind, feature_nums, field_nums, latent_dims)
 

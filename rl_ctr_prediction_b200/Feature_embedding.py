@@ -56,7 +56,7 @@ class Feature_Embedding(nn.Module):
         """Feature_embedding.py:45-49: copy the pre-trained FM's ``feature_embedding.weight``."""
         src = pretrain_params["feature_embedding.weight"]
         with torch.no_grad():
-            self.table.data[:, :self._geom.dim].copy_(torch.as_tensor(np.array(src.cpu())))
+            self.table.data[:, :self._geom.dim].copy_(torch.as_tensor(src).detach())
 
     @torch.no_grad()
     def forward(self, x, out=None):

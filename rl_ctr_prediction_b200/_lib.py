@@ -63,6 +63,11 @@ SIGNATURES = {
     "rlctr_cross_ws_bytes": (_SZ, [_I64, _I32, _I32]),
     "rlctr_cross_fwd": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _P]),
     "rlctr_cross_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _I32, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _P, _SZ, _P]),
+    "rlctr_fieldsq_fwd": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
+    "rlctr_fieldsq_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _P]),
+    "rlctr_afm_ws_bytes": (_SZ, [_I64, _I32]),
+    "rlctr_afm_fwd": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _I32, C.c_float, _P, _P, _P]),
+    "rlctr_afm_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _I64, _I32, _I32, C.c_float, _P, _P, _P, _SZ, _P]),
     "rlctr_gather_rows": (C.c_int, [_P, _I64, _TP, _P, _P]),
     "rlctr_ffm_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "rlctr_featemb_fwd": (C.c_int, [_P, _TP, _P, _I64, _I64, _I32, _P]),

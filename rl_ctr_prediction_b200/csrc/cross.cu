@@ -204,3 +204,96 @@ extern "C" int rlctr_cross_bwd(const float* x0, int64_t ldx, const float* w, con
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// OuterPNN product term (p_model.py:236,245-251).  The reference's kernel matrix is a constant torch.ones((D, D)) (not a
+// parameter, not in the state_dict), so  sum_i (S_j * K[i,j]) * S_j  collapses to D copies of S_j^2, S = sum_f v_f:
+//     out[b, :] = [ E (F*D) | cross (D) ],   cross[d] = sum_{i<D} (S_d * 1) * S_d   (summed in i order like torch.sum(dim=1))
+//     d E[f, d] = g_E[f, d] + g_cross[d] * 2 * D * S_d
+// Warp per sample; the row block is staged in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+namespace rlctr {
+
+__global__ void __launch_bounds__(128)
+fieldsq_fwd_kernel(const float* __restrict__ rows, int64_t ld_rows, float* __restrict__ out, int64_t ld_out, int64_t batch,
+                   int fields, int dim) {
+    extern __shared__ float smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int fd = fields * dim;
+    float* stage = smem + wib * fd;
+    for (int64_t b = (int64_t)blockIdx.x * nw + wib; b < batch; b += (int64_t)gridDim.x * nw) {
+        const float* r = rows + b * ld_rows;
+        float* o = out + b * ld_out;
+        for (int i = lane; i < fd; i += 32) { const float v = __ldg(r + i); stage[i] = v; o[i] = v; }
+        __syncwarp();
+        for (int d = lane; d < dim; d += 32) {
+            float s = 0.f;
+            for (int f = 0; f < fields; ++f) s += stage[f * dim + d];
+            const float sq = s * s;
+            float acc = 0.f;
+            for (int i = 0; i < dim; ++i) acc += sq;
+            o[fd + d] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+fieldsq_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __restrict__ gout, int64_t ld_g,
+                   float* __restrict__ grows, int64_t ld_grows, int64_t batch, int fields, int dim) {
+    extern __shared__ float smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int fd = fields * dim;
+    float* stage = smem + wib * (fd + dim);
+    float* coef = stage + fd;                          // g_cross[d] * 2 * D * S_d
+    for (int64_t b = (int64_t)blockIdx.x * nw + wib; b < batch; b += (int64_t)gridDim.x * nw) {
+        const float* r = rows + b * ld_rows;
+        const float* g = gout + b * ld_g;
+        for (int i = lane; i < fd; i += 32) stage[i] = __ldg(r + i);
+        __syncwarp();
+        for (int d = lane; d < dim; d += 32) {
+            float s = 0.f;
+            for (int f = 0; f < fields; ++f) s += stage[f * dim + d];
+            coef[d] = __ldg(g + fd + d) * (2.f * (float)dim) * s;
+        }
+        __syncwarp();
+        for (int t = lane; t < fd; t += 32) grows[b * ld_grows + t] = __ldg(g + t) + coef[t % dim];
+        __syncwarp();
+    }
+}
+
+}  // namespace rlctr
+
+extern "C" int rlctr_fieldsq_fwd(const float* rows, int64_t ld_rows, float* out, int64_t ld_out, int64_t batch, int32_t fields,
+                                 int32_t dim, rlctr_stream_t stream) {
+    if (!rows || !out || batch < 0 || fields <= 0 || dim <= 0) return RLCTR_EINVAL;
+    const int fd = fields * dim;
+    if (ld_rows < fd || ld_out < fd + dim) return RLCTR_EINVAL;
+    if (batch == 0) return RLCTR_OK;
+    const int nw = 4;
+    const size_t smem = (size_t)nw * fd * sizeof(float);
+    if (smem > 48 * 1024) return RLCTR_EUNSUPPORTED;
+    int64_t want = (batch + nw - 1) / nw;
+    const int64_t cap = (int64_t)RLCTR_SMS * 16;
+    fieldsq_fwd_kernel<<<(int)(want < cap ? want : cap), nw * 32, smem, (cudaStream_t)stream>>>(rows, ld_rows, out, ld_out, batch,
+                                                                                               fields, dim);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_fieldsq_bwd(const float* rows, int64_t ld_rows, const float* gout, int64_t ld_g, float* grows,
+                                 int64_t ld_grows, int64_t batch, int32_t fields, int32_t dim, rlctr_stream_t stream) {
+    if (!rows || !gout || !grows || batch < 0 || fields <= 0 || dim <= 0) return RLCTR_EINVAL;
+    const int fd = fields * dim;
+    if (ld_rows < fd || ld_g < fd + dim || ld_grows < fd) return RLCTR_EINVAL;
+    if (batch == 0) return RLCTR_OK;
+    const int nw = 4;
+    const size_t smem = (size_t)nw * (fd + dim) * sizeof(float);
+    if (smem > 48 * 1024) return RLCTR_EUNSUPPORTED;
+    int64_t want = (batch + nw - 1) / nw;
+    const int64_t cap = (int64_t)RLCTR_SMS * 16;
+    fieldsq_bwd_kernel<<<(int)(want < cap ? want : cap), nw * 32, smem, (cudaStream_t)stream>>>(rows, ld_rows, gout, ld_g, grows,
+                                                                                               ld_grows, batch, fields, dim);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}

@@ -460,3 +460,212 @@ class InnerPNN(FNN):
 
     def _tower_input(self, rows):
         return _PairDots.apply(rows, self.field_nums, self.latent_dims)
+
+
+class _FieldSq(torch.autograd.Function):
+    """rows [B, F*D] -> [E | D * (sum_f v_f)^2] (OuterPNN tower input, p_model.py:245-251): rlctr_fieldsq_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, rows, fields, dim):
+        lib = _lib.load()
+        rows, ld_rows = _mlp._rows_view(rows)
+        B, fd = rows.shape
+        pitch = (fd + dim + 3) // 4 * 4
+        out = torch.empty(B, pitch, dtype=torch.float32, device=rows.device)
+        _lib.call("rlctr_fieldsq_fwd", lib.rlctr_fieldsq_fwd, rows.data_ptr(), ld_rows, _lib.ptr(out), pitch, B, fields, dim,
+                  _lib.stream(), meta={"B": B})
+        ctx.save_for_backward(rows)
+        ctx.geom = (fields, dim, ld_rows)
+        return out[:, :fd + dim] if pitch != fd + dim else out
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (rows,) = ctx.saved_tensors
+        fields, dim, ld_rows = ctx.geom
+        B, fd = rows.shape
+        gout = gout.contiguous()
+        grows = torch.empty(B, fd, dtype=torch.float32, device=rows.device)
+        _lib.call("rlctr_fieldsq_bwd", lib.rlctr_fieldsq_bwd, rows.data_ptr(), ld_rows, _lib.ptr(gout), gout.shape[1],
+                  _lib.ptr(grows), fd, B, fields, dim, _lib.stream(), meta={"B": B})
+        return grows, None, None
+
+
+class OuterPNN(FNN):
+    """p_model.py:202-254  sigma(MLP([concat_f v_f | sum_i (S * K[i]) * S])), S = sum_f v_f.  The reference's ``kernel``
+    is a constant ``torch.ones((D, D)).cuda()`` (:236; not a parameter, not in the state_dict -- SURVEY N8), so the product
+    term is D * S^2 per dimension; it is kept as a plain attribute for code that inspects it."""
+
+    def __init__(self, feature_nums, field_nums, latent_dims, output_dim=1, device=None):
+        super().__init__(feature_nums, field_nums, latent_dims, device)
+        self.kernel = torch.ones((self.latent_dims, self.latent_dims), device=device)
+
+    def _make_tower(self, device):
+        return _tower(self.latent_dims + self.field_nums * self.latent_dims, device)
+
+    def _tower_input(self, rows):
+        return _FieldSq.apply(rows, self.field_nums, self.latent_dims)
+
+
+class _CrossNet(torch.autograd.Function):
+    """x0 [B, F*D], W [L, F*D], Bv [L, F*D] -> x_L (DCN cross network, p_model.py:423-428): rlctr_cross_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, rows, W, Bv):
+        lib = _lib.load()
+        rows, ldx = _mlp._rows_view(rows)
+        B, fd = rows.shape
+        L = W.shape[0]
+        W, Bv = W.detach().contiguous(), Bv.detach().contiguous()
+        out = torch.empty(B, fd, dtype=torch.float32, device=rows.device)
+        s = torch.empty(B, L, dtype=torch.float32, device=rows.device)
+        _lib.call("rlctr_cross_fwd", lib.rlctr_cross_fwd, rows.data_ptr(), ldx, _lib.ptr(W), _lib.ptr(Bv), L, _lib.ptr(out), fd,
+                  _lib.ptr(s), B, fd, _lib.stream(), meta={"B": B, "L": L, "fd": fd})
+        ctx.save_for_backward(rows, W, Bv, s)
+        ctx.ldx = ldx
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        rows, W, Bv, s = ctx.saved_tensors
+        B, fd = rows.shape
+        L = W.shape[0]
+        gout = gout.contiguous()
+        dev = rows.device
+        gx0 = torch.empty(B, fd, dtype=torch.float32, device=dev)
+        dw, db = torch.empty_like(W), torch.empty_like(Bv)
+        ws_bytes = lib.rlctr_cross_ws_bytes(B, fd, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.call("rlctr_cross_bwd", lib.rlctr_cross_bwd, rows.data_ptr(), ctx.ldx, _lib.ptr(W), _lib.ptr(Bv), _lib.ptr(s), L,
+                  _lib.ptr(gout), gout.shape[1], _lib.ptr(gx0), fd, _lib.ptr(dw), _lib.ptr(db), B, fd, _lib.ptr(ws), ws_bytes,
+                  _lib.stream(), meta={"B": B, "L": L, "fd": fd})
+        return gx0, dw, db
+
+
+class DCN(_TableModel):
+    """p_model.py:376-435  sigma(Linear([cross_L(x0) | DN(x0)])), x0 = concat_f v_f: 5 cross layers
+    ``x_{l+1} = x0 <x_l, w_l> + b_l + x_l`` (one kernel, forward and backward) beside the [300, 200] deep net (tcgen05 tower).
+    state_dict keys are the reference's: ``feature_embedding.weight, DN.{0,3}.*, cross_net_w.{l}.weight (1, F*D),
+    cross_net_b.{l} (F*D,), linear.*``."""
+    _kind = "fm"
+    _fm_term = False
+
+    def __init__(self, feature_nums, field_nums, latent_dims, output_dim=1, device=None):
+        super().__init__()
+        assert output_dim == 1
+        self.feature_nums, self.field_nums, self.latent_dims = feature_nums, int(field_nums), int(latent_dims)
+        g = Geometry.fm(feature_nums, self.latent_dims, with_linear=False)
+        self._init_table(g, [(g.emb_col, g.dim)], device)                               # :387
+        fd = self.field_nums * self.latent_dims
+        self.num_neural_layers = 5                                                      # :394
+        mods, d = [], fd
+        for width in (300, 200):                                                        # :396-400 (ends in ReLU, Dropout)
+            mods += [_mlp.Linear(d, width, device=device), nn.ReLU(), nn.Dropout(p=0.2)]
+            d = width
+        self.DN = _mlp.Tower(*mods)
+        self.cross_net_w = nn.ModuleList([nn.Linear(fd, output_dim, bias=False, device=device)
+                                          for _ in range(self.num_neural_layers)])     # :409-411
+        self.cross_net_b = nn.ParameterList([nn.Parameter(torch.zeros((fd,), device=device))
+                                             for _ in range(self.num_neural_layers)])  # :415-417
+        self.linear = _mlp.Linear(200 + fd, output_dim, device=device)                  # :419
+
+    def _ref_items(self):
+        g = self._geom
+        return [("feature_embedding.weight", g.emb_col, g.dim)]
+
+    def forward(self, x):
+        _, rows = self._run(x, True, False)
+        W = torch.cat([m.weight for m in self.cross_net_w], dim=0)
+        Bv = torch.stack(list(self.cross_net_b), dim=0)
+        cn_x = _CrossNet.apply(rows, W, Bv)
+        dn_x = self.DN(rows)
+        return torch.sigmoid(self.linear(torch.cat([cn_x, dn_x], dim=1)))              # :430-435
+
+
+class _AFMAttention(torch.autograd.Function):
+    """rows [B, F*D], packed attention parameters -> fc(attention-pooled pair products) [B, 1]: rlctr_afm_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, rows, packed, fields, dim, drop_p, rng, masks):
+        lib = _lib.load()
+        rows, ld = _mlp._rows_view(rows)
+        B = rows.shape[0]
+        packed = packed.detach().contiguous()
+        out = torch.empty(B, 1, dtype=torch.float32, device=rows.device)
+        use_rng = drop_p > 0.0 and masks is None
+        snap = rng.clone() if use_rng else None                 # the backward regenerates the masks from this snapshot
+        _lib.call("rlctr_afm_fwd", lib.rlctr_afm_fwd, rows.data_ptr(), ld, _lib.ptr(packed), _lib.ptr(out), B, fields, dim,
+                  float(drop_p), _lib.ptr(snap), _lib.ptr(masks), _lib.stream(), meta={"B": B})
+        if use_rng:
+            npair = fields * (fields - 1) // 2
+            _lib.check(lib.rlctr_rng_advance(_lib.ptr(rng), B * (npair + dim), _lib.stream()), "rlctr_rng_advance")
+        ctx.save_for_backward(rows, packed, snap, masks)
+        ctx.geom = (ld, fields, dim, float(drop_p))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        rows, packed, snap, masks = ctx.saved_tensors
+        ld, fields, dim, drop_p = ctx.geom
+        B, fd = rows.shape
+        dev = rows.device
+        gout = gout.reshape(B).contiguous()
+        grows = torch.empty(B, fd, dtype=torch.float32, device=dev)
+        dpacked = torch.empty_like(packed)
+        ws_bytes = lib.rlctr_afm_ws_bytes(B, dim)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.call("rlctr_afm_bwd", lib.rlctr_afm_bwd, rows.data_ptr(), ld, _lib.ptr(packed), _lib.ptr(gout), _lib.ptr(grows), fd,
+                  _lib.ptr(dpacked), B, fields, dim, drop_p, _lib.ptr(snap), _lib.ptr(masks), _lib.ptr(ws), ws_bytes,
+                  _lib.stream(), meta={"B": B})
+        return grows, dpacked, None, None, None, None, None
+
+
+class AFM(_TableModel):
+    """p_model.py:438-485  sigma(bias + sum_f w[x_f] + fc(sum_p softmax_p(attention(v_i*v_j)) v_i*v_j)).
+
+    The two ``F.dropout(p=0.2)`` calls of the reference (:477,479) use the default ``training=True``, i.e. they are
+    stochastic in ``eval()`` too: ``dropout_p`` (0.2) is applied in both modes here as well; set it to 0 for
+    a deterministic model.  Masks come from the counter hash of :mod:`.mlp` (own stream; the reference's CPU Philox
+    stream is not reproducible on a GPU) or from ``forward(x, masks=[B, P+D])`` in the mask-as-input parity tests."""
+    _kind = "fm"
+    _fm_term = False
+
+    def __init__(self, feature_nums, field_nums, latent_dims, output_dim=1, device=None):
+        super().__init__()
+        assert output_dim == 1
+        self.feature_nums, self.field_nums, self.latent_dims = feature_nums, int(field_nums), int(latent_dims)
+        D = self.latent_dims
+        g = Geometry.fm(feature_nums, D)
+        self._init_table(g, [(g.emb_col, g.dim)], device)                               # feature_embedding first (:450)
+        self.attention_net = nn.Linear(D, D, device=device)                             # :459
+        self.attention_softmax = nn.Linear(D, 1, device=device)                         # :462
+        self.fc = nn.Linear(D, output_dim, device=device)                               # :465
+        with torch.no_grad():                                                           # linear drawn after them (:468)
+            dev = self.table.device
+            lin = torch.empty(feature_nums, 1, device=dev).normal_() if dev.type == "cuda" else torch.empty(feature_nums, 1).normal_()
+            self.table.data[:, g.lin_col:g.lin_col + 1].copy_(lin)
+        self.bias = nn.Parameter(torch.zeros((output_dim,), device=device))
+        self.dropout_p = 0.2
+
+    def _ref_items(self):
+        g = self._geom
+        return [("feature_embedding.weight", g.emb_col, g.dim), ("linear.weight", g.lin_col, 1)]
+
+    def _rng_state(self, device):
+        st = getattr(self, "_rlctr_rng", None)
+        if st is None or st.device != device:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            st = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+            self._rlctr_rng = st
+        return st
+
+    def forward(self, x, masks=None):
+        z, rows = self._run(x, True, False)
+        packed = torch.cat([self.attention_net.weight.reshape(-1), self.attention_net.bias,
+                            self.attention_softmax.weight.reshape(-1), self.attention_softmax.bias,
+                            self.fc.weight.reshape(-1), self.fc.bias])
+        p = float(self.dropout_p)
+        rng = self._rng_state(rows.device) if (p > 0.0 and masks is None) else None
+        y = _AFMAttention.apply(rows, packed, self.field_nums, self.latent_dims, p, rng, masks)
+        return torch.sigmoid(z + y)

@@ -50,6 +50,9 @@ _MODELS = {
     "W&D": lambda n, f, d: Model.WideAndDeep(n, f, d),
     "FNN": lambda n, f, d: Model.FNN(n, f, d),
     "IPNN": lambda n, f, d: Model.InnerPNN(n, f, d),
+    "OPNN": lambda n, f, d: Model.OuterPNN(n, f, d),
+    "DCN": lambda n, f, d: Model.DCN(n, f, d),
+    "AFM": lambda n, f, d: Model.AFM(n, f, d),
 }
 
 

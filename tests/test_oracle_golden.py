@@ -164,12 +164,15 @@ def test_training_trajectory_torch_port(golden, name):
         close(m.state_dict()[k].numpy(), v, rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("name", ["WideAndDeep", "FNN", "InnerPNN"])
+@pytest.mark.parametrize("name", ["WideAndDeep", "FNN", "InnerPNN", "OuterPNN", "DCN", "AFM"])
 def test_training_trajectory_torch_port_tails(golden, golden_tails, name):
-    """The restated W&D / FNN / IPNN reproduce the real reference modules' trajectories."""
+    """The restated W&D / FNN / IPNN / OPNN / DCN / AFM reproduce the real reference modules' trajectories
+    (AFM with its always-on dropout switched off on both sides, see tests/golden/make_golden_tails.py)."""
     init = state_from_golden(golden_tails, f"train/{name}/init")
     N = [v for k, v in init.items() if k.endswith("embedding.weight")][0].shape[0]
     m = TP.make_port(name, N, F, D)
+    if name == "AFM":
+        m.dropout_p = 0.0
     m.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})
     m.eval()
     opt = TP.make_adam(m)
@@ -185,6 +188,21 @@ def test_training_trajectory_torch_port_tails(golden, golden_tails, name):
     for k, v in fresh.state_dict().items():
         scale = 0.1 if ("embedding" in k or k == "linear.weight") else 1.0
         close(v.numpy() * scale, init[k], rtol=1e-6, atol=1e-8)
+
+
+def test_afm_port_with_explicit_dropout_masks(golden, golden_tails):
+    """AFM's dropout arithmetic (p_model.py:477,479) with the masks as an input: forward, loss and every gradient."""
+    init = state_from_golden(golden_tails, "afm_mask/init")
+    m = TP.make_port("AFM", init["linear.weight"].shape[0], F, D)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})
+    x, y = torch.from_numpy(golden["train/x"][0]), torch.from_numpy(golden["train/y"][0]).view(-1, 1)
+    p = m(x, masks=torch.from_numpy(golden_tails["afm_mask/masks"]))
+    loss = torch.nn.BCELoss()(p, y.float())
+    loss.backward()
+    close(p.detach().numpy(), golden_tails["afm_mask/pctr"], rtol=1e-6)
+    close(loss.item(), golden_tails["afm_mask/loss"], rtol=1e-6)
+    for k, prm in m.named_parameters():
+        close(prm.grad.numpy(), golden_tails[f"afm_mask/grad/{k}"], rtol=1e-6, atol=1e-9)
 
 
 def test_port_init_matches_reference_seed(golden):
