@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--no-fork", action="store_true", help="capture the models of the step one after another (no parallel graph branches)")
     ap.add_argument("--profile-steps", type=int, default=10, help="steps of the eager per-kernel timing pass")
     return ap.parse_args()
 
@@ -336,7 +337,7 @@ def b200_arm(args):
     use_graph = not args.no_graph
     if use_graph:
         from rl_ctr_prediction_b200 import graphs
-        gstep = graphs.GraphedTrainStep(ms, lossf)
+        gstep = graphs.GraphedTrainStep(ms, lossf, fork=not args.no_fork)
         run_step = lambda x, y: gstep(x, y)
     else:
         gstep = None
@@ -471,7 +472,7 @@ def b200_arm(args):
             # the public call: GraphedTrainStep on pinned HOST batches; the copy of batch i+1 is issued before step i
             # (graphs.GraphedTrainStep.prefetch) and every step's three losses are read back to the host
             from rl_ctr_prediction_b200 import graphs
-            gs = graphs.GraphedTrainStep(ms, lossf)
+            gs = graphs.GraphedTrainStep(ms, lossf, fork=not args.no_fork)
             sink = []
 
             def run_graphed(lo, hi):
@@ -520,7 +521,7 @@ def b200_arm(args):
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world),
                 "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-                "cuda_graph": bool(use_graph)}
+                "cuda_graph": bool(use_graph), "graph_branches": bool(use_graph and not args.no_fork)}
         print(json.dumps(line))
     if world > 1:
         torch.cuda.synchronize()

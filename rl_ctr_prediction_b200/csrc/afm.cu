@@ -300,15 +300,6 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
     if (lane == 0) { mine[D * D + 2 * D] = sbs; mine[D * D + 3 * D + 1] = dfcb; }
 }
 
-__global__ void __launch_bounds__(256)
-afm_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int per, int parts) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int q = 0; q < parts; ++q) s += __ldg(part + (int64_t)q * per + i);
-        out[i] = s;
-    }
-}
-
 static int afm_blocks(int64_t batch, int per_sm) {
     int64_t want = (batch + AFM_WARPS - 1) / AFM_WARPS;
     const int64_t cap = (int64_t)RLCTR_SMS * per_sm;
@@ -339,7 +330,7 @@ static int afm_bwd_launch(const float* rows, int64_t ld_rows, const float* param
     constexpr int NP = D * D + 3 * D + 2;
     afm_bwd_kernel<D><<<blocks, AFM_WARPS * 32, smem, st>>>(rows, ld_rows, params, dr, gout, grows, ld_grows, part, batch, fields);
     RLCTR_LAUNCH_CHECK();
-    afm_reduce_kernel<<<1, 256, 0, st>>>(part, dparams, NP, blocks * AFM_WARPS);
+    colsum_parts_kernel<<<colsum_parts_grid(NP), 256, 0, st>>>(part, dparams, nullptr, NP, 0, NP, blocks * AFM_WARPS);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

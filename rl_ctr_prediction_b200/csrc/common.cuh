@@ -162,6 +162,28 @@ static inline bool shard_view_of(const rlctr_table* t, ShardView* sv) {
     return true;
 }
 
+// ---- fixed-order reduction of per-block partials: out[i] = sum_q part[q * stride + i], i < n_a + n_b ----------------------
+// One warp per column; lane l adds parts l, l + 32, ... (independent loads: the L2 latency is paid once, not once per part),
+// then a butterfly.  The order depends only on `parts`, so results are bit-identical from run to run.  Columns [0, n_a) go to
+// out_a, columns [n_a, n_a + n_b) to out_b (either may be null).
+static __global__ void __launch_bounds__(256)
+colsum_parts_kernel(const float* __restrict__ part, float* __restrict__ out_a, float* __restrict__ out_b, int n_a, int n_b,
+                    int64_t stride, int parts) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= n_a + n_b) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int q = lane; q < parts; q += 32) s += __ldg(part + (int64_t)q * stride + col);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(RLCTR_FULL, s, off);
+    if (lane == 0) {
+        if (col < n_a) { if (out_a) out_a[col] = s; }
+        else if (out_b) out_b[col - n_a] = s;
+    }
+}
+static inline int colsum_parts_grid(int n) { return (n + 7) / 8; }
+
 // ---- counter-based dropout mask (mlp.cu / mlp_tma.cu) ----------------------------------------------------------
 // keep(element) = hash(seed, counter + element index) >= p * 2^32.  (seed, counter) live in device memory so that a
 // CUDA-graph replay draws a fresh mask every step (rlctr_rng_advance moves the counter).  Two rounds of a 32-bit

@@ -7,7 +7,7 @@
 // with a butterfly sum and writes x_L once.  Only the L scalars s_l = <x_l, w_l> are saved: the backward recomputes the
 // x_l from them.  Parameter gradients (dw_l = sum_b ds_l * x_l, db_l = sum_b g_{l+1}) are accumulated per warp in
 // registers, combined per block through shared memory in a fixed order and written as per-block partials, which a
-// fixed-order pass reduces: bit-identical from run to run.
+// fixed-order pass (colsum_parts_kernel) reduces: bit-identical from run to run.
 #include "common.cuh"
 
 namespace rlctr {
@@ -134,15 +134,6 @@ cross_bwd_kernel(const float* __restrict__ x0, int64_t ldx, const float* __restr
     }
 }
 
-__global__ void __launch_bounds__(256)
-cross_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int per, int blocks) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int q = 0; q < blocks; ++q) s += __ldg(part + (int64_t)q * per + i);
-        out[i] = s;
-    }
-}
-
 static int cross_blocks(int64_t batch) {
     int64_t want = (batch + CROSS_WARPS - 1) / CROSS_WARPS;
     const int64_t cap = (int64_t)RLCTR_SMS * 4;
@@ -198,9 +189,9 @@ extern "C" int rlctr_cross_bwd(const float* x0, int64_t ldx, const float* w, con
     }
 #undef LAUNCH_CROSS
     RLCTR_LAUNCH_CHECK();
-    cross_reduce_kernel<<<(per + 255) / 256, 256, 0, st>>>(dw_part, dw, per, blocks);
+    colsum_parts_kernel<<<colsum_parts_grid(per), 256, 0, st>>>(dw_part, dw, nullptr, per, 0, per, blocks);
     RLCTR_LAUNCH_CHECK();
-    cross_reduce_kernel<<<(per + 255) / 256, 256, 0, st>>>(db_part, db, per, blocks);
+    colsum_parts_kernel<<<colsum_parts_grid(per), 256, 0, st>>>(db_part, db, nullptr, per, 0, per, blocks);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

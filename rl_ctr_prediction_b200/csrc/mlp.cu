@@ -480,6 +480,55 @@ outer_rows_kernel(const float* __restrict__ gy, const float* __restrict__ w, flo
     }
 }
 
+
+// ---- backward of a single-output layer in ONE pass over x: dx[r, :] = gy[r] * w (masked by the layer below), dw = sum_r gy[r] x[r, :],
+// db = sum_r gy[r].  Warp per row, lane owns columns lane + 32c; block b owns rows [b*rpb, (b+1)*rpb); per-block partials
+// [dw (K) | db] summed over the 8 warps in a fixed order; splitk_reduce_kernel adds the blocks.
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+gemv_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gy, const float* __restrict__ w,
+                float* __restrict__ dx, float* __restrict__ part, int64_t rows, int K, int rows_per_block, int dx_mask,
+                float dx_scale) {
+    __shared__ float red[8][CMAX * 32 + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float wk[CMAX], acc[CMAX], gsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const int k = lane + 32 * c;
+        wk[c] = k < K ? __ldg(w + k) : 0.f;
+        acc[c] = 0.f;
+    }
+    for (int64_t r = r0 + wib; r < r1; r += 8) {
+        const float g = __ldg(gy + r);
+        gsum += g;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            const int k = lane + 32 * c;
+            if (k < K) {
+                const float xv = __ldg(x + r * ldx + k);
+                acc[c] = fmaf(g, xv, acc[c]);
+                if (dx) {
+                    float v = g * wk[c];
+                    if (dx_mask) v = xv > 0.f ? v * dx_scale : 0.f;
+                    __stcs(dx + r * (int64_t)K + k, v);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) red[wib][lane + 32 * c] = acc[c];
+    if (lane == 0) red[wib][CMAX * 32] = gsum;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= K; i += blockDim.x) {
+        const int col = i < K ? i : CMAX * 32;
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][col];
+        part[(int64_t)blockIdx.x * (K + 1) + i] = t;
+    }
+}
 static int round16(int n) { return (n + 15) / 16 * 16; }
 
 struct GemmPlan {
@@ -543,7 +592,7 @@ static int launch_gemm(const float* A, int64_t sam, int64_t sak, const float* B,
     return RLCTR_OK;
 }
 
-constexpr int COLSUM_ROWS_PER_BLOCK = 512;
+constexpr int COLSUM_ROWS_PER_BLOCK = 128;
 
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 static inline int round4(int n) { return (n + 3) / 4 * 4; }
@@ -673,6 +722,22 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
     float* part = reinterpret_cast<float*>(ws);
     float* cpart = ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.wgrad) : nullptr;
     const int yb = (int)((batch + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK);
+    if (out_dim == 1 && in_dim <= 512) {
+        // one pass over x: dx, dw and db together (the ReLU/dropout mask of the layer below is read off the same x)
+        if (!ws || ws_bytes < l.total) return RLCTR_EWORKSPACE;
+        if (in_dim <= 256)
+            gemv_bwd_kernel<8><<<yb, 256, 0, st>>>(x, ldx, dy, w, dx, cpart, batch, in_dim, COLSUM_ROWS_PER_BLOCK, dx_mask ? 1 : 0,
+                                                   dx_scale);
+        else
+            gemv_bwd_kernel<16><<<yb, 256, 0, st>>>(x, ldx, dy, w, dx, cpart, batch, in_dim, COLSUM_ROWS_PER_BLOCK, dx_mask ? 1 : 0,
+                                                    dx_scale);
+        RLCTR_LAUNCH_CHECK();
+        if (dw || db) {
+            colsum_parts_kernel<<<colsum_parts_grid(in_dim + 1), 256, 0, st>>>(cpart, dw, db, in_dim, 1, in_dim + 1, yb);
+            RLCTR_LAUNCH_CHECK();
+        }
+        return RLCTR_OK;
+    }
     if (out_dim == 1) {
         if (dx) {
             const int64_t n = batch * in_dim;
@@ -685,7 +750,7 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
             dim3 grid((in_dim + 31) / 32, yb);
             colsum_partial_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, cpart, batch, in_dim, COLSUM_ROWS_PER_BLOCK);
             RLCTR_LAUNCH_CHECK();
-            splitk_reduce_kernel<<<(in_dim + 255) / 256, 256, 0, st>>>(cpart, dw, in_dim, yb);
+            colsum_parts_kernel<<<colsum_parts_grid(in_dim), 256, 0, st>>>(cpart, dw, nullptr, in_dim, 0, in_dim, yb);
             RLCTR_LAUNCH_CHECK();
         }
         if (db) {
@@ -693,7 +758,7 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
             dim3 grid(1, yb);
             colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, 1, nullptr, part2, batch, 1, COLSUM_ROWS_PER_BLOCK);
             RLCTR_LAUNCH_CHECK();
-            splitk_reduce_kernel<<<1, 256, 0, st>>>(part2, db, 1, yb);
+            colsum_parts_kernel<<<1, 256, 0, st>>>(part2, db, nullptr, 1, 0, 1, yb);
             RLCTR_LAUNCH_CHECK();
         }
         return RLCTR_OK;
@@ -755,7 +820,7 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         dim3 grid((out_dim + 31) / 32, yb);
         colsum_partial_kernel<<<grid, 256, 0, st>>>(dy, out_dim, nullptr, cpart, batch, out_dim, COLSUM_ROWS_PER_BLOCK);
         RLCTR_LAUNCH_CHECK();
-        splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(cpart, db, out_dim, yb);
+        colsum_parts_kernel<<<colsum_parts_grid(out_dim), 256, 0, st>>>(cpart, db, nullptr, out_dim, 0, out_dim, yb);
         RLCTR_LAUNCH_CHECK();
     }
     return RLCTR_OK;

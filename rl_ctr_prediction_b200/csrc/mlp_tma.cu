@@ -51,6 +51,11 @@ struct Args {
     int a_mn, b_mn;                       // 1: operand is contiguous along M (N) instead of K
     int b_presplit;                       // 1: B arrives as (hi, lo) through mapB / mapBlo
     int relu;
+    int a_tmem;                           // 1: the converters write (A_hi, A_lo) into TENSOR MEMORY and the MMAs read A from there
+    int acc_stride, a_col0;               // TMEM columns: accumulator stage s at s*acc_stride, A stage s at a_col0 + 64*s (hi | lo)
+    int l2_ahead;                         // stages of A the producer prefetches into L2 ahead of the pipeline (0: off)
+    int c_tma;                            // 1: the epilogue stages 32x32 blocks of C in shared memory and TMA-stores them (mapC)
+    long long* dbg;                       // RLCTR_GEMM_DBG: per-stage clock64 stamps of block 0 (scratch/gemm_trace.py), else null
     float* colsum_part;                   // wgrad only: [splits][M] partial column sums of the MN-major A operand (db), or null
     Epilogue epi;                         // fused dropout (forward) / ReLU-dropout mask of the layer below (dgrad)
 };
@@ -112,6 +117,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lanes = rows of A, one 32-bit column per k): no shared-memory read for A
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -150,6 +178,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// shared -> global store of one box (clipped at the tensor bounds), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// pull one box into L2 only (no shared-memory destination, no barrier): the later cp.async.bulk.tensor of the same box hits L2
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+                 "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -235,6 +276,48 @@ __device__ __forceinline__ void split_tile_colsum(uint32_t hi, uint32_t lo, int 
     }
 }
 
+// A-in-TMEM converters: thread t owns row m = t of the 128 x 32 raw A tile.  It reads its 32 k-values from the swizzled
+// shared-memory tile (K-major: eight 16-byte chunks, chunk c stored at c ^ (t & 7) -- a quarter-warp covers all 32 banks;
+// MN-major: one 4-byte element per k-row, a warp reads 128 contiguous bytes), splits them and writes hi to TMEM columns
+// [col, col + 32) and lo to [col + 32, col + 64) of its lane.  Returns the sum of the raw values (wgrad's bias gradient).
+__device__ __forceinline__ float split_row_to_tmem(uint32_t raw, bool a_mn, int t, uint32_t taddr) {
+    uint32_t hi[BK], lo[BK];
+    float sum = 0.f;
+    if (!a_mn) {
+        const uint32_t row = raw + (uint32_t)t * 128u;
+#pragma unroll
+        for (int c = 0; c < BK / 4; ++c) {
+            const float4 x = lds128(row + (uint32_t)((c ^ (t & 7)) << 4));
+            float4 h, l;
+            split4(x, h, l);
+            hi[4 * c] = __float_as_uint(h.x); hi[4 * c + 1] = __float_as_uint(h.y);
+            hi[4 * c + 2] = __float_as_uint(h.z); hi[4 * c + 3] = __float_as_uint(h.w);
+            lo[4 * c] = __float_as_uint(l.x); lo[4 * c + 1] = __float_as_uint(l.y);
+            lo[4 * c + 2] = __float_as_uint(l.z); lo[4 * c + 3] = __float_as_uint(l.w);
+        }
+    } else {
+        const int mm = t & 31;
+        const uint32_t blk = raw + (uint32_t)(t >> 5) * 4096u + (uint32_t)((mm & 7) << 2);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float x = lds32(blk + (uint32_t)k * 128u + (uint32_t)((((mm >> 3) ^ (k & 3))) << 5));
+            const float h = tf32_rn(x);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(x - h);
+            sum += x;
+        }
+    }
+    tmem_st32(taddr, hi);
+    tmem_st32(taddr + (uint32_t)BK, lo);
+    tmem_st_wait();
+    return sum;
+}
+
+#define DBG_STAMP(it, slot)                                                                         \
+    do {                                                                                           \
+        if (g.dbg && blockIdx.x == 0 && (it) < 256) g.dbg[(it) * 16 + (slot)] = clock64();          \
+    } while (0)
+
 struct TileWalk {                          // this CTA's (tile, k-block) sequence, identical in every role
     int tile, kb0, kb1, mt, nt, split;
 };
@@ -268,11 +351,9 @@ struct EpiCtx {
     int mvec;
     float mask_scale;
 };
-// W accumulator columns [n0, n0 + W) of this thread's row: bias, ReLU, vector stores
+// W accumulator columns [n0, n0 + W) of this thread's row: bias, ReLU, dropout, mask of the layer below -> v[]
 template <int W>
-__device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r, int n0) {
-    if (!e.row_ok || n0 >= e.N) return;
-    float v[W];
+__device__ __forceinline__ void epilogue_compute(const EpiCtx& e, const uint32_t* r, int n0, float (&v)[W]) {
 #pragma unroll
     for (int j = 0; j < W; ++j) v[j] = e.zero ? 0.f : __uint_as_float(r[j]);
     if (e.sbias) {
@@ -295,7 +376,7 @@ __device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r
         for (int j = 0; j < W; ++j)
             v[j] = dropout_keep(e.drop_seed, e.drop_base + (uint64_t)(n0 + j), e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
     }
-    if (e.mask_row) {
+    if (e.mask_row && e.row_ok) {
         const float* mr = e.mask_row + n0;
         if (n0 + W <= e.N && e.mvec == 4) {
 #pragma unroll
@@ -312,6 +393,13 @@ __device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r
                 if (n0 + j < e.N) v[j] = __ldg(mr + j) > 0.f ? v[j] * e.mask_scale : 0.f;
         }
     }
+}
+// ... and straight to global memory from the thread's registers (one row per thread: 16-byte pieces of 32 different lines)
+template <int W>
+__device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r, int n0) {
+    if (!e.row_ok || n0 >= e.N) return;
+    float v[W];
+    epilogue_compute<W>(e, r, n0, v);
     float* dst = e.crow + n0;
     if (n0 + W <= e.N && e.cvec == 4) {
 #pragma unroll
@@ -324,6 +412,16 @@ __device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r
         for (int j = 0; j < W; ++j)
             if (n0 + j < e.N) dst[j] = v[j];
     }
+}
+// ... or into this warp's 32 x 32 staging block (SWIZZLE_128B: row = lane, 16-byte chunk c at c ^ (lane & 7): a quarter-warp
+// covers all 32 banks), from where ONE TMA store writes 32 full 128-byte row segments (clipped at the tensor bounds)
+__device__ __forceinline__ void epilogue_stage(const EpiCtx& e, const uint32_t* r, int n0, uint32_t buf, int lane) {
+    float v[32];
+    epilogue_compute<32>(e, r, n0, v);
+    const uint32_t row = buf + (uint32_t)lane * 128u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        sts128(row + (uint32_t)((c ^ (lane & 7)) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
 }
 // one accumulator tile: the TMEM load of chunk c+1 is in flight while chunk c is written out
 template <int W>
@@ -343,9 +441,40 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, uint32_t taddr, i
     }
 }
 
+// the same walk with the 32-column chunks leaving through shared memory + TMA (two staging blocks per warp, toggled per
+// chunk; a block is reused once the bulk group that read it has finished reading); a 16-column tail goes out directly
+__device__ __forceinline__ void epilogue_chunk_tma(const EpiCtx& e, const uint32_t* r, int n0, const CUtensorMap* mapC,
+                                                   uint32_t stage0, int& buf, int m0, int lane) {
+    if (n0 >= e.N) return;                              // warp-uniform
+    if (lane == 0) bulk_wait_read<1>();                 // the group that last read this block (two chunks ago) is done
+    __syncwarp();
+    const uint32_t sb = stage0 + (uint32_t)buf * 4096u;
+    epilogue_stage(e, r, n0, sb, lane);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(mapC, sb, n0, m0); bulk_commit(); }
+    buf ^= 1;
+}
+__device__ __forceinline__ void epilogue_tile_tma(const EpiCtx& e, uint32_t taddr, int n_base, int n_tile, const CUtensorMap* mapC,
+                                                  uint32_t stage0, int& buf, int m0, int lane) {
+    const int nch = n_tile / 32;
+    for (int c = 0; c < nch; ++c) {
+        uint32_t ra[32];
+        tmem_ld<32>(taddr + (uint32_t)(c * 32), ra);
+        tmem_ld_fence<32>(ra);
+        epilogue_chunk_tma(e, ra, n_base + c * 32, mapC, stage0, buf, m0, lane);
+    }
+    if (n_tile & 31) {
+        uint32_t rt[16];
+        tmem_ld<16>(taddr + (uint32_t)(nch * 32), rt);
+        tmem_ld_fence<16>(rt);
+        epilogue_emit<16>(e, rt, n_base + nch * 32);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                  const __grid_constant__ CUtensorMap mapBlo, const Args g) {
+                  const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC, const Args g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t raw_bar[MAX_STAGES], full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
@@ -358,7 +487,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (bias_in_smem)
         for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += THREADS) s_bias[i] = i < g.N ? __ldg(g.bias + i) : 0.f;
     const uint32_t b_bytes = (uint32_t)g.n_tile * 128;
-    const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_bytes;
+    const uint32_t a_bytes = g.a_tmem ? A_TILE_BYTES : 2 * A_TILE_BYTES;       // raw A only when (hi, lo) live in TMEM
+    const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
     const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
 
     if (threadIdx.x == 0) {
@@ -377,6 +507,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
         if (g.b_presplit) tma_prefetch_desc(&mapBlo);
+        if (g.c_tma) tma_prefetch_desc(&mapC);
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
     tc_fence_before();
@@ -387,7 +518,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp < CONV_WARPS) {
         // ================= converters =================
         const int tid = threadIdx.x;
-        int stage = 0;
+        int stage = 0, dbg_it = 0;
         uint32_t phase = 0;
         TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
         const bool colsum = g.colsum_part != nullptr && g.a_mn;
@@ -396,17 +527,36 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             float4 acc[BM / 32];
 #pragma unroll
             for (int j = 0; j < BM / 32; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float row_sum = 0.f;
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(smem_u32(&raw_bar[stage]), phase);
+                if (tid == 0) DBG_STAMP(dbg_it, 1);
+                if (tid == 96) DBG_STAMP(dbg_it, 12);
                 const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-                if (sum_tile) split_tile_colsum(st, st + A_TILE_BYTES, tid, acc);
-                else split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, tid);
-                if (!g.b_presplit) split_tile(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_bytes, b_bytes, tid);
-                fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core
+                if (g.a_tmem) {
+                    // this TMEM slot was last read by the MMAs of the previous round of this stage: they retired before the
+                    // producer refilled the stage (empty_bar), i.e. before raw_bar flipped
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g.a_col0 + stage * 2 * BK);
+                    row_sum += split_row_to_tmem(st, g.a_mn != 0, tid, ta);
+                    if (!g.b_presplit) split_tile(st + a_bytes, st + a_bytes + b_bytes, b_bytes, tid);
+                    tc_fence_before();
+                } else {
+                    if (sum_tile) split_tile_colsum(st, st + A_TILE_BYTES, tid, acc);
+                    else split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, tid);
+                    if (!g.b_presplit) split_tile(st + a_bytes, st + a_bytes + b_bytes, b_bytes, tid);
+                }
+                if (!(g.a_tmem && g.b_presplit)) fence_proxy_async();   // generic-proxy smem stores -> visible to the tensor core
+                if (tid == 0) DBG_STAMP(dbg_it, 2);
+                if (tid == 96) DBG_STAMP(dbg_it, 11);
+                ++dbg_it;
                 mbar_arrive(smem_u32(&full_bar[stage]));
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
-            if (sum_tile) {
+            if (sum_tile && g.a_tmem) {
+                const int m = w.mt * BM + tid;             // thread t owns row m: its k-sum IS the partial column sum
+                if (m < g.M) g.colsum_part[(int64_t)w.split * g.M + m] = row_sum;
+            } else if (sum_tile) {
                 // 16 threads hold partial sums of the same columns: 4 lanes of every warp (the k-row residues r = 0..3,
                 // at lane r*8 + (((lc ^ r) << 1) | half)), times 4 warps.  Butterfly over r, then a fixed-order sum over
                 // the warps through shared memory (the bias staging area: wgrad has no bias).
@@ -439,15 +589,39 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx = A_TILE_BYTES + (g.b_presplit ? 2 * b_bytes : b_bytes);
+        int dbg_it = 0;
+        // The streamed A operand comes from DRAM (1-2 us under load) while a stage can only be requested once its slot is free;
+        // with 3 slots that latency sits on the critical path.  So the A boxes are pulled into L2 `g.l2_ahead` stages ahead of
+        // their real request (the weights are L2-resident anyway).
+        TileWalk pw{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        bool pw_ok = g.l2_ahead > 0 && tile_decode(pw, g, total_tiles);
+        int pkb = pw.kb0;
+        auto prefetch_next = [&]() {
+            if (!pw_ok) return;
+            if (pkb < pw.kb1) {
+                const int pm0 = pw.mt * BM, pk0 = pkb * BK;
+                if (g.a_mn) { for (int j = 0; j < BM / 32; ++j) tma_prefetch_l2_2d(&mapA, pm0 + 32 * j, pk0); }
+                else tma_prefetch_l2_2d(&mapA, pk0, pm0);
+            }
+            if (++pkb >= pw.kb1) {
+                pw.tile += gridDim.x;
+                pw_ok = tile_decode(pw, g, total_tiles);
+                pkb = pw.kb0;
+            }
+        };
+        if (lane == 0)
+            for (int i = 0; i < g.l2_ahead; ++i) prefetch_next();
         TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
         for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
             const int m0 = w.mt * BM, n0 = w.nt * g.n_tile;
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
+                if (lane == 0) prefetch_next();
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 if (lane == 0) {
+                    DBG_STAMP(dbg_it, 0);
                     const uint32_t bar = smem_u32(&raw_bar[stage]);
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + 2 * A_TILE_BYTES;
+                    const uint32_t sb = sa + a_bytes;
                     const int k0 = kb * BK;
                     mbar_expect_tx(bar, tx);
                     if (g.a_mn) {
@@ -466,6 +640,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     }
                 }
                 __syncwarp();
+                ++dbg_it;
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -473,27 +648,45 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // ================= MMA issuer =================
         // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, M = 128, N = n_tile,
         // bit 15 / 16 = A / B is MN-major
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.a_mn ? 1 : 0) << 15) |
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((g.a_mn && !g.a_tmem) ? 1 : 0) << 15) |
                                ((uint32_t)(g.b_mn ? 1 : 0) << 16) | ((uint32_t)(g.n_tile >> 3) << 17) |
                                ((uint32_t)(BM >> 4) << 24);
         const uint32_t a_step = g.a_mn ? 1024u : (uint32_t)UK * 4u;      // bytes per MMA along K
         const uint32_t b_step = g.b_mn ? 1024u : (uint32_t)UK * 4u;
         int stage = 0;
         uint32_t phase = 0;
-        int acc = 0;
+        int acc = 0, dbg_it = 0;
         uint32_t acc_phase = 0;
         TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
         for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+            if (lane == 0) DBG_STAMP(dbg_it, 5);
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);       // epilogue drained this accumulator
+            if (lane == 0) DBG_STAMP(dbg_it, 6);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(smem_u32(&raw_bar[stage]), phase);                 // TMA bytes (the pre-split B tiles) landed
+                if (lane == 0) DBG_STAMP(dbg_it, 8);
                 mbar_wait(smem_u32(&full_bar[stage]), phase);                // converters done
+                if (lane == 0) DBG_STAMP(dbg_it, 9);
                 tc_fence_after();
+                if (lane == 0) DBG_STAMP(dbg_it, 3);
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES, b_hi = sa + 2 * A_TILE_BYTES, b_lo = b_hi + b_bytes;
+                    const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES, b_hi = sa + a_bytes, b_lo = b_hi + b_bytes;
+                    if (g.a_tmem) {
+                        const uint32_t ta_hi = tmem_base + (uint32_t)(g.a_col0 + stage * 2 * BK), ta_lo = ta_hi + (uint32_t)BK;
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            const uint32_t bo = (uint32_t)k * b_step;
+                            const uint64_t dbh = g.b_mn ? desc_mn_major(b_hi + bo) : desc_k_major(b_hi + bo);
+                            const uint64_t dbl = g.b_mn ? desc_mn_major(b_lo + bo) : desc_k_major(b_lo + bo);
+                            const uint32_t first = (kb > w.kb0 || k > 0) ? 1u : 0u;
+                            umma_tf32_ts(d_tmem, ta_lo + (uint32_t)(k * UK), dbh, idesc, first);
+                            umma_tf32_ts(d_tmem, ta_hi + (uint32_t)(k * UK), dbl, idesc, 1u);
+                            umma_tf32_ts(d_tmem, ta_hi + (uint32_t)(k * UK), dbh, idesc, 1u);
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint32_t ao = (uint32_t)k * a_step, bo = (uint32_t)k * b_step;
@@ -506,9 +699,12 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
+                    DBG_STAMP(dbg_it, 10);
                     umma_commit(smem_u32(&empty_bar[stage]));                // frees the smem slot when these MMAs retire
                     if (kb == w.kb1 - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                    DBG_STAMP(dbg_it, 4);
                 }
+                ++dbg_it;
                 __syncwarp();
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
@@ -521,13 +717,15 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int q = warp & 3;                        // TMEM lane quadrant this warp may read
         uint64_t drop_seed = 0, drop_ctr = 0;
         if (g.epi.drop_state) { drop_seed = g.epi.drop_state[0]; drop_ctr = g.epi.drop_state[1]; }
-        int acc = 0;
+        int acc = 0, dbg_tile = 0, cbuf = 0;
+        const uint32_t cstage = smem_u32(smem + (size_t)g.stages * stage_bytes) + (uint32_t)q * 8192u;   // 2 x 4 KB per warp
         uint32_t acc_phase = 0;
         TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
         for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
             const bool empty_split = w.kb1 <= w.kb0;
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
+            if (warp == CONV_WARPS + 2 && lane == 0) DBG_STAMP(dbg_tile * (w.kb1 - w.kb0), 7);
             const int m = w.mt * BM + q * 32 + lane;
             EpiCtx e;
             e.crow = g.C + ((int64_t)w.split * g.M + m) * g.ldc;
@@ -546,13 +744,17 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             e.mask_row = (g.epi.mask_src && g.splits == 1) ? g.epi.mask_src + (int64_t)m * g.epi.mask_ld : nullptr;
             e.mvec = g.epi.mvec;
             e.mask_scale = g.epi.mask_scale;
-            const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-            if (g.n_tile % 32 == 0) epilogue_tile<32>(e, taddr, w.nt * g.n_tile, g.n_tile);
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(q * 32) << 16);
+            if (g.c_tma) epilogue_tile_tma(e, taddr, w.nt * g.n_tile, g.n_tile, &mapC, cstage, cbuf, w.mt * BM + q * 32, lane);
+            else if (g.n_tile % 32 == 0) epilogue_tile<32>(e, taddr, w.nt * g.n_tile, g.n_tile);
             else epilogue_tile<16>(e, taddr, w.nt * g.n_tile, g.n_tile);
             tc_fence_before();
+            if (warp == CONV_WARPS + 2 && lane == 0) DBG_STAMP(dbg_tile * (w.kb1 - w.kb0) + 1, 7);
+            ++dbg_tile;
             mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (g.c_tma && lane == 0) bulk_wait_read<0>();      // the staging blocks must outlive the stores that read them
     }
     tc_fence_before();
     __syncthreads();
@@ -619,9 +821,11 @@ static int round_to(int n, int q) { return (n + q - 1) / q * q; }
 
 struct Plan {
     int n_tile, n_tiles, m_tiles, splits, kb_per_split, stages;
+    int a_tmem, acc_stride, a_col0, c_tma;
     size_t smem;
 };
-static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split) {
+constexpr size_t C_STAGE_BYTES = (size_t)EPI_WARPS * 2 * 4096;     // two 32 x 32 fp32 blocks per epilogue warp
+static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_tma_ok = false) {
     Plan p;
     const int nt_max = env_int("RLCTR_GEMM_NT_MAX", 160);           // <= 160 keeps three 72 KB stages in flight
     const int q = b_mn ? 32 : 16;
@@ -643,12 +847,24 @@ static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split) {
     if (p.kb_per_split < 1) p.kb_per_split = 1;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
     if (p.splits < 1) p.splits = 1;
-    const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.n_tile * 128;
+    // A in tensor memory: the accumulator stages shrink to the tile width and the rest of the 512 columns holds up to
+    // (512 - 2 * acc_stride) / 64 stages of (A_hi | A_lo); shared memory then carries only the raw A tile and B
+    p.acc_stride = round_to(p.n_tile, 32);
+    p.a_col0 = 2 * p.acc_stride;
+    const int tmem_stages = (TMEM_COLS - p.a_col0) / (2 * BK);
+    p.a_tmem = (env_int("RLCTR_GEMM_A_TMEM", 1) != 0 && tmem_stages >= 2) ? 1 : 0;
+    if (!p.a_tmem) { p.acc_stride = 256; p.a_col0 = 0; }
+    const size_t stage_bytes = (p.a_tmem ? 1 : 2) * (size_t)A_TILE_BYTES + 2 * (size_t)p.n_tile * 128;
     int st = (int)((size_t)(220 * 1024) / stage_bytes);
     if (st > MAX_STAGES) st = MAX_STAGES;
+    if (p.a_tmem && st > tmem_stages) st = tmem_stages;
     if (st < 1) st = 1;
     p.stages = st;
-    p.smem = stage_bytes * st + 1024;
+    // TMA-stored C: only when the staging blocks fit beside the pipeline without costing it a stage, and never for split-K
+    // partials (a box clipped at the tensor bound, not at the split's M rows, would spill into the next split)
+    p.c_tma = (c_tma_ok && p.splits == 1 && env_int("RLCTR_GEMM_C_TMA", 1) != 0 &&
+               stage_bytes * st + C_STAGE_BYTES <= (size_t)(220 * 1024)) ? 1 : 0;
+    p.smem = stage_bytes * st + (p.c_tma ? C_STAGE_BYTES : 0) + 1024;
     return p;
 }
 int plan_splits(int M, int N, int K, bool b_mn) { return make_plan(M, N, K, b_mn, true).splits; }
@@ -674,7 +890,7 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     if (!enabled()) return RLCTR_EUNSUPPORTED;
     if (!tma_ok(A.ptr, A.pitch) || !tma_ok(B.ptr, B.pitch) || (B.lo && !tma_ok(B.lo, B.pitch))) return RLCTR_EUNSUPPORTED;
     if (A.lo) return RLCTR_EUNSUPPORTED;                  // the streamed operand is always converted in the kernel
-    const Plan p = make_plan(M, N, K, B.mn_major, allow_split);
+    const Plan p = make_plan(M, N, K, B.mn_major, allow_split, tma_ok(C, ldc));
     if (p.n_tile > 256 || (B.mn_major && p.n_tile % 32 != 0)) return RLCTR_EUNSUPPORTED;
     CUtensorMap mA, mB, mBlo;
     // K-major operand [R rows][K]: dims {K, R}, box {32, tile rows}.  MN-major operand [K rows][R]: dims {R, K}, box {32, 32}.
@@ -682,22 +898,30 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     ok = ok && (B.mn_major ? make_map(&mB, B.ptr, N, K, B.pitch, 32, true) : make_map(&mB, B.ptr, K, N, B.pitch, p.n_tile));
     if (B.lo) ok = ok && (B.mn_major ? make_map(&mBlo, B.lo, N, K, B.pitch, 32, true) : make_map(&mBlo, B.lo, K, N, B.pitch, p.n_tile));
     else mBlo = mB;
+    CUtensorMap mC = mA;
+    if (p.c_tma) ok = ok && make_map(&mC, C, N, M, ldc, 32);          // box {32 n, 32 m}, SWIZZLE_128B
     if (!ok) return RLCTR_EUNSUPPORTED;
     Args g;
     g.C = C; g.ldc = ldc; g.cvec = vec_of(C, ldc); g.bias = bias;
     g.M = M; g.N = N; g.K = K;
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages;
+    g.a_tmem = p.a_tmem; g.acc_stride = p.acc_stride; g.a_col0 = p.a_col0; g.c_tma = p.c_tma;
+    g.l2_ahead = env_int("RLCTR_GEMM_L2_AHEAD", 0);     // measured: no gain (the pipeline is L2->SM bandwidth bound, not DRAM-latency bound)
     g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
     g.colsum_part = (colsum_part && A.mn_major && !bias) ? colsum_part : nullptr;
     if (colsum_part && !g.colsum_part) return RLCTR_EUNSUPPORTED;
+    {
+        const char* d = getenv("RLCTR_GEMM_DBG");             // hex device address of a zeroed long long [256 * 8] buffer
+        g.dbg = (d && *d) ? reinterpret_cast<long long*>(strtoull(d, nullptr, 16)) : nullptr;
+    }
     g.epi = epi ? *epi : Epilogue{};
     if ((g.epi.drop_state || g.epi.mask_src) && p.splits != 1) return RLCTR_EUNSUPPORTED;
     if (g.epi.mask_src) g.epi.mvec = vec_of(g.epi.mask_src, g.epi.mask_ld);
     RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total < RLCTR_SMS ? total : RLCTR_SMS;
-    gemm3x_tma_kernel<<<grid, THREADS, p.smem, st>>>(mA, mB, mBlo, g);
+    gemm3x_tma_kernel<<<grid, THREADS, p.smem, st>>>(mA, mB, mBlo, mC, g);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -47,7 +47,7 @@ class Prefetched:
 
 
 class GraphedTrainStep:
-    def __init__(self, pairs, loss_fn=None, eager_steps=2, steps_ahead=65536):
+    def __init__(self, pairs, loss_fn=None, eager_steps=2, steps_ahead=65536, fork=True):
         self.pairs = list(pairs)
         self.loss_fn = loss_fn if loss_fn is not None else torch.nn.BCELoss()
         self.eager_left = int(eager_steps)
@@ -60,6 +60,8 @@ class GraphedTrainStep:
         self._stage = [None, None]
         self._consumed = [None, None]
         self._slot = 0
+        self.fork = bool(fork)         # capture tower-less models as parallel branches of the graph (see _forked)
+        self._side_streams = []
         self.stream = None             # warm-up steps and the capture share one side stream (autograd's AccumulateGrad
                                        # nodes remember the stream they were created on)
 
@@ -102,6 +104,45 @@ class GraphedTrainStep:
     def _eager(self, x, y):
         return [eager_step(m, opt, self.loss_fn, x, y) for m, opt in self.pairs]
 
+    def _branches(self):
+        """Indices of the models whose step may run on a forked stream inside the capture: tower-less single-GPU models
+        (their step is a handful of HBM-bound kernels: catch-up, gather, loss, segment-reduce + Adam) with an optimizer of
+        their own.  They overlap the tensor-bound tower GEMMs of the models that stay on the capture stream."""
+        if not self.fork:
+            return []
+        opts = [opt for _, opt in self.pairs]
+        side = [i for i, (m, opt) in enumerate(self.pairs)
+                if isinstance(m, Model._TableModel) and getattr(m, "mlp", None) is None and not hasattr(m, "train_step")
+                and not isinstance(m, (Model.DCN, Model.AFM)) and opts.count(opt) == 1]
+        if len(side) == len(self.pairs):
+            side = side[1:]                       # somebody has to stay on the capture stream
+        return side
+
+    def _forked(self, x, y):
+        """The step with the tower-less models on side streams (fork after the shared sort, join before the end): the
+        captured graph gets parallel branches, so the HBM-bound kernels of LR / FM run under DeepFM's GEMMs."""
+        side = self._branches()
+        if not side:
+            return self._eager(x, y)
+        main = torch.cuda.current_stream()
+        first = self.pairs[side[0]][0]
+        Model.sort_ids(Model._check_ids(x), first._geom.n_rows)      # shared by every model fed with this batch: before the fork
+        while len(self._side_streams) < len(side):
+            self._side_streams.append(torch.cuda.Stream(device=first.table.device))
+        losses = [None] * len(self.pairs)
+        for k, i in enumerate(side):
+            st = self._side_streams[k]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                m, opt = self.pairs[i]
+                losses[i] = eager_step(m, opt, self.loss_fn, x, y)
+        for i, (m, opt) in enumerate(self.pairs):
+            if i not in side:
+                losses[i] = eager_step(m, opt, self.loss_fn, x, y)
+        for k in range(len(side)):
+            main.wait_stream(self._side_streams[k])
+        return losses
+
     def _eager_on_side_stream(self, x, y):
         if self.stream is None:
             self.stream = torch.cuda.Stream(device=self.pairs[0][0].table.device)
@@ -128,7 +169,7 @@ class GraphedTrainStep:
             self.stream = torch.cuda.Stream(device=dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self.stream):
-            self.losses = self._eager(self.x, self.y)
+            self.losses = self._forked(self.x, self.y)
         self.launches_per_step = int(lib.rlctr_launch_count() - l0)
         self.graph = g
         # the capture ran the Python side of one step (host counters advanced) but no kernel: replay it now
