@@ -335,7 +335,8 @@ int rlctr_auc_logloss(const float* pred, const int64_t* labels_i64, const float*
 #define RLCTR_MLP_DX_MASK 4     /* bwd: dx *= (x > 0 ? dx_scale : 0): the ReLU (+dropout) backward of the layer that
                                    produced x, fused into this layer's dgrad epilogue */
 size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
-/* Dropout mask: keep(element i) = hash(rng_state[0] (seed), rng_state[1] (counter) + i) >= p * 2^32, i = row * out_dim + col.
+/* Dropout mask: keep(element i) = r16(rng_state[0] (seed), rng_state[1] (counter) + i) >= p * 2^16, i = row * out_dim + col
+ * (16 random bits per element, two elements per 32-bit hash: csrc/common.cuh).
  * rng_state is DEVICE memory so that a captured CUDA graph draws a new mask on every replay; rlctr_rng_advance moves the
  * counter (call it with batch * out_dim after each forward that used the state).  The mask is not stored: the backward
  * recovers it from the saved output (y == 0 <=> clipped by ReLU or dropped; gy_scale = 1 / (1-p)). */

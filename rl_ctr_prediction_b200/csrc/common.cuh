@@ -184,23 +184,29 @@ colsum_parts_kernel(const float* __restrict__ part, float* __restrict__ out_a, f
 }
 static inline int colsum_parts_grid(int n) { return (n + 7) / 8; }
 
-// ---- counter-based dropout mask (mlp.cu / mlp_tma.cu) ----------------------------------------------------------
-// keep(element) = hash(seed, counter + element index) >= p * 2^32.  (seed, counter) live in device memory so that a
-// CUDA-graph replay draws a fresh mask every step (rlctr_rng_advance moves the counter).  Two rounds of a 32-bit
-// avalanche mix (multiply-xorshift) over the 128 bits of (seed, index): enough for dropout, 10 integer ops.
+// ---- counter-based dropout mask (mlp.cu / mlp_tma.cu / afm.cu) ------------------------------------------------------------
+// keep(element) = r16(seed, counter + element index) >= p * 2^16: 16 random bits per element, TWO elements per 32-bit hash
+// (elements 2k and 2k+1 take the low / high half of hash(k)), because the mask is drawn in GEMM epilogues where the integer
+// pipe is the scarce resource: ~4 integer ops per element instead of ~20.  (seed, counter) live in device memory so that a
+// CUDA-graph replay draws a fresh mask every step (rlctr_rng_advance moves the counter).  hash = one round of a 32-bit
+// avalanche mix (multiply-xorshift, "lowbias32") of the pair index under a key that folds in the seed and the index's high word.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
-    uint32_t h = mix32((uint32_t)idx ^ (uint32_t)seed);
-    h = mix32(h ^ (uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32) ^ 0x9e3779b9U);
-    return h >= thresh;
+__device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t pair_hi) {
+    return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) ^ pair_hi ^ 0x9e3779b9U));
 }
-static inline uint32_t dropout_thresh(float p) {
-    double t = (double)p * 4294967296.0;
+__device__ __forceinline__ uint32_t dropout_bits(uint32_t key, uint32_t pair_lo) { return mix32(pair_lo ^ key); }
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
+    const uint64_t pair = idx >> 1;
+    const uint32_t h = dropout_bits(dropout_key(seed, (uint32_t)(pair >> 32)), (uint32_t)pair);
+    return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh;
+}
+static inline uint32_t dropout_thresh(float p) {          // 16-bit threshold: P(drop) = thresh / 65536
+    double t = (double)p * 65536.0;
     if (t < 0.0) t = 0.0;
-    if (t > 4294967295.0) t = 4294967295.0;
+    if (t > 65535.0) t = 65535.0;
     return (uint32_t)t;
 }
 

@@ -53,6 +53,8 @@ struct Args {
     int relu;
     int a_tmem;                           // 1: the converters write (A_hi, A_lo) into TENSOR MEMORY and the MMAs read A from there
     int acc_stride, a_col0;               // TMEM columns: accumulator stage s at s*acc_stride, A stage s at a_col0 + 64*s (hi | lo)
+    int cluster;                          // CTAs per cluster (1 or 2): the B tile is fetched once per cluster (TMA multicast), each CTA
+                                          // owning a different m-tile of the same (n-tile, split)
     int l2_ahead;                         // stages of A the producer prefetches into L2 ahead of the pipeline (0: off)
     int c_tma;                            // 1: the epilogue stages 32x32 blocks of C in shared memory and TMA-stores them (mapC)
     long long* dbg;                       // RLCTR_GEMM_DBG: per-stage clock64 stamps of block 0 (scratch/gemm_trace.py), else null
@@ -192,6 +194,25 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
                  "r"(c1) : "memory");
 }
+// the same box delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -321,13 +342,18 @@ __device__ __forceinline__ float split_row_to_tmem(uint32_t raw, bool a_mn, int 
 struct TileWalk {                          // this CTA's (tile, k-block) sequence, identical in every role
     int tile, kb0, kb1, mt, nt, split;
 };
-__device__ __forceinline__ bool tile_decode(TileWalk& w, const Args& g, int total_tiles) {
+// With clusters, `tile` counts CLUSTER tiles (cluster consecutive m-tiles of one (n-tile, split)): every CTA of a cluster walks
+// the same sequence, CTA `rank` taking m-tile mt*cluster + rank (possibly past the end: it then computes on zero-filled rows and
+// stores nothing, but still takes part in the shared B loads).
+__device__ __forceinline__ bool tile_decode(TileWalk& w, const Args& g, int total_tiles, int rank = 0) {
     if (w.tile >= total_tiles) return false;
-    const int mn = g.m_tiles * g.n_tiles;
+    const int mtc = (g.m_tiles + g.cluster - 1) / g.cluster;
+    const int mn = mtc * g.n_tiles;
     w.split = w.tile / mn;
     const int r = w.tile - w.split * mn;
     w.mt = r / g.n_tiles;
     w.nt = r - w.mt * g.n_tiles;
+    w.mt = w.mt * g.cluster + rank;
     const int kb_total = (g.K + BK - 1) / BK;
     w.kb0 = w.split * g.kb_per_split;
     w.kb1 = min(w.kb0 + g.kb_per_split, kb_total);
@@ -372,9 +398,21 @@ __device__ __forceinline__ void epilogue_compute(const EpiCtx& e, const uint32_t
         for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (e.drop) {
+        const uint64_t i0 = e.drop_base + (uint64_t)n0;                   // element index of column n0 of this row
+        const uint64_t p0 = i0 >> 1, p1 = (i0 + (uint64_t)(W - 1)) >> 1;
+        if (!(i0 & 1) && (p0 >> 32) == (p1 >> 32)) {                      // pairs aligned with the columns, one key: the usual case
+            const uint32_t key = dropout_key(e.drop_seed, (uint32_t)(p0 >> 32)), lo = (uint32_t)p0;
 #pragma unroll
-        for (int j = 0; j < W; ++j)
-            v[j] = dropout_keep(e.drop_seed, e.drop_base + (uint64_t)(n0 + j), e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+            for (int j = 0; j < W; j += 2) {
+                const uint32_t h = dropout_bits(key, lo + (uint32_t)(j >> 1));
+                v[j] = (h & 0xffffu) >= e.drop_thresh ? v[j] * e.drop_scale : 0.f;
+                v[j + 1] = (h >> 16) >= e.drop_thresh ? v[j + 1] * e.drop_scale : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                v[j] = dropout_keep(e.drop_seed, i0 + (uint64_t)j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
+        }
     }
     if (e.mask_row && e.row_ok) {
         const float* mr = e.mask_row + n0;
@@ -489,13 +527,16 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t b_bytes = (uint32_t)g.n_tile * 128;
     const uint32_t a_bytes = g.a_tmem ? A_TILE_BYTES : 2 * A_TILE_BYTES;       // raw A only when (hi, lo) live in TMEM
     const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
-    const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+    const int rank = g.cluster > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = (int)blockIdx.x / g.cluster, n_clusters = (int)gridDim.x / g.cluster;
+    const int total_tiles = ((g.m_tiles + g.cluster - 1) / g.cluster) * g.n_tiles * g.splits;
+    const uint16_t cmask = (uint16_t)((1u << g.cluster) - 1u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&raw_bar[s]), 1);
             mbar_init(smem_u32(&full_bar[s]), CONV_WARPS * 32);
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), (uint32_t)g.cluster);      // every CTA of the cluster has retired its MMAs on the slot
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tmem_full_bar[s]), 1);
@@ -512,6 +553,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp == MMA_WARP) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (g.cluster > 1) cluster_sync_all();                 // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -520,9 +562,9 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int tid = threadIdx.x;
         int stage = 0, dbg_it = 0;
         uint32_t phase = 0;
-        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
+        TileWalk w{cluster_id, 0, 0, 0, 0, 0};
         const bool colsum = g.colsum_part != nullptr && g.a_mn;
-        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+        for (; tile_decode(w, g, total_tiles, rank); w.tile += n_clusters) {
             const bool sum_tile = colsum && w.nt == 0;     // every (split, m-tile) is met exactly once with nt == 0
             float4 acc[BM / 32];
 #pragma unroll
@@ -593,8 +635,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // The streamed A operand comes from DRAM (1-2 us under load) while a stage can only be requested once its slot is free;
         // with 3 slots that latency sits on the critical path.  So the A boxes are pulled into L2 `g.l2_ahead` stages ahead of
         // their real request (the weights are L2-resident anyway).
-        TileWalk pw{(int)blockIdx.x, 0, 0, 0, 0, 0};
-        bool pw_ok = g.l2_ahead > 0 && tile_decode(pw, g, total_tiles);
+        TileWalk pw{cluster_id, 0, 0, 0, 0, 0};
+        bool pw_ok = g.l2_ahead > 0 && tile_decode(pw, g, total_tiles, rank);
         int pkb = pw.kb0;
         auto prefetch_next = [&]() {
             if (!pw_ok) return;
@@ -604,15 +646,15 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 else tma_prefetch_l2_2d(&mapA, pk0, pm0);
             }
             if (++pkb >= pw.kb1) {
-                pw.tile += gridDim.x;
-                pw_ok = tile_decode(pw, g, total_tiles);
+                pw.tile += n_clusters;
+                pw_ok = tile_decode(pw, g, total_tiles, rank);
                 pkb = pw.kb0;
             }
         };
         if (lane == 0)
             for (int i = 0; i < g.l2_ahead; ++i) prefetch_next();
-        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
-        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+        TileWalk w{cluster_id, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles, rank); w.tile += n_clusters) {
             const int m0 = w.mt * BM, n0 = w.nt * g.n_tile;
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 if (lane == 0) prefetch_next();
@@ -629,7 +671,21 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     } else {
                         tma_load_2d(sa, &mapA, k0, m0, bar);
                     }
-                    if (g.b_mn) {
+                    if (g.cluster > 1) {
+                        // this CTA fetches its share of the B tile and multicasts it to the whole cluster; the peers' shares land
+                        // here the same way (raw_bar counts the bytes of the full tile either way)
+                        if (g.b_mn) {
+                            for (int j = rank; j < g.n_tile / 32; j += g.cluster) {
+                                tma_load_2d_mc(sb + j * 4096, &mapB, n0 + 32 * j, k0, bar, cmask);
+                                if (g.b_presplit) tma_load_2d_mc(sb + b_bytes + j * 4096, &mapBlo, n0 + 32 * j, k0, bar, cmask);
+                            }
+                        } else {
+                            const int rows = g.n_tile / g.cluster;                   // box rows of mapB (a multiple of 8)
+                            const uint32_t off = (uint32_t)(rank * rows) * 128u;
+                            tma_load_2d_mc(sb + off, &mapB, k0, n0 + rank * rows, bar, cmask);
+                            if (g.b_presplit) tma_load_2d_mc(sb + b_bytes + off, &mapBlo, k0, n0 + rank * rows, bar, cmask);
+                        }
+                    } else if (g.b_mn) {
                         for (int j = 0; j < g.n_tile / 32; ++j) {
                             tma_load_2d(sb + j * 4096, &mapB, n0 + 32 * j, k0, bar);
                             if (g.b_presplit) tma_load_2d(sb + b_bytes + j * 4096, &mapBlo, n0 + 32 * j, k0, bar);
@@ -657,8 +713,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         uint32_t phase = 0;
         int acc = 0, dbg_it = 0;
         uint32_t acc_phase = 0;
-        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
-        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+        TileWalk w{cluster_id, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles, rank); w.tile += n_clusters) {
             if (lane == 0) DBG_STAMP(dbg_it, 5);
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);       // epilogue drained this accumulator
             if (lane == 0) DBG_STAMP(dbg_it, 6);
@@ -700,7 +756,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
                     DBG_STAMP(dbg_it, 10);
-                    umma_commit(smem_u32(&empty_bar[stage]));                // frees the smem slot when these MMAs retire
+                    if (g.cluster > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), cmask);   // ... in every CTA that writes into it
+                    else umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem slot when these MMAs retire
                     if (kb == w.kb1 - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
                     DBG_STAMP(dbg_it, 4);
                 }
@@ -720,8 +777,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         int acc = 0, dbg_tile = 0, cbuf = 0;
         const uint32_t cstage = smem_u32(smem + (size_t)g.stages * stage_bytes) + (uint32_t)q * 8192u;   // 2 x 4 KB per warp
         uint32_t acc_phase = 0;
-        TileWalk w{(int)blockIdx.x, 0, 0, 0, 0, 0};
-        for (; tile_decode(w, g, total_tiles); w.tile += gridDim.x) {
+        TileWalk w{cluster_id, 0, 0, 0, 0, 0};
+        for (; tile_decode(w, g, total_tiles, rank); w.tile += n_clusters) {
             const bool empty_split = w.kb1 <= w.kb0;
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
@@ -758,6 +815,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (g.cluster > 1) cluster_sync_all();                 // no CTA leaves while a peer may still signal its barriers
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -821,7 +879,7 @@ static int round_to(int n, int q) { return (n + q - 1) / q * q; }
 
 struct Plan {
     int n_tile, n_tiles, m_tiles, splits, kb_per_split, stages;
-    int a_tmem, acc_stride, a_col0, c_tma;
+    int a_tmem, acc_stride, a_col0, c_tma, cluster;
     size_t smem;
 };
 constexpr size_t C_STAGE_BYTES = (size_t)EPI_WARPS * 2 * 4096;     // two 32 x 32 fp32 blocks per epilogue warp
@@ -865,6 +923,12 @@ static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_t
     p.c_tma = (c_tma_ok && p.splits == 1 && env_int("RLCTR_GEMM_C_TMA", 1) != 0 &&
                stage_bytes * st + C_STAGE_BYTES <= (size_t)(220 * 1024)) ? 1 : 0;
     p.smem = stage_bytes * st + (p.c_tma ? C_STAGE_BYTES : 0) + 1024;
+    // CTA pairs sharing every B tile by TMA multicast (RLCTR_GEMM_CLUSTER=2; needs two m-tiles to pair and a B tile that halves on
+    // a swizzle-atom boundary).  Off by default: measured no gain -- the kernel is bound by the shared-memory port of each SM, and a
+    // multicast tile is still written into (and read by the MMAs from) every CTA's own shared memory.
+    p.cluster = 1;
+    if (env_int("RLCTR_GEMM_CLUSTER", 1) >= 2 && p.m_tiles >= 2 && (b_mn || p.n_tile % 16 == 0))
+        p.cluster = 2;
     return p;
 }
 int plan_splits(int M, int N, int K, bool b_mn) { return make_plan(M, N, K, b_mn, true).splits; }
@@ -895,8 +959,9 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     CUtensorMap mA, mB, mBlo;
     // K-major operand [R rows][K]: dims {K, R}, box {32, tile rows}.  MN-major operand [K rows][R]: dims {R, K}, box {32, 32}.
     bool ok = A.mn_major ? make_map(&mA, A.ptr, M, K, A.pitch, 32, true) : make_map(&mA, A.ptr, K, M, A.pitch, BM);
-    ok = ok && (B.mn_major ? make_map(&mB, B.ptr, N, K, B.pitch, 32, true) : make_map(&mB, B.ptr, K, N, B.pitch, p.n_tile));
-    if (B.lo) ok = ok && (B.mn_major ? make_map(&mBlo, B.lo, N, K, B.pitch, 32, true) : make_map(&mBlo, B.lo, K, N, B.pitch, p.n_tile));
+    const int b_box = p.n_tile / p.cluster;            // K-major B: each CTA of a cluster fetches 1/cluster of the tile's rows
+    ok = ok && (B.mn_major ? make_map(&mB, B.ptr, N, K, B.pitch, 32, true) : make_map(&mB, B.ptr, K, N, B.pitch, b_box));
+    if (B.lo) ok = ok && (B.mn_major ? make_map(&mBlo, B.lo, N, K, B.pitch, 32, true) : make_map(&mBlo, B.lo, K, N, B.pitch, b_box));
     else mBlo = mB;
     CUtensorMap mC = mA;
     if (p.c_tma) ok = ok && make_map(&mC, C, N, M, ldc, 32);          // box {32 n, 32 m}, SWIZZLE_128B
@@ -907,6 +972,7 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages;
     g.a_tmem = p.a_tmem; g.acc_stride = p.acc_stride; g.a_col0 = p.a_col0; g.c_tma = p.c_tma;
+    g.cluster = p.cluster;
     g.l2_ahead = env_int("RLCTR_GEMM_L2_AHEAD", 0);     // measured: no gain (the pipeline is L2->SM bandwidth bound, not DRAM-latency bound)
     g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
     g.colsum_part = (colsum_part && A.mn_major && !bias) ? colsum_part : nullptr;
@@ -919,9 +985,33 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     if ((g.epi.drop_state || g.epi.mask_src) && p.splits != 1) return RLCTR_EUNSUPPORTED;
     if (g.epi.mask_src) g.epi.mvec = vec_of(g.epi.mask_src, g.epi.mask_ld);
     RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    const int total = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = total < RLCTR_SMS ? total : RLCTR_SMS;
-    gemm3x_tma_kernel<<<grid, THREADS, p.smem, st>>>(mA, mB, mBlo, mC, g);
+    const int total = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_tiles * p.splits;      // cluster tiles
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(RLCTR_SMS / p.cluster * p.cluster));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = RLCTR_SMS / p.cluster;
+    if (p.cluster > 1) {                                   // clusters that can be resident at once (GPCs with an odd SM count lose one)
+        static int cached_smem = -1, cached = 0;
+        if (cached_smem != (int)p.smem) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel, &cfg) == cudaSuccess && n > 0) cached = n;
+            else cached = RLCTR_SMS / p.cluster;
+            cached_smem = (int)p.smem;
+        }
+        if (cached < max_clusters) max_clusters = cached;
+    }
+    const int grid = (total < max_clusters ? total : max_clusters) * p.cluster;
+    cfg.gridDim = dim3((unsigned)grid);
+    RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel, mA, mB, mBlo, mC, g));
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -130,15 +130,34 @@ class GraphedTrainStep:
         while len(self._side_streams) < len(side):
             self._side_streams.append(torch.cuda.Stream(device=first.table.device))
         losses = [None] * len(self.pairs)
-        for k, i in enumerate(side):
-            st = self._side_streams[k]
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                m, opt = self.pairs[i]
-                losses[i] = eager_step(m, opt, self.loss_fn, x, y)
-        for i, (m, opt) in enumerate(self.pairs):
-            if i not in side:
-                losses[i] = eager_step(m, opt, self.loss_fn, x, y)
+        launched = [False]
+
+        def launch_side():
+            # fork point: everything enqueued on the capture stream so far precedes the side branches
+            launched[0] = True
+            here = torch.cuda.current_stream()
+            for k, i in enumerate(side):
+                st = self._side_streams[k]
+                st.wait_stream(here)
+                with torch.cuda.stream(st):
+                    m, opt = self.pairs[i]
+                    losses[i] = eager_step(m, opt, self.loss_fn, x, y)
+
+        # The side branches are HBM-bound; so are the first kernels of a tower model (catch-up, gather).  Fork AFTER that gather
+        # (p_model._GatherInteract calls the hook once), so that the branches run beside the tower's GEMMs instead of beside
+        # its gather.
+        heavy = [i for i in range(len(self.pairs)) if i not in side]
+        first = self.pairs[heavy[0]][0]
+        if isinstance(first, Model._TableModel) and getattr(first, "mlp", None) is not None:
+            first._after_gather = launch_side
+        else:
+            launch_side()
+        for i in heavy:
+            m, opt = self.pairs[i]
+            losses[i] = eager_step(m, opt, self.loss_fn, x, y)
+        if not launched[0]:
+            first._after_gather = None
+            launch_side()
         for k in range(len(side)):
             main.wait_stream(self._side_streams[k])
         return losses

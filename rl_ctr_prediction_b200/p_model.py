@@ -108,6 +108,10 @@ class _GatherInteract(torch.autograd.Function):
                       _lib.ptr(pctr), 1, _lib.ptr(sums), _lib.ptr(rows), rows_pitch, B, F, flags, _lib.stream(),
                       key=f"rlctr_embed_fwd[{type(module).__name__}]",
                       meta=dict(module._meta(B, F), sums=sums is not None, rows=want_rows))
+        hook = getattr(module, "_after_gather", None)       # graphs.GraphedTrainStep: fork point of the captured step
+        if hook is not None:
+            module._after_gather = None
+            hook()
         ctx.module, ctx.sorted_pair, ctx.apply_sigmoid = module, sorted_pair, apply_sigmoid
         ctx.sums, ctx.partners, ctx.shape = sums, partners, (B, F)
         ctx.has_bias = bias is not None
