@@ -335,6 +335,27 @@ int rlctr_auc_logloss(const float* pred, const int64_t* labels_i64, const float*
 #define RLCTR_MLP_DX_MASK 4     /* bwd: dx *= (x > 0 ? dx_scale : 0): the ReLU (+dropout) backward of the layer that
                                    produced x, fused into this layer's dgrad epilogue */
 size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
+/* ---- replay memory of the RL agents, sampled on the device ----------------------------------------------------
+ * The reference samples on the host: random.sample (DDQN_model.py:183-185) and np.random.choice(n, batch, p=P, replace=False)
+ * after a D2H copy of every priority (v10_Hybrid_TD3_model_PER.py:62-85).  Randomness here: the counter hash under rng_state
+ * (device {seed, counter}; advance it with rlctr_rng_advance by the number the call consumed: 1 for uniform, n_valid for PER).
+ *   store   memory[(counter + i) % memory_size, :] = src[i, :]  (Memory.add :44-60 / store_transition DDQN_model.py:105-120)
+ *   gather  out[i, :] = memory[idx[i], :];   update  priorities[idx[i] * ld] = td[i]  (batch_update :107-108)
+ *   sample_uniform  `batch` DISTINCT indices of [0, n_valid): images of 0..batch-1 under a keyed permutation (random.sample)
+ *   sample_per      greedy == 0: weighted sampling without replacement, w_i = (|priorities[i*ld]| + eps)^alpha
+ *                   (stochastic_sample :62-85; exponential clocks -log(u_i)/w_i, the `batch` smallest);
+ *                   greedy != 0: the `batch` largest raw priorities[i*ld] (greedy_sample :87-105).
+ *                   out_isw[i] = (p_i / min_j p_j)^(-beta), p = w (stochastic) or the raw priority (greedy), j over [0, n_valid). */
+int rlctr_replay_store(float* memory, int64_t memory_size, int32_t width, int64_t counter, const float* src, int64_t n,
+                       int64_t ld_src, rlctr_stream_t stream);
+int rlctr_replay_gather(const float* memory, int32_t width, const int64_t* idx, int64_t n, float* out, rlctr_stream_t stream);
+int rlctr_replay_update(float* priorities, int32_t ld, const int64_t* idx, const float* td, int64_t n, rlctr_stream_t stream);
+int rlctr_replay_sample_uniform(int64_t n_valid, int64_t batch, const uint64_t* rng_state, int64_t* out_idx, rlctr_stream_t stream);
+size_t rlctr_replay_per_ws_bytes(int64_t n_valid);
+int rlctr_replay_sample_per(const float* priorities, int32_t ld, int64_t n_valid, float eps, float alpha, float beta, int32_t greedy,
+                            int64_t batch, const uint64_t* rng_state, int64_t* out_idx, float* out_isw, void* ws, size_t ws_bytes,
+                            rlctr_stream_t stream);
+
 /* Dropout mask: keep(element i) = r16(rng_state[0] (seed), rng_state[1] (counter) + i) >= p * 2^16, i = row * out_dim + col
  * (16 random bits per element, two elements per 32-bit hash: csrc/common.cuh).
  * rng_state is DEVICE memory so that a captured CUDA graph draws a new mask on every replay; rlctr_rng_advance moves the

@@ -68,8 +68,15 @@ class RingMemory:
                 buf[:n - first] = c[first:n]
         self.counter += n
 
+    device_sampling = False        # True: draw the indices on the device (replay.sample_uniform) instead of with Python's RNG
+
     def sample_index(self, batch_size, device):
         pool = self.size if self.counter > self.size else self.counter
+        if self.device_sampling:
+            from . import replay
+            if getattr(self, "_rng", None) is None:
+                self._rng = replay._rng(self.bufs[0].device)
+            return replay.sample_uniform(pool, batch_size, self._rng)                 # no host round trip
         return torch.LongTensor(random.sample(range(pool), batch_size)).to(device)     # host RNG, as the reference
 
 

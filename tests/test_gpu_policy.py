@@ -223,3 +223,114 @@ def test_reinforce_policy_gradient_learn(variant):
         agree = ((p.cpu() - q).abs() <= 2e-6).float().mean().item()
         assert agree >= 0.98, (k, agree)
     assert pg.ep_states.numel() == 0                                            # episode cleared (:176-179)
+
+
+# ------------------------------------------------------------------------------------------------
+# replay memories sampled on the device
+# ------------------------------------------------------------------------------------------------
+def _successive_inclusion(w, k):
+    """Exact inclusion probabilities of weighted sampling WITHOUT replacement (draw one by one, renormalise): what
+    np.random.choice(n, k, p=w/sum(w), replace=False) samples.  Exponential in k: tiny cases only."""
+    import itertools
+    n = len(w)
+    inc = np.zeros(n)
+    for perm in itertools.permutations(range(n), k):
+        p, rest = 1.0, w.sum()
+        for i in perm:
+            p *= w[i] / rest
+            rest -= w[i]
+        inc[list(perm)] += p
+    return inc
+
+
+def test_replay_uniform_sampling_is_a_permutation_prefix():
+    from rl_ctr_prediction_b200 import replay
+    rng = replay._rng(torch.device(DEV), seed=77)
+    for n, k in ((1, 1), (5, 5), (1000, 1000), (100000, 512), (1 << 20, 4096)):
+        idx = replay.sample_uniform(n, k, rng).cpu().numpy()
+        assert idx.min() >= 0 and idx.max() < n
+        assert len(np.unique(idx)) == k                                # distinct, like random.sample
+    # same (seed, counter) -> same draw; the counter moves with every call
+    a = replay.sample_uniform(5000, 64, replay._rng(torch.device(DEV), seed=5))
+    b = replay.sample_uniform(5000, 64, replay._rng(torch.device(DEV), seed=5))
+    assert torch.equal(a, b)
+    r = replay._rng(torch.device(DEV), seed=5)
+    c, d = replay.sample_uniform(5000, 64, r), replay.sample_uniform(5000, 64, r)
+    assert not torch.equal(c, d)
+    # uniform inclusion: every index of a pool of 50 is drawn ~ draws * k / n times
+    r = replay._rng(torch.device(DEV), seed=9)
+    n, k, draws = 50, 10, 4000
+    cnt = np.zeros(n)
+    for _ in range(draws):
+        cnt[replay.sample_uniform(n, k, r).cpu().numpy()] += 1
+    exp = draws * k / n
+    assert np.abs(cnt - exp).max() < 5 * np.sqrt(exp * (1 - k / n))
+    with pytest.raises(ValueError):
+        replay.sample_uniform(10, 11, r)
+
+
+def test_replay_memory_matches_reference_semantics():
+    """Memory.add wrap-around, gather, IS weights and greedy top-k against a numpy restatement of the reference's Memory
+    (v10_Hybrid_TD3_model_PER.py:19-110); stochastic_sample's inclusion frequencies against the exact successive-sampling law."""
+    from rl_ctr_prediction_b200 import replay
+    rs = np.random.default_rng(0)
+    size, T = 10, 3
+    mem = replay.Memory(size, T, DEV, seed=3)
+    ref_mem, ref_pr, counter = np.zeros((size, T), np.float32), np.zeros((size, 2), np.float32), 0
+    for n in (4, 4, 5, 7):                                            # the third and fourth writes wrap
+        tr = rs.standard_normal((n, T)).astype(np.float32)
+        td = np.abs(rs.standard_normal((n, 1))).astype(np.float32)
+        mem.add(torch.as_tensor(td), torch.as_tensor(tr))
+        for i in range(n):
+            ref_mem[(counter + i) % size] = tr[i]
+            ref_pr[(counter + i) % size] = td[i, 0]
+        counter += n
+    assert mem.memory_counter == counter
+    assert np.array_equal(mem.memory.cpu().numpy(), ref_mem) and np.array_equal(mem.prioritys_.cpu().numpy(), ref_pr)
+    # stochastic sample: distinct indices, rows = memory[idx], IS weights = (p / min p)^-beta with p = (|td| + eps)^alpha
+    mem.beta = 0.7
+    idx, batch, isw = mem.stochastic_sample(4)
+    i = idx.cpu().numpy()
+    assert len(np.unique(i)) == 4
+    assert np.array_equal(batch.cpu().numpy(), ref_mem[i])
+    pri = (np.abs(ref_pr[:, 0].astype(np.float64)) + 1e-3) ** 0.6
+    close(isw[:, 0], (pri[i] / pri.min()) ** -0.7, rtol=1e-5)
+    # inclusion frequencies == successive weighted sampling without replacement (np.random.choice(p=P, replace=False))
+    small = replay.Memory(6, 1, DEV, seed=11)
+    td6 = np.array([[0.05], [0.2], [0.4], [0.9], [1.5], [3.0]], np.float32)
+    small.add(torch.as_tensor(td6), torch.zeros(6, 1))
+    w = (np.abs(td6[:, 0].astype(np.float64)) + 1e-3) ** 0.6
+    inc = _successive_inclusion(w, 3)
+    draws, cnt = 6000, np.zeros(6)
+    for _ in range(draws):
+        cnt[small.stochastic_sample(3)[0].cpu().numpy()] += 1
+    freq = cnt / draws
+    assert np.abs(freq - inc).max() < 5 * np.sqrt(0.25 / draws), (freq, inc)
+    # greedy: the largest raw priorities, IS weights on the raw priorities
+    gi, gb, gw = mem.greedy_sample(3)
+    order = np.argsort(-ref_pr[:, 0], kind="stable")[:3]
+    assert np.array_equal(np.sort(gi.cpu().numpy()), np.sort(order))
+    close(gw[:, 0], (ref_pr[gi.cpu().numpy(), 0].astype(np.float64) / ref_pr[:, 0].min()) ** -mem.beta, rtol=1e-5)
+    # batch_update writes column 0 only
+    mem.batch_update(gi, torch.full((3, 1), 9.0))
+    ref_pr[gi.cpu().numpy(), 0] = 9.0
+    assert np.array_equal(mem.prioritys_.cpu().numpy(), ref_pr)
+
+
+def test_ddqn_device_sampling():
+    """DoubleDQN with device-side replay sampling (RingMemory.device_sampling): distinct in-range indices, stored rows back."""
+    from rl_ctr_prediction_b200 import DDQN_model
+    torch.manual_seed(3)
+    F_, D_ = 15, 10
+    agent = DDQN_model.DoubleDQN(300, F_, D_, action_nums=3, memory_size=256, batch_size=32, device=DEV)
+    rs = np.random.default_rng(1)
+    tr = torch.as_tensor(np.concatenate([rs.integers(0, 300, (200, F_)), rs.integers(2, 4, (200, 1)), rs.integers(0, 2, (200, 1))],
+                                        axis=1)).float().to(DEV)
+    agent.store_transition(tr)
+    agent._mem.device_sampling = True
+    idx = agent._mem.sample_index(32, DEV).cpu().numpy()
+    assert len(np.unique(idx)) == 32 and idx.min() >= 0 and idx.max() < 200
+    b_s, b_a, b_r, b_s_ = agent.sample_batch()                     # the learn step consumes these (all_main/main.py:300-306)
+    assert tuple(b_s.shape) == (32, F_) and tuple(b_a.shape) == (32, 1) and tuple(b_r.shape) == (32, 1)
+    rows = {tuple(r) for r in tr[:, :F_].long().cpu().numpy().tolist()}
+    assert all(tuple(r) in rows for r in b_s.cpu().numpy().tolist())
