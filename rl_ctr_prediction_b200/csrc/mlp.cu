@@ -500,18 +500,30 @@ gemv_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restric
         wk[c] = k < K ? __ldg(w + k) : 0.f;
         acc[c] = 0.f;
     }
-    for (int64_t r = r0 + wib; r < r1; r += 8) {
-        const float g = __ldg(gy + r);
-        gsum += g;
+    // four rows per trip: all of their loads are issued before the first use (the loop is latency-bound otherwise)
+    for (int64_t rb = r0 + wib; rb < r1; rb += 32) {
+        float g[4], xv[4][CMAX];
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            const int k = lane + 32 * c;
-            if (k < K) {
-                const float xv = __ldg(x + r * ldx + k);
-                acc[c] = fmaf(g, xv, acc[c]);
-                if (dx) {
-                    float v = g * wk[c];
-                    if (dx_mask) v = xv > 0.f ? v * dx_scale : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = rb + 8 * u;
+            g[u] = r < r1 ? __ldg(gy + r) : 0.f;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                const int k = lane + 32 * c;
+                xv[u][c] = (r < r1 && k < K) ? __ldg(x + r * ldx + k) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = rb + 8 * u;
+            gsum += g[u];
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                const int k = lane + 32 * c;
+                acc[c] = fmaf(g[u], xv[u][c], acc[c]);
+                if (dx && r < r1 && k < K) {
+                    float v = g[u] * wk[c];
+                    if (dx_mask) v = xv[u][c] > 0.f ? v * dx_scale : 0.f;
                     __stcs(dx + r * (int64_t)K + k, v);
                 }
             }
