@@ -261,6 +261,15 @@ size_t rlctr_rows_ws_bytes(int64_t n);
 int rlctr_sort_ids_sharded(const uint32_t* ids_all, int64_t n_all, int32_t world, int32_t rank, int64_t n_rows_global,
                            uint32_t* sorted_rows, uint32_t* sorted_slots, void* ws, size_t ws_bytes,
                            rlctr_stream_t stream);
+
+/* Gradient-side push (the write counterpart of the owner-side pull through rlctr_rowgrad.peer_*): rank `rank` writes row
+ * `slot` of its src[n, width] (per-occurrence gradient rows: DeepFM's tower-input gradients, width = dim) to
+ * peer_recv[owner(ids[slot])] + (rank * n + slot) * width.  peer_recv[r] = base of rank r's receive buffer
+ * [world * n, width] as mapped into THIS process.  After the step's barrier the owner reads only local memory: it passes
+ * rlctr_rowgrad.peer_extra[r] = its own receive buffer + r * n * width.  Posted NVLink writes instead of 2-3 us remote reads
+ * on the dependent path of every row.  Out-of-range ids are skipped; width even: 8-byte stores. */
+int rlctr_push_rows(const int64_t* ids, int64_t n, int32_t world, int32_t rank, int64_t n_rows_global, const float* src,
+                    int32_t width, void* const* peer_recv, rlctr_stream_t stream);
 int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                     const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
                     void* ws, size_t ws_bytes, rlctr_stream_t stream);

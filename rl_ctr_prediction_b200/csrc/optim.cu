@@ -191,12 +191,16 @@ __global__ void __launch_bounds__(256, 5)
 rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
                   GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
                   int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
-    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Blocks stride the positions (the launch caps the grid at ~1/world of them for a sharded table: 7 of 8 blocks of a full
+    // grid would start in the sentinel tail and exit, and launching 100K empty blocks costs more than the update itself).
+    const int64_t nblk = (n * LPR + blockDim.x - 1) / blockDim.x;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t gt = blk * blockDim.x + threadIdx.x;
     const int64_t k = gt / LPR;
     const int c = (int)(gt % LPR), col0 = 4 * c;
     // keys are sorted and everything this table does not own (out-of-range ids; for a sharded table the other ranks'
-    // ids, G-1 out of G positions) sorts last as a sentinel: a block that STARTS in that tail has nothing to do
-    const int64_t k_first = ((int64_t)blockIdx.x * blockDim.x) / LPR;
+    // ids, G-1 out of G positions) sorts last as a sentinel: a block that STARTS in that tail has nothing to do -- now or later
+    const int64_t k_first = (blk * blockDim.x) / LPR;
     if (k_first >= n || __ldg(sorted_ids + k_first) >= (uint64_t)t.n_rows) return;
     bool head = false;
     uint32_t id = 0, slot0 = 0;
@@ -239,6 +243,7 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
     if (APPLY == 0 && a.stamp) {
         __syncwarp();                                    // all chunk lanes read the stamp before lane 0 rewrites it
         if (work && c == 0) a.stamp[id] = step;
+    }
     }
 }
 
@@ -545,11 +550,10 @@ template <int APPLY>
 __global__ void __launch_bounds__(256)
 rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
                    GradView g, TableView t, AdamView a, float* __restrict__ dense_grad) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t id = __ldg(sorted_ids + k);
-    if (id >= (uint64_t)t.n_rows) return;                 // sentinel tail
-    if (k > 0 && __ldg(sorted_ids + k - 1) == id) return;
+    if (id >= (uint64_t)t.n_rows) return;                 // sentinel tail: nothing for this thread here or further on
+    if (k > 0 && __ldg(sorted_ids + k - 1) == id) continue;
     float acc = 0.f;
     int64_t kk = k;
     uint32_t nxt = id;
@@ -562,7 +566,7 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
         if (q.dlogit) gsl += __ldg(q.dlogit + q.slot / (uint32_t)g.fields);
         acc += gsl;
     }
-    if (APPLY == 1) { dense_grad[id] = acc; return; }
+    if (APPLY == 1) { dense_grad[id] = acc; continue; }
     const int step = __ldg(a.step) + 1;
     const int64_t o = (int64_t)id * t.pitch;
     float p = t.data[o], m = a.m[o], v = a.v[o];
@@ -574,6 +578,7 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     const float2 sc = __ldg(&a.sched[step]);
     adam_elem(p, m, v, acc, a.h, sc.x, sc.y);
     t.data[o] = p; a.m[o] = m; a.v[o] = v;
+    }
 }
 __global__ void __launch_bounds__(256)
 rows_catchup_scalar_kernel(const uint32_t* __restrict__ sorted_ids, int64_t n, TableView t, AdamView a) {
@@ -619,6 +624,14 @@ struct RowsWs {
 };
 static inline size_t rows_ws_bytes(int64_t n) { return 16 + sizeof(uint32_t) * (size_t)(n / LONG_RUN + 1); }
 
+// Sharded table: an owner meets ~1/world of the n gathered positions (the rest are sentinels at the end of the sorted view), so
+// the grid covers 1.25/world of them + a margin and the kernels stride: any excess (skewed ownership) takes another trip.
+static inline unsigned capped_blocks(int64_t full, int world) {
+    if (world <= 1) return (unsigned)full;
+    int64_t cap = full / world + full / (4 * world) + 2 * RLCTR_SMS;
+    return (unsigned)(cap < full ? cap : full);
+}
+
 template <int APPLY>
 static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_rowgrad* grad,
                        const rlctr_table* table, const rlctr_adam* opt, float* dense_grad, void* ws, size_t ws_bytes,
@@ -638,7 +651,8 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
     if ((g.flags & RLCTR_DZ_IN_SUMS) && (t.rs <= t.used || !g.sums)) return RLCTR_EINVAL;
     if (t.rs == 1) {
         if (grad->extra || grad->sums) return RLCTR_EUNSUPPORTED;
-        rows_scalar_kernel<APPLY><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad);
+        rows_scalar_kernel<APPLY><<<capped_blocks((n + 255) / 256, grad->world), 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a,
+                                                                                              dense_grad);
         RLCTR_LAUNCH_CHECK();
         return RLCTR_OK;
     }
@@ -652,7 +666,7 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
     RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
     RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
     const int lpr = rlctr_lanes_per_row(t.rs);
-    const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
+    const unsigned blocks = capped_blocks((n * lpr + 255) / 256, grad->world);
 #define LAUNCH_ROWS(L)                                                                                              \
     rows_short_kernel<L, APPLY><<<blocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad,           \
                                                         w.long_count, w.long_list);                                \

@@ -85,3 +85,51 @@ extern "C" int rlctr_bucket_by_owner(const int64_t* ids, int64_t n, int32_t worl
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
+
+// ---- gradient-side push: the source rank WRITES what an owner needs into the owner's memory ---------------------------------
+// Owners used to PULL the per-occurrence gradient rows of remote samples inside the update kernel: 40-600 byte reads with a
+// 2-3 us NVLink round trip each, on the dependent path of every row -- latency-bound (rows_adam 0.14 -> 0.36 ms at 8 GPUs).
+// Remote WRITES are posted: the source streams row `slot` of its [n, width] array to recv[rank * n + slot] in the memory of
+// owner(ids[slot]) and moves on; after the step's barrier the owner's kernel reads only local memory (peer_*[r] = recv + r*n*width).
+namespace rlctr {
+
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const int64_t* __restrict__ ids, int64_t n, int mask, int64_t n_rows, const float* __restrict__ src, int width,
+                 ShardView recv, int64_t base) {
+    const int vec = (width % 2 == 0) ? 2 : 1;
+    const int per = width / vec;
+    const int64_t total = n * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t slot = i / per;
+        const int j = (int)(i - slot * per);
+        const int64_t id = __ldg(ids + slot);
+        if ((uint64_t)id >= (uint64_t)n_rows) continue;                      // out-of-range ids own nothing
+        float* dst = const_cast<float*>(recv.peers[id & mask]) + (base + slot) * width;
+        if (vec == 2) reinterpret_cast<float2*>(dst)[j] = __ldg(reinterpret_cast<const float2*>(src + slot * width) + j);
+        else dst[j] = __ldg(src + slot * width + j);
+    }
+}
+
+}  // namespace rlctr
+
+extern "C" int rlctr_push_rows(const int64_t* ids, int64_t n, int32_t world, int32_t rank, int64_t n_rows_global, const float* src,
+                               int32_t width, void* const* peer_recv, rlctr_stream_t stream) {
+    if (!ids || !src || !peer_recv || n < 0 || width <= 0 || n_rows_global <= 0) return RLCTR_EINVAL;
+    if (world != 2 && world != 4 && world != 8) return RLCTR_EUNSUPPORTED;
+    if (rank < 0 || rank >= world) return RLCTR_EINVAL;
+    if ((((uintptr_t)src) & 7u) != 0) return RLCTR_EALIGN;
+    ShardView sv;
+    sv.shift = 0; sv.mask = world - 1;
+    for (int r = 0; r < RLCTR_MAX_WORLD; ++r) sv.peers[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_recv[r] || (((uintptr_t)peer_recv[r]) & 7u) != 0) return RLCTR_EINVAL;
+        sv.peers[r] = reinterpret_cast<const float*>(peer_recv[r]);
+    }
+    if (n == 0) return RLCTR_OK;
+    const int per = width % 2 == 0 ? width / 2 : width;
+    int64_t blocks = (n * per + 255) / 256;
+    const int grid = (int)(blocks < RLCTR_SMS * 16 ? blocks : RLCTR_SMS * 16);
+    push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ids, n, world - 1, n_rows_global, src, width, sv, (int64_t)rank * n);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}

@@ -25,6 +25,7 @@ is bit-identical from run to run and equal to the single-GPU step on the concate
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -151,6 +152,13 @@ class ShardedCTR(nn.Module):
         self._stash = None
         self._ws = {}
         self._gbuf = {}
+        self._xbuf = {}
+        # how the owners get the gradient side of remote samples: "push" = replicate the per-sample rows (dlogit / column sums)
+        # with one all_gather and let the source ranks WRITE the per-occurrence rows (DeepFM's tower-input gradients) into the
+        # owners' memory, so that the update kernel reads local memory only; "pull" = the owners read everything through the peer
+        # mapping inside the update kernel (2-3 us NVLink round trips on its dependent path; kept for comparison and for FFM's
+        # 600-byte partner rows)
+        self.exchange = os.environ.get("RLCTR_SHARD_EXCHANGE", "push")
 
     # ---- protocol shared with optim.Adam --------------------------------------------------------
     def _apply(self, fn, recurse=True):
@@ -252,6 +260,25 @@ class ShardedCTR(nn.Module):
         self._gbuf[B] = buf
         return buf
 
+    def _exchange_buffers(self, B, F):
+        """Receive side of the "push" exchange for batch size B: the all-gathered per-sample rows of every rank (plain local
+        tensors) and the symmetric buffer the sources write DeepFM's per-occurrence rows into."""
+        xb = self._xbuf.get(B)
+        if xb is not None:
+            return xb
+        g, dev, G = self._geom, self.table.device, self.world
+        bp = (B + 3) // 4 * 4
+        xb = {"dlogit_all": torch.empty(G * bp, dtype=torch.float32, device=dev), "bp": bp, "sums_all": None, "recv": None}
+        if self._kind == "fm":
+            xb["sums_all"] = torch.empty(G * B * g.row_stride, dtype=torch.float32, device=dev)
+        if self.kind == "DeepFM":
+            pm = PeerMemory(G * B * F * g.dim, torch.float32, dev, self.group)
+            pm.local.zero_()
+            xb["recv"] = pm
+            xb["recv_ptrs"] = (C.c_void_p * 8)(*[int(p) for p in pm.ptrs])
+        self._xbuf[B] = xb
+        return xb
+
     # ---- the step ---------------------------------------------------------------------------------
     def _interact(self, x, buf, train):
         """The single-GPU interaction kernels reading rows through the peer table.  Returns (logit[B], tower rows)."""
@@ -344,11 +371,28 @@ class ShardedCTR(nn.Module):
             for p in dense:
                 p.grad = flat[o:o + p.numel()].view_as(p).clone()
                 o += p.numel()
-        self.barrier()                                        # B2: every rank's gradient-side buffers are complete
         peer = None
         if self.world > 1:
             peer = {"world": self.world, "n_per_rank": B * F, "staged": buf["staged_ptrs"], "dlogit": buf["dlogit_ptrs"],
                     "sums": buf["sums_ptrs"], "extra": buf["extra_ptrs"]}
+            if self.exchange == "push":
+                xb = self._exchange_buffers(B, F)
+                g = self._geom
+                if dz_in_sums:                                # dlogit rides in the sums rows: one all_gather serves both
+                    dist.all_gather_into_tensor(xb["sums_all"], buf["sums"], group=self.group)
+                    per = 4 * B * g.row_stride
+                    peer["sums"] = [xb["sums_all"].data_ptr() + r * per for r in range(self.world)]
+                    peer["dlogit"] = [xb["dlogit_all"].data_ptr() + r * 4 * xb["bp"] for r in range(self.world)]   # not read
+                else:
+                    dist.all_gather_into_tensor(xb["dlogit_all"], buf["dlogit"], group=self.group)
+                    peer["dlogit"] = [xb["dlogit_all"].data_ptr() + r * 4 * xb["bp"] for r in range(self.world)]
+                if xb["recv"] is not None:                    # per-occurrence rows: posted writes into the owners' memory
+                    n = B * F
+                    _lib.call("rlctr_push_rows", lib.rlctr_push_rows, _lib.ptr(x), n, self.world, self.rank, self.feature_nums,
+                              _lib.ptr(buf["extra"]), g.dim, xb["recv_ptrs"], st, meta={"n": n, "width": g.dim})
+                    mine = xb["recv"].local.data_ptr()
+                    peer["extra"] = [mine + r * 4 * n * g.dim for r in range(self.world)]
+        self.barrier()                                        # B2: every rank's gradient-side buffers are complete
         self._stash = Model.RowsStash(sorted_ids=srows, sorted_slots=sslots, n=n_all, dlogit=dlogit, sums=buf["sums"],
                                       extra=buf["extra"], staged=buf["staged"], fields=F,
                                       flags=(_lib.RLCTR_STAGED_PARTNER if buf["staged"] is not None else 0) |
