@@ -293,6 +293,11 @@ int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
 int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                      const float* sched, const int32_t* step, double beta1, double beta2, double eps,
                      double weight_decay, rlctr_stream_t stream);
+/* The same step for up to RLCTR_DENSE_MAX tensors in one launch (host arrays of device pointers / sizes; torch's foreach Adam). */
+#define RLCTR_DENSE_MAX 24
+int rlctr_dense_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs, float* const* exp_avg_sqs,
+                           const int64_t* sizes, int32_t count, const float* sched, const int32_t* step, double beta1, double beta2,
+                           double eps, double weight_decay, rlctr_stream_t stream);
 int rlctr_step_advance(int32_t* step, int32_t delta, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ RLCTR_FM_TERM = 1
 RLCTR_STAGED_PARTNER = 1
 RLCTR_DZ_IN_SUMS = 2
 RLCTR_REDUCE_WS_BYTES = 16640
+RLCTR_DENSE_MAX = 24
 RLCTR_MLP_RELU = 1
 RLCTR_MLP_DROPOUT = 2
 RLCTR_MLP_DX_MASK = 4
@@ -89,6 +90,7 @@ SIGNATURES = {
     "rlctr_rows_catchup": (C.c_int, [_P, _I64, _TP, _AP, _P]),
     "rlctr_adam_flush": (C.c_int, [_TP, _AP, _I64, _I64, _P]),
     "rlctr_dense_adam": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F, _F, _F, _F, _P]),
+    "rlctr_dense_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _F, _F, _F, _F, _P]),
     "rlctr_step_advance": (C.c_int, [_P, _I32, _P]),
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),

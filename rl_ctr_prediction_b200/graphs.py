@@ -28,6 +28,8 @@ def eager_step(model, optimizer, loss_fn, x, y):
     from . import pretrain_main as PM
     if hasattr(model, "train_step"):           # sharded.ShardedCTR: the row-sharded step (device barriers, no host sync)
         return model.train_step(x, y, optimizer).detach()
+    if hasattr(model, "logit") and type(loss_fn) is torch.nn.BCELoss and loss_fn.reduction == "mean" and loss_fn.weight is None:
+        return fused_logit_step(model, optimizer, x, y)  # tower models: autograd for the tower, fused sigmoid + BCE head
     if getattr(model, "mlp", None) is not None:          # DeepFM, W&D, FNN, IPNN: the tower goes through autograd
         p = model(x)
         tl = loss_fn(p, y.reshape(-1, 1).float())
@@ -36,6 +38,29 @@ def eager_step(model, optimizer, loss_fn, x, y):
         optimizer.step()
         return tl.detach()             # keep no autograd graph alive between steps (its nodes pin a stream)
     return PM.fused_train_step(model, optimizer, x, y)
+
+
+def fused_logit_step(model, optimizer, x, y):
+    """The loop body of src/main/pretrain_main.py:96-102 for a model with a dense tail (DeepFM, W&D, FNN, IPNN, OPNN, DCN, AFM):
+    ``model.logit(x)`` through autograd, then sigmoid + ``nn.BCELoss`` and their gradient in ONE library call
+    (rlctr_bce_fwd_bwd: torch's clamped-log arithmetic) instead of torch's eight elementwise / reduction kernels,
+    then ``logit.backward(dlogit)`` and the optimizer step.  Same numbers as ``loss(model(x), y); backward()``."""
+    lib = _lib.load()
+    z = model.logit(x)
+    B = z.shape[0]
+    dev = z.device
+    zz = z.detach().reshape(-1).contiguous()
+    yy = y.reshape(-1).contiguous()
+    yi = yy if yy.dtype == torch.int64 else None
+    yf = None if yi is not None else yy.float()
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dlogit = torch.empty(B, dtype=torch.float32, device=dev)
+    _lib.check(lib.rlctr_bce_fwd_bwd(_lib.ptr(zz), _lib.ptr(yi), _lib.ptr(yf), None, _lib.ptr(loss), _lib.ptr(dlogit), None,
+                                     _lib.ptr(model._reduce_ws(dev)), B, _lib.stream()), "rlctr_bce_fwd_bwd")
+    model.zero_grad()
+    z.backward(dlogit.view_as(z))
+    optimizer.step()
+    return loss.reshape(())
 
 
 class Prefetched:

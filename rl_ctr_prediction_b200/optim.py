@@ -104,16 +104,22 @@ class Adam:
                 self._dense_sched = AdamSchedule(self.lr, self.betas, dev)
                 self._dense_done = 0
             self._dense_sched.ensure(self._dense_done + 2)
+            grads = []
             for p in live:
-                state = self._dense_state.get(p)
-                if state is None:
-                    state = (torch.zeros_like(p.data), torch.zeros_like(p.data))
-                    self._dense_state[p] = state
-                grad = p.grad.contiguous()
-                _lib.check(lib.rlctr_dense_adam(_lib.ptr(p.data), _lib.ptr(grad), _lib.ptr(state[0]), _lib.ptr(state[1]),
-                                                p.numel(), _lib.ptr(self._dense_sched.tensor), _lib.ptr(self._dense_step),
-                                                self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
-                           "rlctr_dense_adam")
+                if self._dense_state.get(p) is None:
+                    self._dense_state[p] = (torch.zeros_like(p.data), torch.zeros_like(p.data))
+                grads.append(p.grad.contiguous())
+            for lo in range(0, len(live), _lib.RLCTR_DENSE_MAX):          # one launch per group of tensors (foreach Adam)
+                grp, gg = live[lo:lo + _lib.RLCTR_DENSE_MAX], grads[lo:lo + _lib.RLCTR_DENSE_MAX]
+                k = len(grp)
+                arr = lambda xs: (C.c_void_p * k)(*[x.data_ptr() for x in xs])
+                sizes = (C.c_int64 * k)(*[p.numel() for p in grp])
+                _lib.check(lib.rlctr_dense_adam_multi(arr([p.data for p in grp]), arr(gg),
+                                                      arr([self._dense_state[p][0] for p in grp]),
+                                                      arr([self._dense_state[p][1] for p in grp]), sizes, k,
+                                                      _lib.ptr(self._dense_sched.tensor), _lib.ptr(self._dense_step),
+                                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
+                           "rlctr_dense_adam_multi")
             _lib.check(lib.rlctr_step_advance(_lib.ptr(self._dense_step), 1, st), "rlctr_step_advance")
             self._dense_done += 1
 

@@ -362,9 +362,13 @@ class DeepFM(FM):
         self.field_nums = int(field_nums)
         self.mlp = _tower(self.field_nums * self.latent_dims, device)
 
-    def forward(self, x):
+    def logit(self, x):
+        """Pre-sigmoid output [B, 1] (graphs.eager_step feeds it to the fused sigmoid + BCE head)."""
         z_fm, rows = self._run(x, True, False)
-        return torch.sigmoid(z_fm + self.mlp(rows))
+        return z_fm + self.mlp(rows)
+
+    def forward(self, x):
+        return torch.sigmoid(self.logit(x))
 
 
 class _PairDots(torch.autograd.Function):
@@ -417,9 +421,12 @@ class WideAndDeep(_TableModel):
         g = self._geom
         return [("linear.weight", g.lin_col, 1), ("embedding.weight", g.emb_col, g.dim)]
 
-    def forward(self, x):
+    def logit(self, x):
         z, rows = self._run(x, True, False)
-        return torch.sigmoid(z + self.mlp(rows))
+        return z + self.mlp(rows)
+
+    def forward(self, x):
+        return torch.sigmoid(self.logit(x))
 
 
 class FNN(_TableModel):
@@ -450,9 +457,12 @@ class FNN(_TableModel):
     def _tower_input(self, rows):
         return rows
 
-    def forward(self, x):
+    def logit(self, x):
         _, rows = self._run(x, True, False)
-        return torch.sigmoid(self.mlp(self._tower_input(rows)))
+        return self.mlp(self._tower_input(rows))
+
+    def forward(self, x):
+        return torch.sigmoid(self.logit(x))
 
 
 class InnerPNN(FNN):
@@ -577,13 +587,16 @@ class DCN(_TableModel):
         g = self._geom
         return [("feature_embedding.weight", g.emb_col, g.dim)]
 
-    def forward(self, x):
+    def logit(self, x):
         _, rows = self._run(x, True, False)
         W = torch.cat([m.weight for m in self.cross_net_w], dim=0)
         Bv = torch.stack(list(self.cross_net_b), dim=0)
         cn_x = _CrossNet.apply(rows, W, Bv)
         dn_x = self.DN(rows)
-        return torch.sigmoid(self.linear(torch.cat([cn_x, dn_x], dim=1)))              # :430-435
+        return self.linear(torch.cat([cn_x, dn_x], dim=1))                              # :430-433
+
+    def forward(self, x):
+        return torch.sigmoid(self.logit(x))                                             # :435
 
 
 class _AFMAttention(torch.autograd.Function):
@@ -665,6 +678,9 @@ class AFM(_TableModel):
         return st
 
     def forward(self, x, masks=None):
+        return torch.sigmoid(self.logit(x, masks))
+
+    def logit(self, x, masks=None):
         z, rows = self._run(x, True, False)
         packed = torch.cat([self.attention_net.weight.reshape(-1), self.attention_net.bias,
                             self.attention_softmax.weight.reshape(-1), self.attention_softmax.bias,
@@ -672,4 +688,4 @@ class AFM(_TableModel):
         p = float(self.dropout_p)
         rng = self._rng_state(rows.device) if (p > 0.0 and masks is None) else None
         y = _AFMAttention.apply(rows, packed, self.field_nums, self.latent_dims, p, rng, masks)
-        return torch.sigmoid(z + y)
+        return z + y

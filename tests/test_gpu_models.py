@@ -646,3 +646,34 @@ def test_pairdots_kernels_against_torch():
     assert torch.equal(out[:, :150], buf[:, :150])
     close(out, ref.detach(), rtol=1e-6)
     close(rows.grad, e.grad.view(Bt, -1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["DeepFM", "W&D", "IPNN", "DCN"])
+def test_fused_logit_step_equals_autograd_loop_body(golden, name):
+    """graphs.eager_step for a tower model (model.logit through autograd + ONE fused sigmoid/BCE/gradient call, multi-tensor dense
+    Adam) gives the numbers of the reference loop body ``loss(model(x), y); zero_grad(); backward(); step()`` with nn.BCELoss."""
+    import copy
+    from rl_ctr_prediction_b200 import graphs, optim
+    torch.manual_seed(11)
+    a = build(name, 255)
+    with torch.no_grad():
+        a.table.mul_(0.1)
+    a = a.to(DEV).eval()                         # dropout off: the two paths would draw different masks
+    b = build(name, 255).to(DEV).eval()
+    b.load_state_dict(copy.deepcopy(a.state_dict()))
+    oa = optim.Adam(a.parameters(), lr=1e-3, weight_decay=1e-5)
+    ob = optim.Adam(b.parameters(), lr=1e-3, weight_decay=1e-5)
+    lossf = torch.nn.BCELoss()
+    for s in range(3):
+        x = torch.as_tensor(golden["train/x"][s]).to(DEV)
+        y = torch.as_tensor(golden["train/y"][s]).to(DEV)
+        la = graphs.eager_step(a, oa, lossf, x, y)
+        p = b(x)
+        lb = lossf(p, y.reshape(-1, 1).float())
+        b.zero_grad()
+        lb.backward()
+        ob.step()
+        close(la, lb.detach())
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sb:
+        close(sa[k], sb[k], rtol=2e-5, atol=max(2e-5 * float(sb[k].abs().max()), 5e-6))
