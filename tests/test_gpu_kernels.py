@@ -574,14 +574,25 @@ def padded(x, ld):
     return buf
 
 
+# GEMM data paths behind environment switches (csrc/mlp_tma.cu): "tma" = the default (A operand in tensor memory, C stored by TMA),
+# "tma_smemA" = A read from shared memory + per-thread stores of C (the previous generation), "tma_pair" = the weight tile
+# multicast to a CTA pair, "staged" = the software-staged kernel of csrc/mlp.cu.
+def gemm_path(monkeypatch, path):
+    monkeypatch.setenv("RLCTR_GEMM_TMA", "0" if path == "staged" else "1")
+    monkeypatch.setenv("RLCTR_GEMM_A_TMEM", "0" if path == "tma_smemA" else "1")
+    monkeypatch.setenv("RLCTR_GEMM_C_TMA", "0" if path == "tma_smemA" else "1")
+    monkeypatch.setenv("RLCTR_GEMM_CLUSTER", "2" if path == "tma_pair" else "1")
+    return "tma" if path.startswith("tma") else "staged"
+
+
 # path: "tma" = 16-byte aligned pitch + workspace (TMA-fed kernel, csrc/mlp_tma.cu); "staged" = RLCTR_GEMM_TMA=0, dense x
 # (software-staged kernel, csrc/mlp.cu: what any shape TMA cannot address falls back to).  K = 150 / 255 are not multiples of 4: "tma" pads the pitch.
 @pytest.mark.parametrize("B,K,N", [(1, 150, 300), (128, 32, 16), (1000, 150, 300), (777, 300, 200), (513, 200, 1),
                                    (4096, 255, 1024), (300, 1024, 512), (65536, 150, 300)])
 @pytest.mark.parametrize("relu", [0, 1])
-@pytest.mark.parametrize("path", ["tma", "staged"])
+@pytest.mark.parametrize("path", ["tma", "tma_smemA", "tma_pair", "staged"])
 def test_linear_fwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
-    monkeypatch.setenv("RLCTR_GEMM_TMA", "1" if path == "tma" else "0")
+    path = gemm_path(monkeypatch, path)
     x, w, b = linear_case(B, K, N, B + K + N)
     y = torch.empty(B, N, device=DEV)
     if path == "tma":

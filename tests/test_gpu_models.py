@@ -677,3 +677,80 @@ def test_fused_logit_step_equals_autograd_loop_body(golden, name):
     sa, sb = a.state_dict(), b.state_dict()
     for k in sb:
         close(sa[k], sb[k], rtol=2e-5, atol=max(2e-5 * float(sb[k].abs().max()), 5e-6))
+
+
+@pytest.mark.parametrize("Bt", [1, 2, 33])
+def test_dense_tails_small_batches(Bt):
+    """Ragged ends: the last DataLoader batch of an epoch can have any size (drop_last is never set).  B = 1, 2, 33
+    through every new tail kernel (AFM attention, DCN cross network, OuterPNN term, pair dots, single-output backward) against
+    fp64 autograd of the reference expressions."""
+    from rl_ctr_prediction_b200 import mlp, p_model
+    torch.manual_seed(20 + Bt)
+    Ft, Dt, L = 15, 10, 5
+    fd, npair = Ft * Dt, Ft * (Ft - 1) // 2
+    rows = (torch.randn(Bt, fd, device=DEV) * 0.5).requires_grad_(True)
+    # AFM
+    packed = (torch.randn(Dt * Dt + 3 * Dt + 2, device=DEV) * 0.4).requires_grad_(True)
+    g1 = torch.randn(Bt, 1, device=DEV)
+    y = p_model._AFMAttention.apply(rows, packed, Ft, Dt, 0.0, None, None)
+    y.backward(g1)
+    r64, p64 = rows.detach().double().requires_grad_(True), packed.detach().double().requires_grad_(True)
+    ref = _afm_torch(r64, p64, Ft, Dt, torch.ones(Bt, npair + Dt, device=DEV, dtype=torch.float64))
+    ref.backward(g1.double())
+    close(y, ref.detach(), rtol=1e-5)
+    close(rows.grad, r64.grad, rtol=1e-5)
+    close(packed.grad, p64.grad, rtol=1e-5)
+    # DCN cross network
+    rows.grad = None
+    W = (torch.randn(L, fd, device=DEV) * 0.1).requires_grad_(True)
+    Bv = (torch.randn(L, fd, device=DEV) * 0.1).requires_grad_(True)
+    g2 = torch.randn(Bt, fd, device=DEV)
+    out = p_model._CrossNet.apply(rows, W, Bv)
+    out.backward(g2)
+    r64, W64, B64 = (t.detach().double().requires_grad_(True) for t in (rows, W, Bv))
+    xl = r64
+    for l in range(L):
+        xl = r64 * (xl @ W64[l]).unsqueeze(1) + B64[l] + xl
+    xl.backward(g2.double())
+    close(out, xl.detach(), rtol=1e-5)
+    close(rows.grad, r64.grad, rtol=1e-5)
+    close(W.grad, W64.grad, rtol=1e-5)
+    close(Bv.grad, B64.grad, rtol=1e-5)
+    # OuterPNN term and InnerPNN pair dots
+    for fn, width in ((p_model._FieldSq, fd + Dt), (p_model._PairDots, fd + npair)):
+        rows.grad = None
+        g3 = torch.randn(Bt, width, device=DEV)
+        o = fn.apply(rows, Ft, Dt)
+        o.backward(g3)
+        e = rows.detach().double().view(Bt, Ft, Dt).requires_grad_(True)
+        if fn is p_model._FieldSq:
+            se = e.sum(dim=1)
+            r = torch.cat([e.view(Bt, fd), Dt * se * se], dim=1)
+        else:
+            idx = torch.triu_indices(Ft, Ft, offset=1)
+            r = torch.cat([e.view(Bt, fd), (e[:, idx[0]] * e[:, idx[1]]).sum(dim=2)], dim=1)
+        r.backward(g3.double())
+        close(o, r.detach(), rtol=1e-5)
+        close(rows.grad, e.grad.view(Bt, fd), rtol=1e-5)
+    # tower with a single-output last layer (one-pass backward kernel)
+    torch.manual_seed(3)
+    tower = p_model._tower(fd, DEV).eval()
+    x = (torch.randn(Bt, fd, device=DEV)).requires_grad_(True)
+    yt = tower(x)
+    gt = torch.randn(Bt, 1, device=DEV)
+    yt.backward(gt)
+    ref_t = torch.nn.Sequential(*[torch.nn.Linear(m.in_features, m.out_features) if isinstance(m, mlp.Linear) else type(m)()
+                                  for m in tower if not isinstance(m, torch.nn.Dropout)]).double().to(DEV)
+    lin_src = [m for m in tower if isinstance(m, mlp.Linear)]
+    lin_dst = [m for m in ref_t if isinstance(m, torch.nn.Linear)]
+    for s_, d_ in zip(lin_src, lin_dst):
+        d_.weight.data.copy_(s_.weight.data.double())
+        d_.bias.data.copy_(s_.bias.data.double())
+    x64 = x.detach().double().requires_grad_(True)
+    y64 = ref_t(x64)
+    y64.backward(gt.double())
+    close(yt, y64.detach(), rtol=1e-5)
+    close(x.grad, x64.grad, rtol=1e-5)
+    for s_, d_ in zip(lin_src, lin_dst):
+        close(s_.weight.grad, d_.weight.grad, rtol=1e-5)
+        close(s_.bias.grad, d_.bias.grad, rtol=1e-5)
