@@ -75,10 +75,14 @@ def tensor_peak():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {      # profiles/r1_ncu_top_kernels.md (B=65536, N=10M, D=10); bytes per launch
-    "rlctr_rows_adam[FM]": 246.4e6 + 136.4e6, "rlctr_rows_adam[DeepFM]": 295.3e6 + 137.9e6,
-    "rlctr_rows_catchup[FM]": 238.6e6 + 122.5e6, "rlctr_rows_catchup[DeepFM]": 238.7e6 + 122.3e6,
-    "rlctr_embed_fwd[FM]": 128.7e6 + 5.6e6, "rlctr_embed_fwd[DeepFM]": 130.4e6 + 22.5e6,
+NCU_TRAFFIC = {      # profiles/r1e_ncu_top_kernels.md (B=65536, N=10M, D=10); bytes per launch
+    "rlctr_rows_adam[FM]": 246.4e6 + 137.3e6, "rlctr_rows_adam[DeepFM]": 295.7e6 + 137.6e6,
+    "rlctr_rows_catchup[FM]": 238.7e6 + 124.7e6, "rlctr_rows_catchup[DeepFM]": 238.8e6 + 123.7e6,
+    "rlctr_embed_fwd[FM]": 128.6e6 + 5.7e6, "rlctr_embed_fwd[DeepFM]": 130.5e6 + 23.0e6,
+    # the tower's calls, summed over their kernels (same capture): forward = 150->300, 300->200 GEMMs (+ the 200->1 GEMV, not captured);
+    # backward = gemv_bwd + layer-2 dgrad, wgrad + layer-1 dgrad, wgrad
+    "rlctr_linear_fwd": (40.3e6 + 24.4e6) + (79.2e6 + 22.1e6),
+    "rlctr_linear_bwd": (52.7e6 + 7.1e6) + (131.7e6 + 46.2e6) + (131.2e6 + 6.5e6) + (79.5e6 + 4.8e6) + (118.6e6 + 5.1e6),
 }
 
 
@@ -410,7 +414,10 @@ def b200_arm(args):
         tot_fl = sum(3 * gemm_flops(k, m) for k in keys for _, _, m in prof.records[k])
         achieved = tot_fl / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": top + " (gemm3x_tma_kernel: all tower layers)", "achieved": achieved, "peak": tpeak,
-                "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tpeak_src,
+                "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": NCU_TRAFFIC.get(top),
+                "traffic_note": "DRAM bytes (ncu dram__bytes_read+write) of ALL kernels of this entry point in one step, B=65536 "
+                                "(profiles/r1e_ncu_top_kernels.md); achieved / peak are FLOP rates over the same kernels",
+                "peak_source": tpeak_src,
                 "flops_counted": "3 tf32 MMAs per fp32 product (3xTF32 split)", "share_of_step": groups[top] / Kp / step_ms}
     elif top is not None:
         keys = [k for k in kern if k.split("[")[0] == top]
