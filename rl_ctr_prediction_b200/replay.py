@@ -99,7 +99,7 @@ class Memory(object):
         return self._sample(batch_size, False)
 
     def greedy_sample(self, batch_size):                                         # :87-105 (top-batch of column 0)
-        self.beta = min(1.0, self.beta + self.beta_increment_per_sampling)      # :94
+        self.beta = torch.min(torch.FloatTensor([1., self.beta + self.beta_increment_per_sampling])).item()   # fp32, as the reference      # :94
         return self._sample(batch_size, True)
 
     def batch_update(self, choose_idx, td_errors):                               # :107-108

@@ -46,3 +46,10 @@ def state_from_golden(golden, prefix):
     """Collect {state_dict_key: ndarray} stored under `prefix/`."""
     pre = prefix.rstrip("/") + "/"
     return {k[len(pre):]: golden[k] for k in golden.files if k.startswith(pre)}
+
+
+@pytest.fixture(scope="session")
+def golden_sac():
+    """Hybrid SAC networks / prioritized memory from the real reference (tests/golden/make_golden_sac.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden_sac.npz")
+    return np.load(path, allow_pickle=False)
