@@ -53,3 +53,10 @@ def golden_sac():
     """Hybrid SAC networks / prioritized memory from the real reference (tests/golden/make_golden_sac.py)."""
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_sac.npz")
     return np.load(path, allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_heads():
+    """Hybrid TD3 (v10) / PPO network heads from the real reference (tests/golden/make_golden_heads.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden_heads.npz")
+    return np.load(path, allow_pickle=False)

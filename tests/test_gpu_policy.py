@@ -453,3 +453,88 @@ def test_sac_learn_steps_run(golden_sac):
     assert float(a1.c_log_alpha.detach()) != 0.0 and float(a1.d_log_alpha.detach()) != 0.0
     pr = a1.memory.priorities_[:, 0].cpu().numpy()
     assert (pr[:18] != 1.0).all() and (pr[18:40] == 1.0).all()            # rows 0..17 were sampled and re-prioritised
+
+
+# ------------------------------------------------------------------------------------------------
+# TD3 (v10) and PPO network heads against the real reference
+# ------------------------------------------------------------------------------------------------
+def _load_init(mod, g, prefix):
+    sd = state_from_golden(g, prefix)
+    assert set(mod.state_dict().keys()) == set(sd.keys()), (sorted(mod.state_dict().keys()), sorted(sd.keys()))
+    mod.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    return mod.to(DEV)
+
+
+def _check_grads(mod, g, prefix, rtol=1e-5):
+    gscale = max(float(np.abs(g[f"{prefix}/{k}"]).max()) for k, _ in mod.named_parameters())
+    for k, p in mod.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        close(got, g[f"{prefix}/{k}"], rtol=rtol, atol=rtol * gscale)
+
+
+def test_td3_heads_match_reference(golden_heads):
+    from rl_ctr_prediction_b200 import v10_Hybrid_TD3_model_PER as T
+    g = golden_heads
+    s = torch.as_tensor(g["in/state"]).to(DEV)
+    ca = torch.as_tensor(g["in/c_actions"]).to(DEV)
+    da = torch.as_tensor(g["in/d_actions"]).to(DEV)
+    in_dims, A = s.shape[1], ca.shape[1]
+    cr = _load_init(T.Hybrid_Critic(in_dims, A), g, "td3_critic/init").train()
+    q1, q2 = cr.evaluate(s, ca, da)
+    close(q1, g["td3_critic/q1"])
+    close(q2, g["td3_critic/q2"])
+    tgt = torch.as_tensor(g["td3_critic/target"]).to(DEV)
+    loss = (torch.nn.functional.mse_loss(q1, tgt, reduction="none") + torch.nn.functional.mse_loss(q2, tgt, reduction="none")).mean()
+    close(loss, g["td3_critic/loss"])
+    cr.zero_grad()
+    loss.backward()
+    _check_grads(cr, g, "td3_critic/grad")
+    for k, v in state_from_golden(g, "td3_critic/after").items():       # BatchNorm running statistics after the train-mode forward
+        close(cr.state_dict()[k].float(), v, rtol=1e-5)
+    cr.eval()
+    close(cr.evaluate_q_1(s, ca, da), g["td3_critic/q1_eval"])
+    # actor: act() with the recorded draws, gradients through the softmax / Gumbel heads, evaluate in eval mode
+    ac = _load_init(T.Hybrid_Actor(in_dims, A), g, "td3_actor/init").train()
+    noise = tuple(torch.as_tensor(g[f"td3_actor/{k}"]).to(DEV) for k in ("eps_c", "eps_d", "U"))
+    c_means, ens_c, d_action, ens_d = ac.act(s, 0.7, noise=noise)
+    close(c_means, g["td3_actor/act/c_means"])
+    close(ens_c, g["td3_actor/act/ens_c"])
+    close(d_action, g["td3_actor/act/d_action"], rtol=2e-5)
+    assert np.array_equal(ens_d.cpu().numpy(), g["td3_actor/act/ens_d"])
+    loss = (ens_c * ca).sum(-1).mean() + (d_action * da).sum(-1).mean() + (c_means ** 2).mean()
+    ac.zero_grad()
+    loss.backward()
+    _check_grads(ac, g, "td3_actor/grad", rtol=2e-5)
+    ac.eval()
+    c_e, d_e = ac.evaluate(s)
+    close(c_e, g["td3_actor/eval/c"])
+    close(d_e, g["td3_actor/eval/d"])
+    close(T.boltzmann_softmax(c_e, 0.5), g["td3/boltzmann"])
+    hard = T.gumbel_softmax_sample(d_e, temprature=0.1, hard=True)
+    assert torch.equal(hard.sum(-1), torch.ones(len(s), device=DEV)) and ((hard == 0) | (hard == 1)).all()
+    # the reference module exports its Memory class too
+    assert T.Memory is __import__("rl_ctr_prediction_b200.replay", fromlist=["Memory"]).Memory
+
+
+def test_ppo_head_matches_reference(golden_heads):
+    from rl_ctr_prediction_b200 import Hybrid_PPO_model as P
+    g = golden_heads
+    s = torch.as_tensor(g["in/state"]).to(DEV)
+    ca = torch.as_tensor(g["in/c_actions"]).to(DEV)
+    d_a = torch.as_tensor(g["ppo/d_a"]).to(DEV)
+    pp = _load_init(P.Hybrid_Actor_Critic(s.shape[1], ca.shape[1]), g, "ppo/init").train()
+    sv, clp, cent, dlp, dent = pp.evaluate(s, ca, d_a)
+    for k, v in (("state_value", sv), ("c_logprob", clp), ("c_entropy", cent), ("d_logprob", dlp), ("d_entropy", dent)):
+        close(v, g[f"ppo/evaluate/{k}"])
+    loss = (sv ** 2).mean() - clp.sum(-1).mean() * 0.1 - dlp.mean() - 0.01 * dent.mean()
+    pp.zero_grad()
+    loss.backward()
+    _check_grads(pp, g, "ppo/grad", rtol=2e-5)
+    pp.eval()
+    pp.load_state_dict({**pp.state_dict(), **{k: torch.as_tensor(v) for k, v in state_from_golden(g, "ppo/after").items()}})
+    bc, bd = pp.best_a(s)
+    close(bc, g["ppo/best/c"])
+    close(bd, g["ppo/best/d"])
+    (c_act, c_lp, ens_c), (d_draw, d_lp, ens_d) = pp.act(s, c_noise=torch.zeros_like(ca), d_draw=d_a.view(-1))
+    close(c_act, bc)                                                    # zero noise: the sample is the mean
+    assert torch.equal(ens_d, d_a + 2)
