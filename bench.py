@@ -312,20 +312,10 @@ def b200_arm(args):
     lossf = torch.nn.BCELoss()
 
     def step(ms, x, y):
-        out = []
-        for m, opt in ms:
-            if world > 1:
-                tl = m.train_step(x, y, opt)
-            elif isinstance(m, p_model.DeepFM):
-                p = m(x)
-                tl = lossf(p, y.unsqueeze(1).float())
-                m.zero_grad()
-                tl.backward()
-                opt.step()
-            else:
-                tl = PM.fused_train_step(m, opt, x, y)
-            out.append(tl)
-        return out
+        # the eager form of exactly what the CUDA graph replays (graphs.eager_step): the fused loss head for every model, autograd
+        # for DeepFM's tower, the sharded step for N > 1
+        from rl_ctr_prediction_b200 import graphs as _g
+        return [_g.eager_step(m, opt, lossf, x, y) for m, opt in ms]
 
     def barrier():
         if world > 1:
