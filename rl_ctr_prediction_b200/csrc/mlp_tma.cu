@@ -14,11 +14,21 @@
 //     as MN-major UMMA operands (TMA boxes of 32 mn x 32 k in the SWIZZLE_128B_BASE32B layout): no 4-byte
 //     transposing copies.
 //
+// Third generation (this file's default data path; profiles/r1e_*):
+//   * the A operand lives in TENSOR MEMORY: a converter thread owns one row of the raw 128 x 32 tile, reads its 32 k-values from
+//     the swizzled shared-memory tile, splits them and writes (A_hi, A_lo) with tcgen05.st; the MMAs take A from TMEM
+//     (tcgen05.mma ... [d_tmem], [a_tmem], b_desc), so A crosses the shared-memory port once instead of four times per k-block;
+//   * C leaves through per-warp 32 x 32 staging blocks and TMA stores (cp.async.bulk.tensor ... global.shared::cta): full
+//     128-byte row segments instead of 16-byte pieces of 32 different lines per store instruction;
+//   * kept behind switches: A from shared memory + direct stores (RLCTR_GEMM_A_TMEM=0, RLCTR_GEMM_C_TMA=0), the B tile multicast
+//     to a CTA pair (RLCTR_GEMM_CLUSTER=2), L2 prefetch of A (RLCTR_GEMM_L2_AHEAD), per-stage clock stamps (RLCTR_GEMM_DBG).
+//
 // Warp roles (320 threads, one CTA per SM, persistent over output tiles):
-//     warps 0-3  converters        wait raw[s] -> split -> fence.proxy.async -> arrive full[s]
-//     warp  4    TMA producer      wait empty[s] -> expect_tx + boxes of A, B(hi), B(lo) -> raw[s]
-//     warp  5    MMA issuer        wait full[s] -> 4 k-steps x 3 tcgen05.mma -> commit empty[s] / tmem_full[acc]
-//     warps 6-9  epilogue          tcgen05.ld -> bias / ReLU -> global          (TMEM double-buffered)
+//     warps 0-3  converters        wait raw[s] -> row of A: split -> tcgen05.st (hi | lo) -> arrive full[s]
+//     warp  4    TMA producer      wait empty[s] -> expect_tx + boxes of A (raw), B(hi), B(lo) -> raw[s]
+//     warp  5    MMA issuer        wait raw[s], full[s] -> 4 k-steps x 3 tcgen05.mma (A from TMEM) -> commit empty[s] / tmem_full[acc]
+//     warps 6-9  epilogue          tcgen05.ld -> bias / ReLU / dropout / mask -> staging block -> TMA store   (TMEM double-buffered)
+// TMEM columns: accumulator stage s at s * round32(n_tile); A stage s at 2 * round32(n_tile) + 64 * s (32 columns hi, 32 lo).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
