@@ -75,9 +75,17 @@ class Memory(object):
     def _valid(self):
         return self.memory_size if self.memory_counter >= self.memory_size else self.memory_counter
 
-    def _sample(self, batch_size, greedy):
+    def _sample(self, batch_size, greedy, sample=None):
         lib = _lib.load()
         n = self._valid()
+        if sample is not None:                          # injected indices (reproducible parity runs): everything downstream as usual
+            idx = torch.as_tensor(sample, device=self.device).long().reshape(-1).contiguous()
+            pri = self.get_priority(self.prioritys_[:n, 0:1])
+            isw = torch.pow(torch.div(pri[idx], torch.min(pri)), -self.beta)                         # :80-82
+            batch = torch.empty(idx.numel(), self.transition_lens, dtype=torch.float32, device=self.device)
+            _lib.check(lib.rlctr_replay_gather(_lib.ptr(self.memory), self.transition_lens, _lib.ptr(idx), idx.numel(),
+                                               _lib.ptr(batch), _lib.stream()), "rlctr_replay_gather")
+            return idx, batch, isw
         if batch_size > n:
             raise ValueError("Cannot take a larger sample than population when 'replace=False'")     # numpy's message
         wsb = lib.rlctr_replay_per_ws_bytes(n)
@@ -95,8 +103,8 @@ class Memory(object):
                                            _lib.stream()), "rlctr_replay_gather")
         return idx, batch, isw
 
-    def stochastic_sample(self, batch_size):                                     # :62-85
-        return self._sample(batch_size, False)
+    def stochastic_sample(self, batch_size, sample=None):                        # :62-85
+        return self._sample(batch_size, False, sample)
 
     def greedy_sample(self, batch_size):                                         # :87-105 (top-batch of column 0)
         self.beta = torch.min(torch.FloatTensor([1., self.beta + self.beta_increment_per_sampling])).item()   # fp32, as the reference      # :94

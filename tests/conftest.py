@@ -60,3 +60,10 @@ def golden_heads():
     """Hybrid TD3 (v10) / PPO network heads from the real reference (tests/golden/make_golden_heads.py)."""
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_heads.npz")
     return np.load(path, allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_td3():
+    """Two learn steps of the reference's hybrid TD3 (v10) agent (tests/golden/make_golden_td3.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden_td3.npz")
+    return np.load(path, allow_pickle=False)

@@ -538,3 +538,47 @@ def test_ppo_head_matches_reference(golden_heads):
     (c_act, c_lp, ens_c), (d_draw, d_lp, ens_d) = pp.act(s, c_noise=torch.zeros_like(ca), d_draw=d_a.view(-1))
     close(c_act, bc)                                                    # zero noise: the sample is the mean
     assert torch.equal(ens_d, d_a + 2)
+
+
+def test_td3_learn_steps_match_reference(golden_td3):
+    """Two full ``Hybrid_TD3_Model.learn`` steps (critic update with gradient clipping, priority update, delayed actor update,
+    Polyak targets) from the reference's initial networks, replay contents and recorded random draws: critic losses, priorities
+    and the final actor / critic / target networks."""
+    from rl_ctr_prediction_b200 import v10_Hybrid_TD3_model_PER as T
+    from rl_ctr_prediction_b200.Feature_embedding import Feature_Embedding
+    g = golden_td3
+    F_, D_, A, N, B = 15, 10, 3, 500, 32
+    agent = T.Hybrid_TD3_Model(N, F_, D_, A, memory_size=64, batch_size=B, device=DEV)
+    agent.policy_freq = 1
+    for net, tgt, name in ((agent.Hybrid_Actor, agent.Hybrid_Actor_, "actor"), (agent.Hybrid_Critic, agent.Hybrid_Critic_, "critic")):
+        sd = {k: torch.as_tensor(v) for k, v in state_from_golden(g, f"init/{name}").items()}
+        assert set(sd.keys()) == set(net.state_dict().keys())
+        net.load_state_dict(sd)
+        tgt.load_state_dict(sd)
+    fe = Feature_Embedding(N, F_, D_).to(DEV)
+    fe.load_embedding({"feature_embedding.weight": torch.as_tensor(g["fe/feature_embedding.weight"])})
+    tr = torch.as_tensor(g["transitions"])
+    agent.store_transition(tr[:30])
+    agent.store_transition(tr[30:])
+    assert np.array_equal(agent.memory.prioritys_.cpu().numpy(), g["memory/prioritys_after_store"])
+    for step in range(2):
+        noise = {"eps_d": torch.as_tensor(g[f"step{step}/eps_d"]).to(DEV), "U_next": torch.as_tensor(g[f"step{step}/U_next"]).to(DEV),
+                 "U_now": torch.as_tensor(g[f"step{step}/U_now"]).to(DEV), "eps_c": torch.zeros(B, A, device=DEV)}
+        loss = agent.learn(fe, noise=noise, sample=g[f"step{step}/idx"])
+        close(loss, g[f"step{step}/critic_loss"], rtol=2e-5)
+        close(agent.memory.prioritys_, g[f"step{step}/prioritys_"], rtol=1e-4, atol=2e-5)
+    for name, net in (("actor", agent.Hybrid_Actor), ("critic", agent.Hybrid_Critic), ("actor_target", agent.Hybrid_Actor_),
+                      ("critic_target", agent.Hybrid_Critic_)):
+        for k, v in net.state_dict().items():
+            v = v.detach().float().cpu().numpy()
+            full = f"final/{name}/{k}" in g.files
+            ref = g[f"final/{name}/{k}"] if full else g[f"final/{name}/{k}/sub"]
+            got = v if full else v.reshape(-1)[::17]
+            # Adam moves an element by ~lr per step whatever its gradient's size (lr_C = 1e-2, two steps): an element whose gradient
+            # is rounding noise lands anywhere within a fraction of that step.  So: (almost) every element tight, none far.
+            err = np.abs(got.astype(np.float64) - ref.astype(np.float64)).reshape(-1)
+            tight = 1e-4 * np.abs(ref).reshape(-1) + max(1e-4 * float(np.abs(ref).max()), 2e-5)
+            assert (err > tight).mean() <= 2e-3, (name, k, float((err > tight).mean()))
+            assert err.max() <= 2e-3, (name, k, float(err.max()))
+            if not full:
+                assert abs(v.astype(np.float64).sum() - float(g[f"final/{name}/{k}/sum"])) <= 1e-3 * max(1.0, np.abs(v).sum() ** 0.5)
