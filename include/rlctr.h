@@ -370,6 +370,13 @@ int rlctr_replay_sample_per(const float* priorities, int32_t ld, int64_t n_valid
                             int64_t batch, const uint64_t* rng_state, int64_t* out_idx, float* out_isw, void* ws, size_t ws_bytes,
                             rlctr_stream_t stream);
 
+/* Generalised advantage estimate of the PPO agent (Hybrid_PPO_model.py:206-212): the reference's reversed Python loop with a
+ * host synchronisation per sample, as one fp64 scan:  adv = 0; for i, d in enumerate(reversed(deltas)): adv = c*adv + d;
+ * advantages[i] = adv  (c = gamma * lambda; advantages[i] belongs to sample n-1-i, as written in the reference). */
+size_t rlctr_gae_ws_bytes(int64_t n);
+int rlctr_gae_scan(const float* deltas, int64_t n, double gamma_lambda, float* advantages, void* ws, size_t ws_bytes,
+                   rlctr_stream_t stream);
+
 /* Dropout mask: keep(element i) = r16(rng_state[0] (seed), rng_state[1] (counter) + i) >= p * 2^16, i = row * out_dim + col
  * (16 random bits per element, two elements per 32-bit hash: csrc/common.cuh).
  * rng_state is DEVICE memory so that a captured CUDA graph draws a new mask on every replay; rlctr_rng_advance moves the

@@ -76,6 +76,8 @@ SIGNATURES = {
     "rlctr_replay_per_ws_bytes": (_SZ, [_I64]),
     "rlctr_replay_sample_per": (C.c_int, [_P, _I32, _I64, C.c_float, C.c_float, C.c_float, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "rlctr_push_rows": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _I32, _P, _P]),
+    "rlctr_gae_ws_bytes": (_SZ, [_I64]),
+    "rlctr_gae_scan": (C.c_int, [_P, _I64, _F, _P, _P, _SZ, _P]),
     "rlctr_gather_rows": (C.c_int, [_P, _I64, _TP, _P, _P]),
     "rlctr_ffm_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "rlctr_featemb_fwd": (C.c_int, [_P, _TP, _P, _I64, _I64, _I32, _P]),

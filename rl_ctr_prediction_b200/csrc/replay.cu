@@ -227,3 +227,59 @@ extern "C" int rlctr_replay_sample_per(const float* priorities, int32_t ld, int6
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Generalised advantage estimate of the PPO agent (Hybrid_PPO_model.py:206-212).  The reference walks the TD residuals in
+// REVERSE order in a Python loop with one `.item()` host synchronisation per sample and a Python-float (fp64) accumulator:
+//     adv = 0;  for i, d in enumerate(reversed(deltas)):  adv = c * adv + d;  advantages[i] = adv          (c = gamma * lambda)
+// (so advantages[i] belongs to sample n-1-i: kept as written).  A first-order linear recurrence is an associative scan over
+// pairs (m, v) with (m1, v1) o (m2, v2) = (m1 * m2, v1 * m2 + v2); it runs as one cub::DeviceScan in fp64.
+// ------------------------------------------------------------------------------------------------------------------------
+#include <cub/device/device_scan.cuh>
+
+namespace rlctr {
+
+struct GaePair { double m, v; };
+struct GaeOp {
+    __device__ __forceinline__ GaePair operator()(const GaePair& a, const GaePair& b) const { return GaePair{a.m * b.m, a.v * b.m + b.v}; }
+};
+__global__ void __launch_bounds__(256)
+gae_pairs_kernel(const float* __restrict__ deltas, int64_t n, double c, GaePair* __restrict__ pairs) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        pairs[i] = GaePair{c, (double)__ldg(deltas + (n - 1 - i))};
+}
+__global__ void __launch_bounds__(256)
+gae_out_kernel(const GaePair* __restrict__ pairs, int64_t n, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)pairs[i].v;
+}
+
+}  // namespace rlctr
+
+extern "C" size_t rlctr_gae_ws_bytes(int64_t n) {
+    if (n <= 0) return 256;
+    size_t temp = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, temp, (const GaePair*)nullptr, (GaePair*)nullptr, GaeOp{}, (int)n);
+    return rp_align((size_t)n * sizeof(GaePair)) + temp + 256;
+}
+
+extern "C" int rlctr_gae_scan(const float* deltas, int64_t n, double gamma_lambda, float* advantages, void* ws, size_t ws_bytes,
+                              rlctr_stream_t stream) {
+    if (!deltas || !advantages || n < 0) return RLCTR_EINVAL;
+    if (n == 0) return RLCTR_OK;
+    if (n >= ((int64_t)1 << 31)) return RLCTR_EUNSUPPORTED;
+    if (!ws || ws_bytes < rlctr_gae_ws_bytes(n)) return RLCTR_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    GaePair* pairs = reinterpret_cast<GaePair*>(ws);
+    const size_t arr = rp_align((size_t)n * sizeof(GaePair));
+    void* temp = reinterpret_cast<char*>(ws) + arr;
+    size_t temp_bytes = ws_bytes - arr;
+    gae_pairs_kernel<<<rp_grid(n, RLCTR_SMS * 8), 256, 0, st>>>(deltas, n, gamma_lambda, pairs);
+    RLCTR_LAUNCH_CHECK();
+    cudaError_t e = cub::DeviceScan::InclusiveScan(temp, temp_bytes, pairs, pairs, GaeOp{}, (int)n, st);
+    if (e != cudaSuccess) return (int)e;
+    RLCTR_COUNT_LAUNCH(2);
+    gae_out_kernel<<<rp_grid(n, RLCTR_SMS * 8), 256, 0, st>>>(pairs, n, advantages);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}

@@ -67,3 +67,10 @@ def golden_td3():
     """Two learn steps of the reference's hybrid TD3 (v10) agent (tests/golden/make_golden_td3.py)."""
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_td3.npz")
     return np.load(path, allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_ppo():
+    """One learn() call of the reference's hybrid PPO agent (tests/golden/make_golden_ppo.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden_ppo.npz")
+    return np.load(path, allow_pickle=False)

@@ -582,3 +582,45 @@ def test_td3_learn_steps_match_reference(golden_td3):
             assert err.max() <= 2e-3, (name, k, float(err.max()))
             if not full:
                 assert abs(v.astype(np.float64).sum() - float(g[f"final/{name}/{k}/sum"])) <= 1e-3 * max(1.0, np.abs(v).sum() ** 0.5)
+
+
+def test_ppo_learn_matches_reference(golden_ppo):
+    """The GAE scan against the reference's reversed Python loop, then one full ``Hybrid_PPO_Model.learn`` (3 clipped-surrogate
+    epochs): returned loss and final network."""
+    from rl_ctr_prediction_b200 import Hybrid_PPO_model as P
+    g = golden_ppo
+    adv = P.gae_advantages(torch.as_tensor(g["gae/deltas"]).to(DEV), 1 * 0.95)
+    close(adv, g["gae/advantages"], rtol=1e-6)
+    # a long rollout: the scan equals the sequential fp64 recurrence (c = 1 too: no decay to hide behind)
+    rs = np.random.default_rng(1)
+    d = rs.standard_normal(200_003).astype(np.float32)
+    for c in (0.95, 1.0):
+        ref, a = np.empty_like(d, dtype=np.float64), 0.0
+        for i, x in enumerate(d[::-1].astype(np.float64)):
+            a = c * a + x
+            ref[i] = a
+        got = P.gae_advantages(torch.as_tensor(d).to(DEV), c)
+        close(got[:, 0], ref.astype(np.float32), rtol=1e-6, atol=1e-6 * float(np.abs(ref).max()))
+    F_, D_, A = 15, 10, 3
+    agent = P.Hybrid_PPO_Model(500, F_, D_, A, memory_size=128, batch_size=32, init_lr=1e-3, device=DEV)
+    sd = {k: torch.as_tensor(v) for k, v in state_from_golden(g, "init").items()}
+    assert set(sd.keys()) == set(agent.hybrid_actor_critic.state_dict().keys())
+    agent.hybrid_actor_critic.load_state_dict(sd)
+    t = lambda k: torch.as_tensor(g[f"in/{k}"]).to(DEV)
+    loss = agent.learn(t("states"), t("states"), t("old_c_a"), t("old_c_lp"), t("old_d_a"), t("old_d_lp"), t("rewards"))
+    close(loss, g["loss"], rtol=5e-5)
+    for k, v in agent.hybrid_actor_critic.state_dict().items():
+        v = v.detach().float().cpu().numpy()
+        full = f"final/{k}" in g.files
+        ref = g[f"final/{k}"] if full else g[f"final/{k}/sub"]
+        got = v if full else v.reshape(-1)[::17]
+        err = np.abs(got.astype(np.float64) - ref.astype(np.float64)).reshape(-1)
+        # 3 Adam steps at lr = 1e-3 (step scale 3e-3) through a clipped / min surrogate: an element whose gradient is rounding noise
+        # moves by a fraction of a step either way, so: the bulk tight, the mean error two orders below the step, nothing far
+        tight = 1e-4 * np.abs(ref).reshape(-1) + max(1e-4 * float(np.abs(ref).max()), 2e-5)
+        assert (err > tight).mean() <= 0.05, (k, float((err > tight).mean()))
+        assert err.mean() <= 2e-5, (k, float(err.mean()))
+        assert err.max() <= 1.5e-3, (k, float(err.max()))
+    # the rollout memory keeps the reference's (quirky) write semantics
+    agent.store_memory(torch.ones(5, F_), torch.ones(5, A), torch.ones(5, A), torch.ones(5, 1), torch.ones(5, 1), torch.ones(5, 1))
+    assert float(agent.memory_state[:5].sum()) == 5 * F_ and agent.memory_counter == 0
