@@ -128,9 +128,11 @@ def fused_train_step(model, optimizer, features, labels):
     """One training step of pretrain_main.py:96-102 with the loss head inside the library:
     sort -> catch-up -> gather+interaction -> sigmoid+BCE (+ their autograd) -> segment-reduce+Adam.
     Numerically the same step as ``loss(model(x), y); zero_grad(); backward(); optimizer.step()`` with
-    ``nn.BCELoss``.  LR / FM / FFM (models without a dense tower).  Returns the loss (device scalar)."""
-    if getattr(model, "mlp", None) is not None:
-        raise NotImplementedError("fused_train_step covers the tower-less models; DeepFM / W&D / FNN / IPNN go through autograd")
+    ``nn.BCELoss``.  LR / FM / FFM run entirely in the library; models with a dense tail keep autograd for the tail
+    (graphs.fused_logit_step).  Returns the loss (device scalar)."""
+    if hasattr(model, "logit"):                 # DeepFM / W&D / FNN / IPNN / OPNN / DCN / AFM: autograd for the dense tail, fused head
+        from . import graphs
+        return graphs.fused_logit_step(model, optimizer, features, labels)
     lib = _lib.load()
     x = Model._check_ids(features)
     B, F = x.shape

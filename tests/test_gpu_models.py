@@ -113,11 +113,11 @@ def test_training_trajectory_matches_reference(golden, name, mode):
     assert_state(m, state_from_golden(golden, f"train/{name}/final"))
 
 
-@pytest.mark.parametrize("name", ["LR", "FM", "FFM"])
+@pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
 def test_fused_train_step_matches_reference(golden, name):
     from rl_ctr_prediction_b200 import optim, pretrain_main as PM
     sd = state_from_golden(golden, f"train/{name}/init")
-    m = load(build(name, 255), sd).to(DEV)
+    m = load(build(name, 255), sd).to(DEV).eval()          # eval(): DeepFM's dropout off, as in the golden trajectory
     opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
     for s in range(3):
         x = torch.as_tensor(golden["train/x"][s]).to(DEV)
