@@ -88,80 +88,74 @@ def gae_advantages(deltas, gamma_lambda):
 
 
 class Hybrid_PPO_Model():
-    """:98-259."""
+    """The agent (reference ``:98-259``): a rollout memory of six column blocks, acting through the current network, and ``learn``:
+    TD residuals -> generalised advantages (device scan) -> ``k_epochs`` clipped-surrogate steps on one Adam optimizer."""
+
+    _COLUMNS = (("memory_state", "field_nums"), ("memory_c_a", "action_nums"), ("memory_c_logprobs", "action_nums"),
+                ("memory_d_a", 1), ("memory_d_logprobs", 1), ("memory_reward", 1))
 
     def __init__(self, feature_nums, field_nums=15, latent_dims=5, action_nums=2, campaign_id='1458', init_lr=1e-2, train_epochs=500,
                  reward_decay=1, lr_lamda=0.01, memory_size=4096000, batch_size=256, tau=0.005, k_epochs=3, eps_clip=0.2,
                  device='cuda:0'):
-        self.feature_nums, self.field_nums, self.action_nums, self.campaign_id = feature_nums, field_nums, action_nums, campaign_id
-        self.init_lr, self.train_epochs, self.gamma, self.latent_dims = init_lr, train_epochs, reward_decay, latent_dims
-        self.lr_lamda, self.memory_size, self.batch_size, self.tau, self.device = lr_lamda, memory_size, batch_size, tau, device
-        self.action_std = 0.5
-        self.k_epochs, self.eps_clip = k_epochs, eps_clip
-        self.lamda = 0.95
-        self.memory_counter = 0
-        self.input_dims = self.field_nums * (self.field_nums - 1) // 2 + self.field_nums * self.latent_dims
-        z = lambda w: torch.zeros(size=[self.memory_size, w], device=self.device)
-        self.memory_state, self.memory_c_a, self.memory_c_logprobs = z(self.field_nums), z(self.action_nums), z(self.action_nums)
-        self.memory_d_a, self.memory_d_logprobs, self.memory_reward = z(1), z(1), z(1)
-        self.hybrid_actor_critic = Hybrid_Actor_Critic(self.input_dims, self.action_nums).to(self.device)
-        self.hybrid_actor_critic_old = Hybrid_Actor_Critic(self.input_dims, self.action_nums).to(self.device)
-        self.optimizer = _optim.Adam(self.hybrid_actor_critic.parameters(), lr=self.init_lr, weight_decay=1e-5)   # :150
+        self.feature_nums, self.field_nums, self.latent_dims, self.action_nums = feature_nums, field_nums, latent_dims, action_nums
+        self.campaign_id, self.device = campaign_id, device
+        self.init_lr, self.train_epochs, self.lr_lamda = init_lr, train_epochs, lr_lamda
+        self.gamma, self.lamda, self.tau = reward_decay, 0.95, tau
+        self.memory_size, self.batch_size, self.memory_counter = memory_size, batch_size, 0
+        self.k_epochs, self.eps_clip, self.action_std = k_epochs, eps_clip, 0.5
+        self.input_dims = field_nums * (field_nums - 1) // 2 + field_nums * latent_dims
+        for name, width in self._COLUMNS:
+            w = getattr(self, width) if isinstance(width, str) else width
+            setattr(self, name, torch.zeros(memory_size, w, device=device))
+        self.hybrid_actor_critic = Hybrid_Actor_Critic(self.input_dims, action_nums).to(device)
+        self.hybrid_actor_critic_old = Hybrid_Actor_Critic(self.input_dims, action_nums).to(device)
+        self.optimizer = _optim.Adam(self.hybrid_actor_critic.parameters(), lr=init_lr, weight_decay=1e-5)      # :150
         self.loss_func = nn.MSELoss()
 
     def store_memory(self, states, c_a, c_logprobs, d_a, d_logprobs, rewards):
-        """:154-170 (as written: ``index_end = counter + len`` and the counter is never advanced, so a rollout overwrites the
-        head of the memory)."""
-        n = len(states)
-        lo = self.memory_counter % self.memory_size
-        hi = self.memory_counter + n
-        self.memory_state[lo:hi, :] = states
-        self.memory_c_a[lo:hi, :] = c_a
-        self.memory_c_logprobs[lo:hi, :] = c_logprobs
-        self.memory_d_a[lo:hi, :] = d_a
-        self.memory_d_logprobs[lo:hi, :] = d_logprobs
-        self.memory_reward[lo:hi, :] = rewards
-
-    def choose_a(self, state):
-        self.hybrid_actor_critic.eval()
-        with torch.no_grad():
-            return self.hybrid_actor_critic.act(state)
-
-    def choose_best_a(self, state):
-        self.hybrid_actor_critic.eval()
-        with torch.no_grad():
-            ensemble_c_actions, d_actions = self.hybrid_actor_critic.best_a(state)
-            ensemble_d_actions = torch.argsort(-d_actions)[:, 0] + 2
-        return ensemble_c_actions, ensemble_d_actions.view(-1, 1)
+        """Writes the rollout at ``[counter % size, counter + len)``; the reference never advances the counter (:154-170), so
+        every rollout overwrites the head of the memory -- kept."""
+        lo, hi = self.memory_counter % self.memory_size, self.memory_counter + len(states)
+        for (name, _), block in zip(self._COLUMNS, (states, c_a, c_logprobs, d_a, d_logprobs, rewards)):
+            getattr(self, name)[lo:hi, :] = block
 
     def memory(self):
-        s = self.memory_state.long()
-        return s, s, self.memory_c_a, self.memory_c_logprobs, self.memory_d_a, self.memory_d_logprobs, self.memory_reward
+        ids = self.memory_state.long()
+        return ids, ids, self.memory_c_a, self.memory_c_logprobs, self.memory_d_a, self.memory_d_logprobs, self.memory_reward
+
+    @torch.no_grad()
+    def choose_a(self, state):
+        return self.hybrid_actor_critic.eval().act(state)
+
+    @torch.no_grad()
+    def choose_best_a(self, state):
+        weights, d_probs = self.hybrid_actor_critic.eval().best_a(state)
+        return weights, (torch.argsort(-d_probs)[:, 0] + 2).view(-1, 1)
+
+    def _clipped(self, logp, old_logp, adv):
+        """PPO's pessimistic surrogate -E[min(rho A, clip(rho, 1-e, 1+e) A)], rho = exp(logp - old_logp)."""
+        rho = torch.exp(logp - old_logp)
+        return -torch.min(rho * adv, rho.clamp(1 - self.eps_clip, 1 + self.eps_clip) * adv).mean()
 
     def learn(self, states, states_, old_c_a, old_c_a_logprobs, old_d_a, old_d_a_logprobs, rewards):
-        """:194-258."""
-        ac = self.hybrid_actor_critic
-        return_loss = 0
-        old_d_a = old_d_a.long() if old_d_a.dtype != torch.int64 else old_d_a
-        value_of_states_ = ac.evaluate(states_, old_c_a, old_d_a)
-        value_of_states = ac.evaluate(states, old_c_a, old_d_a)
-        td_target = rewards + self.gamma * value_of_states_[0]
-        deltas = td_target - value_of_states[0]
-        advantages = gae_advantages(deltas, self.gamma * self.lamda)              # :206-209, no per-sample host sync
-        advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-5)
+        """:194-258.  Returns the loss of the last epoch."""
+        net = self.hybrid_actor_critic
+        d_taken = old_d_a.long()
+        v_next = net.evaluate(states_, old_c_a, d_taken)[0]
+        v_now = net.evaluate(states, old_c_a, d_taken)[0]
+        target = rewards + self.gamma * v_next
+        adv = gae_advantages(target - v_now, self.gamma * self.lamda)             # :206-209 without the per-sample host sync
+        adv = (adv - adv.mean()) / (adv.std() + 1e-5)
+        target = target.detach()
+        last = 0
         for _ in range(self.k_epochs):
-            state_values, c_a_logprobs, c_a_entropy, d_a_logprobs, d_a_entropy = ac.evaluate(states, old_c_a, old_d_a)
-            ratios = torch.exp(c_a_logprobs - old_c_a_logprobs)
-            c_a_loss = -torch.min(ratios * advantages, torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages).mean()
-            c_a_entropy_loss = 0.01 * c_a_entropy.mean()
-            ratios = torch.exp(d_a_logprobs - old_d_a_logprobs)
-            d_a_loss = -torch.min(ratios * advantages, torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * advantages).mean()
-            d_a_entropy_loss = 0.01 * d_a_entropy.mean()
-            critic_loss = self.loss_func(state_values, td_target.detach())
-            loss = c_a_loss - c_a_entropy_loss + d_a_loss - d_a_entropy_loss + 0.5 * critic_loss
+            value, c_logp, c_ent, d_logp, d_ent = net.evaluate(states, old_c_a, d_taken)
+            loss = (self._clipped(c_logp, old_c_a_logprobs, adv) - 0.01 * c_ent.mean()
+                    + self._clipped(d_logp, old_d_a_logprobs, adv) - 0.01 * d_ent.mean()
+                    + 0.5 * self.loss_func(value, target))
             self.optimizer.zero_grad()
             loss.backward()
             self.optimizer.step()
-            return_loss = loss.mean().item()
-        self.hybrid_actor_critic_old.load_state_dict(self.hybrid_actor_critic.state_dict())
-        return return_loss
+            last = loss.mean().item()
+        self.hybrid_actor_critic_old.load_state_dict(net.state_dict())
+        return last

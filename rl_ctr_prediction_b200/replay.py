@@ -36,83 +36,122 @@ def sample_uniform(n_valid: int, batch_size: int, rng: torch.Tensor) -> torch.Te
     return out
 
 
-class Memory(object):
-    """v10_Hybrid_TD3_model_PER.py:19-110 on the device."""
+class PrioritizedBuffer(object):
+    """Ring buffer of transitions with one priority per slot, sampled on the device.  The reference has two flavours of the
+    same class, which differ in WHEN (|td| + eps)^alpha is applied and in the priority a new transition gets:
+
+    ===========================  =============================================  ============================================
+    flavour                      ``v10_Hybrid_TD3_model_PER.Memory`` (:19-110)   ``Hybrid_SAC_model.Memory`` (:21-108)
+    ===========================  =============================================  ============================================
+    priority array               ``prioritys_`` [size, 2] (raw td | label)       ``priorities_`` [size, 1] (already ^alpha)
+    ``add``                      caller passes the [n, 2] rows                   new slots get max(old, 1)
+    sampling weight              (|raw| + eps)^alpha                             the stored value
+    ``batch_update``             stores the raw td error                         stores (|td| + eps)^alpha
+    beta                         1.0, grows in ``greedy_sample`` only            0.4, grows in both samplers
+    ===========================  =============================================  ============================================
+
+    Subclasses set ``_COLS`` / ``_RAW`` and the attribute name the reference uses for the priority array."""
+
+    _COLS, _RAW, _PRIO_NAME, _BETA0, _BETA_INC = 2, True, "prioritys_", 1.0, 1e-4
 
     def __init__(self, memory_size, transition_lens, device, seed=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
-            raise _lib.RlctrError("rl_ctr_prediction_b200.replay.Memory lives on a CUDA (sm_100a) device; there is no CPU fallback")
-        self.transition_lens = transition_lens
-        self.epsilon = 1e-3
-        self.alpha = 0.6
-        self.beta = 1.0
-        self.beta_increment_per_sampling = 1e-4
-        self.abs_err_upper = 1
-        self.memory_size = memory_size
-        self.memory_counter = 0
-        self.prioritys_ = torch.zeros(size=[memory_size, 2], device=self.device)
-        self.memory = torch.zeros(size=[memory_size, transition_lens], device=self.device)
+            raise _lib.RlctrError(f"{type(self).__module__}.{type(self).__name__} lives on a CUDA (sm_100a) device; "
+                                  "there is no CPU fallback")
+        self.memory_size, self.transition_lens, self.memory_counter = memory_size, transition_lens, 0
+        self.epsilon, self.alpha, self.abs_err_upper = 1e-3, 0.6, 1
+        self.beta, self.beta_increment_per_sampling = self._BETA0, self._BETA_INC
+        setattr(self, self._PRIO_NAME, torch.zeros(memory_size, self._COLS, device=self.device))
+        self.memory = torch.zeros(memory_size, transition_lens, device=self.device)
         self._rng = _rng(self.device, seed)
         self._ws = None
 
-    def get_priority(self, td_error):                                            # :40-41
+    # ---- pieces ----------------------------------------------------------------------------------------------------
+    @property
+    def _prio(self):
+        return getattr(self, self._PRIO_NAME)
+
+    def get_priority(self, td_error):
         return torch.pow(torch.abs(td_error) + self.epsilon, self.alpha)
 
-    def add(self, td_error, transitions):                                        # :43-60
-        lib = _lib.load()
-        n = len(transitions)
-        tr = transitions.to(self.device, torch.float32).contiguous()
-        p = td_error.to(self.device, torch.float32).expand(n, 2).contiguous() if td_error.shape[-1] != 2 else \
-            td_error.to(self.device, torch.float32).contiguous()
-        st = _lib.stream()
-        _lib.check(lib.rlctr_replay_store(_lib.ptr(self.memory), self.memory_size, self.transition_lens, self.memory_counter,
-                                          _lib.ptr(tr), n, self.transition_lens, st), "rlctr_replay_store")
-        _lib.check(lib.rlctr_replay_store(_lib.ptr(self.prioritys_), self.memory_size, 2, self.memory_counter, _lib.ptr(p), n, 2, st),
-                   "rlctr_replay_store")
-        self.memory_counter += n
-
     def _valid(self):
-        return self.memory_size if self.memory_counter >= self.memory_size else self.memory_counter
+        return min(self.memory_counter, self.memory_size)
 
-    def _sample(self, batch_size, greedy, sample=None):
+    def _bump_beta(self):             # the reference rounds through a FloatTensor
+        self.beta = torch.min(torch.FloatTensor([1., self.beta + self.beta_increment_per_sampling])).item()
+
+    def _ring_write(self, dst, width, rows):
+        lib = _lib.load()
+        rows = rows.to(self.device, torch.float32).contiguous()
+        _lib.check(lib.rlctr_replay_store(_lib.ptr(dst), self.memory_size, width, self.memory_counter, _lib.ptr(rows), len(rows),
+                                          width, _lib.stream()), "rlctr_replay_store")
+
+    def _rows_of(self, idx):
+        lib = _lib.load()
+        out = torch.empty(idx.numel(), self.transition_lens, dtype=torch.float32, device=self.device)
+        _lib.check(lib.rlctr_replay_gather(_lib.ptr(self.memory), self.transition_lens, _lib.ptr(idx), idx.numel(), _lib.ptr(out),
+                                           _lib.stream()), "rlctr_replay_gather")
+        return out
+
+    def _weights_of(self, idx, greedy=False):
+        """(p_i / min_j p_j)^(-beta) over the valid range; p = the sampling weight (raw priority for the greedy sampler)."""
+        col = self._prio[:self._valid(), 0:1]
+        p = self.get_priority(col) if (self._RAW and not greedy) else col
+        return torch.pow(torch.div(p[idx], torch.min(p)), -self.beta)
+
+    def _draw(self, batch_size, greedy):
         lib = _lib.load()
         n = self._valid()
-        if sample is not None:                          # injected indices (reproducible parity runs): everything downstream as usual
-            idx = torch.as_tensor(sample, device=self.device).long().reshape(-1).contiguous()
-            pri = self.get_priority(self.prioritys_[:n, 0:1])
-            isw = torch.pow(torch.div(pri[idx], torch.min(pri)), -self.beta)                         # :80-82
-            batch = torch.empty(idx.numel(), self.transition_lens, dtype=torch.float32, device=self.device)
-            _lib.check(lib.rlctr_replay_gather(_lib.ptr(self.memory), self.transition_lens, _lib.ptr(idx), idx.numel(),
-                                               _lib.ptr(batch), _lib.stream()), "rlctr_replay_gather")
-            return idx, batch, isw
         if batch_size > n:
             raise ValueError("Cannot take a larger sample than population when 'replace=False'")     # numpy's message
-        wsb = lib.rlctr_replay_per_ws_bytes(n)
-        if self._ws is None or self._ws.numel() < wsb:
-            self._ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        need = lib.rlctr_replay_per_ws_bytes(n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         idx = torch.empty(batch_size, dtype=torch.int64, device=self.device)
         isw = torch.empty(batch_size, 1, dtype=torch.float32, device=self.device)
-        _lib.call("rlctr_replay_sample_per", lib.rlctr_replay_sample_per, _lib.ptr(self.prioritys_), 2, n, float(self.epsilon),
-                  float(self.alpha), float(self.beta), 1 if greedy else 0, int(batch_size), _lib.ptr(self._rng), _lib.ptr(idx),
-                  _lib.ptr(isw), _lib.ptr(self._ws), self._ws.numel(), _lib.stream(), meta={"n": n, "batch": batch_size})
+        eps, alpha = (float(self.epsilon), float(self.alpha)) if self._RAW else (0.0, 1.0)    # stored value IS the weight
+        _lib.call("rlctr_replay_sample_per", lib.rlctr_replay_sample_per, _lib.ptr(self._prio), self._COLS, n, eps, alpha,
+                  float(self.beta), 1 if greedy else 0, int(batch_size), _lib.ptr(self._rng), _lib.ptr(idx), _lib.ptr(isw),
+                  _lib.ptr(self._ws), self._ws.numel(), _lib.stream(), meta={"n": n, "batch": batch_size})
         if not greedy:
             _lib.check(lib.rlctr_rng_advance(_lib.ptr(self._rng), n, _lib.stream()), "rlctr_rng_advance")
-        batch = torch.empty(batch_size, self.transition_lens, dtype=torch.float32, device=self.device)
-        _lib.check(lib.rlctr_replay_gather(_lib.ptr(self.memory), self.transition_lens, _lib.ptr(idx), batch_size, _lib.ptr(batch),
-                                           _lib.stream()), "rlctr_replay_gather")
-        return idx, batch, isw
+        return idx, isw                                  # IS weights (p_i / min p)^(-beta) from the same kernel
 
-    def stochastic_sample(self, batch_size, sample=None):                        # :62-85
-        return self._sample(batch_size, False, sample)
+    # ---- the reference's surface -----------------------------------------------------------------------------------
+    def stochastic_sample(self, batch_size, sample=None):
+        """Weighted sampling without replacement (the reference: a D2H copy of every priority + ``np.random.choice``).
+        ``sample`` = injected indices for reproducible parity runs."""
+        if not self._RAW:
+            self._bump_beta()                            # the SAC flavour raises beta before it weighs the sample (:77-81)
+        if sample is not None:
+            idx = torch.as_tensor(sample, device=self.device).long().reshape(-1).contiguous()
+            return idx, self._rows_of(idx), self._weights_of(idx)
+        idx, isw = self._draw(batch_size, False)
+        return idx, self._rows_of(idx), isw
 
-    def greedy_sample(self, batch_size):                                         # :87-105 (top-batch of column 0)
-        self.beta = torch.min(torch.FloatTensor([1., self.beta + self.beta_increment_per_sampling])).item()   # fp32, as the reference      # :94
-        return self._sample(batch_size, True)
+    def greedy_sample(self, batch_size):
+        self._bump_beta()
+        idx, isw = self._draw(batch_size, True)
+        return idx, self._rows_of(idx), isw
 
-    def batch_update(self, choose_idx, td_errors):                               # :107-108
+    def batch_update(self, choose_idx, td_errors):
         lib = _lib.load()
-        td = td_errors.to(self.device, torch.float32).reshape(-1).contiguous()
+        td = td_errors.to(self.device, torch.float32)
+        val = (td if self._RAW else self.get_priority(td)).reshape(-1).contiguous()
         idx = choose_idx.to(self.device, torch.int64).reshape(-1).contiguous()
-        _lib.check(lib.rlctr_replay_update(_lib.ptr(self.prioritys_), 2, _lib.ptr(idx), _lib.ptr(td), idx.numel(), _lib.stream()),
-                   "rlctr_replay_update")
+        _lib.check(lib.rlctr_replay_update(_lib.ptr(self._prio), self._COLS, _lib.ptr(idx), _lib.ptr(val), idx.numel(),
+                                           _lib.stream()), "rlctr_replay_update")
+
+
+class Memory(PrioritizedBuffer):
+    """``v10_Hybrid_TD3_model_PER.Memory``: raw td errors stored beside the click label; ``add(td_error [n, 2], transitions)``."""
+
+    def add(self, td_error, transitions):
+        n = len(transitions)
+        rows = td_error.to(self.device, torch.float32)
+        if rows.shape[-1] != self._COLS:
+            rows = rows.expand(n, self._COLS)
+        self._ring_write(self.memory, self.transition_lens, transitions)
+        self._ring_write(self._prio, self._COLS, rows)
+        self.memory_counter += n
