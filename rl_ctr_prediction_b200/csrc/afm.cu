@@ -12,8 +12,9 @@
 // autograd's copies); here a warp owns a sample, keeps the 15 rows in shared memory and each lane walks its pairs with
 // ip / a in registers, so nothing but the rows is read and one float per sample is written.  The backward recomputes the
 // forward (no saved activations) and regenerates the dropout masks from the (seed, counter) snapshot of the forward.
-// Parameter gradients are accumulated per lane in registers over the whole grid-stride loop, summed over the warp once at
-// the end and written as per-warp partials; a fixed-order pass reduces them, so results are bit-identical run to run.
+// Parameter gradients are accumulated in registers over the whole grid-stride loop (the D x D attention weight distributed by
+// entry over the lanes, the small vectors per lane and summed over the warp once at the end) and written as per-warp partials;
+// a fixed-order pass reduces them, so results are bit-identical run to run.
 //
 // params / dparams (packed, NP = D*D + 3*D + 2 floats):  [W_a (D x D, row k = output k) | b_a | w_s | b_s | fc_w | fc_b]
 // masks (optional, tests): float [batch, P + D] multipliers (0 or 1/(1-p)) used instead of the hash -- mask-as-input parity.
@@ -156,9 +157,15 @@ afm_fwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
     }
 }
 
-// dynamic smem: PAR | AFM_WARPS * (fd + 2 * npair_pad + npair * D) floats | 2 * npair + fields * fields bytes
+// dynamic smem: PAR | AFM_WARPS * (fd + 2 * npair_pad + 3 * npair * D) floats | 2 * npair + fields * fields bytes
+//
+// Parameter gradients: the D x D gradient of the attention weight is an outer-product sum over pairs,
+// dW_a[k][d] = sum_p da_p[k] * ip_p[d].  Accumulating it per lane over the lane's own pairs needs D*D registers per lane (the
+// first version: 255 registers, two warps per scheduler, latency-bound at ~6x its issue-rate estimate).  Instead every pair's
+// da_p and ip_p are staged in shared memory and the D*D entries are DISTRIBUTED over the lanes: lane l owns entries l, l+32, ...
+// (at most ENT = ceil(D*D/32)) and sums over all pairs of the sample.  The small vectors (db_a, dw_s, db_s, dfc) stay per lane.
 template <int D>
-__global__ void __launch_bounds__(AFM_WARPS * 32)
+__global__ void __launch_bounds__(AFM_WARPS * 32, 3)          // <= 168 registers: keeps the compiler from parking all of W_a in registers
 afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __restrict__ params, AfmDrop dr,
                const float* __restrict__ gout, float* __restrict__ grows, int64_t ld_grows, float* __restrict__ part,
                int64_t batch, int fields) {
@@ -166,14 +173,17 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
     constexpr int DP = AfmSmem<D>::DP;
     constexpr int PAR = AfmSmem<D>::PAR;
     constexpr int NP = D * D + 3 * D + 2;
+    constexpr int ENT = (D * D + 31) / 32;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fd = fields * D, npair = fields * (fields - 1) / 2, npp = (npair + 3) / 4 * 4;
-    const int per_warp = fd + 2 * npp + npair * D;
+    const int per_warp = fd + 2 * npp + 3 * npair * D;
     float* par = smem;
     float* stage = smem + PAR + wib * per_warp;
     float* sc = stage + fd;                 // exp(s_p - max)
     float* dsc = sc + npp;                  // d L / d score_p
-    float* dipS = dsc + npp;                // d L / d ip_p [npair, D]
+    float* dipS = dsc + npp;                // d L / d ip_p   [npair, D]
+    float* daS = dipS + npair * D;          // d L / d (pre-ReLU attention activation) [npair, D]
+    float* ipS = daS + npair * D;           // ip_p           [npair, D]
     unsigned char* pi = reinterpret_cast<unsigned char*>(smem + PAR + AFM_WARPS * per_warp);
     unsigned char* pj = pi + npair;
     unsigned char* pidx = pj + npair;
@@ -194,20 +204,24 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
     const float* fcw = ws + DP;
     const int width = npair + D;
 
-    float dWa[D][D], dba[D], dws[D], dfcw[D], dbs = 0.f, dfcb = 0.f;
+    float dWa[ENT], dba[D], dws[D], dfcw[D], dbs = 0.f, dfcb = 0.f;
+    int ek[ENT], ed[ENT];                   // this lane's entries (k, d) of dW_a
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        dba[k] = 0.f; dws[k] = 0.f; dfcw[k] = 0.f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) dWa[k][d] = 0.f;
+    for (int i = 0; i < ENT; ++i) {
+        const int e = lane + 32 * i;
+        dWa[i] = 0.f;
+        ek[i] = e < D * D ? e / D : 0;
+        ed[i] = e < D * D ? e % D : 0;
     }
+#pragma unroll
+    for (int k = 0; k < D; ++k) { dba[k] = 0.f; dws[k] = 0.f; dfcw[k] = 0.f; }
 
     for (int64_t b = (int64_t)blockIdx.x * AFM_WARPS + wib; b < batch; b += (int64_t)gridDim.x * AFM_WARPS) {
         const float* r = rows + b * ld_rows;
         for (int i = lane; i < fd; i += 32) stage[i] = __ldg(r + i);
         __syncwarp();
         const float sum = afm_scores<D>(stage, par, pi, pj, sc, npair, lane);
-        // attention output (needed for d fc_w) -- as in the forward
+        // attention output (needed for d fc_w) -- as in the forward; ip_p is staged for the later passes
         float acc[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] = 0.f;
@@ -216,7 +230,11 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
             const float* vi = stage + pi[p] * D;
             const float* vj = stage + pj[p] * D;
 #pragma unroll
-            for (int d = 0; d < D; ++d) acc[d] = fmaf(sd, vi[d] * vj[d], acc[d]);
+            for (int d = 0; d < D; ++d) {
+                const float ipd = vi[d] * vj[d];
+                ipS[p * D + d] = ipd;
+                acc[d] = fmaf(sd, ipd, acc[d]);
+            }
         }
         const float g = __ldg(gout + b);
         float dattn[D];
@@ -231,25 +249,21 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
         // d score_p and the softmax's inner product
         float dot = 0.f;
         for (int p = lane; p < npair; p += 32) {
-            const float* vi = stage + pi[p] * D;
-            const float* vj = stage + pj[p] * D;
             float t = 0.f;
 #pragma unroll
-            for (int d = 0; d < D; ++d) t = fmaf(dattn[d], vi[d] * vj[d], t);
+            for (int d = 0; d < D; ++d) t = fmaf(dattn[d], ipS[p * D + d], t);
             t *= afm_mask(dr, seed, ctr, b, width, p);
             dsc[p] = t;
             dot = fmaf(sc[p] / sum, t, dot);
         }
         dot = afm_warp_sum(dot);
         for (int p = lane; p < npair; p += 32) {
-            const float* vi = stage + pi[p] * D;
-            const float* vj = stage + pj[p] * D;
             const float score = sc[p] / sum;
             const float dsp = score * (dsc[p] - dot);                      // d L / d s_p
             const float sd = score * afm_mask(dr, seed, ctr, b, width, p);
             float ip[D], dip[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) { ip[d] = vi[d] * vj[d]; dip[d] = sd * dattn[d]; }
+            for (int d = 0; d < D; ++d) { ip[d] = ipS[p * D + d]; dip[d] = sd * dattn[d]; }
             dbs += dsp;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
@@ -259,35 +273,50 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
                 const float da = a > 0.f ? dsp * ws[k] : 0.f;
                 dws[k] = fmaf(dsp, fmaxf(a, 0.f), dws[k]);
                 dba[k] += da;
+                daS[p * D + k] = da;
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    dWa[k][d] = fmaf(da, ip[d], dWa[k][d]);
-                    dip[d] = fmaf(par[k * DP + d], da, dip[d]);
-                }
+                for (int d = 0; d < D; ++d) dip[d] = fmaf(par[k * DP + d], da, dip[d]);
             }
 #pragma unroll
             for (int d = 0; d < D; ++d) dipS[p * D + d] = dip[d];
         }
         __syncwarp();
+        // dW_a entries of this lane: sum over the pairs of the sample, in pair order
+#pragma unroll
+        for (int i = 0; i < ENT; ++i) {
+            float a0 = 0.f, a1 = 0.f;
+            int p = 0;
+            for (; p + 1 < npair; p += 2) {
+                a0 = fmaf(daS[p * D + ek[i]], ipS[p * D + ed[i]], a0);
+                a1 = fmaf(daS[(p + 1) * D + ek[i]], ipS[(p + 1) * D + ed[i]], a1);
+            }
+            if (p < npair) a0 = fmaf(daS[p * D + ek[i]], ipS[p * D + ed[i]], a0);
+            dWa[i] += a0 + a1;
+        }
         // d v_i[d] = sum_{j != i} d ip_{pair(i,j)}[d] * v_j[d], j in order
         for (int t = lane; t < fd; t += 32) {
             const int i = t / D, d = t - i * D;
-            float a = 0.f;
-            for (int j = 0; j < fields; ++j)
-                if (j != i) a = fmaf(dipS[pidx[i * fields + j] * D + d], stage[j * D + d], a);
-            grows[b * ld_grows + t] = a;
+            const unsigned char* prow = pidx + i * fields;
+            float a0 = 0.f, a1 = 0.f;                                      // two chains: the loop is a string of dependent LDS -> FMA
+            int j = 0;
+            for (; j + 1 < fields; j += 2) {
+                if (j != i) a0 = fmaf(dipS[prow[j] * D + d], stage[j * D + d], a0);
+                if (j + 1 != i) a1 = fmaf(dipS[prow[j + 1] * D + d], stage[(j + 1) * D + d], a1);
+            }
+            if (j < fields && j != i) a0 = fmaf(dipS[prow[j] * D + d], stage[j * D + d], a0);
+            grows[b * ld_grows + t] = a0 + a1;
         }
         __syncwarp();
     }
-    // per-warp partials (fixed lane tree), one row of NP floats per warp of the grid
+    // per-warp partials, one row of NP floats per warp of the grid: dW_a entries are already whole-warp sums of their lane
     float* mine = part + ((int64_t)blockIdx.x * AFM_WARPS + wib) * NP;
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
+    for (int i = 0; i < ENT; ++i) {
+        const int e = lane + 32 * i;
+        if (e < D * D) mine[e] = dWa[i];
+    }
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const float s = afm_warp_sum(dWa[k][d]);
-            if (lane == 0) mine[k * D + d] = s;
-        }
+    for (int k = 0; k < D; ++k) {
         const float sb = afm_warp_sum(dba[k]);
         const float sw = afm_warp_sum(dws[k]);
         if (lane == 0) {
@@ -321,12 +350,12 @@ template <int D>
 static int afm_bwd_launch(const float* rows, int64_t ld_rows, const float* params, const AfmDrop& dr, const float* gout,
                           float* grows, int64_t ld_grows, float* dparams, float* part, int64_t batch, int fields, cudaStream_t st) {
     const int fd = fields * D, npair = fields * (fields - 1) / 2, npp = (npair + 3) / 4 * 4;
-    const size_t smem = (size_t)(AfmSmem<D>::PAR + AFM_WARPS * (fd + 2 * npp + npair * D)) * sizeof(float) + 2 * (size_t)npair +
+    const size_t smem = (size_t)(AfmSmem<D>::PAR + AFM_WARPS * (fd + 2 * npp + 3 * npair * D)) * sizeof(float) + 2 * (size_t)npair +
                         (size_t)fields * fields;
     if (smem > 200 * 1024) return RLCTR_EUNSUPPORTED;
     if (smem > 48 * 1024)
         RLCTR_CUDA(cudaFuncSetAttribute(afm_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = afm_blocks(batch, 2);
+    const int blocks = afm_blocks(batch, 3);
     constexpr int NP = D * D + 3 * D + 2;
     afm_bwd_kernel<D><<<blocks, AFM_WARPS * 32, smem, st>>>(rows, ld_rows, params, dr, gout, grows, ld_grows, part, batch, fields);
     RLCTR_LAUNCH_CHECK();
@@ -341,7 +370,7 @@ using namespace rlctr;
 
 extern "C" size_t rlctr_afm_ws_bytes(int64_t batch, int32_t dim) {
     if (batch <= 0 || dim <= 0) return 256;
-    return (size_t)afm_blocks(batch, 2) * AFM_WARPS * (dim * dim + 3 * dim + 2) * sizeof(float) + 256;
+    return (size_t)afm_blocks(batch, 3) * AFM_WARPS * (dim * dim + 3 * dim + 2) * sizeof(float) + 256;
 }
 
 static int afm_drop(AfmDrop* dr, float dropout_p, const uint64_t* rng_state, const float* masks) {
