@@ -288,10 +288,15 @@ pairdots_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float
         __syncwarp();
         for (int t = lane; t < fd; t += 32) {
             const int i = t / dim, d = t - i * dim;
-            float acc = __ldg(g + e_off + t);
-            for (int j = 0; j < fields; ++j)
-                if (j != i) acc = fmaf(gip[pidx[i * fields + j]], stage[j * dim + d], acc);
-            grows[b * ld_grows + t] = acc;
+            const unsigned char* prow = pidx + i * fields;
+            float a0 = __ldg(g + e_off + t), a1 = 0.f;                  // two chains: a string of dependent LDS -> FMA otherwise
+            int j = 0;
+            for (; j + 1 < fields; j += 2) {
+                if (j != i) a0 = fmaf(gip[prow[j]], stage[j * dim + d], a0);
+                if (j + 1 != i) a1 = fmaf(gip[prow[j + 1]], stage[(j + 1) * dim + d], a1);
+            }
+            if (j < fields && j != i) a0 = fmaf(gip[prow[j]], stage[j * dim + d], a0);
+            grows[b * ld_grows + t] = a0 + a1;
         }
         __syncwarp();
     }
