@@ -358,3 +358,43 @@ def reinforce_loss(logits, acts, vt, variant=RF_LITERAL, dtype=F32):
     # d(-log pi_a)/dlogits = pi - onehot
     dlogits = (coef.reshape(-1, 1) * (pi - onehot)).astype(dtype)
     return logp, dtype(loss), dlogits
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY 8f.4 pieces of the RL agents that became device kernels
+# ---------------------------------------------------------------------------------------------
+def gae_advantages(deltas, gamma_lambda):
+    """Hybrid_PPO_model.py:206-212 as written: ``adv = 0; for i, d in enumerate(reversed(deltas)): adv = c*adv + d;
+    advantages[i] = adv`` with a Python-float (fp64) accumulator, stored as fp32 -- note advantages[i] belongs to sample n-1-i."""
+    d = np.asarray(deltas, dtype=np.float64).reshape(-1)
+    out = np.empty(d.size, dtype=np.float32)
+    a = 0.0
+    for i, x in enumerate(d[::-1]):
+        a = gamma_lambda * a + float(np.float32(x))
+        out[i] = a
+    return out.reshape(-1, 1)
+
+
+def per_weights(priorities, eps=1e-3, alpha=0.6):
+    """Sampling weights of the prioritized memory (v10_Hybrid_TD3_model_PER.py:38-39,64-68): (|td| + eps)^alpha."""
+    return (np.abs(np.asarray(priorities, dtype=np.float64)) + eps) ** alpha
+
+
+def per_is_weights(p_all, idx, beta):
+    """Importance-sampling weights (:80-82): (p_i / min_j p_j)^(-beta)."""
+    p_all = np.asarray(p_all, dtype=np.float64)
+    return (p_all[idx] / p_all.min()) ** (-beta)
+
+
+def keep_top_d_actions(d_actions, c_actions, eps=None):
+    """v10_Hybrid_TD3_model_PER.py:427-472 (the O(A^2) nonzero loops): sample b keeps the d_b largest continuous actions,
+    d_b = argmax(d_actions[b]) + 1; kept entries become c (+ N(c, 0.2) = 2c + 0.2 eps when eps is given), the rest 0; clamp to
+    [-1, 1]."""
+    c = np.asarray(c_actions, dtype=np.float32)
+    d = np.argmax(np.asarray(d_actions), axis=-1) + 1
+    order = np.argsort(-c, axis=-1, kind="stable")
+    out = np.zeros_like(c)
+    for b in range(c.shape[0]):
+        for m in order[b, :d[b]]:
+            out[b, m] = c[b, m] if eps is None else c[b, m] + (c[b, m] + 0.2 * eps[b, m])
+    return np.clip(out, -1, 1)

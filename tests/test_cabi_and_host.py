@@ -153,3 +153,27 @@ def test_encoded_text_is_parsed_once_and_cached(tmp_path):
     np.savetxt(path, rows2, delimiter=",", fmt="%d")
     os.utime(path, (os.path.getmtime(path) + 5, os.path.getmtime(path) + 5))
     assert np.array_equal(PM.load_encoded(path), rows2)      # newer text invalidates the image
+
+
+def test_agent_memories_refuse_cpu():
+    """No CPU fallback anywhere on the product path: the replay memories of the agents live on the device."""
+    from rl_ctr_prediction_b200 import _lib, replay, Hybrid_SAC_model
+    for cls in (replay.Memory, Hybrid_SAC_model.Memory):
+        with pytest.raises(_lib.RlctrError):
+            cls(16, 4, "cpu")
+
+
+def test_td3_action_masking_against_oracle():
+    """The rank-comparison form of the TD3 action masking (host torch ops, CPU-checkable) == the oracle's restatement of the
+    reference's nonzero loops (v10_Hybrid_TD3_model_PER.py:427-472)."""
+    from oracle import np_oracle as O
+    from rl_ctr_prediction_b200 import v10_Hybrid_TD3_model_PER as T
+    rs = np.random.default_rng(4)
+    c = np.tanh(rs.standard_normal((64, 5))).astype(np.float32) * 1.3
+    d = rs.random((64, 5)).astype(np.float32)
+    eps = rs.standard_normal((64, 5)).astype(np.float32)
+    agent = T.Hybrid_TD3_Model.__new__(T.Hybrid_TD3_Model)            # the two helpers use no state
+    cur = agent.to_current_state_c_actions(torch.as_tensor(d), torch.as_tensor(c)).numpy()
+    nxt = agent.to_next_state_c_actions(torch.as_tensor(d), torch.as_tensor(c), eps=torch.as_tensor(eps)).numpy()
+    assert np.array_equal(cur, O.keep_top_d_actions(d, c))
+    np.testing.assert_allclose(nxt, O.keep_top_d_actions(d, c, eps), rtol=1e-6, atol=1e-7)

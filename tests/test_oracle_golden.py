@@ -1,5 +1,7 @@
 """Pin the CPU oracle (numpy restatement + CPU-torch port) against vectors produced by
 the real reference modules (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -239,3 +241,19 @@ def test_reinforce(golden):
     logp, loss, dl = O.reinforce_loss(golden["pg/logits"], golden["pg/acts"], golden["pg/vt_raw"], O.RF_LITERAL)
     close(loss, golden["pg/loss_literal_raw"], rtol=1e-5)
     close(dl, golden["pg/dlogits_literal_raw"], rtol=1e-5, atol=1e-7)
+
+
+def test_gae_oracle_matches_reference_loop():
+    """oracle gae_advantages == the advantages the reference's Python loop produced (tests/golden/make_golden_ppo.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden_ppo.npz"), allow_pickle=False)
+    close(O.gae_advantages(g["gae/deltas"], 1 * 0.95), g["gae/advantages"], rtol=1e-6)
+
+
+def test_per_weights_oracle_matches_reference_memory():
+    """oracle IS weights == the reference Memory.stochastic_sample output for the recorded indices (SAC flavour: the stored
+    priority is the weight; tests/golden/make_golden_sac.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden_sac.npz"), allow_pickle=False)
+    pr = g["memory/after_update/priorities"][:, 0]
+    close(O.per_is_weights(pr, g["memory/sample_idx"], 0.4 + 1e-5), g["memory/sample_isw"][:, 0], rtol=1e-5)
+    # and the priorities batch_update wrote are (|td| + eps)^alpha
+    close(pr[g["memory/update_idx"]], O.per_weights(g["memory/update_td"][:, 0]), rtol=1e-6)
