@@ -63,6 +63,7 @@ struct Args {
     int relu;
     int a_tmem;                           // 1: the converters write (A_hi, A_lo) into TENSOR MEMORY and the MMAs read A from there
     int acc_stride, a_col0;               // TMEM columns: accumulator stage s at s*acc_stride, A stage s at a_col0 + 64*s (hi | lo)
+    int pair;                             // 1: cta_group::2 -- a CTA pair computes 256 rows per MMA, each CTA staging HALF of the B tile
     int cluster;                          // CTAs per cluster (1 or 2): the B tile is fetched once per cluster (TMA multicast), each CTA
                                           // owning a different m-tile of the same (n-tile, split)
     int l2_ahead;                         // stages of A the producer prefetches into L2 ahead of the pipeline (0: off)
@@ -213,6 +214,55 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"(mask) : "memory");
+}
+// ---- cta_group::2: one MMA spans the CTA pair (M = 256: 128 rows in each CTA's tensor memory), B is read half from each CTA's
+// shared memory (same offsets), issued by the leader CTA (cluster rank 0) alone
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a),
+        "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit2_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {       // barriers that peers arrive on
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_cluster(bar, parity)) {
+        if ((++spins & 0x3fffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) mbar_timeout(bar, parity);
+        }
+    }
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -520,6 +570,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiCtx& e, uint32_t tadd
     }
 }
 
+// PAIR: the cta_group::2 instantiation (must be launched in clusters of two; the PAIR = false instantiation contains no 2-CTA
+// instruction and runs with any cluster size)
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC, const Args g) {
@@ -534,7 +587,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const bool bias_in_smem = g.bias != nullptr && g.n_tiles * g.n_tile <= BIAS_SMEM;
     if (bias_in_smem)
         for (int i = threadIdx.x; i < g.n_tiles * g.n_tile; i += THREADS) s_bias[i] = i < g.N ? __ldg(g.bias + i) : 0.f;
-    const uint32_t b_bytes = (uint32_t)g.n_tile * 128;
+    const uint32_t b_bytes = (uint32_t)g.n_tile * (PAIR ? 64u : 128u);     // pair: this CTA stages half of the B tile's rows
     const uint32_t a_bytes = g.a_tmem ? A_TILE_BYTES : 2 * A_TILE_BYTES;       // raw A only when (hi, lo) live in TMEM
     const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
     const int rank = g.cluster > 1 ? (int)cluster_ctarank() : 0;
@@ -545,12 +598,12 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&raw_bar[s]), 1);
-            mbar_init(smem_u32(&full_bar[s]), CONV_WARPS * 32);
-            mbar_init(smem_u32(&empty_bar[s]), (uint32_t)g.cluster);      // every CTA of the cluster has retired its MMAs on the slot
+            mbar_init(smem_u32(&full_bar[s]), (uint32_t)(CONV_WARPS * 32 * (PAIR ? 2 : 1)));   // pair: both CTAs' converters (leader's copy)
+            mbar_init(smem_u32(&empty_bar[s]), (uint32_t)(PAIR ? 1 : g.cluster));   // every CTA of the cluster has retired its MMAs on the slot
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[s]), EPI_WARPS * 32);
+            mbar_init(smem_u32(&tmem_empty_bar[s]), (uint32_t)(EPI_WARPS * 32 * (PAIR ? 2 : 1)));
         }
         fence_barrier_init();
     }
@@ -560,7 +613,10 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (g.b_presplit) tma_prefetch_desc(&mapBlo);
         if (g.c_tma) tma_prefetch_desc(&mapC);
     }
-    if (warp == MMA_WARP) tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_alloc2(smem_u32(&tmem_base_smem), TMEM_COLS);
+        else tmem_alloc(smem_u32(&tmem_base_smem), TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     if (g.cluster > 1) cluster_sync_all();                 // the peer's barriers exist before anything is multicast at them
@@ -602,7 +658,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 if (tid == 0) DBG_STAMP(dbg_it, 2);
                 if (tid == 96) DBG_STAMP(dbg_it, 11);
                 ++dbg_it;
-                mbar_arrive(smem_u32(&full_bar[stage]));
+                if (PAIR && rank != 0) mbar_arrive_remote(smem_u32(&full_bar[stage]), 0);      // the leader issues the MMAs of the pair
+                else mbar_arrive(smem_u32(&full_bar[stage]));
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
             if (sum_tile && g.a_tmem) {
@@ -681,7 +738,12 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     } else {
                         tma_load_2d(sa, &mapA, k0, m0, bar);
                     }
-                    if (g.cluster > 1) {
+                    if (PAIR) {
+                        // K-major pre-split B: this CTA stages rows [rank * n_tile/2, (rank + 1) * n_tile/2) of the tile (box = half)
+                        const int rows = g.n_tile / 2;
+                        tma_load_2d(sb, &mapB, k0, n0 + rank * rows, bar);
+                        tma_load_2d(sb + b_bytes, &mapBlo, k0, n0 + rank * rows, bar);
+                    } else if (g.cluster > 1) {
                         // this CTA fetches its share of the B tile and multicasts it to the whole cluster; the peers' shares land
                         // here the same way (raw_bar counts the bytes of the full tile either way)
                         if (g.b_mn) {
@@ -716,7 +778,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // bit 15 / 16 = A / B is MN-major
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((g.a_mn && !g.a_tmem) ? 1 : 0) << 15) |
                                ((uint32_t)(g.b_mn ? 1 : 0) << 16) | ((uint32_t)(g.n_tile >> 3) << 17) |
-                               ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);          // pair: M = 256 over the two CTAs
         const uint32_t a_step = g.a_mn ? 1024u : (uint32_t)UK * 4u;      // bytes per MMA along K
         const uint32_t b_step = g.b_mn ? 1024u : (uint32_t)UK * 4u;
         int stage = 0;
@@ -724,16 +786,19 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         int acc = 0, dbg_it = 0;
         uint32_t acc_phase = 0;
         TileWalk w{cluster_id, 0, 0, 0, 0, 0};
+        if (PAIR && rank != 0) w.tile = total_tiles;                      // the leader CTA issues for the pair
         for (; tile_decode(w, g, total_tiles, rank); w.tile += n_clusters) {
             if (lane == 0) DBG_STAMP(dbg_it, 5);
-            mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);       // epilogue drained this accumulator
+            if (PAIR) mbar_wait_cluster(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);     // BOTH CTAs' epilogues drained it
+            else mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
             if (lane == 0) DBG_STAMP(dbg_it, 6);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
             for (int kb = w.kb0; kb < w.kb1; ++kb) {
                 mbar_wait(smem_u32(&raw_bar[stage]), phase);                 // TMA bytes (the pre-split B tiles) landed
                 if (lane == 0) DBG_STAMP(dbg_it, 8);
-                mbar_wait(smem_u32(&full_bar[stage]), phase);                // converters done
+                if (PAIR) mbar_wait_cluster(smem_u32(&full_bar[stage]), phase);    // both CTAs' converters (hence both halves of B)
+                else mbar_wait(smem_u32(&full_bar[stage]), phase);           // converters done
                 if (lane == 0) DBG_STAMP(dbg_it, 9);
                 tc_fence_after();
                 if (lane == 0) DBG_STAMP(dbg_it, 3);
@@ -748,9 +813,15 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                             const uint64_t dbh = g.b_mn ? desc_mn_major(b_hi + bo) : desc_k_major(b_hi + bo);
                             const uint64_t dbl = g.b_mn ? desc_mn_major(b_lo + bo) : desc_k_major(b_lo + bo);
                             const uint32_t first = (kb > w.kb0 || k > 0) ? 1u : 0u;
-                            umma_tf32_ts(d_tmem, ta_lo + (uint32_t)(k * UK), dbh, idesc, first);
-                            umma_tf32_ts(d_tmem, ta_hi + (uint32_t)(k * UK), dbl, idesc, 1u);
-                            umma_tf32_ts(d_tmem, ta_hi + (uint32_t)(k * UK), dbh, idesc, 1u);
+                            if (PAIR) {
+                                umma_tf32_ts2(d_tmem, ta_lo + (uint32_t)(k * UK), dbh, idesc, first);
+                                umma_tf32_ts2(d_tmem, ta_hi + (uint32_t)(k * UK), dbl, idesc, 1u);
+                                umma_tf32_ts2(d_tmem, ta_hi + (uint32_t)(k * UK), dbh, idesc, 1u);
+                            } else {
+                                umma_tf32_ts(d_tmem, ta_lo + (uint32_t)(k * UK), dbh, idesc, first);
+                                umma_tf32_ts(d_tmem, ta_hi + (uint32_t)(k * UK), dbl, idesc, 1u);
+                                umma_tf32_ts(d_tmem, ta_hi + (uint32_t)(k * UK), dbh, idesc, 1u);
+                            }
                         }
                     } else
 #pragma unroll
@@ -766,16 +837,24 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
                     DBG_STAMP(dbg_it, 10);
-                    if (g.cluster > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), cmask);   // ... in every CTA that writes into it
-                    else umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem slot when these MMAs retire
-                    if (kb == w.kb1 - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                    if (PAIR) {                                            // both CTAs' slots / accumulators, one arrival each
+                        umma_commit2_mc(smem_u32(&empty_bar[stage]), cmask);
+                        if (kb == w.kb1 - 1) umma_commit2_mc(smem_u32(&tmem_full_bar[acc]), cmask);
+                    } else {
+                        if (g.cluster > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), cmask);   // ... in every CTA that writes into it
+                        else umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot when these MMAs retire
+                        if (kb == w.kb1 - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                    }
                     DBG_STAMP(dbg_it, 4);
                 }
                 ++dbg_it;
                 __syncwarp();
                 if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
-            if (w.kb1 <= w.kb0 && lane == 0) umma_commit(smem_u32(&tmem_full_bar[acc]));   // empty split
+            if (w.kb1 <= w.kb0 && lane == 0) {                                                  // empty split
+                if (PAIR) umma_commit2_mc(smem_u32(&tmem_full_bar[acc]), cmask);
+                else umma_commit(smem_u32(&tmem_full_bar[acc]));
+            }
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -818,7 +897,8 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             tc_fence_before();
             if (warp == CONV_WARPS + 2 && lane == 0) DBG_STAMP(dbg_tile * (w.kb1 - w.kb0) + 1, 7);
             ++dbg_tile;
-            mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            if (PAIR && rank != 0) mbar_arrive_remote(smem_u32(&tmem_empty_bar[acc]), 0);
+            else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (g.c_tma && lane == 0) bulk_wait_read<0>();      // the staging blocks must outlive the stores that read them
@@ -826,7 +906,10 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (g.cluster > 1) cluster_sync_all();                 // no CTA leaves while a peer may still signal its barriers
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 // (hi, lo) images of a weight matrix [rows, cols] -> [rows, pitch] (pitch % 4 == 0, zero padded): the B
@@ -889,11 +972,11 @@ static int round_to(int n, int q) { return (n + q - 1) / q * q; }
 
 struct Plan {
     int n_tile, n_tiles, m_tiles, splits, kb_per_split, stages;
-    int a_tmem, acc_stride, a_col0, c_tma, cluster;
+    int a_tmem, acc_stride, a_col0, c_tma, cluster, pair;
     size_t smem;
 };
 constexpr size_t C_STAGE_BYTES = (size_t)EPI_WARPS * 2 * 4096;     // two 32 x 32 fp32 blocks per epilogue warp
-static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_tma_ok = false) {
+static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_tma_ok = false, bool b_presplit = false) {
     Plan p;
     const int nt_max = env_int("RLCTR_GEMM_NT_MAX", 160);           // <= 160 keeps three 72 KB stages in flight
     const int q = b_mn ? 32 : 16;
@@ -922,7 +1005,11 @@ static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_t
     const int tmem_stages = (TMEM_COLS - p.a_col0) / (2 * BK);
     p.a_tmem = (env_int("RLCTR_GEMM_A_TMEM", 1) != 0 && tmem_stages >= 2) ? 1 : 0;
     if (!p.a_tmem) { p.acc_stride = 256; p.a_col0 = 0; }
-    const size_t stage_bytes = (p.a_tmem ? 1 : 2) * (size_t)A_TILE_BYTES + 2 * (size_t)p.n_tile * 128;
+    // cta_group::2 (RLCTR_GEMM_PAIR=1): forward-type GEMMs (K-major pre-split B, A in tensor memory, no split-K) whose tile width
+    // the 2-CTA MMA accepts; each CTA then stages half of the B tile
+    p.pair = (env_int("RLCTR_GEMM_PAIR", 0) != 0 && p.a_tmem && b_presplit && !b_mn && p.splits == 1 && p.m_tiles >= 2 &&
+              p.n_tile % 32 == 0) ? 1 : 0;
+    const size_t stage_bytes = (p.a_tmem ? 1 : 2) * (size_t)A_TILE_BYTES + 2 * (size_t)p.n_tile * (p.pair ? 64 : 128);
     int st = (int)((size_t)(220 * 1024) / stage_bytes);
     if (st > MAX_STAGES) st = MAX_STAGES;
     if (p.a_tmem && st > tmem_stages) st = tmem_stages;
@@ -936,8 +1023,8 @@ static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_t
     // CTA pairs sharing every B tile by TMA multicast (RLCTR_GEMM_CLUSTER=2; needs two m-tiles to pair and a B tile that halves on
     // a swizzle-atom boundary).  Off by default: measured no gain -- the kernel is bound by the shared-memory port of each SM, and a
     // multicast tile is still written into (and read by the MMAs from) every CTA's own shared memory.
-    p.cluster = 1;
-    if (env_int("RLCTR_GEMM_CLUSTER", 1) >= 2 && p.m_tiles >= 2 && (b_mn || p.n_tile % 16 == 0))
+    p.cluster = p.pair ? 2 : 1;
+    if (!p.pair && env_int("RLCTR_GEMM_CLUSTER", 1) >= 2 && p.m_tiles >= 2 && (b_mn || p.n_tile % 16 == 0))
         p.cluster = 2;
     return p;
 }
@@ -964,7 +1051,7 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     if (!enabled()) return RLCTR_EUNSUPPORTED;
     if (!tma_ok(A.ptr, A.pitch) || !tma_ok(B.ptr, B.pitch) || (B.lo && !tma_ok(B.lo, B.pitch))) return RLCTR_EUNSUPPORTED;
     if (A.lo) return RLCTR_EUNSUPPORTED;                  // the streamed operand is always converted in the kernel
-    const Plan p = make_plan(M, N, K, B.mn_major, allow_split, tma_ok(C, ldc));
+    const Plan p = make_plan(M, N, K, B.mn_major, allow_split, tma_ok(C, ldc), B.lo != nullptr);
     if (p.n_tile > 256 || (B.mn_major && p.n_tile % 32 != 0)) return RLCTR_EUNSUPPORTED;
     CUtensorMap mA, mB, mBlo;
     // K-major operand [R rows][K]: dims {K, R}, box {32, tile rows}.  MN-major operand [K rows][R]: dims {R, K}, box {32, 32}.
@@ -982,7 +1069,7 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages;
     g.a_tmem = p.a_tmem; g.acc_stride = p.acc_stride; g.a_col0 = p.a_col0; g.c_tma = p.c_tma;
-    g.cluster = p.cluster;
+    g.cluster = p.cluster; g.pair = p.pair;
     g.l2_ahead = env_int("RLCTR_GEMM_L2_AHEAD", 0);     // measured: no gain (the pipeline is L2->SM bandwidth bound, not DRAM-latency bound)
     g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
     g.colsum_part = (colsum_part && A.mn_major && !bias) ? colsum_part : nullptr;
@@ -994,7 +1081,8 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     g.epi = epi ? *epi : Epilogue{};
     if ((g.epi.drop_state || g.epi.mask_src) && p.splits != 1) return RLCTR_EUNSUPPORTED;
     if (g.epi.mask_src) g.epi.mvec = vec_of(g.epi.mask_src, g.epi.mask_ld);
-    RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    if (p.pair) RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    else RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     const int total = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_tiles * p.splits;      // cluster tiles
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(RLCTR_SMS / p.cluster * p.cluster));
@@ -1011,17 +1099,19 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     int max_clusters = RLCTR_SMS / p.cluster;
     if (p.cluster > 1) {                                   // clusters that can be resident at once (GPCs with an odd SM count lose one)
         static int cached_smem = -1, cached = 0;
-        if (cached_smem != (int)p.smem) {
+        if (cached_smem != (int)p.smem * 2 + p.pair) {
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel, &cfg) == cudaSuccess && n > 0) cached = n;
+            if ((p.pair ? cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel<true>, &cfg)
+                        : cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel<false>, &cfg)) == cudaSuccess && n > 0) cached = n;
             else cached = RLCTR_SMS / p.cluster;
-            cached_smem = (int)p.smem;
+            cached_smem = (int)p.smem * 2 + p.pair;
         }
         if (cached < max_clusters) max_clusters = cached;
     }
     const int grid = (total < max_clusters ? total : max_clusters) * p.cluster;
     cfg.gridDim = dim3((unsigned)grid);
-    RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel, mA, mB, mBlo, mC, g));
+    if (p.pair) RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<true>, mA, mB, mBlo, mC, g));
+    else RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<false>, mA, mB, mBlo, mC, g));
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -576,12 +576,14 @@ def padded(x, ld):
 
 # GEMM data paths behind environment switches (csrc/mlp_tma.cu): "tma" = the default (A operand in tensor memory, C stored by TMA),
 # "tma_smemA" = A read from shared memory + per-thread stores of C (the previous generation), "tma_pair" = the weight tile
-# multicast to a CTA pair, "staged" = the software-staged kernel of csrc/mlp.cu.
+# multicast to a CTA pair, "tma_cta2" = cta_group::2 MMAs over a CTA pair (forward-type GEMMs), "staged" = the software-staged
+# kernel of csrc/mlp.cu.
 def gemm_path(monkeypatch, path):
     monkeypatch.setenv("RLCTR_GEMM_TMA", "0" if path == "staged" else "1")
     monkeypatch.setenv("RLCTR_GEMM_A_TMEM", "0" if path == "tma_smemA" else "1")
     monkeypatch.setenv("RLCTR_GEMM_C_TMA", "0" if path == "tma_smemA" else "1")
     monkeypatch.setenv("RLCTR_GEMM_CLUSTER", "2" if path == "tma_pair" else "1")
+    monkeypatch.setenv("RLCTR_GEMM_PAIR", "1" if path == "tma_cta2" else "0")
     return "tma" if path.startswith("tma") else "staged"
 
 
@@ -590,7 +592,7 @@ def gemm_path(monkeypatch, path):
 @pytest.mark.parametrize("B,K,N", [(1, 150, 300), (128, 32, 16), (1000, 150, 300), (777, 300, 200), (513, 200, 1),
                                    (4096, 255, 1024), (300, 1024, 512), (65536, 150, 300)])
 @pytest.mark.parametrize("relu", [0, 1])
-@pytest.mark.parametrize("path", ["tma", "tma_smemA", "tma_pair", "staged"])
+@pytest.mark.parametrize("path", ["tma", "tma_smemA", "tma_pair", "tma_cta2", "staged"])
 def test_linear_fwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
     path = gemm_path(monkeypatch, path)
     x, w, b = linear_case(B, K, N, B + K + N)
