@@ -117,8 +117,10 @@ def alg_bytes(key, m):
     n = B * F
     per = N / F
     U = F * per * (1.0 - (1.0 - 1.0 / per) ** B)
+    if name == "rlctr_rows_lookup":                            # owner-side lookup: record read once, stage + gathered written
+        return float(U * (24 * logical + 4) + n * (8 + 4 * logical))
     if name == "rlctr_embed_fwd":
-        b = B * (F * 8 + F * 4 * logical + 4)
+        b = B * ((0 if m.get("streamed") else F * 8) + F * 4 * logical + 4)
         if m.get("sums"):
             b += B * 4 * logical
         if m.get("rows"):

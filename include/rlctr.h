@@ -91,7 +91,21 @@ typedef struct rlctr_adam {
      * float(1 - beta2), float(eps), float(weight_decay) exactly as torch derives them in double and casts
      * at the op (1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative) */
     double         beta1, beta2, eps, weight_decay;
+    /* rlctr_rows_lookup's staging array, or NULL.  Non-NULL (rlctr_rows_adam only): the (p | exp_avg | exp_avg_sq) of the
+     * row at sorted position k are read from stage[k * rlctr_lookup_stage_floats(table)] -- already current through *step --
+     * instead of from the table record, and nothing is replayed; the updated record is written to the table as usual. */
+    const float*   stage;
 } rlctr_adam;
+
+/* Where rlctr_rows_lookup leaves the rows of a batch.  gathered[r] is rank r's [n_per_rank, row_stride] lookup buffer as
+ * mapped into THIS process (world <= 1: gathered[0], indexed by slot); a slot of the sorted view is a GLOBAL slot
+ * src_rank * n_per_rank + slot, as in rlctr_rowgrad. */
+typedef struct rlctr_lookup {
+    float*   stage;                       /* [n, rlctr_lookup_stage_floats(table)], 16-byte aligned */
+    int32_t  world;
+    uint32_t n_per_rank;
+    float*   gathered[RLCTR_MAX_WORLD];
+} rlctr_lookup;
 
 /* Where the gradient of a gathered row comes from.  For sorted position k with
  * slot = sorted_slots[k], b = slot / fields, f = slot % fields, the row gradient is
@@ -140,6 +154,8 @@ const char* rlctr_strerror(int code);
  *   rows_out[b*rows_pitch + f*dim + d] = v_f[d]   (bit-exact copy; optional; rows_pitch = 0 means fields*dim;
  *                                                  a pitch that is a multiple of 4 floats lets the tower's first
  *                                                  GEMM fetch the rows by TMA; pad columns are never written)
+ * ids == NULL: the rows are already in sample order (table->data = rlctr_rows_lookup's `gathered`, [batch*fields, row_stride]):
+ * row (b, f) is row b*fields + f -- the streamed forward of the training step.
  * ------------------------------------------------------------------------------------ */
 #define RLCTR_FM_TERM 1
 int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, const float* bias,
@@ -278,6 +294,18 @@ int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, in
 int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                           const rlctr_rowgrad* grad, const rlctr_table* table, float* dense_grad,
                           void* ws, size_t ws_bytes, rlctr_stream_t stream);
+/* Lazy-exact mode, the owner-side LOOKUP of a training step (replaces rlctr_rows_catchup + the by-id gather of the forward;
+ * the gather side of nn.Embedding, p_model.py:23,47,54,303,311,320, under the dense-Adam semantics of SURVEY N3).  For every
+ * distinct id of the sorted view: read its record ONCE, replay in registers the L2-only Adam steps it missed (stamp+1 .. *step),
+ * leave (p | exp_avg | exp_avg_sq) in lookup->stage at its sorted position (rlctr_rows_adam takes them from there through
+ * rlctr_adam.stage: nothing is replayed twice and the table is written once per step), and WRITE the current row to every
+ * sample that gathered it: lookup->gathered[src rank][slot, :] -- for a row-sharded table that is the lookup exchange, as
+ * posted NVLink writes into the requester's buffer.  The forward then runs rlctr_embed_fwd with ids == NULL over `gathered`
+ * (sample-ordered, streamed).  The table itself is not written.  Vector rows need the in-record stamp (stamp_col >= 0) or a
+ * non-lazy optimizer, row_stride <= 16; LR records any stamp.  ws: rlctr_rows_ws_bytes(n) bytes. */
+int64_t rlctr_lookup_stage_floats(const rlctr_table* table);
+int rlctr_rows_lookup(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
+                      const rlctr_adam* opt, const rlctr_lookup* lookup, void* ws, size_t ws_bytes, rlctr_stream_t stream);
 /* Lazy-exact mode: bring every distinct id of the batch up to *step (the completed steps) by
  * replaying the L2-only Adam steps it missed (g = wd*p), so the forward reads exactly what the
  * reference's dense Adam would have produced. */
@@ -293,11 +321,16 @@ int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
 int rlctr_dense_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                      const float* sched, const int32_t* step, double beta1, double beta2, double eps,
                      double weight_decay, rlctr_stream_t stream);
-/* The same step for up to RLCTR_DENSE_MAX tensors in one launch (host arrays of device pointers / sizes; torch's foreach Adam). */
+/* The same step for up to RLCTR_DENSE_MAX tensors in one launch (host arrays of device pointers / sizes; torch's foreach Adam).
+ * torch.optim.Adam keeps one step counter PER PARAMETER (a parameter without a gradient is skipped and its counter stays):
+ * `steps` is a device int32 array of completed-step counters and tensor t uses steps[step_index[t]] (step_index: host array,
+ * NULL = every tensor uses steps[0]).  rlctr_steps_advance adds 1 to the listed counters (count <= RLCTR_DENSE_MAX). */
 #define RLCTR_DENSE_MAX 24
 int rlctr_dense_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs, float* const* exp_avg_sqs,
-                           const int64_t* sizes, int32_t count, const float* sched, const int32_t* step, double beta1, double beta2,
-                           double eps, double weight_decay, rlctr_stream_t stream);
+                           const int64_t* sizes, int32_t count, const float* sched, const int32_t* steps,
+                           const int32_t* step_index, double beta1, double beta2, double eps, double weight_decay,
+                           rlctr_stream_t stream);
+int rlctr_steps_advance(int32_t* steps, const int32_t* step_index, int32_t count, rlctr_stream_t stream);
 int rlctr_step_advance(int32_t* step, int32_t delta, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

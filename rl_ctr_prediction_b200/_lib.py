@@ -39,7 +39,13 @@ class Adam(C.Structure):
     """struct rlctr_adam"""
     _fields_ = [("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("stamp", C.c_void_p),
                 ("sched", C.c_void_p), ("step", C.c_void_p), ("sched_len", C.c_int32), ("stamp_col", C.c_int32),
-                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double)]
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+                ("stage", C.c_void_p)]
+
+
+class Lookup(C.Structure):
+    """struct rlctr_lookup"""
+    _fields_ = [("stage", C.c_void_p), ("world", C.c_int32), ("n_per_rank", C.c_uint32), ("gathered", C.c_void_p * 8)]
 
 
 class RowGrad(C.Structure):
@@ -51,7 +57,7 @@ class RowGrad(C.Structure):
 
 
 _P, _I64, _I32, _SZ, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
-_TP, _AP, _GP = C.POINTER(Table), C.POINTER(Adam), C.POINTER(RowGrad)
+_TP, _AP, _GP, _LP = C.POINTER(Table), C.POINTER(Adam), C.POINTER(RowGrad), C.POINTER(Lookup)
 
 # name -> (restype, argtypes); must list every symbol include/rlctr.h declares
 SIGNATURES = {
@@ -89,10 +95,13 @@ SIGNATURES = {
     "rlctr_rows_ws_bytes": (_SZ, [_I64]),
     "rlctr_rows_adam": (C.c_int, [_P, _P, _I64, _GP, _TP, _AP, _P, _SZ, _P]),
     "rlctr_rows_grad_dense": (C.c_int, [_P, _P, _I64, _GP, _TP, _P, _P, _SZ, _P]),
+    "rlctr_lookup_stage_floats": (_I64, [_TP]),
+    "rlctr_rows_lookup": (C.c_int, [_P, _P, _I64, _TP, _AP, _LP, _P, _SZ, _P]),
     "rlctr_rows_catchup": (C.c_int, [_P, _I64, _TP, _AP, _P]),
     "rlctr_adam_flush": (C.c_int, [_TP, _AP, _I64, _I64, _P]),
     "rlctr_dense_adam": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F, _F, _F, _F, _P]),
-    "rlctr_dense_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _F, _F, _F, _F, _P]),
+    "rlctr_dense_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _F, _F, _F, _F, _P]),
+    "rlctr_steps_advance": (C.c_int, [_P, _P, _I32, _P]),
     "rlctr_step_advance": (C.c_int, [_P, _I32, _P]),
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),

@@ -10,6 +10,9 @@
 
 namespace rlctr {
 
+// id of gathered element e = b * fields + f; ids == NULL: the rows are already in sample order (rlctr_rows_lookup's `gathered`)
+__device__ __forceinline__ int64_t id_at(const int64_t* __restrict__ ids, int64_t e) { return ids ? __ldg(ids + e) : e; }
+
 // ------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------
@@ -40,16 +43,16 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
     int64_t b = warp0;
     int64_t id_a = -1, id_b = -1;                   // first two row slots of the next sample
     if (b < batch && chunk_on) {
-        if (g < fields) id_a = __ldg(ids + b * fields + g);
-        if (g + RPW < fields) id_b = __ldg(ids + b * fields + g + RPW);
+        if (g < fields) id_a = id_at(ids, b * fields + g);
+        if (g + RPW < fields) id_b = id_at(ids, b * fields + g + RPW);
     }
     for (; b < batch; b += nwarps) {
         const int64_t cur_a = id_a, cur_b = id_b;
         const int64_t nb = b + nwarps;
         id_a = -1; id_b = -1;
         if (nb < batch && chunk_on) {
-            if (g < fields) id_a = __ldg(ids + nb * fields + g);
-            if (g + RPW < fields) id_b = __ldg(ids + nb * fields + g + RPW);
+            if (g < fields) id_a = id_at(ids, nb * fields + g);
+            if (g + RPW < fields) id_b = id_at(ids, nb * fields + g + RPW);
         }
         float4 s = f4zero();
         float q = 0.f;
@@ -58,8 +61,8 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
             int64_t ia = -1, ib = -1;
             if (f0 == 0) { ia = cur_a; ib = cur_b; }
             else if (chunk_on) {
-                if (fa < fields) ia = __ldg(ids + b * fields + fa);
-                if (fb < fields) ib = __ldg(ids + b * fields + fb);
+                if (fa < fields) ia = id_at(ids, b * fields + fa);
+                if (fb < fields) ib = id_at(ids, b * fields + fb);
             }
             float4 ra = f4zero(), rb = f4zero();
             const bool oka = (uint64_t)ia < (uint64_t)n_rows, okb = (uint64_t)ib < (uint64_t)n_rows;
@@ -125,7 +128,7 @@ embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict
     for (int64_t b = warp0; b < batch; b += nwarps) {
         float s = 0.f;
         for (int f = lane; f < fields; f += 32) {
-            const int64_t id = __ldg(ids + b * fields + f);
+            const int64_t id = id_at(ids, b * fields + f);
             if ((uint64_t)id < (uint64_t)n_rows) s += __ldg(row_ptr(tab, sv, id, pitch));
         }
 #pragma unroll
@@ -331,7 +334,8 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
                                rlctr_stream_t stream) {
     int rc = check_table(table);
     if (rc) return rc;
-    if (!ids || batch < 0 || fields <= 0) return RLCTR_EINVAL;
+    if (batch < 0 || fields <= 0) return RLCTR_EINVAL;
+    if (!ids && (table->world > 1 || table->n_rows < batch * fields)) return RLCTR_EINVAL;   // sample-ordered rows: local
     if (batch == 0) return RLCTR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int rs = table->row_stride;

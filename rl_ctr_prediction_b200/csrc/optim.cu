@@ -13,6 +13,8 @@
 // (mode B).  With stamp == NULL untouched rows are left alone (mode C, "sparse").
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rlctr {
@@ -41,11 +43,15 @@ struct AdamView {
     const float2* sched;
     const int32_t* step;
     AdamHyper h;
+    const float* stage;  // rlctr_rows_lookup's staging array: (p | exp_avg | exp_avg_sq) of the row at sorted position k, already
+    int stage_pitch;     // current through *step -- the update reads it instead of the table record (floats per position)
 };
-static inline AdamView view_of(const rlctr_adam* a) {
+// floats per sorted position of the staging array: three blocks of the row's ACTIVE chunks (LR: one float4 [w, m, v, 0])
+static inline int stage_pitch_of(const TableView& t) { return t.rs == 1 ? 4 : 3 * ((t.used + 3) & ~3); }
+static inline AdamView view_of(const rlctr_adam* a, const TableView& t) {
     return AdamView{a->exp_avg, a->exp_avg_sq, a->stamp_col >= 0 ? nullptr : a->stamp, a->stamp_col >= 0 ? a->stamp_col : -1,
                     reinterpret_cast<const float2*>(a->sched), a->step,
-                    adam_hyper(a->beta1, a->beta2, a->eps, a->weight_decay)};
+                    adam_hyper(a->beta1, a->beta2, a->eps, a->weight_decay), a->stage, stage_pitch_of(t)};
 }
 __device__ __forceinline__ bool is_lazy(const AdamView& a) { return a.stamp != nullptr || a.stamp_col >= 0; }
 __device__ __forceinline__ int load_stamp(const TableView& t, const AdamView& a, int64_t id) {
@@ -121,41 +127,69 @@ sort_prep_sharded_kernel(const uint32_t* __restrict__ ids_all, int64_t n_all, in
     }
 }
 
-// gradient of columns col0..col0+3 of the row gathered at `slot` (rlctr_rowgrad in rlctr.h)
-__device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t gslot, int col0, const float4& p,
-                                                const TableView& t) {
+// gradient of columns col0..col0+3 of the row gathered at `slot` (rlctr_rowgrad in rlctr.h), in two halves so that a kernel can
+// issue the loads of several rows before it consumes any of them: rowgrad_load (memory) and rowgrad_combine (arithmetic)
+struct GradRaw {
+    float4 r;            // staged[slot]
+    float4 S;            // sums[b]
+    float dz;
+    float ex[4];         // extra[b, f*dim + col - emb_col]
+    bool fm, has_ex, any;
+};
+__device__ __forceinline__ GradRaw rowgrad_load(const GradView& g, uint32_t gslot, int col0, const TableView& t) {
     const GradSrc q = grad_src(g, gslot);
     const uint32_t slot = q.slot;
-    float4 r = f4zero();
-    if (q.staged) r = ldg4(q.staged + (int64_t)slot * t.rs + col0);
+    GradRaw w;
+    w.r = f4zero(); w.S = f4zero(); w.dz = 0.f; w.fm = false; w.has_ex = false; w.any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w.ex[k] = 0.f;
+    if (q.staged) w.r = ldg4(q.staged + (int64_t)slot * t.rs + col0);
     if (g.flags & RLCTR_STAGED_PARTNER) {               // FFM: d z / d row is staged, scale by dL/dz
-        const float dz = __ldg(q.dlogit + slot / (uint32_t)g.fields);
-        return make_float4(dz * r.x, dz * r.y, dz * r.z, dz * r.w);
+        w.dz = __ldg(q.dlogit + slot / (uint32_t)g.fields);
+        return w;
     }
     if (q.dlogit || q.extra) {
+        w.any = true;
         const uint32_t b = slot / (uint32_t)g.fields;
         const uint32_t f = slot - b * (uint32_t)g.fields;
-        const bool fm = q.sums && q.dlogit;
-        float dz = 0.f;
-        if (fm && (g.flags & RLCTR_DZ_IN_SUMS)) dz = __ldg(q.sums + (int64_t)b * t.rs + (t.rs - 1));   // same line as S
-        else if (q.dlogit) dz = __ldg(q.dlogit + b);
-        float4 S = f4zero();
-        if (fm) S = ldg4(q.sums + (int64_t)b * t.rs + col0);
-        const float* ex = q.extra ? q.extra + ((int64_t)b * g.fields + f) * t.dim : nullptr;
+        w.fm = q.sums && q.dlogit;
+        if (w.fm && (g.flags & RLCTR_DZ_IN_SUMS)) w.dz = __ldg(q.sums + (int64_t)b * t.rs + (t.rs - 1));   // same line as S
+        else if (q.dlogit) w.dz = __ldg(q.dlogit + b);
+        if (w.fm) w.S = ldg4(q.sums + (int64_t)b * t.rs + col0);
+        if (q.extra) {
+            w.has_ex = true;
+            const float* ex = q.extra + ((int64_t)b * g.fields + f) * t.dim;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = col0 + k;
+                if (col >= t.emb_col && col < t.emb_col + t.dim) w.ex[k] = __ldg(ex + col - t.emb_col);
+            }
+        }
+    }
+    return w;
+}
+__device__ __forceinline__ float4 rowgrad_combine(const GradView& g, const GradRaw& w, int col0, const float4& p, const TableView& t) {
+    float4 r = w.r;
+    if (g.flags & RLCTR_STAGED_PARTNER) return make_float4(w.dz * r.x, w.dz * r.y, w.dz * r.z, w.dz * r.w);
+    if (w.any) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int col = col0 + k;
             float add = 0.f;
             if (col == t.lin_col) {
-                add = dz;
+                add = w.dz;
             } else if (col >= t.emb_col && col < t.emb_col + t.dim) {
-                if (fm) add = dz * (f4get(S, k) - f4get(p, k));
-                if (ex) add += __ldg(ex + col - t.emb_col);
+                if (w.fm) add = w.dz * (f4get(w.S, k) - f4get(p, k));
+                if (w.has_ex) add += w.ex[k];
             }
             f4set(r, k, f4get(r, k) + add);
         }
     }
     return r;
+}
+__device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t gslot, int col0, const float4& p,
+                                                const TableView& t) {
+    return rowgrad_combine(g, rowgrad_load(g, gslot, col0, t), col0, p, t);
 }
 
 __device__ __forceinline__ void adam_apply4(float4& p, float4& m, float4& v, const float4& g, float2 s,
@@ -177,7 +211,7 @@ __device__ __forceinline__ void finish_row(int64_t id, int col0, float4 p, const
     }
     const int64_t off = id * t.pitch + col0;
     float4 m = m_pre ? *m_pre : ld4(a.m + off), v = v_pre ? *v_pre : ld4(a.v + off);
-    if (is_lazy(a) && stamp_in < step - 1) adam_replay4(p, m, v, stamp_in, step - 1, a.sched, a.h);
+    if (is_lazy(a) && !a.stage && stamp_in < step - 1) adam_replay4(p, m, v, stamp_in, step - 1, a.sched, a.h);
     adam_apply4(p, m, v, acc, __ldg(&a.sched[step]), a.h);
     embed_stamp(p, col0, a, step);
     st4(t.data + off, p);
@@ -220,14 +254,21 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
     const bool work = head && col0 < ((APPLY == 0) ? ((t.used + 3) & ~3) : t.rs);
     int step = 0, stamp_in = 0;
     if (work) {
+        const bool staged = APPLY == 0 && a.stage != nullptr;
         if (APPLY == 0) {
             step = __ldg(a.step) + 1;
-            if (is_lazy(a)) stamp_in = load_stamp(t, a, id);
+            if (is_lazy(a) && !staged) stamp_in = load_stamp(t, a, id);
         }
         const int64_t off = (int64_t)id * t.pitch + col0;
-        const float4 p = ld4(t.data + off);
-        float4 m0 = f4zero(), v0 = f4zero();             // issued with p: one contiguous record when pitch = 3*rs
-        if (APPLY == 0) { m0 = ld4(a.m + off); v0 = ld4(a.v + off); }
+        float4 p, m0 = f4zero(), v0 = f4zero();
+        if (staged) {                                    // (p | m | v) of this position, replayed by rlctr_rows_lookup: coalesced
+            const float* sp = a.stage + k * a.stage_pitch + col0;
+            const int blk = a.stage_pitch / 3;
+            p = ldg4(sp); m0 = ldg4(sp + blk); v0 = ldg4(sp + 2 * blk);
+        } else {
+            p = ld4(t.data + off);                       // issued with m, v: one contiguous record when pitch = 3*rs
+            if (APPLY == 0) { m0 = ld4(a.m + off); v0 = ld4(a.v + off); }
+        }
         float4 acc = rowgrad_chunk(g, slot0, col0, p, t);
         int64_t kk = k + 1;
         uint32_t nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
@@ -237,14 +278,220 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
             nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
             acc = f4add(acc, rowgrad_chunk(g, slot, col0, p, t));
         }
-        if (APPLY == 0 && a.stamp_col >= 0) __syncwarp(__activemask());   // every chunk lane has read the in-record stamp
+        if (APPLY == 0 && a.stamp_col >= 0 && !staged) __syncwarp(__activemask());   // every chunk lane has read the in-record stamp
         finish_row<APPLY>(id, col0, p, acc, t, a, dense_grad, step, stamp_in, &m0, &v0);
+    } else if (APPLY == 0 && a.stage != nullptr && head && col0 < t.rs) {
+        // staged update: the record was NOT read by this kernel, so its lines are not in L2.  Writing only the active chunks
+        // would leave half-written 32-byte sectors that L2 has to fill from DRAM first (ncu: +94 MB of reads per launch);
+        // the padding chunks are zero by construction (p = m = v = 0 stays 0 under Adam), so write them too: whole 64 B blocks.
+        const int64_t off = (int64_t)id * t.pitch + col0;
+        st4(t.data + off, f4zero());
+        st4(a.m + off, f4zero());
+        st4(a.v + off, f4zero());
     }
     if (APPLY == 0 && a.stamp) {
         __syncwarp();                                    // all chunk lanes read the stamp before lane 0 rewrites it
         if (work && c == 0) a.stamp[id] = step;
     }
     }
+}
+
+// Update from the lookup's staging array (rlctr_adam.stage): nothing here is a random READ of the table -- (p | m | v) of sorted
+// position k arrive as a coalesced stream, the gradient side comes from L2-resident per-sample arrays -- so the kernel is a
+// latency pipeline, not a gather.  Each lane group owns R positions per trip and works in three phases: (A) ids / neighbours /
+// first slots of all R, (B) every load of all R head rows (stage chunks + gradient side), (C) reduce, Adam, one record write
+// each (whole 64-byte blocks).  R rows per lane in flight instead of one, ~20x fewer block launches than one position per thread.
+template <int LPR, int R>
+__global__ void __launch_bounds__(256, (R > 2 ? 1 : 2))
+rows_staged_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                   const __grid_constant__ GradView g, const __grid_constant__ TableView t, const __grid_constant__ AdamView a,
+                   int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    constexpr int GPB = 256 / LPR;                       // lane groups per block
+    const int grp = threadIdx.x / LPR, c = threadIdx.x % LPR, col0 = 4 * c;
+    const int blk = a.stage_pitch / 3;                   // floats per (p | m | v) block of a staged row
+    const bool chunk_on = col0 < blk;
+    const bool pad_on = !chunk_on && col0 < t.rs;
+    const int step = __ldg(a.step) + 1;
+    const float2 sc = __ldg(&a.sched[step]);
+    for (int64_t base = (int64_t)blockIdx.x * (GPB * R); base < n; base += (int64_t)gridDim.x * (GPB * R)) {
+        if (__ldg(sorted_ids + base) >= (uint64_t)t.n_rows) return;     // sorted: nothing but sentinels from here on
+        uint32_t id[R], slot0[R];
+        bool head[R], multi[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                    // (A) consecutive lane groups take consecutive positions
+            const int64_t k = base + r * GPB + grp;
+            id[r] = 0xffffffffu; slot0[r] = 0; head[r] = false; multi[r] = false;
+            if (k < n) {
+                id[r] = __ldg(sorted_ids + k);
+                const uint32_t prev = k > 0 ? __ldg(sorted_ids + k - 1) : 0xffffffffu;
+                const uint32_t nxt = (k + 1 < n) ? __ldg(sorted_ids + k + 1) : 0xffffffffu;
+                const uint32_t far = (k + LONG_RUN < n) ? __ldg(sorted_ids + k + LONG_RUN) : 0xffffffffu;
+                slot0[r] = __ldg(sorted_slots + k);
+                head[r] = (id[r] < (uint64_t)t.n_rows) && prev != id[r];
+                if (head[r] && far == id[r]) {
+                    if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)k;
+                    head[r] = false;
+                }
+                multi[r] = head[r] && nxt == id[r];
+            }
+        }
+        float4 p[R], m[R], v[R];
+        GradRaw gr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                    // (B) all loads of all R rows
+            if (head[r] && chunk_on) {
+                const float* sp = a.stage + (base + r * GPB + grp) * a.stage_pitch + col0;
+                p[r] = ldg4(sp); m[r] = ldg4(sp + blk); v[r] = ldg4(sp + 2 * blk);
+                gr[r] = rowgrad_load(g, slot0[r], col0, t);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                    // (C)
+            if (!head[r]) continue;
+            const int64_t off = (int64_t)id[r] * t.pitch + col0;
+            if (chunk_on) {
+                float4 acc = rowgrad_combine(g, gr[r], col0, p[r], t);
+                if (multi[r]) {                          // further occurrences of the same row, in slot order
+                    int64_t kk = base + r * GPB + grp + 1;
+                    uint32_t nx = id[r];
+                    while (nx == id[r]) {
+                        const uint32_t slot = __ldg(sorted_slots + kk);
+                        ++kk;
+                        nx = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
+                        acc = f4add(acc, rowgrad_chunk(g, slot, col0, p[r], t));
+                    }
+                }
+                float4 pp = p[r], mm = m[r], vv = v[r];
+                adam_apply4(pp, mm, vv, acc, sc, a.h);
+                embed_stamp(pp, col0, a, step);
+                st4(t.data + off, pp);
+                st4(a.m + off, mm);
+                st4(a.v + off, vv);
+            } else if (pad_on) {                         // padding chunks are zero by construction: whole 64 B blocks, no sector fills
+                st4(t.data + off, f4zero());
+                st4(a.m + off, f4zero());
+                st4(a.v + off, f4zero());
+            }
+        }
+    }
+}
+
+// The same update as a persistent, double-buffered tile pipeline: what streams (the staged rows, the ids and the slots of a tile
+// of sorted positions) is copied global -> shared memory ASYNCHRONOUSLY (cp.async, no registers held, no thread waiting) one
+// tile ahead of the arithmetic, so the only latency a thread ever waits for is the L2 hit of its gradient-side loads; the record
+// writes are the kernel's DRAM traffic.  Tile = TT positions; a lane group (4 lanes) takes positions g and g + 64 of the tile.
+namespace tile {
+constexpr int TT = 128;                                  // sorted positions per tile
+constexpr int IDS = TT + 4 + LONG_RUN;                   // ids k0-4 .. k0+TT+LONG_RUN-1 (previous id at [3], far id at [4+j+LONG_RUN])
+__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int CH> struct Buf {
+    float rows[TT * 12 * CH];
+    uint32_t ids[IDS];
+    uint32_t slots[TT];
+};
+template <int CH>
+__device__ __forceinline__ void issue(Buf<CH>& b, int64_t tile, int64_t n, const float* __restrict__ stage,
+                                      const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots) {
+    constexpr int RF = 12 * CH;
+    const int64_t k0 = tile * TT;
+    const int64_t rows_here = (n - k0 < TT) ? (n - k0) : TT;
+    for (int i = threadIdx.x; i < rows_here * (RF / 4); i += blockDim.x) cp16(b.rows + 4 * i, stage + k0 * RF + 4 * i);
+    for (int i = threadIdx.x; i < IDS / 4; i += blockDim.x) {
+        const int64_t kk = k0 - 4 + 4 * i;
+        if (kk >= 0 && kk + 4 <= n) cp16(b.ids + 4 * i, sorted_ids + kk);
+        else
+            for (int e = 0; e < 4; ++e) b.ids[4 * i + e] = (kk + e >= 0 && kk + e < n) ? __ldg(sorted_ids + kk + e) : 0xffffffffu;
+    }
+    for (int i = threadIdx.x; i < TT / 4; i += blockDim.x) {
+        const int64_t kk = k0 + 4 * i;
+        if (kk + 4 <= n) cp16(b.slots + 4 * i, sorted_slots + kk);
+        else
+            for (int e = 0; e < 4; ++e) b.slots[4 * i + e] = (kk + e < n) ? __ldg(sorted_slots + kk + e) : 0u;
+    }
+    cp_commit();
+}
+}  // namespace tile
+template <int CH>
+__global__ void __launch_bounds__(256, 3)
+rows_staged_tile_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                        const __grid_constant__ GradView g, const __grid_constant__ TableView t, const __grid_constant__ AdamView a,
+                        int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    using namespace tile;
+    constexpr int RF = 12 * CH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Buf<CH>* bufs = reinterpret_cast<Buf<CH>*>(smem_raw);
+    const int grp = threadIdx.x >> 2, c = threadIdx.x & 3, col0 = 4 * c;
+    const bool chunk_on = c < CH;
+    const bool pad_on = !chunk_on && col0 < t.rs;
+    const int step = __ldg(a.step) + 1;
+    const float2 sc = __ldg(&a.sched[step]);
+    const int64_t tiles = (n + TT - 1) / TT;
+    int64_t tl = blockIdx.x;
+    if (tl >= tiles) return;
+    int cur = 0;
+    issue<CH>(bufs[0], tl, n, a.stage, sorted_ids, sorted_slots);
+    for (; tl < tiles; tl += gridDim.x, cur ^= 1) {
+        const int64_t nt = tl + gridDim.x;
+        if (nt < tiles) { issue<CH>(bufs[cur ^ 1], nt, n, a.stage, sorted_ids, sorted_slots); cp_wait<1>(); }
+        else cp_wait<0>();
+        __syncthreads();
+        const Buf<CH>& b = bufs[cur];
+        if (b.ids[4] >= (uint64_t)t.n_rows) break;       // sorted: this tile and every later one hold sentinels only
+        const int64_t k0 = tl * TT;
+        uint32_t id[2];
+        bool head[2], multi[2];
+        GradRaw gr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = grp + 64 * r;
+            id[r] = b.ids[4 + j];
+            head[r] = (k0 + j < n) && (id[r] < (uint64_t)t.n_rows) && b.ids[3 + j] != id[r];
+            if (head[r] && b.ids[4 + j + LONG_RUN] == id[r]) {
+                if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)(k0 + j);
+                head[r] = false;
+            }
+            multi[r] = head[r] && b.ids[5 + j] == id[r];
+            if (head[r] && chunk_on) gr[r] = rowgrad_load(g, b.slots[j], col0, t);      // both rows' loads before either is used
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!head[r]) continue;
+            const int j = grp + 64 * r;
+            const int64_t off = (int64_t)id[r] * t.pitch + col0;
+            if (chunk_on) {
+                const float* sp = b.rows + j * RF + col0;
+                float4 pp = *reinterpret_cast<const float4*>(sp);
+                float4 mm = *reinterpret_cast<const float4*>(sp + 4 * CH);
+                float4 vv = *reinterpret_cast<const float4*>(sp + 8 * CH);
+                float4 acc = rowgrad_combine(g, gr[r], col0, pp, t);
+                if (multi[r]) {                          // further occurrences of the same row, in slot order
+                    int64_t kk = k0 + j + 1;
+                    uint32_t nx = id[r];
+                    while (nx == id[r]) {
+                        const uint32_t slot = __ldg(sorted_slots + kk);
+                        ++kk;
+                        nx = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
+                        acc = f4add(acc, rowgrad_chunk(g, slot, col0, pp, t));
+                    }
+                }
+                adam_apply4(pp, mm, vv, acc, sc, a.h);
+                embed_stamp(pp, col0, a, step);
+                st4(t.data + off, pp);
+                st4(a.m + off, mm);
+                st4(a.v + off, vv);
+            } else if (pad_on) {                         // padding chunks are zero by construction: whole 64 B blocks, no sector fills
+                st4(t.data + off, f4zero());
+                st4(a.m + off, f4zero());
+                st4(a.v + off, f4zero());
+            }
+        }
+        __syncthreads();                                 // everyone is done with bufs[cur] before the next trip refills it
+    }
+    cp_wait<0>();
 }
 
 // block per long run: NSUB lane-groups stride the run, fixed-shape tree in shared memory
@@ -274,13 +521,15 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
         const int64_t end = s_end;
         float4 p = f4zero(), acc = f4zero();
         int step = 0, stamp_in = 0;
+        const bool staged = APPLY == 0 && a.stage != nullptr;
+        const float* sp = staged ? a.stage + k * a.stage_pitch + col0 : nullptr;
         if (chunk_on) {
-            p = ld4(t.data + (int64_t)id * t.pitch + col0);
+            p = (staged && col0 < a.stage_pitch / 3) ? ldg4(sp) : ld4(t.data + (int64_t)id * t.pitch + col0);
             for (int64_t kk = k + sub; kk < end; kk += NSUB)
                 acc = f4add(acc, rowgrad_chunk(g, __ldg(sorted_slots + kk), col0, p, t));
             if (APPLY == 0 && sub == 0) {
                 step = __ldg(a.step) + 1;
-                if (is_lazy(a)) stamp_in = load_stamp(t, a, id);
+                if (is_lazy(a) && !staged) stamp_in = load_stamp(t, a, id);
             }
         }
         red[threadIdx.x] = acc;
@@ -289,7 +538,20 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
             if (sub < half) red[threadIdx.x] = f4add(red[threadIdx.x], red[threadIdx.x + half * LPR]);
             __syncthreads();
         }
-        if (sub == 0 && chunk_on) finish_row<APPLY>(id, col0, p, red[threadIdx.x], t, a, dense_grad, step, stamp_in);
+        if (sub == 0 && chunk_on) {
+            if (staged) {
+                if (col0 < a.stage_pitch / 3) {          // padding chunks carry no parameters: they are never touched
+                    const int blk = a.stage_pitch / 3;
+                    const float4 m0 = ldg4(sp + blk), v0 = ldg4(sp + 2 * blk);
+                    finish_row<APPLY>(id, col0, p, red[threadIdx.x], t, a, dense_grad, step, stamp_in, &m0, &v0);
+                } else {                                  // whole 64 B blocks (see rows_short_kernel)
+                    const int64_t off = (int64_t)id * t.pitch + col0;
+                    st4(t.data + off, f4zero()); st4(a.m + off, f4zero()); st4(a.v + off, f4zero());
+                }
+            } else {
+                finish_row<APPLY>(id, col0, p, red[threadIdx.x], t, a, dense_grad, step, stamp_in);
+            }
+        }
         __syncthreads();
         if (APPLY == 0 && a.stamp && threadIdx.x == 0) a.stamp[id] = __ldg(a.step) + 1;
     }
@@ -514,6 +776,207 @@ static int launch_replay_rows(const TableView& t, const AdamView& a, int64_t r0,
     return RLCTR_OK;
 }
 
+// ---- rlctr_rows_lookup: the owner-side pass of the lazy-exact step ---------------------------------------------------------
+// One pass over the sorted view replaces "catch-up (read + WRITE every touched record), then gather the rows again by id":
+//   * every run head reads its record once (the only random DRAM access of the forward side), replays the L2-only steps the
+//     row missed IN REGISTERS (per-lane queues as in replay_rows_kernel: no lane waits for another row's staleness),
+//   * leaves (p | m | v), current through *step, in the staging array at its sorted position k -- the update kernel reads that
+//     (coalesced) instead of the table record, so nothing is replayed twice and the table is written once per step, and
+//   * PUSHES the current row to every sample that asked for it: gathered[src rank][slot] (for a sharded table a posted NVLink
+//     write into the requester's buffer: the lookup exchange).  The forward then streams its samples' rows from `gathered`.
+struct LookupView {
+    float* stage;
+    float* gathered[RLCTR_MAX_WORLD];
+    int world;
+    uint32_t n_per_rank;
+    int rs;              // floats per gathered row
+};
+__device__ __forceinline__ float* gathered_row(const LookupView& lk, uint32_t gslot) {
+    if (lk.world <= 1) return lk.gathered[0] + (int64_t)gslot * lk.rs;
+    const uint32_t src = gslot / lk.n_per_rank;
+    return lk.gathered[src] + (int64_t)(gslot - src * lk.n_per_rank) * lk.rs;
+}
+// One LANE GROUP (4 lanes, a 16-byte chunk of p, m and v each) owns a queue of sorted positions g, g + G, g + 2G ...: every access
+// of a record, a staged row or a gathered row is one coalesced 48 / 64-byte request per group.  The groups of a warp advance
+// through their queues independently (a group that finishes a row hands it out and switches to the next one, whose record was
+// requested a whole row earlier), so no group waits for another row's staleness and the replay loop runs with all groups busy.
+struct LookupItem {
+    float4 p, m, v;
+    int64_t off;         // float offset of this lane's chunk of the record; -1: nothing at this position; -2: end of the owned ids
+    uint32_t id, slot0, next_id, far_id;
+};
+__device__ __forceinline__ void lookup_issue(LookupItem& it, int64_t row, int64_t k, int64_t n, int col0, bool chunk_on, const TableView& t,
+                                             const AdamView& a, const uint32_t* __restrict__ sorted_ids,
+                                             const uint32_t* __restrict__ sorted_slots) {
+    it.off = row < 0 ? row : row * t.pitch + col0;
+    it.p = f4zero(); it.m = f4zero(); it.v = f4zero();
+    if (row >= 0) {
+        it.id = (uint32_t)row;
+        it.slot0 = __ldg(sorted_slots + k);
+        it.next_id = (k + 1 < n) ? __ldg(sorted_ids + k + 1) : 0xffffffffu;
+        it.far_id = (k + LONG_RUN < n) ? __ldg(sorted_ids + k + LONG_RUN) : 0xffffffffu;
+        if (chunk_on) {
+            it.p = ld4(t.data + it.off);
+            it.m = ld4(a.m + it.off);
+            it.v = ld4(a.v + it.off);
+        }
+    }
+}
+template <int CH>
+__global__ void __launch_bounds__(256, 4)
+lookup_rows_kernel(const __grid_constant__ TableView t, const __grid_constant__ AdamView a, const __grid_constant__ LookupView lk, int64_t n,
+                   const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots,
+                   int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    constexpr int LPR = 4;
+    const int lane = threadIdx.x & 31;
+    const int c = lane & (LPR - 1), col0 = 4 * c;
+    const bool chunk_on = c < CH;
+    const unsigned gmask = 0xfu << (lane & ~(LPR - 1));                 // the four lanes of this group (always converged)
+    const int stamp_lane = (lane & ~(LPR - 1)) + (a.stamp_col >= 0 ? (a.stamp_col >> 2) : 0);
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) / LPR;     // groups in the grid
+    const int upto = __ldg(a.step);
+    const bool lazy = a.stamp_col >= 0;
+    int64_t kc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    if (kc >= n) return;
+    LookupItem cur, nxt;
+    lookup_issue(cur, replay_row_of<true>(kc, n, 0, sorted_ids, t.n_rows), kc, n, col0, chunk_on, t, a, sorted_ids, sorted_slots);
+    lookup_issue(nxt, replay_row_of<true>(kc + stride, n, 0, sorted_ids, t.n_rows), kc + stride, n, col0, chunk_on, t, a, sorted_ids,
+                 sorted_slots);
+    int64_t row2 = replay_row_of<true>(kc + 2 * stride, n, 0, sorted_ids, t.n_rows);
+    if (cur.off == -2) return;
+    int cur_t = upto;
+    if (lazy) {
+        const int st = __shfl_sync(gmask, __float_as_int(f4get(cur.p, a.stamp_col & 3)), stamp_lane);
+        if (cur.off >= 0) cur_t = st;
+    }
+    while (true) {
+        if (cur_t >= upto) {                             // the row is up to date: hand it out, switch to the next one
+            if (cur.off >= 0) {
+                if (chunk_on) {
+                    float* sp = lk.stage + kc * (12 * CH) + col0;
+                    st4(sp, cur.p);
+                    st4(sp + 4 * CH, cur.m);
+                    st4(sp + 8 * CH, cur.v);
+                }
+                if (lazy && c == (a.stamp_col >> 2)) f4set(cur.p, a.stamp_col & 3, 0.f);      // clean padding column for the samples
+                if (cur.far_id == cur.id) {              // heavy-hitter id: its occurrences are served by lookup_long_kernel
+                    if (c == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)kc;
+                } else {
+                    uint32_t slot = cur.slot0, nid = cur.next_id;
+                    int64_t kk = kc;
+                    while (true) {
+                        if (col0 < lk.rs) st4(gathered_row(lk, slot) + col0, cur.p);          // whole row: padding chunks are zero
+                        if (nid != cur.id) break;
+                        ++kk;
+                        slot = __ldg(sorted_slots + kk);
+                        nid = (kk + 1 < n) ? __ldg(sorted_ids + kk + 1) : 0xffffffffu;
+                    }
+                }
+            }
+            kc += stride;
+            if (kc >= n || nxt.off == -2) break;
+            cur = nxt;
+            lookup_issue(nxt, row2, kc + stride, n, col0, chunk_on, t, a, sorted_ids, sorted_slots);
+            row2 = replay_row_of<true>(kc + 2 * stride, n, 0, sorted_ids, t.n_rows);
+            cur_t = upto;
+            if (lazy) {
+                const int st = __shfl_sync(gmask, __float_as_int(f4get(cur.p, a.stamp_col & 3)), stamp_lane);
+                if (cur.off >= 0) cur_t = st;
+            }
+            continue;
+        }
+        ++cur_t;
+        adam_l2_step4(cur.p, cur.m, cur.v, __ldg(&a.sched[cur_t]), a.h);
+    }
+}
+// block per heavy-hitter run: every occurrence gets the staged (current) row
+template <int CH>
+__global__ void __launch_bounds__(256)
+lookup_long_kernel(const __grid_constant__ LookupView lk, int64_t n, const uint32_t* __restrict__ sorted_ids,
+                   const uint32_t* __restrict__ sorted_slots, const int32_t* __restrict__ long_count,
+                   const uint32_t* __restrict__ long_list, int stamp_col) {
+    __shared__ int64_t s_end;
+    __shared__ float4 s_p[CH];
+    const int nlong = *long_count;
+    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        const int64_t k = long_list[li];
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (threadIdx.x == 0) {
+            int64_t lo = k, hi = n;
+            while (hi - lo > 1) {
+                int64_t mid = (lo + hi) >> 1;
+                if (__ldg(sorted_ids + mid) == id) lo = mid; else hi = mid;
+            }
+            s_end = hi;
+        }
+        if (threadIdx.x < CH) {
+            float4 p = ld4(lk.stage + k * (12 * CH) + 4 * threadIdx.x);
+            if (stamp_col >= 0 && (stamp_col >> 2) == (int)threadIdx.x) f4set(p, stamp_col & 3, 0.f);
+            s_p[threadIdx.x] = p;
+        }
+        __syncthreads();
+        const int rch = lk.rs >> 2;                          // whole rows (padding chunks zero)
+        const int64_t items = (s_end - k) * rch;
+        for (int64_t i = threadIdx.x; i < items; i += blockDim.x) {
+            const int64_t kk = k + i / rch;
+            const int c = (int)(i % rch);
+            st4(gathered_row(lk, __ldg(sorted_slots + kk)) + 4 * c, c < CH ? s_p[c] : f4zero());
+        }
+        __syncthreads();
+    }
+}
+// LR records [w | m | v | stamp]: one lane per sorted position
+__global__ void __launch_bounds__(256)
+lookup_scalar_kernel(TableView t, AdamView a, const __grid_constant__ LookupView lk, int64_t n, const uint32_t* __restrict__ sorted_ids,
+                     const uint32_t* __restrict__ sorted_slots, int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    const int upto = __ldg(a.step);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (id >= (uint64_t)t.n_rows) return;              // sentinel tail
+        if (k > 0 && __ldg(sorted_ids + k - 1) == id) continue;
+        const uint32_t slot0 = __ldg(sorted_slots + k);
+        const uint32_t next_id = (k + 1 < n) ? __ldg(sorted_ids + k + 1) : 0xffffffffu;
+        const uint32_t far_id = (k + LONG_RUN < n) ? __ldg(sorted_ids + k + LONG_RUN) : 0xffffffffu;
+        const int64_t o = (int64_t)id * t.pitch;
+        float p = t.data[o], m = a.m[o], v = a.v[o];
+        if (is_lazy(a)) adam_replay1(p, m, v, load_stamp(t, a, id), upto, a.sched, a.h);
+        st4(lk.stage + 4 * k, make_float4(p, m, v, 0.f));
+        if (far_id == id) { long_list[atomicAdd(long_count, 1)] = (uint32_t)k; continue; }
+        uint32_t slot = slot0, nid = next_id;
+        int64_t kk = k;
+        while (true) {
+            *gathered_row(lk, slot) = p;
+            if (nid != id) break;
+            ++kk;
+            slot = __ldg(sorted_slots + kk);
+            nid = (kk + 1 < n) ? __ldg(sorted_ids + kk + 1) : 0xffffffffu;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+lookup_long_scalar_kernel(const __grid_constant__ LookupView lk, int64_t n, const uint32_t* __restrict__ sorted_ids,
+                          const uint32_t* __restrict__ sorted_slots, const int32_t* __restrict__ long_count,
+                          const uint32_t* __restrict__ long_list) {
+    __shared__ int64_t s_end;
+    const int nlong = *long_count;
+    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        const int64_t k = long_list[li];
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (threadIdx.x == 0) {
+            int64_t lo = k, hi = n;
+            while (hi - lo > 1) {
+                int64_t mid = (lo + hi) >> 1;
+                if (__ldg(sorted_ids + mid) == id) lo = mid; else hi = mid;
+            }
+            s_end = hi;
+        }
+        __syncthreads();
+        const float p = lk.stage[4 * k];
+        for (int64_t kk = k + threadIdx.x; kk < s_end; kk += blockDim.x) *gathered_row(lk, __ldg(sorted_slots + kk)) = p;
+        __syncthreads();
+    }
+}
+
 // stamps are written after the replay kernel has completed (the chunks of one row are replayed by
 // different threads, each of which reads the row's stamp)
 __global__ void __launch_bounds__(256)
@@ -569,10 +1032,15 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
     if (APPLY == 1) { dense_grad[id] = acc; continue; }
     const int step = __ldg(a.step) + 1;
     const int64_t o = (int64_t)id * t.pitch;
-    float p = t.data[o], m = a.m[o], v = a.v[o];
+    float p, m, v;
+    if (a.stage) {                                         // [w, m, v, 0] of this position, replayed by rlctr_rows_lookup
+        const float4 r = ldg4(a.stage + 4 * k);
+        p = r.x; m = r.y; v = r.z;
+    } else {
+        p = t.data[o]; m = a.m[o]; v = a.v[o];
+    }
     if (is_lazy(a)) {
-        const int st = load_stamp(t, a, id);
-        adam_replay1(p, m, v, st, step - 1, a.sched, a.h);
+        if (!a.stage) adam_replay1(p, m, v, load_stamp(t, a, id), step - 1, a.sched, a.h);
         if (a.stamp_col >= 0) t.data[o + a.stamp_col] = __int_as_float(step); else a.stamp[id] = step;
     }
     const float2 sc = __ldg(&a.sched[step]);
@@ -607,6 +1075,10 @@ dense_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
     }
 }
 __global__ void step_advance_kernel(int32_t* step, int32_t delta) { *step += delta; }
+struct StepList { int index[RLCTR_DENSE_MAX]; int count; };
+__global__ void steps_advance_kernel(int32_t* steps, const __grid_constant__ StepList list) {
+    if ((int)threadIdx.x < list.count) steps[list.index[threadIdx.x]] += 1;
+}
 
 // All replicated dense parameters of a model in ONE launch (the reference's foreach Adam; nine launches of a few microseconds
 // each for DeepFM otherwise).  Block b belongs to tensor t with first_block[t] <= b < first_block[t+1].
@@ -617,14 +1089,15 @@ struct DenseGroup {
     float* v[RLCTR_DENSE_MAX];
     int64_t n[RLCTR_DENSE_MAX];
     int first_block[RLCTR_DENSE_MAX + 1];
+    int step_index[RLCTR_DENSE_MAX];     // torch keeps one step counter per parameter: steps[step_index[t]] = completed steps of tensor t
     int count;
 };
 __global__ void __launch_bounds__(256)
-dense_adam_multi_kernel(const __grid_constant__ DenseGroup grp, const float2* __restrict__ sched, const int32_t* __restrict__ step,
+dense_adam_multi_kernel(const __grid_constant__ DenseGroup grp, const float2* __restrict__ sched, const int32_t* __restrict__ steps,
                         AdamHyper h) {
     int t = 0;
     while (t + 1 < grp.count && (int)blockIdx.x >= grp.first_block[t + 1]) ++t;
-    const float2 sc = __ldg(&sched[__ldg(step) + 1]);
+    const float2 sc = __ldg(&sched[__ldg(steps + grp.step_index[t]) + 1]);
     const int nb = grp.first_block[t + 1] - grp.first_block[t];
     float* __restrict__ p = grp.p[t];
     const float* __restrict__ g = grp.g[t];
@@ -673,7 +1146,7 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
     if ((grad->dlogit || grad->extra) && grad->fields <= 0) return RLCTR_EINVAL;
     if (n == 0) return RLCTR_OK;
     TableView t = view_of(table);
-    AdamView a = APPLY == 0 ? view_of(opt) : AdamView{};
+    AdamView a = APPLY == 0 ? view_of(opt, t) : AdamView{};
     if (grad->world > RLCTR_MAX_WORLD || (grad->world > 1 && grad->n_per_rank == 0)) return RLCTR_EINVAL;
     GradView g = grad_view_of(grad);
     if ((g.flags & RLCTR_STAGED_PARTNER) && (!g.staged || !g.dlogit || g.fields <= 0)) return RLCTR_EINVAL;
@@ -701,6 +1174,50 @@ static int launch_rows(const uint32_t* sorted_ids, const uint32_t* sorted_slots,
                                                         w.long_count, w.long_list);                                \
     rows_long_kernel<L, APPLY><<<RLCTR_SMS, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad,         \
                                                           w.long_count, w.long_list)
+    if (APPLY == 0 && a.stage && a.stamp == nullptr && lpr <= 4) {
+        // the lookup's staging array feeds the update: phased kernel (R rows per lane group in flight), then the heavy hitters
+        static int r_env = -1;
+        if (r_env < 0) { const char* e = getenv("RLCTR_ROWS_R"); r_env = e ? atoi(e) : 0; }
+        if (r_env == 0 && lpr == 4) {                    // default: the double-buffered tile pipeline
+            const int ch = (t.used + 3) >> 2;
+            const int64_t tiles = capped_blocks((n + tile::TT - 1) / tile::TT, grad->world);
+            const unsigned tb = (unsigned)(tiles < RLCTR_SMS * 3 ? tiles : RLCTR_SMS * 3);
+#define LAUNCH_TILE(C)                                                                                                \
+            { const size_t sm = 2 * sizeof(tile::Buf<C>);                                                             \
+              RLCTR_CUDA(cudaFuncSetAttribute(rows_staged_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+              rows_staged_tile_kernel<C><<<tb, 256, sm, st>>>(sorted_ids, sorted_slots, n, g, t, a, w.long_count, w.long_list); }
+            switch (ch) {
+                case 1: LAUNCH_TILE(1); break;
+                case 2: LAUNCH_TILE(2); break;
+                case 3: LAUNCH_TILE(3); break;
+                default: LAUNCH_TILE(4); break;
+            }
+#undef LAUNCH_TILE
+            RLCTR_LAUNCH_CHECK();
+            rows_long_kernel<4, 0><<<RLCTR_SMS, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad, w.long_count, w.long_list);
+            RLCTR_LAUNCH_CHECK();
+            return RLCTR_OK;
+        }
+        const int R = r_env == 2 ? 2 : 4;
+        const int64_t per_block = (256 / lpr) * R;
+        int64_t want = (n + per_block - 1) / per_block;
+        want = capped_blocks(want, grad->world);
+        const int64_t cap = (int64_t)RLCTR_SMS * (R > 2 ? 2 : 3) * 4;     // a few trips per resident block
+        const unsigned sblocks = (unsigned)(want < cap ? want : cap);
+#define LAUNCH_STAGED(L)                                                                                              \
+        if (R == 2) rows_staged_kernel<L, 2><<<sblocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, w.long_count, w.long_list); \
+        else rows_staged_kernel<L, 4><<<sblocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, w.long_count, w.long_list);       \
+        rows_long_kernel<L, 0><<<RLCTR_SMS, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, dense_grad, w.long_count, w.long_list)
+        switch (lpr) {
+            case 1: LAUNCH_STAGED(1); break;
+            case 2: LAUNCH_STAGED(2); break;
+            default: LAUNCH_STAGED(4); break;
+        }
+#undef LAUNCH_STAGED
+        RLCTR_COUNT_LAUNCH(1);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
     switch (lpr) {
         case 1: LAUNCH_ROWS(1); break;
         case 2: LAUNCH_ROWS(2); break;
@@ -790,6 +1307,64 @@ extern "C" int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t*
                           (cudaStream_t)stream);
 }
 
+extern "C" int64_t rlctr_lookup_stage_floats(const rlctr_table* table) {
+    if (!table) return 0;
+    return stage_pitch_of(view_of(table));
+}
+
+extern "C" int rlctr_rows_lookup(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
+                                 const rlctr_adam* opt, const rlctr_lookup* lookup, void* ws, size_t ws_bytes,
+                                 rlctr_stream_t stream) {
+    if (!sorted_ids || !sorted_slots || !table || !table->data || !opt || !opt->exp_avg || !opt->exp_avg_sq || !opt->sched ||
+        !opt->step || !lookup || !lookup->stage || n < 0)
+        return RLCTR_EINVAL;
+    if (lookup->world > RLCTR_MAX_WORLD || (lookup->world > 1 && lookup->n_per_rank == 0)) return RLCTR_EINVAL;
+    if (n == 0) return RLCTR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableView t = view_of(table);
+    AdamView a = view_of(opt, t);
+    LookupView lk{};
+    lk.stage = lookup->stage; lk.world = lookup->world; lk.n_per_rank = lookup->n_per_rank; lk.rs = t.rs;
+    const int peers = lookup->world > 1 ? lookup->world : 1;
+    for (int r = 0; r < peers; ++r) {
+        if (!lookup->gathered[r]) return RLCTR_EINVAL;
+        lk.gathered[r] = lookup->gathered[r];
+    }
+    if (ws_bytes < rows_ws_bytes(n) || !ws) return RLCTR_EWORKSPACE;
+    RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
+    RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
+    if (t.rs == 1) {
+        lookup_scalar_kernel<<<capped_blocks((n + 255) / 256, lookup->world), 256, 0, st>>>(t, a, lk, n, sorted_ids, sorted_slots,
+                                                                                            w.long_count, w.long_list);
+        RLCTR_LAUNCH_CHECK();
+        lookup_long_scalar_kernel<<<RLCTR_SMS, 256, 0, st>>>(lk, n, sorted_ids, sorted_slots, w.long_count, w.long_list);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
+    // vector rows: the per-lane replay queues need the stamp inside the record (or no lazy state at all)
+    if (t.rs % 4 != 0 || t.rs > 16 || (opt->stamp && opt->stamp_col < 0)) return RLCTR_EUNSUPPORTED;
+    if (a.stamp_col >= 0 && (a.stamp_col >> 2) != ((t.used + 3) >> 2) - 1) return RLCTR_EUNSUPPORTED;
+    if (!rlctr_aligned16(lookup->stage)) return RLCTR_EALIGN;
+    const int ch = (t.used + 3) >> 2;
+    int64_t blocks = (n * 4 + 255) / 256;               // one 4-lane group per position, queues of a few rows per group
+    blocks = capped_blocks(blocks, lookup->world);
+    const int grid = (int)(blocks < RLCTR_SMS * 4 ? (blocks < 1 ? 1 : blocks) : RLCTR_SMS * 4);
+#define LAUNCH_LOOKUP(C)                                                                                                     \
+    lookup_rows_kernel<C><<<grid, 256, 0, st>>>(t, a, lk, n, sorted_ids, sorted_slots, w.long_count, w.long_list);           \
+    lookup_long_kernel<C><<<RLCTR_SMS, 256, 0, st>>>(lk, n, sorted_ids, sorted_slots, w.long_count, w.long_list, a.stamp_col)
+    switch (ch) {
+        case 1: LAUNCH_LOOKUP(1); break;
+        case 2: LAUNCH_LOOKUP(2); break;
+        case 3: LAUNCH_LOOKUP(3); break;
+        case 4: LAUNCH_LOOKUP(4); break;
+        default: return RLCTR_EUNSUPPORTED;
+    }
+#undef LAUNCH_LOOKUP
+    RLCTR_COUNT_LAUNCH(1);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
 extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table* table,
                                   const rlctr_adam* opt, rlctr_stream_t stream) {
     if (!sorted_ids || !table || !table->data || !opt || (!opt->stamp && opt->stamp_col < 0) || !opt->sched || !opt->step ||
@@ -798,7 +1373,7 @@ extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const r
     if (n == 0) return RLCTR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     TableView t = view_of(table);
-    AdamView a = view_of(opt);
+    AdamView a = view_of(opt, t);
     if (t.rs == 1) {
         rows_catchup_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted_ids, n, t, a);
         RLCTR_LAUNCH_CHECK();
@@ -820,7 +1395,7 @@ extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
     if (row_begin == row_end) return RLCTR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     TableView t = view_of(table);
-    AdamView a = view_of(opt);
+    AdamView a = view_of(opt, t);
     if (t.rs == 1) {
         adam_flush_scalar_kernel<<<grid_1d(row_end - row_begin, RLCTR_SMS * 8), 256, 0, st>>>(t, a, row_begin, row_end);
         RLCTR_LAUNCH_CHECK();
@@ -850,9 +1425,9 @@ extern "C" int rlctr_dense_adam(float* param, const float* grad, float* exp_avg,
 
 extern "C" int rlctr_dense_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
                                       float* const* exp_avg_sqs, const int64_t* sizes, int32_t count, const float* sched,
-                                      const int32_t* step, double beta1, double beta2, double eps, double weight_decay,
-                                      rlctr_stream_t stream) {
-    if (!params || !grads || !exp_avgs || !exp_avg_sqs || !sizes || !sched || !step || count < 0) return RLCTR_EINVAL;
+                                      const int32_t* steps, const int32_t* step_index, double beta1, double beta2, double eps,
+                                      double weight_decay, rlctr_stream_t stream) {
+    if (!params || !grads || !exp_avgs || !exp_avg_sqs || !sizes || !sched || !steps || count < 0) return RLCTR_EINVAL;
     if (count > RLCTR_DENSE_MAX) return RLCTR_EUNSUPPORTED;
     if (count == 0) return RLCTR_OK;
     DenseGroup grp;
@@ -861,12 +1436,29 @@ extern "C" int rlctr_dense_adam_multi(float* const* params, const float* const* 
     for (int t = 0; t < count; ++t) {
         if (!params[t] || !grads[t] || !exp_avgs[t] || !exp_avg_sqs[t] || sizes[t] < 0) return RLCTR_EINVAL;
         grp.p[t] = params[t]; grp.g[t] = grads[t]; grp.m[t] = exp_avgs[t]; grp.v[t] = exp_avg_sqs[t]; grp.n[t] = sizes[t];
+        grp.step_index[t] = step_index ? step_index[t] : 0;
+        if (grp.step_index[t] < 0) return RLCTR_EINVAL;
         grp.first_block[t] = blocks;
         blocks += grid_1d(sizes[t], RLCTR_SMS * 2);
     }
     grp.first_block[count] = blocks;
-    dense_adam_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grp, reinterpret_cast<const float2*>(sched), step,
+    dense_adam_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grp, reinterpret_cast<const float2*>(sched), steps,
                                                                      adam_hyper(beta1, beta2, eps, weight_decay));
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_steps_advance(int32_t* steps, const int32_t* step_index, int32_t count, rlctr_stream_t stream) {
+    if (!steps || !step_index || count < 0) return RLCTR_EINVAL;
+    if (count > RLCTR_DENSE_MAX) return RLCTR_EUNSUPPORTED;
+    if (count == 0) return RLCTR_OK;
+    StepList list;
+    list.count = count;
+    for (int t = 0; t < count; ++t) {
+        if (step_index[t] < 0) return RLCTR_EINVAL;
+        list.index[t] = step_index[t];
+    }
+    steps_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(steps, list);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -101,20 +101,21 @@ class GraphedTrainStep:
     def _note_replayed_step(self):
         for opt in self._optimizers():
             opt._host_step += 1
-            for owner in opt._tables:
-                owner._opt.host_step = opt._host_step
+            for owner in opt._last_tables:              # the replay advanced exactly the counters the captured step did
+                owner._opt.host_step += 1
                 if owner._opt.lazy:
                     owner._opt.dirty = True
-            if opt._dense_step is not None:
-                opt._dense_done += 1
+            opt._note_dense(opt._last_live)
 
     def _room(self):
         """Adam's per-step scalars are tabulated on the device; a captured graph holds the table's address, so
         the table must already cover the steps the graph will be replayed for."""
         for opt in self._optimizers():
             for owner in opt._tables:
-                if opt._host_step + 4 >= owner._opt.sched.length:
+                if owner._opt.host_step + 4 >= owner._opt.sched.length:
                     return False
+            if float(opt.param_groups[0]["lr"]) != opt.lr:
+                opt._sync_hyper()                       # re-tabulated in place: the captured graph reads the same addresses
             if opt._dense_sched is not None and opt._dense_done + 4 >= opt._dense_sched.length:
                 return False
         return True
@@ -122,7 +123,7 @@ class GraphedTrainStep:
     def _reserve(self):
         for opt in self._optimizers():
             for owner in opt._tables:
-                owner._opt.sched.ensure(opt._host_step + self.steps_ahead)
+                owner._opt.sched.ensure(owner._opt.host_step + self.steps_ahead)
             if opt._dense_sched is not None:
                 opt._dense_sched.ensure(opt._dense_done + self.steps_ahead)
 

@@ -23,7 +23,7 @@ from . import mlp as _mlp
 
 class RowsStash:
     """What one backward pass leaves for the optimizer (struct rlctr_rowgrad + the sorted ids)."""
-    __slots__ = ("sorted_ids", "sorted_slots", "n", "dlogit", "sums", "extra", "staged", "fields", "flags", "peer")
+    __slots__ = ("sorted_ids", "sorted_slots", "n", "dlogit", "sums", "extra", "staged", "fields", "flags", "peer", "stage")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -72,6 +72,37 @@ def _sort_ids(x: torch.Tensor, n_rows: int):
     return sid, sslot
 
 
+def lookup_rows(module, sorted_pair, n, fields, gathered=None, world=1, n_per_rank=0, peer_ptrs=None, key=None):
+    """The owner-side lookup of a training step (rlctr_rows_lookup): every distinct row of the sorted view is read once,
+    brought up to date in registers and written (a) to ``stage`` at its sorted position, for the optimizer, and (b) to the
+    sample-ordered ``gathered`` buffer of whoever asked for it.  Returns (stage, gathered)."""
+    lib = _lib.load()
+    g, opt = module._geom, module._opt
+    data = module.table.data
+    dev = data.device
+    t, a = table_struct(data, g), opt.struct()
+    stage = torch.empty(n * lib.rlctr_lookup_stage_floats(C.byref(t)), dtype=torch.float32, device=dev)
+    lk = _lib.Lookup(stage.data_ptr(), world if world > 1 else 0, n_per_rank)
+    if peer_ptrs is None:
+        if gathered is None:
+            gathered = module._gathered_rows(n)
+        lk.gathered[0] = gathered.data_ptr()
+    else:
+        for r, p_ in enumerate(peer_ptrs):
+            lk.gathered[r] = p_
+    ws_bytes = lib.rlctr_rows_ws_bytes(n)
+    ws = module._rows_ws(ws_bytes)
+    _lib.call("rlctr_rows_lookup", lib.rlctr_rows_lookup, _lib.ptr(sorted_pair[0]), _lib.ptr(sorted_pair[1]), n, C.byref(t),
+              C.byref(a), C.byref(lk), _lib.ptr(ws), ws_bytes, _lib.stream(),
+              key=key or f"rlctr_rows_lookup[{type(module).__name__}]", meta=dict(module._meta(n // max(fields, 1), fields), n=n))
+    return stage, gathered
+
+
+def gathered_struct(gathered, n, g):
+    """``gathered`` as the table the forward kernels stream (ids == NULL: row (b, f) is row b * F + f)."""
+    return _lib.Table(gathered.data_ptr(), n, g.row_stride, g.lin_col, g.emb_col, g.dim, g.row_stride)
+
+
 class _GatherInteract(torch.autograd.Function):
     """ids -> fused gather + first/second order -> (out[B,1], rows[B,F*D] | empty).
 
@@ -79,7 +110,7 @@ class _GatherInteract(torch.autograd.Function):
     never materialised: backward stashes it in row form on the module (returns None for it)."""
 
     @staticmethod
-    def forward(ctx, module, ids, table, bias, want_rows, apply_sigmoid, sorted_pair):
+    def forward(ctx, module, ids, table, bias, want_rows, apply_sigmoid, sorted_pair, lookup=None):
         lib = _lib.load()
         g = module._geom
         B, F = ids.shape
@@ -94,6 +125,9 @@ class _GatherInteract(torch.autograd.Function):
         rows = torch.empty(B, rows_pitch, dtype=torch.float32, device=dev) if want_rows else None
         partners = None
         t = table_struct(table, g)
+        ids_ptr = _lib.ptr(ids)
+        if lookup is not None:                              # training step: the rows were pushed into `gathered` in sample order
+            t, ids_ptr = gathered_struct(lookup[1], B * F, g), None
         if module._kind == "ffm":
             if need_bwd:
                 partners = torch.empty(B * F, g.row_stride, dtype=torch.float32, device=dev)
@@ -104,16 +138,17 @@ class _GatherInteract(torch.autograd.Function):
             if need_bwd and module._kind == "fm" and module._fm_term:
                 sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
             flags = _lib.RLCTR_FM_TERM if module._fm_term else 0
-            _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(ids), C.byref(t), _lib.ptr(bias), _lib.ptr(logit),
+            _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, ids_ptr, C.byref(t), _lib.ptr(bias), _lib.ptr(logit),
                       _lib.ptr(pctr), 1, _lib.ptr(sums), _lib.ptr(rows), rows_pitch, B, F, flags, _lib.stream(),
                       key=f"rlctr_embed_fwd[{type(module).__name__}]",
-                      meta=dict(module._meta(B, F), sums=sums is not None, rows=want_rows))
+                      meta=dict(module._meta(B, F), sums=sums is not None, rows=want_rows, streamed=lookup is not None))
         hook = getattr(module, "_after_gather", None)       # graphs.GraphedTrainStep: fork point of the captured step
         if hook is not None:
             module._after_gather = None
             hook()
         ctx.module, ctx.sorted_pair, ctx.apply_sigmoid = module, sorted_pair, apply_sigmoid
         ctx.sums, ctx.partners, ctx.shape = sums, partners, (B, F)
+        ctx.stage = lookup[0] if lookup is not None else None
         ctx.has_bias = bias is not None
         if apply_sigmoid:
             ctx.save_for_backward(out)
@@ -130,6 +165,11 @@ class _GatherInteract(torch.autograd.Function):
         module = ctx.module
         if ctx.sorted_pair is None:
             raise _lib.RlctrError("backward through a forward that ran without gradient bookkeeping")
+        if module._opt is None:
+            raise _lib.RlctrError("the embedding table's gradient exists only in row form (sorted ids + per-sample terms) and is "
+                                  "consumed by rl_ctr_prediction_b200.optim.Adam(model.parameters(), ...): build that optimizer "
+                                  "before calling backward -- a torch.optim optimizer would silently skip the table (its "
+                                  ".grad is never materialised)")
         B, F = ctx.shape
         dev = gout.device
         gout = gout.contiguous()
@@ -152,8 +192,8 @@ class _GatherInteract(torch.autograd.Function):
         sid, sslot = ctx.sorted_pair
         module._stash = RowsStash(sorted_ids=sid, sorted_slots=sslot, n=B * F, dlogit=dlogit, sums=ctx.sums,
                                   extra=extra, staged=ctx.partners, fields=F,
-                                  flags=_lib.RLCTR_STAGED_PARTNER if ctx.partners is not None else 0)
-        return None, None, None, dbias, None, None, None
+                                  flags=_lib.RLCTR_STAGED_PARTNER if ctx.partners is not None else 0, stage=ctx.stage)
+        return None, None, None, dbias, None, None, None, None
 
 
 class _TableModel(nn.Module):
@@ -199,6 +239,24 @@ class _TableModel(nn.Module):
             ws = torch.zeros(_lib.RLCTR_REDUCE_WS_BYTES, dtype=torch.uint8, device=dev)
             self._ws["reduce"] = ws
         return ws
+
+    def _rows_ws(self, nbytes):
+        """Workspace of the row kernels (heavy-hitter list), kept across steps: no allocation on the step's critical path."""
+        ws = self._ws.get("rows")
+        if ws is None or ws.numel() < nbytes or ws.device != self.table.device:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.table.device)
+            self._ws["rows"] = ws
+        return ws
+
+    def _gathered_rows(self, n):
+        """The sample-ordered lookup buffer [n, row_stride] rlctr_rows_lookup fills (kept per batch size: its padding
+        columns are zeroed once and never written)."""
+        key = ("gathered", n)
+        buf = self._ws.get(key)
+        if buf is None:
+            buf = torch.zeros(n, self._geom.row_stride, dtype=torch.float32, device=self.table.device)
+            self._ws[key] = buf
+        return buf
 
     # ---- reference-keyed state_dict -----------------------------------------------------------
     def _ref_items(self):
@@ -261,10 +319,13 @@ class _TableModel(nn.Module):
             raise ValueError(f"expected {self.field_nums} fields, got {x.shape[1]}")
         track = torch.is_grad_enabled() and self.table.requires_grad
         sorted_pair = None
+        lookup = None
         if track:
             sorted_pair = sort_ids(x, self._geom.n_rows)
             opt = self._opt
-            if opt is not None and opt.lazy and opt.dirty:
+            if opt is not None and opt.lookup_on:
+                lookup = lookup_rows(self, sorted_pair, x.numel(), x.shape[1])
+            elif opt is not None and opt.lazy and opt.dirty:
                 lib = _lib.load()
                 t, a = table_struct(self.table.data, self._geom), opt.struct()
                 _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sorted_pair[0]), x.numel(), C.byref(t),
@@ -273,7 +334,7 @@ class _TableModel(nn.Module):
         else:
             self.flush()
         bias = getattr(self, "bias", None)
-        return _GatherInteract.apply(self, x, self.table, bias, want_rows, apply_sigmoid, sorted_pair)
+        return _GatherInteract.apply(self, x, self.table, bias, want_rows, apply_sigmoid, sorted_pair, lookup)
 
     def zero_grad(self, set_to_none: bool = True):
         self._stash = None

@@ -143,7 +143,11 @@ def fused_train_step(model, optimizer, features, labels):
     sid, sslot = Model.sort_ids(x, g.n_rows)
     opt = model._opt
     t = table_struct(model.table.data, g)
-    if opt is not None and opt.lazy and opt.dirty:
+    ids_ptr, stage = _lib.ptr(x), None
+    if opt is not None and opt.lookup_on:
+        stage, gathered = Model.lookup_rows(model, (sid, sslot), x.numel(), F)
+        t, ids_ptr = Model.gathered_struct(gathered, x.numel(), g), None
+    elif opt is not None and opt.lazy and opt.dirty:
         a = opt.struct()
         _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sid), x.numel(), C.byref(t), C.byref(a), st,
                   key=f"rlctr_rows_catchup[{type(model).__name__}]", meta=model._meta(B, F))
@@ -157,9 +161,10 @@ def fused_train_step(model, optimizer, features, labels):
     else:
         if model._kind == "fm":
             sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
-        _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, _lib.ptr(x), C.byref(t), _lib.ptr(model.bias.data),
+        _lib.call("rlctr_embed_fwd", lib.rlctr_embed_fwd, ids_ptr, C.byref(t), _lib.ptr(model.bias.data),
                   _lib.ptr(logit), None, 1, _lib.ptr(sums), None, 0, B, F, _lib.RLCTR_FM_TERM if model._fm_term else 0, st,
-                  key=f"rlctr_embed_fwd[{type(model).__name__}]", meta=dict(model._meta(B, F), sums=sums is not None, rows=False))
+                  key=f"rlctr_embed_fwd[{type(model).__name__}]",
+                  meta=dict(model._meta(B, F), sums=sums is not None, rows=False, streamed=stage is not None))
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     dlogit = torch.empty(B, dtype=torch.float32, device=dev)
     dbias = torch.empty(1, dtype=torch.float32, device=dev)
@@ -169,7 +174,7 @@ def fused_train_step(model, optimizer, features, labels):
                                      _lib.ptr(dbias), _lib.ptr(model._reduce_ws(dev)), B, st), "rlctr_bce_fwd_bwd")
     model._stash = Model.RowsStash(sorted_ids=sid, sorted_slots=sslot, n=B * F, dlogit=dlogit, sums=sums, extra=None,
                                    staged=partners, fields=F,
-                                   flags=_lib.RLCTR_STAGED_PARTNER if partners is not None else 0)
+                                   flags=_lib.RLCTR_STAGED_PARTNER if partners is not None else 0, stage=stage)
     model.bias.grad = dbias
     optimizer.step()
     return loss.reshape(())
@@ -274,6 +279,14 @@ def main(data_path, dataset_name, campaign_id, valid_day, test_day, latent_dims,
         data_path, dataset_name, campaign_id, valid_day, test_day)
     loaders = [BatchSlices(d, batch_size) for d in (train_data, valid_data, test_data)]
     model = get_model(model_name, feature_nums, field_nums, latent_dims).to(device)
+    if model_name in ("IPNN", "OPNN", "FNN"):                              # :164-166: start from the FM checkpoint's embedding
+        # the reference reads 'models/model_params/<campaign>FMbest.pth' relative to its working directory; here the
+        # checkpoint directory this run writes to (the same place the FM run of `main` left FMbest.pth)
+        fm_ckpt = save_param_dir + campaign_id + "FMbest.pth"
+        if not os.path.exists(fm_ckpt):
+            raise FileNotFoundError(f"{model_name} starts from the FM embedding (reference pretrain_main.py:164-166): "
+                                    f"train FM first so that {fm_ckpt} exists")
+        model.load_embedding(torch.load(fm_ckpt, map_location=device))
     loss = nn.BCELoss()
     valid_aucs, valid_losses, early_stop_index, is_early_stop = [], [], 0, False
     ckpt = lambda tag: save_param_dir + campaign_id + model_name + str(tag) + ".pth"

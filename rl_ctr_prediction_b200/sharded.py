@@ -189,6 +189,8 @@ class ShardedCTR(nn.Module):
         self._stash = None
         return super().zero_grad(set_to_none)
 
+    _rows_ws = Model._TableModel._rows_ws
+
     def barrier(self):
         self._pm.barrier()
 

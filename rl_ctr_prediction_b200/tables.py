@@ -14,6 +14,7 @@ so a field costs one aligned 128-bit-chunked read instead of two (or F+1) sector
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -99,25 +100,45 @@ def table_struct(data: torch.Tensor, g: Geometry) -> _lib.Table:
 class AdamSchedule:
     """The two Python-double scalars torch.optim.Adam derives per step (torch/optim/adam.py
     ``_single_tensor_adam``): step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t), tabulated
-    for t = 0..len-1 and kept on the device so the step index can be a device scalar."""
+    for t = 0..len-1 and kept on the device so the step index can be a device scalar.
+
+    ``set_lr(lr, from_step)`` re-tabulates the entries t >= from_step IN PLACE (same device address: a captured CUDA graph
+    keeps working): an ``lr`` edited through ``param_groups`` -- an LR scheduler, or the reference's ``learning_rate += 1e-4``
+    per epoch -- takes effect from that step on, while the lazy replay of earlier steps still sees the lr they ran with."""
 
     def __init__(self, lr, betas, device, length=8192):
         self.lr, self.betas, self.device = float(lr), (float(betas[0]), float(betas[1])), device
         self.length = 0
         self.tensor = None
+        self.rows = [(0.0, 1.0)]
         self.ensure(length)
+
+    def _row(self, t):
+        b1, b2 = self.betas
+        return (self.lr / (1 - b1 ** t), (1 - b2 ** t) ** 0.5)
+
+    def _upload(self, lo, hi):
+        part = torch.tensor(self.rows[lo:hi], dtype=torch.float64).to(torch.float32).to(self.device)
+        self.tensor[lo:hi].copy_(part)
 
     def ensure(self, steps: int):
         if steps < self.length:
             return False
         n = max(steps + 1, 2 * self.length, 1024)
-        b1, b2 = self.betas
-        rows = [(0.0, 1.0)]
-        for t in range(1, n):
-            rows.append((self.lr / (1 - b1 ** t), (1 - b2 ** t) ** 0.5))
-        self.tensor = torch.tensor(rows, dtype=torch.float64).to(torch.float32).to(self.device).contiguous()
+        self.rows.extend(self._row(t) for t in range(len(self.rows), n))
+        self.tensor = torch.tensor(self.rows, dtype=torch.float64).to(torch.float32).to(self.device).contiguous()
         self.length = n
         return True
+
+    def set_lr(self, lr, from_step: int):
+        if float(lr) == self.lr:
+            return
+        self.lr = float(lr)
+        lo = max(int(from_step), 1)
+        for t in range(lo, self.length):
+            self.rows[t] = self._row(t)
+        if lo < self.length:
+            self._upload(lo, self.length)
 
 
 class TableAdamState:
@@ -162,10 +183,26 @@ class TableAdamState:
         """True when untouched rows are owed their L2-only steps (modes 'lazy' and 'dense')."""
         return self.stamp is not None or self.stamp_col >= 0
 
-    def struct(self) -> _lib.Adam:
+    def struct(self, stage=None) -> _lib.Adam:
         return _lib.Adam(self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), _lib.ptr(self.stamp),
                          _lib.ptr(self.sched.tensor), _lib.ptr(self.step), self.sched.length, self.stamp_col,
-                         self.betas[0], self.betas[1], self.eps, self.weight_decay)
+                         self.betas[0], self.betas[1], self.eps, self.weight_decay, _lib.ptr(stage))
+
+    @property
+    def lookup_ok(self):
+        """rlctr_rows_lookup serves this table: LR records, or vector rows of at most 16 floats whose stamp rides inside the
+        record (or that carry no stamp at all: mode 'sparse')."""
+        g = self.geom
+        return g.has_state and (g.row_stride == 1 or (g.row_stride <= 16 and self.stamp is None))
+
+    @property
+    def lookup_on(self):
+        """Whether the training step takes the lookup path (rlctr_rows_lookup -> streamed forward -> update from the stage)
+        instead of catch-up -> gather by id -> update.  Measured on one B200 (profiles/r2_rows_lookup_ab.md): the lookup
+        path moves fewer DRAM bytes (812 vs 950 MB per FM step) but the replay it has to do is instruction-bound, not
+        memory-bound, and the extra staging writes make the step ~6 % SLOWER (1.75 vs 1.65 ms) -- so it is off unless
+        RLCTR_LOOKUP=1.  Kept because it is the owner-pushes-rows form of the sharded lookup."""
+        return self.lookup_ok and os.environ.get("RLCTR_LOOKUP", "0") == "1"
 
     def flush(self, data: torch.Tensor):
         """Replay the L2-only steps every row missed (rlctr_adam_flush)."""

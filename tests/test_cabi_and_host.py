@@ -45,18 +45,20 @@ def test_struct_layouts_match_header(tmp_path):
     import subprocess
     from rl_ctr_prediction_b200 import _lib
     src = tmp_path / "layout.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rlctr.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rlctr.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(rlctr_table), sizeof(rlctr_adam), sizeof(rlctr_rowgrad), offsetof(rlctr_table,row_stride),'
                    'offsetof(rlctr_adam,sched_len), offsetof(rlctr_table,peers), offsetof(rlctr_rowgrad,peer_staged),'
-                   'offsetof(rlctr_rowgrad,peer_extra));return 0;}\n')
+                   'offsetof(rlctr_rowgrad,peer_extra), offsetof(rlctr_adam,stage), sizeof(rlctr_lookup),'
+                   'offsetof(rlctr_lookup,gathered));return 0;}\n')
     exe = tmp_path / "layout"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(_lib.Table), C.sizeof(_lib.Adam), C.sizeof(_lib.RowGrad), _lib.Table.row_stride.offset,
-            _lib.Adam.sched_len.offset, _lib.Table.peers.offset, _lib.RowGrad.peer_staged.offset, _lib.RowGrad.peer_extra.offset]
+            _lib.Adam.sched_len.offset, _lib.Table.peers.offset, _lib.RowGrad.peer_staged.offset, _lib.RowGrad.peer_extra.offset,
+            _lib.Adam.stage.offset, C.sizeof(_lib.Lookup), _lib.Lookup.gathered.offset]
     assert got == want, (got, want)
-    assert C.sizeof(_lib.Table) == 104 and C.sizeof(_lib.Adam) == 80 and C.sizeof(_lib.RowGrad) == 304
+    assert C.sizeof(_lib.Table) == 104 and C.sizeof(_lib.Adam) == 88 and C.sizeof(_lib.RowGrad) == 304
 
 
 def test_argument_errors_need_no_gpu(lib):

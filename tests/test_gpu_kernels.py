@@ -191,7 +191,8 @@ def test_embed_fwd_empty_and_errors(lib):
     tab, g = fused_fm_table(lin, emb)
     t = T().table_struct(tab, g)
     assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(t), None, None, None, 1, None, None, 0, 0, 15, 1, st()) == 0
-    assert lib.rlctr_embed_fwd(None, C.byref(t), None, None, None, 1, None, None, 0, 4, 15, 1, st()) == -1
+    # ids == NULL means sample-ordered rows: the table must then hold batch * fields of them (100 < 7 * 15)
+    assert lib.rlctr_embed_fwd(None, C.byref(t), None, None, None, 1, None, None, 0, 7, 15, 1, st()) == -1
     bad = L().Table(L().ptr(tab), 100, 10, 0, 1, 9)          # stride not a multiple of 4
     assert lib.rlctr_embed_fwd(L().ptr(dev(ids)), C.byref(bad), None, None, None, 1, None, None, 0, 4, 15, 1, st()) == -2
 
@@ -462,6 +463,109 @@ def test_rows_adam_matches_dense_adam(lib, mode):
     close(tab, P, rtol=2e-5, atol=1e-7)
     close(m, Mo, rtol=2e-5, atol=1e-9)
     close(v, Vo, rtol=2e-5, atol=1e-12)
+
+
+
+@pytest.mark.parametrize("kind,D", [("fm", 10), ("fm", 8), ("fm", 2), ("lr", 0)])
+@pytest.mark.parametrize("heavy", [False, True])
+def test_rows_lookup_stage_update_equals_dense_adam(lib, kind, D, heavy):
+    """rlctr_rows_lookup (read once, replay in registers, stage + push to the samples) -> streamed forward rows ->
+    rlctr_rows_adam reading the stage == the reference's dense Adam with L2 over EVERY row.  The table keeps the
+    [row | exp_avg | exp_avg_sq] records with the stamp inside; ids go stale for several steps and come back; `heavy` adds an
+    id with hundreds of occurrences (the block-per-run kernels)."""
+    from rl_ctr_prediction_b200.tables import Geometry, TableAdamState, table_struct
+    B, F, N, STEPS, lr, wd = 96, 15, 600, 7, 1e-3, 1e-5
+    rng = np.random.default_rng(11 + D)
+    g = (Geometry.lr(N) if kind == "lr" else Geometry.fm(N, D)).with_state()
+    rs, used = g.row_stride, g.used
+    tab = torch.zeros(N, g.row_pitch, device=DEV)
+    tab[:, :used] = torch.as_tensor((rng.standard_normal((N, used)) * 0.3).astype(np.float32)).to(DEV)
+    opt = TableAdamState(tab, g, lr, (0.9, 0.999), 1e-8, wd, "lazy")
+    assert opt.lookup_ok and opt.stamp_col >= 0
+    P = np.zeros((N, rs), np.float32)
+    P[:, :used] = tab[:, :used].cpu().numpy()
+    Mo, Vo = np.zeros_like(P), np.zeros_like(P)
+    t = table_struct(tab, g)
+    n = B * F
+    sf = lib.rlctr_lookup_stage_floats(C.byref(t))
+    assert sf == (4 if kind == "lr" else 3 * ((used + 3) // 4 * 4))
+    for s in range(1, STEPS + 1):
+        ids = rng.integers(0, N // 3, size=(B, F)).astype(np.int64) + (s % 3) * (N // 3)
+        if heavy:
+            ids[rng.random((B, F)) < 0.4] = (s % 3) * (N // 3) + 5         # one id with ~570 occurrences
+        ids[0, 0] = N + 7                                                   # out of range: all-zero row, no update
+        dzv = (rng.standard_normal(B) * 0.01).astype(np.float32)
+        sid, ss = do_sort(lib, dev(ids.reshape(-1)), N)
+        stage = torch.full((n * sf,), float("nan"), device=DEV)
+        gathered = torch.zeros(n, rs, device=DEV)
+        a = opt.struct()
+        lk = L().Lookup(stage.data_ptr(), 0, 0)
+        lk.gathered[0] = gathered.data_ptr()
+        wsb = lib.rlctr_rows_ws_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        rc = lib.rlctr_rows_lookup(L().ptr(sid), L().ptr(ss), n, C.byref(t), C.byref(a), C.byref(lk), L().ptr(ws), wsb, st())
+        assert rc == 0, lib.rlctr_strerror(rc)
+        # every sample's row == the dense-Adam state after s-1 steps (out-of-range id: zeros); padding columns clean
+        want = np.zeros((n, rs), np.float32)
+        flat = ids.reshape(-1)
+        ok = flat < N
+        want[ok] = P[flat[ok]]
+        got = gathered.cpu().numpy()
+        close(got[:, :used], want[:, :used], rtol=2e-5, atol=1e-7)
+        assert not got[:, used:].any()
+        # gradient: dz at the linear column (+ dz * (S - v) on the latent columns for the FM rows)
+        sums = None
+        if kind == "fm":
+            S = got.reshape(B, F, rs).sum(axis=1)
+            sums = dev(S)
+        grad = L().RowGrad(None, L().ptr(dev(dzv)), L().ptr(sums), None, F, 0)
+        a2 = opt.struct(stage)
+        assert lib.rlctr_rows_adam(L().ptr(sid), L().ptr(ss), n, C.byref(grad), C.byref(t), C.byref(a2), L().ptr(ws), wsb,
+                                   st()) == 0
+        assert lib.rlctr_step_advance(L().ptr(opt.step), 1, st()) == 0
+        opt.dirty = True
+        G = np.zeros((N, rs), np.float64)
+        rows64 = want.reshape(B, F, rs).astype(np.float64)
+        S64 = rows64.sum(axis=1)
+        for b in range(B):
+            for f in range(F):
+                i = ids[b, f]
+                if i >= N:
+                    continue
+                G[i, 0] += dzv[b]
+                if kind == "fm":
+                    G[i, 1:1 + D] += np.float64(dzv[b]) * (S64[b, 1:1 + D] - rows64[b, f, 1:1 + D])
+        P, Mo, Vo = O.adam_step(P, G.astype(np.float32), Mo, Vo, s, lr, wd)
+        P[:, used:] = 0
+    opt.flush(tab)
+    torch.cuda.synchronize()
+    rec = tab.cpu().numpy()
+    close(rec[:, :used], P[:, :used], rtol=2e-5, atol=1e-7)
+    if kind == "lr":                  # moments: 2e-5 of their scale (the oracle sums the occurrences' gradients in fp64)
+        close(rec[:, 1], Mo[:, 0], rtol=2e-5)
+        close(rec[:, 2], Vo[:, 0], rtol=2e-5)
+    else:
+        close(rec[:, rs:rs + used], Mo[:, :used], rtol=2e-5)
+        close(rec[:, 2 * rs:2 * rs + used], Vo[:, :used], rtol=2e-5)
+    assert (tab[:, opt.stamp_col].view(torch.int32) == STEPS).all()
+
+
+def test_embed_fwd_streamed_rows_equal_gather_by_id(lib):
+    """rlctr_embed_fwd with ids == NULL over sample-ordered rows == the same call gathering by id (bit for bit)."""
+    B, F, N, D = 333, 15, 5000, 10
+    ids, emb, lin, bias, _ = rng_case(5, B, F, N, D)
+    tab, g = fused_fm_table(lin, emb)
+    z0, p0, s0, r0 = run_embed_fwd(lib, ids, tab, g, bias)
+    rows = tab[torch.as_tensor(ids.reshape(-1)).to(DEV)].contiguous()
+    t = L().Table(rows.data_ptr(), B * F, g.row_stride, g.lin_col, g.emb_col, g.dim, g.row_stride)
+    logit, pctr = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
+    sums, out = torch.empty(B, g.row_stride, device=DEV), torch.empty(B, F * D, device=DEV)
+    assert lib.rlctr_embed_fwd(None, C.byref(t), L().ptr(dev(bias)), L().ptr(logit), L().ptr(pctr), 1, L().ptr(sums),
+                               L().ptr(out), 0, B, F, 1, st()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(logit, z0) and torch.equal(pctr, p0) and torch.equal(sums, s0) and torch.equal(out, r0)
+    t.n_rows = B * F - 1                                  # fewer rows than samples x fields: refused
+    assert lib.rlctr_embed_fwd(None, C.byref(t), None, L().ptr(logit), None, 1, None, None, 0, B, F, 1, st()) == -1
 
 
 def test_dense_adam(lib):

@@ -113,6 +113,34 @@ def test_training_trajectory_matches_reference(golden, name, mode):
     assert_state(m, state_from_golden(golden, f"train/{name}/final"))
 
 
+@pytest.mark.parametrize("name", ["LR", "FM", "DeepFM"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_lookup_path_matches_reference(golden, name, fused, monkeypatch):
+    """RLCTR_LOOKUP=1: rlctr_rows_lookup -> streamed forward -> update from the staging array gives the reference trajectory too
+    (drop-in loop and fused step)."""
+    from rl_ctr_prediction_b200 import optim, pretrain_main as PM
+    monkeypatch.setenv("RLCTR_LOOKUP", "1")
+    sd = state_from_golden(golden, f"train/{name}/init")
+    m = load(build(name, 255), sd).to(DEV).eval()
+    opt = optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)
+    assert m._opt.lookup_on
+    lossf = torch.nn.BCELoss()
+    for s in range(3):
+        x = torch.as_tensor(golden["train/x"][s]).to(DEV)
+        y = torch.as_tensor(golden["train/y"][s]).to(DEV)
+        if fused:
+            tl = PM.fused_train_step(m, opt, x, y)
+        else:
+            p = m(x)
+            tl = lossf(p, y.unsqueeze(1).float())
+            m.zero_grad()
+            tl.backward()
+            opt.step()
+            close(p, golden[f"train/{name}/pctr{s}"])
+        close(tl, golden[f"train/{name}/loss{s}"])
+    assert_state(m, state_from_golden(golden, f"train/{name}/final"))
+
+
 @pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
 def test_fused_train_step_matches_reference(golden, name):
     from rl_ctr_prediction_b200 import optim, pretrain_main as PM
