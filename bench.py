@@ -14,8 +14,15 @@ at the end INSIDE the timed region, so the tables at the end are the reference's
 e2e = the same steps through the drop-in API (model(x); BCELoss; zero_grad; backward; optimizer.step();
 loss.item()) with each batch copied from pinned host memory inside the timed region.
 
---impl reference: the reference's own CPU implementation of the same step (oracle/torch_port.py: the
-same stock ATen CPU kernels the reference's modules call, dense torch.optim.Adam) on all host threads.
+--impl reference: the reference's own CPU implementation of the same step on all host threads: the reference's
+modules themselves when its tree is importable (RLCTR_REF_PATH, /root/reference or baseline/_ref; `kind: "reference"`),
+else oracle/torch_port.py (the same stock ATen CPU kernels the reference's modules call, dense torch.optim.Adam;
+`kind: "port"`).  Under torchrun its global batch is batch x N, the B200 arm's global batch.
+
+Beside the headline the line carries `configs` (the other BASELINE.json configurations: C1 FM B=4096 N=1e6, C3 REINFORCE
+fused into the step, C4 FFM + DeepFM, C5 the src/all_main step at batch 1M), `steady_state` (median of several windows
+without the end-of-run flush, the flush timed apart) and `gpu_eager_baseline` (stock PyTorch eager on the same B200:
+the reference's loop body with dense torch.optim.Adam).
 """
 from __future__ import annotations
 
@@ -52,6 +59,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-fork", action="store_true", help="capture the models of the step one after another (no parallel graph branches)")
     ap.add_argument("--profile-steps", type=int, default=10, help="steps of the eager per-kernel timing pass")
+    ap.add_argument("--configs", default="C1,C3,C4,C5", help="other BASELINE.json configurations to time after the headline")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the stock-PyTorch-on-B200 baseline")
+    ap.add_argument("--windows", type=int, default=5, help="steady-state windows of 20 steps after the headline region")
     return ap.parse_args()
 
 
@@ -200,36 +211,74 @@ class Clocks:
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the CPU port of the reference modules, dense Adam, all host threads
+# reference arm / cpu_baseline: the reference's CPU implementation, dense Adam, all host threads
 # ----------------------------------------------------------------------------------------------
-def cpu_models(N, D):
-    from oracle import torch_port as TP
+_REF = {"tried": False, "mod": None}
+
+
+def reference_modules():
+    """The reference's own ``src.models.p_model`` when its tree can be imported (never on the GPU box, which has no copy of it;
+    in the build container it is /root/reference), else None -> the port in oracle/torch_port.py."""
+    if _REF["tried"]:
+        return _REF["mod"]
+    _REF["tried"] = True
+    for cand in (os.environ.get("RLCTR_REF_PATH"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "src", "models", "p_model.py")):
+            try:
+                sys.path.insert(0, cand)
+                import importlib
+                _REF["mod"] = importlib.import_module("src.models.p_model")
+                break
+            except Exception:
+                sys.path.remove(cand)
+    return _REF["mod"]
+
+
+def cpu_kind():
+    return "reference" if reference_modules() is not None else "port"
+
+
+def cpu_models(N, D, names=MODELS):
+    ref = reference_modules()
     torch.manual_seed(1)
     ms = []
-    for name in MODELS:
-        m = TP.PortCTR(name, N, F_FIELDS, D)
+    for name in names:
+        if ref is not None:            # the reference's classes themselves (src/models/p_model.py)
+            m = {"LR": lambda: ref.LR(N), "FM": lambda: ref.FM(N, D), "FFM": lambda: ref.FFM(N, F_FIELDS, D),
+                 "DeepFM": lambda: ref.DeepFM(N, F_FIELDS, D)}[name]()
+            opt = torch.optim.Adam(params=m.parameters(), lr=1e-3, weight_decay=1e-5)     # src/main/pretrain_main.py:181
+        else:
+            from oracle import torch_port as TP
+            m = TP.PortCTR(name, N, F_FIELDS, D)
+            opt = TP.make_adam(m)
         with torch.no_grad():
             for k, p in m.named_parameters():
                 if "embedding" in k or k == "linear.weight":
                     p.mul_(0.1)
         m.train()
-        ms.append((m, TP.make_adam(m)))
+        ms.append((m, opt))
     return ms
 
 
 def cpu_step(ms, x, y):
-    from oracle import torch_port as TP
     lossf = torch.nn.BCELoss()
-    for m, opt in ms:
-        TP.ctr_train_step(m, opt, lossf, x, y.unsqueeze(1))
+    yy = y.unsqueeze(1).float()
+    for m, opt in ms:                   # the loop body of src/main/pretrain_main.py:96-102
+        p = m(x)
+        tl = lossf(p, yy)
+        m.zero_grad()
+        tl.backward()
+        opt.step()
+        tl.item()
 
 
-def run_cpu(B, N, D, steps, warmup):
+def run_cpu(B, N, D, steps, warmup, names=MODELS, batch_fn=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     gen = torch.Generator().manual_seed(1)
-    ms = cpu_models(N, D)
-    batches = [make_batch(gen, B, N, "cpu") for _ in range(min(steps + warmup, 4))]
+    ms = cpu_models(N, D, names)
+    batch_fn = batch_fn or make_batch
+    batches = [batch_fn(gen, B, N, "cpu") for _ in range(min(steps + warmup, 4))]
     for i in range(warmup):
         cpu_step(ms, *batches[i % len(batches)])
     t0 = time.perf_counter()
@@ -243,24 +292,25 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B, N, D = args.batch, args.rows, args.dims
+    world = max(int(args.gpus), 1)
+    B, N, D = args.batch * world, args.rows, args.dims      # the B200 arm's GLOBAL batch (weak scaling: batch per GPU x N)
     # bound the run: one dense-Adam step costs O(N) on the CPU; time a probe step, then shrink N (which
     # only FAVOURS the reference: its step time is ~linear in N) if K steps would not fit
-    sample = f"full workload: B={B}, N={N} rows, all three models, dense Adam"
+    sample = f"full workload: global batch B={B}, N={N} rows, all three models, dense Adam"
     n_used = N
     probe_n = min(N, 1_000_000)
     _, t_probe, cores = run_cpu(B, probe_n, D, 1, 1)
-    est = t_probe * (N / probe_n) * (args.steps + args.warmup)
+    est = (t_probe * (0.3 + 0.7 * N / probe_n)) * (args.steps + args.warmup)
     if est > 200.0:
         n_used = max(int(N * 200.0 / est), 100_000)
-        sample = (f"B={B}, table rows reduced to N={n_used} (of {N}) so that {args.steps}+{args.warmup} steps end within "
-                  f"minutes; the reference's step time is ~linear in N, so this OVERSTATES its throughput")
+        sample = (f"global batch B={B}, table rows reduced to N={n_used} (of {N}) so that {args.steps}+{args.warmup} steps end "
+                  f"within minutes; the reference's step time grows with N, so this OVERSTATES its throughput")
     v, t_step, cores = run_cpu(B, n_used, D, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "train samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, N, D),
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.batch, N, D, world),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": cpu_kind(), "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -274,6 +324,265 @@ def workload_config(B, N, D, world=1):
             "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
             "ids": "uniform over disjoint per-field ranges", "l2": "inputs larger than L2: 3 tables x 3 arrays x "
             f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step"}
+
+
+# ----------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations and the stock-PyTorch-on-B200 baseline
+# ----------------------------------------------------------------------------------------------
+CAMPAIGN_CARD = (24, 40, 300_000, 35, 370, 5, 25_000, 50_000, 21, 14, 4, 4, 130, 5)     # per-field cardinalities, rest -> usertag
+
+
+def make_campaign_batch(gen, B, N, device):
+    """C1 ids: disjoint per-field ranges with campaign-like cardinalities, a Zipf-like (log-uniform rank: density
+    ~ 1/rank) draw within a field, then a fixed random permutation of [0, N) (the first-seen rank interleaving of
+    src/encode/data_.py); ~5 % positive labels.  Generated on the host (B is 4096) from a seed drawn off `gen`."""
+    seed = int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen, device=gen.device).item())
+    rng = np.random.default_rng(seed)
+    card = list(CAMPAIGN_CARD)
+    card.append(max(N - sum(card), 1))
+    perm = np.random.default_rng(7).permutation(N)
+    cols, base = [], 0
+    for c in card:
+        c = max(min(c, N - base), 1)
+        rank = np.minimum(np.floor(np.power(float(c), rng.random(B))).astype(np.int64) - 1, c - 1)
+        cols.append(base + np.maximum(rank, 0))
+        base += c
+    x = perm[np.minimum(np.stack(cols, axis=1), N - 1)]
+    y = (rng.random(B) < 0.05).astype(np.int64)
+    return torch.as_tensor(x).to(device), torch.as_tensor(y).to(device)
+
+
+def _time_steps(ctx, run, steps, warmup, after=None):
+    """(ms per step, max over ranks): CUDA events around `steps` calls of run(i) after `warmup` untimed ones; `after()`
+    (e.g. the lazy flush) runs inside the timed region."""
+    for i in range(warmup):
+        run(i)
+    ctx["barrier"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        run(warmup + i)
+    if after is not None:
+        after()
+    e1.record()
+    ctx["barrier"]()
+    return ctx["max_over_ranks"](e0.elapsed_time(e1)) / steps
+
+
+def _hbm(bytes_per_sample, samples_per_s, peak, what):
+    a = bytes_per_sample * samples_per_s / 1e9
+    return {"bound": "hbm", "algorithmic_bytes_per_sample": bytes_per_sample, "achieved": a, "peak": peak, "unit": "GB/s",
+            "frac": a / peak, "what": what}
+
+
+def run_c1(ctx):
+    """configs[0]: the reference's own CPU-runnable case -- FM, B=4096, N=1e6, campaign-shaped ids -- on the B200 path and,
+    beside it, the reference's CPU implementation on the host cores."""
+    from rl_ctr_prediction_b200 import graphs, optim, p_model
+    dev = ctx["dev"]
+    B, N, D = 4096, 1_000_000, 10
+    gen = torch.Generator(device=dev).manual_seed(11)
+    m = p_model.FM(N, D, device=dev)
+    with torch.no_grad():
+        m.table.mul_(0.1)
+    m.train()
+    opt = optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    step = graphs.GraphedTrainStep([(m, opt)], torch.nn.BCELoss())
+    batches = [make_campaign_batch(gen, B, N, dev) for _ in range(16)]
+    steps = 200
+    ms = _time_steps(ctx, lambda i: step(*batches[i % len(batches)]), steps, 8, after=m.flush)
+    v = B / (ms / 1e3)
+    out = {"workload": "C1: FM train step, B=4096, F=15, D=10, N=1e6, campaign-shaped Zipf ids (SURVEY 8d), graph replay, lazy "
+                       "flush inside the timed region", "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+           "roofline": _hbm(6068, v, ctx["peak"], "FM train step, sparse/lazy update (SURVEY 8d): at B=4096 the step is "
+                                                  "launch-latency bound (a handful of ~5 us kernels), not HBM bound")}
+    del m, opt, step
+    try:
+        vc, t_step, cores = run_cpu(B, N, D, 10, 3, names=("FM",), batch_fn=make_campaign_batch)
+        out["cpu_reference"] = {"value": vc, "unit": "samples/s", "cores": cores, "kind": cpu_kind(), "ms_per_step": t_step * 1e3,
+                                "sample": "10 steps after 3 warm-up, dense Adam over all 1e6 rows (reference semantics)"}
+    except Exception as exc:
+        out["cpu_reference"] = {"error": str(exc)[:200]}
+    return out
+
+
+def _frozen_ctr_models(N, D, dev, names=("LR", "FM", "FFM")):
+    from rl_ctr_prediction_b200 import p_model
+    md = {}
+    for i, name in enumerate(names):
+        m = {"LR": lambda: p_model.LR(N, device=dev), "FM": lambda: p_model.FM(N, D, device=dev),
+             "FFM": lambda: p_model.FFM(N, F_FIELDS, D, device=dev)}[name]()
+        with torch.no_grad():
+            m.table.mul_(0.1)
+        md[i] = m.eval()
+    return md
+
+
+def _policy_flops(widths):
+    return 2.0 * sum(a * b for a, b in zip(widths[:-1], widths[1:]))
+
+
+def run_c3(ctx):
+    """configs[2]: REINFORCE policy over model_dict = {LR, FM, FFM} (src/all_main/main.py:437), reward from generate_preds,
+    the update fused into the step (PG_model.PolicyGradient.fused_step), one CUDA graph."""
+    from rl_ctr_prediction_b200 import PG_model, graphs
+    dev, args = ctx["dev"], ctx["args"]
+    B, N, D = args.batch, args.rows, args.dims
+    md = _frozen_ctr_models(N, D, dev)
+    M = len(md)
+    torch.manual_seed(3)
+    pg = PG_model.PolicyGradient(N, F_FIELDS, D, action_nums=M - 1, device=dev)
+    with torch.no_grad():
+        pg.policy_net.embedding_layer.table.mul_(0.1)
+    gen = torch.Generator(device=dev).manual_seed(13)
+    batches = [make_batch(gen, B, N, dev) for _ in range(8)]
+    step = graphs.GraphedCallable(lambda x, y: pg.fused_step(x, y.reshape(-1, 1), md)[0], [pg.optimizer])
+    steps = 20
+    ms = _time_steps(ctx, lambda i: step(*batches[i % len(batches)]), steps, 5)
+    v = B / (ms / 1e3)
+    P = F_FIELDS * (F_FIELDS - 1) // 2
+    hbm_bytes = 1740 + 184 + 784 + 8584 + (12 * M + 24)       # state encoder + LR, FM, FFM forwards + generate_preds (SURVEY 8d)
+    fl = 3.0 * _policy_flops([P + F_FIELDS * D, 1024, 512, 256, 128, M - 1])          # forward + dgrad + wgrad
+    tf = fl * v / 1e12
+    return {"workload": "C3: Feature_Embedding -> policy MLP (255-1024-512-256-128-2, ReLU, Dropout .2) -> action draw -> "
+                        "generate_preds over {LR, FM, FFM} (N=1e7 rows each) -> +-1 reward -> returns -> REINFORCE loss -> Adam "
+                        "(lr 1e-4, wd 1e-5), B=65536, one CUDA graph, nothing leaves the device",
+            "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "graph_launches_per_step": step.launches_per_step,
+            "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": 3 * tf, "peak": ctx["tpeak"], "unit": "TFLOP/s",
+                         "frac": 3 * tf / ctx["tpeak"], "fp32_equiv_TFLOPs": tf,
+                         "what": "policy MLP GEMMs (3xTF32: 3 tensor-pipe MMAs per fp32 product), 5.7 MFLOP/sample against "
+                                 "11.4 KB/sample of HBM gathers: the step is tensor-bound",
+                         "hbm": _hbm(hbm_bytes, v, ctx["peak"], "state encoder + LR/FM/FFM scoring gathers + generate_preds")}}
+
+
+def run_c4(ctx):
+    """configs[3]: FFM + DeepFM, N=1e7-row tables; one GPU: fused-row tables in HBM; N>1: row-sharded over the GPUs."""
+    from rl_ctr_prediction_b200 import graphs, optim, p_model
+    dev, args, world = ctx["dev"], ctx["args"], ctx["world"]
+    B, N, D = args.batch, args.rows, args.dims
+    ms_ = []
+    for name in ("FFM", "DeepFM"):
+        if world > 1:
+            from rl_ctr_prediction_b200 import sharded
+            m = sharded.ShardedCTR(name, N, F_FIELDS, D, device=dev)
+        else:
+            m = p_model.FFM(N, F_FIELDS, D, device=dev) if name == "FFM" else p_model.DeepFM(N, F_FIELDS, D, device=dev)
+        with torch.no_grad():
+            m.table.mul_(0.1)
+        m.train()
+        ms_.append((m, optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5, mode="lazy")))
+    gen = torch.Generator(device=dev).manual_seed(17 + ctx["rank"])
+    batches = [make_batch(gen, B, N, dev) for _ in range(8)]
+    step = graphs.GraphedTrainStep(ms_, torch.nn.BCELoss(), fork=False)
+    steps = 20
+
+    def flush():
+        for m, _ in ms_:
+            m.flush()
+    ms = _time_steps(ctx, lambda i: step(*batches[i % len(batches)]), steps, 5, after=flush)
+    v = B * world / (ms / 1e3)
+    return {"workload": f"C4: FFM + DeepFM train step, B={B} per GPU, F=15, D=10, N=1e7 rows per table (FFM row = 151 floats), "
+                        + ("single GPU" if world == 1 else f"tables row-sharded over {world} GPUs (id mod G)")
+                        + ", graph replay, lazy flush inside the timed region",
+            "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+            "roofline": _hbm(76268 + 6068, v / world, ctx["peak"], "FFM train 76,268 B/sample + FM-part of DeepFM 6,068 B/sample "
+                                                                   "(SURVEY 8d), per GPU; DeepFM's tower is tensor work on top")}
+
+
+def run_c5(ctx):
+    """configs[4]: the full src/all_main/main.py step (state encoder, DDQN + DDPG acting, generate_preds over {LR, FM, FFM},
+    replay store, DDQN learn, DDPG critic + actor learn, Polyak) at a global batch of 1M; N>1: strong scaling, the batch
+    split over the ranks, frozen tables replicated, policy nets data-parallel (all-reduced gradients, cross-rank BatchNorm)."""
+    from rl_ctr_prediction_b200 import all_main
+    from rl_ctr_prediction_b200.DDQN_model import RingMemory
+    from rl_ctr_prediction_b200.Feature_embedding import Feature_Embedding
+    dev, args, world = ctx["dev"], ctx["args"], ctx["world"]
+    N, D = args.rows, args.dims
+    B_global = 1 << 20
+    B = B_global // world
+    md = _frozen_ctr_models(N, D, dev)
+    M = len(md)
+    torch.manual_seed(5)
+    fe = Feature_Embedding(N, F_FIELDS, D, device=dev)
+    with torch.no_grad():
+        fe.table.mul_(0.1)
+    ddqn, ddpg = all_main.get_model(M, N, F_FIELDS, D, 256, 1 << 21, dev, "1458")
+    if world > 1:
+        all_main.make_data_parallel(ddqn, ddpg)
+    RingMemory.device_sampling = True                     # replay indices drawn on the device (SURVEY 8f.4): no host RNG round trip
+    ddqn.device_rng = ddpg.device_rng = True              # exploration draws on the device too (the reference: CPU rand + H2D)
+    gen = torch.Generator(device=dev).manual_seed(19 + ctx["rank"])
+    batches = [make_batch(gen, B, N, dev) for _ in range(3)]
+    steps = 5
+
+    def run(i):
+        x, y = batches[i % len(batches)]
+        all_main.train_step(ddqn, ddpg, md, x, y.reshape(-1, 1), fe, 0.9, dev)
+    try:
+        ms = _time_steps(ctx, run, steps, 2)
+    finally:
+        RingMemory.device_sampling = False
+    v = B_global / (ms / 1e3)
+    P = F_FIELDS * (F_FIELDS - 1) // 2
+    S = P + F_FIELDS * D
+    fl = _policy_flops([S, 300, 300, 300, M - 1]) + _policy_flops([S + 1, 300, 300, 300, M])     # acting: DDQN + Actor forwards
+    tf = fl * v / 1e12
+    hbm_bytes = 1740 + 184 + 784 + 8584 + (12 * M + 24) + 4 * (F_FIELDS + 2) + 4 * (F_FIELDS + M + 2)
+    return {"workload": f"C5: src/all_main step, global batch {B_global} ({B} per GPU), N=1e7-row frozen tables, M=3 CTR models, "
+                        "replay batch 256, eager launches (the step reads td_error / a_loss on the host like the reference)"
+                        + ("" if world == 1 else "; policy nets data-parallel (all-reduced gradients, cross-rank BatchNorm), "
+                           "frozen tables replicated"),
+            "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "n_gpus": world, "scaling": "strong",
+            "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": 3 * tf, "peak": ctx["tpeak"] * world,
+                         "unit": "TFLOP/s", "frac": 3 * tf / (ctx["tpeak"] * world), "fp32_equiv_TFLOPs": tf,
+                         "what": "acting-path GEMMs of the DDQN and the DDPG actor over the whole batch (eval-mode BatchNorm folded "
+                                 "into the layers); the learn steps run on 256-sample replay batches",
+                         "hbm": _hbm(hbm_bytes, v / world, ctx["peak"], "state encoder + three scoring gathers + generate_preds + "
+                                                                        "replay stores, per GPU")}}
+
+
+def run_eager_gpu(dev, B, N, D, our_value):
+    """BASELINE.md section 1 names it first: the stock-PyTorch path on the same box.  The reference's modules restated on stock
+    ATen ops (oracle/torch_port.PortCTR == src/models/p_model.py) moved to the B200, the reference's loop body, dense
+    torch.optim.Adam over all rows -- what `python src/main/pretrain_main.py --device cuda:0` does per batch."""
+    from oracle import torch_port as TP
+    torch.manual_seed(1)
+    ms = []
+    for name in MODELS:
+        m = TP.PortCTR(name, N, F_FIELDS, D).to(dev)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if "embedding" in k or k == "linear.weight":
+                    p.mul_(0.1)
+        m.train()
+        ms.append((m, torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)))
+    gen = torch.Generator(device=dev).manual_seed(1)
+    batches = [make_batch(gen, B, N, dev) for _ in range(4)]
+    lossf = torch.nn.BCELoss()
+
+    def step(i):
+        x, y = batches[i % len(batches)]
+        yy = y.unsqueeze(1).float()
+        for m, opt in ms:
+            tl = lossf(m(x), yy)
+            m.zero_grad()
+            tl.backward()
+            opt.step()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 8
+    e0.record()
+    for i in range(steps):
+        step(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    v = B / (ms_step / 1e3)
+    return {"value": v, "unit": "samples/s", "ms_per_step": ms_step, "steps": steps, "speedup_of_this_repo": our_value / v,
+            "impl": "stock PyTorch eager on cuda:0: nn.Embedding gathers, autograd (dense embedding gradients), "
+                    "torch.optim.Adam(lr=1e-3, weight_decay=1e-5) over all rows; same workload (C2), fp32, TF32 off"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -357,11 +666,42 @@ def b200_arm(args):
         launches += gstep.launches_per_step * K          # replayed launches are not seen by the host-side tally
     clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    ms_total = max_over_ranks(ms_total)
     value = B * K * world / (ms_total / 1e3)
+
+    # ---------------- steady state: windows of 20 steps WITHOUT the flush, then the flush on its own -----------------
+    # (the headline above charges one full flush of all three tables to K steps; an epoch of the reference is ~500 steps
+    # per flush, so the per-step cost of the lazy mode in production is the window figure plus flush_ms / steps_per_epoch)
+    steady = None
+    if args.windows > 0:
+        win, per_window = 20, []
+        for w in range(args.windows):
+            barrier()
+            e0.record()
+            for i in range(win):
+                run_step(*batches[(w * win + i) % len(batches)])
+            e1.record()
+            barrier()
+            per_window.append(max_over_ranks(e0.elapsed_time(e1)) / win)
+        barrier()
+        e0.record()
+        for m, _ in ms:
+            m.flush()
+        e1.record()
+        barrier()
+        flush_ms = max_over_ranks(e0.elapsed_time(e1))
+        med = statistics.median(per_window)
+        steady = {"value": B * world / (med / 1e3), "unit": "samples/s", "ms_per_step": med, "windows": args.windows,
+                  "steps_per_window": win, "ms_per_step_by_window": [round(v, 4) for v in per_window], "flush_ms": flush_ms,
+                  "note": "graph replay, no flush inside the windows (row staleness has reached its stationary level after the "
+                          "first ~30 steps); flush_ms = settling all rows of all three tables once (end of epoch / state_dict)"}
 
     # ---------------- per-kernel pass: the same steps, eagerly, CUDA events around every library call --------------
     prof = _lib.KernelTimer()
@@ -511,16 +851,39 @@ def b200_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, t_step, cores = run_cpu(B, N, D, args.cpu_steps, 1)
-        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": cpu_kind(),
                "sample": f"{args.cpu_steps} steps (after 1 warm-up) of the same workload (B={B}, N={N}), "
                          f"{t_step:.2f} s/step, dense Adam over all rows (reference semantics)"}
+
+    # ---------------- the other BASELINE.json configurations + the stock-PyTorch-on-B200 baseline ------------------
+    configs, eager_gpu = None, None
+    if not args.no_configs:
+        configs = {}
+        ctx = {"dev": dev, "world": world, "rank": rank, "barrier": barrier, "max_over_ranks": max_over_ranks, "peak": peaks()[0],
+               "tpeak": tensor_peak()[0], "args": args}
+        for name in [c.strip() for c in args.configs.split(",") if c.strip()]:
+            fn = {"C1": run_c1, "C3": run_c3, "C4": run_c4, "C5": run_c5}.get(name)
+            if fn is None or (world > 1 and name in ("C1", "C3")):
+                continue                                  # C1 / C3 are single-GPU configurations
+            try:
+                configs[name] = fn(ctx)
+            except Exception as exc:                      # a config that cannot run must not take the headline down with it
+                configs[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+    if world == 1 and not args.no_eager_gpu:
+        try:
+            eager_gpu = run_eager_gpu(dev, B, N, D, value)
+        except Exception as exc:
+            eager_gpu = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world),
                 "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-                "cuda_graph": bool(use_graph), "graph_branches": bool(use_graph and not args.no_fork)}
+                "cuda_graph": bool(use_graph), "graph_branches": bool(use_graph and not args.no_fork),
+                "steady_state": steady, "configs": configs, "gpu_eager_baseline": eager_gpu}
         print(json.dumps(line))
     if world > 1:
         torch.cuda.synchronize()

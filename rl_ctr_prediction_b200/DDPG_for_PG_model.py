@@ -43,6 +43,9 @@ class Critic(nn.Module):
 
 
 class DDPG:
+    device_rng = False      # see DDQN_model.DoubleDQN
+    grad_sync = None
+
     def __init__(self, feature_nums, field_nums=15, latent_dims=5, action_nums=2, campaign_id="1458", lr_A=1e-4, lr_C=1e-3,
                  reward_decay=1, memory_size=4096000, batch_size=256, tau=0.005, device="cuda:0"):
         self.feature_nums, self.field_nums, self.action_nums, self.campaign_id = feature_nums, field_nums, action_nums, campaign_id
@@ -84,7 +87,7 @@ class DDPG:
         """:175-192."""
         action = self._actor_eval(state, ddqn_a)
         self.Actor.train()
-        random_seeds = torch.rand(len(state), 1).to(self.device)
+        random_seeds = torch.rand(len(state), 1, device=self.device if self.device_rng else None).to(self.device)
         random_action = torch.softmax(torch.normal(action, exploration_rate), dim=1)
         return torch.where(random_seeds >= exploration_rate, action, random_action)
 
@@ -109,6 +112,8 @@ class DDPG:
         td_error = self.loss_func(q, q_target)
         self.optimizer_c.zero_grad()
         td_error.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.Critic.parameters())
         self.optimizer_c.step()
         return td_error.item()
 
@@ -116,5 +121,7 @@ class DDPG:
         a_loss = -self.Critic.forward(b_s, self.Actor.forward(b_s, b_ddqn_a), b_ddqn_a).mean()
         self.optimizer_a.zero_grad()
         a_loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.Actor.parameters())
         self.optimizer_a.step()
         return a_loss.item()

@@ -81,6 +81,9 @@ class RingMemory:
 
 
 class DoubleDQN:
+    device_rng = False      # True: epsilon-greedy draws on the device (no CPU generator + H2D copy per batch); False: as the reference
+    grad_sync = None        # data-parallel training: callable(parameters) that all-reduces the gradients (all_main.make_data_parallel)
+
     def __init__(self, feature_nums, field_nums, latent_dims, campaign_id="1458", action_nums=3, learning_rate=1e-3,
                  reward_decay=1, replace_target_iter=30, memory_size=300, batch_size=32, device="cuda:0"):
         self.action_nums = action_nums - 1                       # :70  Q-values for actions 2..M
@@ -115,9 +118,10 @@ class DoubleDQN:
         """:144-161."""
         action_values = self._q_eval_mode(states)
         self.eval_net.train()
-        random_seeds = torch.rand(len(states), 1).to(self.device)
+        rdev = self.device if self.device_rng else None
+        random_seeds = torch.rand(len(states), 1, device=rdev).to(self.device)
         max_action = torch.argsort(-action_values)[:, 0] + 2
-        random_action = torch.randint(low=2, high=self.action_nums + 2, size=[len(states), 1]).to(self.device)
+        random_action = torch.randint(low=2, high=self.action_nums + 2, size=[len(states), 1], device=rdev).to(self.device)
         return torch.where(random_seeds >= exploration_rate, max_action.view(-1, 1), random_action)
 
     def choose_best_action(self, states):
@@ -151,5 +155,7 @@ class DoubleDQN:
         loss = self.loss_func(q_eval, q_target)
         self.optimizer.zero_grad()
         loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.eval_net.parameters())
         self.optimizer.step()
         return loss

@@ -67,8 +67,15 @@ class Feature_Embedding(nn.Module):
         B, F = x.shape
         width = self.output_dims
         if out is None:
-            out = torch.empty(B, width, dtype=torch.float32, device=x.device)
+            # rows at a pitch of round4(width) floats (256 for the 255-wide state): the [B, width] view handed out is
+            # 16-byte aligned row by row, so the first Linear of a policy net fetches it by TMA (mlp._rows_view passes
+            # the pitch on) instead of falling to the software-staged GEMM; the pad column is never read
+            pitch = (width + 3) // 4 * 4
+            out = torch.empty(B, pitch, dtype=torch.float32, device=x.device)[:, :width]
         t = table_struct(self.table.data, self._geom)
-        _lib.check(lib.rlctr_featemb_fwd(_lib.ptr(x), C.byref(t), _lib.ptr(out), out.stride(0), B, F, _lib.stream()),
-                   "rlctr_featemb_fwd")
+        if not out.is_cuda or out.stride(1) != 1:
+            raise _lib.RlctrError("Feature_Embedding output must be a CUDA tensor with unit column stride")
+        _lib.call("rlctr_featemb_fwd", lib.rlctr_featemb_fwd, _lib.ptr(x), C.byref(t), out.data_ptr(),
+                  out.stride(0) if B > 1 else width, B, F, _lib.stream(),
+                  meta={"B": B, "F": F, "dim": self._geom.dim, "rs": self._geom.row_stride, "n_rows": self._geom.n_rows, "lin": False})
         return out

@@ -155,3 +155,54 @@ class PolicyGradient:
         self.optimizer.step()
         self._clear()
         return loss
+
+    # ------------------------------------------------------------------------------------------
+    def returns_on_device(self, rewards):
+        """``discount_and_norm_rewards`` (:139-154) without leaving the device: the float64 suffix returns
+        ``G_i = r_i + gamma * G_{i+1}`` are one fp64 scan (rlctr_gae_scan, the kernel behind the PPO agent's advantage
+        recurrence), then ``(G - mean) / std`` (population std, as ``np.std``) and the cast to fp32."""
+        import ctypes as C
+        lib = _lib.load()
+        r = rewards.reshape(-1).float().contiguous()
+        n = r.numel()
+        out = torch.empty(n, dtype=torch.float32, device=r.device)
+        ws_bytes = lib.rlctr_gae_ws_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
+        _lib.check(lib.rlctr_gae_scan(_lib.ptr(r), n, float(self.gamma), _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream()),
+                   "rlctr_gae_scan")
+        g = out.flip(0).double()                       # the scan writes G of sample n-1-i at i (Hybrid_PPO_model.py:206-212)
+        g = (g - g.mean()) / g.std(unbiased=False)
+        return g.float()
+
+    def fused_step(self, features, labels, model_dict, prob_weights=None, actions=None):
+        """BASELINE.json configs[2]: the REINFORCE update fused into ONE training step over a batch, nothing leaving the
+        device.  The policy's logits serve both the action draw (``choose_action`` :110-121, device RNG) and the loss;
+        the action a in 1..A is the number of CTR models to ensemble minus one (k = a + 1 in 2..M, the action space of
+        ``src/all_main/main.py:285``); ``generate_preds`` (:183-271) scores the M frozen models and returns the +-1
+        reward; the batch is the episode: returns :139-154, loss :104-107, Adam :87.  Returns (loss, rewards, actions).
+
+        The unfused sequence -- ``choose_action``, ``generate_preds``, ``store_transition``, ``learn`` -- gives the same
+        update for the same actions (tests/test_gpu_policy.py::test_reinforce_fused_step_equals_unfused)."""
+        from .ensemble import generate_preds
+        x = features.long()
+        self.policy_net.train()
+        logits = self.policy_net.logits(x)
+        B, M = x.shape[0], len(model_dict)
+        if self.action_nums != M - 1:
+            raise ValueError(f"fused_step: the policy picks k in 2..M, so action_nums must be M - 1 = {M - 1}")
+        with torch.no_grad():
+            if actions is None:
+                pw = torch.softmax(logits.detach(), dim=1)
+                seeds = torch.rand(B, 1, device=x.device)
+                rand_a = torch.randint(1, self.action_nums + 1, (B, 1), device=x.device)
+                mx, arg = torch.max(pw, 1)
+                actions = torch.where(seeds >= mx.view(-1, 1), arg.view(-1, 1) + 1, rand_a)
+            if prob_weights is None:                   # no weight-emitting actor in this configuration: equal weights
+                prob_weights = torch.full((B, M), 1.0 / M, device=x.device)
+            _, _, rewards = generate_preds(model_dict, x, actions + 1, prob_weights, labels, x.device, "train")
+            vt = self.returns_on_device(rewards)
+        loss = self.loss_func(logits, actions, vt)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return loss, rewards, actions

@@ -80,3 +80,93 @@ def test(ddqn_model, ddpg_for_pg_model, model_dict, embedding_layer, data_loader
     t = torch.cat(targets).cpu().numpy()
     p = torch.cat(predicts).cpu().numpy()
     return roc_auc_score(t, p), sum(losses) / len(losses)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Data-parallel policy nets (no counterpart in the reference, which is single-device):
+# every rank runs the step on its slice of the batch, the frozen tables are replicated, and the learn steps
+# behave like the single-process step on the concatenated replay batch: BatchNorm batch statistics are taken
+# over all ranks' samples and the parameter gradients are averaged before the optimizer step.
+# ---------------------------------------------------------------------------------------------------
+class _CrossRankBatchNorm(torch.autograd.Function):
+    """BatchNorm1d in train mode over the samples of ALL ranks: one all_reduce of (sum, sum of squares, count) forward,
+    one of (sum dy, sum dy * xhat) backward.  Each rank backpropagates its own local loss; the parameter gradients are
+    summed / averaged afterwards by ``grad_sync`` like every other parameter's."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group):
+        import torch.distributed as dist
+        C_ = x.shape[1]
+        stats = torch.cat([x.sum(0), (x * x).sum(0), x.new_tensor([float(x.shape[0])])])
+        dist.all_reduce(stats, group=group)
+        n = stats[-1]
+        mean = stats[:C_] / n
+        var = (stats[C_:2 * C_] / n - mean * mean).clamp_min_(0.0)          # biased, as BatchNorm normalises with
+        invstd = torch.rsqrt(var + eps)
+        xhat = (x - mean) * invstd
+        if running_mean is not None:
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var * (n / (n - 1).clamp_min(1.0)), alpha=momentum)   # unbiased, as torch
+        ctx.save_for_backward(xhat, invstd, weight)
+        ctx.n, ctx.group = n, group
+        return xhat * weight + bias
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        xhat, invstd, weight = ctx.saved_tensors
+        C_ = dy.shape[1]
+        dbias, dweight = dy.sum(0), (dy * xhat).sum(0)
+        s = torch.cat([dbias, dweight])
+        dist.all_reduce(s, group=ctx.group)
+        dx = weight * invstd * (dy - s[:C_] / ctx.n - xhat * (s[C_:] / ctx.n))
+        return dx, dweight, dbias, None, None, None, None, None
+
+
+class CrossRankBatchNorm1d(torch.nn.BatchNorm1d):
+    """``nn.BatchNorm1d`` whose train-mode statistics span the process group (same parameters, buffers and state_dict)."""
+    _group = None
+
+    def forward(self, x):
+        import torch.distributed as dist
+        if not self.training or not dist.is_initialized() or dist.get_world_size(self._group) == 1:
+            return super().forward(x)
+        if self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        return _CrossRankBatchNorm.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                         self.momentum if self.momentum is not None else 0.1, self._group)
+
+
+def make_data_parallel(ddqn_model, ddpg_for_pg_model, group=None):
+    """Turn the two agents of ``get_model`` into data-parallel ones over ``group`` (NCCL over NVLink on the B200 box, gloo in
+    the CPU tests): parameters and buffers are broadcast from rank 0, every BatchNorm1d takes cross-rank batch statistics,
+    and ``learn`` / ``learn_c`` / ``learn_a`` average the gradients over the ranks before the Adam step (one all_reduce of a
+    flat buffer per network)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nets = [ddqn_model.eval_net, ddqn_model.target_net, ddpg_for_pg_model.Actor, ddpg_for_pg_model.Critic,
+            ddpg_for_pg_model.Actor_, ddpg_for_pg_model.Critic_]
+    for net in nets:
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        for m in net.modules():
+            if type(m) is torch.nn.BatchNorm1d:
+                m.__class__ = CrossRankBatchNorm1d
+                m._group = group
+
+    def grad_sync(params):
+        ps = [p for p in params if p.grad is not None]
+        if not ps:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        dist.all_reduce(flat, group=group)
+        flat.div_(world)
+        o = 0
+        for p in ps:
+            p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+
+    ddqn_model.grad_sync = grad_sync
+    ddpg_for_pg_model.grad_sync = grad_sync
+    return grad_sync

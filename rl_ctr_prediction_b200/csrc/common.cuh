@@ -43,6 +43,14 @@ namespace rlctr {
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }
+// One-shot gather of a row that nothing else in the kernel re-reads: no L1 allocation, and the L2 fill limited to the 64 bytes
+// asked for (the default promotes a miss to the whole 128-byte line: ncu showed 128 B of DRAM reads per 64 B row; rowprobe:
+// 36.9 -> 30.8 us for 983,040 random 64 B rows).  SASS: LDG.E.NA.LTC64B.128.CONSTANT.
+__device__ __forceinline__ float4 ldg4_once(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float4 ld4(const float* p) {
     return *reinterpret_cast<const float4*>(p);
 }
@@ -110,13 +118,17 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float sqrt_approx(float x) {       // one MUFU.SQRT (sqrt(0) = 0: no guard needed)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void adam_l2_elem(float& p, float& m, float& v, const AdamHyper& h, float step_size,
                                              float inv_bc2_sqrt) {
     const float g = h.wd * p;
     m = fmaf(h.omb1, g - m, m);
     v = fmaf(h.omb2 * g, g, v * h.beta2);
-    const float sq = v > 0.f ? v * rsqrt_approx(v) : 0.f;
-    const float denom = fmaf(sq, inv_bc2_sqrt, h.eps);
+    const float denom = fmaf(sqrt_approx(v), inv_bc2_sqrt, h.eps);       // 2 MUFU + 7 FMA-pipe instructions per element-step
     p = fmaf(-step_size * m, rcp_approx(denom), p);
 }
 __device__ __forceinline__ void adam_l2_step4(float4& p, float4& m, float4& v, float2 s, const AdamHyper& h) {

@@ -66,8 +66,8 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
             }
             float4 ra = f4zero(), rb = f4zero();
             const bool oka = (uint64_t)ia < (uint64_t)n_rows, okb = (uint64_t)ib < (uint64_t)n_rows;
-            if (oka) ra = ldg4(row_ptr(tab, sv, ia, pitch) + col0);
-            if (okb) rb = ldg4(row_ptr(tab, sv, ib, pitch) + col0);
+            if (oka) ra = ldg4_once(row_ptr(tab, sv, ia, pitch) + col0);
+            if (okb) rb = ldg4_once(row_ptr(tab, sv, ib, pitch) + col0);
             s = f4add(s, f4add(ra, rb));
             if (fm) {
 #pragma unroll
@@ -204,8 +204,8 @@ featemb_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ ta
             if (chunk_on && fa < fields) ia = __ldg(ids + b * fields + fa);
             if (chunk_on && fb < fields) ib = __ldg(ids + b * fields + fb);
             float4 ra = f4zero(), rb = f4zero();
-            if ((uint64_t)ia < (uint64_t)n_rows) ra = ldg4(tab + ia * pitch + col0);
-            if ((uint64_t)ib < (uint64_t)n_rows) rb = ldg4(tab + ib * pitch + col0);
+            if ((uint64_t)ia < (uint64_t)n_rows) ra = ldg4_once(tab + ia * pitch + col0);
+            if ((uint64_t)ib < (uint64_t)n_rows) rb = ldg4_once(tab + ib * pitch + col0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int d = col0 + k - emb_col;

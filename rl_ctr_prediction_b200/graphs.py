@@ -289,3 +289,67 @@ class GraphedTrainStep:
         if self.graph is None:
             self.eager_left -= 1
         return self._eager_on_side_stream(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True))
+
+
+class GraphedCallable:
+    """CUDA-graph replay of any device-only step ``fn(*tensors) -> tensor | tuple of tensors`` whose optimizers are
+    :class:`.optim.Adam` (the REINFORCE step of PG_model.PolicyGradient.fused_step, an inference pass ...): the first
+    ``eager_steps`` calls run eagerly on a side stream (lazily created state must exist before capture), the next one is
+    captured, later ones copy the inputs into the static buffers and replay.  ``fn`` must not synchronise with the host."""
+
+    def __init__(self, fn, optimizers=(), eager_steps=2, steps_ahead=65536):
+        self.fn, self.optimizers = fn, list(optimizers)
+        self.eager_left, self.steps_ahead = int(eager_steps), int(steps_ahead)
+        self.graph, self.inputs, self.outputs, self.stream = None, None, None, None
+        self.launches_per_step = 0
+
+    def _note(self):
+        for opt in self.optimizers:
+            opt._host_step += 1
+            for owner in opt._last_tables:
+                owner._opt.host_step += 1
+                if owner._opt.lazy:
+                    owner._opt.dirty = True
+            opt._note_dense(opt._last_live)
+
+    def _reserve(self):
+        for opt in self.optimizers:
+            for owner in opt._tables:
+                owner._opt.sched.ensure(owner._opt.host_step + self.steps_ahead)
+            if opt._dense_sched is not None:
+                opt._dense_sched.ensure(opt._dense_done + self.steps_ahead)
+
+    def __call__(self, *tensors):
+        dev = tensors[0].device
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=dev)
+        if self.graph is not None:
+            for buf, t in zip(self.inputs, tensors):
+                buf.copy_(t, non_blocking=True)
+            self.graph.replay()
+            self._note()
+            return self.outputs
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                out = self.fn(*tensors)
+            cur.wait_stream(self.stream)
+            return out
+        if _lib.timing():
+            raise _lib.RlctrError("per-kernel timing (KernelTimer) cannot be recorded inside a graph capture")
+        self._reserve()
+        self.inputs = [torch.empty_like(t) for t in tensors]
+        for buf, t in zip(self.inputs, tensors):
+            buf.copy_(t, non_blocking=True)
+        lib = _lib.load()
+        torch.cuda.synchronize()
+        l0 = lib.rlctr_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            self.outputs = self.fn(*self.inputs)
+        self.launches_per_step = int(lib.rlctr_launch_count() - l0)
+        self.graph = g
+        g.replay()                      # the capture ran the host side of one step but no kernel: replay it now
+        return self.outputs

@@ -165,7 +165,8 @@ class _GatherInteract(torch.autograd.Function):
         module = ctx.module
         if ctx.sorted_pair is None:
             raise _lib.RlctrError("backward through a forward that ran without gradient bookkeeping")
-        if module._opt is None:
+        if module._opt is None and not getattr(module, "rows_grad_only", False):
+            # (set ``model.rows_grad_only = True`` to inspect the row-form gradient -- module._stash -- without an optimizer)
             raise _lib.RlctrError("the embedding table's gradient exists only in row form (sorted ids + per-sample terms) and is "
                                   "consumed by rl_ctr_prediction_b200.optim.Adam(model.parameters(), ...): build that optimizer "
                                   "before calling backward -- a torch.optim optimizer would silently skip the table (its "

@@ -512,6 +512,7 @@ def test_afm_explicit_dropout_masks_match_reference(golden, golden_tails):
     comes from the real reference with F.dropout replaced by a multiplication with these masks)."""
     sd = state_from_golden(golden_tails, "afm_mask/init")
     m = load(build("AFM", 255), sd).to(DEV)
+    m.rows_grad_only = True                      # gradients are inspected, no optimizer is built
     x = torch.as_tensor(golden["train/x"][0]).to(DEV)
     y = torch.as_tensor(golden["train/y"][0]).unsqueeze(1).to(DEV)
     masks = torch.as_tensor(golden_tails["afm_mask/masks"]).to(DEV)

@@ -624,3 +624,118 @@ def test_ppo_learn_matches_reference(golden_ppo):
     # the rollout memory keeps the reference's (quirky) write semantics
     agent.store_memory(torch.ones(5, F_), torch.ones(5, A), torch.ones(5, A), torch.ones(5, 1), torch.ones(5, 1), torch.ones(5, 1))
     assert float(agent.memory_state[:5].sum()) == 5 * F_ and agent.memory_counter == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: REINFORCE fused into the step; acting path of the BN policy nets
+# ------------------------------------------------------------------------------------------------
+def _frozen_models(N, F, D):
+    from rl_ctr_prediction_b200 import p_model
+    torch.manual_seed(5)
+    ms = {0: p_model.LR(N, device=DEV), 1: p_model.FM(N, D, device=DEV), 2: p_model.FFM(N, F, D, device=DEV)}
+    for m in ms.values():
+        with torch.no_grad():
+            m.table.mul_(0.1)
+        m.eval()
+    return ms
+
+
+def test_reinforce_fused_step_equals_unfused():
+    """PolicyGradient.fused_step == choose actions, generate_preds, store_transition, learn() for the same actions:
+    same rewards (bit-exact), same normalised returns (device fp64 scan vs the host loop), same loss and update."""
+    import torch.nn as nn
+    from rl_ctr_prediction_b200 import PG_model, ensemble
+    N, F, D, B = 2000, 15, 10, 777
+    md = _frozen_models(N, F, D)
+    M = len(md)
+    rng = np.random.default_rng(2)
+    x = torch.as_tensor(rng.integers(0, N, size=(B, F))).to(DEV)
+    y = torch.as_tensor((rng.random((B, 1)) < 0.3).astype(np.int64)).to(DEV)
+    acts = torch.as_tensor(rng.integers(1, M, size=(B, 1))).to(DEV)
+
+    def make():
+        torch.manual_seed(21)
+        pg = PG_model.PolicyGradient(N, F, D, action_nums=M - 1, device=DEV)
+        for m in pg.policy_net.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
+        return pg
+
+    a, b = make(), make()
+    loss_a, r_a, act_a = a.fused_step(x, y, md, actions=acts)
+    w = torch.full((B, M), 1.0 / M, device=DEV)
+    _, _, r_b = ensemble.generate_preds(md, x, acts + 1, w, y, DEV, "train")
+    assert torch.equal(r_a, r_b) and torch.equal(act_a, acts)
+    b.store_transition(x, acts, r_b)
+    close(a.returns_on_device(r_b), b.discount_and_norm_rewards(), rtol=1e-6)
+    loss_b = b.learn()
+    close(loss_a, loss_b, rtol=1e-5)
+    for (k, p), (_, q) in zip(a.policy_net.mlp.state_dict().items(), b.policy_net.mlp.state_dict().items()):
+        assert torch.equal(p, q), k                      # same kernels, same inputs: bit-identical update
+    # own action draw: in range, and the epsilon-style rule of :110-121 picks argmax where rand >= max pi
+    _, r2, act2 = a.fused_step(x, y, md)
+    assert int(act2.min()) >= 1 and int(act2.max()) <= M - 1 and set(r2.unique().tolist()) <= {-1.0, 1.0}
+
+
+def test_reinforce_fused_step_graph_replay_equals_eager():
+    """graphs.GraphedCallable over fused_step: the replayed step (given actions) leaves the same network as the eager one."""
+    import torch.nn as nn
+    from rl_ctr_prediction_b200 import PG_model, graphs
+    N, F, D, B = 2000, 15, 10, 512
+    md = _frozen_models(N, F, D)
+    rng = np.random.default_rng(3)
+    batches = [(torch.as_tensor(rng.integers(0, N, size=(B, F))).to(DEV),
+                torch.as_tensor((rng.random((B, 1)) < 0.3).astype(np.int64)).to(DEV),
+                torch.as_tensor(rng.integers(1, 3, size=(B, 1))).to(DEV)) for _ in range(5)]
+
+    def make():
+        torch.manual_seed(22)
+        pg = PG_model.PolicyGradient(N, F, D, action_nums=2, device=DEV)
+        for m in pg.policy_net.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
+        return pg
+
+    a, b = make(), make()
+    step = graphs.GraphedCallable(lambda x, y, act: a.fused_step(x, y, md, actions=act)[0], [a.optimizer])
+    for x, y, act in batches:
+        la = step(x, y, act).clone()
+        lb = b.fused_step(x, y, md, actions=act)[0]
+        close(la, lb, rtol=1e-6)
+    assert step.graph is not None
+    torch.cuda.synchronize()
+    for (k, p), (_, q) in zip(a.policy_net.mlp.state_dict().items(), b.policy_net.mlp.state_dict().items()):
+        assert torch.equal(p, q), k
+    assert a.optimizer._dense_count == b.optimizer._dense_count
+
+
+def test_eval_mode_batchnorm_folded_into_gemm_and_padded_state():
+    """Acting path: Linear -> BatchNorm1d(eval) -> ReLU as one GEMM (mlp.Tower folds the running statistics into the layer)
+    over the 256-float-pitch state view == stock torch on the CPU."""
+    import torch.nn as nn
+    from rl_ctr_prediction_b200 import DDQN_model
+    from rl_ctr_prediction_b200.Feature_embedding import Feature_Embedding
+    from oracle import np_oracle as O
+    torch.manual_seed(9)
+    N, F, D, B = 3000, 15, 10, 1000
+    fe = Feature_Embedding(N, F, D, device=DEV)
+    x = torch.randint(0, N, (B, F), device=DEV)
+    s = fe(x)
+    assert s.shape == (B, 255) and s.stride(0) == 256 and s.data_ptr() % 16 == 0          # TMA-addressable rows
+    ref_state = O.feature_embedding(x.cpu().numpy(), fe.state_dict()["feature_embedding.weight"].cpu().numpy())
+    close(s, ref_state)
+    net = DDQN_model.Net(F, N, D, 2, device=DEV)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.3)
+                m.running_var.uniform_(0.5, 2.0)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    net.eval()
+    ref = torch_replica({k: v.cpu().numpy() for k, v in net.state_dict().items()}, 255, 2)
+    with torch.no_grad():
+        q = net(s)                                                                          # folded path
+        close(q, ref.mlp(torch.as_tensor(ref_state)), rtol=2e-5)
+    q_grad = net(s)                                                                         # autograd on: module-by-module path
+    close(q_grad, q, rtol=2e-5)

@@ -99,3 +99,46 @@ def test_shard_rows_and_owned_view():
     assert rows.tolist() == [1, 1, 3] and pos.tolist() == [1, 3, 5]
     rows, pos = sharded.owned_sorted_view_host(ids, 2, 1, 10)          # odd ids: 5, 9, 1 -> rows 2, 4, 0
     assert rows.tolist() == [0, 2, 4] and pos.tolist() == [6, 0, 2]
+
+
+# ---- data-parallel policy nets (all_main.make_data_parallel): cross-rank BatchNorm + averaged gradients == one process ------
+def _dp_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch.nn as nn
+        from rl_ctr_prediction_b200 import all_main
+
+        def net():
+            torch.manual_seed(3)
+            return nn.Sequential(nn.Linear(6, 5), nn.BatchNorm1d(5), nn.ReLU(), nn.Linear(5, 2))
+
+        torch.manual_seed(10)
+        X, Y = torch.randn(2 * 8, 6), torch.randn(2 * 8, 2)                  # the global batch, same on both ranks
+        ref = net()
+        ((ref(X) - Y) ** 2).mean().backward()                                # one process, whole batch
+        dp = net()
+        for m in dp.modules():
+            if type(m) is nn.BatchNorm1d:
+                m.__class__ = all_main.CrossRankBatchNorm1d
+        xs, ys = X[rank * 8:(rank + 1) * 8], Y[rank * 8:(rank + 1) * 8]
+        ((dp(xs) - ys) ** 2).mean().backward()                               # each rank: its slice, its local mean loss
+
+        class Agent:                                                         # the hook make_data_parallel installs
+            pass
+        a, b = Agent(), Agent()
+        a.eval_net = a.target_net = b.Actor = b.Critic = b.Actor_ = b.Critic_ = dp
+        sync = all_main.make_data_parallel(a, b)
+        sync(dp.parameters())
+        for (k, p), (_, q) in zip(dp.named_parameters(), ref.named_parameters()):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7), (k, (p.grad - q.grad).abs().max())
+        assert torch.allclose(dp[1].running_mean, ref[1].running_mean, atol=1e-6)
+        assert torch.allclose(dp[1].running_var, ref[1].running_var, atol=1e-6)
+        assert int(dp[1].num_batches_tracked) == 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_policy_nets_world2():
+    mp.spawn(_dp_worker, args=(2, _free_port()), nprocs=2, join=True)
