@@ -610,7 +610,10 @@ def b200_arm(args):
         for name in MODELS:
             if world > 1:      # BASELINE.json configs[3]: tables row-sharded over the GPUs (peer-mapped shards over NVLink)
                 from rl_ctr_prediction_b200 import sharded
-                m = sharded.ShardedCTR(name, N, F_FIELDS, D, device=dev)
+                own = not args.no_fork                      # a communicator per model: the models can be graph branches
+                m = sharded.ShardedCTR(name, N, F_FIELDS, D, device=dev,
+                                       group=dist.new_group(list(range(world))) if own else None)
+                m.fork_ok = own
             else:
                 m = {"LR": lambda: p_model.LR(N, device=dev), "FM": lambda: p_model.FM(N, D, device=dev),
                      "DeepFM": lambda: p_model.DeepFM(N, F_FIELDS, D, device=dev)}[name]()

@@ -286,6 +286,20 @@ int rlctr_sort_ids_sharded(const uint32_t* ids_all, int64_t n_all, int32_t world
  * on the dependent path of every row.  Out-of-range ids are skipped; width even: 8-byte stores. */
 int rlctr_push_rows(const int64_t* ids, int64_t n, int32_t world, int32_t rank, int64_t n_rows_global, const float* src,
                     int32_t width, void* const* peer_recv, rlctr_stream_t stream);
+/* Owner routing of a batch's ids (replaces the id all_gather + rlctr_sort_ids_sharded, whose per-rank work grows with the
+ * number of GPUs): rank `rank` buckets its n ids by owner, stably, and WRITES (local row, global slot = rank * n + slot) of
+ * bucket o into its segment [rank * cap, (rank + 1) * cap) of owner o's receive arrays peer_keys[o] / peer_vals[o]
+ * (uint32 [world * cap] each, peer-mapped; unused slots get the sentinel key 0xffffffff).  After a barrier each owner
+ * sorts its world * cap received pairs by row with rlctr_sort_routed (ws: rlctr_sort_ws_bytes(world * cap, n_rows_local)
+ * bytes): the same sorted view as rlctr_sort_ids_sharded without the non-owned tail, same (row, source rank, slot) order.
+ * A bucket with more than `cap` ids sets *overflow (device int32, never cleared by the library) != 0: the view is then
+ * incomplete -- rerun with a larger cap.  ws: rlctr_route_ws_bytes(n, world) bytes. */
+size_t rlctr_route_ws_bytes(int64_t n, int32_t world);
+int rlctr_route_ids(const int64_t* ids, int64_t n, int32_t world, int32_t rank, int64_t n_rows_global, int64_t cap,
+                    void* const* peer_keys, void* const* peer_vals, int32_t* overflow, void* ws, size_t ws_bytes,
+                    rlctr_stream_t stream);
+int rlctr_sort_routed(const uint32_t* keys, const uint32_t* vals, int64_t n_in, int64_t n_rows_local, uint32_t* sorted_rows,
+                      uint32_t* sorted_slots, void* ws, size_t ws_bytes, rlctr_stream_t stream);
 int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                     const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
                     void* ws, size_t ws_bytes, rlctr_stream_t stream);

@@ -92,6 +92,9 @@ SIGNATURES = {
     "rlctr_sort_ws_bytes": (_SZ, [_I64, _I64]),
     "rlctr_sort_ids": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "rlctr_sort_ids_sharded": (C.c_int, [_P, _I64, _I32, _I32, _I64, _P, _P, _P, _SZ, _P]),
+    "rlctr_route_ws_bytes": (_SZ, [_I64, _I32]),
+    "rlctr_route_ids": (C.c_int, [_P, _I64, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "rlctr_sort_routed": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "rlctr_rows_ws_bytes": (_SZ, [_I64]),
     "rlctr_rows_adam": (C.c_int, [_P, _P, _I64, _GP, _TP, _AP, _P, _SZ, _P]),
     "rlctr_rows_grad_dense": (C.c_int, [_P, _P, _I64, _GP, _TP, _P, _P, _SZ, _P]),

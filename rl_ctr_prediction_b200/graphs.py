@@ -137,9 +137,14 @@ class GraphedTrainStep:
         if not self.fork:
             return []
         opts = [opt for _, opt in self.pairs]
+        # a row-sharded model may branch off too when it has a process group of its own (sharded.ShardedCTR.fork_ok): its
+        # collectives then run on their own communicator, so the branches' NCCL calls cannot be ordered differently on
+        # different ranks, and its device barriers use the signal pads of its own symmetric allocation
         side = [i for i, (m, opt) in enumerate(self.pairs)
-                if isinstance(m, Model._TableModel) and getattr(m, "mlp", None) is None and not hasattr(m, "train_step")
-                and not isinstance(m, (Model.DCN, Model.AFM)) and opts.count(opt) == 1]
+                if getattr(m, "mlp", None) is None and opts.count(opt) == 1 and
+                ((isinstance(m, Model._TableModel) and not isinstance(m, (Model.DCN, Model.AFM))) or getattr(m, "fork_ok", False))]
+        if any(hasattr(m, "train_step") and not getattr(m, "fork_ok", False) for m, _ in self.pairs):
+            side = []                             # sharded models sharing one communicator: keep the step serial
         if len(side) == len(self.pairs):
             side = side[1:]                       # somebody has to stay on the capture stream
         return side
@@ -152,7 +157,12 @@ class GraphedTrainStep:
             return self._eager(x, y)
         main = torch.cuda.current_stream()
         first = self.pairs[side[0]][0]
-        Model.sort_ids(Model._check_ids(x), first._geom.n_rows)      # shared by every model fed with this batch: before the fork
+        # the sorted view of the batch is shared by every model fed with it: computed before the fork
+        if hasattr(first, "train_step"):
+            from . import sharded as _sh
+            _sh.shared_sorted_view(Model._check_ids(x), first.feature_nums, first.group)
+        else:
+            Model.sort_ids(Model._check_ids(x), first._geom.n_rows)
         while len(self._side_streams) < len(side):
             self._side_streams.append(torch.cuda.Stream(device=first.table.device))
         losses = [None] * len(self.pairs)
@@ -174,7 +184,7 @@ class GraphedTrainStep:
         # its gather.
         heavy = [i for i in range(len(self.pairs)) if i not in side]
         first = self.pairs[heavy[0]][0]
-        if isinstance(first, Model._TableModel) and getattr(first, "mlp", None) is not None:
+        if (isinstance(first, Model._TableModel) or hasattr(first, "train_step")) and getattr(first, "mlp", None) is not None:
             first._after_gather = launch_side
         else:
             launch_side()

@@ -76,12 +76,52 @@ class PeerMemory:
 
 
 _VIEW_CACHE = {"key": None, "x": None, "view": None}
+_ROUTE = {}          # (n, world, device) -> receive buffers of the owner routing
+
+
+def route_capacity(n, world):
+    """Slots each source rank gets in every owner's receive buffer: RLCTR_ROUTE_CAP x the balanced share n / G (default 1.5;
+    ids spread by ``id mod G``, so a bucket is Binomial(n, 1/G): 1.5x is > 100 sigma for the uniform benchmark ids, and a
+    heavy-hitter id that alone exceeds it trips the overflow flag instead of corrupting the step silently)."""
+    f = float(os.environ.get("RLCTR_ROUTE_CAP", "1.5"))
+    return ((int(f * n / world) + 1024) + 255) // 256 * 256
+
+
+def _route_buffers(n, world, dev, group):
+    key = (n, world, str(dev))
+    rb = _ROUTE.get(key)
+    if rb is None:
+        cap = route_capacity(n, world)
+        keys = PeerMemory(world * cap, torch.int32, dev, group)
+        vals = PeerMemory(world * cap, torch.int32, dev, group)
+        keys.local.fill_(-1)
+        vals.local.zero_()
+        rb = {"cap": cap, "keys": keys, "vals": vals, "overflow": torch.zeros(1, dtype=torch.int32, device=dev),
+              "kp": (C.c_void_p * 8)(*[int(p) for p in keys.ptrs]), "vp": (C.c_void_p * 8)(*[int(p) for p in vals.ptrs])}
+        keys.barrier()
+        _ROUTE[key] = rb
+    return rb
+
+
+def check_route_overflow():
+    """Host-side check of the routing overflow flags (one device -> host read each; called from ShardedCTR.flush)."""
+    for (n, world, _), rb in _ROUTE.items():
+        if int(rb["overflow"].item()) != 0:
+            raise _lib.RlctrError(f"owner routing overflow: some rank sent more than {rb['cap']} of its {n} ids to one owner "
+                                  f"(skewed ids); the steps since the last check are incomplete.  Rerun with a larger "
+                                  f"RLCTR_ROUTE_CAP (now {os.environ.get('RLCTR_ROUTE_CAP', '1.5')}) or RLCTR_SHARD_ROUTE=0")
 
 
 def shared_sorted_view(x, n_rows, group):
     """(sorted local rows u32[n_all], sorted global slots u32[n_all], n_all) of the GLOBAL batch as seen by this owner.
-    Models that consume the same batch and shard the same vocabulary share it (one all_gather + one sort per batch)."""
-    key = (id(x), x._version, x.data_ptr(), tuple(x.shape), int(n_rows), id(group))
+    Models that consume the same batch and shard the same vocabulary share it (one exchange + one sort per batch).
+
+    Default (RLCTR_SHARD_ROUTE=1): owner routing -- every rank writes the (local row, global slot) pairs of the ids a peer
+    owns straight into that peer's receive buffer (rlctr_route_ids: posted NVLink writes, fixed capacity per source), one
+    device barrier, and the owner sorts its G * cap ~ 1.5 n received pairs (rlctr_sort_routed): per-rank work independent
+    of G.  RLCTR_SHARD_ROUTE=0: all_gather of the ids + rlctr_sort_ids_sharded over all G * n of them (the first design)."""
+    # (the group is not part of the key: models with process groups of their own -- same ranks -- share the view)
+    key = (id(x), x._version, x.data_ptr(), tuple(x.shape), int(n_rows))
     if _VIEW_CACHE["key"] == key and _VIEW_CACHE["x"] is x:
         return _VIEW_CACHE["view"]
     lib = _lib.load()
@@ -89,6 +129,27 @@ def shared_sorted_view(x, n_rows, group):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = x.device
     n = x.numel()
+    st = _lib.stream()
+    if world > 1 and os.environ.get("RLCTR_SHARD_ROUTE", "1") == "1":
+        rb = _route_buffers(n, world, dev, group)
+        cap = rb["cap"]
+        ws_bytes = lib.rlctr_route_ws_bytes(n, world)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.call("rlctr_route_ids", lib.rlctr_route_ids, _lib.ptr(x), n, world, rank, n_rows, cap, rb["kp"], rb["vp"],
+                  _lib.ptr(rb["overflow"]), _lib.ptr(ws), ws_bytes, st, meta={"n": n, "world": world, "cap": cap})
+        rb["keys"].barrier()                                     # every source's segment of my receive buffer is complete
+        n_all = world * cap
+        srows = torch.empty(n_all, dtype=torch.int32, device=dev)
+        sslots = torch.empty(n_all, dtype=torch.int32, device=dev)
+        n_local = shard_rows(n_rows, world, rank)
+        ws2_bytes = lib.rlctr_sort_ws_bytes(n_all, max(n_local, 1))
+        ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+        _lib.call("rlctr_sort_routed", lib.rlctr_sort_routed, _lib.ptr(rb["keys"].local), _lib.ptr(rb["vals"].local), n_all,
+                  max(n_local, 1), _lib.ptr(srows), _lib.ptr(sslots), _lib.ptr(ws2), ws2_bytes, st, key="rlctr_sort_ids",
+                  meta={"n": n_all})
+        view = (srows, sslots, n_all)
+        _VIEW_CACHE.update(key=key, x=x, view=view)
+        return view
     ids32 = x.reshape(-1).clamp(-1, n_rows).to(torch.int32)          # out-of-range ids stay out of range in 32 bits
     if world > 1:
         all32 = torch.empty(world * n, dtype=torch.int32, device=dev)
@@ -101,7 +162,7 @@ def shared_sorted_view(x, n_rows, group):
     ws_bytes = lib.rlctr_sort_ws_bytes(n_all, n_rows)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _lib.call("rlctr_sort_ids_sharded", lib.rlctr_sort_ids_sharded, _lib.ptr(all32), n_all, world, rank, n_rows, _lib.ptr(srows),
-              _lib.ptr(sslots), _lib.ptr(ws), ws_bytes, _lib.stream(), key="rlctr_sort_ids", meta={"n": n_all})
+              _lib.ptr(sslots), _lib.ptr(ws), ws_bytes, st, key="rlctr_sort_ids", meta={"n": n_all})
     view = (srows, sslots, n_all)
     _VIEW_CACHE.update(key=key, x=x, view=view)
     return view
@@ -159,6 +220,10 @@ class ShardedCTR(nn.Module):
         # mapping inside the update kernel (2-3 us NVLink round trips on its dependent path; kept for comparison and for FFM's
         # 600-byte partner rows)
         self.exchange = os.environ.get("RLCTR_SHARD_EXCHANGE", "push")
+        # True when `group` is used by this model alone: its step may then run as a parallel branch of a captured graph
+        # (graphs.GraphedTrainStep), overlapping its NVLink-bound gathers with another model's GEMMs
+        self.fork_ok = False
+        self._after_gather = None
 
     # ---- protocol shared with optim.Adam --------------------------------------------------------
     def _apply(self, fn, recurse=True):
@@ -177,6 +242,7 @@ class ShardedCTR(nn.Module):
     def flush(self):
         if self._opt is not None:
             self._opt.flush(self.table.data)
+        check_route_overflow()
 
     def _reduce_ws(self, dev):
         ws = self._ws.get("reduce")
@@ -340,6 +406,9 @@ class ShardedCTR(nn.Module):
                       key=f"rlctr_rows_catchup[Sharded{self.kind}]", meta=self._meta(n_all // F, F))
         self.barrier()                                        # B1: all owners caught their rows up | forward reads
         logit, trows = self._interact(x, buf, train=True)
+        hook, self._after_gather = self._after_gather, None     # graphs.GraphedTrainStep: fork point of the captured step
+        if hook is not None:
+            hook()
         tower_out = None
         if self.mlp is not None:
             trows.requires_grad_(True)

@@ -874,6 +874,56 @@ def test_sharded_sort_and_peer_gather(lib, world):
     assert lib.rlctr_embed_fwd(L().ptr(x), C.byref(t), L().ptr(bias), L().ptr(logit), None, 1, None, None, 0, B, F, 1, st()) == -2
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_owner_routing_equals_gather_and_sort(lib, world):
+    """rlctr_route_ids (every source writes the (local row, global slot) pairs a peer owns into that peer's receive buffer)
+    + rlctr_sort_routed == the all-gather + rlctr_sort_ids_sharded view == the host restatement, for every owner; G ranks
+    emulated on one GPU (the receive buffers of all owners live in the same memory).  A bucket beyond the capacity raises
+    the overflow flag."""
+    from rl_ctr_prediction_b200 import sharded
+    N, B, F = 5003, 300, 15
+    n = B * F
+    rng = np.random.default_rng(100 + world)
+    ids = rng.integers(0, N, size=(world, B, F))
+    ids[0, 0, 0] = N + 7                                  # out of range: routed nowhere
+    ids[1, 2, :] = ids[1, 3, :]                           # duplicates
+    cap = sharded.route_capacity(n, world)
+    keys = [torch.full((world * cap,), -1, dtype=torch.int32, device=DEV) for _ in range(world)]
+    vals = [torch.zeros(world * cap, dtype=torch.int32, device=DEV) for _ in range(world)]
+    kp = (C.c_void_p * 8)(*[k.data_ptr() for k in keys])
+    vp = (C.c_void_p * 8)(*[v.data_ptr() for v in vals])
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    wsb = lib.rlctr_route_ws_bytes(n, world)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    for src in range(world):                              # every source rank routes its batch
+        x = dev(ids[src].reshape(-1))
+        assert lib.rlctr_route_ids(L().ptr(x), n, world, src, N, cap, kp, vp, L().ptr(flag), L().ptr(ws), wsb, st()) == 0
+    assert int(flag.item()) == 0
+    ids_all = torch.as_tensor(ids.reshape(-1))
+    for owner in range(world):
+        n_in = world * cap
+        n_local = sharded.shard_rows(N, world, owner)
+        srows = torch.empty(n_in, dtype=torch.int32, device=DEV)
+        sslots = torch.empty(n_in, dtype=torch.int32, device=DEV)
+        wsb2 = lib.rlctr_sort_ws_bytes(n_in, n_local)
+        ws2 = torch.empty(wsb2, dtype=torch.uint8, device=DEV)
+        assert lib.rlctr_sort_routed(L().ptr(keys[owner]), L().ptr(vals[owner]), n_in, n_local, L().ptr(srows), L().ptr(sslots),
+                                     L().ptr(ws2), wsb2, st()) == 0
+        rows_h, pos_h = sharded.owned_sorted_view_host(ids_all, world, owner, N)
+        k = rows_h.numel()
+        assert torch.equal(srows[:k].cpu().long(), rows_h) and torch.equal(sslots[:k].cpu().long(), pos_h)
+        assert bool((srows[k:].cpu() == -1).all())        # sentinel tail (0xffffffff >= any row count)
+    # overflow: a capacity below the largest bucket
+    small = max(n // world // 4, 1)
+    k2 = [torch.empty(world * small, dtype=torch.int32, device=DEV) for _ in range(world)]
+    v2 = [torch.empty(world * small, dtype=torch.int32, device=DEV) for _ in range(world)]
+    kp2 = (C.c_void_p * 8)(*[k.data_ptr() for k in k2])
+    vp2 = (C.c_void_p * 8)(*[v.data_ptr() for v in v2])
+    assert lib.rlctr_route_ids(L().ptr(dev(ids[0].reshape(-1))), n, world, 0, N, small, kp2, vp2, L().ptr(flag), L().ptr(ws), wsb,
+                               st()) == 0
+    assert int(flag.item()) != 0
+
+
 @pytest.mark.parametrize("dz_in_sums", [0, 1])
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_owner_update_equals_single_table(lib, world, dz_in_sums):
