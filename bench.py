@@ -508,7 +508,10 @@ def run_c5(ctx):
         fe.table.mul_(0.1)
     ddqn, ddpg = all_main.get_model(M, N, F_FIELDS, D, 256, 1 << 21, dev, "1458")
     if world > 1:
-        all_main.make_data_parallel(ddqn, ddpg)
+        if os.environ.get("RLCTR_RL_DP", "gather") == "gather":
+            all_main.make_gathered_replay(ddqn, ddpg)         # one all_gather of the replay draws per agent, replicated learn step
+        else:
+            all_main.make_data_parallel(ddqn, ddpg)           # cross-rank BatchNorm + averaged gradients (a collective per layer)
     RingMemory.device_sampling = True                     # replay indices drawn on the device: no host RNG round trip
     ddqn.device_rng = ddpg.device_rng = True              # exploration draws on the device too (the reference: CPU rand + H2D)
     gen = torch.Generator(device=dev).manual_seed(19 + ctx["rank"])
@@ -530,8 +533,9 @@ def run_c5(ctx):
     hbm_bytes = 1740 + 184 + 784 + 8584 + (12 * M + 24) + 4 * (F_FIELDS + 2) + 4 * (F_FIELDS + M + 2)
     return {"workload": f"C5: src/all_main step, global batch {B_global} ({B} per GPU), N=1e7-row frozen tables, M=3 CTR models, "
                         "replay batch 256, eager launches (the step reads td_error / a_loss on the host like the reference)"
-                        + ("" if world == 1 else "; policy nets data-parallel (all-reduced gradients, cross-rank BatchNorm), "
-                           "frozen tables replicated"),
+                        + ("" if world == 1 else "; acting data-parallel over the batch, frozen tables replicated, the ranks' replay "
+                           "draws joined by one all_gather per agent and the learn step replicated (== the single-process step on the "
+                           "joined batch, BatchNorm statistics included; all_main.make_data_parallel is the gradient-all-reduce form)"),
             "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "n_gpus": world, "scaling": "strong",
             "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": 3 * tf, "peak": ctx["tpeak"] * world,
                          "unit": "TFLOP/s", "frac": 3 * tf / (ctx["tpeak"] * world), "fp32_equiv_TFLOPs": tf,
@@ -763,6 +767,39 @@ def b200_arm(args):
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(key), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "launches_timed": n_l, "mean_ms": mean_ms,
                 "share_of_step": groups[top] / Kp / step_ms}
+    if roof is not None and world > 1:
+        # NVLink side of the sharded step (north_star: throughput as a fraction of the HBM / NVLink roofline): ALGORITHMIC bytes a
+        # rank receives per step -- logical row sizes, as for HBM -- against the measured 770 GB/s per direction peer rate
+        n_occ, rho = B * F_FIELDS, (world - 1) / world
+        logical = {"LR": 1, "FM": D + 1, "DeepFM": D + 1}
+        fwd = {m: rho * n_occ * 4 * logical[m] for m in MODELS}                     # remote rows read by the forward gathers
+        rows_rs = 16 if D <= 15 else (D + 1 + 3) // 4 * 4
+        gath = {"LR": (world - 1) * B * 4, "FM": (world - 1) * B * 4 * rows_rs, "DeepFM": (world - 1) * B * 4 * rows_rs}
+        push = rho * n_occ * D * 4                                                   # DeepFM's tower-input gradients, pushed to the owners
+        route = rho * n_occ * 8                                                      # (local row, global slot) pairs written to the owners
+        total = sum(fwd.values()) + sum(gath.values()) + push + route
+        nv_peak = 770.0
+        per_kernel = {}
+        for m in MODELS:
+            k = f"rlctr_embed_fwd[Sharded{m}]"
+            if k in kern and kern[k][1] > 0:
+                gbps = fwd[m] / (kern[k][1] / 1e3) / 1e9
+                per_kernel[k] = {"nvlink_bytes": fwd[m], "mean_ms": kern[k][1], "GBps": gbps, "frac": gbps / nv_peak}
+        if "rlctr_push_rows" in kern and kern["rlctr_push_rows"][1] > 0:
+            gbps = push / (kern["rlctr_push_rows"][1] / 1e3) / 1e9
+            per_kernel["rlctr_push_rows"] = {"nvlink_bytes": push, "mean_ms": kern["rlctr_push_rows"][1], "GBps": gbps, "frac": gbps / nv_peak}
+        if "rlctr_route_ids" in kern and kern["rlctr_route_ids"][1] > 0:
+            gbps = route / (kern["rlctr_route_ids"][1] / 1e3) / 1e9
+            per_kernel["rlctr_route_ids"] = {"nvlink_bytes": route, "mean_ms": kern["rlctr_route_ids"][1], "GBps": gbps, "frac": gbps / nv_peak}
+        step_gbps = total / (step_ms / 1e3) / 1e9
+        roof["nvlink"] = {"bytes_received_per_step_per_gpu": total, "achieved": step_gbps, "peak": nv_peak, "unit": "GB/s",
+                          "frac": step_gbps / nv_peak, "nvlink_frac": step_gbps / nv_peak,
+                          "peak_source": "measured peer copy, 770 GB/s per direction per GPU (B200_PROFILING.md); 900 nominal",
+                          "breakdown_bytes": {"forward_remote_rows": sum(fwd.values()), "all_gather_sums_dlogit": sum(gath.values()),
+                                              "push_tower_input_grads": push, "route_ids": route},
+                          "kernels": per_kernel,
+                          "note": "whole-step figure: the step is not NVLink-bound (the exchanges overlap HBM- and tensor-bound "
+                                  "work on other graph branches); `kernels` are the NVLink-bound launches on their own"}
     if roof is not None:
         roof["share_of_step_by_entry_point"] = shares
         roof["profiled_pass"] = {"steps": Kp, "ms_per_step": ms_prof / Kp, "mode": "eager, CUDA events around every library call"}

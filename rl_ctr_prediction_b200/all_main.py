@@ -34,8 +34,15 @@ def train_step(ddqn_model, ddpg_for_pg_model, model_dict, features, labels, embe
     ddqn_model.store_transition(torch.cat([features, actions, rewards.long()], dim=1))
     ddpg_for_pg_model.store_transition(features, torch.cat([prob_weights_new, rewards], dim=1), actions.float())
     b_s, b_a, b_r, b_s_ = ddqn_model.sample_batch()
+    gather = getattr(ddqn_model, "batch_gather", None)       # data-parallel run (make_gathered_replay): the ranks' samples joined
+    if gather is not None:
+        b_s, b_a, b_r = gather(b_s, b_a, b_r)
+        b_s_ = b_s
     ddqn_model.learn(embedding_layer.forward(b_s), b_a, b_r, embedding_layer.forward(b_s_))
     b_s, b_a, b_r, b_s_, b_pg_a = ddpg_for_pg_model.sample_batch()
+    if gather is not None:
+        b_s, b_a, b_r, b_pg_a = gather(b_s, b_a, b_r, b_pg_a)
+        b_s_ = b_s
     es, es_ = embedding_layer.forward(b_s), embedding_layer.forward(b_s_)
     td_error = ddpg_for_pg_model.learn_c(es, b_a, b_r, es_, b_pg_a)
     a_loss = ddpg_for_pg_model.learn_a(es, b_pg_a)
@@ -170,3 +177,36 @@ def make_data_parallel(ddqn_model, ddpg_for_pg_model, group=None):
     ddqn_model.grad_sync = grad_sync
     ddpg_for_pg_model.grad_sync = grad_sync
     return grad_sync
+
+
+def make_gathered_replay(ddqn_model, ddpg_for_pg_model, group=None):
+    """The cheaper data-parallel form for replay batches of a few hundred transitions: every rank keeps its own replay
+    memory (the transitions of its slice of the batch), draws ``batch_size / G`` of them, the ranks' draws are joined with ONE
+    all_gather per agent, and every rank runs the identical learn step on the joined batch -- the single-process step on the
+    concatenated replay batch, BatchNorm statistics included, with no gradient all-reduce and no per-layer collective
+    (the kernels are deterministic, so the replicas stay bit-identical).  ``make_data_parallel`` is the form for batches too
+    large to replicate."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    for agent in (ddqn_model, ddpg_for_pg_model):
+        if agent.batch_size % world != 0:
+            raise ValueError(f"batch_size {agent.batch_size} is not a multiple of the {world} ranks")
+        agent.batch_size //= world
+    for net in (ddqn_model.eval_net, ddqn_model.target_net, ddpg_for_pg_model.Actor, ddpg_for_pg_model.Critic,
+                ddpg_for_pg_model.Actor_, ddpg_for_pg_model.Critic_):
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+
+    def gather(*tensors):
+        widths = [t.shape[1] for t in tensors]
+        packed = torch.cat([t.double() for t in tensors], dim=1).contiguous()      # ids < 2^53 stay exact
+        out = torch.empty(world * packed.shape[0], packed.shape[1], dtype=torch.float64, device=packed.device)
+        dist.all_gather_into_tensor(out, packed, group=group)
+        res, o = [], 0
+        for t, w in zip(tensors, widths):
+            res.append(out[:, o:o + w].to(t.dtype))
+            o += w
+        return res
+
+    ddqn_model.batch_gather = gather
+    return gather

@@ -142,3 +142,37 @@ def _dp_worker(rank, world, port):
 
 def test_data_parallel_policy_nets_world2():
     mp.spawn(_dp_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _gather_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch.nn as nn
+        from rl_ctr_prediction_b200 import all_main
+
+        class Agent:
+            batch_size = 8
+        a, b = Agent(), Agent()
+        torch.manual_seed(rank)                                              # replicas start different: rank 0's are broadcast
+        net = nn.Linear(3, 2)
+        a.eval_net = a.target_net = b.Actor = b.Critic = b.Actor_ = b.Critic_ = net
+        gather = all_main.make_gathered_replay(a, b)
+        assert a.batch_size == 4 and b.batch_size == 4
+        ref = nn.Linear(3, 2)
+        torch.manual_seed(0)
+        ref = nn.Linear(3, 2)
+        assert torch.equal(net.weight, ref.weight)
+        ids = torch.arange(4 * 5).reshape(4, 5) + 1000 * rank + (1 << 40)    # ids beyond 2^24 survive the packing exactly
+        r = torch.full((4, 1), 0.5 + rank)
+        gi, gr = gather(ids, r)
+        assert gi.dtype == torch.int64 and gi.shape == (8, 5) and gr.shape == (8, 1)
+        want = torch.cat([torch.arange(20).reshape(4, 5) + 1000 * k + (1 << 40) for k in range(world)])
+        assert torch.equal(gi, want) and torch.equal(gr, torch.tensor([[0.5]] * 4 + [[1.5]] * 4))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gathered_replay_world2():
+    mp.spawn(_gather_worker, args=(2, _free_port()), nprocs=2, join=True)
