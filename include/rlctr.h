@@ -395,6 +395,9 @@ int rlctr_auc_logloss(const float* pred, const int64_t* labels_i64, const float*
 #define RLCTR_MLP_DROPOUT 2     /* fwd: y = keep ? y / (1-p) : 0 after bias / ReLU (nn.Dropout in train mode, p_model.py:284) */
 #define RLCTR_MLP_DX_MASK 4     /* bwd: dx *= (x > 0 ? dx_scale : 0): the ReLU (+dropout) backward of the layer that
                                    produced x, fused into this layer's dgrad epilogue */
+#define RLCTR_MLP_FP32 8        /* exact fp32 on the CUDA cores (one FFMA per product, k ascending: the reference's SGEMM arithmetic)
+                                   instead of 3xTF32 on the tensor cores.  For the small-batch learn steps of the BatchNorm policy
+                                   nets, whose backward cancels the dominant part of the gradient (csrc/mlp.cu `simt`) */
 size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
 /* ---- replay memory of the RL agents, sampled on the device ----------------------------------------------------
  * The reference samples on the host: random.sample (DDQN_model.py:183-185) and np.random.choice(n, batch, p=P, replace=False)

@@ -131,6 +131,20 @@ __device__ __forceinline__ void adam_l2_elem(float& p, float& m, float& v, const
     const float denom = fmaf(sqrt_approx(v), inv_bc2_sqrt, h.eps);       // 2 MUFU + 7 FMA-pipe instructions per element-step
     p = fmaf(-step_size * m, rcp_approx(denom), p);
 }
+// The data step of a TABLE row (gradient g from the batch): same formula as adam_elem with the two IEEE divisions and the IEEE
+// square root (~25 instructions each with their fix-up sequences: ncu counted ~770 instructions per lane per row in the update
+// kernel, which made it issue-bound at ~90 M warp instructions per launch) replaced by MUFU.SQRT / MUFU.RCP (1-2 ulp each).
+// The perturbation is ~3e-7 of an update of size ~lr: ~3e-10 per step on parameters of size ~0.1, four orders of magnitude
+// inside the 1e-5 parity bar (tests: final state of every row against torch.optim.Adam).  Dense parameters (bias, tower, policy
+// nets: rlctr_dense_adam*) keep the exact adam_elem.
+__device__ __forceinline__ void adam_elem_fast(float& p, float& m, float& v, float g, const AdamHyper& h, float step_size,
+                                               float inv_bc2_sqrt) {
+    g = fmaf(h.wd, p, g);
+    m = fmaf(h.omb1, g - m, m);
+    v = fmaf(h.omb2 * g, g, v * h.beta2);
+    const float denom = fmaf(sqrt_approx(v), inv_bc2_sqrt, h.eps);
+    p = fmaf(-step_size * m, rcp_approx(denom), p);
+}
 __device__ __forceinline__ void adam_l2_step4(float4& p, float4& m, float4& v, float2 s, const AdamHyper& h) {
     const float ib = rcp_approx(s.y);
     adam_l2_elem(p.x, m.x, v.x, h, s.x, ib);

@@ -584,6 +584,77 @@ static int vec_of(const float* p, int64_t pitch) {
     return 1;
 }
 
+// ---- exact fp32 GEMM on the CUDA cores (RLCTR_MLP_FP32) --------------------------------------------------------------------
+// C[M,N] = sum_k A(m,k) * B(n,k) (+ bias[n]) (ReLU), strides in floats: A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].
+// One FFMA per product, k in ascending order: the reference's fp32 SGEMM arithmetic (error ~1e-7 sqrt(K) of sum |a b|), where
+// the 3xTF32 tensor-core kernels carry ~2e-6 of the output SCALE.  That difference is invisible in a CTR tower but not in the
+// learn steps of the BatchNorm policy nets: BatchNorm's backward subtracts the batch mean of a gradient whose dominant part is
+// one constant (d mean(Q) / dQ), so a 2e-6-of-scale error becomes 5e-4 of what is left (measured against the reference's own
+// modules in float64: tests/test_gpu_parity_scale.py).  Those steps run on replay batches of 32-256 rows -- a few MFLOP, where
+// tensor cores buy nothing -- so small batches take this kernel.  64 x 64 tile, 256 threads, 4 x 4 outputs per thread.
+namespace simt {
+constexpr int TM = 64, TN = 64, TK = 16;
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbn, int64_t sbk,
+             float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int M, int N, int K, int relu) {
+    __shared__ float As[TK][TM + 4], Bs[TK][TN + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += TK) {
+        for (int e = threadIdx.x; e < TK * TM; e += 256) {
+            // the faster-varying index follows the operand's unit stride so that the global loads coalesce
+            const int kk = sak == 1 ? e % TK : e / TM, mm = sak == 1 ? e / TK : e % TM;
+            const int m = m0 + mm, k = k0 + kk;
+            As[kk][mm] = (m < M && k < K) ? __ldg(A + (int64_t)m * sam + (int64_t)k * sak) : 0.f;
+        }
+        for (int e = threadIdx.x; e < TK * TN; e += 256) {
+            const int kk = sbk == 1 ? e % TK : e / TN, nn = sbk == 1 ? e / TK : e % TN;
+            const int n = n0 + nn, k = k0 + kk;
+            Bs[kk][nn] = (n < N && k < K) ? __ldg(B + (int64_t)n * sbn + (int64_t)k * sbk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            C[(int64_t)m * ldc + n] = v;
+        }
+    }
+}
+static int gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int64_t ldc,
+                const float* bias, int M, int N, int K, int relu, cudaStream_t st) {
+    dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+    sgemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+}  // namespace simt
+
 static int launch_gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
                        int64_t ldc, const float* bias, int M, int N, int K, int relu, const GemmPlan& p, cudaStream_t st) {
     GemmArgs g;
@@ -683,6 +754,9 @@ extern "C" int rlctr_linear_fwd(const float* x, int64_t ldx, const float* w, con
         gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
             x, ldx, w, bias, y, batch, in_dim, relu);
         RLCTR_LAUNCH_CHECK();
+    } else if (flags & RLCTR_MLP_FP32) {
+        rc = simt::gemm(x, ldx, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim, relu, st);
+        if (rc) return rc;
     } else {
         const MlpWs l = mlp_ws(batch, in_dim, out_dim);
         float *whi = nullptr, *wlo = nullptr;
@@ -775,7 +849,15 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         }
         return RLCTR_OK;
     }
-    if (dx) {   // dX[B,in] = dY[B,out] * W[out,in]:  B operand = W, contiguous along N
+    const bool fp32 = (flags & RLCTR_MLP_FP32) != 0;
+    if (dx && fp32) {
+        int rc = simt::gemm(dy, out_dim, 1, w, 1, in_dim, dx, in_dim, nullptr, (int)batch, in_dim, out_dim, 0, st);
+        if (rc) return rc;
+        if (dx_mask) {
+            mask_rows_kernel<<<grid_elems(batch * in_dim), 256, 0, st>>>(dx, x, ldx, batch, in_dim, dx_scale);
+            RLCTR_LAUNCH_CHECK();
+        }
+    } else if (dx) {   // dX[B,in] = dY[B,out] * W[out,in]:  B operand = W, contiguous along N
         float *whi = nullptr, *wlo = nullptr;
         int rc = RLCTR_OK;
         bool done = false;
@@ -800,7 +882,10 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         }
     }
     bool db_done = false;
-    if (dw) {   // dW[out,in] = dY^T[out,B] * X[B,in]: both operands contiguous along M / N, K = batch; split-K
+    if (dw && fp32) {   // one pass, k = batch rows in ascending order
+        int rc = simt::gemm(dy, 1, out_dim, x, 1, ldx, dw, in_dim, nullptr, out_dim, in_dim, (int)batch, 0, st);
+        if (rc) return rc;
+    } else if (dw) {   // dW[out,in] = dY^T[out,B] * X[B,in]: both operands contiguous along M / N, K = batch; split-K
         const int64_t mn = (int64_t)out_dim * in_dim;
         int splits = tma::enabled() ? tma::plan_splits(out_dim, in_dim, (int)batch, true) : 0;
         int rc = RLCTR_EUNSUPPORTED;

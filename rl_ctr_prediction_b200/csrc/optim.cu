@@ -194,10 +194,11 @@ __device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t gslo
 
 __device__ __forceinline__ void adam_apply4(float4& p, float4& m, float4& v, const float4& g, float2 s,
                                             const AdamHyper& h) {
-    adam_elem(p.x, m.x, v.x, g.x, h, s.x, s.y);
-    adam_elem(p.y, m.y, v.y, g.y, h, s.x, s.y);
-    adam_elem(p.z, m.z, v.z, g.z, h, s.x, s.y);
-    adam_elem(p.w, m.w, v.w, g.w, h, s.x, s.y);
+    const float ib = rcp_approx(s.y);
+    adam_elem_fast(p.x, m.x, v.x, g.x, h, s.x, ib);
+    adam_elem_fast(p.y, m.y, v.y, g.y, h, s.x, ib);
+    adam_elem_fast(p.z, m.z, v.z, g.z, h, s.x, ib);
+    adam_elem_fast(p.w, m.w, v.w, g.w, h, s.x, ib);
 }
 
 // finish one distinct row: Adam (APPLY==0) or store into the dense gradient (APPLY==1)
@@ -1044,7 +1045,7 @@ rows_scalar_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
         if (a.stamp_col >= 0) t.data[o + a.stamp_col] = __int_as_float(step); else a.stamp[id] = step;
     }
     const float2 sc = __ldg(&a.sched[step]);
-    adam_elem(p, m, v, acc, a.h, sc.x, sc.y);
+    adam_elem_fast(p, m, v, acc, a.h, sc.x, rcp_approx(sc.y));
     t.data[o] = p; a.m[o] = m; a.v[o] = v;
     }
 }

@@ -21,7 +21,18 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+import os
+
 from . import _lib
+
+# Batches of at most this many rows take the exact-fp32 CUDA-core GEMM (RLCTR_MLP_FP32) instead of 3xTF32 on the tensor cores:
+# the learn steps of the policy nets run on replay batches of 32-256 rows, where tensor cores buy nothing and the BatchNorm
+# backward needs the reference's fp32 SGEMM accuracy (csrc/mlp.cu `simt`).  0 disables it.
+FP32_MAX_BATCH = int(os.environ.get("RLCTR_FP32_MAX_BATCH", "1024"))
+
+
+def _fp32_flag(B):
+    return _lib.RLCTR_MLP_FP32 if B <= FP32_MAX_BATCH else 0
 
 
 def _rows_view(x):
@@ -40,7 +51,7 @@ def _fwd(lib, x2, ldx, w, bias, relu, drop_p=0.0, rng=None):
     B, K = x2.shape
     N = w.shape[0]
     y = torch.empty(B, N, dtype=torch.float32, device=x2.device)
-    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DROPOUT if drop_p > 0.0 else 0)
+    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DROPOUT if drop_p > 0.0 else 0) | _fp32_flag(B)
     ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2.device)
     _lib.call("rlctr_linear_fwd", lib.rlctr_linear_fwd, x2.data_ptr(), ldx, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, K, N,
@@ -60,7 +71,7 @@ def _bwd(lib, x2, ldx, w, y, gy2, need_dx, need_dw, need_db, relu, gy_scale=1.0,
     db = torch.empty(N, dtype=torch.float32, device=dev) if need_db else None
     ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DX_MASK if dx_mask else 0)
+    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DX_MASK if dx_mask else 0) | _fp32_flag(B)
     _lib.call("rlctr_linear_bwd", lib.rlctr_linear_bwd, x2.data_ptr(), ldx, _lib.ptr(w), _lib.ptr(y) if relu else None,
               _lib.ptr(gy2), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), B, K, N, flags, float(gy_scale), float(dx_scale),
               _lib.ptr(ws), ws_bytes, _lib.stream(), key=f"rlctr_linear_bwd[{K}x{N}]",

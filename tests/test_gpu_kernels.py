@@ -760,6 +760,36 @@ def test_linear_bwd_3xtf32(lib, B, K, N, relu, path, monkeypatch):
     assert torch.equal(dw, dw2)
 
 
+@pytest.mark.parametrize("B,K,N", [(1, 7, 3), (64, 255, 300), (256, 259, 300), (300, 300, 3), (1000, 150, 300)])
+@pytest.mark.parametrize("relu", [0, 1])
+def test_linear_exact_fp32_path(lib, B, K, N, relu):
+    """RLCTR_MLP_FP32: forward and backward on the CUDA cores, one FFMA per product -- fp32 SGEMM accuracy (1e-6 of the
+    scale against float64, where the 3xTF32 kernels are allowed 1e-5), padded input rows, the masked dgrad and db included."""
+    FP32 = 8
+    x, w, b = linear_case(B, K, N, 21)
+    ld = (K + 3) // 4 * 4 + 4
+    xd = padded(x, ld)
+    y = torch.empty(B, N, device=DEV)
+    wsb = lib.rlctr_mlp_ws_bytes(B, K, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_linear_fwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(dev(b)), L().ptr(y), B, K, N, relu | FP32, 0.0, None,
+                                L().ptr(ws), wsb, st()) == 0
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    if relu:
+        ref = np.maximum(ref, 0)
+    close(y, ref, rtol=1e-6)
+    gy = np.random.default_rng(5).standard_normal((B, N)).astype(np.float32)
+    gyd = dev(gy)
+    dx, dw, db = torch.empty(B, K, device=DEV), torch.empty(N, K, device=DEV), torch.empty(N, device=DEV)
+    yh = y.cpu().numpy()
+    assert lib.rlctr_linear_bwd(L().ptr(xd), ld, L().ptr(dev(w)), L().ptr(y), L().ptr(gyd), L().ptr(dx), L().ptr(dw), L().ptr(db),
+                                B, K, N, relu | FP32 | 4, 1.0, 2.0, L().ptr(ws), wsb, st()) == 0
+    g64 = gy.astype(np.float64) * ((yh > 0) if relu else 1.0)
+    close(dx, (g64 @ w.astype(np.float64)) * np.where(x > 0, 2.0, 0.0), rtol=1e-6)        # RLCTR_MLP_DX_MASK: x is the mask source
+    close(dw, g64.T @ x.astype(np.float64), rtol=1e-6)
+    close(db, g64.sum(axis=0), rtol=1e-5)
+
+
 @pytest.mark.parametrize("path", ["tma", "staged"])
 @pytest.mark.parametrize("B,K,N", [(4096, 152, 300), (1000, 300, 200)])
 def test_linear_fused_dropout_and_masked_dgrad(lib, B, K, N, path, monkeypatch):

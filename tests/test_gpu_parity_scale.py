@@ -213,9 +213,11 @@ def _check_grads(net, golden_grads, prefix):
             continue
         # weight matrices: 1e-5 of their own scale.  1-D parameters (BatchNorm scale / shift, the last bias) are sums over the
         # batch of terms that cancel (d gamma = sum_b dy * xhat is 1e-2 .. 1e-3 of the sum of |terms|): they are read against
-        # the gradient scale of the network, like every other cancelling sum in this suite
+        # the gradient scale of the network, like every other cancelling sum in this suite.  (These learn steps run on the
+        # exact-fp32 GEMM -- batches <= mlp.FP32_MAX_BATCH; on the 3xTF32 tensor-core kernels the same gradients are only good
+        # to ~1e-4 of that scale and the actor's to 5e-4, which is why the small-batch path exists.)
         own = float(np.abs(v).max())
-        atol = 1e-5 * own if v.ndim == 2 else max(1e-5 * own, 1e-4 * gscale)      # (measured: <= 7e-5 of gscale)
+        atol = 1e-5 * (own if v.ndim == 2 else max(own, gscale))
         np.testing.assert_allclose(a, v.astype(np.float64), rtol=1e-5, atol=atol, err_msg=k)
 
 
@@ -257,7 +259,7 @@ def test_ddpg_first_step_gradients_match_reference(golden_grads):
         scale = float(np.abs(v).max()) if v.ndim == 2 else gscale
         mine = np.abs(named[k].grad.detach().cpu().double().numpy() - v).max() / scale
         theirs = np.abs(g32[k].astype(np.float64) - v).max() / scale
-        assert mine <= max(5 * theirs, 1e-5 if v.ndim == 2 else 1e-4), (k, mine, theirs)     # 1-D: see _check_grads
+        assert mine <= max(5 * theirs, 1e-5), (k, mine, theirs)
 
 
 # ------------------------------------------------------------------------------------------------ (v)
