@@ -85,15 +85,17 @@ def tensor_peak():
     return 1400.0 / 2.0, "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {      # profiles/r1e_ncu_top_kernels.md (B=65536, N=10M, D=10); bytes per launch
-    "rlctr_rows_adam[FM]": 246.4e6 + 137.3e6, "rlctr_rows_adam[DeepFM]": 295.7e6 + 137.6e6,
-    "rlctr_rows_catchup[FM]": 238.7e6 + 124.7e6, "rlctr_rows_catchup[DeepFM]": 238.8e6 + 123.7e6,
-    "rlctr_embed_fwd[FM]": 128.6e6 + 5.7e6, "rlctr_embed_fwd[DeepFM]": 130.5e6 + 23.0e6,
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this round
+NCU_TRAFFIC = {      # profiles/r2_ncu_top_kernels.md (B=65536, N=10M, D=10); bytes per launch
+    "rlctr_rows_adam[FM]": 247.7e6 + 139.0e6, "rlctr_rows_adam[DeepFM]": 297.2e6 + 141.5e6,
+    "rlctr_rows_adam[LR]": 95.2e6 + 14.9e6,
+    "rlctr_rows_catchup[FM]": 238.9e6 + 122.4e6, "rlctr_rows_catchup[DeepFM]": 238.9e6 + 122.7e6,
+    "rlctr_rows_catchup[LR]": 91.1e6 + 12.1e6,
+    "rlctr_embed_fwd[FM]": 68.3e6 + 3.7e6, "rlctr_embed_fwd[DeepFM]": 69.8e6 + 8.5e6, "rlctr_embed_fwd[LR]": 96.7e6 + 4.6e6,
     # the tower's calls, summed over their kernels (same capture): forward = 150->300, 300->200 GEMMs (+ the 200->1 GEMV, not captured);
     # backward = gemv_bwd + layer-2 dgrad, wgrad + layer-1 dgrad, wgrad
-    "rlctr_linear_fwd": (40.3e6 + 24.4e6) + (79.2e6 + 22.1e6),
-    "rlctr_linear_bwd": (52.7e6 + 7.1e6) + (131.7e6 + 46.2e6) + (131.2e6 + 6.5e6) + (79.5e6 + 4.8e6) + (118.6e6 + 5.1e6),
+    "rlctr_linear_fwd": (40.3e6 + 23.8e6) + (79.2e6 + 20.3e6),
+    "rlctr_linear_bwd": (52.7e6 + 7.5e6) + (131.7e6 + 45.0e6) + (131.2e6 + 5.1e6) + (79.1e6 + 4.2e6) + (118.7e6 + 4.1e6),
 }
 
 
@@ -448,8 +450,8 @@ def run_c3(ctx):
                         "generate_preds over {LR, FM, FFM} (N=1e7 rows each) -> +-1 reward -> returns -> REINFORCE loss -> Adam "
                         "(lr 1e-4, wd 1e-5), B=65536, one CUDA graph, nothing leaves the device",
             "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "graph_launches_per_step": step.launches_per_step,
-            "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": 3 * tf, "peak": ctx["tpeak"], "unit": "TFLOP/s",
-                         "frac": 3 * tf / ctx["tpeak"], "fp32_equiv_TFLOPs": tf,
+            "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": tf, "peak": ctx["tpeak"], "unit": "TFLOP/s",
+                         "frac": tf / ctx["tpeak"], "tensor_pipe_issued_TFLOPs": 3 * tf, "tensor_pipe_issued_frac": 3 * tf / ctx["tpeak"],
                          "what": "policy MLP GEMMs (3xTF32: 3 tensor-pipe MMAs per fp32 product), 5.7 MFLOP/sample against "
                                  "11.4 KB/sample of HBM gathers: the step is tensor-bound",
                          "hbm": _hbm(hbm_bytes, v, ctx["peak"], "state encoder + LR/FM/FFM scoring gathers + generate_preds")}}
@@ -537,8 +539,9 @@ def run_c5(ctx):
                            "draws joined by one all_gather per agent and the learn step replicated (== the single-process step on the "
                            "joined batch, BatchNorm statistics included; all_main.make_data_parallel is the gradient-all-reduce form)"),
             "value": v, "unit": "samples/s", "ms_per_step": ms, "steps": steps, "n_gpus": world, "scaling": "strong",
-            "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": 3 * tf, "peak": ctx["tpeak"] * world,
-                         "unit": "TFLOP/s", "frac": 3 * tf / (ctx["tpeak"] * world), "fp32_equiv_TFLOPs": tf,
+            "roofline": {"bound": "tensor", "fp32_equiv_flop_per_sample": fl, "achieved": tf, "peak": ctx["tpeak"] * world,
+                         "unit": "TFLOP/s", "frac": tf / (ctx["tpeak"] * world), "tensor_pipe_issued_TFLOPs": 3 * tf,
+                         "tensor_pipe_issued_frac": 3 * tf / (ctx["tpeak"] * world),
                          "what": "acting-path GEMMs of the DDQN and the DDPG actor over the whole batch (eval-mode BatchNorm folded "
                                  "into the layers); the learn steps run on 256-sample replay batches",
                          "hbm": _hbm(hbm_bytes, v / world, ctx["peak"], "state encoder + three scoring gathers + generate_preds + "
@@ -750,14 +753,16 @@ def b200_arm(args):
     if top is not None and top.startswith("rlctr_linear"):
         keys = [k for k in gemm if k.startswith(top)]
         tot_ms = sum(gemm[k]["launches"] * gemm[k]["mean_ms"] for k in keys)
-        tot_fl = sum(3 * gemm_flops(k, m) for k in keys for _, _, m in prof.records[k])
-        achieved = tot_fl / (tot_ms / 1e3) / 1e12
+        tot_fl = sum(gemm_flops(k, m) for k in keys for _, _, m in prof.records[k])
+        achieved = tot_fl / (tot_ms / 1e3) / 1e12           # ALGORITHMIC (fp32-equivalent) FLOP/s: 2*B*K*N per GEMM
         roof = {"bound": "tensor", "kernel": top + " (gemm3x_tma_kernel: all tower layers)", "achieved": achieved, "peak": tpeak,
-                "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": NCU_TRAFFIC.get(top),
+                "unit": "TFLOP/s", "frac": achieved / tpeak, "tensor_pipe_issued_TFLOPs": 3 * achieved,
+                "tensor_pipe_issued_frac": 3 * achieved / tpeak, "traffic": NCU_TRAFFIC.get(top),
                 "traffic_note": "DRAM bytes (ncu dram__bytes_read+write) of ALL kernels of this entry point in one step, B=65536 "
-                                "(profiles/r1e_ncu_top_kernels.md); achieved / peak are FLOP rates over the same kernels",
+                                "(profiles/r2_ncu_top_kernels.md); achieved / peak are FLOP rates over the same kernels",
                 "peak_source": tpeak_src,
-                "flops_counted": "3 tf32 MMAs per fp32 product (3xTF32 split)", "share_of_step": groups[top] / Kp / step_ms}
+                "flops_counted": "algorithmic fp32-equivalent FLOPs; the 3xTF32 split issues 3 tf32 MMAs per product "
+                                 "(tensor_pipe_issued_*)", "share_of_step": groups[top] / Kp / step_ms}
     elif top is not None:
         keys = [k for k in kern if k.split("[")[0] == top]
         key = max(keys, key=lambda k: kern[k][0] * kern[k][1])        # the heaviest launch of the dominant entry point

@@ -165,6 +165,11 @@ __device__ __forceinline__ void adam_replay1(float& p, float& m, float& v, int f
     }
 }
 
+__device__ __forceinline__ float ldg1_once(const float* p) {       // the same for a single float (the LR weight of a 16-byte record)
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 // row-sharded tables: id -> (rank id & mask, local row id >> shift); mask == 0: one local table
 struct ShardView {
     const float* peers[RLCTR_MAX_WORLD];

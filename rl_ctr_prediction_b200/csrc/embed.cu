@@ -129,7 +129,7 @@ embed_fwd_scalar_kernel(const int64_t* __restrict__ ids, const float* __restrict
         float s = 0.f;
         for (int f = lane; f < fields; f += 32) {
             const int64_t id = id_at(ids, b * fields + f);
-            if ((uint64_t)id < (uint64_t)n_rows) s += __ldg(row_ptr(tab, sv, id, pitch));
+            if ((uint64_t)id < (uint64_t)n_rows) s += ldg1_once(row_ptr(tab, sv, id, pitch));
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(RLCTR_FULL, s, off);
