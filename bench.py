@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-fork", action="store_true", help="capture the models of the step one after another (no parallel graph branches)")
+    ap.add_argument("--no-colocate", action="store_true", help="single GPU: keep LR / FM / DeepFM in three separate tables instead "
+                    "of one co-located record per id (rl_ctr_prediction_b200/colocated.py)")
     ap.add_argument("--profile-steps", type=int, default=10, help="steps of the eager per-kernel timing pass")
     ap.add_argument("--configs", default="C1,C3,C4,C5", help="other BASELINE.json configurations to time after the headline")
     ap.add_argument("--no-configs", action="store_true")
@@ -130,6 +132,13 @@ def alg_bytes(key, m):
     n = B * F
     per = N / F
     U = F * per * (1.0 - (1.0 - 1.0 / per) ** B)
+    if name in ("rlctr_group_fwd", "rlctr_group_rows_adam"):   # co-located record: `logical` = the members' parameters of one id
+        M = len(m["members"])
+        tower = sum(d for nm, d in m["members"] if nm in ("DeepFM", "WideAndDeep"))
+        if name == "rlctr_group_fwd":
+            train = key.endswith("[train]")
+            return float(B * (F * 8 + F * 4 * logical + 4 * M) + (B * 4 * logical if train else 0) + n * tower * 4)
+        return float(U * (24 * logical + 8) + n * 8 + B * 4 * M + B * 4 * logical + n * tower * 4)
     if name == "rlctr_rows_lookup":                            # owner-side lookup: record read once, stage + gathered written
         return float(U * (24 * logical + 4) + n * (8 + 4 * logical))
     if name == "rlctr_embed_fwd":
@@ -317,7 +326,7 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(B, N, D, world=1):
+def workload_config(B, N, D, world=1, colocated=False):
     return {"workload": "C2: LR+FM+DeepFM train step (fwd, BCE, bwd, Adam lr=1e-3 wd=1e-5, reference dense-Adam "
                         "numerics) on one batch" + ("" if world == 1 else f"; tables row-sharded over {world} GPUs "
                         "(id mod G) in peer-mapped symmetric memory: forward gathers read remote shards over NVLink, owners "
@@ -325,7 +334,10 @@ def workload_config(B, N, D, world=1):
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "single GPU" if world == 1 else f"dp{world} x row-sharded tables",
             "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
             "ids": "uniform over disjoint per-field ranges", "l2": "inputs larger than L2: 3 tables x 3 arrays x "
-            f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step"}
+            f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step",
+            "layout": ("co-located records: the three models' parameters + Adam moments of one id in one 384-byte record "
+                       "(3 x 128-byte lines), one gather / catch-up / update per step for all three"
+                       if colocated else "one fused-row table per model")}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -612,7 +624,22 @@ def b200_arm(args):
     torch.manual_seed(1 + rank)
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
 
-    def build_models():
+    colocate = world == 1 and not args.no_colocate
+
+    def build_models(colocated=None):
+        if colocate if colocated is None else colocated:
+            # one record per id for the three models (colocated.py): one gather, one catch-up, one update per step
+            from rl_ctr_prediction_b200 import colocated as _co
+            members = [p_model.LR(N, device=dev), p_model.FM(N, D, device=dev), p_model.DeepFM(N, F_FIELDS, D, device=dev)]
+            with torch.no_grad():
+                for m in members:
+                    m.table.mul_(0.1)
+                    m.train()
+            group = _co.colocate(members)
+            del members
+            torch.cuda.empty_cache()
+            group.train()
+            return [(group, optim.Adam(group.parameters(), lr=1e-3, weight_decay=1e-5, mode="lazy"))]
         ms = []
         for name in MODELS:
             if world > 1:      # BASELINE.json configs[3]: tables row-sharded over the GPUs (peer-mapped shards over NVLink)
@@ -877,7 +904,13 @@ def b200_arm(args):
                    "api": "graphs.GraphedTrainStep: step.prefetch(pinned host features, labels); losses = step(handle); "
                           "every step's losses copied to pinned host memory and read there one step later"}
             del gs
-            ms = build_models()
+            ms = None
+            torch.cuda.empty_cache()
+            ms = build_models(colocated=False)             # the reference's per-model loop body: three stand-alone models
+        elif colocate:
+            ms = None
+            torch.cuda.empty_cache()
+            ms = build_models(colocated=False)
         for i in range(W):
             e2e_step_eager(*host[i])
         ms_eager = timed(lambda: [e2e_step_eager(*host[W + i]) for i in range(K)])
@@ -925,7 +958,7 @@ def b200_arm(args):
     if rank == 0:
         line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world, colocate),
                 "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
                 "cuda_graph": bool(use_graph), "graph_branches": bool(use_graph and not args.no_fork),
                 "steady_state": steady, "configs": configs, "gpu_eager_baseline": eager_gpu}

@@ -303,6 +303,48 @@ int rlctr_sort_routed(const uint32_t* keys, const uint32_t* vals, int64_t n_in, 
 int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                     const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
                     void* ws, size_t ws_bytes, rlctr_stream_t stream);
+/* ------------------------------------------------------------------------------------
+ * Co-located records: several models trained on the SAME id stream (the reference trains LR, FM, DeepFM ... one after the
+ * other on the same encoded batches, src/main/pretrain_main.py:25-45,96-103; the RL ensemble scores M of them per sample,
+ * src/all_main/main.py:183-271) keep the parameters of one id in ONE record:
+ *     [ p: member columns .. | stamp ]  [ exp_avg ]  [ exp_avg_sq ]      three blocks, `block` floats apart
+ * A random HBM access costs the same whether it returns 4 or 128 bytes (profiles/r2_rowprobe.md), so the gather of LR + FM +
+ * DeepFM (4 + 44 + 44 bytes) is ONE 128-byte line instead of three, and the optimizer touches three lines per id instead of
+ * seven.  The joint table is an ordinary rlctr_table (row_stride = active floats rounded to 4, <= 32; lin_col = -1, emb_col = 0,
+ * dim = used columns; rlctr_adam.exp_avg / exp_avg_sq = data + block / + 2*block, stamp_col = the first unused column), so
+ * rlctr_rows_catchup / rlctr_adam_flush serve it unchanged; the two calls below are its forward and its update.
+ * A member is one model's view of the record: the columns it owns, where its outputs go, where its gradient side comes from.
+ * Members with an FM term keep the chunk alignment of their stand-alone row (emb_col % 4 as in the stand-alone table): their
+ * logits and updates are then bit-identical to the stand-alone kernels'.
+ * ------------------------------------------------------------------------------------ */
+#define RLCTR_GROUP_MAX 4
+typedef struct rlctr_member {
+    int32_t      lin_col;      /* column of the first-order weight in the joint row, -1 = none */
+    int32_t      emb_col;      /* first latent column */
+    int32_t      dim;          /* latent dims, 0 = none (LR) */
+    int32_t      flags;        /* RLCTR_FM_TERM */
+    const float* bias;         /* device scalar or NULL */
+    /* forward outputs (rlctr_group_fwd), each optional */
+    float*       logit;        /* [B] */
+    float*       pctr;         /* [B * pctr_stride] */
+    int64_t      pctr_stride;
+    float*       rows_out;     /* [B, rows_pitch]: rows_out[b, f*dim + d] = v_f[d] (tower input) */
+    int64_t      rows_pitch;   /* 0 = fields*dim */
+    /* gradient side (rlctr_group_rows_adam) */
+    const float* dlogit;       /* [B] dL/dlogit of this member */
+    const float* extra;        /* [B, fields*dim] dense-tail gradient on the latent columns, or NULL */
+} rlctr_member;
+/* One gather per (sample, field) for every member: logit / pctr / rows_out per member as rlctr_embed_fwd would produce them
+ * from the member's stand-alone table; sums[b, :] = column sums of the joint rows ([B, row_stride], optional: the backward's S). */
+int rlctr_group_fwd(const int64_t* ids, const rlctr_table* table, const rlctr_member* members, int32_t n_members,
+                    float* sums, int64_t batch, int32_t fields, rlctr_stream_t stream);
+/* rlctr_rows_adam over the joint record: per column the gradient of the member that owns it
+ * (first-order: dlogit_m[b]; latent: dlogit_m[b] * (sums[b, col] - row[col]) if RLCTR_FM_TERM, + extra_m[b, f*dim + d]),
+ * reduced over the occurrences of an id in slot order, then ONE Adam step on the record.  ws: rlctr_rows_ws_bytes(n). */
+int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
+                          const rlctr_adam* opt, const rlctr_member* members, int32_t n_members, const float* sums,
+                          int32_t fields, void* ws, size_t ws_bytes, rlctr_stream_t stream);
+
 /* Same reduction, but the sums are stored into a dense [n_rows,row_stride] gradient
  * (rows of untouched ids are not written): the literal embedding_dense_backward. */
 int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,

@@ -57,8 +57,18 @@ class RowGrad(C.Structure):
                 ("peer_dlogit", C.c_void_p * 8), ("peer_sums", C.c_void_p * 8), ("peer_extra", C.c_void_p * 8)]
 
 
+class Member(C.Structure):
+    """struct rlctr_member: one model's view of a co-located record"""
+    _fields_ = [("lin_col", C.c_int32), ("emb_col", C.c_int32), ("dim", C.c_int32), ("flags", C.c_int32),
+                ("bias", C.c_void_p), ("logit", C.c_void_p), ("pctr", C.c_void_p), ("pctr_stride", C.c_int64),
+                ("rows_out", C.c_void_p), ("rows_pitch", C.c_int64), ("dlogit", C.c_void_p), ("extra", C.c_void_p)]
+
+
+RLCTR_GROUP_MAX = 4
+
 _P, _I64, _I32, _SZ, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
 _TP, _AP, _GP, _LP = C.POINTER(Table), C.POINTER(Adam), C.POINTER(RowGrad), C.POINTER(Lookup)
+_MP = C.POINTER(Member)
 
 # name -> (restype, argtypes); must list every symbol include/rlctr.h declares
 SIGNATURES = {
@@ -98,6 +108,8 @@ SIGNATURES = {
     "rlctr_sort_routed": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "rlctr_rows_ws_bytes": (_SZ, [_I64]),
     "rlctr_rows_adam": (C.c_int, [_P, _P, _I64, _GP, _TP, _AP, _P, _SZ, _P]),
+    "rlctr_group_fwd": (C.c_int, [_P, _TP, _MP, _I32, _P, _I64, _I32, _P]),
+    "rlctr_group_rows_adam": (C.c_int, [_P, _P, _I64, _TP, _AP, _MP, _I32, _P, _I32, _P, _SZ, _P]),
     "rlctr_rows_grad_dense": (C.c_int, [_P, _P, _I64, _GP, _TP, _P, _P, _SZ, _P]),
     "rlctr_lookup_stage_floats": (_I64, [_TP]),
     "rlctr_rows_lookup": (C.c_int, [_P, _P, _I64, _TP, _AP, _LP, _P, _SZ, _P]),

@@ -61,7 +61,17 @@ __device__ __forceinline__ int load_stamp(const TableView& t, const AdamView& a,
 __device__ __forceinline__ void embed_stamp(float4& p, int col0, const AdamView& a, int value) {
     if (a.stamp_col >= 0 && (a.stamp_col & ~3) == col0) f4set(p, a.stamp_col & 3, __int_as_float(value));
 }
+// co-located record (rlctr_group_rows_adam): which member model owns a column of the joint row and what its gradient is made of
+struct GroupCols {
+    int n;                                   // 0: an ordinary single-model table
+    const float* dz[RLCTR_GROUP_MAX];        // dL/dlogit of member m, [B]
+    const float* extra[RLCTR_GROUP_MAX];     // dense-tail gradient on member m's latent columns, [B, fields * dim_m], or NULL
+    int emb_col[RLCTR_GROUP_MAX], dim[RLCTR_GROUP_MAX];
+    signed char member[32];                  // column -> member, -1: padding / stamp
+    signed char role[32];                    // 0 none, 1 first-order weight, 2 latent column with the FM term, 3 latent column without
+};
 struct GradView {
+    GroupCols grp;
     const float* staged;
     const float* dlogit;
     const float* sums;
@@ -176,16 +186,62 @@ __device__ __forceinline__ float4 rowgrad_combine(const GradView& g, const GradR
         for (int k = 0; k < 4; ++k) {
             const int col = col0 + k;
             float add = 0.f;
+            // explicit roundings (no FMA contraction): rowgrad_group below must give the same bits for the same member
             if (col == t.lin_col) {
                 add = w.dz;
             } else if (col >= t.emb_col && col < t.emb_col + t.dim) {
-                if (w.fm) add = w.dz * (f4get(w.S, k) - f4get(p, k));
-                if (w.has_ex) add += w.ex[k];
+                if (w.fm) add = __fmul_rn(w.dz, f4get(w.S, k) - f4get(p, k));
+                if (w.has_ex) add = __fadd_rn(add, w.ex[k]);
             }
-            f4set(r, k, f4get(r, k) + add);
+            f4set(r, k, __fadd_rn(f4get(r, k), add));
         }
     }
     return r;
+}
+// Co-located record: the four columns of a lane may belong to different member models.  (member, role) of each column are
+// looked up once per thread; per occurrence the lane reads S (one float4 of the joint column sums, coalesced with the other
+// chunks of the row), the dL/dlogit of the members it holds columns of, and the dense-tail terms.
+struct GroupLane {
+    int mem[4], role[4];
+};
+__device__ __forceinline__ GroupLane group_lane(const GradView& g, int col0) {
+    GroupLane gl;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int col = col0 + k;
+        gl.mem[k] = col < 32 ? (int)g.grp.member[col] : -1;
+        gl.role[k] = col < 32 ? (int)g.grp.role[col] : 0;
+    }
+    return gl;
+}
+__device__ __forceinline__ float4 rowgrad_group(const GradView& g, const GroupLane& gl, uint32_t slot, int col0, const float4& p,
+                                                const TableView& t) {
+    const uint32_t b = slot / (uint32_t)g.fields;
+    const uint32_t f = slot - b * (uint32_t)g.fields;
+    const float4 S = ldg4(g.sums + (int64_t)b * t.rs + col0);
+    float4 r = f4zero();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int m = gl.mem[k];
+        if (m < 0) continue;
+        const float dz = __ldg(g.grp.dz[m] + b);
+        float add = 0.f;
+        if (gl.role[k] == 1) {
+            add = dz;
+        } else {
+            if (gl.role[k] == 2) add = __fmul_rn(dz, f4get(S, k) - f4get(p, k));
+            const float* ex = g.grp.extra[m];
+            if (ex) add = __fadd_rn(add, __ldg(ex + ((int64_t)b * g.fields + f) * g.grp.dim[m] + (col0 + k - g.grp.emb_col[m])));
+        }
+        f4set(r, k, __fadd_rn(0.f, add));
+    }
+    return r;
+}
+template <bool GROUP>
+__device__ __forceinline__ float4 rowgrad_any(const GradView& g, const GroupLane& gl, uint32_t slot, int col0, const float4& p,
+                                              const TableView& t) {
+    if (GROUP) return rowgrad_group(g, gl, slot, col0, p, t);
+    return rowgrad_combine(g, rowgrad_load(g, slot, col0, t), col0, p, t);
 }
 __device__ __forceinline__ float4 rowgrad_chunk(const GradView& g, uint32_t gslot, int col0, const float4& p,
                                                 const TableView& t) {
@@ -221,11 +277,13 @@ __device__ __forceinline__ void finish_row(int64_t id, int col0, float4 p, const
 }
 
 // one lane-group (LPR lanes, a float4 chunk each) per sorted position; only run heads work
-template <int LPR, int APPLY>
+template <int LPR, int APPLY, bool GROUP = false>
 __global__ void __launch_bounds__(256, 5)
 rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
-                  GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
+                  const __grid_constant__ GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
                   int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    GroupLane gl{};
+    if (GROUP) gl = group_lane(g, 4 * (int)(threadIdx.x % LPR));
     // Blocks stride the positions (the launch caps the grid at ~1/world of them for a sharded table: 7 of 8 blocks of a full
     // grid would start in the sentinel tail and exit, and launching 100K empty blocks costs more than the update itself).
     const int64_t nblk = (n * LPR + blockDim.x - 1) / blockDim.x;
@@ -270,14 +328,14 @@ rows_short_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __res
             p = ld4(t.data + off);                       // issued with m, v: one contiguous record when pitch = 3*rs
             if (APPLY == 0) { m0 = ld4(a.m + off); v0 = ld4(a.v + off); }
         }
-        float4 acc = rowgrad_chunk(g, slot0, col0, p, t);
+        float4 acc = rowgrad_any<GROUP>(g, gl, slot0, col0, p, t);
         int64_t kk = k + 1;
         uint32_t nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
         while (nxt == id) {                              // further occurrences of the same row, in slot order
             const uint32_t slot = __ldg(sorted_slots + kk);
             ++kk;
             nxt = (kk < n) ? __ldg(sorted_ids + kk) : 0xffffffffu;
-            acc = f4add(acc, rowgrad_chunk(g, slot, col0, p, t));
+            acc = f4add(acc, rowgrad_any<GROUP>(g, gl, slot, col0, p, t));
         }
         if (APPLY == 0 && a.stamp_col >= 0 && !staged) __syncwarp(__activemask());   // every chunk lane has read the in-record stamp
         finish_row<APPLY>(id, col0, p, acc, t, a, dense_grad, step, stamp_in, &m0, &v0);
@@ -496,13 +554,15 @@ rows_staged_tile_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t*
 }
 
 // block per long run: NSUB lane-groups stride the run, fixed-shape tree in shared memory
-template <int LPR, int APPLY>
-__global__ void __launch_bounds__(256)
+template <int LPR, int APPLY, bool GROUP = false, int NT = 256>
+__global__ void __launch_bounds__(NT)
 rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
-                 GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
+                 const __grid_constant__ GradView g, TableView t, AdamView a, float* __restrict__ dense_grad,
                  const int32_t* __restrict__ long_count, const uint32_t* __restrict__ long_list) {
-    constexpr int NSUB = 256 / LPR;
-    __shared__ float4 red[256];
+    constexpr int NSUB = NT / LPR;                       // a co-located record (LPR = 8) runs 512 threads: the 64 sub-groups -- and so
+    GroupLane gl{};                                      // the partial sums and their tree -- of a stand-alone 16-float row (LPR = 4)
+    if (GROUP) gl = group_lane(g, 4 * (int)(threadIdx.x % LPR));
+    __shared__ float4 red[NT];
     __shared__ int64_t s_end;
     const int sub = threadIdx.x / LPR, c = threadIdx.x % LPR, col0 = 4 * c;
     const bool chunk_on = col0 < t.rs;
@@ -527,7 +587,7 @@ rows_long_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __rest
         if (chunk_on) {
             p = (staged && col0 < a.stage_pitch / 3) ? ldg4(sp) : ld4(t.data + (int64_t)id * t.pitch + col0);
             for (int64_t kk = k + sub; kk < end; kk += NSUB)
-                acc = f4add(acc, rowgrad_chunk(g, __ldg(sorted_slots + kk), col0, p, t));
+                acc = f4add(acc, rowgrad_any<GROUP>(g, gl, __ldg(sorted_slots + kk), col0, p, t));
             if (APPLY == 0 && sub == 0) {
                 step = __ldg(a.step) + 1;
                 if (is_lazy(a) && !staged) stamp_in = load_stamp(t, a, id);
@@ -699,59 +759,86 @@ __device__ __forceinline__ int64_t replay_row_of(int64_t k, int64_t n_items, int
     return prev != id ? (int64_t)id : -1;
 }
 // issue the loads of a whole record WITHOUT looking at its stamp first: one DRAM round trip instead of two, and
-// nothing in the caller depends on the data until the item becomes current (a full replay of another row later)
+// nothing in the caller depends on the data until the item becomes current (a full replay of another row later).
+// LPRR lanes share a row (co-located records of 5..8 chunks): lane slice h owns chunks h*CH .. h*CH+CH-1, `live` of them active.
 template <int CH>
-__device__ __forceinline__ void replay_row_issue(ReplayRow<CH>& it, int64_t row, const TableView& t, const AdamView& a) {
-    it.off = row < 0 ? row : row * t.pitch;
+__device__ __forceinline__ void replay_row_issue(ReplayRow<CH>& it, int64_t row, const TableView& t, const AdamView& a, int first_col,
+                                                 int live) {
+    it.off = row < 0 ? row : row * t.pitch + first_col;
     if (row >= 0) {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-            it.p[c] = ld4(t.data + it.off + 4 * c);
-            it.m[c] = ld4(a.m + it.off + 4 * c);
-            it.v[c] = ld4(a.v + it.off + 4 * c);
+            if (c < live) {
+                it.p[c] = ld4(t.data + it.off + 4 * c);
+                it.m[c] = ld4(a.m + it.off + 4 * c);
+                it.v[c] = ld4(a.v + it.off + 4 * c);
+            } else {
+                it.p[c] = f4zero(); it.m[c] = f4zero(); it.v[c] = f4zero();
+            }
         }
     }
 }
 // the item becomes current: read the in-record stamp out of the data that has landed; up-to-date rows are dropped
-template <int CH>
-__device__ __forceinline__ void replay_row_arm(ReplayRow<CH>& it, const AdamView& a, int upto) {
+template <int CH, int LPRR>
+__device__ __forceinline__ void replay_row_arm(ReplayRow<CH>& it, const AdamView& a, int upto, int h) {
     it.t = upto;
-    if (it.off < 0) return;
-    // the in-record stamp sits in the first padding column (= `used`, tables.Geometry.stamp_col), i.e. always in the
-    // LAST active chunk: a compile-time register, only the element inside it is a run-time select
-    const int st = __float_as_int(f4get(it.p[CH - 1], a.stamp_col & 3));
+    if (it.off < 0) return;                              // the same for every lane of a row
+    int st;
+    if (LPRR == 1) {
+        // the in-record stamp sits in the first padding column (= `used`, tables.Geometry.stamp_col), i.e. always in the
+        // LAST active chunk: a compile-time register, only the element inside it is a run-time select
+        st = __float_as_int(f4get(it.p[CH - 1], a.stamp_col & 3));
+    } else {
+        // the lane whose slice holds the stamp's chunk hands it to the row's other lanes (they took the same path here: the
+        // lanes of a row always have the same staleness, so they switch rows in the same iteration)
+        const int sc = a.stamp_col >> 2, hs = sc / CH, lc = sc - hs * CH;
+        float4 pc = it.p[0];
+#pragma unroll
+        for (int c = 1; c < CH; ++c)
+            if (lc == c) pc = it.p[c];
+        const int lane = threadIdx.x & 31;
+        const unsigned mask = ((1u << LPRR) - 1u) << (lane & ~(LPRR - 1));
+        st = __shfl_sync(mask, __float_as_int(f4get(pc, a.stamp_col & 3)), (lane & ~(LPRR - 1)) + hs);
+    }
     if (st >= upto) it.off = -1; else it.t = st;
 }
-template <int CH, bool CATCHUP>
+template <int CH, int LPRR, bool CATCHUP>
 __global__ void __launch_bounds__(128, 3)
 replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) / LPRR;  // rows between two items of one lane
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = (int)(gt % LPRR);
+    const int first_col = 4 * CH * h;
+    int live = CH;
+    if (LPRR > 1) { live = ((t.used + 3) >> 2) - CH * h; live = live > CH ? CH : live; }
     const int upto = __ldg(a.step);
-    int64_t kc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // index of the current item
+    int64_t kc = gt / LPRR;                                           // index of the current item
     if (kc >= n_items) return;
     ReplayRow<CH> cur, nxt;
-    replay_row_issue<CH>(cur, replay_row_of<CATCHUP>(kc, n_items, r0, sorted_ids, t.n_rows), t, a);
-    replay_row_issue<CH>(nxt, replay_row_of<CATCHUP>(kc + stride, n_items, r0, sorted_ids, t.n_rows), t, a);
+    replay_row_issue<CH>(cur, replay_row_of<CATCHUP>(kc, n_items, r0, sorted_ids, t.n_rows), t, a, first_col, live);
+    replay_row_issue<CH>(nxt, replay_row_of<CATCHUP>(kc + stride, n_items, r0, sorted_ids, t.n_rows), t, a, first_col, live);
     int64_t row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
     if (cur.off == -2) return;
-    replay_row_arm<CH>(cur, a, upto);
+    replay_row_arm<CH, LPRR>(cur, a, upto, h);
     while (true) {
         if (cur.t >= upto) {                             // current item finished (or had nothing to do): switch
             if (cur.off >= 0) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    embed_stamp(cur.p[c], 4 * c, a, upto);
-                    st4(t.data + cur.off + 4 * c, cur.p[c]);
-                    st4(a.m + cur.off + 4 * c, cur.m[c]);
-                    st4(a.v + cur.off + 4 * c, cur.v[c]);
+                    if (c < live) {
+                        embed_stamp(cur.p[c], first_col + 4 * c, a, upto);
+                        st4(t.data + cur.off + 4 * c, cur.p[c]);
+                        st4(a.m + cur.off + 4 * c, cur.m[c]);
+                        st4(a.v + cur.off + 4 * c, cur.v[c]);
+                    }
                 }
             }
             kc += stride;
             if (kc >= n_items || nxt.off == -2) break;   // end of the queue, or of the ids this table owns
             cur = nxt;                                   // its loads were issued one whole item ago
-            replay_row_issue<CH>(nxt, row2, t, a);       // row2's id was fetched one item ago: no dependent wait here
+            replay_row_issue<CH>(nxt, row2, t, a, first_col, live);   // row2's id was fetched one item ago: no dependent wait here
             row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
-            replay_row_arm<CH>(cur, a, upto);
+            replay_row_arm<CH, LPRR>(cur, a, upto, h);
             continue;
         }
         ++cur.t;
@@ -764,13 +851,17 @@ template <bool CATCHUP>
 static int launch_replay_rows(const TableView& t, const AdamView& a, int64_t r0, int64_t n_items,
                               const uint32_t* sorted_ids, cudaStream_t st) {
     const int ch = (t.used + 3) >> 2;
-    int64_t blocks = (n_items + 127) / 128;
+    const int lprr = ch > 4 ? 2 : 1;                     // co-located records (5..8 chunks): two lanes per row
+    if (a.stamp_col >> 2 != ch - 1) return RLCTR_EUNSUPPORTED;        // the stamp rides in the last active chunk
+    int64_t blocks = (n_items * lprr + 127) / 128;
     const int grid = (int)(blocks < RLCTR_SMS * 8 ? (blocks < 1 ? 1 : blocks) : RLCTR_SMS * 8);
     switch (ch) {
-        case 1: replay_rows_kernel<1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
-        case 2: replay_rows_kernel<2, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
-        case 3: replay_rows_kernel<3, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
-        case 4: replay_rows_kernel<4, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 1: replay_rows_kernel<1, 1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 2: replay_rows_kernel<2, 1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 3: replay_rows_kernel<3, 1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 4: replay_rows_kernel<4, 1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 5: case 6: replay_rows_kernel<3, 2, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
+        case 7: case 8: replay_rows_kernel<4, 2, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
         default: return RLCTR_EUNSUPPORTED;
     }
     RLCTR_LAUNCH_CHECK();
@@ -1299,6 +1390,57 @@ extern "C" int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorte
                                const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt, void* ws,
                                size_t ws_bytes, rlctr_stream_t stream) {
     return launch_rows<0>(sorted_ids, sorted_slots, n, grad, table, opt, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
+                                     const rlctr_adam* opt, const rlctr_member* members, int32_t n_members, const float* sums,
+                                     int32_t fields, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
+    if (!sorted_ids || !sorted_slots || !table || !table->data || !opt || !opt->exp_avg || !opt->exp_avg_sq || !opt->sched ||
+        !opt->step || !members || !sums || n < 0 || fields <= 0)
+        return RLCTR_EINVAL;
+    if (n_members < 1 || n_members > RLCTR_GROUP_MAX) return RLCTR_EINVAL;
+    if (table->world > 1 || opt->stage) return RLCTR_EUNSUPPORTED;
+    if (n == 0) return RLCTR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableView t = view_of(table);
+    AdamView a = view_of(opt, t);
+    if (t.rs % 4 != 0 || t.rs <= 8 || t.rs > 32) return RLCTR_EUNSUPPORTED;
+    if (opt->stamp_col >= t.pitch) return RLCTR_EINVAL;
+    if (!rlctr_aligned16(sums)) return RLCTR_EALIGN;
+    GradView g{};
+    g.sums = sums; g.fields = fields; g.world = 0;
+    g.grp.n = n_members;
+    for (int col = 0; col < 32; ++col) { g.grp.member[col] = -1; g.grp.role[col] = 0; }
+    for (int m = 0; m < n_members; ++m) {
+        const rlctr_member& mm = members[m];
+        if (!mm.dlogit || mm.dim < 0 || mm.emb_col < 0 || mm.emb_col + mm.dim > t.rs || mm.lin_col >= t.rs) return RLCTR_EINVAL;
+        g.grp.dz[m] = mm.dlogit; g.grp.extra[m] = mm.extra; g.grp.emb_col[m] = mm.emb_col; g.grp.dim[m] = mm.dim;
+        if (mm.lin_col >= 0) {
+            if (g.grp.member[mm.lin_col] >= 0) return RLCTR_EINVAL;              // two members claim one column
+            g.grp.member[mm.lin_col] = (signed char)m; g.grp.role[mm.lin_col] = 1;
+        }
+        for (int d = 0; d < mm.dim; ++d) {
+            const int col = mm.emb_col + d;
+            if (g.grp.member[col] >= 0) return RLCTR_EINVAL;
+            g.grp.member[col] = (signed char)m; g.grp.role[col] = (mm.flags & RLCTR_FM_TERM) ? 2 : 3;
+        }
+    }
+    if (opt->stamp_col >= 0 && opt->stamp_col < 32 && g.grp.member[opt->stamp_col] >= 0) return RLCTR_EINVAL;
+    if (ws_bytes < rows_ws_bytes(n) || !ws) return RLCTR_EWORKSPACE;
+    RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
+    RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
+    const int lpr = rlctr_lanes_per_row(t.rs);
+    const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
+    if (lpr == 4) {
+        rows_short_kernel<4, 0, true><<<blocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);
+        rows_long_kernel<4, 0, true><<<RLCTR_SMS, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);
+    } else {
+        rows_short_kernel<8, 0, true><<<blocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);
+        rows_long_kernel<8, 0, true, 512><<<RLCTR_SMS, 512, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);
+    }
+    RLCTR_COUNT_LAUNCH(1);                              // two kernels, one check
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
 }
 
 extern "C" int rlctr_rows_grad_dense(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,

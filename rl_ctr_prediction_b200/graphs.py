@@ -257,12 +257,13 @@ class GraphedTrainStep:
         """Start the device -> host copy of a step's losses into a pinned buffer and return ``fetch``: calling it waits
         for THAT copy only and returns the list of floats.  Fetch step i-1 after launching step i and the host never
         stalls the GPU (the reference's loop stalls it once per batch with ``train_loss.item()``)."""
-        if getattr(self, "_host_losses", None) is None or self._host_losses[0].numel() != len(losses):
-            self._host_losses = [torch.empty(len(losses), dtype=torch.float32).pin_memory() for _ in range(3)]
+        flat = torch.cat([l.reshape(-1) for l in losses])   # a co-located group returns one loss per member
+        if getattr(self, "_host_losses", None) is None or self._host_losses[0].numel() != flat.numel():
+            self._host_losses = [torch.empty(flat.numel(), dtype=torch.float32).pin_memory() for _ in range(3)]
             self._host_slot = 0
         buf = self._host_losses[self._host_slot]
         self._host_slot = (self._host_slot + 1) % 3
-        buf.copy_(torch.stack([l.reshape(()) for l in losses]), non_blocking=True)
+        buf.copy_(flat, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
 

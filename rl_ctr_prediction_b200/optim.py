@@ -103,6 +103,16 @@ class Adam:
             if stash is None:
                 continue                      # torch skips a parameter whose .grad is None: no step, no L2 decay, no counter
             opt.sched.ensure(opt.host_step + 2)
+            if hasattr(owner, "_group_update"):  # co-located record (colocated.ColocatedCTR): one update for every member
+                owner._group_update(stash, opt, st)
+                _lib.check(lib.rlctr_step_advance(_lib.ptr(opt.step), 1, st), "rlctr_step_advance")
+                opt.host_step += 1
+                self._last_tables.append(owner)
+                if opt.lazy:
+                    opt.dirty = True
+                    if self.mode == "dense":
+                        opt.flush(owner.table.data)
+                continue
             data = owner.table.data
             t, a = table_struct(data, owner._geom), opt.struct(getattr(stash, "stage", None))
             g = _lib.RowGrad(_lib.ptr(stash.staged), _lib.ptr(stash.dlogit), _lib.ptr(stash.sums),

@@ -225,7 +225,8 @@ class _TableModel(nn.Module):
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
-        self.table._rlctr_owner = self          # .to(device) may have replaced the Parameter object
+        # .to(device) may have replaced the Parameter object; a member of a co-located group shares the group's table
+        self.table._rlctr_owner = self.__dict__.get("_group") or self
         self._ws = {}
         return out
 
@@ -266,6 +267,9 @@ class _TableModel(nn.Module):
 
     def flush(self):
         """Make the table equal to what the reference's dense Adam would hold right now."""
+        grp = self.__dict__.get("_group")
+        if grp is not None:
+            return grp.flush()                  # member of a co-located group: the group owns the table and its Adam state
         if self._opt is not None:
             self._opt.flush(self.table.data)
 
@@ -321,6 +325,12 @@ class _TableModel(nn.Module):
         track = torch.is_grad_enabled() and self.table.requires_grad
         sorted_pair = None
         lookup = None
+        if self.__dict__.get("_group") is not None:
+            # member of a co-located group (colocated.py): inference only -- the group's train_step trains all members at once
+            if track and self.training:
+                raise _lib.RlctrError("this model is a member of a co-located group: train it with group.train_step(x, y, opt); "
+                                      "call the member itself under torch.no_grad() / model.eval()")
+            track = False
         if track:
             sorted_pair = sort_ids(x, self._geom.n_rows)
             opt = self._opt
@@ -354,7 +364,7 @@ class LR(_TableModel):
         self.bias = nn.Parameter(torch.zeros((output_dim,), device=device))
 
     def _ref_items(self):
-        return [("linear.weight", 0, 1)]
+        return [("linear.weight", self._geom.lin_col, 1)]
 
     def forward(self, x):
         return self._run(x, False, True)[0]
@@ -401,6 +411,12 @@ class FFM(_TableModel):
 
     def forward(self, x):
         return self._run(x, False, True)[0]
+
+
+def colocate(models):
+    """Re-home LR / FM-type models trained on the same id stream into ONE joint table (colocated.ColocatedCTR)."""
+    from .colocated import ColocatedCTR
+    return ColocatedCTR(models)
 
 
 def _tower(in_dims: int, device=None) -> nn.Sequential:

@@ -44,14 +44,21 @@ class Geometry:
     emb_col: int
     dim: int
     pitch: int = 0            # floats between rows; 0 = row_stride.  3*row_stride: [p | exp_avg | exp_avg_sq] records
+    block: int = 0            # floats between the p / exp_avg / exp_avg_sq blocks of a record; 0 = row_stride.  A co-located
+                              # record (colocated.py) keeps each block in its own 128-byte line: row_stride 24, block 32, pitch 96
+    stamp_at: int = -1        # >= 0: the lazy-Adam stamp's column, chosen by whoever laid the record out (colocated.py)
 
     @property
     def row_pitch(self):
         return self.pitch or self.row_stride
 
     @property
+    def block_floats(self):
+        return self.block or self.row_stride
+
+    @property
     def has_state(self):
-        return self.row_pitch >= 3 * self.row_stride
+        return self.row_pitch >= 3 * self.block_floats
 
     @property
     def used(self):
@@ -64,6 +71,8 @@ class Geometry:
         stamp there; anything else (full rows, wide FFM rows) uses a separate int32 array."""
         if not self.has_state:
             return -1
+        if self.stamp_at >= 0:
+            return self.stamp_at
         if self.row_stride == 1:
             return 3 if self.row_pitch >= 4 else -1
         if self.row_stride <= 16 and self.used % 4 != 0:
@@ -157,9 +166,10 @@ class TableAdamState:
         dev = param.device
         rs = geom.row_stride
         if geom.has_state:            # [p | exp_avg | exp_avg_sq] records: the state lives inside the table's rows
-            param[:, rs:3 * rs].zero_()
-            self.exp_avg = param[:, rs:2 * rs]
-            self.exp_avg_sq = param[:, 2 * rs:3 * rs]
+            blk = geom.block_floats
+            param[:, blk:3 * blk].zero_()
+            self.exp_avg = param[:, blk:blk + rs]
+            self.exp_avg_sq = param[:, 2 * blk:2 * blk + rs]
         else:
             self.exp_avg = torch.zeros_like(param)
             self.exp_avg_sq = torch.zeros_like(param)

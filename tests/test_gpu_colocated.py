@@ -1,0 +1,177 @@
+"""Co-located records (rl_ctr_prediction_b200/colocated.py): LR + FM + DeepFM trained on one joint table must give the numbers
+of the three stand-alone models -- FM and DeepFM bit for bit (same reduction trees, same arithmetic), LR within rounding of
+its 15-term logit sum (the stand-alone scalar kernel sums in another order) -- and therefore the reference's
+(src/main/pretrain_main.py:96-102 with dense torch.optim.Adam): the golden-trajectory test at the end pins that directly.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import state_from_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+F, D = 15, 10
+
+
+def _models(N, seed=3, names=("LR", "FM", "DeepFM"), eval_tower=True):
+    from rl_ctr_prediction_b200 import pretrain_main as PM
+    torch.manual_seed(seed)
+    ms = [PM.get_model(n, N, F, D).to(DEV) for n in names]
+    for m in ms:
+        m.train()
+        if eval_tower and getattr(m, "mlp", None) is not None:
+            m.mlp.eval()                      # no dropout: the towers of the two arms then see the same arithmetic
+    return ms
+
+
+def _batches(N, B, steps, seed=11, zipf=False):
+    g = torch.Generator().manual_seed(seed)
+    per = N // F
+    out = []
+    for _ in range(steps):
+        if zipf:
+            x = (torch.rand(B, F, generator=g) ** 6 * per).long().clamp_(0, per - 1)      # heavy hitters: long runs of one id
+        else:
+            x = torch.randint(0, per, (B, F), generator=g)
+        x = x + torch.arange(F) * per
+        y = (torch.rand(B, generator=g) < 0.3).long()
+        out.append((x.to(DEV), y.to(DEV)))
+    return out
+
+
+def _train_separate(models, batches, mode="lazy"):
+    from rl_ctr_prediction_b200 import graphs, optim
+    opts = [optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5, mode=mode) for m in models]
+    loss_fn = torch.nn.BCELoss()
+    losses = []
+    for x, y in batches:
+        losses.append([float(graphs.eager_step(m, o, loss_fn, x, y)) for m, o in zip(models, opts)])
+    return np.array(losses)
+
+
+def _train_group(models, batches, mode="lazy"):
+    from rl_ctr_prediction_b200 import colocated, optim
+    group = colocated.colocate(models)
+    opt = optim.Adam(group.parameters(), lr=1e-3, weight_decay=1e-5, mode=mode)
+    losses = [group.train_step(x, y, opt).cpu().numpy().copy() for x, y in batches]
+    return group, np.array(losses)
+
+
+@pytest.mark.parametrize("zipf", [False, True])
+def test_group_equals_standalone_models(zipf):
+    N, B, steps = 3000, 512, 6
+    sep = _models(N)
+    grp_members = [copy.deepcopy(m) for m in sep]
+    batches = _batches(N, B, steps, zipf=zipf)
+    l_sep = _train_separate(sep, batches)
+    group, l_grp = _train_group(grp_members, batches)
+    assert group._geom.row_stride == 24 and group._geom.stamp_col == 23
+    # FM and DeepFM: same bits, losses and every parameter of every row
+    assert np.array_equal(l_sep[:, 1:], l_grp[:, 1:])
+    np.testing.assert_allclose(l_grp[:, 0], l_sep[:, 0], rtol=2e-6)
+    for i, name in enumerate(("LR", "FM", "DeepFM")):
+        a, b = sep[i].state_dict(), grp_members[i].state_dict()
+        assert set(a) == set(b)
+        for k in a:
+            if i == 0:
+                torch.testing.assert_close(b[k], a[k], rtol=0, atol=2e-6), (name, k)
+            else:
+                assert torch.equal(a[k], b[k]), (name, k)
+
+
+def test_group_inference_and_member_views():
+    N, B = 2000, 300
+    sep = _models(N)
+    members = [copy.deepcopy(m) for m in sep]
+    batches = _batches(N, B, 3)
+    _train_separate(sep, batches)
+    group, _ = _train_group(members, batches)
+    x = batches[0][0]
+    with torch.no_grad():
+        for m in sep + members:
+            m.eval()
+        want = torch.cat([m(x) for m in sep], dim=1)
+        got = group(x)                                   # one gather, [B, 3]
+        per_member = torch.cat([m(x) for m in members], dim=1)
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-7)
+    # a member called on its own runs the stand-alone gather kernel over the wider joint row (8 lanes per row: another
+    # summation order for the 15-term sums -- rounding-level differences in logits of size ~10)
+    torch.testing.assert_close(per_member, want, rtol=1e-4, atol=1e-5)
+    assert torch.equal(got[:, 1], want[:, 1])            # FM: the group kernel reproduces the stand-alone tree
+    # a member refuses to train on its own; checkpoints round-trip through the reference keys
+    members[1].train()
+    with pytest.raises(Exception):
+        members[1](x)
+    sd = {k: v.clone() for k, v in members[2].state_dict().items()}
+    assert set(sd) == set(sep[2].state_dict())
+    members[2].load_state_dict(sd)
+    for k, v in members[2].state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_group_lazy_equals_dense_and_long_staleness():
+    """lazy + flush == dense Adam on the joint record (two lanes per row in the replay kernel), with rows that stay untouched
+    for many steps."""
+    N, B, steps = 6000, 64, 40
+    a = _models(N, seed=5)
+    b = [copy.deepcopy(m) for m in a]
+    batches = _batches(N, B, steps, seed=2)
+    ga, la = _train_group(a, batches, mode="lazy")
+    gb, lb = _train_group(b, batches, mode="dense")
+    assert np.array_equal(la, lb)
+    ga.flush()
+    gb.flush()
+    assert torch.equal(ga.table.data[:, :24], gb.table.data[:, :24])
+    assert torch.equal(ga.table.data[:, 32:56], gb.table.data[:, 32:56])
+    assert torch.equal(ga.table.data[:, 64:88], gb.table.data[:, 64:88])
+
+
+def test_group_graphed_step_equals_eager():
+    from rl_ctr_prediction_b200 import colocated, graphs, optim
+    N, B, steps = 4000, 256, 7
+    a = _models(N, seed=9, eval_tower=False)             # train-mode dropout: the device RNG state is replayed too
+    b = [copy.deepcopy(m) for m in a]
+    batches = _batches(N, B, steps, seed=4)
+    ga, gb = colocated.colocate(a), colocated.colocate(b)
+    oa = optim.Adam(ga.parameters(), lr=1e-3, weight_decay=1e-5)
+    ob = optim.Adam(gb.parameters(), lr=1e-3, weight_decay=1e-5)
+    step = graphs.GraphedTrainStep([(ga, oa)])
+    torch.manual_seed(77)                                # the towers draw their dropout seed at their first training forward
+    la = [step(x, y)[0].clone() for x, y in batches]
+    torch.manual_seed(77)
+    lb = [gb.train_step(x, y, ob).clone() for x, y in batches]
+    assert step.graph is not None
+    for u, v in zip(la, lb):
+        assert torch.equal(u, v)
+    ga.flush()
+    gb.flush()
+    assert torch.equal(ga.table.data, gb.table.data)
+    for pa, pb in zip(ga.parameters(), gb.parameters()):
+        assert torch.equal(pa, pb)
+
+
+@pytest.mark.parametrize("names", [("LR", "FM", "DeepFM"), ("FM", "LR"), ("DeepFM", "FM", "LR", "LR")])
+def test_group_matches_reference_trajectory(golden, names):
+    """The reference's own three training steps (tests/golden/make_golden.py: real p_model classes, dense torch.optim.Adam)
+    for every member, trained as ONE group."""
+    from test_gpu_models import assert_state, build, close, load
+    from rl_ctr_prediction_b200 import colocated, optim
+    xs, ys = golden["train/x"], golden["train/y"]
+    members = []
+    for n in names:
+        m = load(build(n, 255), state_from_golden(golden, f"train/{n}/init")).to(DEV).train()
+        if getattr(m, "mlp", None) is not None:
+            m.mlp.eval()                                 # the golden trajectories were recorded with dropout off
+        members.append(m)
+    group = colocated.colocate(members)
+    opt = optim.Adam(group.parameters(), lr=1e-3, weight_decay=1e-5)
+    for s in range(3):
+        losses = group.train_step(torch.as_tensor(xs[s]).to(DEV), torch.as_tensor(ys[s]).to(DEV), opt)
+        for i, n in enumerate(names):
+            close(losses[i], golden[f"train/{n}/loss{s}"])
+    for m, n in zip(members, names):
+        assert_state(m, state_from_golden(golden, f"train/{n}/final"))
