@@ -45,6 +45,18 @@ def run(K, N, ld):
         for name, fn in (("fwd", f), ("dgrad", d), ("wgrad", g)):
             us = timeit(fn)
             out[f"{tag}.{name}"] = {"us": round(us, 1), "fp32_TFLOPs": round(fl / us / 1e6, 1)}
+    # cuBLAS on the same shapes (verdict r1: is 76-116 fp32-equivalent TFLOP/s good?): SGEMM (allow_tf32 = False: what the reference's
+    # nn.Linear runs on a GPU) and cuBLAS' own 1xTF32 (1e-3 error: fails the 1e-5 parity bar, shown as the tensor-core ceiling)
+    xk = x[:, :K].contiguous()
+    fl = 2.0 * B * K * N
+    for tag, tf32 in (("cublas_sgemm", False), ("cublas_tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        yy = torch.empty(B, N, device=dev)
+        for name, fn in (("fwd", lambda: torch.addmm(b, xk, w.t(), out=yy)), ("dgrad", lambda: torch.mm(gy, w, out=dx)),
+                         ("wgrad", lambda: torch.mm(gy.t(), xk, out=dw))):
+            us = timeit(fn)
+            out[f"{tag}.{name}"] = {"us": round(us, 1), "fp32_TFLOPs": round(fl / us / 1e6, 1)}
+    torch.backends.cuda.matmul.allow_tf32 = False
     ref = x[:, :K].double() @ w.double().T + b.double()
     os.environ["RLCTR_GEMM_TMA"] = "1"
     _lib.check(lib.rlctr_linear_fwd(x.data_ptr(), ld, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, N, 0, 0.0, None, ws.data_ptr(), wsb, st), "fwd")
