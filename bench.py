@@ -136,7 +136,7 @@ def alg_bytes(key, m):
         M = len(m["members"])
         tower = sum(d for nm, d in m["members"] if nm in ("DeepFM", "WideAndDeep"))
         if name == "rlctr_group_fwd":
-            train = key.endswith("[train]")
+            train = "infer" not in key
             return float(B * (F * 8 + F * 4 * logical + 4 * M) + (B * 4 * logical if train else 0) + n * tower * 4)
         return float(U * (24 * logical + 8) + n * 8 + B * 4 * M + B * 4 * logical + n * tower * 4)
     if name == "rlctr_rows_lookup":                            # owner-side lookup: record read once, stage + gathered written
@@ -337,6 +337,8 @@ def workload_config(B, N, D, world=1, colocated=False):
             f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step",
             "layout": ("co-located records: the three models' parameters + Adam moments of one id in one 384-byte record "
                        "(3 x 128-byte lines), one gather / catch-up / update per step for all three"
+                       + ("" if world == 1 else "; the joint table row-sharded (id mod G), one per-sample exchange row of 128 bytes "
+                          "all-gathered per step")
                        if colocated else "one fused-row table per model")}
 
 
@@ -624,9 +626,18 @@ def b200_arm(args):
     torch.manual_seed(1 + rank)
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
 
-    colocate = world == 1 and not args.no_colocate
+    colocate = not args.no_colocate
 
     def build_models(colocated=None):
+        if (colocate if colocated is None else colocated) and world > 1:
+            # the co-located record row-sharded over the GPUs (sharded.ShardedGroup): one routed view, one remote gather, one
+            # all_gather of per-sample rows, one push, one all_reduce, one update per step for the three models
+            from rl_ctr_prediction_b200 import sharded
+            group = sharded.ShardedGroup(MODELS, N, F_FIELDS, D, device=dev)
+            with torch.no_grad():
+                group.table.mul_(0.1)
+            group.train()
+            return [(group, optim.Adam(group.parameters(), lr=1e-3, weight_decay=1e-5, mode="lazy"))]
         if colocate if colocated is None else colocated:
             # one record per id for the three models (colocated.py): one gather, one catch-up, one update per step
             from rl_ctr_prediction_b200 import colocated as _co
@@ -809,11 +820,14 @@ def b200_arm(args):
         gath = {"LR": (world - 1) * B * 4, "FM": (world - 1) * B * 4 * rows_rs, "DeepFM": (world - 1) * B * 4 * rows_rs}
         push = rho * n_occ * D * 4                                                   # DeepFM's tower-input gradients, pushed to the owners
         route = rho * n_occ * 8                                                      # (local row, global slot) pairs written to the owners
+        if colocate:                                                                 # one joint gather, one exchange row per sample
+            fwd = {"group": rho * n_occ * 4 * sum(logical.values())}
+            gath = {"group": (world - 1) * B * 4 * 32}
         total = sum(fwd.values()) + sum(gath.values()) + push + route
         nv_peak = 770.0
         per_kernel = {}
-        for m in MODELS:
-            k = f"rlctr_embed_fwd[Sharded{m}]"
+        for m in (["group"] if colocate else MODELS):
+            k = "rlctr_group_fwd[ShardedGroup]" if colocate else f"rlctr_embed_fwd[Sharded{m}]"
             if k in kern and kern[k][1] > 0:
                 gbps = fwd[m] / (kern[k][1] / 1e3) / 1e9
                 per_kernel[k] = {"nvlink_bytes": fwd[m], "mean_ms": kern[k][1], "GBps": gbps, "frac": gbps / nv_peak}
@@ -855,7 +869,7 @@ def b200_arm(args):
             total = 0.0
             for m, opt in ms:
                 if world > 1:
-                    total += m.train_step(x, yh.to(dev, non_blocking=True), opt).item()
+                    total += m.train_step(x, yh.to(dev, non_blocking=True), opt).sum().item()
                     continue
                 p = m(x)                                   # src/main/pretrain_main.py:96-103, per model
                 tl = lossf(p, y.float())
@@ -906,8 +920,8 @@ def b200_arm(args):
             del gs
             ms = None
             torch.cuda.empty_cache()
-            ms = build_models(colocated=False)             # the reference's per-model loop body: three stand-alone models
-        elif colocate:
+            ms = build_models(colocated=False if world == 1 else None)   # one GPU: the reference's per-model loop body
+        elif colocate and world == 1:
             ms = None
             torch.cuda.empty_cache()
             ms = build_models(colocated=False)

@@ -331,19 +331,24 @@ typedef struct rlctr_member {
     float*       rows_out;     /* [B, rows_pitch]: rows_out[b, f*dim + d] = v_f[d] (tower input) */
     int64_t      rows_pitch;   /* 0 = fields*dim */
     /* gradient side (rlctr_group_rows_adam) */
-    const float* dlogit;       /* [B] dL/dlogit of this member */
+    const float* dlogit;       /* [B] dL/dlogit of this member; NULL: it rides in the sums rows, column sums_pitch - RLCTR_GROUP_MAX + m
+                                * (one line per sample carries S and every member's dL/dlogit: what the row-sharded step all-gathers) */
     const float* extra;        /* [B, fields*dim] dense-tail gradient on the latent columns, or NULL */
 } rlctr_member;
 /* One gather per (sample, field) for every member: logit / pctr / rows_out per member as rlctr_embed_fwd would produce them
- * from the member's stand-alone table; sums[b, :] = column sums of the joint rows ([B, row_stride], optional: the backward's S). */
+ * from the member's stand-alone table; sums[b * sums_pitch + col] = column sums of the joint rows (optional: the backward's S;
+ * sums_pitch = 0 means row_stride).  A row-sharded joint table (table->world > 1) is read through peers[] like rlctr_embed_fwd. */
 int rlctr_group_fwd(const int64_t* ids, const rlctr_table* table, const rlctr_member* members, int32_t n_members,
-                    float* sums, int64_t batch, int32_t fields, rlctr_stream_t stream);
+                    float* sums, int32_t sums_pitch, int64_t batch, int32_t fields, rlctr_stream_t stream);
 /* rlctr_rows_adam over the joint record: per column the gradient of the member that owns it
- * (first-order: dlogit_m[b]; latent: dlogit_m[b] * (sums[b, col] - row[col]) if RLCTR_FM_TERM, + extra_m[b, f*dim + d]),
- * reduced over the occurrences of an id in slot order, then ONE Adam step on the record.  ws: rlctr_rows_ws_bytes(n). */
+ * (first-order: dlogit_m[b]; latent: dlogit_m[b] * (sums[b, col] - row[col]) if RLCTR_FM_TERM, + extra_m[slot * dim + d]),
+ * reduced over the occurrences of an id in slot order, then ONE Adam step on the record.  b = slot / fields: for a row-sharded
+ * table the slots are GLOBAL (src rank * n_per_rank + slot), `sums` is the all-gathered [world * B, sums_pitch] array, extra_m the
+ * owner's receive buffer of rlctr_push_rows, and `world` sizes the grid for the owned ~1/world of the sorted view (the rest are
+ * sentinels).  ws: rlctr_rows_ws_bytes(n). */
 int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
                           const rlctr_adam* opt, const rlctr_member* members, int32_t n_members, const float* sums,
-                          int32_t fields, void* ws, size_t ws_bytes, rlctr_stream_t stream);
+                          int32_t sums_pitch, int32_t fields, int32_t world, void* ws, size_t ws_bytes, rlctr_stream_t stream);
 
 /* Same reduction, but the sums are stored into a dense [n_rows,row_stride] gradient
  * (rows of untouched ids are not written): the literal embedding_dense_backward. */

@@ -177,7 +177,7 @@ class ColocatedCTR(Model._TableModel):
         out = torch.empty(B, len(self.members), dtype=torch.float32, device=x.device)
         arr, logits, rows = self._member_structs(B, F, x.device, False, pctr=out)
         t = table_struct(self.table.data, self._geom)
-        _lib.call("rlctr_group_fwd", lib.rlctr_group_fwd, _lib.ptr(x), C.byref(t), arr, len(self.members), None, B, F,
+        _lib.call("rlctr_group_fwd", lib.rlctr_group_fwd, _lib.ptr(x), C.byref(t), arr, len(self.members), None, 0, B, F,
                   _lib.stream(), key="rlctr_group_fwd[infer]", meta=self._meta(B, F))
         for i, m in enumerate(self.members):
             if rows[i] is not None:
@@ -209,7 +209,7 @@ class ColocatedCTR(Model._TableModel):
         M = len(self.members)
         arr, logits, rows = self._member_structs(B, F, dev, True)
         sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
-        _lib.call("rlctr_group_fwd", lib.rlctr_group_fwd, _lib.ptr(x), C.byref(t), arr, M, _lib.ptr(sums), B, F, st,
+        _lib.call("rlctr_group_fwd", lib.rlctr_group_fwd, _lib.ptr(x), C.byref(t), arr, M, _lib.ptr(sums), 0, B, F, st,
                   key="rlctr_group_fwd[train]", meta=self._meta(B, F))
         losses = torch.empty(M, dtype=torch.float32, device=dev)
         dlogits, extras = [], []
@@ -257,7 +257,7 @@ class ColocatedCTR(Model._TableModel):
         ws_bytes = lib.rlctr_rows_ws_bytes(stash.n)
         ws = self._rows_ws(ws_bytes)
         _lib.call("rlctr_group_rows_adam", lib.rlctr_group_rows_adam, _lib.ptr(stash.sorted_ids), _lib.ptr(stash.sorted_slots),
-                  stash.n, C.byref(t), C.byref(a), arr, len(self.members), _lib.ptr(stash.sums), stash.fields, _lib.ptr(ws),
+                  stash.n, C.byref(t), C.byref(a), arr, len(self.members), _lib.ptr(stash.sums), 0, stash.fields, 1, _lib.ptr(ws),
                   ws_bytes, st, key="rlctr_group_rows_adam", meta=self._meta(stash.n // stash.fields, stash.fields))
 
 

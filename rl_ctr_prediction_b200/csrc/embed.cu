@@ -207,7 +207,7 @@ __device__ __forceinline__ void group_accumulate(float4 r[4], const int64_t id[4
 }
 // butterflies, per-member logits (lane m finishes member m from the staged column sums / per-chunk t), tower rows, saved sums
 __device__ __forceinline__ void group_finish(float4 sA, float4 sB, float qA, float qB, const GroupLaneFwd& L, float* wsm,
-                                             const GroupFwdView& gv, float* __restrict__ sums, int rs, int64_t b, int fields) {
+                                             const GroupFwdView& gv, float* __restrict__ sums, int sums_pitch, int64_t b, int fields) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int off = 8; off < 32; off <<= 1) {
@@ -228,7 +228,7 @@ __device__ __forceinline__ void group_finish(float4 sA, float4 sB, float qA, flo
     if (L.g == 0) {
         *reinterpret_cast<float4*>(wsm + L.col0) = s;
         wsm[32 + L.c] = t;
-        if (sums && L.chunk_on) st4(sums + b * rs + L.col0, s);
+        if (sums && L.chunk_on) st4(sums + b * sums_pitch + L.col0, s);
     }
     __syncwarp();
     if (lane < gv.n) {
@@ -265,7 +265,8 @@ __device__ __forceinline__ void group_finish(float4 sA, float4 sB, float qA, flo
 template <int LD, bool ONE>      // ONE: fields <= 16, a single block of row loads per sample: software-pipelined
 __global__ void __launch_bounds__(256, 3)
 group_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab, const __grid_constant__ ShardView sv, int64_t n_rows,
-                 int pitch, int rs, const __grid_constant__ GroupFwdView gv, float* __restrict__ sums, int64_t batch, int fields) {
+                 int pitch, int rs, const __grid_constant__ GroupFwdView gv, float* __restrict__ sums, int sums_pitch, int64_t batch,
+                 int fields) {
     extern __shared__ __align__(16) float gsm[];
     const int lane = threadIdx.x & 31;
     GroupLaneFwd L;
@@ -310,7 +311,7 @@ group_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
             float4 sA = f4zero(), sB = f4zero();
             float qA = 0.f, qB = 0.f;
             group_accumulate(r_c, id_c, n_rows, 0, fields, L, sA, sB, qA, qB);
-            group_finish(sA, sB, qA, qB, L, wsm, gv, sums, rs, b, fields);
+            group_finish(sA, sB, qA, qB, L, wsm, gv, sums, sums_pitch, b, fields);
 #pragma unroll
             for (int u = 0; u < 4; ++u) { r_c[u] = r_n[u]; id_c[u] = id_n[u]; id_n[u] = id_nn[u]; }
         }
@@ -325,7 +326,7 @@ group_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tab,
                 group_issue<LD>(r, id, tab, sv, n_rows, pitch, L);
                 group_accumulate(r, id, n_rows, f0, fields, L, sA, sB, qA, qB);
             }
-            group_finish(sA, sB, qA, qB, L, wsm, gv, sums, rs, b, fields);
+            group_finish(sA, sB, qA, qB, L, wsm, gv, sums, sums_pitch, b, fields);
         }
     }
 }
@@ -586,13 +587,15 @@ extern "C" int rlctr_embed_fwd(const int64_t* ids, const rlctr_table* table, con
 }
 
 extern "C" int rlctr_group_fwd(const int64_t* ids, const rlctr_table* table, const rlctr_member* members, int32_t n_members,
-                               float* sums, int64_t batch, int32_t fields, rlctr_stream_t stream) {
+                               float* sums, int32_t sums_pitch, int64_t batch, int32_t fields, rlctr_stream_t stream) {
     int rc = check_table(table);
     if (rc) return rc;
     if (!ids || !members || n_members < 1 || n_members > RLCTR_GROUP_MAX || batch < 0 || fields <= 0) return RLCTR_EINVAL;
     const int rs = table->row_stride;
     if (rs == 1 || rs > 32) return RLCTR_EUNSUPPORTED;
     if (sums && !rlctr_aligned16(sums)) return RLCTR_EALIGN;
+    if (sums_pitch == 0) sums_pitch = rs;
+    if (sums_pitch < rs || sums_pitch % 4 != 0) return RLCTR_EINVAL;
     if (batch == 0) return RLCTR_OK;
     ShardView sv;
     if (!shard_view_of(table, &sv)) return RLCTR_EUNSUPPORTED;
@@ -643,9 +646,9 @@ extern "C" int rlctr_group_fwd(const int64_t* ids, const rlctr_table* table, con
     if (ld_env < 0) { const char* e = getenv("RLCTR_GROUP_LD"); ld_env = e ? atoi(e) : 1; }
 #define LAUNCH_GROUP(L)                                                                                                          \
     if (fields <= 16) group_fwd_kernel<L, true><<<grid, 256, smem, (cudaStream_t)stream>>>(ids, table->data, sv, table->n_rows,       \
-                                                                                          pitch_of(table), rs, gv, sums, batch, fields); \
+                                                                                          pitch_of(table), rs, gv, sums, sums_pitch, batch, fields); \
     else group_fwd_kernel<L, false><<<grid, 256, smem, (cudaStream_t)stream>>>(ids, table->data, sv, table->n_rows, pitch_of(table), \
-                                                                               rs, gv, sums, batch, fields)
+                                                                               rs, gv, sums, sums_pitch, batch, fields)
     if (ld_env == 1) { LAUNCH_GROUP(1); } else if (ld_env == 2) { LAUNCH_GROUP(2); } else { LAUNCH_GROUP(0); }
 #undef LAUNCH_GROUP
     RLCTR_LAUNCH_CHECK();

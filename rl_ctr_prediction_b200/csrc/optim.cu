@@ -67,6 +67,8 @@ struct GroupCols {
     const float* dz[RLCTR_GROUP_MAX];        // dL/dlogit of member m, [B]
     const float* extra[RLCTR_GROUP_MAX];     // dense-tail gradient on member m's latent columns, [B, fields * dim_m], or NULL
     int emb_col[RLCTR_GROUP_MAX], dim[RLCTR_GROUP_MAX];
+    int sums_pitch;                          // floats between the sums rows; dz[m] == NULL: dL/dlogit of member m rides in column
+                                             // sums_pitch - RLCTR_GROUP_MAX + m of the sample's sums row
     signed char member[32];                  // column -> member, -1: padding / stamp
     signed char role[32];                    // 0 none, 1 first-order weight, 2 latent column with the FM term, 3 latent column without
 };
@@ -218,13 +220,15 @@ __device__ __forceinline__ float4 rowgrad_group(const GradView& g, const GroupLa
                                                 const TableView& t) {
     const uint32_t b = slot / (uint32_t)g.fields;
     const uint32_t f = slot - b * (uint32_t)g.fields;
-    const float4 S = ldg4(g.sums + (int64_t)b * t.rs + col0);
+    const float* srow = g.sums + (int64_t)b * g.grp.sums_pitch;
+    const float4 S = ldg4(srow + col0);
     float4 r = f4zero();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int m = gl.mem[k];
         if (m < 0) continue;
-        const float dz = __ldg(g.grp.dz[m] + b);
+        const float* dzp = g.grp.dz[m];
+        const float dz = dzp ? __ldg(dzp + b) : __ldg(srow + g.grp.sums_pitch - RLCTR_GROUP_MAX + m);
         float add = 0.f;
         if (gl.role[k] == 1) {
             add = dz;
@@ -1394,7 +1398,8 @@ extern "C" int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorte
 
 extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
                                      const rlctr_adam* opt, const rlctr_member* members, int32_t n_members, const float* sums,
-                                     int32_t fields, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
+                                     int32_t sums_pitch, int32_t fields, int32_t world, void* ws, size_t ws_bytes,
+                                     rlctr_stream_t stream) {
     if (!sorted_ids || !sorted_slots || !table || !table->data || !opt || !opt->exp_avg || !opt->exp_avg_sq || !opt->sched ||
         !opt->step || !members || !sums || n < 0 || fields <= 0)
         return RLCTR_EINVAL;
@@ -1407,13 +1412,17 @@ extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t*
     if (t.rs % 4 != 0 || t.rs <= 8 || t.rs > 32) return RLCTR_EUNSUPPORTED;
     if (opt->stamp_col >= t.pitch) return RLCTR_EINVAL;
     if (!rlctr_aligned16(sums)) return RLCTR_EALIGN;
+    if (sums_pitch == 0) sums_pitch = t.rs;
+    if (sums_pitch < t.rs || sums_pitch % 4 != 0 || world < 0 || world > RLCTR_MAX_WORLD) return RLCTR_EINVAL;
     GradView g{};
     g.sums = sums; g.fields = fields; g.world = 0;
     g.grp.n = n_members;
+    g.grp.sums_pitch = sums_pitch;
     for (int col = 0; col < 32; ++col) { g.grp.member[col] = -1; g.grp.role[col] = 0; }
     for (int m = 0; m < n_members; ++m) {
         const rlctr_member& mm = members[m];
-        if (!mm.dlogit || mm.dim < 0 || mm.emb_col < 0 || mm.emb_col + mm.dim > t.rs || mm.lin_col >= t.rs) return RLCTR_EINVAL;
+        if (mm.dim < 0 || mm.emb_col < 0 || mm.emb_col + mm.dim > t.rs || mm.lin_col >= t.rs) return RLCTR_EINVAL;
+        if (!mm.dlogit && sums_pitch - RLCTR_GROUP_MAX < t.rs) return RLCTR_EINVAL;      // no room for dL/dlogit in the sums rows
         g.grp.dz[m] = mm.dlogit; g.grp.extra[m] = mm.extra; g.grp.emb_col[m] = mm.emb_col; g.grp.dim[m] = mm.dim;
         if (mm.lin_col >= 0) {
             if (g.grp.member[mm.lin_col] >= 0) return RLCTR_EINVAL;              // two members claim one column
@@ -1430,7 +1439,7 @@ extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t*
     RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
     RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
     const int lpr = rlctr_lanes_per_row(t.rs);
-    const unsigned blocks = (unsigned)((n * lpr + 255) / 256);
+    const unsigned blocks = capped_blocks((n * lpr + 255) / 256, world);
     if (lpr == 4) {
         rows_short_kernel<4, 0, true><<<blocks, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);
         rows_long_kernel<4, 0, true><<<RLCTR_SMS, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);

@@ -470,3 +470,270 @@ class ShardedCTR(nn.Module):
                                             (_lib.RLCTR_DZ_IN_SUMS if dz_in_sums else 0), peer=peer)
         optimizer.step()
         return loss.reshape(())
+
+
+# ---------------------------------------------------------------------------------------------------
+class _MemberGeom:
+    """Stand-in carrying the stand-alone geometry of a member kind for colocated._layout."""
+
+    def __init__(self, kind, n, d):
+        self._geom = Geometry.lr(n) if kind == "LR" else Geometry.fm(n, d)
+
+
+class ShardedGroup(nn.Module):
+    """Co-located records (colocated.py) over a row-sharded joint table: LR / FM / DeepFM trained on the same id stream share one
+    384-byte record per id, ``owner(id) = id mod G``.  Per step and rank: ONE routed sorted view (shared_sorted_view), one
+    catch-up of the owned records, one gather through the peer mapping (rlctr_group_fwd: one NVLink read per (sample, field)
+    for all members instead of one per member), one all_gather of the per-sample rows [B, 32] = column sums + every member's
+    dL/dlogit, one push of the tower-input gradients, one all_reduce of all dense gradients, two device barriers, one update
+    (rlctr_group_rows_adam).  The update equals the single-GPU group step on the concatenated global batch."""
+
+    SUMS_PITCH = 32                    # one 128-byte line per sample: S (<= 28 floats) | dL/dlogit of members 0..3
+
+    def __init__(self, kinds, feature_nums, field_nums, latent_dims, group=None, device=None):
+        super().__init__()
+        from . import colocated as _co
+        kinds = tuple(kinds)
+        if not all(k in ("LR", "FM", "DeepFM") for k in kinds) or not 1 <= len(kinds) <= _lib.RLCTR_GROUP_MAX:
+            raise _lib.RlctrError("ShardedGroup members: LR, FM, DeepFM (up to four)")
+        self.kinds, self.feature_nums, self.field_nums, self.latent_dims = kinds, int(feature_nums), int(field_nums), int(latent_dims)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world not in (1, 2, 4, 8):
+            raise _lib.RlctrError("row sharding supports 1, 2, 4 or 8 GPUs (owner = id & (G-1))")
+        n_local = max(shard_rows(self.feature_nums, self.world, self.rank), 1)
+        n_alloc = max(shard_rows(self.feature_nums, self.world, 0), 1)
+        self._cols, used = _co._layout([_MemberGeom(k, n_local, self.latent_dims) for k in kinds])
+        rs = (used + 1 + 3) // 4 * 4
+        if rs > self.SUMS_PITCH - _lib.RLCTR_GROUP_MAX:
+            raise _lib.RlctrError("joint row too wide for the per-sample exchange row (28 floats)")
+        self._geom = Geometry(n_local, rs, -1, 0, used, pitch=96, block=32, stamp_at=used)
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._pm = PeerMemory(n_alloc * 96, torch.float32, dev, group)
+        data = self._pm.local.view(n_alloc, 96)
+        data.zero_()
+        for lin, emb, dim in self._cols:
+            cols = ([lin] if lin >= 0 else []) + list(range(emb, emb + dim))
+            data[:n_local, cols] = torch.randn(n_local, len(cols), device=dev)
+        self.table = nn.Parameter(data)
+        self.table._rlctr_owner = self
+        self.biases = nn.ParameterList([nn.Parameter(torch.zeros(1, device=dev)) for _ in kinds])
+        self.mlps = nn.ModuleList([Model._tower(self.field_nums * self.latent_dims, dev) if k == "DeepFM" else nn.Identity()
+                                   for k in kinds])
+        self._opt, self._stash, self._ws, self._buf = None, None, {}, {}
+        self.fork_ok = False
+
+    # ---- protocol shared with optim.Adam / graphs ----------------------------------------------------------------------
+    def _apply(self, fn, recurse=True):
+        saved = self._parameters.pop("table")            # the shard lives in symmetric memory: .to() must not move it
+        out = super()._apply(fn, recurse)
+        self._parameters["table"] = saved
+        self.table._rlctr_owner = self
+        return out
+
+    def _meta(self, B, F):
+        g = self._geom
+        return {"model": "Sharded" + "+".join(self.kinds), "B": B, "F": max(F, 1), "rs": g.row_stride, "dim": g.dim,
+                "n_rows": g.n_rows, "lin": False, "members": [(k, c[2]) for k, c in zip(self.kinds, self._cols)]}
+
+    def flush(self):
+        if self._opt is not None:
+            self._opt.flush(self.table.data)
+        check_route_overflow()
+
+    _reduce_ws = ShardedCTR._reduce_ws
+    _rows_ws = Model._TableModel._rows_ws
+
+    def zero_grad(self, set_to_none=True):
+        self._stash = None
+        return super().zero_grad(set_to_none)
+
+    def barrier(self):
+        self._pm.barrier()
+
+    @classmethod
+    def from_group(cls, cg, group=None):
+        """Shard a single-GPU colocated.ColocatedCTR (same parameters on every rank) over the process group."""
+        kinds = [type(m).__name__ for m in cg.members]
+        m0 = cg.members[-1]
+        self = cls(kinds, cg.feature_nums, getattr(m0, "field_nums", 15), max(getattr(m, "latent_dims", 1) for m in cg.members),
+                   group=group, device=cg.table.device)
+        assert self._cols == cg._cols
+        cg.flush()
+        with torch.no_grad():
+            shard = cg.table.data[self.rank::self.world]
+            self.table.data[:shard.shape[0]].copy_(shard)
+            for i, m in enumerate(cg.members):
+                self.biases[i].data.copy_(m.bias.data)
+                if getattr(m, "mlp", None) is not None:
+                    self.mlps[i].load_state_dict(m.mlp.state_dict())
+        self.barrier()
+        return self
+
+    def gather_table(self):
+        """The full joint table [N, 96], rebuilt on every rank (tests / checkpointing)."""
+        self.flush()
+        mine = self.table.data.contiguous()
+        if self.world == 1:
+            return mine[:self.feature_nums].clone()
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        full = torch.empty(self.feature_nums, 96, dtype=torch.float32, device=mine.device)
+        for r in range(self.world):
+            full[r::self.world] = parts[r][:shard_rows(self.feature_nums, self.world, r)]
+        return full
+
+    def _global_struct(self):
+        g = self._geom
+        t = _lib.Table(self.table.data.data_ptr(), self.feature_nums, g.row_stride, g.lin_col, g.emb_col, g.dim, g.row_pitch)
+        if self.world > 1:
+            t.world = self.world
+            for r, p in enumerate(self._pm.ptrs):
+                t.peers[r] = p
+        return t
+
+    def _exchange(self, B, F):
+        """Per batch size: this rank's per-sample exchange rows [B, 32], their all-gathered copy [G*B, 32], and per tower member
+        the symmetric receive buffer [G*n, D] the source ranks push their tower-input gradients into."""
+        b = self._buf.get(B)
+        if b is None:
+            dev, G, D = self.table.device, self.world, self.latent_dims
+            b = {"sums": torch.zeros(B, self.SUMS_PITCH, dtype=torch.float32, device=dev),
+                 "sums_all": torch.zeros(G * B, self.SUMS_PITCH, dtype=torch.float32, device=dev), "recv": {}}
+            for i, k in enumerate(self.kinds):
+                if k == "DeepFM" and G > 1:
+                    pm = PeerMemory(G * B * F * D, torch.float32, dev, self.group)
+                    pm.local.zero_()
+                    b["recv"][i] = (pm, (C.c_void_p * 8)(*[int(p) for p in pm.ptrs]))
+            self._buf[B] = b
+        return b
+
+    def _members(self, B, F, dev):
+        arr = (_lib.Member * len(self.kinds))()
+        logits, rows = [], []
+        for i, (k, (lin, emb, dim)) in enumerate(zip(self.kinds, self._cols)):
+            s = arr[i]
+            s.lin_col, s.emb_col, s.dim = lin, emb, dim
+            s.flags = _lib.RLCTR_FM_TERM if k in ("FM", "DeepFM") else 0
+            s.bias = _lib.ptr(self.biases[i].data)
+            z = torch.empty(B, dtype=torch.float32, device=dev)
+            s.logit = _lib.ptr(z)
+            logits.append(z)
+            r = None
+            if k == "DeepFM":
+                pitch = (F * dim + 3) // 4 * 4
+                r = torch.empty(B, pitch, dtype=torch.float32, device=dev)
+                s.rows_out, s.rows_pitch = r.data_ptr(), pitch
+            rows.append(r)
+        return arr, logits, rows
+
+    @torch.no_grad()
+    def forward(self, x):
+        """pCTR of every member, float32 [B, M]."""
+        lib = _lib.load()
+        x = Model._check_ids(x)
+        B, F = x.shape
+        self.flush()
+        self.barrier()
+        arr, logits, rows = self._members(B, F, x.device)
+        t = self._global_struct()
+        _lib.call("rlctr_group_fwd", lib.rlctr_group_fwd, _lib.ptr(x), C.byref(t), arr, len(self.kinds), None, 0, B, F, _lib.stream(),
+                  key="rlctr_group_fwd[sharded infer]", meta=self._meta(B, F))
+        out = []
+        for i, k in enumerate(self.kinds):
+            z = logits[i]
+            if rows[i] is not None:
+                z = z + self.mlps[i](rows[i][:, :F * self._cols[i][2]]).reshape(-1)
+            out.append(torch.sigmoid(z))
+        self.barrier()
+        return torch.stack(out, dim=1)
+
+    def train_step(self, features, labels, optimizer):
+        """One step of every member on the local batch; returns the local mean BCE losses, float32 [M]."""
+        lib = _lib.load()
+        opt = self._opt
+        if opt is None:
+            raise _lib.RlctrError("build rl_ctr_prediction_b200.optim.Adam(group.parameters(), ...) before training the group")
+        x = Model._check_ids(features)
+        B, F = x.shape
+        dev, st, G, M = x.device, _lib.stream(), self.world, len(self.kinds)
+        y = labels.reshape(-1).contiguous()
+        yi = y if y.dtype == torch.int64 else None
+        yf = None if yi is not None else y.float()
+        buf = self._exchange(B, F)
+        srows, sslots, n_all = shared_sorted_view(x, self.feature_nums, self.group)
+        if opt.lazy and opt.dirty:
+            t, a = table_struct(self.table.data, self._geom), opt.struct()
+            _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(srows), n_all, C.byref(t), C.byref(a), st,
+                      key="rlctr_rows_catchup[ShardedGroup]", meta=self._meta(n_all // F, F))
+        self.barrier()                                        # B1: all owners caught their rows up | forward reads
+        arr, logits, rows = self._members(B, F, dev)
+        t = self._global_struct()
+        sums = buf["sums"]
+        _lib.call("rlctr_group_fwd", lib.rlctr_group_fwd, _lib.ptr(x), C.byref(t), arr, M, _lib.ptr(sums), self.SUMS_PITCH, B, F, st,
+                  key="rlctr_group_fwd[ShardedGroup]", meta=dict(self._meta(B, F), n_rows=self.feature_nums))
+        losses = torch.empty(M, dtype=torch.float32, device=dev)
+        ws = self._reduce_ws(dev)
+        for p in self.parameters():
+            p.grad = None
+        extras = [None] * M
+        for i, k in enumerate(self.kinds):
+            dl = torch.empty(B, dtype=torch.float32, device=dev)
+            dbias = torch.empty(1, dtype=torch.float32, device=dev)
+            z, tower_out, leaf = logits[i], None, None
+            if rows[i] is not None:
+                leaf = rows[i][:, :F * self._cols[i][2]].detach().requires_grad_(True)
+                with torch.enable_grad():
+                    tower_out = self.mlps[i](leaf).reshape(-1)
+                z = z + tower_out.detach()
+            _lib.check(lib.rlctr_bce_fwd_bwd(_lib.ptr(z), _lib.ptr(yi), _lib.ptr(yf), None, losses.data_ptr() + 4 * i, _lib.ptr(dl),
+                                             _lib.ptr(dbias) if tower_out is None else None, _lib.ptr(ws), B, st), "rlctr_bce_fwd_bwd")
+            if tower_out is not None:                         # as the single-GPU group (and the stand-alone backward) sum it
+                _lib.check(lib.rlctr_sigmoid_bwd(None, None, _lib.ptr(dl), _lib.ptr(dbias), _lib.ptr(ws), B, st), "rlctr_sigmoid_bwd")
+            if G > 1:                                         # gradient of the GLOBAL mean loss
+                dl.mul_(1.0 / G)
+                dbias.mul_(1.0 / G)
+            sums[:, self.SUMS_PITCH - _lib.RLCTR_GROUP_MAX + i] = dl    # dL/dlogit rides in the sample's exchange row
+            if tower_out is not None:
+                tower_out.backward(dl)
+                extras[i] = leaf.grad.contiguous()
+            self.biases[i].grad = dbias
+        if G > 1:
+            dense = [p for p in self.parameters() if p is not self.table and p.grad is not None]
+            flat = torch.cat([p.grad.reshape(-1) for p in dense])
+            dist.all_reduce(flat, group=self.group)
+            o = 0
+            for p in dense:
+                p.grad = flat[o:o + p.numel()].view_as(p).clone()
+                o += p.numel()
+            dist.all_gather_into_tensor(buf["sums_all"], sums, group=self.group)
+            sums_all = buf["sums_all"]
+            for i, (pm, ptrs) in buf["recv"].items():          # per-occurrence rows: posted writes into the owners' memory
+                n = B * F
+                _lib.call("rlctr_push_rows", lib.rlctr_push_rows, _lib.ptr(x), n, G, self.rank, self.feature_nums,
+                          _lib.ptr(extras[i]), self.latent_dims, ptrs, st, meta={"n": n, "width": self.latent_dims})
+                extras[i] = pm.local
+        else:
+            sums_all = sums
+        self.barrier()                                        # B2: every rank's gradient-side buffers are complete
+        self._stash = {"sorted_ids": srows, "sorted_slots": sslots, "n": n_all, "fields": F, "sums": sums_all, "extra": extras}
+        optimizer.step()
+        return losses
+
+    def _group_update(self, stash, opt_state, st):
+        lib = _lib.load()
+        arr = (_lib.Member * len(self.kinds))()
+        for i, (k, (lin, emb, dim)) in enumerate(zip(self.kinds, self._cols)):
+            s = arr[i]
+            s.lin_col, s.emb_col, s.dim = lin, emb, dim
+            s.flags = _lib.RLCTR_FM_TERM if k in ("FM", "DeepFM") else 0
+            s.dlogit = None                                   # in the exchange rows
+            s.extra = _lib.ptr(stash["extra"][i])
+        t, a = table_struct(self.table.data, self._geom), opt_state.struct()
+        n, F = stash["n"], stash["fields"]
+        ws_bytes = lib.rlctr_rows_ws_bytes(n)
+        ws = self._rows_ws(ws_bytes)
+        _lib.call("rlctr_group_rows_adam", lib.rlctr_group_rows_adam, _lib.ptr(stash["sorted_ids"]), _lib.ptr(stash["sorted_slots"]),
+                  n, C.byref(t), C.byref(a), arr, len(self.kinds), _lib.ptr(stash["sums"]), self.SUMS_PITCH, F, self.world,
+                  _lib.ptr(ws), ws_bytes, st, key="rlctr_group_rows_adam[ShardedGroup]", meta=self._meta(n // F, F))

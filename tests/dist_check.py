@@ -59,6 +59,43 @@ def main():
         ok = ok and good
         if rank == 0:
             print(json.dumps({"model": name, "world": world, "ok": good, "max_rel_err_vs_single_gpu": errs}))
+    # ---- co-located group: ShardedGroup on G ranks x B/G == colocated.ColocatedCTR on the global batch
+    from rl_ctr_prediction_b200 import colocated
+    torch.manual_seed(9)
+    members = [PM.get_model(n, N, F, D) for n in ("LR", "FM", "DeepFM")]
+    for mm in members:
+        with torch.no_grad():
+            mm.table.mul_(0.1)
+        mm.to(dev).train()
+        if getattr(mm, "mlp", None) is not None:
+            mm.mlp.eval()
+    cg = colocated.colocate(members)
+    sg = sharded.ShardedGroup.from_group(cg)
+    for mlp in sg.mlps:
+        mlp.eval()
+    opt_s = optim.Adam(cg.parameters(), lr=1e-3, weight_decay=1e-5)
+    opt_m = optim.Adam(sg.parameters(), lr=1e-3, weight_decay=1e-5)
+    rng = np.random.default_rng(13)
+    for s in range(STEPS):
+        x = torch.as_tensor(rng.integers(0, N, size=(B, F))).to(dev)
+        y = torch.as_tensor((rng.random(B) < 0.3).astype(np.int64)).to(dev)
+        cg.train_step(x, y, opt_s)
+        lo, hi = rank * (B // world), (rank + 1) * (B // world)
+        sg.train_step(x[lo:hi].contiguous(), y[lo:hi].contiguous(), opt_m)
+    cg.flush()
+    full = sg.gather_table()
+    scale = cg.table.data[:, :24].abs().max().item()
+    errs = {"table": (full - cg.table.data)[:, :24].abs().max().item() / scale,
+            "exp_avg_sq": ((full - cg.table.data)[:, 64:88].abs().max() / cg.table.data[:, 64:88].abs().max()).item()}
+    for i, mm in enumerate(cg.members):
+        errs[f"bias{i}"] = (sg.biases[i].data - mm.bias.data).abs().max().item()
+        if getattr(mm, "mlp", None) is not None:
+            for (k, a), (_, b) in zip(sg.mlps[i].state_dict().items(), mm.mlp.state_dict().items()):
+                errs["mlp." + k] = ((a - b).abs().max() / b.abs().max()).item()
+    good = all(v <= 2e-5 for v in errs.values())
+    ok = ok and good
+    if rank == 0:
+        print(json.dumps({"model": "group(LR+FM+DeepFM)", "world": world, "ok": good, "max_rel_err_vs_single_gpu": errs}))
     # every rank has printed / compared; leave without tearing the symmetric-memory mappings down collectively
     torch.cuda.synchronize()
     sys.stdout.flush()

@@ -175,3 +175,33 @@ def test_group_matches_reference_trajectory(golden, names):
             close(losses[i], golden[f"train/{n}/loss{s}"])
     for m, n in zip(members, names):
         assert_state(m, state_from_golden(golden, f"train/{n}/final"))
+
+
+def test_sharded_group_world1_equals_colocated():
+    """sharded.ShardedGroup on one rank (the exchange-row layout: sums at a 32-float pitch with every member's dL/dlogit riding in
+    it, the capped grid, the peer-table forward) == colocated.ColocatedCTR, bit for bit."""
+    from rl_ctr_prediction_b200 import colocated, optim, sharded
+    N, B, steps = 3001, 384, 5
+    a = _models(N, seed=21)
+    cg = colocated.colocate(a)
+    sg = sharded.ShardedGroup.from_group(cg)
+    for mlp in sg.mlps:
+        mlp.eval()
+    oa = optim.Adam(cg.parameters(), lr=1e-3, weight_decay=1e-5)
+    ob = optim.Adam(sg.parameters(), lr=1e-3, weight_decay=1e-5)
+    for x, y in _batches(N, B, steps, seed=6, zipf=True):
+        la = cg.train_step(x, y, oa)
+        lb = sg.train_step(x, y, ob)
+        assert torch.equal(la, lb)
+    cg.flush()
+    assert torch.equal(sg.gather_table(), cg.table.data)
+    for i, m in enumerate(cg.members):
+        assert torch.equal(sg.biases[i].data, m.bias.data)
+        if getattr(m, "mlp", None) is not None:
+            for (k, u), (_, v) in zip(sg.mlps[i].state_dict().items(), m.mlp.state_dict().items()):
+                assert torch.equal(u, v), k
+    x = _batches(N, B, 1, seed=8)[0][0]
+    with torch.no_grad():
+        for m in cg.members:
+            m.eval()
+        assert torch.equal(sg(x), cg(x))
