@@ -164,7 +164,10 @@ def alg_bytes(key, m):
             b += U * 8
         return float(b)
     if name == "rlctr_rows_catchup":
-        return float(n * 4 + U * 4)                            # lower bound: stale rows add 24*logical each
+        # every distinct row that was NOT touched in the previous step is stale (uniform ids: a fraction U / N was): its record is
+        # read, replayed and written back -- 24 * logical bytes, the same record traffic as the update's
+        stale = U * (1.0 - U / N)
+        return float(n * 4 + U * 4 + stale * 24 * logical)
     if name == "rlctr_ffm_fwd":
         return float(B * (F * 8 + F * 4 * logical + 4) + n * 4 * logical)
     return 0.0

@@ -98,8 +98,11 @@ replay_keys_kernel(const float* __restrict__ prio, int ld, int64_t n, float eps,
         if (mode == 0) {
             const uint64_t idx = ctr + (uint64_t)i;
             const uint32_t h = mix32((uint32_t)idx ^ dropout_key(seed, (uint32_t)(idx >> 32)));
-            const float u = ((float)(h >> 8) + 0.5f) * (1.0f / 16777216.0f);           // (0, 1)
-            key = -logf(u) / per_priority(p, eps, alpha);                               // > 0: float bits sort like the value
+            // Exp(1) clock from all 32 hash bits: E = -log1p(-u), u in (0, 1).  The draw is decided among the SMALLEST keys,
+            // i.e. u near 0, where a float resolves u to 2^-32 (a 24-bit uniform fed to -log(u) had its winners at u near 1,
+            // spaced 6e-8 apart: ~0.25 slots per level at memory_size 4,096,000 -- ties broken by slot index)
+            const float u = fminf(((float)h + 0.5f) * (1.0f / 4294967296.0f), 0.99999994f);
+            key = -log1pf(-u) / per_priority(p, eps, alpha);                            // > 0: float bits sort like the value
         } else {
             key = -p;
         }

@@ -317,6 +317,32 @@ def test_replay_memory_matches_reference_semantics():
     assert np.array_equal(mem.prioritys_.cpu().numpy(), ref_pr)
 
 
+def test_per_sampling_frequencies_at_a_million_slots():
+    """Weighted sampling without replacement at the size the reference's agents run (memory_size ~ millions): the share of draws
+    per priority class and the absence of a slot-index bias inside a class (the exponential clocks use all 32 hash bits:
+    with a 24-bit uniform the winning keys were quantised to ~4 slots per level and ties went to the lower slot index)."""
+    from rl_ctr_prediction_b200 import replay
+    n, k, draws = 1 << 20, 256, 160
+    mem = replay.Memory(n, 1, DEV, seed=5)
+    td = np.full((n, 1), 0.1, np.float32)
+    td[1::2] = 1.6                                                     # odd slots: the heavy class
+    mem.add(torch.as_tensor(td), torch.zeros(n, 1))
+    w = (np.abs(np.array([0.1, 1.6], np.float64)) + 1e-3) ** 0.6
+    share = w[1] / w.sum()                                             # k << n: draws are ~independent, P(heavy) = w1 / (w0 + w1)
+    heavy, pos = 0, []
+    for _ in range(draws):
+        i = mem.stochastic_sample(k)[0].cpu().numpy()
+        assert len(np.unique(i)) == k
+        heavy += int((i % 2 == 1).sum())
+        pos.append(i[i % 2 == 1])
+    tot = draws * k
+    assert abs(heavy / tot - share) < 5 * np.sqrt(share * (1 - share) / tot), (heavy / tot, share)
+    pos = np.concatenate(pos).astype(np.float64)
+    # slot indices of the heavy draws are uniform over [0, n): mean n/2 within 5 sigma, no pile-up at low indices
+    assert abs(pos.mean() - n / 2) < 5 * n / np.sqrt(12 * len(pos)), pos.mean()
+    assert abs((pos < n / 16).mean() - 1 / 16) < 5 * np.sqrt((1 / 16) * (15 / 16) / len(pos))
+
+
 def test_ddqn_device_sampling():
     """DoubleDQN with device-side replay sampling (RingMemory.device_sampling): distinct in-range indices, stored rows back."""
     from rl_ctr_prediction_b200 import DDQN_model
