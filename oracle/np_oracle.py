@@ -264,13 +264,15 @@ GP_DDQN_DDPG = 0     # src/all_main/main.py:183-271  (k in 2..M, rewards +1/-1, 
 GP_TD3_PER = 1       # src/all_main/hybrid_td3_main_per.py:56-133 (k in 1..M, rewards 1/0, all-model mean)
 
 
-def generate_preds(pctr, w, action, label, variant=GP_DDQN_DDPG, dtype=F32):
+def generate_preds(pctr, w, action, label, variant=GP_DDQN_DDPG, dtype=F32, return_margin=False):
     """Per-sample ensemble prediction, returned weights and reward.
 
     pctr [B,M] frozen-model predictions, w [B,M] continuous action, action [B] int in
     {2..M} (variant 0) / {1..M} (variant 1), label [B] in {0,1}.
     Returns y [B,1], w_out [B,M], reward [B,1].  Ties in `w` are resolved by lower model
     index first (the reference's torch.sort is unstable -- SURVEY N12; avoid ties in tests).
+    return_margin: also |y - base| [B], the distance of the reward's comparison from a tie (two correct
+    fp32 evaluations may disagree on a reward only where this is at rounding level).
     """
     pctr = _as(pctr, dtype)
     w = _as(w, dtype)
@@ -281,6 +283,7 @@ def generate_preds(pctr, w, action, label, variant=GP_DDQN_DDPG, dtype=F32):
     y = np.ones((B,), dtype=dtype)                 # all_main/main.py:185
     r = np.ones((B,), dtype=dtype)                 # :186
     w_out = np.zeros((B, M), dtype=dtype)          # :192
+    margin = np.full((B,), np.inf, dtype=np.float64)
     mean_all = pctr.mean(axis=1, dtype=dtype)
     k_lo = 2 if variant == GP_DDQN_DDPG else 1
     pos, neg = (dtype(1), dtype(-1)) if variant == GP_DDQN_DDPG else (dtype(1), dtype(0))
@@ -312,6 +315,9 @@ def generate_preds(pctr, w, action, label, variant=GP_DDQN_DDPG, dtype=F32):
         clk = label[sel] == 1
         good = np.where(clk, yk >= base, yk <= base)                   # :219-231,254-267
         r[sel] = np.where(good, pos, neg)
+        margin[sel] = np.abs(yk.astype(np.float64) - base.astype(np.float64))
+    if return_margin:
+        return y.reshape(-1, 1), w_out, r.reshape(-1, 1), margin
     return y.reshape(-1, 1), w_out, r.reshape(-1, 1)
 
 

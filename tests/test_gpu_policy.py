@@ -159,10 +159,11 @@ def test_rl_ctr_step_runs_and_is_consistent():
     w = torch.softmax(torch.randn(B, M, device=DEV), dim=1)
     act = torch.randint(2, M + 1, (B, 1), device=DEV)
     yv, wv, rv = ensemble.generate_preds(models, x, act, w, y, DEV, "train", pctr=pctr)
-    yo, wo, ro = O.generate_preds(pctr.cpu().numpy(), w.cpu().numpy(), act.cpu().numpy(), y.cpu().numpy())
+    yo, wo, ro, margin = O.generate_preds(pctr.cpu().numpy(), w.cpu().numpy(), act.cpu().numpy(), y.cpu().numpy(), return_margin=True)
     close(yv, yo)
     close(wv, wo)
-    assert (rv.cpu().numpy() != ro).mean() < 0.01
+    bad = (rv.cpu().numpy() != ro).reshape(-1)
+    assert np.all(margin[bad] <= 2e-7), margin[bad]        # a reward may differ only where y == base to rounding (a tie)
 
 
 @pytest.mark.parametrize("variant", ["literal", "per_sample"])
