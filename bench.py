@@ -88,7 +88,9 @@ def tensor_peak():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this round
-NCU_TRAFFIC = {      # profiles/r2_ncu_top_kernels.md (B=65536, N=10M, D=10); bytes per launch
+NCU_TRAFFIC = {      # profiles/r2f_ncu_top_kernels.md (co-located step) / r2_ncu_top_kernels.md (three tables); B=65536, N=10M, D=10
+    "rlctr_group_fwd[train]": 129.3e6 + 24.0e6, "rlctr_group_rows_adam": 443.0e6 + 232.7e6,
+    "rlctr_rows_catchup[group]": 363.4e6 + 205.4e6,
     "rlctr_rows_adam[FM]": 247.7e6 + 139.0e6, "rlctr_rows_adam[DeepFM]": 297.2e6 + 141.5e6,
     "rlctr_rows_adam[LR]": 95.2e6 + 14.9e6,
     "rlctr_rows_catchup[FM]": 238.9e6 + 122.4e6, "rlctr_rows_catchup[DeepFM]": 238.9e6 + 122.7e6,
@@ -800,7 +802,7 @@ def b200_arm(args):
                 "unit": "TFLOP/s", "frac": achieved / tpeak, "tensor_pipe_issued_TFLOPs": 3 * achieved,
                 "tensor_pipe_issued_frac": 3 * achieved / tpeak, "traffic": NCU_TRAFFIC.get(top),
                 "traffic_note": "DRAM bytes (ncu dram__bytes_read+write) of ALL kernels of this entry point in one step, B=65536 "
-                                "(profiles/r2_ncu_top_kernels.md); achieved / peak are FLOP rates over the same kernels",
+                                "(profiles/r2f_ncu_top_kernels.md); achieved / peak are FLOP rates over the same kernels",
                 "peak_source": tpeak_src,
                 "flops_counted": "algorithmic fp32-equivalent FLOPs; the 3xTF32 split issues 3 tf32 MMAs per product "
                                  "(tensor_pipe_issued_*)", "share_of_step": groups[top] / Kp / step_ms}
