@@ -216,6 +216,18 @@ __device__ __forceinline__ GroupLane group_lane(const GradView& g, int col0) {
     }
     return gl;
 }
+// gradient of one column of a co-located record for one occurrence (the arithmetic every group kernel shares, so that they agree
+// bit for bit): role 1 first-order weight, 2 latent column with the FM term, 3 latent column without, 0 padding
+__device__ __forceinline__ float group_col_grad(int role, float dz, float S, float p, bool has_ex, float ex) {
+    float add = 0.f;
+    if (role == 1) {
+        add = dz;
+    } else if (role != 0) {
+        if (role == 2) add = __fmul_rn(dz, S - p);
+        if (has_ex) add = __fadd_rn(add, ex);
+    }
+    return __fadd_rn(0.f, add);
+}
 __device__ __forceinline__ float4 rowgrad_group(const GradView& g, const GroupLane& gl, uint32_t slot, int col0, const float4& p,
                                                 const TableView& t) {
     const uint32_t b = slot / (uint32_t)g.fields;
@@ -229,15 +241,9 @@ __device__ __forceinline__ float4 rowgrad_group(const GradView& g, const GroupLa
         if (m < 0) continue;
         const float* dzp = g.grp.dz[m];
         const float dz = dzp ? __ldg(dzp + b) : __ldg(srow + g.grp.sums_pitch - RLCTR_GROUP_MAX + m);
-        float add = 0.f;
-        if (gl.role[k] == 1) {
-            add = dz;
-        } else {
-            if (gl.role[k] == 2) add = __fmul_rn(dz, f4get(S, k) - f4get(p, k));
-            const float* ex = g.grp.extra[m];
-            if (ex) add = __fadd_rn(add, __ldg(ex + ((int64_t)b * g.fields + f) * g.grp.dim[m] + (col0 + k - g.grp.emb_col[m])));
-        }
-        f4set(r, k, __fadd_rn(0.f, add));
+        const float* ex = gl.role[k] >= 2 ? g.grp.extra[m] : nullptr;
+        const float exv = ex ? __ldg(ex + ((int64_t)b * g.fields + f) * g.grp.dim[m] + (col0 + k - g.grp.emb_col[m])) : 0.f;
+        f4set(r, k, group_col_grad(gl.role[k], dz, f4get(S, k), f4get(p, k), ex != nullptr, exv));
     }
     return r;
 }
@@ -555,6 +561,120 @@ rows_staged_tile_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t*
         __syncthreads();                                 // everyone is done with bufs[cur] before the next trip refills it
     }
     cp_wait<0>();
+}
+
+// ---- co-located records, TWO lanes per record ------------------------------------------------------------------------------
+// rows_short_kernel<8, 0, GROUP> spends eight lanes (six active) on one record and ~580 warp instructions on four of them: the
+// per-position bookkeeping (run head? long run? slot -> sample, 64-bit addresses, member / role of every column) is repeated by
+// every lane for its one 16-byte chunk, and ncu shows the kernel half issue-bound, half waiting on its own load chain
+// (profiles/r2f_ncu_top_kernels.md).  Here a lane owns CH chunks of the record -- lane h of the pair takes chunks h, h+2, h+4
+// (, h+6), so each load instruction of the pair covers one whole 32-byte sector of each block -- and does the bookkeeping once
+// for 12-16 columns: 16 records per warp instead of 4, no idle lanes, ~2x the records in flight per register.  Same arithmetic
+// as the eight-lane kernel, column by column (group_col_grad, adam_apply4): bit-identical results.
+template <int CH>
+__global__ void __launch_bounds__(256, 2)
+group_rows2_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ sorted_slots, int64_t n,
+                   const __grid_constant__ GradView g, const __grid_constant__ TableView t, const __grid_constant__ AdamView a,
+                   int32_t* __restrict__ long_count, uint32_t* __restrict__ long_list) {
+    const int h = threadIdx.x & 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned pmask = 3u << (lane & ~1);
+    const int chunks = (t.used + 3) >> 2;
+    // per chunk of this lane: packed (member, role) of its four columns, and the dense-tail gradient of its vector member
+    int desc[CH];                        // 4 x (role 2 bits | member 2 bits)
+    const float* exb[CH];                // extra_m - emb_col_m + col0 of the chunk, or NULL
+    int exd[CH];                         // dim_m
+    bool live[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int c = h + 2 * j, col0 = 4 * c;
+        live[j] = c < chunks;
+        desc[j] = 0; exb[j] = nullptr; exd[j] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = col0 + k;
+            const int m = (live[j] && col < 32) ? (int)g.grp.member[col] : -1;
+            const int role = m >= 0 ? (int)g.grp.role[col] : 0;
+            desc[j] |= ((role & 3) | ((m & 3) << 2)) << (4 * k);
+            if (role >= 2 && g.grp.extra[m]) { exb[j] = g.grp.extra[m] + (col0 - g.grp.emb_col[m]); exd[j] = g.grp.dim[m]; }
+        }
+    }
+    const int sc5 = a.stamp_col >= 0 ? (a.stamp_col >> 2) : 0;         // chunk that holds the in-record stamp
+    const int stamp_src = (lane & ~1) + (sc5 & 1), stamp_j = sc5 >> 1;
+    const int step = __ldg(a.step) + 1;
+    const float2 sc = __ldg(&a.sched[step]);
+    const int64_t G = ((int64_t)gridDim.x * blockDim.x) >> 1;
+    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1; k < n; k += G) {
+        const uint32_t id = __ldg(sorted_ids + k);
+        if (id >= (uint64_t)t.n_rows) return;                            // sorted: nothing but sentinels from here on
+        const uint32_t prev = k > 0 ? __ldg(sorted_ids + k - 1) : 0xffffffffu;
+        const uint32_t far = (k + LONG_RUN < n) ? __ldg(sorted_ids + k + LONG_RUN) : 0xffffffffu;
+        uint32_t slot = __ldg(sorted_slots + k);
+        uint32_t nxt = (k + 1 < n) ? __ldg(sorted_ids + k + 1) : 0xffffffffu;
+        if (prev == id) continue;                                        // not a run head
+        if (far == id) {                                                 // heavy hitter: rows_long_kernel
+            if (h == 0) long_list[atomicAdd(long_count, 1)] = (uint32_t)k;
+            continue;
+        }
+        const int64_t off = (int64_t)id * t.pitch + 4 * h;
+        float4 p[CH], m[CH], v[CH], acc[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            p[j] = f4zero(); m[j] = f4zero(); v[j] = f4zero(); acc[j] = f4zero();
+            if (live[j]) { p[j] = ld4(t.data + off + 8 * j); m[j] = ld4(a.m + off + 8 * j); v[j] = ld4(a.v + off + 8 * j); }
+        }
+        int64_t kk = k;
+        bool first = true;
+        while (true) {                                                   // the occurrences of this row, in slot order
+            const uint32_t b = slot / (uint32_t)g.fields;
+            const float* srow = g.sums + (int64_t)b * g.grp.sums_pitch;
+            float dzv[RLCTR_GROUP_MAX];
+#pragma unroll
+            for (int mm = 0; mm < RLCTR_GROUP_MAX; ++mm) {
+                dzv[mm] = 0.f;
+                if (mm < g.grp.n) dzv[mm] = g.grp.dz[mm] ? __ldg(g.grp.dz[mm] + b) : __ldg(srow + g.grp.sums_pitch - RLCTR_GROUP_MAX + mm);
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if (!live[j]) continue;
+                const float4 S = ldg4(srow + 4 * (h + 2 * j));
+                const float* ex = exb[j] ? exb[j] + (int64_t)slot * exd[j] : nullptr;
+                float4 gr;
+#pragma unroll
+                for (int kq = 0; kq < 4; ++kq) {
+                    const int d4 = (desc[j] >> (4 * kq)) & 15, role = d4 & 3, mm = d4 >> 2;
+                    const float dz = mm == 0 ? dzv[0] : (mm == 1 ? dzv[1] : (mm == 2 ? dzv[2] : dzv[3]));
+                    const bool has_ex = ex != nullptr && role >= 2;
+                    const float exv = has_ex ? __ldg(ex + kq) : 0.f;
+                    f4set(gr, kq, group_col_grad(role, dz, f4get(S, kq), f4get(p[j], kq), has_ex, exv));
+                }
+                acc[j] = first ? gr : f4add(acc[j], gr);
+            }
+            first = false;
+            if (nxt != id) break;
+            ++kk;
+            slot = __ldg(sorted_slots + kk);
+            nxt = (kk + 1 < n) ? __ldg(sorted_ids + kk + 1) : 0xffffffffu;
+        }
+        int stamp_in = step - 1;
+        if (a.stamp_col >= 0) {
+            float4 pc = p[0];
+#pragma unroll
+            for (int j = 1; j < CH; ++j)
+                if (stamp_j == j) pc = p[j];
+            stamp_in = __shfl_sync(pmask, __float_as_int(f4get(pc, a.stamp_col & 3)), stamp_src);
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            if (!live[j]) continue;
+            if (a.stamp_col >= 0 && stamp_in < step - 1) adam_replay4(p[j], m[j], v[j], stamp_in, step - 1, a.sched, a.h);
+            adam_apply4(p[j], m[j], v[j], acc[j], sc, a.h);
+            embed_stamp(p[j], 4 * (h + 2 * j), a, step);
+            st4(t.data + off + 8 * j, p[j]);
+            st4(a.m + off + 8 * j, m[j]);
+            st4(a.v + off + 8 * j, v[j]);
+        }
+    }
 }
 
 // block per long run: NSUB lane-groups stride the run, fixed-shape tree in shared memory
@@ -1452,6 +1572,23 @@ extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t*
     RowsWs w{reinterpret_cast<int32_t*>(ws), reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 16)};
     RLCTR_CUDA(cudaMemsetAsync(w.long_count, 0, sizeof(int32_t), st));
     const int lpr = rlctr_lanes_per_row(t.rs);
+    // RLCTR_GROUP_ROWS2=0: the eight-lanes-per-record kernel.  Both take ~250 us for 936 K records at B = 65536 (read per call: the
+    // tests switch it): 2.5x fewer instructions and 1.7x more records in flight buy nothing, because the update already runs at the
+    // memory system's random-access rate -- 3 lines read + 3 written per record + the dense-tail rows = ~27 G line operations/s
+    const char* r2e = getenv("RLCTR_GROUP_ROWS2");
+    const int rows2_env = r2e ? atoi(r2e) : 1;
+    if (rows2_env && !opt->stamp && (t.used + 3) / 4 <= 8 && lpr == 8) {
+        // two lanes per record on a persistent grid (2 resident blocks per SM), then the heavy hitters
+        int64_t want = capped_blocks((2 * n + 255) / 256, world);
+        const int64_t cap = (int64_t)RLCTR_SMS * 2 * (rows_grid_env() > 0 ? rows_grid_env() : 64);
+        const unsigned b2 = (unsigned)(want < cap ? want : cap);
+        if ((t.used + 3) / 4 <= 6) group_rows2_kernel<3><<<b2, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, w.long_count, w.long_list);
+        else group_rows2_kernel<4><<<b2, 256, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, w.long_count, w.long_list);
+        rows_long_kernel<8, 0, true, 512><<<RLCTR_SMS, 512, 0, st>>>(sorted_ids, sorted_slots, n, g, t, a, nullptr, w.long_count, w.long_list);
+        RLCTR_COUNT_LAUNCH(1);
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
     unsigned blocks = capped_blocks((n * lpr + 255) / 256, world);
     if (rows_grid_env() > 0 && blocks > (unsigned)(RLCTR_SMS * 5 * rows_grid_env())) blocks = RLCTR_SMS * 5 * rows_grid_env();
     if (lpr == 4) {

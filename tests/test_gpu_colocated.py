@@ -61,8 +61,10 @@ def _train_group(models, batches, mode="lazy"):
     return group, np.array(losses)
 
 
+@pytest.mark.parametrize("rows2", ["1", "0"])
 @pytest.mark.parametrize("zipf", [False, True])
-def test_group_equals_standalone_models(zipf):
+def test_group_equals_standalone_models(zipf, rows2, monkeypatch):
+    monkeypatch.setenv("RLCTR_GROUP_ROWS2", rows2)       # two lanes per record (default) / eight lanes per record
     N, B, steps = 3000, 512, 6
     sep = _models(N)
     grp_members = [copy.deepcopy(m) for m in sep]
