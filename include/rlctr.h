@@ -300,6 +300,15 @@ int rlctr_route_ids(const int64_t* ids, int64_t n, int32_t world, int32_t rank, 
                     rlctr_stream_t stream);
 int rlctr_sort_routed(const uint32_t* keys, const uint32_t* vals, int64_t n_in, int64_t n_rows_local, uint32_t* sorted_rows,
                       uint32_t* sorted_slots, void* ws, size_t ws_bytes, rlctr_stream_t stream);
+/* The same sort with the RECEIVE POSITION (index into keys / vals) as the value: sorted_pos[k] = r, the global slot is vals[r].
+ * With it the gradient-side rows can travel in the routed order too: rlctr_push_rows_routed writes row `slot` of src[n, width]
+ * (width even) to peer_recv[owner] + (rank * cap + bucket position) * width -- the position its (row, slot) pair got from
+ * rlctr_route_ids, whose workspace `route_ws` (same ids, same n) still holds the bucket order -- so consecutive threads write
+ * consecutive bytes over NVLink and an owner's receive buffer is [world * cap, width], dense.  ws (sort): rlctr_sort_ws_bytes. */
+int rlctr_sort_routed_pos(const uint32_t* keys, int64_t n_in, int64_t n_rows_local, uint32_t* sorted_rows, uint32_t* sorted_pos,
+                          void* ws, size_t ws_bytes, rlctr_stream_t stream);
+int rlctr_push_rows_routed(const void* route_ws, int64_t n, int32_t world, int32_t rank, int64_t cap, const float* src,
+                           int32_t width, void* const* peer_recv, rlctr_stream_t stream);
 int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n,
                     const rlctr_rowgrad* grad, const rlctr_table* table, const rlctr_adam* opt,
                     void* ws, size_t ws_bytes, rlctr_stream_t stream);
@@ -345,10 +354,14 @@ int rlctr_group_fwd(const int64_t* ids, const rlctr_table* table, const rlctr_me
  * reduced over the occurrences of an id in slot order, then ONE Adam step on the record.  b = slot / fields: for a row-sharded
  * table the slots are GLOBAL (src rank * n_per_rank + slot), `sums` is the all-gathered [world * B, sums_pitch] array, extra_m the
  * owner's receive buffer of rlctr_push_rows, and `world` sizes the grid for the owned ~1/world of the sorted view (the rest are
- * sentinels).  ws: rlctr_rows_ws_bytes(n). */
+ * sentinels).  ws: rlctr_rows_ws_bytes(n).
+ * slot_of (optional, the routed exchange): sorted_slots then holds RECEIVE positions r of the owner's routing buffers
+ * (rlctr_sort_routed_pos); the global slot is slot_of[r] (the `vals` rlctr_route_ids delivered) and extra_m is indexed by r (the rows
+ * rlctr_push_rows_routed delivered): dense per-source segments instead of a [world * n, dim] buffer of which 1/world is used. */
 int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
                           const rlctr_adam* opt, const rlctr_member* members, int32_t n_members, const float* sums,
-                          int32_t sums_pitch, int32_t fields, int32_t world, void* ws, size_t ws_bytes, rlctr_stream_t stream);
+                          int32_t sums_pitch, int32_t fields, int32_t world, const uint32_t* slot_of, void* ws, size_t ws_bytes,
+                          rlctr_stream_t stream);
 
 /* Same reduction, but the sums are stored into a dense [n_rows,row_stride] gradient
  * (rows of untouched ids are not written): the literal embedding_dense_backward. */

@@ -257,8 +257,8 @@ class ColocatedCTR(Model._TableModel):
         ws_bytes = lib.rlctr_rows_ws_bytes(stash.n)
         ws = self._rows_ws(ws_bytes)
         _lib.call("rlctr_group_rows_adam", lib.rlctr_group_rows_adam, _lib.ptr(stash.sorted_ids), _lib.ptr(stash.sorted_slots),
-                  stash.n, C.byref(t), C.byref(a), arr, len(self.members), _lib.ptr(stash.sums), 0, stash.fields, 1, _lib.ptr(ws),
-                  ws_bytes, st, key="rlctr_group_rows_adam", meta=self._meta(stash.n // stash.fields, stash.fields))
+                  stash.n, C.byref(t), C.byref(a), arr, len(self.members), _lib.ptr(stash.sums), 0, stash.fields, 1, None,
+                  _lib.ptr(ws), ws_bytes, st, key="rlctr_group_rows_adam", meta=self._meta(stash.n // stash.fields, stash.fields))
 
 
 def colocate(models) -> ColocatedCTR:

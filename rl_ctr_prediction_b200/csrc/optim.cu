@@ -67,6 +67,8 @@ struct GroupCols {
     const float* dz[RLCTR_GROUP_MAX];        // dL/dlogit of member m, [B]
     const float* extra[RLCTR_GROUP_MAX];     // dense-tail gradient on member m's latent columns, [B, fields * dim_m], or NULL
     int emb_col[RLCTR_GROUP_MAX], dim[RLCTR_GROUP_MAX];
+    const uint32_t* slot_of;                 // non-NULL (routed exchange): sorted_slots holds RECEIVE positions r; the global slot
+                                             // (-> sample, for S and dL/dlogit) is slot_of[r], the dense-tail row is extra_m[r]
     int sums_pitch;                          // floats between the sums rows; dz[m] == NULL: dL/dlogit of member m rides in column
                                              // sums_pitch - RLCTR_GROUP_MAX + m of the sample's sums row
     signed char member[32];                  // column -> member, -1: padding / stamp
@@ -230,8 +232,9 @@ __device__ __forceinline__ float group_col_grad(int role, float dz, float S, flo
 }
 __device__ __forceinline__ float4 rowgrad_group(const GradView& g, const GroupLane& gl, uint32_t slot, int col0, const float4& p,
                                                 const TableView& t) {
+    const uint32_t erow = slot;                          // row of the dense-tail gradients: the slot, or the receive position
+    if (g.grp.slot_of) slot = __ldg(g.grp.slot_of + slot);
     const uint32_t b = slot / (uint32_t)g.fields;
-    const uint32_t f = slot - b * (uint32_t)g.fields;
     const float* srow = g.sums + (int64_t)b * g.grp.sums_pitch;
     const float4 S = ldg4(srow + col0);
     float4 r = f4zero();
@@ -242,7 +245,7 @@ __device__ __forceinline__ float4 rowgrad_group(const GradView& g, const GroupLa
         const float* dzp = g.grp.dz[m];
         const float dz = dzp ? __ldg(dzp + b) : __ldg(srow + g.grp.sums_pitch - RLCTR_GROUP_MAX + m);
         const float* ex = gl.role[k] >= 2 ? g.grp.extra[m] : nullptr;
-        const float exv = ex ? __ldg(ex + ((int64_t)b * g.fields + f) * g.grp.dim[m] + (col0 + k - g.grp.emb_col[m])) : 0.f;
+        const float exv = ex ? __ldg(ex + (int64_t)erow * g.grp.dim[m] + (col0 + k - g.grp.emb_col[m])) : 0.f;
         f4set(r, k, group_col_grad(gl.role[k], dz, f4get(S, k), f4get(p, k), ex != nullptr, exv));
     }
     return r;
@@ -626,6 +629,8 @@ group_rows2_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
         int64_t kk = k;
         bool first = true;
         while (true) {                                                   // the occurrences of this row, in slot order
+            const uint32_t erow = slot;                                  // dense-tail row: the slot, or the receive position
+            if (g.grp.slot_of) slot = __ldg(g.grp.slot_of + slot);
             const uint32_t b = slot / (uint32_t)g.fields;
             const float* srow = g.sums + (int64_t)b * g.grp.sums_pitch;
             float dzv[RLCTR_GROUP_MAX];
@@ -638,7 +643,7 @@ group_rows2_kernel(const uint32_t* __restrict__ sorted_ids, const uint32_t* __re
             for (int j = 0; j < CH; ++j) {
                 if (!live[j]) continue;
                 const float4 S = ldg4(srow + 4 * (h + 2 * j));
-                const float* ex = exb[j] ? exb[j] + (int64_t)slot * exd[j] : nullptr;
+                const float* ex = exb[j] ? exb[j] + (int64_t)erow * exd[j] : nullptr;
                 float4 gr;
 #pragma unroll
                 for (int kq = 0; kq < 4; ++kq) {
@@ -1531,8 +1536,8 @@ extern "C" int rlctr_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorte
 
 extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t* sorted_slots, int64_t n, const rlctr_table* table,
                                      const rlctr_adam* opt, const rlctr_member* members, int32_t n_members, const float* sums,
-                                     int32_t sums_pitch, int32_t fields, int32_t world, void* ws, size_t ws_bytes,
-                                     rlctr_stream_t stream) {
+                                     int32_t sums_pitch, int32_t fields, int32_t world, const uint32_t* slot_of, void* ws,
+                                     size_t ws_bytes, rlctr_stream_t stream) {
     if (!sorted_ids || !sorted_slots || !table || !table->data || !opt || !opt->exp_avg || !opt->exp_avg_sq || !opt->sched ||
         !opt->step || !members || !sums || n < 0 || fields <= 0)
         return RLCTR_EINVAL;
@@ -1551,6 +1556,7 @@ extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t*
     g.sums = sums; g.fields = fields; g.world = 0;
     g.grp.n = n_members;
     g.grp.sums_pitch = sums_pitch;
+    g.grp.slot_of = slot_of;
     for (int col = 0; col < 32; ++col) { g.grp.member[col] = -1; g.grp.role[col] = 0; }
     for (int m = 0; m < n_members; ++m) {
         const rlctr_member& mm = members[m];

@@ -250,6 +250,80 @@ extern "C" int rlctr_route_ids(const int64_t* ids, int64_t n, int32_t world, int
     return RLCTR_OK;
 }
 
+namespace rlctr {
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)i;
+}
+// rows of `src` (width floats, even) in the bucket order rlctr_route_ids computed: row sslots[i] goes to owner skeys[i] at
+// recv[owner][(rank * cap + i - starts[owner]) * width]: consecutive threads write consecutive bytes of an owner's segment
+__global__ void __launch_bounds__(256)
+push_routed_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ sslots, const int64_t* __restrict__ starts,
+                   int64_t n, int world, int64_t seg0, int64_t cap, const float* __restrict__ src, int width,
+                   const __grid_constant__ ShardView sv) {
+    const int per = width >> 1;
+    const int64_t total = n * per;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / per;
+        const int j = (int)(t - i * per);
+        const uint32_t o = __ldg(skeys + i);
+        if (o >= (uint32_t)world) continue;
+        const int64_t pos = i - starts[o];
+        if (pos >= cap) continue;                                   // overflow: flagged by rlctr_route_ids
+        const uint32_t slot = __ldg(sslots + i);
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + (int64_t)slot * width) + j);
+        float* dst = const_cast<float*>(sv.peers[o]) + (seg0 + pos) * width;
+        reinterpret_cast<float2*>(dst)[j] = v;
+    }
+}
+}  // namespace rlctr
+
+extern "C" int rlctr_push_rows_routed(const void* route_ws, int64_t n, int32_t world, int32_t rank, int64_t cap, const float* src,
+                                      int32_t width, void* const* peer_recv, rlctr_stream_t stream) {
+    if (!route_ws || !src || !peer_recv || n < 0 || width <= 0 || cap <= 0) return RLCTR_EINVAL;
+    if (world != 2 && world != 4 && world != 8) return RLCTR_EUNSUPPORTED;
+    if (rank < 0 || rank >= world || width % 2 != 0) return RLCTR_EINVAL;
+    if ((((uintptr_t)src) & 7u) != 0) return RLCTR_EALIGN;
+    ShardView sv;
+    sv.shift = 0; sv.mask = world - 1;
+    for (int r = 0; r < RLCTR_MAX_WORLD; ++r) sv.peers[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_recv[r] || (((uintptr_t)peer_recv[r]) & 7u) != 0) return RLCTR_EINVAL;
+        sv.peers[r] = reinterpret_cast<const float*>(peer_recv[r]);
+    }
+    if (n == 0) return RLCTR_OK;
+    // the layout rlctr_route_ids gave its workspace: keys | vals | sorted owner keys | sorted slots | bucket starts
+    const size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const char* base = reinterpret_cast<const char*>(route_ws);
+    const uint32_t* skeys = reinterpret_cast<const uint32_t*>(base + 2 * arr);
+    const uint32_t* sslots = reinterpret_cast<const uint32_t*>(base + 3 * arr);
+    const int64_t* starts = reinterpret_cast<const int64_t*>(base + 4 * arr);
+    int64_t blocks = (n * (width / 2) + 255) / 256;
+    const int grid = (int)(blocks < RLCTR_SMS * 16 ? blocks : RLCTR_SMS * 16);
+    push_routed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(skeys, sslots, starts, n, world, (int64_t)rank * cap, cap, src, width, sv);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" int rlctr_sort_routed_pos(const uint32_t* keys, int64_t n_in, int64_t n_rows_local, uint32_t* sorted_rows,
+                                     uint32_t* sorted_pos, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
+    if (!keys || !sorted_rows || !sorted_pos || !ws || n_in < 0 || n_rows_local <= 0) return RLCTR_EINVAL;
+    if (n_in == 0) return RLCTR_OK;
+    const size_t arr = ((size_t)n_in * sizeof(uint32_t) + 255) & ~(size_t)255;
+    if (ws_bytes < arr + 256) return RLCTR_EWORKSPACE;
+    uint32_t* pos = reinterpret_cast<uint32_t*>(ws);
+    int64_t blocks = (n_in + 255) / 256;
+    iota_kernel<<<(int)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, (cudaStream_t)stream>>>(pos, n_in);
+    RLCTR_LAUNCH_CHECK();
+    int bits = 1;
+    while (bits < 32 && ((int64_t)1 << bits) <= n_rows_local) ++bits;               // the sentinel (all ones) sorts last
+    size_t temp_bytes = ws_bytes - arr;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(static_cast<void*>(reinterpret_cast<char*>(ws) + arr), temp_bytes, keys, sorted_rows,
+                                                    static_cast<const uint32_t*>(pos), sorted_pos, n_in, 0, bits, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    RLCTR_COUNT_LAUNCH(2 + (bits + 7) / 8);
+    return RLCTR_OK;
+}
+
 extern "C" int rlctr_sort_routed(const uint32_t* keys, const uint32_t* vals, int64_t n_in, int64_t n_rows_local,
                                  uint32_t* sorted_rows, uint32_t* sorted_slots, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
     if (!keys || !vals || !sorted_rows || !sorted_slots || !ws || n_in < 0 || n_rows_local <= 0) return RLCTR_EINVAL;

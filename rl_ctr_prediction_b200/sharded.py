@@ -472,6 +472,30 @@ class ShardedCTR(nn.Module):
         return loss.reshape(())
 
 
+def routed_view_pos(x, n_rows, group):
+    """The routed sorted view with RECEIVE POSITIONS as values (rlctr_sort_routed_pos), plus what the routed gradient push needs:
+    {"rows", "pos", "n_all", "cap", "route_ws" (bucket order of this rank's ids), "slot_of" (global slot at every receive position)}."""
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev, n, st = x.device, x.numel(), _lib.stream()
+    rb = _route_buffers(n, world, dev, group)
+    cap = rb["cap"]
+    ws_bytes = lib.rlctr_route_ws_bytes(n, world)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("rlctr_route_ids", lib.rlctr_route_ids, _lib.ptr(x), n, world, rank, n_rows, cap, rb["kp"], rb["vp"],
+              _lib.ptr(rb["overflow"]), _lib.ptr(ws), ws_bytes, st, meta={"n": n, "world": world, "cap": cap})
+    rb["keys"].barrier()                                         # every source's segment of my receive buffer is complete
+    n_all = world * cap
+    srows = torch.empty(n_all, dtype=torch.int32, device=dev)
+    spos = torch.empty(n_all, dtype=torch.int32, device=dev)
+    n_local = max(shard_rows(n_rows, world, rank), 1)
+    ws2_bytes = lib.rlctr_sort_ws_bytes(n_all, n_local)
+    ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("rlctr_sort_routed_pos", lib.rlctr_sort_routed_pos, _lib.ptr(rb["keys"].local), n_all, n_local, _lib.ptr(srows),
+              _lib.ptr(spos), _lib.ptr(ws2), ws2_bytes, st, key="rlctr_sort_ids", meta={"n": n_all})
+    return {"rows": srows, "pos": spos, "n_all": n_all, "cap": cap, "route_ws": ws, "slot_of": rb["vals"].local}
+
+
 # ---------------------------------------------------------------------------------------------------
 class _MemberGeom:
     """Stand-in carrying the stand-alone geometry of a member kind for colocated._layout."""
@@ -602,8 +626,8 @@ class ShardedGroup(nn.Module):
             b = {"sums": torch.zeros(B, self.SUMS_PITCH, dtype=torch.float32, device=dev),
                  "sums_all": torch.zeros(G * B, self.SUMS_PITCH, dtype=torch.float32, device=dev), "recv": {}}
             for i, k in enumerate(self.kinds):
-                if k == "DeepFM" and G > 1:
-                    pm = PeerMemory(G * B * F * D, torch.float32, dev, self.group)
+                if k == "DeepFM" and G > 1:                   # dense per-source segments: [G * cap, D] (routed push)
+                    pm = PeerMemory(G * route_capacity(B * F, G) * D, torch.float32, dev, self.group)
                     pm.local.zero_()
                     b["recv"][i] = (pm, (C.c_void_p * 8)(*[int(p) for p in pm.ptrs]))
             self._buf[B] = b
@@ -662,7 +686,12 @@ class ShardedGroup(nn.Module):
         yi = y if y.dtype == torch.int64 else None
         yf = None if yi is not None else y.float()
         buf = self._exchange(B, F)
-        srows, sslots, n_all = shared_sorted_view(x, self.feature_nums, self.group)
+        view = None
+        if G > 1:                                             # routed exchange: positions in the owner's receive buffers
+            view = routed_view_pos(x, self.feature_nums, self.group)
+            srows, sslots, n_all = view["rows"], view["pos"], view["n_all"]
+        else:
+            srows, sslots, n_all = shared_sorted_view(x, self.feature_nums, self.group)
         if opt.lazy and opt.dirty:
             t, a = table_struct(self.table.data, self._geom), opt.struct()
             _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(srows), n_all, C.byref(t), C.byref(a), st,
@@ -709,15 +738,17 @@ class ShardedGroup(nn.Module):
                 o += p.numel()
             dist.all_gather_into_tensor(buf["sums_all"], sums, group=self.group)
             sums_all = buf["sums_all"]
-            for i, (pm, ptrs) in buf["recv"].items():          # per-occurrence rows: posted writes into the owners' memory
-                n = B * F
-                _lib.call("rlctr_push_rows", lib.rlctr_push_rows, _lib.ptr(x), n, G, self.rank, self.feature_nums,
-                          _lib.ptr(extras[i]), self.latent_dims, ptrs, st, meta={"n": n, "width": self.latent_dims})
+            for i, (pm, ptrs) in buf["recv"].items():          # per-occurrence rows, in the routed bucket order: coalesced posted
+                n = B * F                                      # writes into dense per-source segments of the owners' memory
+                _lib.call("rlctr_push_rows_routed", lib.rlctr_push_rows_routed, _lib.ptr(view["route_ws"]), n, G, self.rank,
+                          view["cap"], _lib.ptr(extras[i]), self.latent_dims, ptrs, st, key="rlctr_push_rows",
+                          meta={"n": n, "width": self.latent_dims})
                 extras[i] = pm.local
         else:
             sums_all = sums
         self.barrier()                                        # B2: every rank's gradient-side buffers are complete
-        self._stash = {"sorted_ids": srows, "sorted_slots": sslots, "n": n_all, "fields": F, "sums": sums_all, "extra": extras}
+        self._stash = {"sorted_ids": srows, "sorted_slots": sslots, "n": n_all, "fields": F, "sums": sums_all, "extra": extras,
+                       "slot_of": view["slot_of"] if view is not None else None}
         optimizer.step()
         return losses
 
@@ -736,4 +767,4 @@ class ShardedGroup(nn.Module):
         ws = self._rows_ws(ws_bytes)
         _lib.call("rlctr_group_rows_adam", lib.rlctr_group_rows_adam, _lib.ptr(stash["sorted_ids"]), _lib.ptr(stash["sorted_slots"]),
                   n, C.byref(t), C.byref(a), arr, len(self.kinds), _lib.ptr(stash["sums"]), self.SUMS_PITCH, F, self.world,
-                  _lib.ptr(ws), ws_bytes, st, key="rlctr_group_rows_adam[ShardedGroup]", meta=self._meta(n // F, F))
+                  _lib.ptr(stash["slot_of"]), _lib.ptr(ws), ws_bytes, st, key="rlctr_group_rows_adam[ShardedGroup]", meta=self._meta(n // F, F))

@@ -207,3 +207,53 @@ def test_sharded_group_world1_equals_colocated():
         for m in cg.members:
             m.eval()
         assert torch.equal(sg(x), cg(x))
+
+
+def test_group_update_with_receive_positions():
+    """The routed exchange of the row-sharded group (rlctr_group_rows_adam(slot_of=...)): the sorted view carries RECEIVE
+    positions r, the global slot is slot_of[r] and the dense-tail rows are stored by r.  Emulated on one GPU with a random
+    permutation as the receive order: same bits as the plain update."""
+    import ctypes as C
+    from rl_ctr_prediction_b200 import _lib, colocated, optim, tables
+    lib = _lib.load()
+    N, B, steps = 3000, 256, 3
+    a = _models(N, seed=31)
+    b = [copy.deepcopy(m) for m in a]
+    ga, gb = colocated.colocate(a), colocated.colocate(b)
+    oa = optim.Adam(ga.parameters(), lr=1e-3, weight_decay=1e-5)
+    ob = optim.Adam(gb.parameters(), lr=1e-3, weight_decay=1e-5)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+
+    def permuted_update(stash, opt_state, st):
+        n = stash.n
+        slot_of = torch.randperm(n, generator=gen, device=DEV).to(torch.int32)          # receive position -> slot
+        inv = torch.empty(n, dtype=torch.int64, device=DEV)
+        inv[slot_of.long()] = torch.arange(n, device=DEV)
+        spos = inv[stash.sorted_slots.long()].to(torch.int32)                             # the sorted view, as positions
+        arr = (_lib.Member * len(gb.members))()
+        keep = []
+        for i, (m, (lin, emb, dim)) in enumerate(zip(gb.members, gb._cols)):
+            s = arr[i]
+            s.lin_col, s.emb_col, s.dim = lin, emb, dim
+            s.flags = _lib.RLCTR_FM_TERM if m._fm_term else 0
+            s.dlogit = _lib.ptr(stash.dlogit[i])
+            if stash.extra[i] is not None:
+                ex = stash.extra[i].reshape(n, dim)[slot_of.long()].contiguous()          # dense-tail rows in receive order
+                keep.append(ex)
+                s.extra = _lib.ptr(ex)
+        t, ad = tables.table_struct(gb.table.data, gb._geom), opt_state.struct()
+        wsb = lib.rlctr_rows_ws_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        _lib.check(lib.rlctr_group_rows_adam(_lib.ptr(stash.sorted_ids), _lib.ptr(spos), n, C.byref(t), C.byref(ad), arr,
+                                             len(gb.members), _lib.ptr(stash.sums), 0, stash.fields, 1, _lib.ptr(slot_of), _lib.ptr(ws),
+                                             wsb, st), "rlctr_group_rows_adam")
+        torch.cuda.synchronize()
+
+    gb._group_update = permuted_update
+    for x, y in _batches(N, B, steps, seed=12, zipf=True):
+        la = ga.train_step(x, y, oa)
+        lb = gb.train_step(x, y, ob)
+        assert torch.equal(la, lb)
+    ga.flush()
+    gb.flush()
+    assert torch.equal(ga.table.data, gb.table.data)
