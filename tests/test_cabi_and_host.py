@@ -61,12 +61,56 @@ def test_struct_layouts_match_header(tmp_path):
     assert C.sizeof(_lib.Table) == 104 and C.sizeof(_lib.Adam) == 88 and C.sizeof(_lib.RowGrad) == 304
 
 
+def test_member_struct_layout_matches_header(tmp_path):
+    """struct rlctr_member (co-located records) as gcc lays it out == the ctypes mirror."""
+    import subprocess
+    from rl_ctr_prediction_b200 import _lib
+    src = tmp_path / "member.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rlctr.h"\nint main(void){printf("%zu %zu %zu %zu %zu %d\\n",'
+                   'sizeof(rlctr_member), offsetof(rlctr_member,bias), offsetof(rlctr_member,pctr_stride),'
+                   'offsetof(rlctr_member,rows_pitch), offsetof(rlctr_member,extra), RLCTR_GROUP_MAX);return 0;}\n')
+    exe = tmp_path / "member"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.Member), _lib.Member.bias.offset, _lib.Member.pctr_stride.offset, _lib.Member.rows_pitch.offset,
+            _lib.Member.extra.offset, _lib.RLCTR_GROUP_MAX]
+    assert got == want, (got, want)
+
+
+def test_colocated_layout_rules():
+    """colocated._layout: vector members keep their stand-alone chunk alignment, scalar members take padding columns, the stamp
+    gets a free column of the last active chunk, and the joint row stays within one 128-byte line."""
+    from rl_ctr_prediction_b200 import colocated, tables, _lib
+
+    class M:
+        def __init__(self, g):
+            self._geom = g
+    lr, fm = (lambda: M(tables.Geometry.lr(100))), (lambda d=10: M(tables.Geometry.fm(100, d)))
+    cols, used = colocated._layout([lr(), fm(), fm()])                      # LR + FM + DeepFM, D = 10
+    assert cols == [(11, 0, 0), (0, 1, 10), (12, 13, 10)] and used == 23    # LR's weight in FM's padding column, stamp at 23
+    cols, used = colocated._layout([fm(), lr(), lr(), fm()])
+    assert cols == [(0, 1, 10), (11, 0, 0), (23, 0, 0), (12, 13, 10)] and used == 25      # no free column left: a dummy, then the stamp
+    cols, used = colocated._layout([fm(11), lr()])                          # a full 12-float block: LR opens a new chunk
+    assert cols == [(0, 1, 11), (12, 0, 0)] and used == 13
+    for c, _ in [colocated._layout([fm(), fm()]), colocated._layout([lr()])]:
+        assert all(e % 4 == 1 for _, e, d in c if d)                        # latent columns start at 1 mod 4, as stand-alone
+    with pytest.raises(_lib.RlctrError):
+        colocated._layout([fm(), fm(), fm()])                               # 36 + stamp floats: wider than one line
+    with pytest.raises(_lib.RlctrError):
+        colocated._layout([M(tables.Geometry.ffm(100, 15, 10))])
+
+
 def test_argument_errors_need_no_gpu(lib):
     # argument validation happens before any CUDA call
     assert lib.rlctr_embed_fwd(None, None, None, None, None, 1, None, None, 0, 4, 15, 1, None) == -1
     assert lib.rlctr_generate_preds(None, None, None, None, None, None, None, 4, 3, 0, None) == -1
     assert lib.rlctr_sort_ids(None, 1, 1, None, None, None, 0, None) == -1
     assert lib.rlctr_rows_ws_bytes(1000) >= 16
+    assert lib.rlctr_group_fwd(None, None, None, 0, None, 0, 4, 15, None) != 0
+    assert lib.rlctr_group_rows_adam(None, None, 4, None, None, None, 1, None, 0, 15, 1, None, None, 0, None) == -1
+    assert lib.rlctr_push_rows_routed(None, 4, 2, 0, 8, None, 10, None, None) == -1
+    assert lib.rlctr_sort_routed_pos(None, 4, 10, None, None, None, 0, None) == -1
 
 
 @pytest.mark.parametrize("name", ["LR", "FM", "FFM", "DeepFM"])
