@@ -120,14 +120,16 @@ class DoubleDQN:
         self.eval_net.train()
         rdev = self.device if self.device_rng else None
         random_seeds = torch.rand(len(states), 1, device=rdev).to(self.device)
-        max_action = torch.argsort(-action_values)[:, 0] + 2
+        # argsort(-Q)[:, 0] (:154) is the arg max of the row; a full sort of every row (0.7 ms at a 1M batch) is not needed for it
+        # (rows with exactly tied Q-values have no defined winner in the reference either: its sort is unstable)
+        max_action = torch.argmax(action_values, dim=1) + 2
         random_action = torch.randint(low=2, high=self.action_nums + 2, size=[len(states), 1], device=rdev).to(self.device)
         return torch.where(random_seeds >= exploration_rate, max_action.view(-1, 1), random_action)
 
     def choose_best_action(self, states):
         """:164-172 (leaves the net in eval mode, like the reference)."""
         action_values = self._q_eval_mode(states)
-        return (torch.argsort(-action_values)[:, 0] + 2).view(-1, 1)
+        return (torch.argmax(action_values, dim=1) + 2).view(-1, 1)
 
     def soft_update(self, net, net_target):
         with torch.no_grad():

@@ -593,31 +593,61 @@ static int vec_of(const float* p, int64_t pitch) {
 // modules in float64: tests/test_gpu_parity_scale.py).  Those steps run on replay batches of 32-256 rows -- a few MFLOP, where
 // tensor cores buy nothing -- so small batches take this kernel.  64 x 64 tile, 256 threads, 4 x 4 outputs per thread.
 namespace simt {
-constexpr int TM = 64, TN = 64, TK = 16;
-__global__ void __launch_bounds__(256)
+constexpr int TK = 16;
+// TM x TN output tile, (TM/4) x (TN/4) threads with a 4 x 4 micro-tile each; every output element is ONE fma chain over k in
+// ascending order whatever the tile shape, so the tile only decides how many blocks there are.  The learn steps of the policy
+// nets are 256 x 300 x 300 problems: 64 x 64 tiles give 20 blocks on 148 SMs (48 us per GEMM, 3 ms of the C5 step over its 63
+// launches); 32 x 32 tiles give 80.
+template <int TM, int TN>
+__global__ void __launch_bounds__((TM / 4) * (TN / 4))
 sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbn, int64_t sbk,
              float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int M, int N, int K, int relu) {
+    constexpr int NT = (TM / 4) * (TN / 4);
+    constexpr int LA = TK * TM / NT, LB = TK * TN / NT;       // operand elements each thread fetches per k-tile
     __shared__ float As[TK][TM + 4], Bs[TK][TN + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x % (TN / 4), ty = threadIdx.x / (TN / 4);
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += TK) {
-        for (int e = threadIdx.x; e < TK * TM; e += 256) {
+    // the next k-tile travels global -> registers while the current one is multiplied out of shared memory (a small problem puts
+    // one block of two warps on an SM: nothing else would hide the load latency)
+    float ra[LA], rb[LB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < LA; ++u) {
+            const int e = threadIdx.x + u * NT;
             // the faster-varying index follows the operand's unit stride so that the global loads coalesce
             const int kk = sak == 1 ? e % TK : e / TM, mm = sak == 1 ? e / TK : e % TM;
             const int m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < M && k < K) ? __ldg(A + (int64_t)m * sam + (int64_t)k * sak) : 0.f;
+            ra[u] = (m < M && k < K) ? __ldg(A + (int64_t)m * sam + (int64_t)k * sak) : 0.f;
         }
-        for (int e = threadIdx.x; e < TK * TN; e += 256) {
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+            const int e = threadIdx.x + u * NT;
             const int kk = sbk == 1 ? e % TK : e / TN, nn = sbk == 1 ? e / TK : e % TN;
             const int n = n0 + nn, k = k0 + kk;
-            Bs[kk][nn] = (n < N && k < K) ? __ldg(B + (int64_t)n * sbn + (int64_t)k * sbk) : 0.f;
+            rb[u] = (n < N && k < K) ? __ldg(B + (int64_t)n * sbn + (int64_t)k * sbk) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+        for (int u = 0; u < LA; ++u) {
+            const int e = threadIdx.x + u * NT;
+            const int kk = sak == 1 ? e % TK : e / TM, mm = sak == 1 ? e / TK : e % TM;
+            As[kk][mm] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+            const int e = threadIdx.x + u * NT;
+            const int kk = sbk == 1 ? e % TK : e / TN, nn = sbk == 1 ? e / TK : e % TN;
+            Bs[kk][nn] = rb[u];
         }
         __syncthreads();
+        if (k0 + TK < K) fetch(k0 + TK);
 #pragma unroll
         for (int kk = 0; kk < TK; ++kk) {
             float a[4], b[4];
@@ -648,8 +678,14 @@ sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float*
 }
 static int gemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int64_t ldc,
                 const float* bias, int M, int N, int K, int relu, cudaStream_t st) {
-    dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-    sgemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu);
+    const int64_t big = (int64_t)((N + 63) / 64) * ((M + 63) / 64);
+    if (big >= 2 * RLCTR_SMS) {
+        dim3 grid((N + 63) / 64, (M + 63) / 64);
+        sgemm_kernel<64, 64><<<grid, 256, 0, st>>>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu);
+    } else {
+        dim3 grid((N + 31) / 32, (M + 31) / 32);
+        sgemm_kernel<32, 32><<<grid, 64, 0, st>>>(A, sam, sak, B, sbn, sbk, C, ldc, bias, M, N, K, relu);
+    }
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }
