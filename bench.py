@@ -331,20 +331,23 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(B, N, D, world=1, colocated=False):
+def workload_config(B, N, D, world=1):
     return {"workload": "C2: LR+FM+DeepFM train step (fwd, BCE, bwd, Adam lr=1e-3 wd=1e-5, reference dense-Adam "
-                        "numerics) on one batch" + ("" if world == 1 else f"; tables row-sharded over {world} GPUs "
-                        "(id mod G) in peer-mapped symmetric memory: forward gathers read remote shards over NVLink, owners "
-                        "pull gradients in the fused reduce+Adam kernel, one id all_gather per batch, dense grads all-reduced"),
+                        "numerics) on one batch" + ("" if world == 1 else f"; global batch split over {world} GPUs, tables row-sharded "
+                        "(id mod G), dense parameters data-parallel"),
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "single GPU" if world == 1 else f"dp{world} x row-sharded tables",
             "fields": F_FIELDS, "latent_dims": D, "table_rows": N,
             "ids": "uniform over disjoint per-field ranges", "l2": "inputs larger than L2: 3 tables x 3 arrays x "
-            f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step",
-            "layout": ("co-located records: the three models' parameters + Adam moments of one id in one 384-byte record "
+            f"{N * 4 * 12 / 1e6:.0f} MB touched at random rows, fresh batch every step"}
+
+
+def table_layout(world, colocated):
+    """How THIS implementation stores the tables (not part of the workload: the reference arm prints the same `config`)."""
+    return ("co-located records: the three models' parameters + Adam moments of one id in one 384-byte record "
                        "(3 x 128-byte lines), one gather / catch-up / update per step for all three"
                        + ("" if world == 1 else "; the joint table row-sharded (id mod G), one per-sample exchange row of 128 bytes "
                           "all-gathered per step")
-                       if colocated else "one fused-row table per model")}
+                       if colocated else "one fused-row table per model")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -977,7 +980,7 @@ def b200_arm(args):
     if rank == 0:
         line = {"metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world, colocate),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, N, D, world), "table_layout": table_layout(world, colocate),
                 "roofline": roof, "gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
                 "cuda_graph": bool(use_graph), "graph_branches": bool(use_graph and not args.no_fork),
                 "steady_state": steady, "configs": configs, "gpu_eager_baseline": eager_gpu}
