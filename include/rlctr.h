@@ -234,6 +234,24 @@ int rlctr_featemb_fwd(const int64_t* ids, const rlctr_table* table, float* out, 
                       int64_t batch, int32_t fields, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * BatchNorm1d in TRAINING mode fused with the ReLU behind it: the hidden layers of the policy nets in their learn steps
+ * (Linear -> BatchNorm1d -> ReLU: src/models/DDQN_model.py:32-46, DDPG_for_PG_model.py:27-40; torch runs native_batch_norm +
+ * relu and three backward kernels there).
+ *   fwd: mean / biased variance per column over the batch (two exact passes), y = [relu](gamma * (x - mean) * rsqrt(var + eps) + beta),
+ *        running_mean / running_var updated like torch (momentum, UNBIASED variance), save_mean / save_invstd kept for the backward;
+ *   bwd: dy_r = gy * (y > 0) if relu; dbeta = sum dy_r; dgamma = invstd * sum dy_r (x - mean);
+ *        dx = gamma * invstd * (dy_r - dbeta / B - (x - mean) * invstd^2 * sum dy_r (x - mean) / B)     (batch_norm_backward).
+ * x / y / gy / dx: [batch, n] at their pitches; batch <= 65536 (replay batches; RLCTR_EUNSUPPORTED beyond); gamma / beta /
+ * running_* / dx / dgamma / dbeta optional.  Eval-mode BatchNorm never comes here: it is folded into the GEMM by the host.
+ * ------------------------------------------------------------------------------------ */
+int rlctr_bn_relu_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float momentum, float eps, float* y, int64_t ldy, float* save_mean, float* save_invstd, int64_t batch,
+                      int32_t n, int32_t relu, rlctr_stream_t stream);
+int rlctr_bn_relu_bwd(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* gy, int64_t ldg, const float* gamma,
+                      const float* save_mean, const float* save_invstd, float* dx, int64_t lddx, float* dgamma, float* dbeta,
+                      int64_t batch, int32_t n, int32_t relu, rlctr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Loss head: torch.sigmoid + nn.BCELoss(mean) forward AND their autograd
  * (p_model.py:55; src/main/pretrain_main.py:167,98,101), with torch's exact clamp
  * semantics (log >= -100; (p-y)/max((1-p)p,1e-12)):

@@ -9,8 +9,9 @@ Python's ``random.sample`` (:183-185); ``learn`` is double-Q with MSE, hard targ
 ``replace_target_iter`` calls (:198-224).
 
 What runs on the B200 path: every Linear is :class:`.mlp.Linear` (tcgen05 3xTF32 GEMMs), the update is
-:class:`.optim.Adam` (fused dense-Adam kernel).  BatchNorm1d stays a torch op between the GEMMs (train-mode
-batch statistics / eval-mode running statistics as in the reference, :148-151).
+:class:`.optim.Adam` (fused dense-Adam kernel).  BatchNorm1d + ReLU between the GEMMs: in training mode (the learn steps) one
+library kernel each way (rlctr_bn_relu_fwd / _bwd: batch statistics, normalisation, affine map, ReLU, running statistics); in
+eval mode (the acting path, :148-151) folded into the GEMM (mlp.Tower).
 """
 from __future__ import annotations
 

@@ -98,6 +98,8 @@ SIGNATURES = {
     "rlctr_gather_rows": (C.c_int, [_P, _I64, _TP, _P, _P]),
     "rlctr_ffm_fwd": (C.c_int, [_P, _TP, _P, _P, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "rlctr_featemb_fwd": (C.c_int, [_P, _TP, _P, _I64, _I64, _I32, _P]),
+    "rlctr_bn_relu_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_float, C.c_float, _P, _I64, _P, _P, _I64, _I32, _I32, _P]),
+    "rlctr_bn_relu_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_bce_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "rlctr_sigmoid_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
     "rlctr_sort_ws_bytes": (_SZ, [_I64, _I64]),

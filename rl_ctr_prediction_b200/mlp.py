@@ -117,6 +117,59 @@ class Linear(nn.Linear):
         return _LinearFn.apply(x, self.weight, self.bias, relu)
 
 
+BN_FUSED_MAX_BATCH = 1 << 16
+
+
+class _BnReluFn(torch.autograd.Function):
+    """nn.BatchNorm1d (training mode) [+ nn.ReLU] as ONE library call each way: rlctr_bn_relu_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+        lib = _lib.load()
+        x2, ldx = _rows_view(x)
+        B, N = x2.shape
+        dev = x2.device
+        y = torch.empty(B, N, dtype=torch.float32, device=dev)
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        invstd = torch.empty(N, dtype=torch.float32, device=dev)
+        _lib.call("rlctr_bn_relu_fwd", lib.rlctr_bn_relu_fwd, x2.data_ptr(), ldx, _lib.ptr(weight.detach() if weight is not None else None),
+                  _lib.ptr(bias.detach() if bias is not None else None), _lib.ptr(running_mean), _lib.ptr(running_var),
+                  float(momentum), float(eps), _lib.ptr(y), N, _lib.ptr(mean), _lib.ptr(invstd), B, N, 1 if relu else 0,
+                  _lib.stream(), meta={"B": B, "N": N})
+        ctx.save_for_backward(x2, y, weight, mean, invstd)
+        ctx.ldx, ctx.relu, ctx.in_shape, ctx.has_bias = ldx, relu, x.shape, bias is not None
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x2, y, weight, mean, invstd = ctx.saved_tensors
+        B, N = y.shape
+        dev = y.device
+        g2 = gy.reshape(B, N).contiguous().float()
+        dx = torch.empty(B, N, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dgamma = torch.empty(N, dtype=torch.float32, device=dev) if (weight is not None and ctx.needs_input_grad[1]) else None
+        dbeta = torch.empty(N, dtype=torch.float32, device=dev) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        _lib.call("rlctr_bn_relu_bwd", lib.rlctr_bn_relu_bwd, x2.data_ptr(), ctx.ldx, _lib.ptr(y), N, _lib.ptr(g2), N,
+                  _lib.ptr(weight.detach() if weight is not None else None), _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(dx), N,
+                  _lib.ptr(dgamma), _lib.ptr(dbeta), B, N, 1 if ctx.relu else 0, _lib.stream(), meta={"B": B, "N": N})
+        if dx is not None:
+            dx = dx.reshape(ctx.in_shape)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def bn_relu(bn: nn.BatchNorm1d, x, relu: bool):
+    """``relu(bn(x))`` for a training-mode ``nn.BatchNorm1d`` on the library kernels (same running-statistics bookkeeping as
+    ``nn.BatchNorm1d.forward``: momentum None = cumulative average, num_batches_tracked)."""
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    return _BnReluFn.apply(x, bn.weight if bn.affine else None, bn.bias if bn.affine else None, rm, rv, momentum, bn.eps, relu)
+
+
 class _TowerFn(torch.autograd.Function):
     """All layers of a Linear[-ReLU][-Dropout] stack as one autograd node (see the module docstring)."""
 
@@ -236,6 +289,14 @@ class Tower(nn.Sequential):
                 y = _fwd(_lib.load(), x2, ldx, (m.weight * scale[:, None]).contiguous(), shift.contiguous(), relu)
                 x = y.reshape(*x.shape[:-1], y.shape[1])
                 i += 3 if relu else 2
+                continue
+            if (type(m) is nn.BatchNorm1d and m.training and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+                    and 1 < x.shape[0] <= BN_FUSED_MAX_BATCH):
+                # learn steps (training mode): batch statistics, normalisation, affine map and the ReLU behind it in one kernel
+                # (and one for their backward) instead of native_batch_norm + relu (+ three backward kernels)
+                relu = isinstance(nxt, nn.ReLU)
+                x = bn_relu(m, x, relu)
+                i += 2 if relu else 1
                 continue
             if isinstance(m, Linear) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
                 x = m(x, relu=True)

@@ -1049,3 +1049,71 @@ def test_auc_logloss_matches_sklearn(lib, case):
     assert np.array_equal(out, out2)
     # one class only: AUC undefined (sklearn raises; here NaN)
     assert np.isnan(metrics.auc_logloss(dev(p), torch.zeros(n, dtype=torch.int64, device=DEV)).cpu().numpy()[0])
+
+
+@pytest.mark.parametrize("B,N,relu", [(256, 300, True), (16, 5, True), (1000, 33, False), (4096, 128, True)])
+def test_bn_relu_matches_torch(B, N, relu):
+    """rlctr_bn_relu_fwd / _bwd (training-mode BatchNorm1d [+ ReLU], the policy nets' hidden layers in their learn steps,
+    DDQN_model.py:32-46) against torch's own BatchNorm1d + ReLU in float64: outputs, input / gamma / beta gradients, running
+    statistics (momentum, unbiased variance) and num_batches_tracked."""
+    from rl_ctr_prediction_b200 import mlp
+    torch.manual_seed(B + N)
+    bn = torch.nn.BatchNorm1d(N).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+    ref = torch.nn.BatchNorm1d(N).to(DEV).double().train()
+    ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    base = torch.randn(B, N + 3, device=DEV) * 2.0 + 0.7
+    x = base[:, :N].detach().requires_grad_(True)                        # a pitched view, like the GEMM outputs the kernel is fed
+    xr = base[:, :N].double().detach().requires_grad_(True)
+    gy = torch.randn(B, N, device=DEV)
+    y = mlp.bn_relu(bn, x, relu)
+    yr = ref(xr)
+    close(y, torch.relu(yr) if relu else yr, rtol=1e-5)
+    # the backward takes the ReLU mask of the kernel's own output (mask as input): an activation within rounding of zero may fall
+    # on either side in fp32 / fp64, and one flipped element shifts the column sums -- and with them the whole column of dx
+    yr = yr * (y > 0).double() if relu else yr
+    y.backward(gy)
+    yr.backward(gy.double())
+    close(x.grad, xr.grad, rtol=1e-5)
+    close(bn.weight.grad, ref.weight.grad, rtol=1e-5)
+    close(bn.bias.grad, ref.bias.grad, rtol=1e-5)
+    close(bn.running_mean, ref.running_mean, rtol=1e-5)
+    close(bn.running_var, ref.running_var, rtol=1e-5)
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+    # the Tower routes a training-mode Linear -> BatchNorm1d -> ReLU stack through it: same numbers as the same stack with torch's
+    # own BatchNorm1d / ReLU modules between the same GEMMs (fusion switched off)
+    import copy
+    from rl_ctr_prediction_b200 import DDQN_model
+    torch.manual_seed(1)
+    net = DDQN_model.bn_mlp(N, 3, hidden=(64, 32), device=DEV).train()
+    twin = copy.deepcopy(net)
+    inp = torch.randn(B, N, device=DEV)
+    out = net(inp)
+    out.sum().backward()
+    saved, mlp.BN_FUSED_MAX_BATCH = mlp.BN_FUSED_MAX_BATCH, 0
+    try:
+        out_ref = twin(inp)
+        out_ref.sum().backward()
+    finally:
+        mlp.BN_FUSED_MAX_BATCH = saved
+    close(out, out_ref, rtol=2e-5)
+    for (k, p), (_, q) in zip(net.named_parameters(), twin.named_parameters()):
+        # every one of these gradients is a sum over the B samples of O(1) terms that largely cancel (the loss is out.sum()), so
+        # two correct fp32 evaluations differ by ~1e-7 * B in absolute terms; the biases in front of a BatchNorm have an exactly
+        # zero gradient (the batch mean is subtracted again) and carry nothing but that noise
+        if k in ("0.bias", "3.bias"):
+            assert float(p.grad.abs().max()) <= 5e-6 * B and float(q.grad.abs().max()) <= 5e-6 * B, k
+            continue
+        close(p.grad, q.grad, rtol=5e-5, atol=max(5e-5 * float(q.grad.abs().max()), 1e-6 * B)), k
+    for (k, u), (_, v) in zip(net.named_buffers(), twin.named_buffers()):
+        close(u.float(), v.float(), rtol=1e-5), k
+
+
+def _plain_linear(m):
+    lin = torch.nn.Linear(m.in_features, m.out_features, device=m.weight.device)
+    lin.load_state_dict(m.state_dict())
+    return lin
