@@ -15,6 +15,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import mlp as _mlp
 from . import optim as _optim
 from .DDQN_model import RingMemory, bn_mlp, state_dims
 
@@ -27,7 +28,7 @@ class Actor(nn.Module):
         self.mlp = bn_mlp(input_dims + 1, action_nums, device=device)
 
     def forward(self, input, ddqn_a):
-        obs = torch.cat([input, self.bn_input(ddqn_a)], dim=1)
+        obs = torch.cat([input, _mlp.apply_bn(self.bn_input, ddqn_a)], dim=1)
         return torch.softmax(self.mlp(obs), dim=1)
 
 
@@ -38,7 +39,7 @@ class Critic(nn.Module):
         self.mlp = bn_mlp(input_dims + action_nums + 1, action_nums, device=device)
 
     def forward(self, input, action, ddqn_a):
-        obs = torch.cat([input, self.bn_input(ddqn_a)], dim=1)
+        obs = torch.cat([input, _mlp.apply_bn(self.bn_input, ddqn_a)], dim=1)
         return self.mlp(torch.cat([obs, action], dim=1))
 
 

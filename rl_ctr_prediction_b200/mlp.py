@@ -170,6 +170,15 @@ def bn_relu(bn: nn.BatchNorm1d, x, relu: bool):
     return _BnReluFn.apply(x, bn.weight if bn.affine else None, bn.bias if bn.affine else None, rm, rv, momentum, bn.eps, relu)
 
 
+def apply_bn(bn, x):
+    """``bn(x)``: on the library kernel when ``bn`` is a plain training-mode ``nn.BatchNorm1d`` on a CUDA batch, else the module
+    itself (eval mode, cross-rank statistics, batches beyond the kernel's range)."""
+    if (type(bn) is nn.BatchNorm1d and bn.training and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+            and 1 < x.shape[0] <= BN_FUSED_MAX_BATCH):
+        return bn_relu(bn, x, False)
+    return bn(x)
+
+
 class _TowerFn(torch.autograd.Function):
     """All layers of a Linear[-ReLU][-Dropout] stack as one autograd node (see the module docstring)."""
 
