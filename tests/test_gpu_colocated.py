@@ -257,3 +257,29 @@ def test_group_update_with_receive_positions():
     ga.flush()
     gb.flush()
     assert torch.equal(ga.table.data, gb.table.data)
+
+
+def test_group_with_more_than_sixteen_fields():
+    """20 fields: the gather walks two 16-field blocks per sample (the non-pipelined path of group_fwd_kernel) and must still
+    reproduce the stand-alone kernels' summation order: FM / DeepFM bit for bit."""
+    from rl_ctr_prediction_b200 import colocated, graphs, optim, pretrain_main as PM
+    F20, N, B, steps = 20, 4000, 300, 4
+    torch.manual_seed(17)
+    sep = [PM.get_model(n, N, F20, D).to(DEV).train() for n in ("LR", "FM", "DeepFM")]
+    sep[2].mlp.eval()
+    grp = [copy.deepcopy(m) for m in sep]
+    g = torch.Generator().manual_seed(23)
+    batches = [(torch.randint(0, N, (B, F20), generator=g).to(DEV), (torch.rand(B, generator=g) < 0.3).long().to(DEV))
+               for _ in range(steps)]
+    opts = [optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5) for m in sep]
+    lossf = torch.nn.BCELoss()
+    l_sep = np.array([[float(graphs.eager_step(m, o, lossf, x, y)) for m, o in zip(sep, opts)] for x, y in batches])
+    group = colocated.colocate(grp)
+    gopt = optim.Adam(group.parameters(), lr=1e-3, weight_decay=1e-5)
+    l_grp = np.array([group.train_step(x, y, gopt).cpu().numpy() for x, y in batches])
+    assert np.array_equal(l_sep[:, 1:], l_grp[:, 1:])
+    np.testing.assert_allclose(l_grp[:, 0], l_sep[:, 0], rtol=2e-6)
+    for i in (1, 2):
+        a, b = sep[i].state_dict(), grp[i].state_dict()
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
