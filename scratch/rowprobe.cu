@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <vector>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
@@ -152,7 +153,8 @@ int main(int argc, char** argv) {
     CK(cudaDeviceGetLimit(&lim, cudaLimitMaxL2FetchGranularity));
     printf("MaxL2FetchGranularity = %zu, n_rows = %lld\n", lim, (long long)n_rows);
     const int64_t n = 983040;
-    const int pitch = 64;                                            // floats: 256 B per record slot (all layouts fit inside)
+    const bool rec384 = argc > 3 && std::string(argv[3]) == "rec384";   // the co-located record: 3 lines per id
+    const int pitch = rec384 ? 96 : 64;                              // floats: 256 B per record slot (all layouts fit inside)
     float* tab; CK(cudaMalloc(&tab, (size_t)n_rows * pitch * 4));
     fill_kernel<<<148 * 8, 256>>>(tab, n_rows * pitch, 1.0f);
     Ctx c; c.flush_n = 96 << 20; CK(cudaMalloc(&c.flush, c.flush_n * 4));
@@ -175,6 +177,21 @@ int main(int argc, char** argv) {
 #define GATHER(LPR, RIF, MODE, IDS, NN, P, TAG)                                                                       \
     { float us = timed(c, [&] { gather_kernel<LPR, RIF, MODE><<<grid_for((NN) * LPR / RIF), 256>>>(IDS, NN, tab, P, out); }); \
       snprintf(name, sizeof name, "gather %3dB pitch %3dB rif%d mode%d %s", LPR * 16, P * 4, RIF, MODE, TAG); report(name, us, NN, LPR * 16); }
+    if (rec384) {
+        // what the co-located step does to its table, stripped of everything else: the gather reads the first line of a 384-byte
+        // record per occurrence; catch-up and update each read and write the record's three lines once per distinct id
+        GATHER(8, 1, 0, ids_r, n, 96, "random (group gather pattern)");
+        GATHER(8, 2, 0, ids_r, n, 96, "random (group gather pattern)");
+        GATHER(8, 4, 0, ids_r, n, 96, "random (group gather pattern)");
+        { float us = timed(c, [&] { rmw_kernel<8, 3, 1><<<grid_for(nu * 8), 256>>>(ids_s, nu, tab, 96); });
+          report("rmw 384B pitch 384B lpr8 ch3 rif1 sorted (catch-up / update pattern)", us, nu, 2 * 384); }
+        { float us = timed(c, [&] { rmw_kernel<8, 3, 2><<<grid_for(nu * 8 / 2), 256>>>(ids_s, nu, tab, 96); });
+          report("rmw 384B pitch 384B lpr8 ch3 rif2 sorted (catch-up / update pattern)", us, nu, 2 * 384); }
+        { float us = timed(c, [&] { rmw_kernel<8, 3, 4><<<grid_for(nu * 8 / 4), 256>>>(ids_s, nu, tab, 96); });
+          report("rmw 384B pitch 384B lpr8 ch3 rif4 sorted (catch-up / update pattern)", us, nu, 2 * 384); }
+        printf("done\n");
+        return 0;
+    }
     // 64 B rows at 64 B / 192 B / 256 B pitch (the table slot is 256 B: smaller pitches use a prefix of the allocation)
     GATHER(4, 1, 0, ids_r, n, 16, "random");
     GATHER(4, 1, 0, ids_r, n, 48, "random");
