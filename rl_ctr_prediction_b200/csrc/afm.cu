@@ -110,7 +110,7 @@ template <int D>
 __global__ void __launch_bounds__(AFM_WARPS * 32)
 afm_fwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __restrict__ params, AfmDrop dr,
                float* __restrict__ out, int64_t batch, int fields) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     constexpr int DP = AfmSmem<D>::DP;
     constexpr int PAR = AfmSmem<D>::PAR;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,7 +157,7 @@ afm_fwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
     }
 }
 
-// dynamic smem: PAR | AFM_WARPS * (fd + 2 * npair_pad + 3 * npair * D) floats | 2 * npair + fields * fields bytes
+// dynamic smem: PAR | AFM_WARPS * (fd + 2 * npair_pad + 3 * npair * DP) floats | 2 * npair + fields * fields bytes
 //
 // Parameter gradients: the D x D gradient of the attention weight is an outer-product sum over pairs,
 // dW_a[k][d] = sum_p da_p[k] * ip_p[d].  Accumulating it per lane over the lane's own pairs needs D*D registers per lane (the
@@ -169,24 +169,26 @@ __global__ void __launch_bounds__(AFM_WARPS * 32, 3)          // <= 168 register
 afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __restrict__ params, AfmDrop dr,
                const float* __restrict__ gout, float* __restrict__ grows, int64_t ld_grows, float* __restrict__ part,
                int64_t batch, int fields) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     constexpr int DP = AfmSmem<D>::DP;
     constexpr int PAR = AfmSmem<D>::PAR;
     constexpr int NP = D * D + 3 * D + 2;
-    constexpr int ENT = (D * D + 31) / 32;
+    constexpr int CHK = DP / 4;                         // float4 chunks of a (padded) row of D values
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fd = fields * D, npair = fields * (fields - 1) / 2, npp = (npair + 3) / 4 * 4;
-    const int per_warp = fd + 2 * npp + 3 * npair * D;
+    const int fdp = (fd + 3) & ~3;                  // every per-warp array starts on a 16-byte boundary
+    const int per_warp = fdp + 2 * npp + 3 * npair * DP;
     float* par = smem;
     float* stage = smem + PAR + wib * per_warp;
-    float* sc = stage + fd;                 // exp(s_p - max)
+    float* sc = stage + fdp;                // exp(s_p - max)
     float* dsc = sc + npp;                  // d L / d score_p
-    float* dipS = dsc + npp;                // d L / d ip_p   [npair, D]
-    float* daS = dipS + npair * D;          // d L / d (pre-ReLU attention activation) [npair, D]
-    float* ipS = daS + npair * D;           // ip_p           [npair, D]
+    float* dipS = dsc + npp;                // d L / d ip_p   [npair, DP]   (rows padded to DP floats: 128-bit accesses)
+    float* daS = dipS + npair * DP;         // d L / d (pre-ReLU attention activation) [npair, DP]
+    float* ipS = daS + npair * DP;          // ip_p           [npair, DP]
     unsigned char* pi = reinterpret_cast<unsigned char*>(smem + PAR + AFM_WARPS * per_warp);
     unsigned char* pj = pi + npair;
     unsigned char* pidx = pj + npair;
+    static_assert(PAR % 4 == 0, "the per-warp arrays follow the parameters at a 16-byte boundary");
     AfmSmem<D>::load(par, params);
     for (int i = threadIdx.x; i < fields; i += blockDim.x) {
         const int base = i * fields - i * (i + 1) / 2;
@@ -204,15 +206,12 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
     const float* fcw = ws + DP;
     const int width = npair + D;
 
-    float dWa[ENT], dba[D], dws[D], dfcw[D], dbs = 0.f, dfcb = 0.f;
-    int ek[ENT], ed[ENT];                   // this lane's entries (k, d) of dW_a
-#pragma unroll
-    for (int i = 0; i < ENT; ++i) {
-        const int e = lane + 32 * i;
-        dWa[i] = 0.f;
-        ek[i] = e < D * D ? e / D : 0;
-        ed[i] = e < D * D ? e % D : 0;
-    }
+    // dW_a: lane l < D * CHK owns row k = l / CHK, columns 4 (l % CHK) .. +3 -- one scalar (da_p[k]) and one 128-bit (ip_p chunk)
+    // shared-memory read per pair instead of two scalar reads per ENTRY (the first layout: entries l, l + 32, ...)
+    float dba[D], dws[D], dfcw[D], dbs = 0.f, dfcb = 0.f;
+    float4 dWa4 = f4zero();
+    const bool wa_on = lane < D * CHK;
+    const int wk = wa_on ? lane / CHK : 0, wc = wa_on ? lane % CHK : 0;
 #pragma unroll
     for (int k = 0; k < D; ++k) { dba[k] = 0.f; dws[k] = 0.f; dfcw[k] = 0.f; }
 
@@ -232,7 +231,7 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const float ipd = vi[d] * vj[d];
-                ipS[p * D + d] = ipd;
+                ipS[p * DP + d] = ipd;
                 acc[d] = fmaf(sd, ipd, acc[d]);
             }
         }
@@ -251,7 +250,7 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
         for (int p = lane; p < npair; p += 32) {
             float t = 0.f;
 #pragma unroll
-            for (int d = 0; d < D; ++d) t = fmaf(dattn[d], ipS[p * D + d], t);
+            for (int d = 0; d < D; ++d) t = fmaf(dattn[d], ipS[p * DP + d], t);
             t *= afm_mask(dr, seed, ctr, b, width, p);
             dsc[p] = t;
             dot = fmaf(sc[p] / sum, t, dot);
@@ -263,7 +262,7 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
             const float sd = score * afm_mask(dr, seed, ctr, b, width, p);
             float ip[D], dip[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) { ip[d] = ipS[p * D + d]; dip[d] = sd * dattn[d]; }
+            for (int d = 0; d < D; ++d) { ip[d] = ipS[p * DP + d]; dip[d] = sd * dattn[d]; }
             dbs += dsp;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
@@ -273,25 +272,31 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
                 const float da = a > 0.f ? dsp * ws[k] : 0.f;
                 dws[k] = fmaf(dsp, fmaxf(a, 0.f), dws[k]);
                 dba[k] += da;
-                daS[p * D + k] = da;
+                daS[p * DP + k] = da;
 #pragma unroll
                 for (int d = 0; d < D; ++d) dip[d] = fmaf(par[k * DP + d], da, dip[d]);
             }
 #pragma unroll
-            for (int d = 0; d < D; ++d) dipS[p * D + d] = dip[d];
+            for (int d = 0; d < D; ++d) dipS[p * DP + d] = dip[d];
         }
         __syncwarp();
-        // dW_a entries of this lane: sum over the pairs of the sample, in pair order
-#pragma unroll
-        for (int i = 0; i < ENT; ++i) {
-            float a0 = 0.f, a1 = 0.f;
+        // dW_a chunk of this lane: sum over the pairs of the sample, in pair order (two chains: even / odd pairs)
+        if (wa_on) {
+            float4 a0 = f4zero(), a1 = f4zero();
             int p = 0;
             for (; p + 1 < npair; p += 2) {
-                a0 = fmaf(daS[p * D + ek[i]], ipS[p * D + ed[i]], a0);
-                a1 = fmaf(daS[(p + 1) * D + ek[i]], ipS[(p + 1) * D + ed[i]], a1);
+                const float d0 = daS[p * DP + wk], d1 = daS[(p + 1) * DP + wk];
+                const float4 i0 = *reinterpret_cast<const float4*>(ipS + p * DP + 4 * wc);
+                const float4 i1 = *reinterpret_cast<const float4*>(ipS + (p + 1) * DP + 4 * wc);
+                a0.x = fmaf(d0, i0.x, a0.x); a0.y = fmaf(d0, i0.y, a0.y); a0.z = fmaf(d0, i0.z, a0.z); a0.w = fmaf(d0, i0.w, a0.w);
+                a1.x = fmaf(d1, i1.x, a1.x); a1.y = fmaf(d1, i1.y, a1.y); a1.z = fmaf(d1, i1.z, a1.z); a1.w = fmaf(d1, i1.w, a1.w);
             }
-            if (p < npair) a0 = fmaf(daS[p * D + ek[i]], ipS[p * D + ed[i]], a0);
-            dWa[i] += a0 + a1;
+            if (p < npair) {
+                const float d0 = daS[p * DP + wk];
+                const float4 i0 = *reinterpret_cast<const float4*>(ipS + p * DP + 4 * wc);
+                a0.x = fmaf(d0, i0.x, a0.x); a0.y = fmaf(d0, i0.y, a0.y); a0.z = fmaf(d0, i0.z, a0.z); a0.w = fmaf(d0, i0.w, a0.w);
+            }
+            dWa4.x += a0.x + a1.x; dWa4.y += a0.y + a1.y; dWa4.z += a0.z + a1.z; dWa4.w += a0.w + a1.w;
         }
         // d v_i[d] = sum_{j != i} d ip_{pair(i,j)}[d] * v_j[d], j in order
         for (int t = lane; t < fd; t += 32) {
@@ -300,20 +305,20 @@ afm_bwd_kernel(const float* __restrict__ rows, int64_t ld_rows, const float* __r
             float a0 = 0.f, a1 = 0.f;                                      // two chains: the loop is a string of dependent LDS -> FMA
             int j = 0;
             for (; j + 1 < fields; j += 2) {
-                if (j != i) a0 = fmaf(dipS[prow[j] * D + d], stage[j * D + d], a0);
-                if (j + 1 != i) a1 = fmaf(dipS[prow[j + 1] * D + d], stage[(j + 1) * D + d], a1);
+                if (j != i) a0 = fmaf(dipS[prow[j] * DP + d], stage[j * D + d], a0);
+                if (j + 1 != i) a1 = fmaf(dipS[prow[j + 1] * DP + d], stage[(j + 1) * D + d], a1);
             }
-            if (j < fields && j != i) a0 = fmaf(dipS[prow[j] * D + d], stage[j * D + d], a0);
+            if (j < fields && j != i) a0 = fmaf(dipS[prow[j] * DP + d], stage[j * D + d], a0);
             grows[b * ld_grows + t] = a0 + a1;
         }
         __syncwarp();
     }
     // per-warp partials, one row of NP floats per warp of the grid: dW_a entries are already whole-warp sums of their lane
     float* mine = part + ((int64_t)blockIdx.x * AFM_WARPS + wib) * NP;
+    if (wa_on) {
 #pragma unroll
-    for (int i = 0; i < ENT; ++i) {
-        const int e = lane + 32 * i;
-        if (e < D * D) mine[e] = dWa[i];
+        for (int q = 0; q < 4; ++q)
+            if (4 * wc + q < D) mine[wk * D + 4 * wc + q] = f4get(dWa4, q);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -350,7 +355,7 @@ template <int D>
 static int afm_bwd_launch(const float* rows, int64_t ld_rows, const float* params, const AfmDrop& dr, const float* gout,
                           float* grows, int64_t ld_grows, float* dparams, float* part, int64_t batch, int fields, cudaStream_t st) {
     const int fd = fields * D, npair = fields * (fields - 1) / 2, npp = (npair + 3) / 4 * 4;
-    const size_t smem = (size_t)(AfmSmem<D>::PAR + AFM_WARPS * (fd + 2 * npp + 3 * npair * D)) * sizeof(float) + 2 * (size_t)npair +
+    const size_t smem = (size_t)(AfmSmem<D>::PAR + AFM_WARPS * (((fd + 3) & ~3) + 2 * npp + 3 * npair * AfmSmem<D>::DP)) * sizeof(float) + 2 * (size_t)npair +
                         (size_t)fields * fields;
     if (smem > 200 * 1024) return RLCTR_EUNSUPPORTED;
     if (smem > 48 * 1024)
