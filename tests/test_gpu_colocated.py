@@ -283,3 +283,27 @@ def test_group_with_more_than_sixteen_fields():
         a, b = sep[i].state_dict(), grp[i].state_dict()
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("B", [1, 33])
+def test_group_ragged_batches_and_out_of_range_ids(B):
+    """Tiny / odd batch sizes and ids outside the vocabulary (zero row, no update -- include/rlctr.h conventions): the group
+    follows the stand-alone models there too."""
+    N, steps = 500, 3
+    sep = _models(N, seed=41)
+    grp = [copy.deepcopy(m) for m in sep]
+    g = torch.Generator().manual_seed(3)
+    batches = []
+    for _ in range(steps):
+        x = torch.randint(0, N, (B, F), generator=g)
+        x[0, 0] = N + 7                                   # out of range
+        x[-1, 3] = -1
+        batches.append((x.to(DEV), (torch.rand(B, generator=g) < 0.5).long().to(DEV)))
+    l_sep = _train_separate(sep, batches)
+    group, l_grp = _train_group(grp, batches)
+    assert np.array_equal(l_sep[:, 1:], l_grp[:, 1:])
+    np.testing.assert_allclose(l_grp[:, 0], l_sep[:, 0], rtol=2e-6)
+    for i in (1, 2):
+        a, b = sep[i].state_dict(), grp[i].state_dict()
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
