@@ -228,14 +228,14 @@ class ColocatedCTR(Model._TableModel):
                 leaf = rows[i][:, :fd].detach().requires_grad_(True)
                 z = logits[i].view(B, 1) + m.mlp(leaf)
                 zz = z.detach().reshape(-1).contiguous()
+                # (the head's own sum of dlogit is the bias gradient: the same block partition and tree as the stand-alone
+                # backward's rlctr_sigmoid_bwd sum -- the same bits, one launch less)
                 _lib.check(lib.rlctr_bce_fwd_bwd(_lib.ptr(zz), _lib.ptr(yi), _lib.ptr(yf), None, losses.data_ptr() + 4 * i,
-                                                 _lib.ptr(dl), None, _lib.ptr(ws), B, st), "rlctr_bce_fwd_bwd")
+                                                 _lib.ptr(dl), _lib.ptr(dbias) if bias is not None else None, _lib.ptr(ws), B, st),
+                           "rlctr_bce_fwd_bwd")
                 m.zero_grad()
                 z.backward(dl.view_as(z))
                 extras.append(leaf.grad.contiguous())
-                if bias is not None:                         # the stand-alone backward sums dlogit with the same tree
-                    _lib.check(lib.rlctr_sigmoid_bwd(None, None, _lib.ptr(dl), _lib.ptr(dbias), _lib.ptr(ws), B, st),
-                               "rlctr_sigmoid_bwd")
             if bias is not None:
                 bias.grad = dbias
             dlogits.append(dl)

@@ -396,6 +396,20 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, in
     }
 }
 
+// the same for two partial arrays in one launch (a layer's dW and db: one graph node instead of two; the same sums in the same order)
+__global__ void __launch_bounds__(256)
+splitk_reduce2_kernel(const float* __restrict__ part_a, float* __restrict__ out_a, int64_t n_a, const float* __restrict__ part_b,
+                      float* __restrict__ out_b, int64_t n_b, int splits) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_a + n_b; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool a = i < n_a;
+        const float* src = a ? part_a + i : part_b + (i - n_a);
+        const int64_t stride = a ? n_a : n_b;
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += __ldg(src + (int64_t)k * stride);
+        if (a) out_a[i] = s; else out_b[i - n_a] = s;
+    }
+}
+
 // column sums of dY [B, N] (the bias gradient), fixed-shape: each block owns 32 columns, 8 warps stride the
 // rows, smem tree over the 8 partials.
 // wt != null: rows are scaled by wt[r] first (dW of a single-output layer: sum_b gy[b] * x[b, :])
@@ -918,6 +932,7 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         }
     }
     bool db_done = false;
+    const float* dbp_pending = nullptr;
     if (dw && fp32) {   // one pass, k = batch rows in ascending order
         int rc = simt::gemm(dy, 1, out_dim, x, 1, ldx, dw, in_dim, nullptr, out_dim, in_dim, (int)batch, 0, st);
         if (rc) return rc;
@@ -931,8 +946,12 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
             rc = tma::gemm(tma::Operand{dy, nullptr, out_dim, true}, tma::Operand{x, nullptr, ldx, true}, splits == 1 ? dw : part,
                            in_dim, nullptr, out_dim, in_dim, (int)batch, 0, true, st, nullptr, dbp);
             if (rc == RLCTR_OK && dbp) {
-                splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(dbp, db, out_dim, splits);
-                RLCTR_LAUNCH_CHECK();
+                if (splits > 1) {
+                    dbp_pending = dbp;                   // reduced together with dW below
+                } else {
+                    splitk_reduce_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(dbp, db, out_dim, splits);
+                    RLCTR_LAUNCH_CHECK();
+                }
                 db_done = true;
             }
         }
@@ -943,7 +962,11 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
                              0, p, st);
         }
         if (rc) return rc;
-        if (splits > 1) {
+        if (splits > 1 && dbp_pending) {
+            int64_t blocks = (mn + out_dim + 255) / 256;
+            splitk_reduce2_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(part, dw, mn, dbp_pending, db, out_dim, splits);
+            RLCTR_LAUNCH_CHECK();
+        } else if (splits > 1) {
             int64_t blocks = (mn + 255) / 256;
             splitk_reduce_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(part, dw, mn, splits);
             RLCTR_LAUNCH_CHECK();

@@ -717,9 +717,7 @@ class ShardedGroup(nn.Module):
                     tower_out = self.mlps[i](leaf).reshape(-1)
                 z = z + tower_out.detach()
             _lib.check(lib.rlctr_bce_fwd_bwd(_lib.ptr(z), _lib.ptr(yi), _lib.ptr(yf), None, losses.data_ptr() + 4 * i, _lib.ptr(dl),
-                                             _lib.ptr(dbias) if tower_out is None else None, _lib.ptr(ws), B, st), "rlctr_bce_fwd_bwd")
-            if tower_out is not None:                         # as the single-GPU group (and the stand-alone backward) sum it
-                _lib.check(lib.rlctr_sigmoid_bwd(None, None, _lib.ptr(dl), _lib.ptr(dbias), _lib.ptr(ws), B, st), "rlctr_sigmoid_bwd")
+                                             _lib.ptr(dbias), _lib.ptr(ws), B, st), "rlctr_bce_fwd_bwd")
             if G > 1:                                         # gradient of the GLOBAL mean loss
                 dl.mul_(1.0 / G)
                 dbias.mul_(1.0 / G)
