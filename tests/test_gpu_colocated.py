@@ -307,3 +307,60 @@ def test_group_ragged_batches_and_out_of_range_ids(B):
         a, b = sep[i].state_dict(), grp[i].state_dict()
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_group_at_benchmark_batch_against_cpu_oracle():
+    """The benchmark's own path and batch (B = 65536; N = 1e6): two steps of LR + FM + DeepFM as ONE co-located group against the
+    CPU oracle port (three stock-ATen models, dense torch Adam over every row): every loss, every touched row, 10^4 untouched
+    rows of every table -- and, at this size, FM / DeepFM still bit-identical to the stand-alone CUDA models."""
+    from oracle import torch_port as TP
+    from rl_ctr_prediction_b200 import colocated, graphs, optim, pretrain_main as PM
+    N, B = 1_000_000, 65536
+    names = ("LR", "FM", "DeepFM")
+    ports, members, alone = [], [], []
+    for n in names:
+        torch.manual_seed(1)
+        port = TP.PortCTR(n, N, F, D).eval()                 # eval(): DeepFM's dropout off
+        with torch.no_grad():
+            for k, p in port.named_parameters():
+                if "embedding" in k or k == "linear.weight":
+                    p.mul_(0.1)
+        ports.append((port, TP.make_adam(port)))
+        for bag in (members, alone):
+            m = PM.get_model(n, N, F, D)
+            m.load_state_dict(port.state_dict())
+            bag.append(m.to(DEV).eval())
+    group = colocated.colocate(members)
+    gopt = optim.Adam(group.parameters(), lr=1e-3, weight_decay=1e-5)
+    aopts = [optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5) for m in alone]
+    lossf = torch.nn.BCELoss()
+    rng = np.random.default_rng(0)
+    per = N // F
+    touched = []
+    for s in range(2):
+        x = torch.as_tensor(rng.integers(0, per, size=(B, F)) + np.arange(F) * per)
+        y = torch.as_tensor((rng.random(B) < 0.05).astype(np.int64))
+        touched.append(x.reshape(-1))
+        ref = [TP.ctr_train_step(port, popt, lossf, x, y.unsqueeze(1)) for port, popt in ports]
+        got = group.train_step(x.to(DEV), y.to(DEV), gopt).cpu().numpy()
+        sep = [float(graphs.eager_step(m, o, lossf, x.to(DEV), y.to(DEV))) for m, o in zip(alone, aopts)]
+        for i in range(3):
+            assert abs(got[i] - ref[i]) <= 1e-5 * abs(ref[i]), (s, names[i], got[i], ref[i])
+        assert got[1] == np.float32(sep[1]) and got[2] == np.float32(sep[2])
+    rows = torch.unique(torch.cat(touched))
+    extra = torch.as_tensor(rng.choice(N, 10_000, replace=False))
+    for i, (m, (port, _)) in enumerate(zip(members, ports)):
+        ref_sd, sd, sd_alone = port.state_dict(), m.state_dict(), alone[i].state_dict()
+        for k, v in ref_sd.items():
+            if i > 0:
+                assert torch.equal(sd[k], sd_alone[k]), (names[i], k)          # == the stand-alone CUDA model, bit for bit
+            if not (v.dim() == 2 and v.shape[0] == N):
+                continue                                                          # dense parameters: covered by the equality above
+            got_t = sd[k].cpu()
+            for sel in (rows, extra):
+                a, b = got_t[sel].double().numpy(), v[sel].double().numpy()
+                bad = np.abs(a - b) > 2e-5 * np.abs(b) + 2e-5 * float(np.abs(b).max())
+                if names[i] == "DeepFM":      # tower-borne gradients at rounding level: see test_gpu_parity_scale.py
+                    assert bad.mean() <= 1e-4 and np.abs(a - b).max() <= 2.2 * 1e-3 * 2
+                else:
+                    assert not bad.any(), (names[i], k, int(bad.sum()), float(np.abs(a - b).max()))
