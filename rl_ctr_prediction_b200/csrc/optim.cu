@@ -1583,7 +1583,18 @@ extern "C" int rlctr_group_rows_adam(const uint32_t* sorted_ids, const uint32_t*
     // memory system's random-access rate -- 3 lines read + 3 written per record + the dense-tail rows = ~27 G line operations/s
     const char* r2e = getenv("RLCTR_GROUP_ROWS2");
     const int rows2_env = r2e ? atoi(r2e) : 1;
-    if (rows2_env && !opt->stamp && (t.used + 3) / 4 <= 8 && lpr == 8) {
+    bool one_member_per_chunk = true;                    // group_rows2_kernel keeps ONE dense-tail pointer per 16-byte chunk
+    for (int ch = 0; ch < 8; ++ch) {
+        int owner = -1;
+        for (int q = 0; q < 4; ++q) {
+            const int col = 4 * ch + q;
+            if (g.grp.role[col] >= 2) {
+                if (owner >= 0 && owner != g.grp.member[col]) one_member_per_chunk = false;
+                owner = g.grp.member[col];
+            }
+        }
+    }
+    if (rows2_env && one_member_per_chunk && !opt->stamp && (t.used + 3) / 4 <= 8 && lpr == 8) {
         // two lanes per record on a persistent grid (2 resident blocks per SM), then the heavy hitters
         int64_t want = capped_blocks((2 * n + 255) / 256, world);
         const int64_t cap = (int64_t)RLCTR_SMS * 2 * (rows_grid_env() > 0 ? rows_grid_env() : 64);
