@@ -405,7 +405,15 @@ splitk_reduce2_kernel(const float* __restrict__ part_a, float* __restrict__ out_
         const float* src = a ? part_a + i : part_b + (i - n_a);
         const int64_t stride = a ? n_a : n_b;
         float s = 0.f;
-        for (int k = 0; k < splits; ++k) s += __ldg(src + (int64_t)k * stride);
+        int k = 0;
+        for (; k + 8 <= splits; k += 8) {                // eight independent loads in flight, added in split order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (int64_t)(k + u) * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; k < splits; ++k) s += __ldg(src + (int64_t)k * stride);
         if (a) out_a[i] = s; else out_b[i - n_a] = s;
     }
 }

@@ -44,6 +44,6 @@ busy = sum(e.time_range.end - e.time_range.start for e in seg)
 print(f"replay span {t1 - t0:.1f} us, kernels {len(seg)}, busy {busy:.1f} us, gaps {t1 - t0 - busy:.1f} us")
 prev_end = t0
 for e in seg:
-    if e.time_range.end - e.time_range.start > 30:
+    if e.time_range.end - e.time_range.start > 30 or "splitk" in e.name or "bce" in e.name:
         print(f"{e.time_range.start - t0:9.1f} +{e.time_range.end - e.time_range.start:7.1f}  gap {e.time_range.start - prev_end:6.1f}  {e.name[:70]}")
     prev_end = max(prev_end, e.time_range.end)
