@@ -932,7 +932,7 @@ __device__ __forceinline__ void replay_row_arm(ReplayRow<CH>& it, const AdamView
     if (st >= upto) it.off = -1; else it.t = st;
 }
 template <int CH, int LPRR, bool CATCHUP>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, (CH == 3 ? 4 : 3))
 replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) / LPRR;  // rows between two items of one lane
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
