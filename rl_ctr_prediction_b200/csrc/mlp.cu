@@ -489,6 +489,48 @@ gemv_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
         }
     }
 }
+// the same layer for 16-byte-aligned rows of at most 256 floats: a lane holds its (at most two) float4 of w, a warp takes four
+// rows per trip with all eight 16-byte loads issued before the first use
+__global__ void __launch_bounds__(256)
+gemv_rows4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int64_t rows, int K4, int relu) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const bool on0 = lane < K4, on1 = lane + 32 < K4;
+    const float4 w0 = on0 ? __ldg(w4 + lane) : zero, w1 = on1 ? __ldg(w4 + lane + 32) : zero;
+    const float b0 = bias ? __ldg(bias) : 0.f;
+    for (int64_t r = warp0 * 4; r < rows; r += nwarps * 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4* xr = reinterpret_cast<const float4*>(x + (r + u) * ldx);
+            const bool ok = r + u < rows;
+            a[u] = (ok && on0) ? __ldg(xr + lane) : zero;
+            b[u] = (ok && on1) ? __ldg(xr + lane + 32) : zero;
+        }
+        float s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float t = a[u].x * w0.x;
+            t = fmaf(a[u].y, w0.y, t); t = fmaf(a[u].z, w0.z, t); t = fmaf(a[u].w, w0.w, t);
+            t = fmaf(b[u].x, w1.x, t); t = fmaf(b[u].y, w1.y, t); t = fmaf(b[u].z, w1.z, t); t = fmaf(b[u].w, w1.w, t);
+            s[u] = t;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(RLCTR_FULL, s[u], off);
+        }
+        if (lane < 4 && r + lane < rows) {
+            float v = (lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3]) + b0;
+            if (relu) v = fmaxf(v, 0.f);
+            y[r + lane] = v;
+        }
+    }
+}
 __global__ void __launch_bounds__(256)
 outer_rows_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ dx, int64_t rows, int K,
                   const float* __restrict__ x, int64_t ldx, float scale) {
@@ -808,9 +850,15 @@ extern "C" int rlctr_linear_fwd(const float* x, int64_t ldx, const float* w, con
     bool fused_drop = false;
     int rc = RLCTR_OK;
     if (out_dim == 1) {
-        int64_t blocks = (batch + 7) / 8;
-        gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
-            x, ldx, w, bias, y, batch, in_dim, relu);
+        if (in_dim % 4 == 0 && in_dim <= 256 && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0) {
+            const int64_t blocks = (batch + 31) / 32;                      // 8 warps x 4 rows
+            gemv_rows4_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
+                x, ldx, w, bias, y, batch, in_dim / 4, relu);
+        } else {
+            const int64_t blocks = (batch + 7) / 8;
+            gemv_rows_kernel<<<(unsigned)(blocks < RLCTR_SMS * 8 ? blocks : RLCTR_SMS * 8), 256, 0, st>>>(
+                x, ldx, w, bias, y, batch, in_dim, relu);
+        }
         RLCTR_LAUNCH_CHECK();
     } else if (flags & RLCTR_MLP_FP32) {
         rc = simt::gemm(x, ldx, 1, w, in_dim, 1, y, out_dim, bias, (int)batch, out_dim, in_dim, relu, st);

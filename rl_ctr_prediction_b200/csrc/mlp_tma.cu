@@ -805,10 +805,13 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES, b_hi = sa + a_bytes, b_lo = b_hi + b_bytes;
+                    // the last k-block of a K that is no multiple of 32 is zero-filled by TMA: its all-zero k-steps are not issued
+                    const int ksteps = min(BK / UK, (g.K - kb * BK + UK - 1) / UK);
                     if (g.a_tmem) {
                         const uint32_t ta_hi = tmem_base + (uint32_t)(g.a_col0 + stage * 2 * BK), ta_lo = ta_hi + (uint32_t)BK;
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
+                            if (k >= ksteps) break;
                             const uint32_t bo = (uint32_t)k * b_step;
                             const uint64_t dbh = g.b_mn ? desc_mn_major(b_hi + bo) : desc_k_major(b_hi + bo);
                             const uint64_t dbl = g.b_mn ? desc_mn_major(b_lo + bo) : desc_k_major(b_lo + bo);
@@ -826,6 +829,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     } else
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
+                        if (k >= ksteps) break;
                         const uint32_t ao = (uint32_t)k * a_step, bo = (uint32_t)k * b_step;
                         const uint64_t dah = g.a_mn ? desc_mn_major(a_hi + ao) : desc_k_major(a_hi + ao);
                         const uint64_t dal = g.a_mn ? desc_mn_major(a_lo + ao) : desc_k_major(a_lo + ao);

@@ -694,6 +694,7 @@ def gemm_path(monkeypatch, path):
 # path: "tma" = 16-byte aligned pitch + workspace (TMA-fed kernel, csrc/mlp_tma.cu); "staged" = RLCTR_GEMM_TMA=0, dense x
 # (software-staged kernel, csrc/mlp.cu: what any shape TMA cannot address falls back to).  K = 150 / 255 are not multiples of 4: "tma" pads the pitch.
 @pytest.mark.parametrize("B,K,N", [(1, 150, 300), (128, 32, 16), (1000, 150, 300), (777, 300, 200), (513, 200, 1),
+                                   (1001, 203, 1), (1003, 256, 1), (6, 300, 1),
                                    (4096, 255, 1024), (300, 1024, 512), (65536, 150, 300)])
 @pytest.mark.parametrize("relu", [0, 1])
 @pytest.mark.parametrize("path", ["tma", "tma_smemA", "tma_pair", "tma_cta2", "staged"])
