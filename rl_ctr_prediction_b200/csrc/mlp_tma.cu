@@ -622,6 +622,13 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (g.cluster > 1) cluster_sync_all();                 // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (g.dbg && threadIdx.x == 0) {                       // RLCTR_GEMM_DBG: per-CTA (start, end, SM) behind the stage stamps
+        uint64_t now; uint32_t sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g.dbg[4096 + 4 * blockIdx.x] = (long long)now;
+        g.dbg[4096 + 4 * blockIdx.x + 2] = (long long)sm;
+    }
 
     if (warp < CONV_WARPS) {
         // ================= converters =================
@@ -909,6 +916,11 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (g.dbg && threadIdx.x == 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        g.dbg[4096 + 4 * blockIdx.x + 1] = (long long)now;
+    }
     if (g.cluster > 1) cluster_sync_all();                 // no CTA leaves while a peer may still signal its barriers
     if (warp == MMA_WARP) {
         if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
