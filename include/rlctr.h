@@ -434,6 +434,14 @@ int rlctr_step_advance(int32_t* step, int32_t delta, rlctr_stream_t stream);
 int rlctr_generate_preds(const float* pctr, const float* w, const int64_t* action, const int64_t* label,
                          float* y, float* w_out, float* reward, int64_t batch, int32_t models,
                          int32_t variant, rlctr_stream_t stream);
+/* The v10 form, src/all_main/hybrid_td3_main_per_v10.py:54-164: models chosen by descending `w` (prob_weights), softmax over the
+ * k largest `c_actions` in their own descending order, reward 1/0 on strict comparisons with the all-model mean, and
+ * return_c_actions -> c_out [B, M].  As in the reference (:117) the c_out entries of a partial ensemble (action < M) come from the
+ * sorted c_actions of batch row r, r = the sample's rank among the samples with the same action.  ws: _ws_bytes(batch) bytes. */
+size_t rlctr_generate_preds_v10_ws_bytes(int64_t batch);
+int rlctr_generate_preds_v10(const float* pctr, const float* w, const float* c_actions, const int64_t* action,
+                             const int64_t* label, float* y, float* c_out, float* reward, int64_t batch, int32_t models,
+                             void* ws, size_t ws_bytes, rlctr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * REINFORCE head: PG_model.py:53-58,104-107 (softmax, -log pi(a), loss, and its autograd).

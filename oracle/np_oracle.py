@@ -321,6 +321,55 @@ def generate_preds(pctr, w, action, label, variant=GP_DDQN_DDPG, dtype=F32, retu
     return y.reshape(-1, 1), w_out, r.reshape(-1, 1)
 
 
+def generate_preds_v10(pctr, w, c_actions, action, label, dtype=F32, return_margin=False):
+    """src/all_main/hybrid_td3_main_per_v10.py:54-164: y [B,1], reward [B,1], return_c_actions [B,M].
+
+    Models are chosen by descending ``w`` (prob_weights, :62), the softmax runs over the k LARGEST ``c_actions`` in their own
+    descending order (:63,:103-105) -- the two sorts are independent; k == M scores sum(w * pctr) and returns the row's c_actions
+    (:88-96).  Rewards are 1 / 0 on strict comparisons with the mean over all M models (:127-146); actions outside 1..M keep
+    the defaults y = 1, reward = 1, return_c_actions = 0 (:56-57,:73).
+    As written (:117) the returned c_action of slot m of a partial ensemble is read from ``sort_c_actions`` at the row's RANK
+    within its action group (a subset-relative index applied to the whole-batch tensor), not at the row itself: reproduced.
+    """
+    pctr = _as(pctr, dtype)
+    w = _as(w, dtype)
+    c = _as(c_actions, dtype)
+    action = np.asarray(action).reshape(-1)
+    label = np.asarray(label).reshape(-1)
+    B, M = pctr.shape
+    order = np.argsort(-w, axis=1, kind="stable")                   # :62
+    c_desc = -np.sort(-c, axis=1, kind="stable")                    # :63 (values only)
+    y = np.ones((B,), dtype=dtype)
+    r = np.ones((B,), dtype=dtype)
+    c_out = np.zeros((B, M), dtype=dtype)
+    margin = np.full((B,), np.inf, dtype=np.float64)
+    mean_all = pctr.mean(axis=1, dtype=dtype)
+    for k in range(1, M + 1):
+        sel = np.nonzero(action == k)[0]
+        if sel.size == 0:
+            continue
+        if k == M:
+            yk = (w[sel] * pctr[sel]).sum(axis=1, dtype=dtype)       # :89
+            c_out[sel] = c[sel]                                     # :96
+        else:
+            sw = softmax(c_desc[sel, :k], dtype)                    # :103-105
+            top = order[sel, :k]
+            tp = np.take_along_axis(pctr[sel], top, axis=1)         # :110-115
+            yk = (sw * tp).sum(axis=1, dtype=dtype)                 # :119
+            rank = np.arange(sel.size)                              # :117: rows 0..len(sel)-1 of the WHOLE batch
+            ck = np.zeros((sel.size, M), dtype=dtype)
+            np.put_along_axis(ck, top, c_desc[rank, :k], axis=1)
+            c_out[sel] = ck
+        y[sel] = yk
+        clk = label[sel] == 1
+        good = np.where(clk, yk > mean_all[sel], yk < mean_all[sel])  # :127-146 (strict)
+        r[sel] = np.where(good, dtype(1), dtype(0))
+        margin[sel] = np.abs(yk.astype(np.float64) - mean_all[sel].astype(np.float64))
+    if return_margin:
+        return y.reshape(-1, 1), r.reshape(-1, 1), c_out, margin
+    return y.reshape(-1, 1), r.reshape(-1, 1), c_out
+
+
 # --------------------------------------------------------------------------
 # REINFORCE (PG_model.py, with the N9 input-dim fix applied by the caller)
 # --------------------------------------------------------------------------

@@ -124,6 +124,8 @@ SIGNATURES = {
     "rlctr_steps_advance": (C.c_int, [_P, _P, _I32, _P]),
     "rlctr_step_advance": (C.c_int, [_P, _I32, _P]),
     "rlctr_generate_preds": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "rlctr_generate_preds_v10_ws_bytes": (_SZ, [_I64]),
+    "rlctr_generate_preds_v10": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _SZ, _P]),
     "rlctr_reinforce_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "rlctr_auc_ws_bytes": (_SZ, [_I64]),
     "rlctr_auc_logloss": (C.c_int, [_P, _P, _P, _I64, _P, _P, _SZ, _P]),

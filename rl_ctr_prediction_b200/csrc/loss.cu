@@ -196,6 +196,144 @@ generate_preds_kernel(const float* __restrict__ pctr, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// K6, v10 form (src/all_main/hybrid_td3_main_per_v10.py:54-164): models chosen by descending prob_weights, softmax over the k
+// largest c_actions in their own order, rewards 1 / 0 on strict comparisons, and return_c_actions -- whose partial-ensemble rows
+// read sort_c_actions at the sample's RANK within its action group (:117 indexes the whole-batch tensor with subset-relative
+// positions).  The rank is an exclusive count of earlier samples with the same action: per-block counts, a scan over the blocks,
+// then match_any inside the block.
+// ------------------------------------------------------------------------------------------
+constexpr int GP10_THREADS = 256;
+
+__global__ void __launch_bounds__(GP10_THREADS)
+gp10_count_kernel(const int64_t* __restrict__ action, int64_t batch, int M, int* __restrict__ counts) {
+    __shared__ int s[GP_MAX];
+    if (threadIdx.x < GP_MAX) s[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * GP10_THREADS + threadIdx.x;
+    const int64_t k = b < batch ? __ldg(action + b) : 0;
+    if (k >= 1 && k <= M) atomicAdd(&s[k - 1], 1);                   // integer counts: order-free
+    __syncthreads();
+    if (threadIdx.x < GP_MAX) counts[(int64_t)blockIdx.x * GP_MAX + threadIdx.x] = s[threadIdx.x];
+}
+// counts[block][a] -> number of samples with action a + 1 in EARLIER blocks.  One warp per action; a lane owns a contiguous run of
+// blocks (sum, warp scan of the run totals, second pass writes the exclusive prefixes).
+__global__ void __launch_bounds__(GP_MAX * 32)
+gp10_scan_kernel(int* __restrict__ counts, int nblocks) {
+    const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (nblocks + 31) / 32;
+    const int i0 = lane * per, i1 = min(i0 + per, nblocks);
+    int total = 0;
+    for (int i = i0; i < i1; ++i) total += counts[(int64_t)i * GP_MAX + a];
+    int incl = total;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(RLCTR_FULL, incl, off);
+        if (lane >= off) incl += t;
+    }
+    int run = incl - total;
+    for (int i = i0; i < i1; ++i) {
+        const int v = counts[(int64_t)i * GP_MAX + a];
+        counts[(int64_t)i * GP_MAX + a] = run;
+        run += v;
+    }
+}
+// descending stable insertion sort of GP_MAX values (the -inf padding stays last)
+__device__ __forceinline__ void gp_sort_desc(float (&v)[GP_MAX]) {
+#pragma unroll
+    for (int i = 1; i < GP_MAX; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j) {
+            if (v[j] > v[j - 1]) { const float t = v[j]; v[j] = v[j - 1]; v[j - 1] = t; }
+        }
+    }
+}
+__global__ void __launch_bounds__(GP10_THREADS)
+generate_preds_v10_kernel(const float* __restrict__ pctr, const float* __restrict__ w, const float* __restrict__ c_actions,
+                          const int64_t* __restrict__ action, const int64_t* __restrict__ label, float* __restrict__ y,
+                          float* __restrict__ c_out, float* __restrict__ reward, int64_t batch, int M,
+                          const int* __restrict__ prefix) {
+    __shared__ int s_cnt[GP10_THREADS / 32][GP_MAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * GP10_THREADS + threadIdx.x;
+    const bool in = b < batch;
+    const int64_t k64 = in ? __ldg(action + b) : 0;
+    const int k = (k64 >= 1 && k64 <= M) ? (int)k64 : 0;              // 0: outside 1..M (defaults)
+    // rank of this sample among the samples of the batch with the same action
+    if (lane < GP_MAX) s_cnt[warp][lane] = 0;
+    __syncwarp();
+    const unsigned same = __match_any_sync(RLCTR_FULL, k);
+    if (k > 0 && lane == __ffs(same) - 1) s_cnt[warp][k - 1] = __popc(same);
+    __syncthreads();
+    int64_t rank = 0;
+    if (k > 0) {
+        rank = prefix[(int64_t)blockIdx.x * GP_MAX + k - 1] + __popc(same & ((1u << lane) - 1u));
+        for (int q = 0; q < warp; ++q) rank += s_cnt[q][k - 1];
+    }
+    if (!in) return;
+    float p[GP_MAX], wt[GP_MAX], sw[GP_MAX], sp[GP_MAX], cv[GP_MAX], cs[GP_MAX], oc[GP_MAX];
+    int si[GP_MAX];
+#pragma unroll
+    for (int m = 0; m < GP_MAX; ++m) {
+        p[m] = m < M ? __ldg(pctr + b * M + m) : 0.f;
+        wt[m] = m < M ? __ldg(w + b * M + m) : -INFINITY;
+        cv[m] = m < M ? __ldg(c_actions + b * M + m) : -INFINITY;
+        oc[m] = 0.f;
+        sw[m] = wt[m]; sp[m] = p[m]; si[m] = m; cs[m] = cv[m];
+    }
+    // models by descending prob_weights (:62), tuples moved by the sort
+#pragma unroll
+    for (int i = 1; i < GP_MAX; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j) {
+            if (sw[j] > sw[j - 1]) {
+                float tw = sw[j]; sw[j] = sw[j - 1]; sw[j - 1] = tw;
+                float tp = sp[j]; sp[j] = sp[j - 1]; sp[j - 1] = tp;
+                int ti = si[j]; si[j] = si[j - 1]; si[j - 1] = ti;
+            }
+        }
+    }
+    gp_sort_desc(cs);                                                 // this row's c_actions, descending (:63)
+    const int lab = (int)__ldg(label + b);
+    float psum = 0.f;
+#pragma unroll
+    for (int m = 0; m < GP_MAX; ++m) if (m < M) psum += p[m];
+    const float mean_all = psum / (float)M;
+    float yv = 1.0f, rv = 1.0f;
+    if (k > 0) {
+        if (k == M) {                                                 // :88-96
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < GP_MAX; ++m) if (m < M) { acc += wt[m] * p[m]; oc[m] = cv[m]; }
+            yv = acc;
+        } else {                                                      // :97-123
+            float cr[GP_MAX];                                         // sort_c_actions of row `rank` of the whole batch (:117)
+#pragma unroll
+            for (int m = 0; m < GP_MAX; ++m) cr[m] = m < M ? __ldg(c_actions + rank * M + m) : -INFINITY;
+            gp_sort_desc(cr);
+            float e[GP_MAX], esum = 0.f;
+#pragma unroll
+            for (int j = 0; j < GP_MAX; ++j) { e[j] = j < k ? expf(cs[j] - cs[0]) : 0.f; esum += e[j]; }
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < GP_MAX; ++j) {
+                if (j < k) {
+                    acc += (e[j] / esum) * sp[j];
+#pragma unroll
+                    for (int m = 0; m < GP_MAX; ++m) if (si[j] == m) oc[m] = cr[j];
+                }
+            }
+            yv = acc;
+        }
+        const bool good = lab == 1 ? (yv > mean_all) : (yv < mean_all);     // strict (:127-146)
+        rv = good ? 1.0f : 0.0f;
+    }
+    y[b] = yv;
+    reward[b] = rv;
+#pragma unroll
+    for (int m = 0; m < GP_MAX; ++m) if (m < M) c_out[b * M + m] = oc[m];
+}
+
+// ------------------------------------------------------------------------------------------
 // REINFORCE head
 // ------------------------------------------------------------------------------------------
 constexpr int RF_MAX = 32;
@@ -299,6 +437,28 @@ extern "C" int rlctr_generate_preds(const float* pctr, const float* w, const int
     if (batch == 0) return RLCTR_OK;
     generate_preds_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         pctr, w, action, label, y, w_out, reward, batch, models, variant);
+    RLCTR_LAUNCH_CHECK();
+    return RLCTR_OK;
+}
+
+extern "C" size_t rlctr_generate_preds_v10_ws_bytes(int64_t batch) {
+    if (batch < 0) return 0;
+    return (size_t)((batch + GP10_THREADS - 1) / GP10_THREADS + 1) * GP_MAX * sizeof(int);
+}
+extern "C" int rlctr_generate_preds_v10(const float* pctr, const float* w, const float* c_actions, const int64_t* action,
+                                        const int64_t* label, float* y, float* c_out, float* reward, int64_t batch,
+                                        int32_t models, void* ws, size_t ws_bytes, rlctr_stream_t stream) {
+    if (!pctr || !w || !c_actions || !action || !label || !y || !c_out || !reward || batch < 0) return RLCTR_EINVAL;
+    if (models < 1 || models > GP_MAX || batch > ((int64_t)1 << 31)) return RLCTR_EUNSUPPORTED;
+    if (batch == 0) return RLCTR_OK;
+    if (!ws || ws_bytes < rlctr_generate_preds_v10_ws_bytes(batch)) return RLCTR_EWORKSPACE;
+    const int nblocks = (int)((batch + GP10_THREADS - 1) / GP10_THREADS);
+    int* counts = reinterpret_cast<int*>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    gp10_count_kernel<<<nblocks, GP10_THREADS, 0, st>>>(action, batch, models, counts);
+    gp10_scan_kernel<<<1, GP_MAX * 32, 0, st>>>(counts, nblocks);
+    generate_preds_v10_kernel<<<nblocks, GP10_THREADS, 0, st>>>(pctr, w, c_actions, action, label, y, c_out, reward, batch,
+                                                                 models, counts);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -63,6 +63,13 @@ def golden_heads():
 
 
 @pytest.fixture(scope="session")
+def golden_gp10():
+    """generate_preds of hybrid_td3_main_per_v10.py from the real reference (tests/golden/make_golden_gp10.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "ref_golden_gp10.npz")
+    return np.load(path, allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
 def golden_td3():
     """Two learn steps of the reference's hybrid TD3 (v10) agent (tests/golden/make_golden_td3.py)."""
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_td3.npz")

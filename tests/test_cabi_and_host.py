@@ -105,6 +105,8 @@ def test_argument_errors_need_no_gpu(lib):
     # argument validation happens before any CUDA call
     assert lib.rlctr_embed_fwd(None, None, None, None, None, 1, None, None, 0, 4, 15, 1, None) == -1
     assert lib.rlctr_generate_preds(None, None, None, None, None, None, None, 4, 3, 0, None) == -1
+    assert lib.rlctr_generate_preds_v10(None, None, None, None, None, None, None, None, 4, 3, None, 0, None) == -1
+    assert lib.rlctr_generate_preds_v10_ws_bytes(1000) >= 4 * 8 * 4
     assert lib.rlctr_sort_ids(None, 1, 1, None, None, None, 0, None) == -1
     assert lib.rlctr_rows_ws_bytes(1000) >= 16
     assert lib.rlctr_group_fwd(None, None, None, 0, None, 0, 4, 15, None) != 0

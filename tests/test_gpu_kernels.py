@@ -636,6 +636,49 @@ def test_generate_preds_random_vs_oracle(lib):
             assert mism.mean() < 1e-3
 
 
+def _gp10(lib, pctr, w, c, act, lab):
+    B, M = pctr.shape
+    y = torch.empty(B, device=DEV)
+    co = torch.empty(B, M, device=DEV)
+    r = torch.empty(B, device=DEV)
+    wsb = lib.rlctr_generate_preds_v10_ws_bytes(B)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=DEV)
+    assert lib.rlctr_generate_preds_v10(L().ptr(dev(pctr)), L().ptr(dev(w)), L().ptr(dev(c)), L().ptr(dev(act.reshape(-1))),
+                                        L().ptr(dev(lab.reshape(-1))), L().ptr(y), L().ptr(co), L().ptr(r), B, M, L().ptr(ws),
+                                        wsb, st()) == 0
+    return y.cpu().numpy(), r.cpu().numpy(), co.cpu().numpy()
+
+
+@pytest.mark.parametrize("M", [3, 5, 6, 4])
+def test_generate_preds_v10_golden(lib, golden_gp10, M):
+    """src/all_main/hybrid_td3_main_per_v10.py:54-164 on the real reference's outputs: y to 1e-5, rewards and the returned
+    c_actions (rank-indexed, :117) bit-exact."""
+    g = lambda k: golden_gp10[f"gp10/M{M}/{k}"]
+    y, r, co = _gp10(lib, g("pctr"), g("w"), g("c"), g("action"), g("label"))
+    close(y, g("y").reshape(-1), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(r, g("reward").reshape(-1))
+    assert np.array_equal(co, g("c_out"))
+
+
+@pytest.mark.parametrize("B,M", [(1, 2), (255, 3), (5000, 8), (70001, 5), (300000, 6)])
+def test_generate_preds_v10_random_vs_oracle(lib, B, M):
+    """Ranks across many blocks (the scan over per-block counts), actions outside 1..M, every ensemble size."""
+    rng = np.random.default_rng(B + M)
+    pctr = rng.random((B, M)).astype(np.float32)
+    w = O.softmax(rng.standard_normal((B, M)).astype(np.float32) * 2)
+    c = np.tanh(rng.standard_normal((B, M))).astype(np.float32)
+    lab = (rng.random(B) < 0.5).astype(np.int64)
+    act = rng.integers(1, M + 1, size=B).astype(np.int64)
+    act[::97] = 0
+    act[5::1013] = M + 3
+    y, r, co = _gp10(lib, pctr, w, c, act, lab)
+    yo, ro, co_o, margin = O.generate_preds_v10(pctr, w, c, act, lab, return_margin=True)
+    close(y, yo.reshape(-1), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(co, co_o)
+    mism = r != ro.reshape(-1)
+    assert not (mism & (margin > 2e-7)).any()          # two fp32 evaluations may disagree on a reward only at a tie
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_reinforce_head(lib, golden, variant):
     logits, acts = golden["pg/logits"], golden["pg/acts"].reshape(-1)

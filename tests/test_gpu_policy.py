@@ -766,3 +766,29 @@ def test_eval_mode_batchnorm_folded_into_gemm_and_padded_state():
         close(q, ref.mlp(torch.as_tensor(ref_state)), rtol=2e-5)
     q_grad = net(s)                                                                         # autograd on: module-by-module path
     close(q_grad, q, rtol=2e-5)
+
+
+# the main of the v10 TD3 agent scores the ensemble with its own generate_preds
+@pytest.mark.parametrize("M", [3, 6])
+def test_generate_preds_v10_host_api(golden_gp10, M):
+    """ensemble.generate_preds_v10(model_dict, features, actions, prob_weights, c_actions, labels, device, mode): the
+    reference's argument order and return values (hybrid_td3_main_per_v10.py:54-55,164) on the reference's own outputs."""
+    from rl_ctr_prediction_b200 import ensemble
+    g = lambda k: torch.as_tensor(golden_gp10[f"gp10/M{M}/{k}"]).to(DEV)
+    pctr = g("pctr")
+
+    class Frozen(torch.nn.Module):
+        def __init__(self, col):
+            super().__init__()
+            self.col = col
+
+        def forward(self, feats):
+            return self.col
+
+    md = {i: Frozen(pctr[:, i:i + 1]) for i in range(M)}
+    feats = torch.zeros(pctr.shape[0], 15, dtype=torch.long, device=DEV)
+    y, r, c_out = ensemble.generate_preds_v10(md, feats, g("action"), g("w"), g("c"), g("label"), DEV, mode="train")
+    assert y.shape == (pctr.shape[0], 1) and r.shape == y.shape and c_out.shape == pctr.shape
+    np.testing.assert_allclose(y.cpu().numpy(), golden_gp10[f"gp10/M{M}/y"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(r.cpu().numpy(), golden_gp10[f"gp10/M{M}/reward"])
+    assert np.array_equal(c_out.cpu().numpy(), golden_gp10[f"gp10/M{M}/c_out"])

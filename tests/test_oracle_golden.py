@@ -230,6 +230,22 @@ def test_generate_preds(golden, M):
     assert np.array_equal(r1, golden[f"gp/v1_M{M}/reward"])
 
 
+@pytest.mark.parametrize("M", [3, 5, 6, 4])
+def test_generate_preds_v10(golden_gp10, M):
+    """hybrid_td3_main_per_v10.py:54-164, incl. the rank-indexed return_c_actions (:117); M = 4 is the single-action batch."""
+    g = lambda k: golden_gp10[f"gp10/M{M}/{k}"]
+    y, r, c_out = O.generate_preds_v10(g("pctr"), g("w"), g("c"), g("action"), g("label"))
+    close(y, g("y"), atol=1.5e-7)
+    assert np.array_equal(r, g("reward"))
+    assert np.array_equal(c_out, g("c_out"))
+    if M != 4:                                   # the rank quirk is visible: some returned value is not from the row's own c_actions
+        own = np.sort(g("c"), axis=1)
+        got = np.sort(np.where(c_out != 0, c_out, np.inf), axis=1)
+        partial = g("action").reshape(-1) < M
+        foreign = [(~np.isin(got[i][np.isfinite(got[i])], own[i])).any() for i in np.nonzero(partial)[0]]
+        assert any(foreign)
+
+
 def test_reinforce(golden):
     vt = O.discount_and_norm_rewards(golden["pg/rs"], 1.0)
     close(vt, golden["pg/vt_norm"], rtol=1e-12, atol=1e-12)
