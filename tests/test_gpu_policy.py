@@ -792,3 +792,56 @@ def test_generate_preds_v10_host_api(golden_gp10, M):
     np.testing.assert_allclose(y.cpu().numpy(), golden_gp10[f"gp10/M{M}/y"], rtol=1e-5, atol=1e-7)
     assert np.array_equal(r.cpu().numpy(), golden_gp10[f"gp10/M{M}/reward"])
     assert np.array_equal(c_out.cpu().numpy(), golden_gp10[f"gp10/M{M}/c_out"])
+
+
+def test_td3_v10_main_step_is_consistent():
+    """hybrid_td3_main_per_v10.py:354-410 for a few batches: random acting while batch_index < 1000 (no learning), then acting by
+    the actor and one learn step.  The stored transition is [features | return_c_actions | d_q_values | d_action | reward]
+    (:366-367) with return_c_actions / rewards equal to the CPU restatement on the step's own draws."""
+    from oracle import np_oracle as O
+    from rl_ctr_prediction_b200 import ensemble, p_model, hybrid_td3_main_per_v10 as V10, v10_Hybrid_TD3_model_PER as T
+    from rl_ctr_prediction_b200.Feature_embedding import Feature_Embedding
+    torch.manual_seed(5)
+    N, F, D, B, M = 5000, 15, 10, 384, 3
+    models = {0: p_model.LR(N), 1: p_model.FM(N, D), 2: p_model.FFM(N, F, D)}
+    for m in models.values():
+        with torch.no_grad():
+            m.table.mul_(0.1)
+        m.to(DEV).eval()
+    fe = Feature_Embedding(N, F, D).to(DEV)
+    fe.load_embedding(models[1].state_dict())
+    agent = T.Hybrid_TD3_Model(N, F, D, M, memory_size=4 * B, batch_size=64, device=DEV)
+    drawn = []
+    act0 = agent.choose_action
+
+    def recording(state, random):
+        out = act0(state, random)
+        drawn.append(out)
+        return out
+
+    agent.choose_action = recording
+    rng = np.random.default_rng(1)
+    for it, (index, learn) in enumerate(((0, None), (999, None), (1000, None))):
+        x = torch.as_tensor(rng.integers(0, N, size=(B, F))).to(DEV)
+        y = torch.as_tensor((rng.random((B, 1)) < 0.3).astype(np.int64)).to(DEV)
+        y_preds, rewards, critic_loss = V10.train_step(agent, models, x, y, fe, index, DEV)
+        assert (critic_loss is None) == (index < V10.RANDOM_STEPS)
+        if critic_loss is not None:
+            assert np.isfinite(float(critic_loss))
+        c_a, e_c_a, d_q, d_a = drawn[-1]
+        assert d_a.shape == (B, 1) and int(d_a.min()) >= 1 and int(d_a.max()) <= M
+        pctr = ensemble.score_models(models, x)
+        yo, ro, co, margin = O.generate_preds_v10(pctr.cpu().numpy(), e_c_a.cpu().numpy(), c_a.cpu().numpy(), d_a.cpu().numpy(),
+                                                  y.cpu().numpy(), return_margin=True)
+        close(y_preds, yo)
+        bad = (rewards.cpu().numpy() != ro).reshape(-1)
+        assert np.all(margin[bad] <= 2e-7)
+        stored = agent.memory.memory[it * B:(it + 1) * B]
+        assert torch.equal(stored[:, :F].long(), x)
+        assert np.array_equal(stored[:, F:F + M].cpu().numpy(), co)
+        assert torch.equal(stored[:, F + M:F + 2 * M], d_q.float())
+        assert torch.equal(stored[:, F + 2 * M].long(), d_a.reshape(-1))
+        assert torch.equal(stored[:, -1], rewards.reshape(-1))
+    assert agent.memory.memory_counter == 3 * B
+    yt, rt, at, wt = V10.test_batch(agent, models, x, y, fe, DEV)
+    assert yt.shape == (B, 1) and set(np.unique(rt.cpu().numpy())) <= {0.0, 1.0} and wt.shape == (B, M)
