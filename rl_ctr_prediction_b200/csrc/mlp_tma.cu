@@ -68,6 +68,7 @@ struct Args {
                                           // owning a different m-tile of the same (n-tile, split)
     int l2_ahead;                         // stages of A the producer prefetches into L2 ahead of the pipeline (0: off)
     int c_tma;                            // 1: the epilogue stages 32x32 blocks of C in shared memory and TMA-stores them (mapC)
+    int m_tma;                            // 1: the dgrad mask arrives as TMA-loaded 32x32 blocks (mapM), one block per epilogue warp
     long long* dbg;                       // RLCTR_GEMM_DBG: per-stage clock64 stamps of block 0 (scratch/gemm_trace.py), else null
     float* colsum_part;                   // wgrad only: [splits][M] partial column sums of the MN-major A operand (db), or null
     Epilogue epi;                         // fused dropout (forward) / ReLU-dropout mask of the layer below (dgrad)
@@ -436,6 +437,7 @@ struct EpiCtx {
     const float* mask_row;
     int mvec;
     float mask_scale;
+    uint32_t mbuf;             // != 0: the chunk's mask sits in this warp's TMA-loaded 32 x 32 block (applied in epilogue_stage)
 };
 // W accumulator columns [n0, n0 + W) of this thread's row: bias, ReLU, dropout, mask of the layer below -> v[]
 template <int W>
@@ -474,7 +476,7 @@ __device__ __forceinline__ void epilogue_compute(const EpiCtx& e, const uint32_t
                 v[j] = dropout_keep(e.drop_seed, i0 + (uint64_t)j, e.drop_thresh) ? v[j] * e.drop_scale : 0.f;
         }
     }
-    if (e.mask_row && e.row_ok) {
+    if (e.mask_row && e.row_ok && !(W == 32 && e.mbuf)) {
         const float* mr = e.mask_row + n0;
         if (n0 + W <= e.N && e.mvec == 4) {
 #pragma unroll
@@ -513,10 +515,23 @@ __device__ __forceinline__ void epilogue_emit(const EpiCtx& e, const uint32_t* r
 }
 // ... or into this warp's 32 x 32 staging block (SWIZZLE_128B: row = lane, 16-byte chunk c at c ^ (lane & 7): a quarter-warp
 // covers all 32 banks), from where ONE TMA store writes 32 full 128-byte row segments (clipped at the tensor bounds)
+template <bool MASK>
 __device__ __forceinline__ void epilogue_stage(const EpiCtx& e, const uint32_t* r, int n0, uint32_t buf, int lane) {
     float v[32];
     epilogue_compute<32>(e, r, n0, v);
     const uint32_t row = buf + (uint32_t)lane * 128u;
+    if (MASK && e.mbuf) {
+        // the mask block has the staging block's layout (TMA SWIZZLE_128B box {32 n, 32 m}): same offsets, 16 bytes at a time
+        const uint32_t mrow = e.mbuf + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t off = (uint32_t)((c ^ (lane & 7)) << 4);
+            const float4 x = lds128(mrow + off);
+            sts128(row + off, make_float4(x.x > 0.f ? v[4 * c] * e.mask_scale : 0.f, x.y > 0.f ? v[4 * c + 1] * e.mask_scale : 0.f,
+                                          x.z > 0.f ? v[4 * c + 2] * e.mask_scale : 0.f, x.w > 0.f ? v[4 * c + 3] * e.mask_scale : 0.f));
+        }
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         sts128(row + (uint32_t)((c ^ (lane & 7)) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
@@ -541,26 +556,45 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, uint32_t taddr, i
 
 // the same walk with the 32-column chunks leaving through shared memory + TMA (two staging blocks per warp, toggled per
 // chunk; a block is reused once the bulk group that read it has finished reading); a 16-column tail goes out directly
+template <bool MASK>
 __device__ __forceinline__ void epilogue_chunk_tma(const EpiCtx& e, const uint32_t* r, int n0, const CUtensorMap* mapC,
                                                    uint32_t stage0, int& buf, int m0, int lane) {
     if (n0 >= e.N) return;                              // warp-uniform
     if (lane == 0) bulk_wait_read<1>();                 // the group that last read this block (two chunks ago) is done
     __syncwarp();
     const uint32_t sb = stage0 + (uint32_t)buf * 4096u;
-    epilogue_stage(e, r, n0, sb, lane);
+    epilogue_stage<MASK>(e, r, n0, sb, lane);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) { tma_store_2d(mapC, sb, n0, m0); bulk_commit(); }
     buf ^= 1;
 }
+// TMA-loaded dgrad mask: one 32 x 32 block per epilogue warp, requested one chunk ahead (the first chunk of a tile before the
+// accumulator is awaited), landing on the warp's own mbarrier.  Read per thread from global memory the same 4 KB are eight 16-byte
+// pieces of 32 different lines per load instruction -- 2x the sectors and 8x the L1 wavefronts: +41 us on the 300 -> 200 dgrad.
+// (the block and its barrier are addressed from the warp's C staging area: nothing but the barrier phase stays live)
+__device__ __forceinline__ void mask_request(const CUtensorMap* mapM, uint32_t mbuf, uint32_t mbar, int n0, int m0, int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(mbar, 4096u);
+        tma_load_2d(mbuf, mapM, n0, m0, mbar);
+    }
+}
+template <bool MASK>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiCtx& e, uint32_t taddr, int n_base, int n_tile, const CUtensorMap* mapC,
-                                                  uint32_t stage0, int& buf, int m0, int lane) {
+                                                  uint32_t stage0, int& buf, int m0, int lane, const CUtensorMap* mapM,
+                                                  uint32_t mbar, uint32_t& mphase) {
     const int nch = n_tile / 32;
     for (int c = 0; c < nch; ++c) {
         uint32_t ra[32];
         tmem_ld<32>(taddr + (uint32_t)(c * 32), ra);
         tmem_ld_fence<32>(ra);
-        epilogue_chunk_tma(e, ra, n_base + c * 32, mapC, stage0, buf, m0, lane);
+        const int n0 = n_base + c * 32;
+        if (MASK && e.mbuf && n0 < e.N) {                   // warp-uniform
+            mbar_wait(mbar, mphase);
+            mphase ^= 1;
+        }
+        epilogue_chunk_tma<MASK>(e, ra, n0, mapC, stage0, buf, m0, lane);      // ends behind a __syncwarp: every lane has read the mask block
+        if (MASK && e.mbuf && c + 1 < nch && n0 + 32 < e.N) mask_request(mapM, e.mbuf, mbar, n0 + 32, m0, lane);
     }
     if (n_tile & 31) {
         uint32_t rt[16];
@@ -572,13 +606,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiCtx& e, uint32_t tadd
 
 // PAIR: the cta_group::2 instantiation (must be launched in clusters of two; the PAIR = false instantiation contains no 2-CTA
 // instruction and runs with any cluster size)
-template <bool PAIR>
+// MASK: the dgrad instantiation whose epilogue takes the mask of the layer below from TMA-loaded blocks (its own instantiation:
+// the mask pipeline's registers must not cost the other GEMMs theirs -- measured +2-3 us each when it was a runtime switch)
+template <bool PAIR, bool MASK>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                  const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC, const Args g) {
+                  const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
+                  const __grid_constant__ CUtensorMap mapM, const Args g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t raw_bar[MAX_STAGES], full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t mask_bar[EPI_WARPS];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[BIAS_SMEM];
 
@@ -601,6 +639,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mbar_init(smem_u32(&full_bar[s]), (uint32_t)(CONV_WARPS * 32 * (PAIR ? 2 : 1)));   // pair: both CTAs' converters (leader's copy)
             mbar_init(smem_u32(&empty_bar[s]), (uint32_t)(PAIR ? 1 : g.cluster));   // every CTA of the cluster has retired its MMAs on the slot
         }
+        for (int s = 0; s < EPI_WARPS; ++s) mbar_init(smem_u32(&mask_bar[s]), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tmem_full_bar[s]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[s]), (uint32_t)(EPI_WARPS * 32 * (PAIR ? 2 : 1)));
@@ -612,6 +651,7 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tma_prefetch_desc(&mapB);
         if (g.b_presplit) tma_prefetch_desc(&mapBlo);
         if (g.c_tma) tma_prefetch_desc(&mapC);
+        if (g.m_tma) tma_prefetch_desc(&mapM);
     }
     if (warp == MMA_WARP) {
         if (PAIR) tmem_alloc2(smem_u32(&tmem_base_smem), TMEM_COLS);
@@ -877,9 +917,14 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         int acc = 0, dbg_tile = 0, cbuf = 0;
         const uint32_t cstage = smem_u32(smem + (size_t)g.stages * stage_bytes) + (uint32_t)q * 8192u;   // 2 x 4 KB per warp
         uint32_t acc_phase = 0;
+        uint32_t mphase = 0;
         TileWalk w{cluster_id, 0, 0, 0, 0, 0};
         for (; tile_decode(w, g, total_tiles, rank); w.tile += n_clusters) {
             const bool empty_split = w.kb1 <= w.kb0;
+            // the previous tile's last chunk ended behind a __syncwarp: the block is free for this tile's first chunk
+            const uint32_t mbuf = (MASK && g.m_tma) ? cstage + (uint32_t)((EPI_WARPS - q) * 8192 + q * 4096) : 0u;   // behind the C staging blocks
+            if (MASK && mbuf && w.nt * g.n_tile < g.N && g.n_tile >= 32)
+                mask_request(&mapM, mbuf, smem_u32(&mask_bar[q]), w.nt * g.n_tile, w.mt * BM + q * 32, lane);
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
             if (warp == CONV_WARPS + 2 && lane == 0) DBG_STAMP(dbg_tile * (w.kb1 - w.kb0), 7);
@@ -901,8 +946,10 @@ gemm3x_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             e.mask_row = (g.epi.mask_src && g.splits == 1) ? g.epi.mask_src + (int64_t)m * g.epi.mask_ld : nullptr;
             e.mvec = g.epi.mvec;
             e.mask_scale = g.epi.mask_scale;
+            e.mbuf = mbuf;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(q * 32) << 16);
-            if (g.c_tma) epilogue_tile_tma(e, taddr, w.nt * g.n_tile, g.n_tile, &mapC, cstage, cbuf, w.mt * BM + q * 32, lane);
+            if (g.c_tma) epilogue_tile_tma<MASK>(e, taddr, w.nt * g.n_tile, g.n_tile, &mapC, cstage, cbuf, w.mt * BM + q * 32, lane, &mapM,
+                                           smem_u32(&mask_bar[q]), mphase);
             else if (g.n_tile % 32 == 0) epilogue_tile<32>(e, taddr, w.nt * g.n_tile, g.n_tile);
             else epilogue_tile<16>(e, taddr, w.nt * g.n_tile, g.n_tile);
             tc_fence_before();
@@ -992,6 +1039,7 @@ struct Plan {
     size_t smem;
 };
 constexpr size_t C_STAGE_BYTES = (size_t)EPI_WARPS * 2 * 4096;     // two 32 x 32 fp32 blocks per epilogue warp
+constexpr size_t M_STAGE_BYTES = (size_t)EPI_WARPS * 4096;         // one 32 x 32 mask block per epilogue warp (dgrad, behind C's)
 static Plan make_plan(int M, int N, int K, bool b_mn, bool allow_split, bool c_tma_ok = false, bool b_presplit = false) {
     Plan p;
     const int nt_max = env_int("RLCTR_GEMM_NT_MAX", 160);           // <= 160 keeps three 72 KB stages in flight
@@ -1076,15 +1124,23 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     ok = ok && (B.mn_major ? make_map(&mB, B.ptr, N, K, B.pitch, 32, true) : make_map(&mB, B.ptr, K, N, B.pitch, b_box));
     if (B.lo) ok = ok && (B.mn_major ? make_map(&mBlo, B.lo, N, K, B.pitch, 32, true) : make_map(&mBlo, B.lo, K, N, B.pitch, b_box));
     else mBlo = mB;
-    CUtensorMap mC = mA;
+    CUtensorMap mC = mA, mM = mA;
     if (p.c_tma) ok = ok && make_map(&mC, C, N, M, ldc, 32);          // box {32 n, 32 m}, SWIZZLE_128B
     if (!ok) return RLCTR_EUNSUPPORTED;
+    // the dgrad mask through TMA: beside TMA-stored C, when its blocks fit behind the pipeline and the mask rows are addressable
+    size_t smem = p.smem;
+    int m_tma = 0;
+    if (epi && epi->mask_src && p.c_tma && p.splits == 1 && tma_ok(epi->mask_src, epi->mask_ld) && p.smem + M_STAGE_BYTES <= (size_t)(221 * 1024) &&
+        env_int("RLCTR_GEMM_M_TMA", 1) != 0 && make_map(&mM, epi->mask_src, N, M, epi->mask_ld, 32)) {
+        m_tma = 1;
+        smem += M_STAGE_BYTES;
+    }
     Args g;
     g.C = C; g.ldc = ldc; g.cvec = vec_of(C, ldc); g.bias = bias;
     g.M = M; g.N = N; g.K = K;
     g.n_tile = p.n_tile; g.m_tiles = p.m_tiles; g.n_tiles = p.n_tiles; g.splits = p.splits; g.kb_per_split = p.kb_per_split;
     g.stages = p.stages;
-    g.a_tmem = p.a_tmem; g.acc_stride = p.acc_stride; g.a_col0 = p.a_col0; g.c_tma = p.c_tma;
+    g.a_tmem = p.a_tmem; g.acc_stride = p.acc_stride; g.a_col0 = p.a_col0; g.c_tma = p.c_tma; g.m_tma = m_tma;
     g.cluster = p.cluster; g.pair = p.pair;
     g.l2_ahead = env_int("RLCTR_GEMM_L2_AHEAD", 0);     // measured: no gain (the pipeline is L2->SM bandwidth bound, not DRAM-latency bound)
     g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0; g.b_presplit = B.lo ? 1 : 0; g.relu = relu;
@@ -1097,13 +1153,14 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     g.epi = epi ? *epi : Epilogue{};
     if ((g.epi.drop_state || g.epi.mask_src) && p.splits != 1) return RLCTR_EUNSUPPORTED;
     if (g.epi.mask_src) g.epi.mvec = vec_of(g.epi.mask_src, g.epi.mask_ld);
-    if (p.pair) RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    else RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    if (p.pair) RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (m_tma) RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else RLCTR_CUDA(cudaFuncSetAttribute(gemm3x_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_tiles * p.splits;      // cluster tiles
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(RLCTR_SMS / p.cluster * p.cluster));
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = p.smem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1115,19 +1172,20 @@ int gemm(const Operand& A, const Operand& B, float* C, int64_t ldc, const float*
     int max_clusters = RLCTR_SMS / p.cluster;
     if (p.cluster > 1) {                                   // clusters that can be resident at once (GPCs with an odd SM count lose one)
         static int cached_smem = -1, cached = 0;
-        if (cached_smem != (int)p.smem * 2 + p.pair) {
+        if (cached_smem != (int)smem * 2 + p.pair) {
             int n = 0;
-            if ((p.pair ? cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel<true>, &cfg)
-                        : cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel<false>, &cfg)) == cudaSuccess && n > 0) cached = n;
+            if ((p.pair ? cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel<true, false>, &cfg)
+                        : cudaOccupancyMaxActiveClusters(&n, gemm3x_tma_kernel<false, false>, &cfg)) == cudaSuccess && n > 0) cached = n;
             else cached = RLCTR_SMS / p.cluster;
-            cached_smem = (int)p.smem * 2 + p.pair;
+            cached_smem = (int)smem * 2 + p.pair;
         }
         if (cached < max_clusters) max_clusters = cached;
     }
     const int grid = (total < max_clusters ? total : max_clusters) * p.cluster;
     cfg.gridDim = dim3((unsigned)grid);
-    if (p.pair) RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<true>, mA, mB, mBlo, mC, g));
-    else RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<false>, mA, mB, mBlo, mC, g));
+    if (p.pair) RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<true, false>, mA, mB, mBlo, mC, mM, g));
+    else if (m_tma) RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<false, true>, mA, mB, mBlo, mC, mM, g));
+    else RLCTR_CUDA(cudaLaunchKernelEx(&cfg, gemm3x_tma_kernel<false, false>, mA, mB, mBlo, mC, mM, g));
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
 }

@@ -43,7 +43,8 @@ def run(K, N, ld):
         g = lambda: _lib.check(lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), None, dw.data_ptr(), None, B, K, N, 0, 1.0, 1.0, ws.data_ptr(), wsb, st), "wgrad")
         tag = "tma" if mode == "1" else "staged"
         fl = 2.0 * B * K * N
-        for name, fn in (("fwd", f), ("dgrad", d), ("wgrad", g)):
+        dm = lambda: _lib.check(lib.rlctr_linear_bwd(x.data_ptr(), ld, w.data_ptr(), None, gy.data_ptr(), dx.data_ptr(), None, None, B, K, N, _lib.RLCTR_MLP_DX_MASK, 1.0, 2.0, ws.data_ptr(), wsb, st), "dgrad_mask")
+        for name, fn in (("fwd", f), ("dgrad", d), ("dgrad_mask", dm), ("wgrad", g)):
             us = timeit(fn)
             out[f"{tag}.{name}"] = {"us": round(us, 1), "fp32_TFLOPs": round(fl / us / 1e6, 1)}
     # cuBLAS on the same shapes (verdict r1: is 76-116 fp32-equivalent TFLOP/s good?): SGEMM (allow_tf32 = False: what the reference's

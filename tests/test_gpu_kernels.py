@@ -835,7 +835,7 @@ def test_linear_exact_fp32_path(lib, B, K, N, relu):
 
 
 @pytest.mark.parametrize("path", ["tma", "staged"])
-@pytest.mark.parametrize("B,K,N", [(4096, 152, 300), (1000, 300, 200)])
+@pytest.mark.parametrize("B,K,N", [(4096, 152, 300), (1000, 300, 200), (65536, 300, 200), (777, 100, 48), (40000, 36, 304)])
 def test_linear_fused_dropout_and_masked_dgrad(lib, B, K, N, path, monkeypatch):
     """Forward: y = dropout(relu(x w^T + b)) with the counter-hash mask: kept elements equal relu(.)/(1-p), the kept fraction is
     1-p, the mask moves when the counter is advanced and repeats when it is not.  Backward of the layer above with
@@ -863,7 +863,8 @@ def test_linear_fused_dropout_and_masked_dgrad(lib, B, K, N, path, monkeypatch):
     assert abs((y3n[pos] != 0).mean() - (1 - p)) < 0.01
     assert ((y1n[pos] != 0) != (y3n[pos] != 0)).mean() > 0.2      # a different mask after the counter moved
     close(y1n[pos][kept], (ref[pos] / (1 - p))[kept], rtol=1e-5)
-    assert (y1n[ref == 0] == 0).all()
+    pre = x.astype(np.float64) @ w.astype(np.float64).T + b
+    assert (y1n[pre < -1e-5 * np.abs(pre).max()] == 0).all()     # clipped (beyond rounding of the pre-activation) -> 0
     # both kernels draw the same mask (the fused epilogue and the elementwise fallback share the hash)
     monkeypatch.setenv("RLCTR_GEMM_TMA", "0" if path == "tma" else "1")
     y4 = torch.empty(B, N, device=DEV)
@@ -882,6 +883,13 @@ def test_linear_fused_dropout_and_masked_dgrad(lib, B, K, N, path, monkeypatch):
                                 1.0, s, L().ptr(ws), wsb, st()) == 0
     refdx = (gy.astype(np.float64) @ w.astype(np.float64)) * np.where(xm > 0, s, 0.0)
     close(dx, refdx, rtol=1e-5)
+    assert (dx.cpu().numpy()[xm == 0] == 0).all()
+    if path == "tma":                                    # the mask through TMA blocks == the mask read per thread, bit for bit
+        monkeypatch.setenv("RLCTR_GEMM_M_TMA", "0")
+        dx2 = torch.empty(B, K, device=DEV)
+        assert lib.rlctr_linear_bwd(L().ptr(dev(xm)), K, L().ptr(wd), None, L().ptr(dev(gy)), L().ptr(dx2), None, None, B, K, N, 4,
+                                    1.0, s, L().ptr(ws), wsb, st()) == 0
+        assert torch.equal(dx, dx2)
 
 
 # ------------------------------------------------------------------------------------------------
