@@ -484,6 +484,9 @@ int rlctr_auc_logloss(const float* pred, const int64_t* labels_i64, const float*
 #define RLCTR_MLP_FP32 8        /* exact fp32 on the CUDA cores (one FFMA per product, k ascending: the reference's SGEMM arithmetic)
                                    instead of 3xTF32 on the tensor cores.  For the small-batch learn steps of the BatchNorm policy
                                    nets, whose backward cancels the dominant part of the gradient (csrc/mlp.cu `simt`) */
+#define RLCTR_MLP_W_PRESPLIT 16 /* bwd: `ws` is the workspace the forward call of this layer ran with (same batch / dims / flags, weights
+                                 * unchanged since): the (W_hi, W_lo) images it left there feed the dgrad GEMM, the split kernel is skipped.
+                                 * Only meaningful where the forward took the 3xTF32 path (not RLCTR_MLP_FP32, out_dim > 1). */
 size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_dim);
 /* ---- replay memory of the RL agents, sampled on the device ----------------------------------------------------
  * The reference samples on the host: random.sample (DDQN_model.py:183-185) and np.random.choice(n, batch, p=P, replace=False)

@@ -22,6 +22,7 @@ RLCTR_DENSE_MAX = 24
 RLCTR_MLP_RELU = 1
 RLCTR_MLP_DROPOUT = 2
 RLCTR_MLP_DX_MASK = 4
+RLCTR_MLP_W_PRESPLIT = 16
 RLCTR_MLP_FP32 = 8
 
 

@@ -810,14 +810,15 @@ extern "C" size_t rlctr_mlp_ws_bytes(int64_t batch, int32_t in_dim, int32_t out_
 }
 
 // (W_hi, W_lo) images of the weight at the end of the workspace; null when the workspace is absent / too small
+// reuse: the images are already there (RLCTR_MLP_W_PRESPLIT: this workspace served the layer's forward call with the same weights)
 static bool split_weights_into(void* ws, size_t ws_bytes, const MlpWs& l, const float* w, int in_dim, int out_dim,
-                               cudaStream_t st, float** whi, float** wlo, int* rc) {
+                               cudaStream_t st, float** whi, float** wlo, int* rc, bool reuse = false) {
     *rc = RLCTR_OK;
     if (!tma::enabled() || !ws || ws_bytes < l.total || !rlctr_aligned16(ws) || out_dim == 1) return false;
     char* base = reinterpret_cast<char*>(ws) + l.wgrad + l.colsum;
     *whi = reinterpret_cast<float*>(base);
     *wlo = reinterpret_cast<float*>(base + l.wsplit);
-    *rc = tma::split_weight(w, *whi, *wlo, out_dim, in_dim, l.in_pitch, st);
+    if (!reuse) *rc = tma::split_weight(w, *whi, *wlo, out_dim, in_dim, l.in_pitch, st);
     return *rc == RLCTR_OK;
 }
 
@@ -967,7 +968,7 @@ extern "C" int rlctr_linear_bwd(const float* x, int64_t ldx, const float* w, con
         float *whi = nullptr, *wlo = nullptr;
         int rc = RLCTR_OK;
         bool done = false;
-        if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &rc)) {
+        if (split_weights_into(ws, ws_bytes, l, w, in_dim, out_dim, st, &whi, &wlo, &rc, (flags & RLCTR_MLP_W_PRESPLIT) != 0)) {
             tma::Epilogue epi;
             if (dx_mask) { epi.mask_src = x; epi.mask_ld = ldx; epi.mask_scale = dx_scale; }
             rc = tma::gemm(tma::Operand{dy, nullptr, out_dim, false}, tma::Operand{whi, wlo, l.in_pitch, true}, dx, in_dim,

@@ -31,6 +31,11 @@ from . import _lib
 FP32_MAX_BATCH = int(os.environ.get("RLCTR_FP32_MAX_BATCH", "1024"))
 
 
+# The dgrad of a tower layer reuses the (W_hi, W_lo) images its forward left in the workspace (RLCTR_MLP_W_PRESPLIT): one launch
+# less per layer and step.  0 = split again (A/B switch; tests compare the two bit for bit).
+REUSE_SPLIT = os.environ.get("RLCTR_MLP_REUSE_SPLIT", "1") != "0"
+
+
 def _fp32_flag(B):
     return _lib.RLCTR_MLP_FP32 if B <= FP32_MAX_BATCH else 0
 
@@ -47,7 +52,8 @@ def _rows_view(x):
     return x2, K
 
 
-def _fwd(lib, x2, ldx, w, bias, relu, drop_p=0.0, rng=None):
+def _fwd(lib, x2, ldx, w, bias, relu, drop_p=0.0, rng=None, keep_ws=False):
+    """keep_ws: also return the call's workspace -- it holds the (W_hi, W_lo) images the layer's dgrad can reuse (RLCTR_MLP_W_PRESPLIT)."""
     B, K = x2.shape
     N = w.shape[0]
     y = torch.empty(B, N, dtype=torch.float32, device=x2.device)
@@ -59,10 +65,13 @@ def _fwd(lib, x2, ldx, w, bias, relu, drop_p=0.0, rng=None):
               key=f"rlctr_linear_fwd[{K}x{N}]", meta={"B": B, "K": K, "N": N})
     if drop_p > 0.0:
         _lib.check(lib.rlctr_rng_advance(_lib.ptr(rng), B * N, _lib.stream()), "rlctr_rng_advance")
+    if keep_ws:
+        return y, (ws if (N > 1 and not (flags & _lib.RLCTR_MLP_FP32)) else None)
     return y
 
 
-def _bwd(lib, x2, ldx, w, y, gy2, need_dx, need_dw, need_db, relu, gy_scale=1.0, dx_mask=False, dx_scale=1.0):
+def _bwd(lib, x2, ldx, w, y, gy2, need_dx, need_dw, need_db, relu, gy_scale=1.0, dx_mask=False, dx_scale=1.0, fwd_ws=None):
+    """fwd_ws: the workspace of this layer's forward call (weights unchanged since): its weight split is reused."""
     B, K = x2.shape
     N = w.shape[0]
     dev = x2.device
@@ -70,8 +79,10 @@ def _bwd(lib, x2, ldx, w, y, gy2, need_dx, need_dw, need_db, relu, gy_scale=1.0,
     dw = torch.empty(N, K, dtype=torch.float32, device=dev) if need_dw else None
     db = torch.empty(N, dtype=torch.float32, device=dev) if need_db else None
     ws_bytes = lib.rlctr_mlp_ws_bytes(B, K, N)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    flags = (_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DX_MASK if dx_mask else 0) | _fp32_flag(B)
+    reuse = REUSE_SPLIT and fwd_ws is not None and fwd_ws.numel() >= ws_bytes and not _fp32_flag(B)
+    ws = fwd_ws if reuse else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    flags = ((_lib.RLCTR_MLP_RELU if relu else 0) | (_lib.RLCTR_MLP_DX_MASK if dx_mask else 0) | _fp32_flag(B) |
+             (_lib.RLCTR_MLP_W_PRESPLIT if reuse else 0))
     _lib.call("rlctr_linear_bwd", lib.rlctr_linear_bwd, x2.data_ptr(), ldx, _lib.ptr(w), _lib.ptr(y) if relu else None,
               _lib.ptr(gy2), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), B, K, N, flags, float(gy_scale), float(dx_scale),
               _lib.ptr(ws), ws_bytes, _lib.stream(), key=f"rlctr_linear_bwd[{K}x{N}]",
@@ -187,16 +198,18 @@ class _TowerFn(torch.autograd.Function):
         # spec: tuple of (relu, drop_p, has_bias) per layer; params: weight_0, bias_0, weight_1, bias_1, ... (bias may be None)
         lib = _lib.load()
         h, ld = _rows_view(x)
-        acts, lds, ws_ = [], [], []
+        acts, lds, ws_, fwd_ws = [], [], [], []
         for i, (relu, drop_p, has_bias) in enumerate(spec):
             w = params[2 * i].detach().contiguous()
             b = params[2 * i + 1].detach() if has_bias else None
             acts.append(h)
             lds.append(ld)
             ws_.append(w)
-            h = _fwd(lib, h, ld, w, b, relu, drop_p, rng)
+            h, fws = _fwd(lib, h, ld, w, b, relu, drop_p, rng, keep_ws=True)
+            fwd_ws.append(fws)
             ld = h.shape[1]
         ctx.spec, ctx.lds = spec, lds
+        ctx.fwd_ws = fwd_ws                                   # (W_hi, W_lo) of every layer: the dgrads reuse them
         ctx.in_shape = x.shape
         ctx.n_layers = len(spec)
         last_relu = spec[-1][0]
@@ -228,7 +241,8 @@ class _TowerFn(torch.autograd.Function):
             need_db = has_bias and ctx.needs_input_grad[3 + 2 * i + 1]
             gy_scale = 1.0 / (1.0 - drop_p) if (own_mask and drop_p > 0.0) else 1.0
             dx, dw, db = _bwd(lib, acts[i], ctx.lds[i], ws_[i], saved[2 * L] if own_mask else None, g, need_dx, need_dw,
-                              need_db, own_mask, gy_scale, dx_mask, dx_scale)
+                              need_db, own_mask, gy_scale, dx_mask, dx_scale, fwd_ws=ctx.fwd_ws[i])
+            ctx.fwd_ws[i] = None
             grads[2 * i], grads[2 * i + 1] = dw, db
             g = dx
         dx0 = g.reshape(ctx.in_shape) if (g is not None and ctx.needs_input_grad[0]) else None

@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-export GEMM_BENCH_FAST=1
-timeout 400 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "linear or tower" 2>&1 | tail -4
-timeout 300 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "tower or deepfm or DeepFM" 2>&1 | tail -2
-for i in 1 2; do timeout 120 python scratch/gemm_bench.py 2>&1 | tail -2 | cut -c1-420; done
+timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_models.py tests/test_gpu_colocated.py -x -q -m gpu -k "linear or tower or deepfm or DeepFM or group or colocat" 2>&1 | tail -4
+bash scratch/ab_bench.sh RLCTR_MLP_REUSE_SPLIT 0 1 2>&1 | tail -4

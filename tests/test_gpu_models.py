@@ -324,6 +324,27 @@ def test_tower_matches_torch_fp32():
         close(p.grad, q.grad)
 
 
+@pytest.mark.parametrize("B", [4096, 512])
+def test_tower_dgrad_reuses_forward_weight_split(B, monkeypatch):
+    """RLCTR_MLP_W_PRESPLIT: the dgrad of every tower layer runs on the (W_hi, W_lo) images its forward call left in the workspace.
+    Same bits as splitting again (train mode: dropout + masked dgrads; B = 512 takes the exact-fp32 path, which never splits)."""
+    from rl_ctr_prediction_b200 import p_model, mlp
+    out = {}
+    for reuse in (True, False):
+        monkeypatch.setattr(mlp, "REUSE_SPLIT", reuse)
+        torch.manual_seed(11)
+        tower = p_model._tower(150).to(DEV).train()
+        x = torch.randn(B, 150, device=DEV).requires_grad_(True)
+        torch.manual_seed(77)                                    # the dropout (seed, counter) is drawn lazily from the CPU generator
+        y = tower(x)
+        y.backward(torch.randn(B, 1, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5)))
+        out[reuse] = [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in tower.parameters()]
+        y2 = tower(x)                                            # a second pass on the same module: fresh workspaces, fresh split
+        y2.sum().backward()
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
+
+
 @pytest.fixture(scope="module")
 def single_rank_group():
     import torch.distributed as dist
