@@ -20,6 +20,9 @@
 //     (tcgen05.mma ... [d_tmem], [a_tmem], b_desc), so A crosses the shared-memory port once instead of four times per k-block;
 //   * C leaves through per-warp 32 x 32 staging blocks and TMA stores (cp.async.bulk.tensor ... global.shared::cta): full
 //     128-byte row segments instead of 16-byte pieces of 32 different lines per store instruction;
+//   * dgrad takes the ReLU / dropout mask of the layer below from TMA-loaded 32 x 32 blocks, one per epilogue warp, requested a
+//     chunk ahead (instantiation <PAIR = false, MASK = true>; RLCTR_GEMM_M_TMA=0 reads it per thread as before, same bits);
+//   * the all-zero k-steps of a ragged last k-block (K % 32 != 0: TMA zero fill) are not issued;
 //   * kept behind switches: A from shared memory + direct stores (RLCTR_GEMM_A_TMEM=0, RLCTR_GEMM_C_TMA=0), the B tile multicast
 //     to a CTA pair (RLCTR_GEMM_CLUSTER=2), L2 prefetch of A (RLCTR_GEMM_L2_AHEAD), per-stage clock stamps (RLCTR_GEMM_DBG).
 //
