@@ -406,6 +406,14 @@ int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const rlctr_table*
 /* Replay the missed L2-only steps of rows [row_begin,row_end) up to *step.  Called once per
  * step this IS dense Adam (mode A); called before eval/state_dict/epoch end it is
  * the flush of the lazy mode (mode B). */
+/* The same catch-up from the batch's ids in BATCH order (int64 [n], duplicates and out-of-range ids allowed): no sorted view is
+ * needed, so a training step can sort on another stream while catch-up, gather and tower run (p_model.py:270's read needs current rows,
+ * the scatter only needs the sorted view at the end).  Occurrences of one id are told apart by a claim bit per table row (`claim`:
+ * rlctr_rows_claim_bytes(n_rows) bytes of scratch, zeroed by the call); the result is independent of which occurrence wins.
+ * In-record stamps and co-located records (5..8 active 16-byte chunks) only; RLCTR_EUNSUPPORTED otherwise. */
+size_t rlctr_rows_claim_bytes(int64_t n_rows);
+int rlctr_rows_catchup_ids(const int64_t* ids, int64_t n, const rlctr_table* table, const rlctr_adam* opt, void* claim,
+                           size_t claim_bytes, rlctr_stream_t stream);
 int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt,
                      int64_t row_begin, int64_t row_end, rlctr_stream_t stream);
 /* Dense Adam for the replicated parameters (bias, tower, policy nets): applies step *step+1

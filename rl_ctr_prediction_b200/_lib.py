@@ -119,6 +119,8 @@ SIGNATURES = {
     "rlctr_lookup_stage_floats": (_I64, [_TP]),
     "rlctr_rows_lookup": (C.c_int, [_P, _P, _I64, _TP, _AP, _LP, _P, _SZ, _P]),
     "rlctr_rows_catchup": (C.c_int, [_P, _I64, _TP, _AP, _P]),
+    "rlctr_rows_claim_bytes": (_SZ, [_I64]),
+    "rlctr_rows_catchup_ids": (C.c_int, [_P, _I64, _TP, _AP, _P, _SZ, _P]),
     "rlctr_adam_flush": (C.c_int, [_TP, _AP, _I64, _I64, _P]),
     "rlctr_dense_adam": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F, _F, _F, _F, _P]),
     "rlctr_dense_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _F, _F, _F, _F, _P]),

@@ -25,6 +25,7 @@ model's (tests/test_gpu_colocated.py).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -32,6 +33,13 @@ import torch.nn as nn
 from . import _lib
 from . import p_model as Model
 from .tables import Geometry, round4, table_struct
+
+
+# 1: the group's catch-up works from the ids in batch order and the sort of the batch runs on a side stream (see train_step);
+# 0 (default): sort first, catch-up over the sorted run heads.  The two leave the same bits in the table.  Measured A/B on one
+# B200 (C2 step): 1.347 ms sorted, 1.422 ms with the sort off the critical path -- the batch-order catch-up with its claim
+# atomics and the concurrent sort cost more than the 66 us of sorting they hide, so it stays an option.
+UNSORTED_CATCHUP = os.environ.get("RLCTR_GROUP_UNSORTED_CATCHUP", "0") != "0"
 
 
 class GroupStash:
@@ -115,6 +123,7 @@ class ColocatedCTR(Model._TableModel):
         self.table = nn.Parameter(joint)
         self.table._rlctr_owner = self
         self._opt, self._stash, self._ws = None, None, {}
+        self._sort_stream, self._claim = None, None
         self._cols = cols
         for m, (lin, emb, dim) in zip(models, cols):
             m.table = self.table                             # shared Parameter: the member's view of the joint record
@@ -200,12 +209,32 @@ class ColocatedCTR(Model._TableModel):
         yy = y.reshape(-1).contiguous()
         yi = yy if yy.dtype == torch.int64 else None
         yf = None if yi is not None else yy.float()
-        sid, sslot = Model.sort_ids(x, g.n_rows)
         t = table_struct(self.table.data, g)
-        if opt.lazy and opt.dirty:
-            a = opt.struct()
-            _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sid), x.numel(), C.byref(t), C.byref(a), st,
-                      key="rlctr_rows_catchup[group]", meta=self._meta(B, F))
+        # The sorted view is needed by the scatter at the END of the step only: with the catch-up working from the ids in batch
+        # order (rlctr_rows_catchup_ids: a claim bit per row tells the occurrences of an id apart) the sort runs on its own
+        # stream -- a parallel branch of a captured step -- beside catch-up, gather and tower instead of in front of them.
+        side = None
+        if UNSORTED_CATCHUP and opt.lazy and opt.stamp_col >= 0 and (g.used + 3) // 4 >= 5:    # joint records of 5..8 chunks
+            cur = torch.cuda.current_stream(dev)
+            side = self._sort_stream
+            if side is None or side.device != dev:
+                side = self._sort_stream = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sid, sslot = Model.sort_ids(x, g.n_rows)
+            if opt.dirty:
+                a = opt.struct()
+                cb = lib.rlctr_rows_claim_bytes(g.n_rows)
+                if self._claim is None or self._claim.numel() < cb or self._claim.device != dev:
+                    self._claim = torch.empty(cb, dtype=torch.uint8, device=dev)
+                _lib.call("rlctr_rows_catchup_ids", lib.rlctr_rows_catchup_ids, _lib.ptr(x), x.numel(), C.byref(t), C.byref(a),
+                          _lib.ptr(self._claim), cb, st, key="rlctr_rows_catchup[group]", meta=self._meta(B, F))
+        else:
+            sid, sslot = Model.sort_ids(x, g.n_rows)
+            if opt.lazy and opt.dirty:
+                a = opt.struct()
+                _lib.call("rlctr_rows_catchup", lib.rlctr_rows_catchup, _lib.ptr(sid), x.numel(), C.byref(t), C.byref(a), st,
+                          key="rlctr_rows_catchup[group]", meta=self._meta(B, F))
         M = len(self.members)
         arr, logits, rows = self._member_structs(B, F, dev, True)
         sums = torch.empty(B, g.row_stride, dtype=torch.float32, device=dev)
@@ -240,6 +269,8 @@ class ColocatedCTR(Model._TableModel):
                 bias.grad = dbias
             dlogits.append(dl)
         self._stash = GroupStash(sorted_ids=sid, sorted_slots=sslot, n=B * F, fields=F, sums=sums, dlogit=dlogits, extra=extras)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)     # join: the scatter reads the sorted view
         optimizer.step()
         return losses
 

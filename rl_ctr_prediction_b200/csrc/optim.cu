@@ -872,7 +872,17 @@ struct ReplayRow {
     float4 p[CH], m[CH], v[CH];
     int64_t off;
     int t;
+    uint32_t lost;                                       // UNSORTED: another occurrence of the id claimed the record first
 };
+// UNSORTED catch-up (rlctr_rows_catchup_ids): the work items are the batch's ids in BATCH order -- no sorted view needed, so the
+// sort leaves the critical path of the step.  Every occurrence requests its record; the occurrences of one id are told apart by a
+// claim bit per table row (atomicOr on a bitmap zeroed by the call: the first to arrive replays, the others drop the item).
+// The result does not depend on who wins: the replay is a function of the record alone.
+__device__ __forceinline__ int64_t replay_row_unsorted(int64_t k, int64_t n_items, const int64_t* __restrict__ ids, int64_t n_rows) {
+    if (k >= n_items) return -2;
+    const int64_t id = __ldg(ids + k);
+    return (id >= 0 && id < n_rows) ? id : -1;         // out-of-range ids own no record
+}
 // row of work item k: FLUSH -> r0 + k; CATCHUP -> the id at sorted position k if that position is a run head
 // (-1: nothing to do at this position; -2: past the end -- of the items, or of the ids this table owns: out-of-range and,
 // for a sharded table, non-owned ids sort last as sentinels and may outnumber the real ones G-1 to 1).
@@ -890,11 +900,16 @@ __device__ __forceinline__ int64_t replay_row_of(int64_t k, int64_t n_items, int
 // issue the loads of a whole record WITHOUT looking at its stamp first: one DRAM round trip instead of two, and
 // nothing in the caller depends on the data until the item becomes current (a full replay of another row later).
 // LPRR lanes share a row (co-located records of 5..8 chunks): lane slice h owns chunks h*CH .. h*CH+CH-1, `live` of them active.
-template <int CH>
+template <int CH, bool UNSORTED = false>
 __device__ __forceinline__ void replay_row_issue(ReplayRow<CH>& it, int64_t row, const TableView& t, const AdamView& a, int first_col,
-                                                 int live) {
+                                                 int live, uint32_t* __restrict__ claim = nullptr, bool claimer = false) {
     it.off = row < 0 ? row : row * t.pitch + first_col;
+    it.lost = 0;
     if (row >= 0) {
+        if (UNSORTED && claimer) {                       // one lane per row; its answer is consumed a whole item later
+            const uint32_t bit = 1u << (row & 31);
+            it.lost = atomicOr(claim + (row >> 5), bit) & bit;
+        }
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             if (c < live) {
@@ -908,10 +923,19 @@ __device__ __forceinline__ void replay_row_issue(ReplayRow<CH>& it, int64_t row,
     }
 }
 // the item becomes current: read the in-record stamp out of the data that has landed; up-to-date rows are dropped
-template <int CH, int LPRR>
+template <int CH, int LPRR, bool UNSORTED = false>
 __device__ __forceinline__ void replay_row_arm(ReplayRow<CH>& it, const AdamView& a, int upto, int h) {
     it.t = upto;
     if (it.off < 0) return;                              // the same for every lane of a row
+    if (UNSORTED) {
+        uint32_t lost = it.lost;
+        if (LPRR > 1) {                                  // slice 0 of the row asked
+            const int lane = threadIdx.x & 31;
+            const unsigned mask = ((1u << LPRR) - 1u) << (lane & ~(LPRR - 1));
+            lost = __shfl_sync(mask, lost, lane & ~(LPRR - 1));
+        }
+        if (lost) { it.off = -1; return; }
+    }
     int st;
     if (LPRR == 1) {
         // the in-record stamp sits in the first padding column (= `used`, tables.Geometry.stamp_col), i.e. always in the
@@ -931,9 +955,10 @@ __device__ __forceinline__ void replay_row_arm(ReplayRow<CH>& it, const AdamView
     }
     if (st >= upto) it.off = -1; else it.t = st;
 }
-template <int CH, int LPRR, bool CATCHUP>
+template <int CH, int LPRR, bool CATCHUP, bool UNSORTED = false>
 __global__ void __launch_bounds__(128, (CH == 3 ? 4 : 3))
-replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids) {
+replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const uint32_t* __restrict__ sorted_ids,
+                   const int64_t* __restrict__ ids64 = nullptr, uint32_t* __restrict__ claim = nullptr) {
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) / LPRR;  // rows between two items of one lane
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int h = (int)(gt % LPRR);
@@ -944,11 +969,14 @@ replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const u
     int64_t kc = gt / LPRR;                                           // index of the current item
     if (kc >= n_items) return;
     ReplayRow<CH> cur, nxt;
-    replay_row_issue<CH>(cur, replay_row_of<CATCHUP>(kc, n_items, r0, sorted_ids, t.n_rows), t, a, first_col, live);
-    replay_row_issue<CH>(nxt, replay_row_of<CATCHUP>(kc + stride, n_items, r0, sorted_ids, t.n_rows), t, a, first_col, live);
-    int64_t row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
+    auto row_of = [&](int64_t k) -> int64_t {
+        return UNSORTED ? replay_row_unsorted(k, n_items, ids64, t.n_rows) : replay_row_of<CATCHUP>(k, n_items, r0, sorted_ids, t.n_rows);
+    };
+    replay_row_issue<CH, UNSORTED>(cur, row_of(kc), t, a, first_col, live, claim, h == 0);
+    replay_row_issue<CH, UNSORTED>(nxt, row_of(kc + stride), t, a, first_col, live, claim, h == 0);
+    int64_t row2 = row_of(kc + 2 * stride);
     if (cur.off == -2) return;
-    replay_row_arm<CH, LPRR>(cur, a, upto, h);
+    replay_row_arm<CH, LPRR, UNSORTED>(cur, a, upto, h);
     while (true) {
         if (cur.t >= upto) {                             // current item finished (or had nothing to do): switch
             if (cur.off >= 0) {
@@ -965,9 +993,9 @@ replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const u
             kc += stride;
             if (kc >= n_items || nxt.off == -2) break;   // end of the queue, or of the ids this table owns
             cur = nxt;                                   // its loads were issued one whole item ago
-            replay_row_issue<CH>(nxt, row2, t, a, first_col, live);   // row2's id was fetched one item ago: no dependent wait here
-            row2 = replay_row_of<CATCHUP>(kc + 2 * stride, n_items, r0, sorted_ids, t.n_rows);
-            replay_row_arm<CH, LPRR>(cur, a, upto, h);
+            replay_row_issue<CH, UNSORTED>(nxt, row2, t, a, first_col, live, claim, h == 0);   // row2's id was fetched one item ago: no dependent wait here
+            row2 = row_of(kc + 2 * stride);
+            replay_row_arm<CH, LPRR, UNSORTED>(cur, a, upto, h);
             continue;
         }
         ++cur.t;
@@ -978,7 +1006,7 @@ replay_rows_kernel(TableView t, AdamView a, int64_t r0, int64_t n_items, const u
 }
 template <bool CATCHUP>
 static int launch_replay_rows(const TableView& t, const AdamView& a, int64_t r0, int64_t n_items,
-                              const uint32_t* sorted_ids, cudaStream_t st) {
+                              const uint32_t* sorted_ids, cudaStream_t st, const int64_t* ids64 = nullptr, uint32_t* claim = nullptr) {
     const int ch = (t.used + 3) >> 2;
     const int lprr = ch > 4 ? 2 : 1;                     // co-located records (5..8 chunks): two lanes per row
     if (a.stamp_col >> 2 != ch - 1) return RLCTR_EUNSUPPORTED;        // the stamp rides in the last active chunk
@@ -987,6 +1015,15 @@ static int launch_replay_rows(const TableView& t, const AdamView& a, int64_t r0,
     if (rgrid_env < 0) { const char* e = getenv("RLCTR_REPLAY_GRID"); rgrid_env = e ? atoi(e) : 8; }
     const int cap = RLCTR_SMS * (rgrid_env > 0 ? rgrid_env : 8);
     const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+    if (CATCHUP && ids64) {                              // batch-order ids + claim bits (the co-located records: 5..8 chunks)
+        switch (ch) {
+            case 5: case 6: replay_rows_kernel<3, 2, true, true><<<grid, 128, 0, st>>>(t, a, r0, n_items, nullptr, ids64, claim); break;
+            case 7: case 8: replay_rows_kernel<4, 2, true, true><<<grid, 128, 0, st>>>(t, a, r0, n_items, nullptr, ids64, claim); break;
+            default: return RLCTR_EUNSUPPORTED;
+        }
+        RLCTR_LAUNCH_CHECK();
+        return RLCTR_OK;
+    }
     switch (ch) {
         case 1: replay_rows_kernel<1, 1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
         case 2: replay_rows_kernel<2, 1, CATCHUP><<<grid, 128, 0, st>>>(t, a, r0, n_items, sorted_ids); break;
@@ -1706,6 +1743,23 @@ extern "C" int rlctr_rows_catchup(const uint32_t* sorted_ids, int64_t n, const r
     catchup_stamp_kernel<<<grid_1d(n, RLCTR_SMS * 8), 256, 0, st>>>(sorted_ids, n, t.n_rows, a.stamp, a.step);
     RLCTR_LAUNCH_CHECK();
     return RLCTR_OK;
+}
+
+extern "C" size_t rlctr_rows_claim_bytes(int64_t n_rows) {
+    return n_rows > 0 ? (size_t)((n_rows + 31) / 32) * sizeof(uint32_t) : 0;
+}
+extern "C" int rlctr_rows_catchup_ids(const int64_t* ids, int64_t n, const rlctr_table* table, const rlctr_adam* opt, void* claim,
+                                      size_t claim_bytes, rlctr_stream_t stream) {
+    if (!ids || !table || !table->data || !opt || !opt->sched || !opt->step || n < 0) return RLCTR_EINVAL;
+    if (opt->stamp_col < 0) return RLCTR_EUNSUPPORTED;                // in-record stamps only (the joint records)
+    if (n == 0) return RLCTR_OK;
+    if (!claim || claim_bytes < rlctr_rows_claim_bytes(table->n_rows)) return RLCTR_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableView t = view_of(table);
+    AdamView a = view_of(opt, t);
+    if (t.rs % 4 != 0 || ((t.used + 3) >> 2) < 5) return RLCTR_EUNSUPPORTED;
+    RLCTR_CUDA(cudaMemsetAsync(claim, 0, rlctr_rows_claim_bytes(table->n_rows), st));
+    return launch_replay_rows<true>(t, a, 0, n, nullptr, st, ids, reinterpret_cast<uint32_t*>(claim));
 }
 
 extern "C" int rlctr_adam_flush(const rlctr_table* table, const rlctr_adam* opt, int64_t row_begin, int64_t row_end,

@@ -107,6 +107,8 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.rlctr_generate_preds(None, None, None, None, None, None, None, 4, 3, 0, None) == -1
     assert lib.rlctr_generate_preds_v10(None, None, None, None, None, None, None, None, 4, 3, None, 0, None) == -1
     assert lib.rlctr_generate_preds_v10_ws_bytes(1000) >= 4 * 8 * 4
+    assert lib.rlctr_rows_catchup_ids(None, 4, None, None, None, 0, None) == -1
+    assert lib.rlctr_rows_claim_bytes(1000) == 32 * 4 and lib.rlctr_rows_claim_bytes(0) == 0
     assert lib.rlctr_sort_ids(None, 1, 1, None, None, None, 0, None) == -1
     assert lib.rlctr_rows_ws_bytes(1000) >= 16
     assert lib.rlctr_group_fwd(None, None, None, 0, None, 0, 4, 15, None) != 0

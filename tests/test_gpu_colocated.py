@@ -61,10 +61,14 @@ def _train_group(models, batches, mode="lazy"):
     return group, np.array(losses)
 
 
+@pytest.mark.parametrize("catchup", ["ids", "sorted"])
 @pytest.mark.parametrize("rows2", ["1", "0"])
 @pytest.mark.parametrize("zipf", [False, True])
-def test_group_equals_standalone_models(zipf, rows2, monkeypatch):
+def test_group_equals_standalone_models(zipf, rows2, catchup, monkeypatch):
+    from rl_ctr_prediction_b200 import colocated
     monkeypatch.setenv("RLCTR_GROUP_ROWS2", rows2)       # two lanes per record (default) / eight lanes per record
+    # catch-up from the ids in batch order with claim bits, the sort on a side stream (default) / sort first, run heads
+    monkeypatch.setattr(colocated, "UNSORTED_CATCHUP", catchup == "ids")
     N, B, steps = 3000, 512, 6
     sep = _models(N)
     grp_members = [copy.deepcopy(m) for m in sep]
