@@ -805,7 +805,8 @@ def b200_arm(args):
                 "unit": "TFLOP/s", "frac": achieved / tpeak, "tensor_pipe_issued_TFLOPs": 3 * achieved,
                 "tensor_pipe_issued_frac": 3 * achieved / tpeak, "traffic": NCU_TRAFFIC.get(top),
                 "traffic_note": "DRAM bytes (ncu dram__bytes_read+write) of ALL kernels of this entry point in one step, B=65536 "
-                                "(profiles/r2f_ncu_top_kernels.md); achieved / peak are FLOP rates over the same kernels",
+                                "(profiles/r2f_ncu_top_kernels.md; re-captured on the final build, same figures within 1 %: profiles/r2r_ncu_gemm.md); "
+                                "achieved / peak are FLOP rates over the same kernels",
                 "peak_source": tpeak_src,
                 "flops_counted": "algorithmic fp32-equivalent FLOPs; the 3xTF32 split issues 3 tf32 MMAs per product "
                                  "(tensor_pipe_issued_*)", "share_of_step": groups[top] / Kp / step_ms}
